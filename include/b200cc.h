@@ -1,0 +1,138 @@
+/*
+ * b200cc.h -- C ABI of libb200cc.so: hand-written sm_100a kernels for the closed-shell
+ * RHF-CCSD amplitude iteration and the (T) correction of CrawfordGroup/pycc.
+ *
+ * The reference (pure Python) has no FFI; its single contraction choke point is
+ * ContractionBackend.__call__ (pycc/device.py:64-86, opt_einsum -> torch.tensordot -> cuBLAS),
+ * plus ATen elementwise ops and the Python loops of cctriples.py.  Each entry point below names
+ * the reference lines it replaces.  Conventions:
+ *   - all pointers are DEVICE pointers to float64 unless stated otherwise; the caller (torch) owns
+ *     every buffer, the library owns nothing but a small per-device scratch for reductions;
+ *   - sizes/strides are in ELEMENTS (doubles), `long long`;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
+ *     stream-ordered, no call synchronises unless stated;
+ *   - return value 0 = OK, non-zero = error, text via b200cc_last_error() (thread-local).
+ * There is NO CPU implementation behind any of these: without a CUDA device every compute call
+ * fails with a non-zero status.
+ */
+#ifndef B200CC_H
+#define B200CC_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef long long b200cc_i64;
+
+int b200cc_version(void);
+const char* b200cc_last_error(void);
+/* number of kernels launched by this library in this process (for bench.py's gpu_launches) */
+b200cc_i64 b200cc_launch_count(void);
+int b200cc_device_info(int* sm_count, int* cc_major, int* cc_minor, b200cc_i64* free_bytes, b200cc_i64* total_bytes);
+
+/* ---- FP64 tensor-core (DMMA m8n8k4) GEMM -----------------------------------------------------
+ * Replaces every two-operand contraction that opt_einsum lowers to tensordot/cuBLAS DGEMM
+ * (pycc/device.py:84), incl. the particle-particle ladder (ccwfn.py:931), the ring terms
+ * (ccwfn.py:644-645,683,715,933-938), Wmnij (603,930) and the t3 build (cctriples.py:50-62).
+ *
+ *   C[b](m,n) = alpha * ( sum_k opA1[b](m,k) opB1[b](n,k)  [+ sum_k opA2[b](m,k) opB2[b](n,k)] ) + beta * C[b](m,n)
+ *
+ * transA = 0: A is "K-major", element (m,k) at A[m*lda + k];  transA = 1: "M-major", A[k*lda + m].
+ * transB = 0: B is "K-major", element (n,k) at B[n*ldb + k];  transB = 1: "N-major", B[k*ldb + n].
+ * C is row-major (m,n) at C[m*ldc + n].  The optional second K-segment (K2 > 0) accumulates a second
+ * product into the same tile before the epilogue (used by (T): particle + hole term in one pass).
+ * Batching: either constant strides (strideA1.., `table` NULL) or a device table of
+ * 5 x batch absolute addresses {A1,B1,A2,B2,C} (int64) per batch entry.
+ * ksplit > 1 splits the K loop over gridDim.z and reduces through `workspace`
+ * (>= ksplit*batch*M*N doubles); deterministic (no atomics).                                    */
+typedef struct {
+  int M, N;
+  int transA, transB;
+  int K1, K2;                      /* K2 = 0: single segment */
+  const double *A1, *B1, *A2, *B2;
+  b200cc_i64 lda1, ldb1, lda2, ldb2;
+  b200cc_i64 strideA1, strideB1, strideA2, strideB2;
+  double* C;
+  b200cc_i64 ldc, strideC;
+  double alpha, beta;
+  int batch;
+  const b200cc_i64* table;         /* device, [batch][5] or NULL */
+  int table_align16;               /* table mode: caller vouches every address is 16-byte aligned */
+  int ksplit;
+  double* workspace;
+} b200cc_gemm_desc;
+
+int b200cc_dgemm(const b200cc_gemm_desc* d, void* stream);
+
+/* ---- tensor permutation / strided axpby -------------------------------------------------------
+ * out[sum_d i_d*so[d]] = alpha * in[sum_d i_d*si[d]] + beta * out[...]  for i_d < shape[d], rank <= 6.
+ * Replaces tensordot's permute+contiguous copies and swapaxes/clone/+ ATen passes
+ * (e.g. ccwfn.py:757,759,922,933-934).  beta == 0 never reads `out`.                            */
+int b200cc_permute(int rank, const b200cc_i64* shape, const b200cc_i64* si, const b200cc_i64* so,
+                   double alpha, const double* in, double beta, double* out, void* stream);
+
+/* z = a*x + b*y  (n elements; z may alias x or y).  helper_diis error vectors (utils.py:291-293). */
+int b200cc_axpbyz(b200cc_i64 n, double a, const double* x, double b, const double* y, double* z, void* stream);
+
+/* tau = f1*t2 + f2*t1(x)t1   (build_tau, ccwfn.py:455) */
+int b200cc_build_tau(int no, int nv, double f1, double f2, const double* t1, const double* t2,
+                     double* tau, void* stream);
+
+/* out[i,j,a,b] = in[i,j,a,b] / (eo[i]+eo[j]-ev[a]-ev[b])  (ccwfn.py:195-198,211); in-place allowed.
+ * t1 form: out[i,a] = in[i,a] / (eo[i]-ev[a]).                                                   */
+int b200cc_div_d2(int no, int nv, const double* eo, const double* ev, const double* in, double* out, void* stream);
+int b200cc_div_d1(int no, int nv, const double* eo, const double* ev, const double* in, double* out, void* stream);
+
+/* Fused Jacobi update of solve_cc (ccwfn.py:281-284) with the r2 symmetrisation of r_T2 (ccwfn.py:790):
+ *   r2 = half + half^T(ij<->ji, ab<->ba);  t1 += r1/Dia;  t2 += r2/Dijab;
+ *   sumsq[0] = sum (r1/Dia)^2 + sum (r2/Dijab)^2          (device scalar; rms = sqrt on host)
+ * `r2_half` is overwritten with the symmetrised r2 when write_r2 != 0.  `symmetrize` = 0 treats
+ * r2_half as already symmetric.  scratch: >= 4096 doubles.                                       */
+int b200cc_update_amps(int no, int nv, const double* eo, const double* ev, const double* r1,
+                       double* r2_half, int symmetrize, int write_r2, double* t1, double* t2,
+                       double* sumsq, double* scratch, void* stream);
+
+/* r2 = half + half^T in place (r_T2, ccwfn.py:790) */
+int b200cc_symmetrize_r2(int no, int nv, double* r2, void* stream);
+
+/* E = 2 sum f_ia t_ia + sum (t2 + t1 t1)_ijab L_ijab   (cc_energy, ccwfn.py:1160-1161).
+ * fov: (no,nv) view with leading dimension ldf.  scratch: >= 4096 doubles.                       */
+int b200cc_cc_energy(int no, int nv, const double* fov, b200cc_i64 ldf, const double* t1, const double* t2,
+                     const double* Loovv, double* e_out, double* scratch, void* stream);
+
+/* out[q] = sum_i x[i]*y_q[i], q < m <= 16; `ys` is a HOST array of m device pointers.
+ * One pass over x; deterministic two-stage reduction.  (helper_diis B matrix, utils.py:330-339;
+ * rms contractions ccwfn.py:283.)  scratch: >= 16*1024 doubles.                                  */
+int b200cc_multi_dot(b200cc_i64 n, const double* x, int m, const double* const* ys, double* out,
+                     double* scratch, void* stream);
+
+/* out = sum_q c[q]*xs[q], q < m <= 16; `xs` HOST array of device pointers, `c` HOST coefficients.
+ * (helper_diis extrapolation, utils.py:353-355).  out may not alias any xs[q].                   */
+int b200cc_multi_axpy(b200cc_i64 n, int m, const double* c, const double* const* xs, double* out, void* stream);
+
+/* ---- (T): Lee-Rendell energy of a batch of (i>=j>=k) triples ---------------------------------
+ * Replaces the per-triple epilogue of t_tjl (cctriples.py:208-237: t3d_ijk, the 1/(1+delta)
+ * scaling, X3/Y3/Z3, denominators, the a>=b>=c sum).  Input: for each of `ntrip` triples the six
+ * GEMM outputs Q1..Q6 (each (nv*nv) x nv) produced by b200cc_dgemm:
+ *   W[a,b,c] = Q1[a,b,c]+Q2[a,c,b]+Q3[c,a,b]+Q4[c,b,a]+Q5[b,c,a]+Q6[b,a,c]
+ * Q: device, [ntrip][6][nv^3].  ijk: device int32 [ntrip][3].  fov: (no,nv) view, leading dim ldf.
+ * et_out[0] (+)= sum over the batch (accumulate != 0 adds to the existing value).
+ * scratch >= number of CTAs doubles (b200cc_t_energy_scratch).                                   */
+b200cc_i64 b200cc_t_energy_scratch(int nv, int ntrip);
+int b200cc_t_energy_batch(int no, int nv, int ntrip, const int* ijk, const double* Q,
+                          const double* t1, const double* t2, const double* oovv,
+                          const double* fov, b200cc_i64 ldf, const double* eo, const double* ev,
+                          double* et_out, int accumulate, double* scratch, void* stream);
+
+/* The connected (w3_out, = t3c_ijk) and disconnected (v3_out, = t3d_ijk) t3 numerators of ONE triple
+ * as (nv,nv,nv) arrays, w3 assembled from Q1..Q6 -- the per-triple parity hook for
+ * cctriples.py:27-72 and 108-147.  with_denom != 0 divides both by D_ijkabc.  v3_out may be NULL. */
+int b200cc_t3_assemble(int no, int nv, int i, int j, int k, const double* Q,
+                       const double* t1, const double* t2, const double* oovv,
+                       const double* fov, b200cc_i64 ldf, const double* eo, const double* ev,
+                       int with_denom, double* w3_out, double* v3_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

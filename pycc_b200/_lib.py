@@ -1,0 +1,120 @@
+"""ctypes binding of libb200cc.so (the C ABI declared in include/b200cc.h).
+
+The library is built in-tree (``pycc_b200/csrc/build.sh`` / ``__graft_entry__.build()``) and
+loaded from ``pycc_b200/libb200cc.so``.  There is no CPU implementation anywhere in this
+package: if the shared object is missing, or a tensor handed to a kernel is not a CUDA
+tensor, the call raises :class:`B200ccError` -- it never falls back to torch/numpy math.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+from .exceptions import PyCCError
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb200cc.so")
+
+i64 = C.c_longlong
+dptr = C.c_void_p
+
+
+class B200ccError(PyCCError, RuntimeError):
+    """A libb200cc call failed, or the CUDA extension / device is unavailable."""
+
+
+class GemmDesc(C.Structure):
+    """Mirror of ``b200cc_gemm_desc`` (include/b200cc.h)."""
+    _fields_ = [
+        ("M", C.c_int), ("N", C.c_int),
+        ("transA", C.c_int), ("transB", C.c_int),
+        ("K1", C.c_int), ("K2", C.c_int),
+        ("A1", dptr), ("B1", dptr), ("A2", dptr), ("B2", dptr),
+        ("lda1", i64), ("ldb1", i64), ("lda2", i64), ("ldb2", i64),
+        ("strideA1", i64), ("strideB1", i64), ("strideA2", i64), ("strideB2", i64),
+        ("C", dptr),
+        ("ldc", i64), ("strideC", i64),
+        ("alpha", C.c_double), ("beta", C.c_double),
+        ("batch", C.c_int),
+        ("table", dptr),
+        ("table_align16", C.c_int),
+        ("ksplit", C.c_int),
+        ("workspace", dptr),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/b200cc.h declares
+SIGNATURES = {
+    "b200cc_version": (C.c_int, []),
+    "b200cc_last_error": (C.c_char_p, []),
+    "b200cc_launch_count": (i64, []),
+    "b200cc_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3 + [C.POINTER(i64)] * 2),
+    "b200cc_dgemm": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
+    "b200cc_permute": (C.c_int, [C.c_int, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64),
+                                 C.c_double, dptr, C.c_double, dptr, C.c_void_p]),
+    "b200cc_axpbyz": (C.c_int, [i64, C.c_double, dptr, C.c_double, dptr, dptr, C.c_void_p]),
+    "b200cc_build_tau": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_double, dptr, dptr, dptr, C.c_void_p]),
+    "b200cc_div_d2": (C.c_int, [C.c_int, C.c_int, dptr, dptr, dptr, dptr, C.c_void_p]),
+    "b200cc_div_d1": (C.c_int, [C.c_int, C.c_int, dptr, dptr, dptr, dptr, C.c_void_p]),
+    "b200cc_update_amps": (C.c_int, [C.c_int, C.c_int, dptr, dptr, dptr, dptr, C.c_int, C.c_int,
+                                     dptr, dptr, dptr, dptr, C.c_void_p]),
+    "b200cc_symmetrize_r2": (C.c_int, [C.c_int, C.c_int, dptr, C.c_void_p]),
+    "b200cc_cc_energy": (C.c_int, [C.c_int, C.c_int, dptr, i64, dptr, dptr, dptr, dptr, dptr, C.c_void_p]),
+    "b200cc_multi_dot": (C.c_int, [i64, dptr, C.c_int, C.POINTER(dptr), dptr, dptr, C.c_void_p]),
+    "b200cc_multi_axpy": (C.c_int, [i64, C.c_int, C.POINTER(C.c_double), C.POINTER(dptr), dptr, C.c_void_p]),
+    "b200cc_t_energy_scratch": (i64, [C.c_int, C.c_int]),
+    "b200cc_t_energy_batch": (C.c_int, [C.c_int, C.c_int, C.c_int, dptr, dptr, dptr, dptr, dptr, dptr, i64,
+                                        dptr, dptr, dptr, C.c_int, dptr, C.c_void_p]),
+    "b200cc_t3_assemble": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, dptr, dptr, dptr, dptr,
+                                     dptr, i64, dptr, dptr, C.c_int, dptr, dptr, C.c_void_p]),
+}
+
+_LIB = None
+# Test seam ONLY (tests/emu.py): lets the host-side logic be driven on CPU tensors against a numpy
+# double of the C ABI.  The product never clears it.
+REQUIRE_CUDA = True
+
+
+def load(path=LIB_PATH):
+    """dlopen libb200cc.so and attach prototypes.  Raises B200ccError if it is not built."""
+    if not os.path.exists(path):
+        raise B200ccError(
+            "libb200cc.so not found at %s: build it with pycc_b200/csrc/build.sh "
+            "(or __graft_entry__.build()).  pycc_b200 has no CPU fallback." % path)
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)        # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+def get():
+    global _LIB
+    if _LIB is None:
+        _LIB = load()
+    return _LIB
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = get().b200cc_last_error()
+        raise B200ccError("%s failed: %s" % (what, msg.decode() if isinstance(msg, bytes) else msg))
+
+
+def ptr(t):
+    """Device address of a float64/int tensor (validated)."""
+    if t is None:
+        return None
+    if REQUIRE_CUDA and not t.is_cuda:
+        raise B200ccError("pycc_b200 kernels need CUDA tensors (got a %s tensor); there is no CPU path"
+                          % t.device)
+    return t.data_ptr()
+
+
+def stream():
+    if REQUIRE_CUDA:
+        return torch.cuda.current_stream().cuda_stream
+    return None

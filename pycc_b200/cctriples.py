@@ -1,0 +1,281 @@
+"""(T) correction on B200 (reference: pycc/cctriples.py:27-354).
+
+``t_tjl(ccwfn)`` -- the (T) that ``solve_cc`` calls -- is re-built around two kernels:
+
+1. the connected t3 numerator of a *batch* of (i>=j>=k) triples is six two-segment FP64 DMMA GEMMs
+   per triple in ONE launch (``b200cc_dgemm`` in address-table mode):
+       Q1[(a,b),c] = sum_e <ib|ea>... i.e.  ovvv[i][e,(a,b)]^T t2[k,j][c,e]^T  -  t2[i][m,(a,b)]^T <jk|mc>
+   particle term (K = v) and hole term (K = o) chained into the same accumulators; <mb|ef> and t2 are
+   read in their natural layouts (no permuted copies), only the small <mn|ie> block is pre-permuted;
+2. ``b200cc_t_energy_batch`` reads Q1..Q6 once and does everything else of cctriples.py:208-237 on the
+   fly (disconnected part, 1/(1+delta), X3/Y3/Z3, denominators, a>=b>=c reduction).
+
+Triples are independent: with a ``comm`` (parallel.Comm) they are dealt round-robin to the ranks and
+the energy is summed with one scalar all-reduce.
+
+The other public names of the reference's triples module that sit on the energy path keep their
+signatures: ``t3c_ijk``, ``t3d_ijk`` (generic in the passed W blocks), ``t_vikings`` and
+``t_vikings_inverted`` (cross-check formulations, same E(T)).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import kernels as K
+from ._lib import B200ccError
+
+F64 = torch.float64
+
+# per term q: (occupied index of the <mb|ef> slab and of the t2[x] slab,
+#              (p,q) of t2[p,q] in the particle GEMM, (p,q) of Y[p,q] in the hole GEMM)
+# as positions into (i,j,k); see DESIGN.md "(T)" for the derivation from cctriples.py:50-62
+_TERMS = (
+    (0, (2, 1), (1, 2)),   # Q1[(a,b),c]: ovvv[i], t2[k,j] ; t2[i], <jk|mc>
+    (0, (1, 2), (2, 1)),   # Q2[(a,c),b]: ovvv[i], t2[j,k] ; t2[i], <kj|mb>
+    (2, (1, 0), (0, 1)),   # Q3[(c,a),b]: ovvv[k], t2[j,i] ; t2[k], <ij|mb>
+    (2, (0, 1), (1, 0)),   # Q4[(c,b),a]: ovvv[k], t2[i,j] ; t2[k], <ji|ma>
+    (1, (0, 2), (2, 0)),   # Q5[(b,c),a]: ovvv[j], t2[i,k] ; t2[j], <ki|ma>
+    (1, (2, 0), (0, 2)),   # Q6[(b,a),c]: ovvv[j], t2[k,i] ; t2[j], <ik|mc>
+)
+
+
+def triples_list(no):
+    """All (i >= j >= k), in the reference's loop order (cctriples.py:204-206)."""
+    return [(i, j, k) for i in range(no) for j in range(i + 1) for k in range(j + 1)]
+
+
+class TriplesEngine:
+    """Owns the constant operands of the (T) GEMMs for one wavefunction state."""
+
+    def __init__(self, ccwfn, t1=None, t2=None, q_bytes=None):
+        self.w = ccwfn
+        H = ccwfn.H
+        self.no, self.nv = ccwfn.no, ccwfn.nv
+        self.t1 = (ccwfn.t1 if t1 is None else t1).contiguous()
+        self.t2 = (ccwfn.t2 if t2 is None else t2).contiguous()
+        self.ovvv = H.block("ovvv")
+        self.oovv = H.block("oovv")
+        # Y[j,k,c,m] = -<mc|jk> = -ooov[j,k,m,c]
+        self.Y = K.permuted(H.block("ooov"), (0, 1, 3, 2), -1.0)
+        self.fov = H.F[ccwfn.o, ccwfn.v]
+        self.dev = self.t2.device
+        nv = self.nv
+        per = 6 * nv ** 3 * 8
+        if q_bytes is None:
+            q_bytes = 8 << 30
+            if self.dev.type == "cuda":
+                free, _ = torch.cuda.mem_get_info(self.dev)
+                q_bytes = max(per, min(q_bytes * 2, int(free * 0.5)))
+        self.nb_max = int(max(1, min(q_bytes // max(per, 1), 65535 // 6, 4096)))
+        self._Q = None
+
+    def qbuf(self, nb):
+        need = nb * 6 * self.nv ** 3
+        if self._Q is None or self._Q.numel() < need:
+            self._Q = None
+            self._Q = torch.empty(need, dtype=F64, device=self.dev)
+        return self._Q
+
+    def table(self, trip, Q):
+        """int64 [6*nb, 5] device table of {A1, B1, A2, B2, C} addresses for b200cc_dgemm."""
+        T = np.asarray(trip, dtype=np.int64).reshape(-1, 3)
+        nb = T.shape[0]
+        no, nv = self.no, self.nv
+        v2, v3 = nv * nv, nv ** 3
+        p_ovvv, p_t2, p_Y, p_Q = (x.data_ptr() for x in (self.ovvv, self.t2, self.Y, Q))
+        tab = np.empty((nb, 6, 5), dtype=np.int64)
+        for q, (x, (p1, q1), (p2, q2)) in enumerate(_TERMS):
+            tab[:, q, 0] = p_ovvv + 8 * T[:, x] * v3
+            tab[:, q, 1] = p_t2 + 8 * (T[:, p1] * no + T[:, q1]) * v2
+            tab[:, q, 2] = p_t2 + 8 * T[:, x] * no * v2
+            tab[:, q, 3] = p_Y + 8 * (T[:, p2] * no + T[:, q2]) * nv * no
+            tab[:, q, 4] = p_Q + 8 * (np.arange(nb) * 6 + q) * v3
+        aligned = bool(np.all(tab % 16 == 0))
+        return torch.from_numpy(tab.reshape(nb * 6, 5)).to(self.dev), aligned
+
+    def build_q(self, trip, Q=None):
+        """Launch the 6*len(trip) two-segment GEMMs; returns the Q buffer ([nb][6][v^3])."""
+        nb = len(trip)
+        Q = self.qbuf(nb) if Q is None else Q
+        tab, aligned = self.table(trip, Q)
+        no, nv = self.no, self.nv
+        K.dgemm(nv * nv, nv, nv, self.ovvv, nv * nv, 1, self.t2, nv, 0, Q, nv, 1.0, 0.0,
+                batch=6 * nb, seg2=(self.t2, nv * nv, self.Y, no, no, 0, 0),
+                table=tab, table_align16=aligned, ksplit=1)
+        return Q
+
+    def energy(self, trip):
+        """Sum of the Lee-Rendell contributions of the given triples, as a 1-element device tensor."""
+        et = torch.zeros(1, dtype=F64, device=self.dev)
+        w = self.w
+        for s in range(0, len(trip), self.nb_max):
+            chunk = trip[s:s + self.nb_max]
+            Q = self.build_q(chunk)
+            ijk = torch.tensor(np.asarray(chunk, dtype=np.int32).reshape(-1, 3), dtype=torch.int32).to(self.dev)
+            K.t_energy_batch(self.no, self.nv, ijk, Q, self.t1, self.t2, self.oovv, self.fov,
+                             w.eps_o, w.eps_v, et, accumulate=True)
+        return et
+
+    def t3_parts(self, i, j, k, with_denom):
+        """(connected, disconnected) t3 numerators of one triple as (v,v,v) tensors."""
+        Q = self.build_q([(i, j, k)])
+        return K.t3_assemble(self.no, self.nv, i, j, k, Q, self.t1, self.t2, self.oovv, self.fov,
+                             self.w.eps_o, self.w.eps_v, with_denom)
+
+
+def t_tjl(ccwfn, triples=None):
+    """E(T), Lee-Rendell formulation (reference: cctriples.py:177-239).  Returns a 0-d device tensor."""
+    eng = TriplesEngine(ccwfn)
+    comm = getattr(ccwfn, "comm", None)
+    trip = triples_list(ccwfn.no) if triples is None else list(triples)
+    # i = j = k contributes exactly zero (the bracket vanishes identically): skip those tiles
+    trip = [t for t in trip if not (t[0] == t[1] == t[2])]
+    if comm is not None and comm.size > 1:
+        trip = trip[comm.rank::comm.size]
+    et = eng.energy(trip)
+    if comm is not None and comm.size > 1:
+        comm.all_reduce_sum(et)
+    return et[0]
+
+
+# ---- per-triple building blocks with the reference's signatures -----------------------------------------
+def _eps(F, o, v):
+    d = torch.diagonal(F)
+    return d[o].contiguous(), d[v].contiguous()
+
+
+def t3c_ijk(o, v, i, j, k, t2, Wvvvo, Wovoo, F, contract, WithDenom=True):
+    """Connected t3 for fixed (i,j,k) from ARBITRARY W blocks (reference: cctriples.py:27-72); the
+    twelve contractions go through ``contract`` (DMMA GEMMs), the denominator through the t3 kernel."""
+    nv, no = t2.shape[2], t2.shape[0]
+    Wv = {x: Wvvvo[:, :, :, x] for x in {i, j, k}}
+    t3 = contract('bae,ce->abc', Wv[i], t2[k, j])
+    for sub, x, (p, q) in (('cae,be->abc', i, (j, k)), ('ace,be->abc', k, (j, i)), ('bce,ae->abc', k, (i, j)),
+                           ('cbe,ae->abc', j, (i, k)), ('abe,ce->abc', j, (k, i))):
+        contract(sub, Wv[x], t2[p, q], out=t3, alpha=1.0, beta=1.0)
+    for sub, (p, q), x in (('mc,mab->abc', (j, k), i), ('mb,mac->abc', (k, j), i), ('mb,mca->abc', (i, j), k),
+                           ('ma,mcb->abc', (j, i), k), ('ma,mbc->abc', (k, i), j), ('mc,mba->abc', (i, k), j)):
+        contract(sub, Wovoo[:, :, p, q], t2[x], out=t3, alpha=-1.0, beta=1.0)
+    if not WithDenom:
+        return t3
+    eo, ev = _eps(F, o, v)
+    Q = torch.zeros(6 * nv ** 3, dtype=F64, device=t3.device)
+    K.strided_axpby(Q[:nv ** 3].view(nv, nv, nv), t3, 1.0, 0.0)
+    z1 = torch.zeros((no, nv), dtype=F64, device=t3.device)
+    z2 = torch.zeros((no, no, nv, nv), dtype=F64, device=t3.device)
+    w3, _ = K.t3_assemble(no, nv, i, j, k, Q, z1, z2, z2, z1, eo, ev, True)
+    return w3
+
+
+def t3d_ijk(o, v, i, j, k, t1, t2, Woovv, F, contract, WithDenom=True):
+    """Disconnected t3 for fixed (i,j,k) (reference: cctriples.py:108-147)."""
+    no, nv = t1.shape
+    eo, ev = _eps(F, o, v)
+    Q = torch.zeros(6 * nv ** 3, dtype=F64, device=t2.device)
+    Wc = Woovv if Woovv.is_contiguous() else K.permuted(Woovv, (0, 1, 2, 3))
+    _, d3 = K.t3_assemble(no, nv, i, j, k, Q, t1.contiguous(), t2.contiguous(), Wc, F[o, v], eo, ev, WithDenom)
+    return d3
+
+
+def t_vikings(ccwfn):
+    """E(T), Helgaker-Jorgensen-Olsen full-loop formulation (reference: cctriples.py:243-307).  Cross-check
+    only (6x the work of t_tjl): t3 tiles come from the same GEMM + assemble kernels, the X1/X2
+    contractions go through the generic contraction backend."""
+    ct = ccwfn.contract.engine
+    H = ccwfn.H
+    no, nv = ccwfn.no, ccwfn.nv
+    o, v = ccwfn.o, ccwfn.v
+    eng = TriplesEngine(ccwfn)
+    t1, t2 = eng.t1, eng.t2
+    dev = t2.device
+    X1 = torch.zeros_like(t1)
+    X2 = torch.zeros_like(t2)
+    Loovv = H.derived("Loovv")
+    ovvv, ooov = H.block("ovvv"), H.block("ooov")
+    Fov = K.permuted(H.F[o, v], (0, 1))
+    for i in range(no):
+        for j in range(no):
+            for k in range(no):
+                t3, _ = eng.t3_parts(i, j, k, True)
+                u = K.permuted(t3, (0, 1, 2))                           # t3 - t3[c,b,a]
+                K.strided_axpby(u, t3.permute(2, 1, 0), -1.0, 1.0)
+                w = K.permuted(t3, (0, 1, 2), 2.0)                      # 2 t3 - t3[a,c,b] - t3[c,b,a]
+                K.strided_axpby(w, t3.permute(0, 2, 1), -1.0, 1.0)
+                K.strided_axpby(w, t3.permute(2, 1, 0), -1.0, 1.0)
+                ct('abc,bc->a', u, Loovv[j, k], out=X1[i], alpha=1.0, beta=1.0)
+                ct('abc,dcb->ad', w, ovvv[k], out=X2[i, j], alpha=1.0, beta=1.0)   # <dk|bc> = ovvv[k,d,c,b]
+                ct('abc,lc->lab', w, ooov[j, k], out=X2[i], alpha=-1.0, beta=1.0)
+                ct('abc,c->ab', u, Fov[k], out=X2[i, j], alpha=1.0, beta=1.0)
+    s = K.permuted(t2, (0, 1, 2, 3), 4.0)
+    K.strided_axpby(s, t2.permute(0, 1, 3, 2), -2.0, 1.0)
+    d1 = K.multi_dot(t1.reshape(-1), [X1.reshape(-1)])
+    d2 = K.multi_dot(s.reshape(-1), [X2.reshape(-1)])
+    out = torch.empty(1, dtype=F64, device=dev)
+    K.axpbyz(2.0, d1, 1.0, d2, out)
+    return out[0]
+
+
+def t_vikings_inverted(ccwfn):
+    """E(T), virtual-batched "vikings" form (reference: cctriples.py:311-354): fixed (a,b,c), all (i,j,k).
+    Cross-check only; every contraction goes through the generic contraction backend."""
+    ct = ccwfn.contract.engine
+    H = ccwfn.H
+    no, nv = ccwfn.no, ccwfn.nv
+    o, v = ccwfn.o, ccwfn.v
+    t1, t2 = ccwfn.t1.contiguous(), ccwfn.t2.contiguous()
+    dev = t2.device
+    ovvv, ooov = H.block("ovvv"), H.block("ooov")
+    Loovv = H.derived("Loovv")
+    Fov = K.permuted(H.F[o, v], (0, 1))
+    X1 = torch.zeros((nv, no), dtype=F64, device=dev)
+    X2 = torch.zeros((nv, nv, no, no), dtype=F64, device=dev)
+    # Wvvvo[x,y,e,i] = ovvv[i,e,y,x] -> Wv[x,y][e,i];  Wovoo[m,x,j,k] = ooov[j,k,m,x]
+    Wvvvo = ovvv.permute(3, 2, 1, 0)
+    Wovoo = ooov.permute(2, 3, 0, 1)
+    t2v = K.permuted(t2, (2, 3, 0, 1))                 # [a,b,i,j]
+    # denominators through the d1 kernel on the (ij, k) view: t3[(i,j),k] / (rows[(i,j)] - negk[k]),
+    # rows = e_i + e_j - (e_a+e_b+e_c), negk = -e_k
+    eo, ev = ccwfn.eps_o, ccwfn.eps_v
+    rows0 = torch.empty((no, no), dtype=F64, device=dev)
+    K.strided_axpby(rows0, eo.view(-1, 1).expand(no, no), 1.0, 0.0)
+    K.strided_axpby(rows0, eo.view(1, -1).expand(no, no), 1.0, 1.0)
+    rows0 = rows0.view(-1)
+    ones = torch.ones(no * no, dtype=F64, device=dev)
+    rows = torch.empty(no * no, dtype=F64, device=dev)
+    negk = torch.empty(no, dtype=F64, device=dev)
+    K.axpbyz(-1.0, eo, 0.0, None, negk)
+    ev_h = ev.tolist()
+    for a in range(nv):
+        for b in range(nv):
+            for c in range(nv):
+                t3 = ct('ei,kje->ijk', Wvvvo[b, a], t2[:, :, c])
+                for sub, (x, y), z in (('ei,jke->ijk', (c, a), b), ('ek,jie->ijk', (a, c), b),
+                                       ('ek,ije->ijk', (b, c), a), ('ej,ike->ijk', (c, b), a),
+                                       ('ej,kie->ijk', (a, b), c)):
+                    ct(sub, Wvvvo[x, y], t2[:, :, z], out=t3, alpha=1.0, beta=1.0)
+                for sub, x, (y, z) in (('mjk,im->ijk', c, (a, b)), ('mkj,im->ijk', b, (a, c)),
+                                       ('mij,km->ijk', b, (c, a)), ('mji,km->ijk', a, (c, b)),
+                                       ('mki,jm->ijk', a, (b, c)), ('mik,jm->ijk', c, (b, a))):
+                    ct(sub, Wovoo[:, x], t2v[y, z], out=t3, alpha=-1.0, beta=1.0)
+                K.axpbyz(1.0, rows0, -(ev_h[a] + ev_h[b] + ev_h[c]), ones, rows)
+                t3 = K.div_d1(t3.view(no * no, no), rows, negk).view(no, no, no)
+                u = K.permuted(t3, (0, 1, 2))
+                K.strided_axpby(u, t3.permute(2, 1, 0), -1.0, 1.0)
+                w = K.permuted(t3, (0, 1, 2), 2.0)
+                K.strided_axpby(w, t3.permute(0, 2, 1), -1.0, 1.0)
+                K.strided_axpby(w, t3.permute(2, 1, 0), -1.0, 1.0)
+                ct('ijk,jk->i', u, Loovv[:, :, b, c], out=X1[a], alpha=1.0, beta=1.0)
+                # ERI[v,o,v,v][d,k,b,c] = ovvv[k,d,c,b]
+                ct('ijk,kd->dij', w, ovvv[:, :, c, b], out=X2[a], alpha=1.0, beta=1.0)
+                ct('ijk,jkl->il', w, ooov[:, :, :, c], out=X2[a, b], alpha=-1.0, beta=1.0)
+                ct('ijk,k->ij', u, Fov[:, c], out=X2[a, b], alpha=1.0, beta=1.0)
+    # (4 t2 - 2 t2.swapaxes(2,3)) against X2.T, literally: s[a,d,i,j] = 4 t2[j,i,d,a] - 2 t2[j,i,a,d]
+    s = K.permuted(t2, (3, 2, 1, 0), 4.0)
+    K.strided_axpby(s, t2.permute(2, 3, 1, 0), -2.0, 1.0)
+    t1T = K.permuted(t1, (1, 0))
+    d1 = K.multi_dot(t1T.reshape(-1), [X1.reshape(-1)])
+    d2 = K.multi_dot(s.reshape(-1), [X2.reshape(-1)])
+    out = torch.empty(1, dtype=F64, device=dev)
+    K.axpbyz(2.0, d1, 1.0, d2, out)
+    return out[0]

@@ -1,0 +1,162 @@
+// permute.cu -- strided tensor permutation / axpby, HBM-bound.
+//   out[sum_d i_d*so[d]] = alpha * in[sum_d i_d*si[d]] + beta * out[...]
+// Two kernels:
+//   rowcopy  : the fastest-varying loop dimension is (near-)contiguous on both sides; one thread per
+//              element, consecutive threads along that dimension (coalesced loads and stores).
+//   transpose: input and output are contiguous along DIFFERENT dimensions; a 32x32 tile of those two
+//              dimensions goes through shared memory (33-column padding) so both sides are coalesced.
+#include "common.cuh"
+
+namespace b200cc {
+
+constexpr int MAXR = 6;
+
+struct PermParams {
+  int rank;
+  i64 shape[MAXR], si[MAXR], so[MAXR];
+  double alpha, beta;
+  i64 total;
+  // transpose kernel: dx = dimension contiguous in the input, dy = dimension contiguous in the output
+  int dx, dy;
+  i64 tiles_x, tiles_y, outer;
+};
+
+__global__ void __launch_bounds__(256) permute_rowcopy_kernel(const PermParams p, const double* __restrict__ in,
+                                                              double* __restrict__ out) {
+  for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < p.total; e += (i64)gridDim.x * blockDim.x) {
+    i64 r = e, oi = 0, oo = 0;
+#pragma unroll
+    for (int d = MAXR - 1; d >= 0; --d) {
+      if (d < p.rank) {
+        const i64 s = p.shape[d];
+        const i64 qd = r / s;
+        const i64 id = r - qd * s;
+        r = qd;
+        oi += id * p.si[d];
+        oo += id * p.so[d];
+      }
+    }
+    const double v = p.alpha * in[oi];
+    out[oo] = (p.beta != 0.0) ? v + p.beta * out[oo] : v;
+  }
+}
+
+// grid.x enumerates (outer index, tile_y, tile_x); block = 32 x 8
+__global__ void __launch_bounds__(256) permute_transpose_kernel(const PermParams p, const double* __restrict__ in,
+                                                                double* __restrict__ out) {
+  __shared__ double tile[32][33];
+  i64 bid = blockIdx.x;
+  const i64 tx = bid % p.tiles_x; bid /= p.tiles_x;
+  const i64 ty = bid % p.tiles_y; bid /= p.tiles_y;
+  // remaining dims (all except dx, dy) from bid
+  i64 oi = 0, oo = 0, r = bid;
+#pragma unroll
+  for (int d = MAXR - 1; d >= 0; --d) {
+    if (d < p.rank && d != p.dx && d != p.dy) {
+      const i64 s = p.shape[d];
+      const i64 qd = r / s;
+      const i64 id = r - qd * s;
+      r = qd;
+      oi += id * p.si[d];
+      oo += id * p.so[d];
+    }
+  }
+  const i64 x0 = tx * 32, y0 = ty * 32;
+  const i64 nx = p.shape[p.dx], ny = p.shape[p.dy];
+  const i64 six = p.si[p.dx], siy = p.si[p.dy], sox = p.so[p.dx], soy = p.so[p.dy];
+  // load: threadIdx.x runs along dx (input-contiguous)
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const i64 x = x0 + threadIdx.x, y = y0 + threadIdx.y + k;
+    if (x < nx && y < ny) tile[threadIdx.y + k][threadIdx.x] = in[oi + x * six + y * siy];
+  }
+  __syncthreads();
+  // store: threadIdx.x runs along dy (output-contiguous)
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const i64 y = y0 + threadIdx.x, x = x0 + threadIdx.y + k;
+    if (x < nx && y < ny) {
+      const i64 o = oo + x * sox + y * soy;
+      const double v = p.alpha * tile[threadIdx.x][threadIdx.y + k];
+      out[o] = (p.beta != 0.0) ? v + p.beta * out[o] : v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) axpbyz_kernel(i64 n, double a, const double* x, double b, const double* y,
+                                                     double* z) {
+  for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (i64)gridDim.x * blockDim.x) {
+    double v = 0.0;
+    if (a != 0.0) v += a * x[e];
+    if (b != 0.0) v += b * y[e];
+    z[e] = v;
+  }
+}
+
+static i64 iabs(i64 x) { return x < 0 ? -x : x; }
+
+}  // namespace b200cc
+
+using namespace b200cc;
+
+extern "C" int b200cc_permute(int rank, const b200cc_i64* shape, const b200cc_i64* si, const b200cc_i64* so,
+                              double alpha, const double* in, double beta, double* out, void* stream) {
+  if (rank < 0 || rank > MAXR) { set_error("b200cc_permute: rank %d not in [0,%d]", rank, MAXR); return 1; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PermParams p;
+  // drop extent-1 dims, detect empty
+  p.rank = 0;
+  p.total = 1;
+  for (int d = 0; d < rank; ++d) {
+    if (shape[d] < 0) { set_error("b200cc_permute: negative extent"); return 1; }
+    if (shape[d] == 0) return 0;
+    if (shape[d] == 1) continue;
+    p.shape[p.rank] = shape[d]; p.si[p.rank] = si[d]; p.so[p.rank] = so[d];
+    p.total *= shape[d];
+    ++p.rank;
+  }
+  if (p.rank == 0) { p.rank = 1; p.shape[0] = 1; p.si[0] = 0; p.so[0] = 0; }
+  // sort loop dims by DEcreasing |output stride| so that the last dim is the output-fastest one
+  for (int a = 0; a < p.rank; ++a)
+    for (int b = a + 1; b < p.rank; ++b)
+      if (iabs(p.so[b]) > iabs(p.so[a])) {
+        i64 t;
+        t = p.shape[a]; p.shape[a] = p.shape[b]; p.shape[b] = t;
+        t = p.si[a]; p.si[a] = p.si[b]; p.si[b] = t;
+        t = p.so[a]; p.so[a] = p.so[b]; p.so[b] = t;
+      }
+  for (int d = p.rank; d < MAXR; ++d) { p.shape[d] = 1; p.si[d] = 0; p.so[d] = 0; }
+  p.alpha = alpha; p.beta = beta;
+  const int last = p.rank - 1;
+  // input-fastest dim
+  int dx = 0;
+  for (int d = 1; d < p.rank; ++d)
+    if (p.si[d] != 0 && (p.si[dx] == 0 || iabs(p.si[d]) < iabs(p.si[dx]))) dx = d;
+  const bool need_transpose = p.rank >= 2 && dx != last && iabs(p.si[last]) != 1 && p.si[dx] != 0 &&
+                              p.shape[dx] >= 8 && p.shape[last] >= 8;
+  const int cap = sm_count() * 16;
+  if (!need_transpose) {
+    i64 blocks = (p.total + 255) / 256;
+    if (blocks > cap) blocks = cap;
+    permute_rowcopy_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, in, out);
+    return check_launch("permute_rowcopy_kernel");
+  }
+  p.dx = dx; p.dy = last;
+  p.tiles_x = (p.shape[dx] + 31) / 32;
+  p.tiles_y = (p.shape[last] + 31) / 32;
+  p.outer = p.total / (p.shape[dx] * p.shape[last]);
+  const i64 nblocks = p.tiles_x * p.tiles_y * p.outer;
+  if (nblocks > 2147483647LL) { set_error("b200cc_permute: grid too large"); return 1; }
+  permute_transpose_kernel<<<(unsigned)nblocks, dim3(32, 8), 0, st>>>(p, in, out);
+  return check_launch("permute_transpose_kernel");
+}
+
+extern "C" int b200cc_axpbyz(b200cc_i64 n, double a, const double* x, double b, const double* y, double* z,
+                             void* stream) {
+  if (n <= 0) return 0;
+  i64 blocks = (n + 255) / 256;
+  const int cap = sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  axpbyz_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(n, a, x, b, y, z);
+  return check_launch("axpbyz_kernel");
+}

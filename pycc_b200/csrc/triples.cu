@@ -1,0 +1,166 @@
+// triples.cu -- the Lee-Rendell (T) epilogue, fused.
+//
+// The six two-segment GEMMs of b200cc_dgemm leave, per (i>=j>=k) triple, Q1..Q6 of shape (nv,nv,nv)
+// with   W[a,b,c] = Q1[a,b,c] + Q2[a,c,b] + Q3[c,a,b] + Q4[c,b,a] + Q5[b,c,a] + Q6[b,a,c]
+// (the connected numerator of cctriples.py:50-62; particle and hole terms already summed).
+// This kernel reads every Q element exactly once and never materialises W, V, X3, Y3, Z3 or the
+// denominator cube: a CTA owns an 8x8x8 block of the sorted (a>=b>=c) index space, each thread one
+// (a,b,c); it gathers the 36 Q values that make W at the six permutations of (a,b,c), adds the
+// disconnected part on the fly from t1/t2/<ij|ab>/f_ov (cctriples.py:131-137), applies the
+// 1/(1+delta) factor (210-213), forms the Lee-Rendell bracket (215-237) and reduces.
+#include "common.cuh"
+
+namespace b200cc {
+
+constexpr int TT = 8;  // cube edge
+
+struct TArgs {
+  int no, nv, nt;
+  const int* ijk;
+  const double* Q;
+  const double *t1, *t2, *oovv, *fov, *eo, *ev;
+  i64 ldf;
+};
+
+__device__ __forceinline__ double wsum(const double* __restrict__ Q, i64 v3, int nv, int x, int y, int z) {
+  const i64 xyz = ((i64)x * nv + y) * nv + z, xzy = ((i64)x * nv + z) * nv + y;
+  const i64 zxy = ((i64)z * nv + x) * nv + y, zyx = ((i64)z * nv + y) * nv + x;
+  const i64 yzx = ((i64)y * nv + z) * nv + x, yxz = ((i64)y * nv + x) * nv + z;
+  return Q[xyz] + Q[v3 + xzy] + Q[2 * v3 + zxy] + Q[3 * v3 + zyx] + Q[4 * v3 + yzx] + Q[5 * v3 + yxz];
+}
+
+struct Disc {  // row pointers for the disconnected part of one (i,j,k)
+  const double *Kij, *Kik, *Kjk, *Tij, *Tik, *Tjk, *t1i, *t1j, *t1k, *fi, *fj, *fk;
+  int nv;
+  __device__ __forceinline__ double operator()(int x, int y, int z) const {
+    return Kij[x * nv + y] * t1k[z] + Kik[x * nv + z] * t1j[y] + Kjk[y * nv + z] * t1i[x] +
+           Tij[x * nv + y] * fk[z] + Tik[x * nv + z] * fj[y] + Tjk[y * nv + z] * fi[x];
+  }
+};
+
+__device__ __forceinline__ Disc make_disc(const TArgs& p, int i, int j, int k) {
+  const i64 vv = (i64)p.nv * p.nv;
+  Disc d;
+  d.Kij = p.oovv + ((i64)i * p.no + j) * vv; d.Kik = p.oovv + ((i64)i * p.no + k) * vv;
+  d.Kjk = p.oovv + ((i64)j * p.no + k) * vv;
+  d.Tij = p.t2 + ((i64)i * p.no + j) * vv; d.Tik = p.t2 + ((i64)i * p.no + k) * vv;
+  d.Tjk = p.t2 + ((i64)j * p.no + k) * vv;
+  d.t1i = p.t1 + (i64)i * p.nv; d.t1j = p.t1 + (i64)j * p.nv; d.t1k = p.t1 + (i64)k * p.nv;
+  d.fi = p.fov + (i64)i * p.ldf; d.fj = p.fov + (i64)j * p.ldf; d.fk = p.fov + (i64)k * p.ldf;
+  d.nv = p.nv;
+  return d;
+}
+
+// grid = (sorted 8-cube triples, ntrip); block = 512
+__global__ void __launch_bounds__(512) t_energy_kernel(const TArgs p, double* scratch) {
+  __shared__ double red[16];
+  // decode blockIdx.x -> (TA >= TB >= TC)
+  int rem = blockIdx.x, TA = 0;
+  while ((TA + 1) * (TA + 2) * (TA + 3) / 6 <= rem) ++TA;
+  rem -= TA * (TA + 1) * (TA + 2) / 6;
+  int TB = 0;
+  while ((TB + 1) * (TB + 2) / 2 <= rem) ++TB;
+  const int TC = rem - TB * (TB + 1) / 2;
+  const int trip = blockIdx.y;
+  const int i = p.ijk[3 * trip], j = p.ijk[3 * trip + 1], k = p.ijk[3 * trip + 2];
+  const int lc = threadIdx.x & 7, lb = (threadIdx.x >> 3) & 7, la = threadIdx.x >> 6;
+  const int a = TA * TT + la, b = TB * TT + lb, c = TC * TT + lc;
+  const int nv = p.nv;
+  double e = 0.0;
+  if (a < nv && b <= a && c <= b) {
+    const i64 v3 = (i64)nv * nv * nv;
+    const double* Q = p.Q + (i64)trip * 6 * v3;
+    const Disc D = make_disc(p, i, j, k);
+    const double sc = 1.0 / (1.0 + (a == b ? 1.0 : 0.0) + (a == c ? 1.0 : 0.0) + (b == c ? 1.0 : 0.0));
+    const double Wabc = wsum(Q, v3, nv, a, b, c), Wacb = wsum(Q, v3, nv, a, c, b);
+    const double Wbac = wsum(Q, v3, nv, b, a, c), Wbca = wsum(Q, v3, nv, b, c, a);
+    const double Wcab = wsum(Q, v3, nv, c, a, b), Wcba = wsum(Q, v3, nv, c, b, a);
+    const double Vabc = (Wabc + D(a, b, c)) * sc, Vacb = (Wacb + D(a, c, b)) * sc;
+    const double Vbac = (Wbac + D(b, a, c)) * sc, Vbca = (Wbca + D(b, c, a)) * sc;
+    const double Vcab = (Wcab + D(c, a, b)) * sc, Vcba = (Wcba + D(c, b, a)) * sc;
+    const double X = Wabc * Vabc + Wacb * Vacb + Wbac * Vbac + Wbca * Vbca + Wcab * Vcab + Wcba * Vcba;
+    const double Y = Vabc + Vbca + Vcab, Z = Vacb + Vbac + Vcba;
+    const double Wc = Wabc + Wbca + Wcab, Wo = Wacb + Wbac + Wcba;
+    const double den = p.eo[i] + p.eo[j] + p.eo[k] - p.ev[a] - p.ev[b] - p.ev[c];
+    const double occ = 2.0 - ((i == j ? 1.0 : 0.0) + (i == k ? 1.0 : 0.0) + (j == k ? 1.0 : 0.0));
+    e = ((Y - 2.0 * Z) * Wc + (Z - 2.0 * Y) * Wo + 3.0 * X) * occ / den;
+  }
+  // block reduce over 16 warps
+  e = warp_sum(e);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double s = threadIdx.x < 16 ? red[threadIdx.x] : 0.0;
+    s = warp_sum(s);
+    if (threadIdx.x == 0) scratch[(i64)trip * gridDim.x + blockIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) t3_assemble_kernel(const TArgs p, int i, int j, int k, int with_denom,
+                                                          double* w3, double* v3o) {
+  const int nv = p.nv;
+  const i64 v3 = (i64)nv * nv * nv;
+  const Disc D = make_disc(p, i, j, k);
+  for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < v3; e += (i64)gridDim.x * blockDim.x) {
+    const int c = (int)(e % nv);
+    const int b = (int)((e / nv) % nv);
+    const int a = (int)(e / ((i64)nv * nv));
+    double w = wsum(p.Q, v3, nv, a, b, c);   // t3c_ijk numerator
+    double v = D(a, b, c);                   // t3d_ijk numerator
+    if (with_denom) {
+      const double den = p.eo[i] + p.eo[j] + p.eo[k] - p.ev[a] - p.ev[b] - p.ev[c];
+      v /= den;
+      w /= den;
+    }
+    w3[e] = w;
+    if (v3o) v3o[e] = v;
+  }
+}
+
+static int sorted_cubes(int nv) {
+  const int nt = (nv + TT - 1) / TT;
+  return nt * (nt + 1) * (nt + 2) / 6;
+}
+
+}  // namespace b200cc
+
+using namespace b200cc;
+
+extern "C" b200cc_i64 b200cc_t_energy_scratch(int nv, int ntrip) {
+  return (b200cc_i64)sorted_cubes(nv) * ntrip;
+}
+
+extern "C" int b200cc_t_energy_batch(int no, int nv, int ntrip, const int* ijk, const double* Q, const double* t1,
+                                     const double* t2, const double* oovv, const double* fov, b200cc_i64 ldf,
+                                     const double* eo, const double* ev, double* et_out, int accumulate,
+                                     double* scratch, void* stream) {
+  if (ntrip <= 0 || nv <= 0) return 0;
+  if (ntrip > 65535) { set_error("b200cc_t_energy_batch: ntrip > 65535"); return 1; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TArgs p;
+  p.no = no; p.nv = nv; p.nt = (nv + TT - 1) / TT;
+  p.ijk = ijk; p.Q = Q; p.t1 = t1; p.t2 = t2; p.oovv = oovv; p.fov = fov; p.eo = eo; p.ev = ev; p.ldf = ldf;
+  const int ncube = sorted_cubes(nv);
+  t_energy_kernel<<<dim3(ncube, ntrip), 512, 0, st>>>(p, scratch);
+  if (check_launch("t_energy_kernel")) return 1;
+  const i64 nparts = (i64)ncube * ntrip;
+  if (nparts > 2147483647LL) { set_error("b200cc_t_energy_batch: too many partials"); return 1; }
+  return launch_final_reduce(scratch, (int)nparts, 0, 1, et_out, accumulate, 1.0, st);
+}
+
+extern "C" int b200cc_t3_assemble(int no, int nv, int i, int j, int k, const double* Q, const double* t1,
+                                  const double* t2, const double* oovv, const double* fov, b200cc_i64 ldf,
+                                  const double* eo, const double* ev, int with_denom, double* w3_out,
+                                  double* v3_out, void* stream) {
+  if (nv <= 0) return 0;
+  TArgs p;
+  p.no = no; p.nv = nv; p.nt = (nv + TT - 1) / TT;
+  p.ijk = nullptr; p.Q = Q; p.t1 = t1; p.t2 = t2; p.oovv = oovv; p.fov = fov; p.eo = eo; p.ev = ev; p.ldf = ldf;
+  const i64 v3 = (i64)nv * nv * nv;
+  i64 blocks = (v3 + 255) / 256;
+  const int cap = sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  t3_assemble_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, i, j, k, with_denom,
+                                                                                    w3_out, v3_out);
+  return check_launch("t3_assemble_kernel");
+}

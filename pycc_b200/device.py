@@ -1,0 +1,75 @@
+"""Device / precision policy and the contraction backend -- the drop-in seam of the reference
+(pycc/device.py:38-173), re-targeted: ``ContractionBackend.__call__(subscripts, *operands)`` keeps
+its signature but runs on ``b200cc_dgemm`` / ``b200cc_permute`` instead of opt_einsum + cuBLAS, and
+there is no CPU device: this package is the ``device='GPU'`` implementation only.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .contract import Contractor
+from .exceptions import InvalidKeywordError, PyCCError
+
+
+class ContractionBackend(object):
+    """``contract(subscripts, *operands)`` on the B200 kernels (reference: device.py:64-86).
+
+    Operands that are not yet resident on the compute device (numpy arrays, CPU tensors -- the
+    reference keeps ERI/L on the host) are uploaded first, exactly as the reference does per call;
+    resident float64 CUDA tensors (views included) are used in place.
+    """
+
+    def __init__(self, device='GPU', device1=None):
+        if device != 'GPU':
+            raise PyCCError("pycc_b200 only implements device='GPU' (use pycc itself for the CPU path)")
+        self.device = device
+        self.device1 = device1 if device1 is not None else torch.device(
+            'cuda:0' if torch.cuda.is_available() else 'cpu')
+        self.engine = Contractor()
+
+    def _resident(self, x):
+        if not isinstance(x, torch.Tensor):
+            x = torch.from_numpy(np.ascontiguousarray(x))
+        if x.is_complex():
+            raise NotImplementedError("complex operands are outside the accelerated path")
+        if x.device != self.device1 or x.dtype != torch.float64:
+            x = x.to(self.device1, dtype=torch.float64)
+        return x
+
+    def __call__(self, subscripts, *operands, **kw):
+        return self.engine(subscripts, *[self._resident(x) for x in operands], **kw)
+
+
+class DeviceManager(object):
+    """Validates ``device`` / ``precision`` and owns the contraction backend (reference: device.py:89-173).
+
+    Differences, all deliberate: 'CPU' is rejected (there is no CPU path here), and both the "storage"
+    and the "compute" handle are the GPU -- integrals live in HBM as blocks, nothing is staged on the host.
+    """
+
+    VALID_DEVICE = ['CPU', 'GPU']
+    VALID_PRECISION = ['SP', 'DP']
+
+    def __init__(self, device='GPU', precision='DP'):
+        if precision.upper() not in self.VALID_PRECISION:
+            raise InvalidKeywordError('precision', precision, self.VALID_PRECISION)
+        self.precision = precision.upper()
+        if device.upper() not in self.VALID_DEVICE:
+            raise InvalidKeywordError('device', device, self.VALID_DEVICE)
+        self.device = device.upper()
+        if self.device != 'GPU':
+            raise PyCCError("pycc_b200 only implements device='GPU' (use pycc itself for the CPU path)")
+        if self.precision != 'DP':
+            raise NotImplementedError("precision='SP' (float32 / TF32-split) is not implemented yet; "
+                                      "the FP64 DMMA path is precision='DP'")
+        self.device1 = torch.device('cuda:0' if torch.cuda.is_available() else 'cpu')
+        self.device0 = self.device1
+        self.real_dtype = np.float64
+        self._torch_dtype = torch.float64
+        self.contract = ContractionBackend(device=self.device, device1=self.device1)
+
+    def seed_compute(self, a):
+        return torch.as_tensor(np.asarray(a), dtype=self._torch_dtype).to(self.device1)
+
+    seed_store = seed_compute

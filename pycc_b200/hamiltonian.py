@@ -1,0 +1,196 @@
+"""Device-resident MO integrals for the closed-shell CC path.
+
+The reference builds the full n^4 ``ERI`` and ``L = 2*ERI - ERI.swapaxes(2,3)`` on the host
+(pycc/hamiltonian.py:67-70) and re-uploads slices per contraction (pycc/device.py:70-74).
+Here only the SIX unique Dirac blocks of a real, 8-fold-symmetric integral tensor live in HBM,
+
+    oooo[m,n,i,j]  ooov[m,n,i,e]  oovv[m,n,e,f]  ovov[m,b,j,e]  ovvv[m,b,e,f]  vvvv[a,b,e,f]
+
+(107 GB x 2 on the host at o=40,v=300 becomes 75 GB on the device, `vvvv` optionally a-sharded),
+and ``H.ERI[o,v,v,o]`` / ``H.L[o,o,v,v]`` style slicing -- the data contract of the reference's
+``Hamiltonian`` (attributes F, eps, ERI, L) -- is served lazily from those blocks through the
+symmetry relations <pq|rs> = <qp|sr> = <rs|pq> = <rq|ps> = <ps|rq> (+ products).
+"""
+from __future__ import annotations
+
+import itertools
+
+import numpy as np
+import torch
+
+from . import kernels as K
+from ._lib import B200ccError
+from .contract import Contractor
+
+STORED = ("oooo", "ooov", "oovv", "ovov", "ovvv", "vvvv")
+
+# the 8 index permutations that leave a real <pq|rs> invariant, as position maps new[t] = old[g[t]]
+_SYM = set()
+_gens = [(2, 1, 0, 3), (0, 3, 2, 1), (1, 0, 3, 2)]
+_frontier = [(0, 1, 2, 3)]
+while _frontier:
+    g = _frontier.pop()
+    if g in _SYM:
+        continue
+    _SYM.add(g)
+    for h in _gens:
+        _frontier.append(tuple(g[h[t]] for t in range(4)))
+_SYM = sorted(_SYM)
+assert len(_SYM) == 8
+
+
+def block_source(pattern):
+    """('stored name', perm) such that ERI[pattern] == stored.permute(perm)."""
+    for g in _SYM:
+        # new[t] = old[g[t]]  =>  pattern[t] = name[g[t]]
+        for name in STORED:
+            if all(pattern[t] == name[g[t]] for t in range(4)):
+                return name, g
+    raise B200ccError("no stored block for ERI pattern %r" % pattern)
+
+
+class _BlockView:
+    """``H.ERI`` / ``H.L``: supports ``X[o,v,v,o]`` with the wavefunction's own o/v slices."""
+
+    def __init__(self, H, kind):
+        self.H, self.kind = H, kind
+        self._cache = {}
+
+    def _pattern(self, key):
+        if not (isinstance(key, tuple) and len(key) == 4):
+            raise B200ccError("block integrals are indexed as X[o,v,v,o] with the wavefunction's o/v slices")
+        pat = ""
+        for s in key:
+            if s == self.H.o:
+                pat += "o"
+            elif s == self.H.v:
+                pat += "v"
+            else:
+                raise B200ccError("only the active occupied/virtual slices are available on the device "
+                                  "(got %r)" % (s,))
+        return pat
+
+    def __getitem__(self, key):
+        pat = self._pattern(key)
+        if self.kind == "ERI":
+            name, g = block_source(pat)
+            return self.H.block(name).permute(*g)
+        if pat not in self._cache:
+            # L_pqrs = 2<pq|rs> - <pq|sr>
+            a = self.H.ERI[key]
+            swapped = (key[0], key[1], key[3], key[2])
+            b = self.H.ERI[swapped].permute(0, 1, 3, 2)
+            out = torch.empty(tuple(a.shape), dtype=a.dtype, device=a.device)
+            K.strided_axpby(out, a, 2.0, 0.0)
+            K.strided_axpby(out, b, -1.0, 1.0)
+            self._cache[pat] = out
+        return self._cache[pat]
+
+
+class BlockHamiltonian:
+    """F, eps and the six integral blocks on one device (float64)."""
+
+    def __init__(self, F, blocks, no, nfzc=0, device="cuda", a_range=None):
+        self.device = torch.device(device)
+        F = torch.as_tensor(np.asarray(F) if not isinstance(F, torch.Tensor) else F, dtype=torch.float64)
+        self.F = F.to(self.device).contiguous()
+        self.nmo = self.F.shape[0]
+        self.no, self.nfzc = int(no), int(nfzc)
+        self.nv = self.nmo - self.no - self.nfzc
+        self.o = slice(self.nfzc, self.nfzc + self.no)
+        self.v = slice(self.nfzc + self.no, self.nmo)
+        self.eps = torch.diagonal(self.F).clone()
+        self._blocks = {}
+        # vvvv may hold only rows a in [a_lo, a_hi) (multi-GPU ladder sharding)
+        self.a_range = (0, self.nv) if a_range is None else (int(a_range[0]), int(a_range[1]))
+        for name in STORED:
+            if name in blocks and blocks[name] is not None:
+                t = blocks[name]
+                if not isinstance(t, torch.Tensor):
+                    t = torch.from_numpy(np.ascontiguousarray(t, dtype=np.float64))
+                self._blocks[name] = t.to(self.device, dtype=torch.float64).contiguous()
+        self.ERI = _BlockView(self, "ERI")
+        self.L = _BlockView(self, "L")
+        self._derived = {}
+
+    def block(self, name):
+        try:
+            return self._blocks[name]
+        except KeyError:
+            raise B200ccError("integral block %r is not resident" % name)
+
+    def has(self, name):
+        return name in self._blocks
+
+    # ---- constructors ---------------------------------------------------------------------------
+    @classmethod
+    def from_full(cls, F, ERI, no, nfzc=0, device="cuda"):
+        """From a host n^4 Dirac array (small molecules / the reference's own Hamiltonian.ERI)."""
+        ERI = np.asarray(ERI)
+        n = ERI.shape[0]
+        sl = {"o": slice(nfzc, nfzc + no), "v": slice(nfzc + no, n)}
+        blocks = {k: np.ascontiguousarray(ERI[sl[k[0]], sl[k[1]], sl[k[2]], sl[k[3]]]) for k in STORED}
+        return cls(F, blocks, no, nfzc, device)
+
+    @classmethod
+    def from_factor(cls, syn, device="cuda", a_range=None, chunk_bytes=4 << 30):
+        """From a factorised synthetic problem (pycc_b200.synthetic): every block is contracted on the
+        device with the package's own GEMM, <pq|rs> = scale * sum_P B[P,p,r] B[P,q,s]; `vvvv` in row
+        chunks so no temporary larger than ``chunk_bytes`` exists."""
+        dev = torch.device(device)
+        B = torch.from_numpy(syn.B).to(dev)
+        no, nv = syn.no, syn.nv
+        ct = Contractor()
+        sl = {"o": slice(0, no), "v": slice(no, no + nv)}
+        blocks = {}
+        for name in STORED:
+            p, q, r, s = (sl[c] for c in name)
+            if name != "vvvv":
+                blocks[name] = ct("Ppr,Pqs->pqrs", B[:, p, r], B[:, q, s], alpha=syn.scale)
+                continue
+            a_lo, a_hi = (0, nv) if a_range is None else a_range
+            na = a_hi - a_lo
+            out = torch.empty((na, nv, nv, nv), dtype=torch.float64, device=dev)
+            Bqs = K.permuted(B[:, q, s], (1, 2, 0))                  # [(b,f), P]  K-major
+            rows = max(1, min(na, int(chunk_bytes // (8 * nv ** 3))))
+            for a0 in range(0, na, rows):
+                a1 = min(na, a0 + rows)
+                Bpr = K.permuted(B[:, no + a_lo + a0:no + a_lo + a1, r], (1, 2, 0))   # [(a,e), P]
+                tmp = ct("aeP,bfP->aebf", Bpr, Bqs, alpha=syn.scale)
+                K.strided_axpby(out[a0:a1], tmp.permute(0, 2, 1, 3), 1.0, 0.0)
+                del tmp, Bpr
+            blocks[name] = out
+        return cls(syn.F, blocks, no, 0, dev, a_range)
+
+    # ---- derived constant layouts (built once, cached) ---------------------------------------------
+    def derived(self, key):
+        """Constant rearrangements of the blocks used by the fused residual (see ccwfn.py):
+           Loovv       [m,n,e,f] = 2<mn|ef> - <mn|fe>
+           Looov       [m,n,i,e] = 2<mn|ie> - <nm|ie>
+           oovv_menf   [m,e,n,f] = <mn|ef>         Loovv_menf [m,e,n,f] = Loovv[m,n,e,f]
+           oovv_mfne   [m,e,n,f] = <mn|fe>         ovov_mejb  [m,e,j,b] = <mb|je>
+        """
+        if key in self._derived:
+            return self._derived[key]
+        oovv = self.block("oovv")
+        if key == "Loovv":
+            t = torch.empty_like(oovv)
+            K.strided_axpby(t, oovv, 2.0, 0.0)
+            K.strided_axpby(t, oovv.permute(0, 1, 3, 2), -1.0, 1.0)
+        elif key == "Looov":
+            ooov = self.block("ooov")
+            t = torch.empty_like(ooov)
+            K.strided_axpby(t, ooov, 2.0, 0.0)
+            K.strided_axpby(t, ooov.permute(1, 0, 2, 3), -1.0, 1.0)
+        elif key == "oovv_menf":
+            t = K.permuted(oovv, (0, 2, 1, 3))
+        elif key == "Loovv_menf":
+            t = K.permuted(self.derived("Loovv"), (0, 2, 1, 3))
+        elif key == "oovv_mfne":
+            t = K.permuted(oovv, (0, 3, 1, 2))
+        elif key == "ovov_mejb":
+            t = K.permuted(self.block("ovov"), (0, 3, 2, 1))
+        else:
+            raise B200ccError("unknown derived block %r" % key)
+        self._derived[key] = t
+        return t

@@ -1,0 +1,252 @@
+"""Tensor-level wrappers over the C ABI (include/b200cc.h).
+
+Everything here takes torch CUDA float64 tensors (or views of them), turns them into raw
+addresses + element strides, and launches the hand-written kernels on torch's current stream.
+No arithmetic is done in torch/numpy on this path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import GemmDesc, B200ccError, i64
+
+NSM = 148                   # B200
+F64 = torch.float64
+
+
+def _addr(x):
+    """tensor | (tensor, element_offset) | int address -> int address"""
+    if isinstance(x, int):
+        return x
+    if isinstance(x, tuple):
+        t, off = x
+        return _lib.ptr(t) + 8 * int(off)
+    return _lib.ptr(x)
+
+
+def _dev(x):
+    if isinstance(x, tuple):
+        x = x[0]
+    return x.device
+
+
+def auto_ksplit(M, N, K, batch):
+    """Split-K factor for small-output / long-K shapes (Fae, Fmi, r1 terms, Wmnij): aim at ~2 CTAs per SM."""
+    tiles = ((M + 127) // 128) * ((N + 127) // 128) * batch
+    kt = (K + 15) // 16
+    if tiles >= NSM or kt < 64:
+        return 1
+    return int(max(1, min((2 * NSM + tiles - 1) // tiles, kt // 16, 256)))
+
+
+def dgemm(M, N, K, A, lda, transA, B, ldb, transB, Cmat, ldc, alpha=1.0, beta=0.0,
+          batch=1, sA=0, sB=0, sC=0, seg2=None, table=None, table_align16=False, ksplit=None):
+    """C[b] = alpha * (opA[b] opB[b]^T [+ second K segment]) + beta * C[b]; see b200cc_dgemm.
+
+    A, B, Cmat: tensor, (tensor, element offset) or raw address.  seg2 = (A2, lda2, B2, ldb2, K2, sA2, sB2).
+    """
+    if M == 0 or N == 0 or batch == 0:
+        return
+    d = GemmDesc()
+    d.M, d.N, d.transA, d.transB = int(M), int(N), int(bool(transA)), int(bool(transB))
+    d.K1 = int(K)
+    d.A1, d.B1, d.C = _addr(A), _addr(B), _addr(Cmat)
+    d.lda1, d.ldb1, d.ldc = int(lda), int(ldb), int(ldc)
+    d.strideA1, d.strideB1, d.strideC = int(sA), int(sB), int(sC)
+    K2 = 0
+    if seg2 is not None:
+        A2, lda2, B2, ldb2, K2, sA2, sB2 = seg2
+        d.A2, d.B2, d.lda2, d.ldb2, d.K2 = _addr(A2), _addr(B2), int(lda2), int(ldb2), int(K2)
+        d.strideA2, d.strideB2 = int(sA2), int(sB2)
+    d.alpha, d.beta, d.batch = float(alpha), float(beta), int(batch)
+    d.table = _lib.ptr(table) if table is not None else None
+    d.table_align16 = int(bool(table_align16))
+    if ksplit is None:
+        ksplit = auto_ksplit(M, N, K + K2, batch)
+    d.ksplit = int(ksplit)
+    ws = None
+    if ksplit > 1:
+        dev = _dev(table if table is not None else Cmat)
+        ws = torch.empty(ksplit * batch * M * N, dtype=F64, device=dev)
+        d.workspace = _lib.ptr(ws)
+    # chunk batches beyond the grid.y limit
+    if batch > 65535:
+        if table is not None:
+            raise B200ccError("table-mode batch > 65535")
+        done = 0
+        while done < batch:
+            nb = min(65535, batch - done)
+            dgemm(M, N, K, _addr(A) + 8 * sA * done, lda, transA, _addr(B) + 8 * sB * done, ldb, transB,
+                  _addr(Cmat) + 8 * sC * done, ldc, alpha, beta, nb, sA, sB, sC,
+                  None if seg2 is None else (_addr(seg2[0]) + 8 * seg2[5] * done, seg2[1],
+                                             _addr(seg2[2]) + 8 * seg2[6] * done, seg2[3], seg2[4], seg2[5], seg2[6]),
+                  None, False, ksplit if ksplit == 1 else None)
+            done += nb
+        return
+    _lib.check(_lib.get().b200cc_dgemm(C.byref(d), _lib.stream()), "b200cc_dgemm")
+    del ws
+
+
+def strided_axpby(out, inp, alpha=1.0, beta=0.0):
+    """out = alpha * inp + beta * out for two equally-shaped views with arbitrary strides
+    (e.g. ``strided_axpby(buf, t2.permute(0, 1, 3, 2), -1.0, 1.0)``)."""
+    if tuple(out.shape) != tuple(inp.shape):
+        raise B200ccError("strided_axpby: shape mismatch %s vs %s" % (tuple(out.shape), tuple(inp.shape)))
+    r = out.dim()
+    if r > 6:
+        raise B200ccError("strided_axpby: rank > 6")
+    if out.numel() == 0:
+        return out
+    arr = i64 * max(r, 1)
+    shape = arr(*([int(s) for s in out.shape] or [1]))
+    si = arr(*([int(s) for s in inp.stride()] or [0]))
+    so = arr(*([int(s) for s in out.stride()] or [0]))
+    _lib.check(_lib.get().b200cc_permute(max(r, 1) if r else 1, shape, si, so, float(alpha), _lib.ptr(inp),
+                                         float(beta), _lib.ptr(out), _lib.stream()), "b200cc_permute")
+    return out
+
+
+def permuted(inp, perm, alpha=1.0):
+    """A new contiguous tensor holding alpha * inp.permute(perm)."""
+    v = inp.permute(*perm)
+    out = torch.empty(tuple(v.shape), dtype=inp.dtype, device=inp.device)
+    return strided_axpby(out, v, alpha, 0.0)
+
+
+def axpbyz(a, x, b, y, z):
+    """z = a*x + b*y on contiguous, equally sized tensors (z may alias x or y)."""
+    n = z.numel()
+    for t in (x, y, z):
+        if t is not None and (t.numel() != n or not t.is_contiguous()):
+            raise B200ccError("axpbyz: operands must be contiguous and equally sized")
+    _lib.check(_lib.get().b200cc_axpbyz(n, float(a), _lib.ptr(x if x is not None else z), float(b),
+                                        _lib.ptr(y if y is not None else z), _lib.ptr(z), _lib.stream()),
+               "b200cc_axpbyz")
+    return z
+
+
+def _c(t, name):
+    if not t.is_contiguous():
+        raise B200ccError("%s must be contiguous" % name)
+    return t
+
+
+def build_tau(t1, t2, f1=1.0, f2=1.0, out=None):
+    no, nv = t1.shape
+    out = torch.empty_like(t2, memory_format=torch.contiguous_format) if out is None else out
+    _lib.check(_lib.get().b200cc_build_tau(no, nv, float(f1), float(f2), _lib.ptr(_c(t1, "t1")),
+                                           _lib.ptr(_c(t2, "t2")), _lib.ptr(_c(out, "tau")), _lib.stream()),
+               "b200cc_build_tau")
+    return out
+
+
+def div_d2(x, eo, ev, out=None):
+    no, nv = x.shape[0], x.shape[2]
+    out = torch.empty_like(x) if out is None else out
+    _lib.check(_lib.get().b200cc_div_d2(no, nv, _lib.ptr(eo), _lib.ptr(ev), _lib.ptr(_c(x, "x")),
+                                        _lib.ptr(_c(out, "out")), _lib.stream()), "b200cc_div_d2")
+    return out
+
+
+def div_d1(x, eo, ev, out=None):
+    no, nv = x.shape
+    out = torch.empty_like(x) if out is None else out
+    _lib.check(_lib.get().b200cc_div_d1(no, nv, _lib.ptr(eo), _lib.ptr(ev), _lib.ptr(_c(x, "x")),
+                                        _lib.ptr(_c(out, "out")), _lib.stream()), "b200cc_div_d1")
+    return out
+
+
+def _scratch(dev, n=16 * 1024):
+    return torch.empty(n, dtype=F64, device=dev)
+
+
+def update_amps(r1, r2, eo, ev, t1, t2, symmetrize=True, write_r2=True):
+    """Fused r2 symmetrisation + Jacobi update + sum((r/D)^2).  Returns a 1-element device tensor."""
+    no, nv = t1.shape
+    out = torch.empty(1, dtype=F64, device=t2.device)
+    sc = _scratch(t2.device, 4096)
+    _lib.check(_lib.get().b200cc_update_amps(no, nv, _lib.ptr(eo), _lib.ptr(ev), _lib.ptr(_c(r1, "r1")),
+                                             _lib.ptr(_c(r2, "r2")), int(symmetrize), int(write_r2),
+                                             _lib.ptr(_c(t1, "t1")), _lib.ptr(_c(t2, "t2")), _lib.ptr(out),
+                                             _lib.ptr(sc), _lib.stream()), "b200cc_update_amps")
+    return out
+
+
+def symmetrize_r2(r2):
+    no, nv = r2.shape[0], r2.shape[2]
+    _lib.check(_lib.get().b200cc_symmetrize_r2(no, nv, _lib.ptr(_c(r2, "r2")), _lib.stream()),
+               "b200cc_symmetrize_r2")
+    return r2
+
+
+def cc_energy(fov, t1, t2, Loovv):
+    """2 f.t1 + (t2 + t1 t1).L as a 1-element device tensor.  ``fov`` may be a strided (no,nv) view."""
+    no, nv = t1.shape
+    if fov.stride(1) != 1 and nv > 1:
+        raise B200ccError("cc_energy: fov must be unit-stride along the virtual index")
+    out = torch.empty(1, dtype=F64, device=t2.device)
+    sc = _scratch(t2.device, 4096)
+    _lib.check(_lib.get().b200cc_cc_energy(no, nv, _lib.ptr(fov), int(fov.stride(0)), _lib.ptr(_c(t1, "t1")),
+                                           _lib.ptr(_c(t2, "t2")), _lib.ptr(_c(Loovv, "Loovv")), _lib.ptr(out),
+                                           _lib.ptr(sc), _lib.stream()), "b200cc_cc_energy")
+    return out
+
+
+def multi_dot(x, ys):
+    """[x . y for y in ys] as a len(ys) device tensor; one pass over x (len(ys) <= 16)."""
+    m = len(ys)
+    n = x.numel()
+    for y in ys:
+        if y.numel() != n or not y.is_contiguous():
+            raise B200ccError("multi_dot: operands must be contiguous and equally sized")
+    out = torch.empty(m, dtype=F64, device=x.device)
+    sc = _scratch(x.device, 16 * 1024)
+    arr = (_lib.dptr * m)(*[_lib.ptr(y) for y in ys])
+    _lib.check(_lib.get().b200cc_multi_dot(n, _lib.ptr(_c(x, "x")), m, arr, _lib.ptr(out), _lib.ptr(sc),
+                                           _lib.stream()), "b200cc_multi_dot")
+    return out
+
+
+def multi_axpy(coeffs, xs, out):
+    """out = sum_q coeffs[q] * xs[q]  (len <= 16, out aliases no xs[q])."""
+    m = len(xs)
+    n = out.numel()
+    for x in xs:
+        if x.numel() != n or not x.is_contiguous():
+            raise B200ccError("multi_axpy: operands must be contiguous and equally sized")
+        if x.data_ptr() == out.data_ptr():
+            raise B200ccError("multi_axpy: out aliases an input")
+    arr = (_lib.dptr * m)(*[_lib.ptr(x) for x in xs])
+    cs = (C.c_double * m)(*[float(c) for c in coeffs])
+    _lib.check(_lib.get().b200cc_multi_axpy(n, m, cs, arr, _lib.ptr(_c(out, "out")), _lib.stream()),
+               "b200cc_multi_axpy")
+    return out
+
+
+def t_energy_batch(no, nv, ijk, Q, t1, t2, oovv, fov, eo, ev, et, accumulate=True):
+    ntrip = ijk.shape[0]
+    n = int(_lib.get().b200cc_t_energy_scratch(nv, ntrip))
+    sc = _scratch(Q.device, max(n, 1))
+    _lib.check(_lib.get().b200cc_t_energy_batch(no, nv, ntrip, _lib.ptr(ijk), _lib.ptr(Q), _lib.ptr(_c(t1, "t1")),
+                                                _lib.ptr(_c(t2, "t2")), _lib.ptr(_c(oovv, "oovv")), _lib.ptr(fov),
+                                                int(fov.stride(0)), _lib.ptr(eo), _lib.ptr(ev), _lib.ptr(et),
+                                                int(accumulate), _lib.ptr(sc), _lib.stream()),
+               "b200cc_t_energy_batch")
+    return et
+
+
+def t3_assemble(no, nv, i, j, k, Q, t1, t2, oovv, fov, eo, ev, with_denom):
+    w3 = torch.empty((nv, nv, nv), dtype=F64, device=Q.device)
+    d3 = torch.empty((nv, nv, nv), dtype=F64, device=Q.device)
+    _lib.check(_lib.get().b200cc_t3_assemble(no, nv, int(i), int(j), int(k), _lib.ptr(Q), _lib.ptr(_c(t1, "t1")),
+                                             _lib.ptr(_c(t2, "t2")), _lib.ptr(_c(oovv, "oovv")), _lib.ptr(fov),
+                                             int(fov.stride(0)), _lib.ptr(eo), _lib.ptr(ev), int(bool(with_denom)),
+                                             _lib.ptr(w3), _lib.ptr(d3), _lib.stream()), "b200cc_t3_assemble")
+    return w3, d3
+
+
+def launch_count():
+    return int(_lib.get().b200cc_launch_count())

@@ -1,0 +1,130 @@
+"""DIIS extrapolation on the device + the solver's text output (reference: pycc/utils.py:200-361).
+
+``helper_diis`` keeps the reference's interface and Pulay algebra (utils.py:272-361) but not its cost:
+each stored state is ONE flat device buffer (t1 then t2), the error-overlap matrix B is cached and
+only its new row is computed -- one fused multi-dot pass over the newest error vector
+(``b200cc_multi_dot``) instead of m(m+1)/2 separate dots -- and the extrapolant is one fused
+multi-axpy pass (``b200cc_multi_axpy``).  The (m+1)x(m+1) Pulay system is solved on the host.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import kernels as K
+
+
+class helper_diis(object):
+    def __init__(self, t1, t2, max_diis, precision='DP'):
+        self.max_diis = max_diis
+        self.precision = precision
+        self.shapes = (tuple(t1.shape), tuple(t2.shape))
+        self.n1, self.n2 = t1.numel(), t2.numel()
+        self.diis_size = 0
+        self.last_coefficients = None
+        if max_diis == 0:
+            return
+        self.old = self._flat(t1, t2)
+        self.vals = [self._clone(self.old)]
+        self.errors = []
+        self._ids = []              # identity of each error vector (for the B cache)
+        self._next_id = 0
+        self._dots = {}
+
+    # -- flat storage -----------------------------------------------------------------------------
+    def _flat(self, t1, t2):
+        buf = torch.empty(self.n1 + self.n2, dtype=t2.dtype, device=t2.device)
+        K.strided_axpby(buf[:self.n1].view(self.shapes[0]), t1, 1.0, 0.0)
+        K.strided_axpby(buf[self.n1:].view(self.shapes[1]), t2, 1.0, 0.0)
+        return buf
+
+    @staticmethod
+    def _clone(buf):
+        out = torch.empty_like(buf)
+        return K.axpbyz(1.0, buf, 0.0, None, out)
+
+    def _split(self, buf):
+        return buf[:self.n1].view(self.shapes[0]), buf[self.n1:].view(self.shapes[1])
+
+    # -- reference interface -----------------------------------------------------------------------
+    def add_error_vector(self, t1, t2):
+        """Store the new iterate and e = t - t_prev  (utils.py:284-295)."""
+        if self.max_diis == 0:
+            return
+        val = self._flat(t1, t2)
+        err = torch.empty_like(val)
+        K.axpbyz(1.0, val, -1.0, self.old, err)
+        self.vals.append(val)
+        self.errors.append(err)
+        self._ids.append(self._next_id)
+        self._next_id += 1
+        self.old = self._clone(val)
+        # new row of B in one pass over the newest error vector
+        dots = K.multi_dot(err, self.errors[-16:]).tolist()
+        new = self._ids[-1]
+        for eid, d in zip(self._ids[-16:], dots):
+            self._dots[(eid, new)] = self._dots[(new, eid)] = d
+
+    def extrapolate(self, t1, t2):
+        """Pulay extrapolation (utils.py:297-361); returns (t1, t2) unchanged when max_diis == 0."""
+        if self.max_diis == 0:
+            return t1, t2
+        if len(self.errors) > self.max_diis:
+            dead = self._ids.pop(0)
+            del self.vals[0]
+            del self.errors[0]
+            self._dots = {k: v for k, v in self._dots.items() if dead not in k}
+        m = self.diis_size = len(self.errors)
+        B = -np.ones((m + 1, m + 1))
+        B[-1, -1] = 0.0
+        for p in range(m):
+            for q in range(m):
+                B[p, q] = self._dots[(self._ids[p], self._ids[q])]
+        B[:-1, :-1] /= np.abs(B[:-1, :-1]).max()
+        rhs = np.zeros(m + 1)
+        rhs[-1] = -1.0
+        c = np.linalg.solve(B, rhs)
+        self.last_coefficients = c[:m].copy()
+        new = torch.empty_like(self.old)
+        K.multi_axpy(c[:m], self.vals[1:m + 1], new)
+        self.old = self._clone(new)
+        return self._split(new)
+
+
+# ---- solver text output: same lines as the reference prints (utils.py:200-254) -------------------------
+def title(text):
+    return "\n" + text
+
+
+def iteration(niter, energy=None, de=None, rms=None, e_label="Ecorr", note=None):
+    cols = []
+    if energy is not None:
+        cols.append("%s = %.15f" % (e_label, energy))
+    if de is not None:
+        cols.append("dE = % .5E" % de)
+    if rms is not None:
+        cols.append("rms = % .5E" % rms)
+    if note is not None:
+        cols.append(note)
+    return "Iter %3d: %s" % (niter, "  ".join(cols))
+
+
+def converged(name, elapsed):
+    return "%s converged in %.3f seconds." % (name, elapsed)
+
+
+def timing(label, seconds):
+    return "%s built in %.3f seconds." % (label, seconds)
+
+
+def field(label, value, width=22):
+    return "  %-*s : %s" % (width, label, value)
+
+
+def solve_params(method, e_conv, r_conv, maxiter, max_diis, start_diis):
+    rows = ["\n%s solve" % method,
+            field("energy convergence", "%.2E" % e_conv),
+            field("residual convergence", "%.2E" % r_conv),
+            field("max iterations", "%d" % maxiter),
+            field("DIIS max / start", "%d / %d" % (max_diis, start_diis))]
+    return "\n".join(rows)

@@ -1,0 +1,79 @@
+"""What the CC solver needs from an SCF reference (reference: pycc/wavefunction.py:111-188, 293-332).
+
+pycc takes a psi4 ``Wavefunction`` and builds the full MO Hamiltonian through psi4's MintsHelper.
+psi4 is an optional dependency here: anything that can provide (F, <pq|rs> or its six blocks, no,
+nfzc, E_ref) works, through :class:`IntegralReference`:
+
+* ``IntegralReference.from_arrays(F, ERI, no, nfzc, eref)`` -- host arrays (e.g. dumped from psi4);
+* ``IntegralReference.from_synthetic(syn)``                 -- factorised synthetic integrals, contracted
+                                                              into blocks on the device;
+* ``IntegralReference.from_psi4(scf_wfn)``                  -- same calls as pycc/hamiltonian.py:58-68.
+A raw psi4 wavefunction or a ``Synthetic`` passed to ``CCwfn`` is converted automatically.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .hamiltonian import BlockHamiltonian
+from .synthetic import Synthetic
+
+
+class IntegralReference:
+    def __init__(self, eref=0.0):
+        self.eref = float(eref)
+        self._make = None
+
+    def energy(self):
+        return self.eref
+
+    def hamiltonian(self, device, comm=None):
+        return self._make(device, comm)
+
+    @classmethod
+    def from_arrays(cls, F, ERI, no, nfzc=0, eref=0.0):
+        r = cls(eref)
+        r._make = lambda device, comm: BlockHamiltonian.from_full(F, ERI, no, nfzc, device)
+        return r
+
+    @classmethod
+    def from_blocks(cls, F, blocks, no, nfzc=0, eref=0.0):
+        r = cls(eref)
+        r._make = lambda device, comm: BlockHamiltonian(F, blocks, no, nfzc, device)
+        return r
+
+    @classmethod
+    def from_synthetic(cls, syn):
+        r = cls(syn.eref)
+
+        def make(device, comm):
+            a_range = None if comm is None else comm.a_range(syn.nv)
+            return BlockHamiltonian.from_factor(syn, device, a_range=a_range)
+        r._make = make
+        return r
+
+    @classmethod
+    def from_psi4(cls, scf_wfn):
+        import psi4                                   # optional; same calls as hamiltonian.py:58-68
+        C = scf_wfn.Ca_subset("AO", "ALL")
+        npC = np.asarray(C)
+        F = npC.T @ np.asarray(scf_wfn.Fa_subset("AO")) @ npC
+        mints = psi4.core.MintsHelper(scf_wfn.basisset())
+        ERI = np.asarray(mints.mo_eri(C, C, C, C)).swapaxes(1, 2)
+        nfzc = int(sum(scf_wfn.frzcpi()))
+        no = int(sum(scf_wfn.doccpi())) - nfzc
+        return cls.from_arrays(F, ERI, no, nfzc, scf_wfn.energy())
+
+
+def resolve_reference(x):
+    if isinstance(x, IntegralReference):
+        return x
+    if isinstance(x, Synthetic):
+        return IntegralReference.from_synthetic(x)
+    if isinstance(x, BlockHamiltonian):
+        r = IntegralReference(0.0)
+        r._make = lambda device, comm: x
+        return r
+    if hasattr(x, "frzcpi") and hasattr(x, "Ca_subset"):
+        return IntegralReference.from_psi4(x)
+    raise TypeError("CCwfn needs a psi4 Wavefunction, an IntegralReference, a Synthetic or a BlockHamiltonian "
+                    "(got %s)" % type(x).__name__)

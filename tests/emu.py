@@ -1,0 +1,272 @@
+"""TEST DOUBLE of the libb200cc C ABI (numpy, CPU) -- tests only, never imported by pycc_b200.
+
+There is no GPU in the build container, so the host-side logic of the package (contraction
+planning, pointer/stride arithmetic, the residual orchestration, DIIS bookkeeping, triple
+batching, rank sharding) is exercised here against an object that exposes the SAME entry points as
+``include/b200cc.h`` with the SAME raw-address calling convention, implemented with numpy on host
+memory.  ``install()`` swaps it in for the ctypes library and lifts the "CUDA tensors only" check;
+the product path itself has no such fallback (``pycc_b200._lib`` raises without the .so / a GPU).
+"""
+import ctypes as C
+
+import numpy as np
+from numpy.lib.stride_tricks import as_strided
+
+from pycc_b200 import _lib
+
+
+def _arr(addr, shape, strides):
+    """float64 view of raw memory: element strides, non-negative."""
+    if isinstance(addr, C.c_void_p):
+        addr = addr.value
+    shape = tuple(int(s) for s in shape)
+    strides = tuple(int(s) for s in strides)
+    n = 1 + sum((s - 1) * st for s, st in zip(shape, strides))
+    if any(s == 0 for s in shape):
+        return np.zeros(shape)
+    buf = (C.c_double * n).from_address(int(addr))
+    base = np.frombuffer(buf, dtype=np.float64)
+    return as_strided(base, shape, tuple(8 * st for st in strides))
+
+
+def _vec(addr, n):
+    return _arr(addr, (n,), (1,))
+
+
+def _ints(addr, n, ctype=C.c_int):
+    buf = (ctype * n).from_address(int(addr))
+    return np.frombuffer(buf, dtype=np.int32 if ctype is C.c_int else np.int64)
+
+
+class EmuLib:
+    def __init__(self):
+        self.launches = 0
+        self.err = b""
+        self.calls = {}
+
+    def _count(self, name, n=1):
+        self.launches += n
+        self.calls[name] = self.calls.get(name, 0) + 1
+
+    def b200cc_version(self):
+        return 100
+
+    def b200cc_last_error(self):
+        return self.err
+
+    def b200cc_launch_count(self):
+        return self.launches
+
+    # ---- GEMM -----------------------------------------------------------------------------------
+    def b200cc_dgemm(self, dref, stream):
+        d = dref._obj
+        self._count("dgemm")
+        M, N = d.M, d.N
+        if M == 0 or N == 0 or d.batch == 0:
+            return 0
+        tab = None
+        if d.table:
+            tab = _ints(d.table, 5 * d.batch, C.c_longlong).reshape(d.batch, 5)
+
+        def mat(addr, rows, K, ld, trans):
+            if K == 0:
+                return np.zeros((rows, 0))
+            return _arr(addr, (rows, K), (1, ld) if trans else (ld, 1))
+
+        for b in range(d.batch):
+            if tab is not None:
+                a1, b1, a2, b2, c = (int(x) for x in tab[b])
+            else:
+                a1 = d.A1 + 8 * b * d.strideA1
+                b1 = d.B1 + 8 * b * d.strideB1
+                a2 = (d.A2 or 0) + 8 * b * d.strideA2
+                b2 = (d.B2 or 0) + 8 * b * d.strideB2
+                c = d.C + 8 * b * d.strideC
+            acc = mat(a1, M, d.K1, d.lda1, d.transA) @ mat(b1, N, d.K1, d.ldb1, d.transB).T
+            if d.K2 > 0:
+                acc = acc + mat(a2, M, d.K2, d.lda2, d.transA) @ mat(b2, N, d.K2, d.ldb2, d.transB).T
+            Cm = _arr(c, (M, N), (d.ldc, 1))
+            if d.beta != 0.0:
+                Cm[...] = d.alpha * acc + d.beta * Cm
+            else:
+                Cm[...] = d.alpha * acc
+        return 0
+
+    # ---- permute / axpby ---------------------------------------------------------------------------
+    def b200cc_permute(self, rank, shape, si, so, alpha, inp, beta, out, stream):
+        self._count("permute")
+        shp = [int(shape[d]) for d in range(rank)]
+        a = _arr(inp, shp, [int(si[d]) for d in range(rank)])
+        o = _arr(out, shp, [int(so[d]) for d in range(rank)])
+        if beta != 0.0:
+            o[...] = alpha * a + beta * o
+        else:
+            o[...] = alpha * a
+        return 0
+
+    def b200cc_axpbyz(self, n, a, x, b, y, z, stream):
+        self._count("axpbyz")
+        r = 0.0
+        if a != 0.0:
+            r = r + a * _vec(x, n)
+        if b != 0.0:
+            r = r + b * _vec(y, n)
+        _vec(z, n)[...] = r
+        return 0
+
+    # ---- elementwise --------------------------------------------------------------------------------
+    def b200cc_build_tau(self, no, nv, f1, f2, t1, t2, tau, stream):
+        self._count("tau")
+        T1 = _arr(t1, (no, nv), (nv, 1))
+        T2 = _vec(t2, no * no * nv * nv).reshape(no, no, nv, nv)
+        _vec(tau, no * no * nv * nv).reshape(no, no, nv, nv)[...] = f1 * T2 + f2 * np.einsum("ia,jb->ijab", T1, T1)
+        return 0
+
+    @staticmethod
+    def _d2(no, nv, eo, ev):
+        eo, ev = _vec(eo, no), _vec(ev, nv)
+        return eo[:, None, None, None] + eo[None, :, None, None] - ev[None, None, :, None] - ev
+
+    def b200cc_div_d2(self, no, nv, eo, ev, inp, out, stream):
+        self._count("div_d2")
+        n = no * no * nv * nv
+        _vec(out, n)[...] = (_vec(inp, n).reshape(no, no, nv, nv) / self._d2(no, nv, eo, ev)).ravel()
+        return 0
+
+    def b200cc_div_d1(self, no, nv, eo, ev, inp, out, stream):
+        self._count("div_d1")
+        D = _vec(eo, no)[:, None] - _vec(ev, nv)[None, :]
+        _vec(out, no * nv)[...] = (_vec(inp, no * nv).reshape(no, nv) / D).ravel()
+        return 0
+
+    def b200cc_update_amps(self, no, nv, eo, ev, r1, r2, symmetrize, write_r2, t1, t2, sumsq, scratch, stream):
+        self._count("update_amps", 2)
+        n2 = no * no * nv * nv
+        R2 = _vec(r2, n2).reshape(no, no, nv, nv)
+        full = R2 + R2.transpose(1, 0, 3, 2) if symmetrize else R2.copy()
+        if symmetrize and write_r2:
+            R2[...] = full
+        d2 = full / self._d2(no, nv, eo, ev)
+        _vec(t2, n2)[...] += d2.ravel()
+        s = float(np.sum(d2 * d2))
+        if r1:
+            D = _vec(eo, no)[:, None] - _vec(ev, nv)[None, :]
+            d1 = _vec(r1, no * nv).reshape(no, nv) / D
+            _vec(t1, no * nv)[...] += d1.ravel()
+            s += float(np.sum(d1 * d1))
+        _vec(sumsq, 1)[0] = s
+        return 0
+
+    def b200cc_symmetrize_r2(self, no, nv, r2, stream):
+        self._count("symmetrize")
+        R2 = _vec(r2, no * no * nv * nv).reshape(no, no, nv, nv)
+        R2[...] = R2 + R2.transpose(1, 0, 3, 2)
+        return 0
+
+    def b200cc_cc_energy(self, no, nv, fov, ldf, t1, t2, L, e_out, scratch, stream):
+        self._count("cc_energy", 2)
+        f = _arr(fov, (no, nv), (ldf, 1))
+        T1 = _arr(t1, (no, nv), (nv, 1))
+        n2 = no * no * nv * nv
+        tau = _vec(t2, n2).reshape(no, no, nv, nv) + np.einsum("ia,jb->ijab", T1, T1)
+        _vec(e_out, 1)[0] = 2.0 * np.sum(f * T1) + np.sum(tau * _vec(L, n2).reshape(no, no, nv, nv))
+        return 0
+
+    def b200cc_multi_dot(self, n, x, m, ys, out, scratch, stream):
+        self._count("multi_dot", 2)
+        X = _vec(x, n)
+        o = _vec(out, m)
+        for q in range(m):
+            o[q] = float(np.dot(X, _vec(ys[q], n)))
+        return 0
+
+    def b200cc_multi_axpy(self, n, m, c, xs, out, stream):
+        self._count("multi_axpy")
+        r = np.zeros(n)
+        for q in range(m):
+            r += c[q] * _vec(xs[q], n)
+        _vec(out, n)[...] = r
+        return 0
+
+    # ---- (T) ------------------------------------------------------------------------------------------
+    def b200cc_t_energy_scratch(self, nv, ntrip):
+        nt = (nv + 7) // 8
+        return nt * (nt + 1) * (nt + 2) // 6 * ntrip
+
+    @staticmethod
+    def _W(Q, nv):
+        Q = Q.reshape(6, nv, nv, nv)
+        return (Q[0] + Q[1].transpose(0, 2, 1) + Q[2].transpose(1, 2, 0) + Q[3].transpose(2, 1, 0)
+                + Q[4].transpose(2, 0, 1) + Q[5].transpose(1, 0, 2))
+
+    @staticmethod
+    def _disc(no, nv, i, j, k, t1, t2, oovv, fov, ldf):
+        T1 = _arr(t1, (no, nv), (nv, 1))
+        n2 = no * no * nv * nv
+        T2 = _vec(t2, n2).reshape(no, no, nv, nv)
+        Kv = _vec(oovv, n2).reshape(no, no, nv, nv)
+        f = _arr(fov, (no, nv), (ldf, 1))
+        e = np.einsum
+        return (e("ab,c->abc", Kv[i, j], T1[k]) + e("ac,b->abc", Kv[i, k], T1[j]) + e("bc,a->abc", Kv[j, k], T1[i])
+                + e("ab,c->abc", T2[i, j], f[k]) + e("ac,b->abc", T2[i, k], f[j]) + e("bc,a->abc", T2[j, k], f[i]))
+
+    @staticmethod
+    def _den(no, nv, i, j, k, eo, ev):
+        eo, ev = _vec(eo, no), _vec(ev, nv)
+        return eo[i] + eo[j] + eo[k] - ev[:, None, None] - ev[None, :, None] - ev[None, None, :]
+
+    def b200cc_t_energy_batch(self, no, nv, ntrip, ijk, Q, t1, t2, oovv, fov, ldf, eo, ev, et, accumulate,
+                              scratch, stream):
+        self._count("t_energy", 2)
+        trip = _ints(ijk, 3 * ntrip).reshape(ntrip, 3)
+        v3 = nv ** 3
+        a = np.arange(nv)
+        eq = ((a[:, None, None] == a[None, :, None]).astype(float) + (a[:, None, None] == a[None, None, :])
+              + (a[None, :, None] == a[None, None, :]))
+        mask = (a[:, None, None] >= a[None, :, None]) & (a[None, :, None] >= a[None, None, :])
+        tot = 0.0
+        for n in range(ntrip):
+            i, j, k = (int(x) for x in trip[n])
+            W = self._W(_vec(Q + 8 * n * 6 * v3, 6 * v3), nv)
+            V = (W + self._disc(no, nv, i, j, k, t1, t2, oovv, fov, ldf)) / (1.0 + eq)
+            p = lambda X, *ax: X.transpose(*ax)
+            X3 = (W * V + p(W, 0, 2, 1) * p(V, 0, 2, 1) + p(W, 1, 0, 2) * p(V, 1, 0, 2) + p(W, 1, 2, 0) * p(V, 1, 2, 0)
+                  + p(W, 2, 0, 1) * p(V, 2, 0, 1) + p(W, 2, 1, 0) * p(V, 2, 1, 0))
+            Y = V + p(V, 1, 2, 0) + p(V, 2, 0, 1)
+            Z = p(V, 0, 2, 1) + p(V, 1, 0, 2) + p(V, 2, 1, 0)
+            Wc = W + p(W, 1, 2, 0) + p(W, 2, 0, 1)
+            Wo = p(W, 0, 2, 1) + p(W, 1, 0, 2) + p(W, 2, 1, 0)
+            occ = 2.0 - (float(i == j) + float(i == k) + float(j == k))
+            e = ((Y - 2 * Z) * Wc + (Z - 2 * Y) * Wo + 3 * X3) * occ / self._den(no, nv, i, j, k, eo, ev)
+            tot += float(np.sum(e[mask]))
+        o = _vec(et, 1)
+        o[0] = o[0] + tot if accumulate else tot
+        return 0
+
+    def b200cc_t3_assemble(self, no, nv, i, j, k, Q, t1, t2, oovv, fov, ldf, eo, ev, with_denom, w3, d3, stream):
+        self._count("t3_assemble")
+        v3 = nv ** 3
+        W = self._W(_vec(Q, 6 * v3), nv)
+        Dd = self._disc(no, nv, i, j, k, t1, t2, oovv, fov, ldf)
+        if with_denom:
+            den = self._den(no, nv, i, j, k, eo, ev)
+            W, Dd = W / den, Dd / den
+        _vec(w3, v3)[...] = W.ravel()
+        if d3:
+            _vec(d3, v3)[...] = Dd.ravel()
+        return 0
+
+
+class install:
+    """Context manager / fixture helper: route pycc_b200 through the numpy double on CPU tensors."""
+
+    def __enter__(self):
+        self.saved = (_lib._LIB, _lib.REQUIRE_CUDA)
+        self.lib = EmuLib()
+        _lib._LIB = self.lib
+        _lib.REQUIRE_CUDA = False
+        return self.lib
+
+    def __exit__(self, *exc):
+        _lib._LIB, _lib.REQUIRE_CUDA = self.saved
+        return False

@@ -1,0 +1,213 @@
+"""pycc_b200 (fused residual, solve_cc, DIIS, (T), the reference-API building blocks) against the
+reference's golden vectors (tests/golden/ref_*.npz, outputs of the reference's own code).
+
+Every test runs twice: `emu` -- host-side logic through the numpy double of the C ABI (tests/emu.py;
+`-m "not gpu"`, the build container has no GPU) -- and `cuda` -- the real kernels through
+libb200cc.so on a B200 (`-m gpu`, the parity tests proper).  FP64 tolerances: 1e-10 Eh on energies,
+1e-9 max-abs on amplitudes (north_star); most checks are far tighter."""
+import numpy as np
+import pytest
+import torch
+
+import pycc_b200
+from pycc_b200 import cctriples
+from pycc_b200.synthetic import full_eri
+from pycc_b200.wavefunction import IntegralReference
+from tests import emu
+
+
+DEV = [torch.device("cpu")]
+
+
+def T(x):
+    return torch.from_numpy(np.array(x, dtype=np.float64, order="C", copy=True)).to(DEV[0])
+
+
+@pytest.fixture(params=[pytest.param("emu"), pytest.param("cuda", marks=pytest.mark.gpu)])
+def dev(request):
+    """'emu': host logic on CPU tensors through the numpy double of the C ABI (no GPU in the build
+    container).  'cuda': the real libb200cc.so kernels on a B200 -- the parity tests proper."""
+    if request.param == "emu":
+        DEV[0] = torch.device("cpu")
+        with emu.install():
+            yield DEV[0]
+    else:
+        assert torch.cuda.is_available(), "-m gpu tests need a CUDA device"
+        DEV[0] = torch.device("cuda:0")
+        yield DEV[0]
+        DEV[0] = torch.device("cpu")
+
+
+def make_wfn(syn, model="CCSD", from_factor=True):
+    ref = IntegralReference.from_synthetic(syn) if from_factor else \
+        IntegralReference.from_arrays(syn.F, full_eri(syn), syn.no)
+    return pycc_b200.ccwfn(ref, model=model, device='GPU', quiet=True)
+
+
+def test_block_views_match_full_eri(golden, dev):
+    g, syn = golden
+    cc = make_wfn(syn)
+    ERI = full_eri(syn)
+    L = 2.0 * ERI - ERI.swapaxes(2, 3)
+    o, v = cc.o, cc.v
+    for pat in ("oooo", "ooov", "oovo", "ovoo", "vooo", "oovv", "vvoo", "ovov", "vovo", "ovvo", "voov",
+                "ovvv", "vovv", "vvov", "vvvo", "vvvv"):
+        key = tuple(o if c == "o" else v for c in pat)
+        assert np.abs(cc.H.ERI[key].cpu().numpy() - ERI[key]).max() < 1e-13, pat
+    for pat in ("oovv", "ovvv", "ooov", "ovvo", "oovo"):
+        key = tuple(o if c == "o" else v for c in pat)
+        assert np.abs(cc.H.L[key].cpu().numpy() - L[key]).max() < 1e-13, pat
+
+
+@pytest.mark.parametrize("from_factor", [True, False])
+def test_residuals_and_intermediates(golden, dev, from_factor):
+    g, syn = golden
+    cc = make_wfn(syn, from_factor=from_factor)
+    o, v, H = cc.o, cc.v, cc.H
+    t1, t2 = T(g["rand_t1"]), T(g["rand_t2"])
+    F = H.F
+    tol = 1e-12
+    assert np.abs(cc.build_Fae(o, v, F, H.L, t1, t2).cpu().numpy() - g["rand_Fae"]).max() < tol
+    assert np.abs(cc.build_Fmi(o, v, F, H.L, t1, t2).cpu().numpy() - g["rand_Fmi"]).max() < tol
+    assert np.abs(cc.build_Fme(o, v, F, H.L, t1).cpu().numpy() - g["rand_Fme"]).max() < tol
+    assert np.abs(cc.build_Wmnij(o, v, H.ERI, t1, t2).cpu().numpy() - g["rand_Wmnij"]).max() < tol
+    assert np.abs(cc.build_Wmbej(o, v, H.ERI, H.L, t1, t2).cpu().numpy() - g["rand_Wmbej"]).max() < tol
+    assert np.abs(cc.build_Wmbje(o, v, H.ERI, t1, t2).cpu().numpy() - g["rand_Wmbje"]).max() < tol
+    assert np.abs(cc.build_Zmbij(o, v, H.ERI, t1, t2).cpu().numpy() - g["rand_Zmbij"]).max() < tol
+    for (f1, f2) in ((1.0, 1.0), (1.0, 0.5), (0.5, 1.0)):
+        assert np.abs(cc.build_tau(t1, t2, f1, f2).cpu().numpy() - g["rand_tau_%g_%g" % (f1, f2)]).max() < tol
+    r1, r2 = cc.residuals(F, t1, t2)
+    assert np.abs(r1.cpu().numpy() - g["rand_r1"]).max() < tol
+    assert np.abs(r2.cpu().numpy() - g["rand_r2"]).max() < tol
+    assert np.abs(cc.r_T1(o, v, F, H.ERI, H.L, t1, t2).cpu().numpy() - g["rand_r1"]).max() < tol
+    assert np.abs(cc.r_T2(o, v, F, H.ERI, t1, t2).cpu().numpy() - g["rand_r2"]).max() < tol
+    assert abs(float(cc.cc_energy(o, v, F, H.L, t1, t2)) - float(g["rand_ecc"])) < tol
+    # the lazily built denominators
+    eo, ev = syn.eps[:syn.no], syn.eps[syn.no:]
+    assert np.abs(cc.Dia.cpu().numpy() - (eo[:, None] - ev)).max() < 1e-14
+    D2 = eo[:, None, None, None] + eo[None, :, None, None] - ev[None, None, :, None] - ev
+    assert np.abs(cc.Dijab.cpu().numpy() - D2).max() < 1e-14
+
+
+def test_solve_cc_trace(golden, dev):
+    g, syn = golden
+    cc = make_wfn(syn, "CCSD(T)")
+    ecc = cc.solve_cc(1e-12, 1e-12, 100)
+    ref = g["trace_ecc_rms"]
+    tr = np.array(cc.trace)
+    assert len(tr) == len(ref)
+    assert np.abs(tr[:, 0] - ref[:, 0]).max() < 1e-11
+    assert np.all(np.abs(tr[:, 1] - ref[:, 1]) <= 1e-5 * np.abs(ref[:, 1]) + 1e-14)
+    assert abs(float(ecc) - float(g["e_total_ccsd_t"])) < 1e-11
+    assert np.abs(cc.t1.cpu().numpy() - g["conv_t1"]).max() < 1e-10
+    assert np.abs(cc.t2.cpu().numpy() - g["conv_t2"]).max() < 1e-10
+    assert float(cc.ecc) == float(ecc)
+
+
+def test_diis_matches_reference(golden, dev):
+    g, syn = golden
+    d1, d2 = g["diis_in_t1"], g["diis_in_t2"]
+    diis = pycc_b200.helper_diis(T(d1[0]), T(d2[0]), 4)
+    x1, x2 = d1[0], d2[0]
+    for n in range(1, 7):
+        x1 = x1 + d1[n]
+        x2 = x2 + d2[n]
+        diis.add_error_vector(T(x1), T(x2))
+        y1, y2 = diis.extrapolate(T(x1), T(x2))
+        x1, x2 = y1.cpu().numpy().copy(), y2.cpu().numpy().copy()
+        assert np.abs(x1 - g["diis_out_t1"][n - 1]).max() < 1e-10
+        assert np.abs(x2 - g["diis_out_t2"][n - 1]).max() < 1e-10
+    off = pycc_b200.helper_diis(T(d1[0]), T(d2[0]), 0)
+    a, b = off.extrapolate(T(d1[1]), T(d2[1]))
+    assert np.array_equal(a.cpu().numpy(), d1[1]) and np.array_equal(b.cpu().numpy(), d2[1])
+
+
+def test_triples(golden, dev):
+    g, syn = golden
+    cc = make_wfn(syn, "CCSD(T)")
+    cc.t1, cc.t2 = T(g["conv_t1"]), T(g["conv_t2"])
+    o, v, H = cc.o, cc.v, cc.H
+    et = cctriples.t_tjl(cc)
+    assert abs(float(et) - float(g["e_t_tjl"])) < 1e-12
+    eng = cctriples.TriplesEngine(cc)
+    for n, (i, j, k) in enumerate(g["triples"]):
+        i, j, k = int(i), int(j), int(k)
+        w3, d3 = eng.t3_parts(i, j, k, False)
+        assert np.abs(w3.cpu().numpy() - g["W3"][n]).max() < 1e-12
+        assert np.abs((w3 + d3).cpu().numpy() - g["V3"][n]).max() < 1e-12
+        # reference-signature functions with the reference's own slicing of H.ERI
+        t3c = cctriples.t3c_ijk(o, v, i, j, k, cc.t2, H.ERI[v, v, v, o], H.ERI[o, v, o, o], H.F, cc.contract, True)
+        t3d = cctriples.t3d_ijk(o, v, i, j, k, cc.t1, cc.t2, H.ERI[o, o, v, v], H.F, cc.contract, True)
+        assert np.abs(t3c.cpu().numpy() - g["t3c_denom"][n]).max() < 1e-12
+        assert np.abs(t3d.cpu().numpy() - g["t3d_denom"][n]).max() < 1e-12
+    # small batches exercise the chunking of the triple list
+    eng2 = cctriples.TriplesEngine(cc, q_bytes=1)
+    assert eng2.nb_max == 1
+    tl = [t for t in cctriples.triples_list(cc.no) if not (t[0] == t[1] == t[2])]
+    assert abs(float(eng2.energy(tl)[0]) - float(g["e_t_tjl"])) < 1e-12
+
+
+def test_vikings_cross_formulations(dev):
+    # the reference's own cross-check (tests/test_005_ccsd_t_energy.py:30-36), on the smallest golden case
+    from tests.conftest import load_golden, GOLDEN
+    g, syn = load_golden([p for p in GOLDEN if "o3v7" in p][0])
+    cc = make_wfn(syn, "CCSD(T)")
+    cc.t1, cc.t2 = T(g["conv_t1"]), T(g["conv_t2"])
+    assert abs(float(cctriples.t_vikings(cc)) - float(g["e_t_vikings"])) < 1e-12
+    assert abs(float(cctriples.t_vikings_inverted(cc)) - float(g["e_t_vikings_inverted"])) < 1e-12
+
+
+def test_ccd_is_ccsd_without_singles(dev):
+    from tests.conftest import load_golden, GOLDEN
+    from oracle import ccsd_oracle as co
+    g, syn = load_golden(GOLDEN[0])
+    cc = make_wfn(syn, "CCD")
+    e = cc.solve_cc(1e-11, 1e-11)
+    assert float(torch.abs(cc.t1).max()) == 0.0
+    # oracle CCD: CCSD equations with t1 pinned to zero (reference ccwfn.py: the CCD branches drop every t1 term)
+    P = co.Problem(co.blocks_from_full(full_eri(syn), syn.no), syn.F, syn.no)
+    t1, t2 = P.guess()
+    ecc = P.cc_energy(syn.F, t1, t2)
+    diis = co.Diis(t1, t2, 8)
+    for it in range(100):
+        last = ecc
+        r1, r2 = P.residuals(syn.F, t1, t2)
+        t2 = t2 + r2 / P.Dijab
+        rms = np.sqrt(np.sum((r2 / P.Dijab) ** 2))
+        ecc = P.cc_energy(syn.F, t1, t2)
+        if abs(ecc - last) < 1e-11 and rms < 1e-11:
+            break
+        diis.add_error_vector(t1, t2)
+        t1, t2 = diis.extrapolate(t1, t2)
+        t1 = np.zeros_like(t1)
+    assert abs(float(e) - ecc) < 1e-10
+
+
+def test_keyword_errors():
+    from pycc_b200.exceptions import InvalidKeywordError, PyCCError
+    from pycc_b200.synthetic import make_synthetic
+    syn = make_synthetic(2, 3)
+    with pytest.raises(InvalidKeywordError):
+        pycc_b200.ccwfn(syn, model="CCSDT")
+    with pytest.raises(ValueError):
+        pycc_b200.ccwfn(syn, model="nope")
+    with pytest.raises(PyCCError):
+        pycc_b200.ccwfn(syn, model="CCSD", bogus=1)
+    with pytest.raises(TypeError):
+        pycc_b200.ccwfn(syn, frozen_core=True)
+    with pytest.raises(InvalidKeywordError):
+        pycc_b200.ccwfn(syn, precision="HP")
+    with pytest.raises(PyCCError):
+        pycc_b200.ccwfn(syn, device="CPU")
+    with pytest.raises(TypeError):
+        pycc_b200.ccwfn(object())
+
+
+def test_no_cpu_fallback():
+    """Without the test double the package must refuse CPU tensors loudly."""
+    from pycc_b200 import kernels as K
+    from pycc_b200._lib import B200ccError
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(B200ccError):
+        K.axpbyz(1.0, torch.zeros(4, dtype=torch.float64), 0.0, None, torch.zeros(4, dtype=torch.float64))
