@@ -211,3 +211,36 @@ def test_no_cpu_fallback():
         pytest.skip("GPU present")
     with pytest.raises(B200ccError):
         K.axpbyz(1.0, torch.zeros(4, dtype=torch.float64), 0.0, None, torch.zeros(4, dtype=torch.float64))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("no,nv,seed,noise", [(8, 40, 0, 0.0), (7, 33, 1, 0.01), (10, 64, 2, 0.0)])
+def test_medium_size_vs_oracle(no, nv, seed, noise):
+    """CUDA path vs the numpy oracle on the same seeded synthetic inputs, at sizes the oracle does in
+    seconds: E(CCSD), E(T) within 1e-10 Eh, amplitudes within 1e-9 (north_star tolerances)."""
+    from oracle import ccsd_oracle as co, triples_oracle as to
+    from pycc_b200.synthetic import make_synthetic, blocks_from_factor
+    assert torch.cuda.is_available()
+    DEV[0] = torch.device("cuda:0")
+    try:
+        syn = make_synthetic(no, nv, seed=seed, fock_noise=noise)
+        b = blocks_from_factor(syn)
+        P = co.Problem(b, syn.F, no)
+        e_ref, t1_ref, t2_ref, trace = co.solve_cc(P, 1e-11, 1e-11, 100)
+        et_ref = to.t_tjl(t1_ref, t2_ref, syn.F, b["ovvv"], b["ooov"], b["oovv"])
+        cc = make_wfn(syn, "CCSD(T)")
+        e = cc.solve_cc(1e-11, 1e-11, 100)
+        assert len(cc.trace) == len(trace)
+        e_ccsd = cc.trace[-1][0]
+        assert abs(e_ccsd - e_ref) < 1e-10
+        assert abs(float(e) - (e_ref + et_ref)) < 1e-10
+        assert np.abs(cc.t1.cpu().numpy() - t1_ref).max() < 1e-9
+        assert np.abs(cc.t2.cpu().numpy() - t2_ref).max() < 1e-9
+        # first-iteration residuals (pre-DIIS), amplitude-independent check of every term
+        r1_ref, r2_ref = P.residuals(syn.F, *P.guess())
+        cc2 = make_wfn(syn, "CCSD")
+        r1, r2 = cc2.residuals(cc2.H.F, cc2.t1, cc2.t2)
+        assert np.abs(r1.cpu().numpy() - r1_ref).max() < 1e-11
+        assert np.abs(r2.cpu().numpy() - r2_ref).max() < 1e-11
+    finally:
+        DEV[0] = torch.device("cpu")
