@@ -33,6 +33,7 @@ from .exceptions import InvalidKeywordError, PyCCError
 from .hamiltonian import BlockHamiltonian
 from .utils import helper_diis, title, iteration, converged, timing, solve_params
 from .wavefunction import resolve_reference
+from .parallel import Serial
 
 F64 = torch.float64
 
@@ -72,6 +73,7 @@ class CCwfn(object):
             raise TypeError("the 'frozen_core' argument was removed; the frozen core comes from the reference "
                             "wavefunction")
         self.comm = kwargs.pop('comm', None)          # parallel.Comm for multi-GPU runs (None = single GPU)
+        self.part = self.comm if self.comm is not None else Serial()
         if kwargs:
             raise PyCCError("Unexpected keyword argument(s): %s" % sorted(kwargs))
 
@@ -142,13 +144,7 @@ class CCwfn(object):
         self.trace = []
         for niter in range(1, maxiter + 1):
             ecc_last = ecc
-            r1, half = self._residuals_half(F, self.t1, self.t2)
-            # r2 = half + half^T, t += r/D, sum (r/D)^2 : one fused pass (ccwfn.py:790, 281-284)
-            ssq = K.update_amps(r1, half, self.eps_o, self.eps_v, self.t1, self.t2, symmetrize=True,
-                                write_r2=False)
-            e_dev = self.cc_energy(o, v, F, self.H.L, self.t1, self.t2)
-            ssq_h, ecc = (float(x) for x in torch.stack((ssq[0], e_dev)).tolist())   # one D2H sync per iteration
-            rms = ssq_h ** 0.5
+            ecc, rms = self.iterate(F)
             ediff = ecc - ecc_last
             self.trace.append((ecc, rms))
             say(iteration(niter, energy=ecc, de=ediff, rms=rms, e_label="CC Ecorr"))
@@ -167,11 +163,27 @@ class CCwfn(object):
                 self.ecc = ecc_t
                 say("E(TOT)  = %20.15f" % (float(ecc_t) + self.eref))
                 return ecc_t
-            diis.add_error_vector(self.t1, self.t2)
-            if niter >= start_diis:
-                self.t1, self.t2 = diis.extrapolate(self.t1, self.t2)
+            self.diis_step(diis, niter >= start_diis)
         # not converged: the reference falls off the loop and returns None (ccwfn.py:268-319)
         return None
+
+    def iterate(self, F=None):
+        """One Jacobi step of solve_cc (ccwfn.py:272-286): residuals, then ONE fused pass doing
+        r2 = half + half^T (790), t += r/D and sum (r/D)^2 (281-284), then the energy (286).
+        Returns (ecc, rms) as host floats -- the single device->host sync of the iteration."""
+        F = self.H.F if F is None else F
+        r1, half = self._residuals_half(F, self.t1, self.t2)
+        ssq = K.update_amps(r1, half, self.eps_o, self.eps_v, self.t1, self.t2, symmetrize=True,
+                            write_r2=False)
+        e_dev = self.cc_energy(self.o, self.v, F, self.H.L, self.t1, self.t2)
+        ssq_h, ecc = torch.stack((ssq[0], e_dev)).tolist()
+        return ecc, ssq_h ** 0.5
+
+    def diis_step(self, diis, extrapolate=True):
+        """ccwfn.py:317-319"""
+        diis.add_error_vector(self.t1, self.t2)
+        if extrapolate:
+            self.t1, self.t2 = diis.extrapolate(self.t1, self.t2)
 
     # =============================================================================================
     # residuals (ccwfn.py:321-372)
@@ -191,13 +203,16 @@ class CCwfn(object):
         return F if F.is_contiguous() else F.contiguous()
 
     def _residuals_half(self, F, t1, t2):
-        """r1 and the UNsymmetrised half of r2 (ccwfn.py:922-940), fused formulation."""
+        """r1 and the UNsymmetrised half of r2 (ccwfn.py:922-940), fused formulation.  With several ranks
+        each computes its share of r2 (see parallel.py) and ONE all-reduce sums them."""
         F = self._check_F(F)
         t1 = t1.contiguous()
         t2 = t2.contiguous()
         I = self._intermediates(F, t1, t2)
         r1 = self._r1(F, t1, t2, I)
         half = self._r2_half(F, t1, t2, I)
+        if self.part.size > 1:
+            self.part.all_reduce_sum(half)
         if self.model == 'CCD':
             r1.zero_()
         return r1, half
@@ -213,12 +228,15 @@ class CCwfn(object):
         A["s_iame"] = s
         return A
 
-    def _intermediates(self, F, t1, t2):
+    def _intermediates(self, F, t1, t2, full=False):
+        """Fae, Fmi, Fme (replicated) and the LOCAL slices of Wmnij (rows i_g), W1/W2 (columns j_g) and
+        Z' (rows i_g).  ``full=True`` ignores the rank partition (public build_* methods)."""
         H, ct = self.H, self._ct
         o, v, no, nv = self.o, self.v, self.no, self.nv
-        dev = self.device1
+        i0, i1 = (0, no) if full else self.part.occ_range(no)
+        ni = i1 - i0
         A = self._amps(t1, t2)
-        I = {"amps": A}
+        I = {"amps": A, "occ": (i0, i1)}
         ccd = self.model == 'CCD'
         Fov = F[o, v]
         Loovv = H.derived("Loovv")
@@ -246,49 +264,54 @@ class CCwfn(object):
             ct("ne,mnie->mi", t1, H.derived("Looov"), out=Fmi, alpha=1.0, beta=1.0)
         I["Fmi"] = Fmi
         del tauh
+        if ni == 0:
+            return I
 
-        # ---------------- Wmnij[m,n,i,j]                                 (ccwfn.py:596-603)
+        # ---------------- Wmnij[m,n,i_g,j]                               (ccwfn.py:596-603)
         ooov = H.block("ooov")
-        Wmnij = K.permuted(H.block("oooo"), (0, 1, 2, 3))
-        ct("ijef,mnef->mnij", A["tau"], H.block("oovv"), out=Wmnij, alpha=1.0, beta=1.0)
+        Wfull = K.permuted(H.block("oooo"), (0, 1, 2, 3))
         if not ccd:
-            ct("je,mnie->mnij", t1, ooov, out=Wmnij, alpha=1.0, beta=1.0)
-            ct("ie,nmje->mnij", t1, ooov, out=Wmnij, alpha=1.0, beta=1.0)     # <mn|ej> = <nm|je>
+            ct("je,mnie->mnij", t1, ooov, out=Wfull, alpha=1.0, beta=1.0)
+            ct("ie,nmje->mnij", t1, ooov, out=Wfull, alpha=1.0, beta=1.0)     # <mn|ej> = <nm|je>
+        Wmnij = K.permuted(Wfull[:, :, i0:i1, :], (0, 1, 2, 3))
+        del Wfull
+        ct("ijef,mnef->mnij", A["tau"][i0:i1], H.block("oovv"), out=Wmnij, alpha=1.0, beta=1.0)
         I["Wmnij"] = Wmnij
 
-        # ---------------- ring intermediates in [m,e,j,b] layout
+        # ---------------- ring intermediates in [m,e,j_g,b] layout
         #   W1[m,e,j,b] = Wmbej[m,b,e,j]    (ccwfn.py:641-645)
         #   W2[m,e,j,b] = Wmbje[m,b,j,e]    (ccwfn.py:680-683)
         taut = K.build_tau(t1, t2, 0.5, 0.0 if ccd else 1.0)
-        taut_jbnf = K.permuted(taut, (0, 3, 1, 2))                # [j,b,n,f] = tau(1/2,1)[j,n,f,b]
+        taut_jbnf = K.permuted(taut[i0:i1], (0, 3, 1, 2))         # [j,b,n,f] = tau(1/2,1)[j,n,f,b]
         del taut
-        t2_jbnf = K.permuted(t2, (1, 3, 0, 2))                    # [j,b,n,f] = t2[n,j,f,b]
+        t2_jbnf = K.permuted(t2[:, i0:i1], (1, 3, 0, 2))          # [j,b,n,f] = t2[n,j,f,b]
         oovv_menf = H.derived("oovv_menf")
-        W1 = K.permuted(oovv_menf, (0, 1, 2, 3))                  # <mb|ej> = <mj|eb> -> [m,e,j,b]
+        W1 = K.permuted(oovv_menf[:, :, i0:i1, :], (0, 1, 2, 3))  # <mb|ej> = <mj|eb> -> [m,e,j,b]
         ct("menf,jbnf->mejb", oovv_menf, taut_jbnf, out=W1, alpha=-1.0, beta=1.0)
         ct("menf,jbnf->mejb", H.derived("Loovv_menf"), t2_jbnf, out=W1, alpha=0.5, beta=1.0)
         del t2_jbnf
-        W2 = K.permuted(H.derived("ovov_mejb"), (0, 1, 2, 3), -1.0)
+        W2 = K.permuted(H.derived("ovov_mejb")[:, :, i0:i1, :], (0, 1, 2, 3), -1.0)
         ct("menf,jbnf->mejb", H.derived("oovv_mfne"), taut_jbnf, out=W2, alpha=1.0, beta=1.0)
         del taut_jbnf
         if not ccd:
             ovvv = H.block("ovvv")
+            t1g = t1[i0:i1]
             # + t_jf <mb|ef>: natural GEMM output is [m,b,e,j]; fold into [m,e,j,b]
-            tmp = ct("mbef,jf->mbej", ovvv, t1)
+            tmp = ct("mbef,jf->mbej", ovvv, t1g)
             K.strided_axpby(W1, tmp.permute(0, 2, 3, 1), 1.0, 1.0)
             # - t_jf <mb|fe>: batch (m,b): C[j,e] = t1[j,:] . ovvv[m,b][f,e]   -> [m,b,j,e]
-            K.dgemm(no, nv, nv, t1, nv, 0, ovvv, nv, 1, tmp, nv, 1.0, 0.0,
-                    batch=no * nv, sA=0, sB=nv * nv, sC=no * nv)
-            K.strided_axpby(W2, tmp.view(no, nv, no, nv).permute(0, 3, 2, 1), -1.0, 1.0)
+            K.dgemm(ni, nv, nv, t1g, nv, 0, ovvv, nv, 1, tmp, nv, 1.0, 0.0,
+                    batch=no * nv, sA=0, sB=nv * nv, sC=ni * nv)
+            K.strided_axpby(W2, tmp.view(no, nv, ni, nv).permute(0, 3, 2, 1), -1.0, 1.0)
             del tmp
             # - t_nb <mn|ej> = - t_nb ooov[n,m,j,e]  and  + t_nb <mn|je>
-            ct("nb,nmje->mejb", t1, ooov, out=W1, alpha=-1.0, beta=1.0)
-            ct("nb,mnje->mejb", t1, ooov, out=W2, alpha=1.0, beta=1.0)
+            ct("nb,nmje->mejb", t1, ooov[:, :, i0:i1, :], out=W1, alpha=-1.0, beta=1.0)
+            ct("nb,mnje->mejb", t1, ooov[:, :, i0:i1, :], out=W2, alpha=1.0, beta=1.0)
         I["W1"], I["W2"] = W1, W2
 
-        # ---------------- Z'[i,j,m,b] = Zmbij[m,b,i,j] = <mb|ef> tau_ijef   (ccwfn.py:715)
+        # ---------------- Z'[i_g,j,m,b] = Zmbij[m,b,i,j] = <mb|ef> tau_ijef   (ccwfn.py:715)
         if not ccd:
-            I["Zijmb"] = ct("ijef,mbef->ijmb", A["tau"], H.block("ovvv"))
+            I["Zijmb"] = ct("ijef,mbef->ijmb", A["tau"][i0:i1], H.block("ovvv"))
         return I
 
     def _fae_ovvv(self, t1, Fae):
@@ -306,7 +329,7 @@ class CCwfn(object):
         ones = torch.ones(no, dtype=F64, device=self.device1)
         self._ct("m,mae->ae", ones, tmp, out=Fae, alpha=1.0, beta=1.0)
 
-    # ---- r1 (ccwfn.py:754-760) ----------------------------------------------------------------------
+    # ---- r1 (ccwfn.py:754-760), replicated on every rank ------------------------------------------------
     def _r1(self, F, t1, t2, I):
         H, ct = self.H, self._ct
         o, v, no, nv = self.o, self.v, self.no, self.nv
@@ -337,67 +360,82 @@ class CCwfn(object):
         ct("mnae,mnie->ia", t2, H.derived("Looov"), out=r1, alpha=-1.0, beta=1.0)
         return r1
 
-    # ---- r2, unsymmetrised half (ccwfn.py:922-940) -----------------------------------------------------
+    # ---- r2, unsymmetrised half (ccwfn.py:922-940): this rank's share -------------------------------------
     def _r2_half(self, F, t1, t2, I):
         H, ct = self.H, self._ct
         o, v, no, nv = self.o, self.v, self.no, self.nv
         A = I["amps"]
         ccd = self.model == 'CCD'
+        i0, i1 = I["occ"]
+        ni = i1 - i0
         oovv = H.block("oovv")
-        r2 = K.permuted(oovv, (0, 1, 2, 3), 0.5)                                  # 1/2 <ab|ij>       922
+        whole = ni == no
+        r2 = torch.empty_like(t2) if whole else torch.zeros_like(t2)
+        # 1/2 tau_ijef <ab|ef>  -- the particle-particle ladder, local a rows, all (i,j)      931
+        if ni > 0:
+            K.strided_axpby(r2[i0:i1], oovv[i0:i1], 0.5, 0.0)                      # 1/2 <ab|ij>       922
+        self._ladder(A["tau"], r2)
+        if ni == 0:
+            return r2
+        rg = r2[i0:i1]                                                             # rows i_g (contiguous)
+        t2g, t1g = t2[i0:i1], t1[i0:i1]
         # t2_ijae (F_be - 1/2 t_mb F_me)                                           923-925
         Fx = I["Fae"]
         if not ccd:
             Fx = K.permuted(Fx, (0, 1))
             ct("mb,me->be", t1, I["Fme"], out=Fx, alpha=-0.5, beta=1.0)
-        ct("ijae,be->ijab", t2, Fx, out=r2, alpha=1.0, beta=1.0)
+        ct("ijae,be->ijab", t2g, Fx, out=rg, alpha=1.0, beta=1.0)
         # - t2_imab (F_mj + 1/2 t_je F_me)                                         926-928
         Fy = I["Fmi"]
         if not ccd:
             Fy = K.permuted(Fy, (0, 1))
             ct("je,me->mj", t1, I["Fme"], out=Fy, alpha=0.5, beta=1.0)
-        K.dgemm(no, nv * nv, no, Fy, no, 1, t2, nv * nv, 1, r2, nv * nv, -1.0, 1.0,
-                batch=no, sA=0, sB=no * nv * nv, sC=no * nv * nv)
+        K.dgemm(no, nv * nv, no, Fy, no, 1, t2g, nv * nv, 1, rg, nv * nv, -1.0, 1.0,
+                batch=ni, sA=0, sB=no * nv * nv, sC=no * nv * nv)
         # 1/2 tau_mnab W_mnij                                                       930
-        ct("mnij,mnab->ijab", I["Wmnij"], A["tau"], out=r2, alpha=0.5, beta=1.0)
-        # 1/2 tau_ijef <ab|ef>  -- the particle-particle ladder                     931
-        self._ladder(A["tau"], r2)
-        # ring terms in [i,a,j,b] layout                                            933-935
+        ct("mnij,mnab->ijab", I["Wmnij"], A["tau"], out=rg, alpha=0.5, beta=1.0)
+        # ring terms, columns j_g, in [i,a,j,b] layout                              933-935
         R = ct("iame,mejb->iajb", A["s_iame"], I["W1"])          # (2t2 - t2^T) W_mbej
         ct("iame,mejb->iajb", A["t2_iame"], I["W2"], out=R, alpha=1.0, beta=1.0)   # t2 W_mbje^T
-        K.strided_axpby(r2, R.permute(0, 2, 1, 3), 1.0, 1.0)
+        K.strided_axpby(r2[:, i0:i1], R.permute(0, 2, 1, 3), 1.0, 1.0)
         t2_jame = K.permuted(t2, (1, 2, 0, 3))                   # [j,a,m,e] = t2[m,j,a,e]
         ct("jame,meib->jaib", t2_jame, I["W2"], out=R, alpha=1.0, beta=0.0)        # t2_mjae W_mbie
-        K.strided_axpby(r2, R.permute(2, 0, 1, 3), 1.0, 1.0)
+        K.strided_axpby(rg, R.permute(2, 0, 1, 3), 1.0, 1.0)
         del R, t2_jame
         if not ccd:
             ooov, ovov = H.block("ooov"), H.block("ovov")
             # - t_ma ( Z_mbij + <mb|ij> + t_ie <mb|ej> )  as one batched product    932, 940, 936-937
             Zs = I["Zijmb"]
-            K.strided_axpby(Zs, ooov, 1.0, 1.0)                                    # <mb|ij> = ooov[i,j,m,b]
+            K.strided_axpby(Zs, ooov[i0:i1], 1.0, 1.0)                             # <mb|ij> = ooov[i,j,m,b]
             # Y1[i,j,m,b] = sum_e t_ie <jm|be>: batch (j,m)
-            K.dgemm(no, nv, nv, t1, nv, 0, oovv, nv, 0, Zs, no * no * nv, 1.0, 1.0,
+            K.dgemm(ni, nv, nv, t1g, nv, 0, oovv, nv, 0, Zs, no * no * nv, 1.0, 1.0,
                     batch=no * no, sA=0, sB=nv * nv, sC=nv)
-            K.dgemm(nv, nv, no, t1, nv, 1, Zs, nv, 1, r2, nv, -1.0, 1.0,
-                    batch=no * no, sA=0, sB=no * nv, sC=nv * nv)
+            K.dgemm(nv, nv, no, t1, nv, 1, Zs, nv, 1, rg, nv, -1.0, 1.0,
+                    batch=ni * no, sA=0, sB=no * nv, sC=nv * nv)
             # - t_ie t_mb <ma|je>                                                    938
-            Y2 = torch.empty((no, no, no, nv), dtype=F64, device=self.device1)       # [i,j,m,a]
-            K.dgemm(no, no * nv, nv, t1, nv, 0, ovov, no * nv, 0, Y2, no * no * nv, 1.0, 0.0,
+            Y2 = torch.empty((ni, no, no, nv), dtype=F64, device=self.device1)       # [i,j,m,a]
+            K.dgemm(ni, no * nv, nv, t1g, nv, 0, ovov, no * nv, 0, Y2, no * no * nv, 1.0, 0.0,
                     batch=no, sA=0, sB=nv, sC=no * nv)
-            K.dgemm(nv, nv, no, Y2, nv, 1, t1, nv, 1, r2, nv, -1.0, 1.0,
-                    batch=no * no, sA=no * nv, sB=0, sC=nv * nv)
+            K.dgemm(nv, nv, no, Y2, nv, 1, t1, nv, 1, rg, nv, -1.0, 1.0,
+                    batch=ni * no, sA=no * nv, sB=0, sC=nv * nv)
             # t_ie <ab|ej>,  <ab|ej> = <ja|be>                                        939
-            ct("ie,jabe->ijab", t1, H.block("ovvv"), out=r2, alpha=1.0, beta=1.0)
+            ct("ie,jabe->ijab", t1g, H.block("ovvv"), out=rg, alpha=1.0, beta=1.0)
         return r2
 
     def _ladder(self, tau, r2):
         """r2[i,j,a,b] += 1/2 sum_ef tau[i,j,e,f] <ab|ef>  (ccwfn.py:931): M=o^2, N=K=v^2, <ab|ef> streamed
-        once, in place.  With an a-sharded <ab|ef> only the local rows are touched (see parallel.py)."""
+        once, in place.  With an a-sharded <ab|ef> only the local rows a_g are touched."""
         no, nv = self.no, self.nv
         vvvv = self.H.block("vvvv")
-        a_lo, a_hi = self.H.a_range
+        r_lo, r_hi = self.H.a_range                 # rows resident on this device
+        a_lo, a_hi = self.part.a_range(nv)          # rows this rank is responsible for
+        if a_lo < r_lo or a_hi > r_hi:
+            raise B200ccError("<ab|ef> rows [%d,%d) needed but only [%d,%d) are resident" % (a_lo, a_hi, r_lo, r_hi))
         na = a_hi - a_lo
-        K.dgemm(no * no, na * nv, nv * nv, tau, nv * nv, 0, vvvv, nv * nv, 0, (r2, a_lo * nv), nv * nv, 0.5, 1.0)
+        if na == 0:
+            return
+        K.dgemm(no * no, na * nv, nv * nv, tau, nv * nv, 0, (vvvv, (a_lo - r_lo) * nv ** 3), nv * nv, 0,
+                (r2, a_lo * nv), nv * nv, 0.5, 1.0)
 
     # =============================================================================================
     # the reference's public building blocks, reference layouts (used by tests and downstream code)
@@ -411,7 +449,7 @@ class CCwfn(object):
                                       "use the wavefunction's own H.ERI / H.L")
 
     def _I(self, F, t1, t2):
-        return self._intermediates(self._check_F(F), t1.contiguous(), t2.contiguous())
+        return self._intermediates(self._check_F(F), t1.contiguous(), t2.contiguous(), full=True)
 
     def build_Fae(self, o, v, F, L, t1, t2):
         self._own(L=L)
@@ -466,6 +504,8 @@ class CCwfn(object):
         F = self._check_F(F)
         t1, t2 = t1.contiguous(), t2.contiguous()
         half = self._r2_half(F, t1, t2, self._intermediates(F, t1, t2))
+        if self.part.size > 1:
+            self.part.all_reduce_sum(half)
         return K.symmetrize_r2(half)
 
     def cc_energy(self, o, v, F, L, t1, t2):

@@ -1,0 +1,75 @@
+"""One process per GPU: how the CCSD residual and (T) are split across ranks.
+
+The reference has no distributed code at all.  Here ``torch.distributed`` (NCCL over NVLink/NVSwitch on
+B200; gloo in the CPU tests) is plumbing only -- ONE all-reduce of the half-residual r2 (o^2 v^2
+doubles) per CCSD iteration and ONE scalar all-reduce for E(T):
+
+* <ab|ef> is held a-sharded: rank g owns rows a in ``a_range(nv)`` and computes the ladder
+  contribution to r2[:, :, a_g, :] from the (replicated) tau;
+* every other o^3v^3 / o^4v^2 / o^2v^3 term of r2 is split over an occupied index -- rank g computes
+  r2[i_g] rows (F/W_mnij/Z/t1-driven terms) and r2[:, j_g] columns (ring terms, whose W_mbej/W_mbje
+  intermediates are built only for the local j_g, so they are never gathered);
+* t1, t2, DIIS and the fused update are replicated: after the all-reduce every rank holds the same r2
+  and performs the same (deterministic) update, so the amplitudes stay bitwise identical on all ranks
+  and no all-gather of t2 is needed;
+* (T): the (i>=j>=k) triples are dealt round-robin (equal cost), energies summed with a scalar all-reduce.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def split(n, size, rank):
+    """Balanced contiguous partition of range(n): (lo, hi) of part ``rank``."""
+    base, rem = divmod(n, size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class Comm:
+    """Rank / size and the two collectives the path needs."""
+
+    def __init__(self, group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised (launch with torchrun / init_process_group)")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.size = dist.get_world_size(group)
+
+    def a_range(self, nv):
+        return split(nv, self.size, self.rank)
+
+    def occ_range(self, no):
+        return split(no, self.size, self.rank)
+
+    def all_reduce_sum(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def all_reduce_max_scalar(self, x):
+        t = torch.tensor([float(x)], dtype=torch.float64)
+        if dist.get_backend(self.group) == "nccl":
+            t = t.cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return float(t[0])
+
+    def barrier(self):
+        dist.barrier(group=self.group)
+
+
+class Serial:
+    """The single-GPU stand-in: full ranges, no communication."""
+    rank, size = 0, 1
+
+    def a_range(self, nv):
+        return 0, nv
+
+    def occ_range(self, no):
+        return 0, no
+
+    def all_reduce_sum(self, t):
+        return t
+
+    def barrier(self):
+        pass

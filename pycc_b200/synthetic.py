@@ -47,10 +47,12 @@ class Synthetic:
         return slice(self.no, self.n)
 
 
-def make_synthetic(no, nv, seed=0, fock_noise=0.0, naux=None, target=0.15):
+def make_synthetic(no, nv, seed=0, fock_noise=0.0, naux=None, target=0.15, device=None):
     """Seeded synthetic problem of shape (no, nv).  ``fock_noise`` > 0 adds a
     symmetric off-diagonal Fock perturbation |f_pq| <= fock_noise (variant B of
-    SURVEY 8(d)) so the non-canonical F_me terms are exercised."""
+    SURVEY 8(d)) so the non-canonical F_me terms are exercised.  With ``device``
+    the MP1-norm that fixes the scale is evaluated on that device with the
+    package's own kernels (bench sizes); otherwise on the host with numpy."""
     rng = np.random.default_rng(seed)
     n = no + nv
     naux = 2 * n if naux is None else naux
@@ -63,6 +65,8 @@ def make_synthetic(no, nv, seed=0, fock_noise=0.0, naux=None, target=0.15):
         N = 0.5 * (N + N.T)
         np.fill_diagonal(N, 0.0)
         F = F + N
+    if device is not None:
+        return Synthetic(no, nv, B, F, _device_scale(B, eps, no, nv, target, device), seed)
     # scale from the MP1 doubles norm:  <ij|ab> = sum_P B[P,i,a] B[P,j,b]
     Bov = B[:, :no, no:]
     oovv = np.einsum('Pia,Pjb->ijab', Bov, Bov, optimize=True)
@@ -87,3 +91,16 @@ def block_from_factor(syn, name):
 
 def blocks_from_factor(syn, names=BLOCK_NAMES):
     return {k: block_from_factor(syn, k) for k in names}
+
+
+def _device_scale(B, eps, no, nv, target, device):
+    """target / || <ij|ab> / D_ijab ||_F with the GEMM / denominator / dot kernels of the package."""
+    import torch
+    from . import kernels as K
+    from .contract import Contractor
+    Bov = torch.from_numpy(np.ascontiguousarray(B[:, :no, no:])).to(device)
+    oovv = Contractor()("Pia,Pjb->ijab", Bov, Bov)
+    eo = torch.from_numpy(eps[:no].copy()).to(device)
+    ev = torch.from_numpy(eps[no:].copy()).to(device)
+    t = K.div_d2(oovv, eo, ev).view(-1)
+    return target / float(K.multi_dot(t, [t])[0]) ** 0.5

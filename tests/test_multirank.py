@@ -1,0 +1,75 @@
+"""N > 1 host logic on CPU: two gloo ranks, each driving the numpy double of the C ABI.  Checks the
+rank partition of the residual (a-sharded ladder, occupied-sliced ring/W/Z terms, one all-reduce of r2)
+and the round-robin (T) against the reference goldens."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, golden_path, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import pycc_b200
+        from pycc_b200 import cctriples
+        from pycc_b200.parallel import Comm
+        from tests import emu
+        from tests.conftest import load_golden
+        g, syn = load_golden(golden_path)
+        with emu.install():
+            comm = Comm()
+            cc = pycc_b200.ccwfn(syn, model="CCSD(T)", device="GPU", quiet=True, comm=comm)
+            assert cc.H.block("vvvv").shape[0] == comm.a_range(syn.nv)[1] - comm.a_range(syn.nv)[0]
+            t1 = torch.from_numpy(g["rand_t1"].copy())
+            t2 = torch.from_numpy(g["rand_t2"].copy())
+            r1, r2 = cc.residuals(cc.H.F, t1, t2)
+            e1 = float(np.abs(r1.numpy() - g["rand_r1"]).max())
+            e2 = float(np.abs(r2.numpy() - g["rand_r2"]).max())
+            ecc = cc.solve_cc(1e-11, 1e-11)
+            ee = abs(float(ecc) - float(g["e_total_ccsd_t"]))
+            cc.t1 = torch.from_numpy(g["conv_t1"].copy())
+            cc.t2 = torch.from_numpy(g["conv_t2"].copy())
+            et = abs(float(cctriples.t_tjl(cc)) - float(g["e_t_tjl"]))
+            q.put((rank, e1, e2, ee, et, len(cc.trace)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_two_ranks_match_reference(world):
+    from tests.conftest import GOLDEN
+    path = [p for p in GOLDEN if "o4v10_s1" in p][0]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 500) + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, path, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    iters = set()
+    for rank, e1, e2, ee, et, n in res:
+        assert e1 < 1e-12 and e2 < 1e-12, (rank, e1, e2)
+        assert ee < 1e-10 and et < 1e-12, (rank, ee, et)
+        iters.add(n)
+    assert len(iters) == 1
+
+
+def test_split_is_a_partition():
+    from pycc_b200.parallel import split
+    for n in (0, 1, 7, 40, 300):
+        for size in (1, 2, 3, 8, 11):
+            parts = [split(n, size, r) for r in range(size)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[r][1] == parts[r + 1][0] for r in range(size - 1))
+            assert max(hi - lo for lo, hi in parts) - min(hi - lo for lo, hi in parts) <= 1
