@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py -- CCSD seconds/iteration and (T) FP64 TFLOP/s at o=40, v=300 on N B200s (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this package (CUDA, FP64 DMMA)
+    python bench.py --impl reference [...]                          # the reference's algorithm on host cores
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N    # N ranks, one per GPU, NCCL
+
+A step = ONE full CCSD iteration of solve_cc (reference ccwfn.py:268-319): residuals (all intermediates,
+r1, r2 incl. the v^4 ladder), the fused symmetrise/Jacobi-update/rms pass, the energy, and the DIIS
+add + extrapolate -- on synthetic integrals of the named shape (SURVEY.md 8d recipe, seed 0) held in HBM.
+Work is fixed as N grows (strong scaling): <ab|ef> is a-sharded, the other r2 terms are split over an
+occupied index, one all-reduce of r2 per iteration (pycc_b200/parallel.py).
+
+One JSON line on stdout (rank 0).  value = seconds per iteration (lower is better), timed with CUDA
+events around exactly K steps after W warm-up steps, max over ranks.  Extra keys: roofline (the ladder
+GEMM, the dominant kernel, timed live), cpu_baseline, e2e, t (the (T) rate), clocks, gpu_launches.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "CCSD s/iter + (T) FP64 TFLOP/s at o=40 v=300, 1/2/4/8 B200 vs host CPU"
+FP64_PEAK_FALLBACK = 36.18     # TFLOP/s, cuBLAS DGEMM 8192^3 measured on this pool's B200 (profiles/probe_r01_first.json)
+
+
+def ccsd_flops(o, v, factorised=True):
+    """Algorithmic flop of one CCSD iteration: ladder + o^3v^3 terms (7 when the two t1 x t1
+    terms are factorised, 9 as written in the reference) + 2 x o^4v^2 + 8 x o^2v^3."""
+    n33 = 7 if factorised else 9
+    return 2 * o**2 * v**4 + n33 * 2 * o**3 * v**3 + 2 * 2 * o**4 * v**2 + 8 * 2 * o**2 * v**3
+
+
+def t_flops_per_triple(o, v):
+    return 12 * v**4 + 12 * o * v**3
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 7 and r[3 + k].lower() == "active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(o_s, v_s, o, v, threads, reps=1):
+    """The oracle (numpy restatement of the reference algorithm) timed on the host cores for one full
+    CCSD iteration at the reduced size (o_s, v_s), scaled to (o, v) by the reference's algorithmic flops."""
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    from oracle import ccsd_oracle as co
+    from pycc_b200.synthetic import make_synthetic, blocks_from_factor
+    syn = make_synthetic(o_s, v_s, seed=0)
+    P = co.Problem(blocks_from_factor(syn), syn.F, o_s)
+    t1, t2 = P.guess()
+    diis = co.Diis(t1, t2, 8)
+    times = []
+    for _ in range(reps + 1):                       # first pass warms BLAS / einsum paths
+        t0 = time.perf_counter()
+        r1, r2 = P.residuals(syn.F, t1, t2)
+        t1 = t1 + r1 / P.Dia
+        t2 = t2 + r2 / P.Dijab
+        P.cc_energy(syn.F, t1, t2)
+        diis.add_error_vector(t1, t2)
+        t1, t2 = diis.extrapolate(t1, t2)
+        times.append(time.perf_counter() - t0)
+    t_s = min(times[1:])
+    scale = ccsd_flops(o, v, False) / ccsd_flops(o_s, v_s, False)
+    sample = ("oracle (numpy port of ccwfn.py:321-372 + update/energy/DIIS) full CCSD iteration at o=%d,v=%d: %.3f s; "
+              "scaled to o=%d,v=%d by reference algorithmic flops x%.1f (estimate)" % (o_s, v_s, t_s, o, v, scale))
+    return t_s * scale, t_s, sample
+
+
+def run_reference(args):
+    """--impl reference: the reference's own algorithm on the host cores (oracle port; the reference is
+    pure Python + psi4 and cannot travel to the GPU box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    vals = []
+    sample = ""
+    for _ in range(max(1, args.steps)):
+        est, t_s, sample = cpu_sample(args.cpu_o, args.cpu_v, args.o, args.v, cores)
+        vals.append(est)
+    v = float(np.median(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "s/iter", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": v * 1e3, "higher_is_better": False,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "RHF-CCSD iteration o=%d v=%d FP64 (synthetic integrals, seed 0)" % (args.o, args.v)},
+            "cpu_baseline": {"value": v, "unit": "s/iter", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "s/iter", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200cc", choices=["b200cc", "reference"])
+    ap.add_argument("--o", type=int, default=40)
+    ap.add_argument("--v", type=int, default=300)
+    ap.add_argument("--cpu-o", type=int, default=16)
+    ap.add_argument("--cpu-v", type=int, default=120)
+    ap.add_argument("--t-triples", type=int, default=48, help="(T) sample: triples timed per rank-set")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import pycc_b200
+    from pycc_b200 import kernels as K, cctriples
+    from pycc_b200.synthetic import make_synthetic
+    from pycc_b200.parallel import Comm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path); use --impl reference for the host baseline")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    comm = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        comm = Comm()
+    o, v = args.o, args.v
+
+    def sync():
+        if comm is not None:
+            comm.barrier()
+        torch.cuda.synchronize()
+
+    # ---- problem: synthetic factor on the host (seeded), integral blocks contracted on the device
+    t_setup = time.time()
+    syn = make_synthetic(o, v, seed=0, device=dev)
+    cc = pycc_b200.ccwfn(syn, model="CCSD(T)", device="GPU", quiet=True, comm=comm)
+    diis = pycc_b200.helper_diis(cc.t1, cc.t2, 8)
+    sync()
+    t_setup = time.time() - t_setup
+
+    def step():
+        ecc, rms = cc.iterate()
+        cc.diis_step(diis, True)
+        return ecc, rms
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    # ---- timed region: exactly K steps; inputs (integral blocks, amplitudes) resident in HBM.
+    # The working set of one step (>= 75 GB of integrals streamed) is far larger than the 126 MB L2.
+    sampler = ClockSampler(local)
+    sync()
+    sampler.start()
+    l0 = K.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        ecc, rms = step()
+    ev1.record()
+    sync()
+    clocks = sampler.stop()
+    launches = K.launch_count() - l0
+    sec = ev0.elapsed_time(ev1) * 1e-3
+    if comm is not None:
+        sec = comm.all_reduce_max_scalar(sec)
+    s_iter = sec / args.steps
+
+    # ---- roofline of the dominant kernel, timed live: the ladder GEMM (this rank's a-slice)
+    tau = K.build_tau(cc.t1, cc.t2)
+    r2 = torch.zeros_like(cc.t2)
+    a_lo, a_hi = cc.part.a_range(v)
+    lad_flops = 2.0 * o * o * (a_hi - a_lo) * v * v * v
+    cc._ladder(tau, r2)
+    torch.cuda.synchronize()
+    la, lb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nl = 3
+    la.record()
+    for _ in range(nl):
+        cc._ladder(tau, r2)
+    lb.record()
+    torch.cuda.synchronize()
+    t_lad = la.elapsed_time(lb) * 1e-3 / nl
+    del tau, r2
+    peak = FP64_PEAK_FALLBACK
+    peak_src = "cuBLAS DGEMM 8192^3 measured on this pool (profiles/probe_r01_first.json); MEASURED_PEAKS.json has no FP64 entry"
+    try:   # live re-measurement of the denominator on this very GPU (library GEMM, not on the product path)
+        A = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+        C = torch.empty_like(A)
+        torch.matmul(A, A, out=C)
+        torch.cuda.synchronize()
+        pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pa.record()
+        for _ in range(3):
+            torch.matmul(A, A, out=C)
+        pb.record()
+        torch.cuda.synchronize()
+        peak = 3 * 2.0 * 8192**3 / (pa.elapsed_time(pb) * 1e-3) / 1e12
+        peak_src = "cuBLAS DGEMM 8192^3 measured live in this run (MEASURED_PEAKS.json has no FP64 entry)"
+        del A, C
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "kernel": "dgemm_kernel (ladder, ccwfn.py:931)", "achieved": lad_flops / t_lad / 1e12,
+                "peak": peak, "unit": "TFLOP/s", "frac": lad_flops / t_lad / 1e12 / peak, "traffic": None,
+                "peak_source": peak_src, "launch_ms": t_lad * 1e3,
+                "share_of_step": t_lad / s_iter,
+                "whole_step_tflops_per_gpu": ccsd_flops(o, v) / world / s_iter / 1e12}
+
+    # ---- (T): FP64 TFLOP/s on a bounded sample of (i>=j>=k) triples, sharded round-robin over the ranks
+    trip = [t for t in cctriples.triples_list(o) if not (t[0] == t[1] == t[2])]
+    nt = min(len(trip), args.t_triples * world)
+    sample_trip = trip[:: max(1, len(trip) // nt)][:nt]
+    cctriples.t_tjl(cc, sample_trip[:world * 2])           # warm-up
+    sync()
+    ta, tb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ta.record()
+    et = cctriples.t_tjl(cc, sample_trip)
+    tb.record()
+    sync()
+    t_t = ta.elapsed_time(tb) * 1e-3
+    if comm is not None:
+        t_t = comm.all_reduce_max_scalar(t_t)
+    t_rate = t_flops_per_triple(o, v) * len(sample_trip) / t_t / 1e12
+    t_info = {"tflops": t_rate, "unit": "TFLOP/s (FP64, whole job)", "triples_timed": len(sample_trip),
+              "triples_total": len(trip), "seconds": t_t, "full_t_seconds_est": t_t * len(trip) / len(sample_trip),
+              "frac_of_fp64_peak_per_gpu": t_rate / world / peak, "e_t_sample": float(et)}
+
+    # ---- e2e: the same step through the public API with HOST amplitudes: every step uploads t1, t2 (and F)
+    # from pinned host memory, runs the iteration, and reads (ecc, rms) back
+    h_t1 = cc.t1.cpu().pin_memory()
+    h_t2 = cc.t2.cpu().pin_memory()
+    h_F = cc.H.F.cpu().pin_memory()
+    d_F = torch.empty_like(cc.H.F)
+    e2e_steps = max(2, min(args.steps, 3))
+    sync()
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record()
+    for _ in range(e2e_steps):
+        cc.t1.copy_(h_t1, non_blocking=True)
+        cc.t2.copy_(h_t2, non_blocking=True)
+        d_F.copy_(h_F, non_blocking=True)
+        ecc2, rms2 = cc.iterate(d_F)                     # returns host floats (D2H of 2 doubles)
+        cc.diis_step(diis, True)
+    eb.record()
+    sync()
+    t_e2e = ea.elapsed_time(eb) * 1e-3 / e2e_steps
+    if comm is not None:
+        t_e2e = comm.all_reduce_max_scalar(t_e2e)
+    e2e = {"value": t_e2e, "unit": "s/iter", "h2d_bytes_per_step": int((h_t1.numel() + h_t2.numel() + h_F.numel()) * 8),
+           "d2h_bytes_per_step": 16}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu and world >= 1:
+            cores = os.cpu_count() or 1
+            est, t_s, sample = cpu_sample(args.cpu_o, args.cpu_v, o, v, cores)
+            cpu = {"value": est, "unit": "s/iter", "cores": cores, "kind": "port", "sample": sample}
+        line = {"metric": METRIC, "value": s_iter, "unit": "s/iter", "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": s_iter * 1e3, "higher_is_better": False,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "RHF-CCSD iteration o=%d v=%d FP64 (synthetic integrals, seed 0); inputs >> L2 "
+                                       "(75 GB of integrals streamed per step)" % (o, v),
+                           "parallelism": "a-sharded ladder + occupied-sliced ring terms, 1 all-reduce/iter" if world > 1 else "single GPU",
+                           "diis": 8, "setup_s": t_setup},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "t": t_info, "clocks": clocks,
+                "gpu_launches": int(launches), "ecc_last": ecc, "rms_last": rms}
+        print(json.dumps(line), flush=True)
+    if comm is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

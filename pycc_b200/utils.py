@@ -83,7 +83,10 @@ class helper_diis(object):
         B[:-1, :-1] /= np.abs(B[:-1, :-1]).max()
         rhs = np.zeros(m + 1)
         rhs[-1] = -1.0
-        c = np.linalg.solve(B, rhs)
+        try:
+            c = np.linalg.solve(B, rhs)
+        except np.linalg.LinAlgError:          # exactly singular B (repeated iterates): minimum-norm solution
+            c = np.linalg.lstsq(B, rhs, rcond=None)[0]
         self.last_coefficients = c[:m].copy()
         new = torch.empty_like(self.old)
         K.multi_axpy(c[:m], self.vals[1:m + 1], new)
