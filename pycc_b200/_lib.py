@@ -42,6 +42,7 @@ class GemmDesc(C.Structure):
         ("table_align16", C.c_int),
         ("ksplit", C.c_int),
         ("workspace", dptr),
+        ("config", C.c_int),
     ]
 
 

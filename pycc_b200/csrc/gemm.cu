@@ -1,30 +1,39 @@
 // gemm.cu -- FP64 tensor-core GEMM for sm_100a (DMMA.8x8x4 via mma.sync.m8n8k4.f64).
 //
 // tcgen05.mma has no f64 kind, so double precision on Blackwell is the warp-level DMMA path with
-// register accumulators (nvcc 12.9 lowers every f64 mma shape to DMMA.8x8x4 on sm_100a).
+// register accumulators (nvcc 12.9 lowers every f64 mma shape to DMMA.8x8x4 on sm_100a; one DMMA
+// occupies an SM sub-partition's tensor pipe for 16 cycles = 64 FMA/clk/SM).
 //
-//   CTA tile 128 x 128 x 16, 8 warps as 4(M) x 2(N); each warp owns 4 x 8 interleaved 8x8 fragments
-//   (fragment f of a row/column belongs to warp f % 4 / f % 2) so ragged edges are skipped at
-//   8-row granularity and stay balanced across warps.  Operands are staged global->shared with a
-//   4-deep cp.async pipeline (zero-fill handles every M/N/K tail); one __syncthreads per 16-wide
-//   k-tile (= 128 DMMA per warp).  Either operand may be K-major or M/N-major; shared tiles are
-//   padded (+4 doubles per row) so all fragment loads (LDS.64) are bank-conflict free.
-//   Two K-segments can be chained into the same accumulators; split-K goes through a workspace and a
-//   deterministic reduction.
+//   * PERSISTENT: one CTA per SM walks a list of work units (output tile x batch entry x K-split);
+//     the 4-deep cp.async operand pipeline runs ACROSS unit boundaries, so the next tile's operands
+//     stream in while the current tile is finished and stored (no per-tile prologue/epilogue bubble --
+//     this matters for the short-K GEMMs of (T) and of the o^3v^3 ring terms).
+//   * CTA tile BM x BN x 16 from a compile-time config <WARPS_M, WARPS_N, MI, NI>; each warp owns
+//     MI x NI INTERLEAVED 8x8 fragments (fragment f of a row/column belongs to warp f % WARPS), so ragged
+//     edges are skipped at 8-row granularity and stay balanced over warps and SM sub-partitions.
+//   * Either operand K-major or M/N-major; shared tiles are padded (+4 doubles per row) so every
+//     fragment load (LDS.64) is bank-conflict free; cp.async zero-fill handles all M/N/K tails.
+//   * Two K-segments can be chained into the same accumulators ((T): particle + hole term);
+//     split-K goes through a workspace and a deterministic reduction; batches by stride or address table.
 #include "common.cuh"
 
 namespace b200cc {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, NTHREADS = 256;
-constexpr int WARPS_M = 4, WARPS_N = 2;
-constexpr int MI = BM / (8 * WARPS_M);  // 4 M-fragments per warp
-constexpr int NI = BN / (8 * WARPS_N);  // 8 N-fragments per warp
-constexpr int LDK = BK + 4;             // K-major shared row pitch (doubles): 160 B -> rows 32 B apart mod 128
-constexpr int LDMN = BM + 4;            // M/N-major shared row pitch: 1056 B -> rows 32 B apart mod 128
-constexpr int TILE = BM * LDK;          // 2560 doubles per operand per stage (>= BK*LDMN = 2112)
-constexpr int SMEM_BYTES = STAGES * 2 * TILE * (int)sizeof(double);  // 163840
-static_assert(BM == BN, "shared tile helpers assume square CTA tiles");
-static_assert(BK * LDMN <= TILE, "tile buffer too small");
+constexpr int BK = 16, STAGES = 4;
+constexpr int LDK = BK + 4;  // K-major shared row pitch (doubles): 160 B -> consecutive rows 32 B apart mod 128
+
+template <int WM_, int WN_, int MI_, int NI_>
+struct Cfg {
+  static constexpr int WARPS_M = WM_, WARPS_N = WN_, MI = MI_, NI = NI_;
+  static constexpr int BM = 8 * WM_ * MI_, BN = 8 * WN_ * NI_, NT = 32 * WM_ * WN_;
+  static constexpr int TILE_A = (BM * LDK > BK * (BM + 4)) ? BM * LDK : BK * (BM + 4);
+  static constexpr int TILE_B = (BN * LDK > BK * (BN + 4)) ? BN * LDK : BK * (BN + 4);
+  static constexpr int STAGE = TILE_A + TILE_B;
+  static constexpr int SMEM_BYTES = STAGES * STAGE * (int)sizeof(double);
+};
+typedef Cfg<4, 4, 4, 4> CfgA;  // 128 x 128, 16 warps (4 per sub-partition)
+typedef Cfg<4, 2, 4, 8> CfgB;  // 128 x 128,  8 warps
+typedef Cfg<2, 4, 5, 4> CfgC;  //  80 x 128,  8 warps (M = o^2 = 400, 1600, ... divide by 80)
 
 struct KParams {
   int M, N, K1, K2;
@@ -34,9 +43,10 @@ struct KParams {
   i64 ldc, sC;
   double alpha, beta;
   const i64* table;
-  int tiles_m, tiles_n;
+  int tiles_m, tiles_n, tiles;
   int kt1, kt_total, kt_per_split;
-  int ksplit, batch, cvec;
+  int ksplit, batch, cvec, nfast;
+  int units;
   double* ws;
 };
 
@@ -61,18 +71,19 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
       : "d"(a), "d"(b));
 }
 
-// Stage one operand tile.  TRANS=false: global (row, k) at G[row*ld + k]  -> shared [128][LDK].
-//                          TRANS=true : global (k, row) at G[k*ld + row]  -> shared [16][LDMN].
+// Stage one operand tile of ROWS rows.  TRANS=false: global (row,k) at G[row*ld + k] -> shared [ROWS][LDK].
+//                                       TRANS=true : global (k,row) at G[k*ld + row] -> shared [BK][ROWS+4].
 // Out-of-range rows / k are zero-filled (cp.async src-size), so no tail code exists downstream.
-template <bool TRANS, int VEC>
+template <bool TRANS, int VEC, int ROWS, int NT>
 __device__ __forceinline__ void load_tile(double* sm, const double* __restrict__ G, i64 ld, int row0,
                                           int nrows, int k0, int K, int tid) {
   if (!TRANS) {
-    constexpr int CPR = BK / VEC;  // chunks per row
-    constexpr int NCH = BM * CPR;
+    constexpr int CPR = BK / VEC;
+    constexpr int NCH = ROWS * CPR;
 #pragma unroll
-    for (int i = 0; i < NCH / NTHREADS; ++i) {
-      const int c = tid + i * NTHREADS;
+    for (int i = 0; i < (NCH + NT - 1) / NT; ++i) {
+      const int c = tid + i * NT;
+      if (NCH % NT != 0 && c >= NCH) break;
       const int r = c / CPR, kc = (c % CPR) * VEC;
       const int gr = row0 + r, gk = k0 + kc;
       const int valid = (gr < nrows) ? min(max(K - gk, 0), VEC) : 0;
@@ -82,11 +93,13 @@ __device__ __forceinline__ void load_tile(double* sm, const double* __restrict__
       else cp_async8(dst, src, valid * 8);
     }
   } else {
-    constexpr int CPR = BM / VEC;
+    constexpr int LDMN = ROWS + 4;
+    constexpr int CPR = ROWS / VEC;
     constexpr int NCH = BK * CPR;
 #pragma unroll
-    for (int i = 0; i < NCH / NTHREADS; ++i) {
-      const int c = tid + i * NTHREADS;
+    for (int i = 0; i < (NCH + NT - 1) / NT; ++i) {
+      const int c = tid + i * NT;
+      if (NCH % NT != 0 && c >= NCH) break;
       const int kr = c / CPR, mc = (c % CPR) * VEC;
       const int gk = k0 + kr, gm = row0 + mc;
       const int valid = (gk < K) ? min(max(nrows - gm, 0), VEC) : 0;
@@ -100,22 +113,23 @@ __device__ __forceinline__ void load_tile(double* sm, const double* __restrict__
 
 // One 16-wide k-tile: 4 k4-steps x (MI x NI) DMMA per warp.
 // Fragment ownership (PTX m8n8k4.f64): lane = 4*g + q holds A[g][q], B[q][g], C[g][2q], C[g][2q+1].
-template <bool TA, bool TB, bool CHECK>
+template <class CF, bool TA, bool TB, bool CHECK>
 __device__ __forceinline__ void compute_tile(const double* __restrict__ As, const double* __restrict__ Bs,
-                                             double (&acc)[MI][NI][2], int wm, int wn, int g, int q,
+                                             double (&acc)[CF::MI][CF::NI][2], int wm, int wn, int g, int q,
                                              uint32_t mmask, uint32_t nmask) {
+  constexpr int MI = CF::MI, NI = CF::NI;
 #pragma unroll
   for (int ks = 0; ks < BK / 4; ++ks) {
     double a[MI], b[NI];
 #pragma unroll
     for (int i = 0; i < MI; ++i) {
-      const int r = 8 * (wm + WARPS_M * i) + g;
-      a[i] = TA ? As[(ks * 4 + q) * LDMN + r] : As[r * LDK + ks * 4 + q];
+      const int r = 8 * (wm + CF::WARPS_M * i) + g;
+      a[i] = TA ? As[(ks * 4 + q) * (CF::BM + 4) + r] : As[r * LDK + ks * 4 + q];
     }
 #pragma unroll
     for (int j = 0; j < NI; ++j) {
-      const int r = 8 * (wn + WARPS_N * j) + g;
-      b[j] = TB ? Bs[(ks * 4 + q) * LDMN + r] : Bs[r * LDK + ks * 4 + q];
+      const int r = 8 * (wn + CF::WARPS_N * j) + g;
+      b[j] = TB ? Bs[(ks * 4 + q) * (CF::BN + 4) + r] : Bs[r * LDK + ks * 4 + q];
     }
 #pragma unroll
     for (int i = 0; i < MI; ++i) {
@@ -129,115 +143,154 @@ __device__ __forceinline__ void compute_tile(const double* __restrict__ As, cons
   }
 }
 
-template <bool TA, bool TB, int VEC>
-__global__ void __launch_bounds__(NTHREADS, 1) dgemm_kernel(const KParams p) {
+struct Unit {
+  int m0, n0, b, z, kt_begin, nkt;
+};
+
+template <class CF>
+__device__ __forceinline__ Unit decode_unit(const KParams& p, int u) {
+  Unit w;
+  const int per = p.tiles * p.batch;
+  w.z = u / per;
+  const int rem = u - w.z * per;
+  w.b = rem / p.tiles;
+  const int t = rem - w.b * p.tiles;
+  int tm, tn;
+  if (p.nfast) { tn = t % p.tiles_n; tm = t / p.tiles_n; }
+  else { tm = t % p.tiles_m; tn = t / p.tiles_m; }
+  w.m0 = tm * CF::BM;
+  w.n0 = tn * CF::BN;
+  w.kt_begin = w.z * p.kt_per_split;
+  const int e = min(w.kt_begin + p.kt_per_split, p.kt_total);
+  w.nkt = e > w.kt_begin ? e - w.kt_begin : 0;
+  return w;
+}
+
+template <class CF, bool TA, bool TB, int VEC>
+__global__ void __launch_bounds__(CF::NT, 1) dgemm_kernel(const KParams p) {
   extern __shared__ __align__(16) double smem[];
+  constexpr int MI = CF::MI, NI = CF::NI;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp % WARPS_M, wn = warp / WARPS_M;
+  const int wn = warp % CF::WARPS_N, wm = warp / CF::WARPS_N;
   const int g = lane >> 2, q = lane & 3;
-  const int tm = blockIdx.x % p.tiles_m, tn = blockIdx.x / p.tiles_m;
-  const int m0 = tm * BM, n0 = tn * BN;
-  const int b = blockIdx.y, z = blockIdx.z;
+  const int G = gridDim.x;
 
-  const double *A1, *B1, *A2, *B2;
-  double* C;
-  if (p.table) {
-    const i64* t = p.table + 5 * (i64)b;
-    A1 = reinterpret_cast<const double*>(t[0]);
-    B1 = reinterpret_cast<const double*>(t[1]);
-    A2 = reinterpret_cast<const double*>(t[2]);
-    B2 = reinterpret_cast<const double*>(t[3]);
-    C = reinterpret_cast<double*>(t[4]);
-  } else {
-    A1 = p.A1 + (i64)b * p.sA1;
-    B1 = p.B1 + (i64)b * p.sB1;
-    A2 = p.A2 + (i64)b * p.sA2;
-    B2 = p.B2 + (i64)b * p.sB2;
-    C = p.C + (i64)b * p.sC;
-  }
-
-  const int kt_begin = z * p.kt_per_split;
-  const int nkt = min(kt_begin + p.kt_per_split, p.kt_total) - kt_begin;  // may be <= 0
-
-  uint32_t mmask = 0, nmask = 0;
-#pragma unroll
-  for (int i = 0; i < MI; ++i) mmask |= (m0 + 8 * (wm + WARPS_M * i) < p.M) ? (1u << i) : 0u;
-#pragma unroll
-  for (int j = 0; j < NI; ++j) nmask |= (n0 + 8 * (wn + WARPS_N * j) < p.N) ? (1u << j) : 0u;
-  const bool full = (m0 + BM <= p.M) && (n0 + BN <= p.N);
-
-  double acc[MI][NI][2];
-#pragma unroll
-  for (int i = 0; i < MI; ++i)
-#pragma unroll
-    for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-  auto issue = [&](int kt_rel, int stage) {
-    const int kt = kt_begin + kt_rel;
-    double* As = smem + stage * (2 * TILE);
-    double* Bs = As + TILE;
-    if (kt < p.kt1) {
-      const int k0 = kt * BK;
-      load_tile<TA, VEC>(As, A1, p.lda1, m0, p.M, k0, p.K1, tid);
-      load_tile<TB, VEC>(Bs, B1, p.ldb1, n0, p.N, k0, p.K1, tid);
-    } else {
-      const int k0 = (kt - p.kt1) * BK;
-      load_tile<TA, VEC>(As, A2, p.lda2, m0, p.M, k0, p.K2, tid);
-      load_tile<TB, VEC>(Bs, B2, p.ldb2, n0, p.N, k0, p.K2, tid);
+  // ---- load cursor: (unit, k-tile) of the next operand tile to stage; skips units with no k-tiles
+  int lu = blockIdx.x, lkt = 0, lnkt = 0;
+  auto seek = [&]() {
+    while (lu < p.units) {
+      lnkt = decode_unit<CF>(p, lu).nkt;
+      if (lnkt > 0) break;
+      lu += G;
     }
+    lkt = 0;
+  };
+  auto issue_next = [&](int stage) {
+    if (lu < p.units) {
+      const Unit w = decode_unit<CF>(p, lu);
+      const double *A1, *B1, *A2, *B2;
+      if (p.table) {
+        const i64* t = p.table + 5 * (i64)w.b;
+        A1 = reinterpret_cast<const double*>(t[0]);
+        B1 = reinterpret_cast<const double*>(t[1]);
+        A2 = reinterpret_cast<const double*>(t[2]);
+        B2 = reinterpret_cast<const double*>(t[3]);
+      } else {
+        A1 = p.A1 + (i64)w.b * p.sA1;
+        B1 = p.B1 + (i64)w.b * p.sB1;
+        A2 = p.A2 + (i64)w.b * p.sA2;
+        B2 = p.B2 + (i64)w.b * p.sB2;
+      }
+      double* As = smem + stage * CF::STAGE;
+      double* Bs = As + CF::TILE_A;
+      const int kt = w.kt_begin + lkt;
+      if (kt < p.kt1) {
+        const int k0 = kt * BK;
+        load_tile<TA, VEC, CF::BM, CF::NT>(As, A1, p.lda1, w.m0, p.M, k0, p.K1, tid);
+        load_tile<TB, VEC, CF::BN, CF::NT>(Bs, B1, p.ldb1, w.n0, p.N, k0, p.K1, tid);
+      } else {
+        const int k0 = (kt - p.kt1) * BK;
+        load_tile<TA, VEC, CF::BM, CF::NT>(As, A2, p.lda2, w.m0, p.M, k0, p.K2, tid);
+        load_tile<TB, VEC, CF::BN, CF::NT>(Bs, B2, p.ldb2, w.n0, p.N, k0, p.K2, tid);
+      }
+      if (++lkt == lnkt) {
+        lu += G;
+        seek();
+      }
+    }
+    cp_async_commit();
   };
 
+  seek();
 #pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < nkt) issue(s, s);
-    cp_async_commit();
-  }
-  for (int t = 0; t < nkt; ++t) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    const int nt = t + STAGES - 1;
-    if (nt < nkt) issue(nt, nt % STAGES);
-    cp_async_commit();
-    const double* As = smem + (t % STAGES) * (2 * TILE);
-    const double* Bs = As + TILE;
-    if (full) compute_tile<TA, TB, false>(As, Bs, acc, wm, wn, g, q, mmask, nmask);
-    else compute_tile<TA, TB, true>(As, Bs, acc, wm, wn, g, q, mmask, nmask);
-  }
-  cp_async_wait<0>();
+  for (int s = 0; s < STAGES - 1; ++s) issue_next(s);
+  int cstage = 0, lstage = STAGES - 1;
 
-  // ---- epilogue: C = alpha*acc + beta*C, or raw partials into the split-K workspace
-  const bool split = p.ksplit > 1;
-  double* out = split ? p.ws + ((i64)z * p.batch + b) * (i64)p.M * p.N : C;
-  const i64 ldo = split ? (i64)p.N : p.ldc;
-  const double alpha = split ? 1.0 : p.alpha, beta = split ? 0.0 : p.beta;
-  const bool vec = split ? ((p.N & 1) == 0 && (((i64)p.M * p.N) & 1) == 0) : (p.cvec != 0);
+  for (int cu = blockIdx.x; cu < p.units; cu += G) {
+    const Unit w = decode_unit<CF>(p, cu);
+    uint32_t mmask = 0, nmask = 0;
 #pragma unroll
-  for (int i = 0; i < MI; ++i) {
-    const int row = m0 + 8 * (wm + WARPS_M * i) + g;
-    if (row >= p.M) continue;
+    for (int i = 0; i < MI; ++i) mmask |= (w.m0 + 8 * (wm + CF::WARPS_M * i) < p.M) ? (1u << i) : 0u;
 #pragma unroll
-    for (int j = 0; j < NI; ++j) {
-      const int col = n0 + 8 * (wn + WARPS_N * j) + 2 * q;
-      if (col >= p.N) continue;
-      double* c = out + (i64)row * ldo + col;
-      double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
-      if (vec && col + 1 < p.N) {
-        if (beta != 0.0) {
-          const double2 o = *reinterpret_cast<const double2*>(c);
-          v0 += beta * o.x;
-          v1 += beta * o.y;
-        }
-        *reinterpret_cast<double2*>(c) = make_double2(v0, v1);
-      } else {
-        if (beta != 0.0) v0 += beta * c[0];
-        c[0] = v0;
-        if (col + 1 < p.N) {
-          if (beta != 0.0) v1 += beta * c[1];
-          c[1] = v1;
+    for (int j = 0; j < NI; ++j) nmask |= (w.n0 + 8 * (wn + CF::WARPS_N * j) < p.N) ? (1u << j) : 0u;
+    const bool full = (w.m0 + CF::BM <= p.M) && (w.n0 + CF::BN <= p.N);
+
+    double acc[MI][NI][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+      for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int t = 0; t < w.nkt; ++t) {
+      cp_async_wait<STAGES - 2>();
+      __syncthreads();
+      issue_next(lstage);
+      lstage = (lstage + 1 == STAGES) ? 0 : lstage + 1;
+      const double* As = smem + cstage * CF::STAGE;
+      const double* Bs = As + CF::TILE_A;
+      if (full) compute_tile<CF, TA, TB, false>(As, Bs, acc, wm, wn, g, q, mmask, nmask);
+      else compute_tile<CF, TA, TB, true>(As, Bs, acc, wm, wn, g, q, mmask, nmask);
+      cstage = (cstage + 1 == STAGES) ? 0 : cstage + 1;
+    }
+
+    // ---- epilogue: C = alpha*acc + beta*C, or raw partials into the split-K workspace
+    const bool split = p.ksplit > 1;
+    double* C;
+    if (split) C = p.ws + ((i64)w.z * p.batch + w.b) * (i64)p.M * p.N;
+    else if (p.table) C = reinterpret_cast<double*>(p.table[5 * (i64)w.b + 4]);
+    else C = p.C + (i64)w.b * p.sC;
+    const i64 ldo = split ? (i64)p.N : p.ldc;
+    const double alpha = split ? 1.0 : p.alpha, beta = split ? 0.0 : p.beta;
+    const bool vec = split ? ((p.N & 1) == 0 && (((i64)p.M * p.N) & 1) == 0) : (p.cvec != 0);
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+      const int row = w.m0 + 8 * (wm + CF::WARPS_M * i) + g;
+      if (row >= p.M) continue;
+#pragma unroll
+      for (int j = 0; j < NI; ++j) {
+        const int col = w.n0 + 8 * (wn + CF::WARPS_N * j) + 2 * q;
+        if (col >= p.N) continue;
+        double* c = C + (i64)row * ldo + col;
+        double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
+        if (vec && col + 1 < p.N) {
+          if (beta != 0.0) {
+            const double2 o = *reinterpret_cast<const double2*>(c);
+            v0 += beta * o.x;
+            v1 += beta * o.y;
+          }
+          *reinterpret_cast<double2*>(c) = make_double2(v0, v1);
+        } else {
+          if (beta != 0.0) v0 += beta * c[0];
+          c[0] = v0;
+          if (col + 1 < p.N) {
+            if (beta != 0.0) v1 += beta * c[1];
+            c[1] = v1;
+          }
         }
       }
     }
   }
+  cp_async_wait<0>();
 }
 
 // C[b] = alpha * sum_z ws[z][b] + beta * C[b]
@@ -257,20 +310,51 @@ __global__ void splitk_reduce_kernel(const double* __restrict__ ws, int ksplit, 
   }
 }
 
-template <bool TA, bool TB, int VEC>
-static int launch(const KParams& p, dim3 grid, cudaStream_t st) {
+template <class CF, bool TA, bool TB, int VEC>
+static int launch(const KParams& p, int grid, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    B200CC_CUDA_OK(cudaFuncSetAttribute(dgemm_kernel<TA, TB, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        SMEM_BYTES));
+    B200CC_CUDA_OK(cudaFuncSetAttribute(dgemm_kernel<CF, TA, TB, VEC>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES));
     configured = true;
   }
-  dgemm_kernel<TA, TB, VEC><<<grid, NTHREADS, SMEM_BYTES, st>>>(p);
+  dgemm_kernel<CF, TA, TB, VEC><<<grid, CF::NT, CF::SMEM_BYTES, st>>>(p);
   return check_launch("dgemm_kernel");
+}
+
+template <class CF>
+static int dispatch(KParams& p, int ta, int tb, bool v2, cudaStream_t st) {
+  p.tiles_m = (p.M + CF::BM - 1) / CF::BM;
+  p.tiles_n = (p.N + CF::BN - 1) / CF::BN;
+  const i64 tiles = (i64)p.tiles_m * p.tiles_n;
+  const i64 units = tiles * p.batch * p.ksplit;
+  if (tiles > 2000000000LL || units > 2000000000LL) { set_error("b200cc_dgemm: too many tiles"); return 1; }
+  p.tiles = (int)tiles;
+  p.units = (int)units;
+  // raster: the index with FEWER tiles varies fastest, so co-running CTAs share the larger operand panel in L2
+  p.nfast = p.tiles_n < p.tiles_m ? 1 : 0;
+  const int nsm = sm_count();
+  const int grid = units < nsm ? (int)units : nsm;
+#define B200CC_GO(TA, TB) (v2 ? launch<CF, TA, TB, 2>(p, grid, st) : launch<CF, TA, TB, 1>(p, grid, st))
+  if (!ta && !tb) return B200CC_GO(false, false);
+  if (!ta && tb) return B200CC_GO(false, true);
+  if (ta && !tb) return B200CC_GO(true, false);
+  return B200CC_GO(true, true);
+#undef B200CC_GO
 }
 
 static inline bool even(i64 x) { return (x & 1) == 0; }
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// effective padded extent of a dimension of size n cut into tiles of `tile` rows handled as interleaved
+// 8-row fragments over `warps` warps (a ragged last tile costs ceil(frags/warps)/MI of a full one)
+static double eff_extent(int n, int tile, int warps) {
+  const int full = n / tile, rem = n - full * tile;
+  if (rem == 0) return (double)full * tile;
+  const int frags = (rem + 7) / 8;
+  const int per_warp = (frags + warps - 1) / warps;
+  return (double)full * tile + (double)per_warp * warps * 8;
+}
 
 }  // namespace b200cc
 
@@ -282,7 +366,6 @@ extern "C" int b200cc_dgemm(const b200cc_gemm_desc* d, void* stream) {
     set_error("b200cc_dgemm: negative dimension"); return 1;
   }
   if (d->M == 0 || d->N == 0 || d->batch == 0) return 0;
-  if (d->batch > 65535) { set_error("b200cc_dgemm: batch %d > 65535 (chunk it)", d->batch); return 1; }
   const int ksplit = d->ksplit > 1 ? d->ksplit : 1;
   if (ksplit > 65535) { set_error("b200cc_dgemm: ksplit too large"); return 1; }
   if (ksplit > 1 && !d->workspace) { set_error("b200cc_dgemm: ksplit > 1 needs a workspace"); return 1; }
@@ -299,7 +382,6 @@ extern "C" int b200cc_dgemm(const b200cc_gemm_desc* d, void* stream) {
   p.C = d->C; p.ldc = d->ldc; p.sC = d->strideC;
   p.alpha = d->alpha; p.beta = d->beta;
   p.table = d->table;
-  p.tiles_m = (d->M + BM - 1) / BM; p.tiles_n = (d->N + BN - 1) / BN;
   p.kt1 = (d->K1 + BK - 1) / BK;
   p.kt_total = p.kt1 + (d->K2 + BK - 1) / BK;
   p.ksplit = ksplit; p.batch = d->batch; p.ws = d->workspace;
@@ -325,19 +407,20 @@ extern "C" int b200cc_dgemm(const b200cc_gemm_desc* d, void* stream) {
   }
   p.cvec = vc ? 1 : 0;
   const bool v2 = va && vb;
-
-  const i64 tiles = (i64)p.tiles_m * p.tiles_n;
-  if (tiles > 2147483647LL) { set_error("b200cc_dgemm: too many tiles"); return 1; }
-  dim3 grid((unsigned)tiles, (unsigned)d->batch, (unsigned)ksplit);
   const int ta = d->transA ? 1 : 0, tb = d->transB ? 1 : 0;
+
+  // tile configuration: 0 = auto
+  int cfg = d->config;
+  if (cfg == 0) {
+    cfg = 1;
+    const double e128 = eff_extent(d->M, 128, 4), e80 = eff_extent(d->M, 80, 2);
+    if (d->M >= 80 && e80 < 0.93 * e128) cfg = 3;
+  }
   int rc;
-#define B200CC_GO(TA, TB)                                             \
-  rc = v2 ? launch<TA, TB, 2>(p, grid, st) : launch<TA, TB, 1>(p, grid, st)
-  if (!ta && !tb) { B200CC_GO(false, false); }
-  else if (!ta && tb) { B200CC_GO(false, true); }
-  else if (ta && !tb) { B200CC_GO(true, false); }
-  else { B200CC_GO(true, true); }
-#undef B200CC_GO
+  if (cfg == 1) rc = dispatch<CfgA>(p, ta, tb, v2, st);
+  else if (cfg == 2) rc = dispatch<CfgB>(p, ta, tb, v2, st);
+  else if (cfg == 3) rc = dispatch<CfgC>(p, ta, tb, v2, st);
+  else { set_error("b200cc_dgemm: unknown tile config %d", cfg); return 1; }
   if (rc) return rc;
   if (ksplit > 1) {
     const i64 total = (i64)d->M * d->N * d->batch;

@@ -43,7 +43,7 @@ def auto_ksplit(M, N, K, batch):
 
 
 def dgemm(M, N, K, A, lda, transA, B, ldb, transB, Cmat, ldc, alpha=1.0, beta=0.0,
-          batch=1, sA=0, sB=0, sC=0, seg2=None, table=None, table_align16=False, ksplit=None):
+          batch=1, sA=0, sB=0, sC=0, seg2=None, table=None, table_align16=False, ksplit=None, config=0):
     """C[b] = alpha * (opA[b] opB[b]^T [+ second K segment]) + beta * C[b]; see b200cc_dgemm.
 
     A, B, Cmat: tensor, (tensor, element offset) or raw address.  seg2 = (A2, lda2, B2, ldb2, K2, sA2, sB2).
@@ -67,25 +67,12 @@ def dgemm(M, N, K, A, lda, transA, B, ldb, transB, Cmat, ldc, alpha=1.0, beta=0.
     if ksplit is None:
         ksplit = auto_ksplit(M, N, K + K2, batch)
     d.ksplit = int(ksplit)
+    d.config = int(config)
     ws = None
     if ksplit > 1:
         dev = _dev(table if table is not None else Cmat)
         ws = torch.empty(ksplit * batch * M * N, dtype=F64, device=dev)
         d.workspace = _lib.ptr(ws)
-    # chunk batches beyond the grid.y limit
-    if batch > 65535:
-        if table is not None:
-            raise B200ccError("table-mode batch > 65535")
-        done = 0
-        while done < batch:
-            nb = min(65535, batch - done)
-            dgemm(M, N, K, _addr(A) + 8 * sA * done, lda, transA, _addr(B) + 8 * sB * done, ldb, transB,
-                  _addr(Cmat) + 8 * sC * done, ldc, alpha, beta, nb, sA, sB, sC,
-                  None if seg2 is None else (_addr(seg2[0]) + 8 * seg2[5] * done, seg2[1],
-                                             _addr(seg2[2]) + 8 * seg2[6] * done, seg2[3], seg2[4], seg2[5], seg2[6]),
-                  None, False, ksplit if ksplit == 1 else None)
-            done += nb
-        return
     _lib.check(_lib.get().b200cc_dgemm(C.byref(d), _lib.stream()), "b200cc_dgemm")
     del ws
 

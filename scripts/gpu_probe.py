@@ -15,6 +15,7 @@ from pycc_b200 import kernels as K   # noqa: E402
 
 DEV = torch.device("cuda:0")
 OUT = {}
+CONFIGS = (1, 2, 3)
 
 
 def timeit(fn, warm=2, reps=5):
@@ -50,10 +51,12 @@ def gemm_case(name, M, N, Kd, ta=0, tb=0, batch=1, cublas=True, reps=5):
     flops = 2.0 * M * N * Kd * batch
     lda = M if ta else Kd
     ldb = N if tb else Kd
-    best, avg = timeit(lambda: K.dgemm(M, N, Kd, A, lda, ta, B, ldb, tb, C, N, batch=batch, sA=M * Kd, sB=N * Kd,
-                                       sC=M * N, ksplit=1), reps=reps)
-    r = {"M": M, "N": N, "K": Kd, "batch": batch, "ta": ta, "tb": tb, "b200cc_tflops_best": flops / best / 1e12,
-         "b200cc_tflops_avg": flops / avg / 1e12, "clocks_after": clocks()}
+    r = {"M": M, "N": N, "K": Kd, "batch": batch, "ta": ta, "tb": tb}
+    for cfg in CONFIGS:
+        best, avg = timeit(lambda: K.dgemm(M, N, Kd, A, lda, ta, B, ldb, tb, C, N, batch=batch, sA=M * Kd, sB=N * Kd,
+                                           sC=M * N, ksplit=1, config=cfg), reps=reps)
+        r["b200cc_cfg%d_tflops" % cfg] = flops / best / 1e12
+    r["clocks_after"] = clocks()
     if cublas:
         Am = A.transpose(1, 2) if ta else A
         Bm = B if tb else B.transpose(1, 2)
