@@ -146,6 +146,10 @@ __device__ __forceinline__ void compute_tile(const double* __restrict__ As, cons
 struct Unit {
   int m0, n0, b, z, kt_begin, nkt;
 };
+struct LState {
+  const double *A1, *B1, *A2, *B2;
+  int m0, n0, kt_begin, pad;
+};
 
 template <class CF>
 __device__ __forceinline__ Unit decode_unit(const KParams& p, int u) {
@@ -175,43 +179,57 @@ __global__ void __launch_bounds__(CF::NT, 1) dgemm_kernel(const KParams p) {
   const int g = lane >> 2, q = lane & 3;
   const int G = gridDim.x;
 
-  // ---- load cursor: (unit, k-tile) of the next operand tile to stage; skips units with no k-tiles
-  int lu = blockIdx.x, lkt = 0, lnkt = 0;
+  // ---- load cursor: (unit, k-tile) of the next operand tile to stage; skips units with no k-tiles.
+  // The decoded unit (tile origin, operand base pointers, k range) lives in shared memory, double
+  // buffered, and is rewritten only when the cursor enters a new unit -- the per-k-tile path has no
+  // integer divisions.  Every issue_next() is preceded by a __syncthreads(), which orders the
+  // (thread 0) write of slot s^1 before all reads of it and after all reads of its previous content.
+  __shared__ LState ls[2];
+  int lu = blockIdx.x, lkt = 0, lnkt = 0, lslot = 1;
   auto seek = [&]() {
+    Unit w;
+    w.nkt = 0;
     while (lu < p.units) {
-      lnkt = decode_unit<CF>(p, lu).nkt;
-      if (lnkt > 0) break;
+      w = decode_unit<CF>(p, lu);
+      if (w.nkt > 0) break;
       lu += G;
     }
     lkt = 0;
+    lnkt = w.nkt;
+    lslot ^= 1;
+    if (tid == 0 && lu < p.units) {
+      LState& d = ls[lslot];
+      if (p.table) {
+        const i64* t = p.table + 5 * (i64)w.b;
+        d.A1 = reinterpret_cast<const double*>(t[0]);
+        d.B1 = reinterpret_cast<const double*>(t[1]);
+        d.A2 = reinterpret_cast<const double*>(t[2]);
+        d.B2 = reinterpret_cast<const double*>(t[3]);
+      } else {
+        d.A1 = p.A1 + (i64)w.b * p.sA1;
+        d.B1 = p.B1 + (i64)w.b * p.sB1;
+        d.A2 = p.A2 + (i64)w.b * p.sA2;
+        d.B2 = p.B2 + (i64)w.b * p.sB2;
+      }
+      d.m0 = w.m0;
+      d.n0 = w.n0;
+      d.kt_begin = w.kt_begin;
+    }
   };
   auto issue_next = [&](int stage) {
     if (lu < p.units) {
-      const Unit w = decode_unit<CF>(p, lu);
-      const double *A1, *B1, *A2, *B2;
-      if (p.table) {
-        const i64* t = p.table + 5 * (i64)w.b;
-        A1 = reinterpret_cast<const double*>(t[0]);
-        B1 = reinterpret_cast<const double*>(t[1]);
-        A2 = reinterpret_cast<const double*>(t[2]);
-        B2 = reinterpret_cast<const double*>(t[3]);
-      } else {
-        A1 = p.A1 + (i64)w.b * p.sA1;
-        B1 = p.B1 + (i64)w.b * p.sB1;
-        A2 = p.A2 + (i64)w.b * p.sA2;
-        B2 = p.B2 + (i64)w.b * p.sB2;
-      }
+      const LState& d = ls[lslot];
       double* As = smem + stage * CF::STAGE;
       double* Bs = As + CF::TILE_A;
-      const int kt = w.kt_begin + lkt;
+      const int kt = d.kt_begin + lkt;
       if (kt < p.kt1) {
         const int k0 = kt * BK;
-        load_tile<TA, VEC, CF::BM, CF::NT>(As, A1, p.lda1, w.m0, p.M, k0, p.K1, tid);
-        load_tile<TB, VEC, CF::BN, CF::NT>(Bs, B1, p.ldb1, w.n0, p.N, k0, p.K1, tid);
+        load_tile<TA, VEC, CF::BM, CF::NT>(As, d.A1, p.lda1, d.m0, p.M, k0, p.K1, tid);
+        load_tile<TB, VEC, CF::BN, CF::NT>(Bs, d.B1, p.ldb1, d.n0, p.N, k0, p.K1, tid);
       } else {
         const int k0 = (kt - p.kt1) * BK;
-        load_tile<TA, VEC, CF::BM, CF::NT>(As, A2, p.lda2, w.m0, p.M, k0, p.K2, tid);
-        load_tile<TB, VEC, CF::BN, CF::NT>(Bs, B2, p.ldb2, w.n0, p.N, k0, p.K2, tid);
+        load_tile<TA, VEC, CF::BM, CF::NT>(As, d.A2, p.lda2, d.m0, p.M, k0, p.K2, tid);
+        load_tile<TB, VEC, CF::BN, CF::NT>(Bs, d.B2, p.ldb2, d.n0, p.N, k0, p.K2, tid);
       }
       if (++lkt == lnkt) {
         lu += G;
@@ -223,7 +241,10 @@ __global__ void __launch_bounds__(CF::NT, 1) dgemm_kernel(const KParams p) {
 
   seek();
 #pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) issue_next(s);
+  for (int s = 0; s < STAGES - 1; ++s) {
+    __syncthreads();
+    issue_next(s);
+  }
   int cstage = 0, lstage = STAGES - 1;
 
   for (int cu = blockIdx.x; cu < p.units; cu += G) {
@@ -293,6 +314,242 @@ __global__ void __launch_bounds__(CF::NT, 1) dgemm_kernel(const KParams p) {
   cp_async_wait<0>();
 }
 
+// =====================================================================================================
+// Warp-specialised variant (config 4): 8 consumer warps (32x64 warp tiles, the CfgB geometry) that execute
+// nothing but LDS.64 + DMMA, and 4 producer warps that stage the operand tiles with cp.async and signal
+// per-stage mbarriers (cp.async.mbarrier.arrive).  No __syncthreads in the main loop: a consumer warp only
+// ever waits for "stage s is full", a producer only for "stage s is empty", so the warps of one SM
+// sub-partition drift apart and one warp's bookkeeping hides behind the other's DMMAs (each DMMA holds
+// its warp for 16 cycles anyway).  Consumers keep fragments double-buffered across k-steps and across the
+// full-barrier wait of the next k-tile, so the tensor pipe does not drain at tile boundaries.
+// Registers are re-partitioned with setmaxnreg (producers 64, consumers 216: 128*64 + 256*216 <= 384*168, the CTA's launch allocation -- the pool setmaxnreg draws from).
+// =====================================================================================================
+constexpr int WS_PRODUCER_WARPS = 4;
+constexpr int WS_PRODUCER_THREADS = 32 * WS_PRODUCER_WARPS;
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cp_async(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      "WAIT_%=:\n"
+      " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      " @p bra DONE_%=;\n"
+      " bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+template <int R>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(R)); }
+template <int R>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(R)); }
+
+template <class CF, bool TA, bool TB>
+__device__ __forceinline__ void load_frags(const double* __restrict__ As, const double* __restrict__ Bs, int ks,
+                                           double (&a)[CF::MI], double (&b)[CF::NI], int wm, int wn, int g, int q) {
+#pragma unroll
+  for (int i = 0; i < CF::MI; ++i) {
+    const int r = 8 * (wm + CF::WARPS_M * i) + g;
+    a[i] = TA ? As[(ks * 4 + q) * (CF::BM + 4) + r] : As[r * LDK + ks * 4 + q];
+  }
+#pragma unroll
+  for (int j = 0; j < CF::NI; ++j) {
+    const int r = 8 * (wn + CF::WARPS_N * j) + g;
+    b[j] = TB ? Bs[(ks * 4 + q) * (CF::BN + 4) + r] : Bs[r * LDK + ks * 4 + q];
+  }
+}
+
+template <class CF, bool CHECK>
+__device__ __forceinline__ void mma_frags(double (&acc)[CF::MI][CF::NI][2], const double (&a)[CF::MI],
+                                          const double (&b)[CF::NI], uint32_t mmask, uint32_t nmask) {
+#pragma unroll
+  for (int i = 0; i < CF::MI; ++i) {
+    if (CHECK && !((mmask >> i) & 1u)) continue;
+#pragma unroll
+    for (int j = 0; j < CF::NI; ++j) {
+      if (CHECK && !((nmask >> j) & 1u)) continue;
+      dmma(acc[i][j], a[i], b[j]);
+    }
+  }
+}
+
+template <class CF, bool TA, bool TB, int VEC>
+__global__ void __launch_bounds__(CF::NT + WS_PRODUCER_THREADS, 1) dgemm_ws_kernel(const KParams p) {
+  extern __shared__ __align__(16) double smem[];
+  constexpr int MI = CF::MI, NI = CF::NI;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * CF::STAGE);
+  uint64_t* empty_bar = full_bar + STAGES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int G = gridDim.x;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar + s, WS_PRODUCER_THREADS);
+      mbar_init(empty_bar + s, CF::NT / 32);
+    }
+  }
+  __syncthreads();
+
+  if (warp >= CF::NT / 32) {
+    // ================================ producers ================================
+    reg_dec<64>();
+    const int ptid = tid - CF::NT;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int u = blockIdx.x; u < p.units; u += G) {
+      const Unit w = decode_unit<CF>(p, u);
+      if (w.nkt == 0) continue;
+      const double *A1, *B1, *A2, *B2;
+      if (p.table) {
+        const i64* t = p.table + 5 * (i64)w.b;
+        A1 = reinterpret_cast<const double*>(t[0]);
+        B1 = reinterpret_cast<const double*>(t[1]);
+        A2 = reinterpret_cast<const double*>(t[2]);
+        B2 = reinterpret_cast<const double*>(t[3]);
+      } else {
+        A1 = p.A1 + (i64)w.b * p.sA1;
+        B1 = p.B1 + (i64)w.b * p.sB1;
+        A2 = p.A2 + (i64)w.b * p.sA2;
+        B2 = p.B2 + (i64)w.b * p.sB2;
+      }
+      for (int t = 0; t < w.nkt; ++t) {
+        mbar_wait(empty_bar + stage, phase ^ 1u);      // slot free (passes immediately on the first lap)
+        double* As = smem + stage * CF::STAGE;
+        double* Bs = As + CF::TILE_A;
+        const int kt = w.kt_begin + t;
+        if (kt < p.kt1) {
+          const int k0 = kt * BK;
+          load_tile<TA, VEC, CF::BM, WS_PRODUCER_THREADS>(As, A1, p.lda1, w.m0, p.M, k0, p.K1, ptid);
+          load_tile<TB, VEC, CF::BN, WS_PRODUCER_THREADS>(Bs, B1, p.ldb1, w.n0, p.N, k0, p.K1, ptid);
+        } else {
+          const int k0 = (kt - p.kt1) * BK;
+          load_tile<TA, VEC, CF::BM, WS_PRODUCER_THREADS>(As, A2, p.lda2, w.m0, p.M, k0, p.K2, ptid);
+          load_tile<TB, VEC, CF::BN, WS_PRODUCER_THREADS>(Bs, B2, p.ldb2, w.n0, p.N, k0, p.K2, ptid);
+        }
+        mbar_arrive_cp_async(full_bar + stage);         // fires when this thread's copies have landed
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+    cp_async_wait<0>();
+    return;
+  }
+
+  // ================================ consumers ================================
+  reg_inc<216>();
+  const int wn = warp % CF::WARPS_N, wm = warp / CF::WARPS_N;
+  const int g = lane >> 2, q = lane & 3;
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int cu = blockIdx.x; cu < p.units; cu += G) {
+    const Unit w = decode_unit<CF>(p, cu);
+    uint32_t mmask = 0, nmask = 0;
+#pragma unroll
+    for (int i = 0; i < MI; ++i) mmask |= (w.m0 + 8 * (wm + CF::WARPS_M * i) < p.M) ? (1u << i) : 0u;
+#pragma unroll
+    for (int j = 0; j < NI; ++j) nmask |= (w.n0 + 8 * (wn + CF::WARPS_N * j) < p.N) ? (1u << j) : 0u;
+    const bool full = (w.m0 + CF::BM <= p.M) && (w.n0 + CF::BN <= p.N);
+
+    double acc[MI][NI][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+      for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    double a0[MI], b0[NI], a1[MI], b1[NI];
+    if (w.nkt > 0) {
+      mbar_wait(full_bar + stage, phase);
+      load_frags<CF, TA, TB>(smem + stage * CF::STAGE, smem + stage * CF::STAGE + CF::TILE_A, 0, a0, b0, wm, wn, g, q);
+    }
+    for (int t = 0; t < w.nkt; ++t) {
+      const double* As = smem + stage * CF::STAGE;
+      const double* Bs = As + CF::TILE_A;
+      // ks = 0: prefetch ks = 1
+      load_frags<CF, TA, TB>(As, Bs, 1, a1, b1, wm, wn, g, q);
+      if (full) mma_frags<CF, false>(acc, a0, b0, mmask, nmask); else mma_frags<CF, true>(acc, a0, b0, mmask, nmask);
+      // ks = 1: prefetch ks = 2
+      load_frags<CF, TA, TB>(As, Bs, 2, a0, b0, wm, wn, g, q);
+      if (full) mma_frags<CF, false>(acc, a1, b1, mmask, nmask); else mma_frags<CF, true>(acc, a1, b1, mmask, nmask);
+      // ks = 2: prefetch ks = 3
+      load_frags<CF, TA, TB>(As, Bs, 3, a1, b1, wm, wn, g, q);
+      if (full) mma_frags<CF, false>(acc, a0, b0, mmask, nmask); else mma_frags<CF, true>(acc, a0, b0, mmask, nmask);
+      // ks = 3: prefetch ks = 0 of the next k-tile of this unit (its stage must be full first)
+      int nstage = stage + 1;
+      uint32_t nphase = phase;
+      if (nstage == STAGES) { nstage = 0; nphase ^= 1u; }
+      if (t + 1 < w.nkt) {
+        mbar_wait(full_bar + nstage, nphase);
+        load_frags<CF, TA, TB>(smem + nstage * CF::STAGE, smem + nstage * CF::STAGE + CF::TILE_A, 0, a0, b0, wm, wn,
+                               g, q);
+      }
+      if (full) mma_frags<CF, false>(acc, a1, b1, mmask, nmask); else mma_frags<CF, true>(acc, a1, b1, mmask, nmask);
+      // every shared read of `stage` has been consumed by a DMMA above: hand the slot back
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar + stage);
+      stage = nstage;
+      phase = nphase;
+    }
+
+    // ---- epilogue (same as the plain kernel)
+    const bool split = p.ksplit > 1;
+    double* C;
+    if (split) C = p.ws + ((i64)w.z * p.batch + w.b) * (i64)p.M * p.N;
+    else if (p.table) C = reinterpret_cast<double*>(p.table[5 * (i64)w.b + 4]);
+    else C = p.C + (i64)w.b * p.sC;
+    const i64 ldo = split ? (i64)p.N : p.ldc;
+    const double alpha = split ? 1.0 : p.alpha, beta = split ? 0.0 : p.beta;
+    const bool vec = split ? ((p.N & 1) == 0 && (((i64)p.M * p.N) & 1) == 0) : (p.cvec != 0);
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+      const int row = w.m0 + 8 * (wm + CF::WARPS_M * i) + g;
+      if (row >= p.M) continue;
+#pragma unroll
+      for (int j = 0; j < NI; ++j) {
+        const int col = w.n0 + 8 * (wn + CF::WARPS_N * j) + 2 * q;
+        if (col >= p.N) continue;
+        double* c = C + (i64)row * ldo + col;
+        double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
+        if (vec && col + 1 < p.N) {
+          if (beta != 0.0) {
+            const double2 o = *reinterpret_cast<const double2*>(c);
+            v0 += beta * o.x;
+            v1 += beta * o.y;
+          }
+          *reinterpret_cast<double2*>(c) = make_double2(v0, v1);
+        } else {
+          if (beta != 0.0) v0 += beta * c[0];
+          c[0] = v0;
+          if (col + 1 < p.N) {
+            if (beta != 0.0) v1 += beta * c[1];
+            c[1] = v1;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <class CF, bool TA, bool TB, int VEC>
+static int launch_ws(const KParams& p, int grid, cudaStream_t st) {
+  constexpr int SMEM = CF::SMEM_BYTES + 2 * STAGES * (int)sizeof(uint64_t);
+  static bool configured = false;
+  if (!configured) {
+    B200CC_CUDA_OK(cudaFuncSetAttribute(dgemm_ws_kernel<CF, TA, TB, VEC>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  dgemm_ws_kernel<CF, TA, TB, VEC><<<grid, CF::NT + WS_PRODUCER_THREADS, SMEM, st>>>(p);
+  return check_launch("dgemm_ws_kernel");
+}
+
 // C[b] = alpha * sum_z ws[z][b] + beta * C[b]
 __global__ void splitk_reduce_kernel(const double* __restrict__ ws, int ksplit, int batch, int M, int N,
                                      double alpha, double beta, double* C, i64 ldc, i64 sC,
@@ -322,7 +579,7 @@ static int launch(const KParams& p, int grid, cudaStream_t st) {
   return check_launch("dgemm_kernel");
 }
 
-template <class CF>
+template <class CF, bool WS>
 static int dispatch(KParams& p, int ta, int tb, bool v2, cudaStream_t st) {
   p.tiles_m = (p.M + CF::BM - 1) / CF::BM;
   p.tiles_n = (p.N + CF::BN - 1) / CF::BN;
@@ -335,11 +592,15 @@ static int dispatch(KParams& p, int ta, int tb, bool v2, cudaStream_t st) {
   p.nfast = p.tiles_n < p.tiles_m ? 1 : 0;
   const int nsm = sm_count();
   const int grid = units < nsm ? (int)units : nsm;
-#define B200CC_GO(TA, TB) (v2 ? launch<CF, TA, TB, 2>(p, grid, st) : launch<CF, TA, TB, 1>(p, grid, st))
-  if (!ta && !tb) return B200CC_GO(false, false);
-  if (!ta && tb) return B200CC_GO(false, true);
-  if (ta && !tb) return B200CC_GO(true, false);
-  return B200CC_GO(true, true);
+#define B200CC_GO(TA, TB)                                                                         \
+  do {                                                                                            \
+    if constexpr (WS) return v2 ? launch_ws<CF, TA, TB, 2>(p, grid, st) : launch_ws<CF, TA, TB, 1>(p, grid, st); \
+    else return v2 ? launch<CF, TA, TB, 2>(p, grid, st) : launch<CF, TA, TB, 1>(p, grid, st);    \
+  } while (0)
+  if (!ta && !tb) B200CC_GO(false, false);
+  if (!ta && tb) B200CC_GO(false, true);
+  if (ta && !tb) B200CC_GO(true, false);
+  B200CC_GO(true, true);
 #undef B200CC_GO
 }
 
@@ -412,14 +673,17 @@ extern "C" int b200cc_dgemm(const b200cc_gemm_desc* d, void* stream) {
   // tile configuration: 0 = auto
   int cfg = d->config;
   if (cfg == 0) {
-    cfg = 1;
+    // warp-specialised kernels; the 80-row tile when it wastes clearly less of a ragged M (M = o^2 = 400, ...)
+    cfg = 4;
     const double e128 = eff_extent(d->M, 128, 4), e80 = eff_extent(d->M, 80, 2);
-    if (d->M >= 80 && e80 < 0.93 * e128) cfg = 3;
+    if (d->M >= 80 && e80 < 0.93 * e128) cfg = 5;
   }
   int rc;
-  if (cfg == 1) rc = dispatch<CfgA>(p, ta, tb, v2, st);
-  else if (cfg == 2) rc = dispatch<CfgB>(p, ta, tb, v2, st);
-  else if (cfg == 3) rc = dispatch<CfgC>(p, ta, tb, v2, st);
+  if (cfg == 1) rc = dispatch<CfgA, false>(p, ta, tb, v2, st);
+  else if (cfg == 2) rc = dispatch<CfgB, false>(p, ta, tb, v2, st);
+  else if (cfg == 3) rc = dispatch<CfgC, false>(p, ta, tb, v2, st);
+  else if (cfg == 4) rc = dispatch<CfgB, true>(p, ta, tb, v2, st);
+  else if (cfg == 5) rc = dispatch<CfgC, true>(p, ta, tb, v2, st);
   else { set_error("b200cc_dgemm: unknown tile config %d", cfg); return 1; }
   if (rc) return rc;
   if (ksplit > 1) {

@@ -7,6 +7,7 @@ No arithmetic is done in torch/numpy on this path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -14,6 +15,8 @@ from . import _lib
 from ._lib import GemmDesc, B200ccError, i64
 
 NSM = 148                   # B200
+# tile-config override for experiments (0 = library heuristic); see b200cc_gemm_desc.config
+DEFAULT_GEMM_CONFIG = int(os.environ.get("B200CC_GEMM_CONFIG", "0"))
 F64 = torch.float64
 
 
@@ -67,7 +70,7 @@ def dgemm(M, N, K, A, lda, transA, B, ldb, transB, Cmat, ldc, alpha=1.0, beta=0.
     if ksplit is None:
         ksplit = auto_ksplit(M, N, K + K2, batch)
     d.ksplit = int(ksplit)
-    d.config = int(config)
+    d.config = int(config) if config else DEFAULT_GEMM_CONFIG
     ws = None
     if ksplit > 1:
         dev = _dev(table if table is not None else Cmat)

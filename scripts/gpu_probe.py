@@ -15,7 +15,7 @@ from pycc_b200 import kernels as K   # noqa: E402
 
 DEV = torch.device("cuda:0")
 OUT = {}
-CONFIGS = (1, 2, 3)
+CONFIGS = tuple(int(x) for x in os.environ.get("PROBE_CONFIGS", "2,4").split(","))
 
 
 def timeit(fn, warm=2, reps=5):
