@@ -60,9 +60,9 @@ typedef struct {
   int table_align16;               /* table mode: caller vouches every address is 16-byte aligned */
   int ksplit;
   double* workspace;
-  int config;                      /* CTA tile: 0 auto, 1 = 128x128/16 warps, 2 = 128x128/8 warps, 3 = 80x128/8 warps,
-                                      4 = 128x128 warp-specialised (8 DMMA warps + 4 cp.async producer warps, mbarriers),
-                                      5 = 80x128 warp-specialised */
+  int config;                      /* kernel: 0 auto (4 or 5 by a cost model); 2 = plain 128x128 multistage kernel (8 warps,
+                                      __syncthreads pipeline; kept as a cross-check); 4 = 128x128 warp-specialised
+                                      (8 DMMA warps + 4 cp.async producer warps, mbarrier pipeline); 5 = 80x128 ditto */
 } b200cc_gemm_desc;
 
 int b200cc_dgemm(const b200cc_gemm_desc* d, void* stream);

@@ -26,6 +26,7 @@ from . import kernels as K
 from ._lib import B200ccError
 
 F64 = torch.float64
+_QCACHE = {}
 
 # per term q: (occupied index of the <mb|ef> slab and of the t2[x] slab,
 #              (p,q) of t2[p,q] in the particle GEMM, (p,q) of Y[p,q] in the hole GEMM)
@@ -68,14 +69,18 @@ class TriplesEngine:
                 free, _ = torch.cuda.mem_get_info(self.dev)
                 q_bytes = max(per, min(q_bytes * 2, int(free * 0.5)))
         self.nb_max = int(max(1, min(q_bytes // max(per, 1), 65535 // 6, 4096)))
-        self._Q = None
 
     def qbuf(self, nb):
+        """The Q workspace ([nb][6][v^3] doubles) is kept per device across engines (grow-only), so repeated
+        (T) evaluations do not pay a multi-GB cudaMalloc each."""
         need = nb * 6 * self.nv ** 3
-        if self._Q is None or self._Q.numel() < need:
-            self._Q = None
-            self._Q = torch.empty(need, dtype=F64, device=self.dev)
-        return self._Q
+        buf = _QCACHE.get(self.dev)
+        if buf is None or buf.numel() < need:
+            _QCACHE.pop(self.dev, None)
+            buf = None
+            buf = torch.empty(need, dtype=F64, device=self.dev)
+            _QCACHE[self.dev] = buf
+        return buf
 
     def table(self, trip, Q):
         """int64 [6*nb, 5] device table of {A1, B1, A2, B2, C} addresses for b200cc_dgemm."""

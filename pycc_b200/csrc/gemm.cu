@@ -31,7 +31,6 @@ struct Cfg {
   static constexpr int STAGE = TILE_A + TILE_B;
   static constexpr int SMEM_BYTES = STAGES * STAGE * (int)sizeof(double);
 };
-typedef Cfg<4, 4, 4, 4> CfgA;  // 128 x 128, 16 warps (4 per sub-partition)
 typedef Cfg<4, 2, 4, 8> CfgB;  // 128 x 128,  8 warps
 typedef Cfg<2, 4, 5, 4> CfgC;  //  80 x 128,  8 warps (M = o^2 = 400, 1600, ... divide by 80)
 
@@ -353,6 +352,12 @@ __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.al
 template <int R>
 __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(R)); }
 
+// Ragged tiles: a predicated-off DMMA still occupies the tensor pipe for its 16 cycles (measured with ncu:
+// pipe-active time of the N = 280 (T) GEMM equalled 3 FULL N tiles), so out-of-range fragments must be
+// skipped by real, warp-uniform control flow.  In-range fragments of a warp form a prefix (fragments are
+// interleaved over the warps); `code` selects one of 8 straight-line DMMA blocks:
+//   rows  : all MI fragments, or the first ceil(MI/2)         (code >> 2)
+//   cols  : the first 1/4, 2/4, 3/4 or 4/4 of the NI fragments (code & 3)
 template <class CF, bool TA, bool TB>
 __device__ __forceinline__ void load_frags(const double* __restrict__ As, const double* __restrict__ Bs, int ks,
                                            double (&a)[CF::MI], double (&b)[CF::NI], int wm, int wn, int g, int q) {
@@ -368,17 +373,88 @@ __device__ __forceinline__ void load_frags(const double* __restrict__ As, const 
   }
 }
 
-template <class CF, bool CHECK>
-__device__ __forceinline__ void mma_frags(double (&acc)[CF::MI][CF::NI][2], const double (&a)[CF::MI],
-                                          const double (&b)[CF::NI], uint32_t mmask, uint32_t nmask) {
+template <class CF, int MC, int NC>
+__device__ __forceinline__ void mma_block(double (&acc)[CF::MI][CF::NI][2], const double (&a)[CF::MI],
+                                          const double (&b)[CF::NI]) {
 #pragma unroll
-  for (int i = 0; i < CF::MI; ++i) {
-    if (CHECK && !((mmask >> i) & 1u)) continue;
+  for (int i = 0; i < MC; ++i)
 #pragma unroll
-    for (int j = 0; j < CF::NI; ++j) {
-      if (CHECK && !((nmask >> j) & 1u)) continue;
-      dmma(acc[i][j], a[i], b[j]);
-    }
+    for (int j = 0; j < NC; ++j) dmma(acc[i][j], a[i], b[j]);
+}
+
+template <class CF>
+__device__ __forceinline__ void mma_select(double (&acc)[CF::MI][CF::NI][2], const double (&a)[CF::MI],
+                                           const double (&b)[CF::NI], int code) {
+  constexpr int MI = CF::MI, MH = (CF::MI + 1) / 2, NQ = CF::NI / 4;
+  static_assert(CF::NI % 4 == 0, "NI must be a multiple of 4");
+  switch (code) {
+    case 3: mma_block<CF, MI, 4 * NQ>(acc, a, b); break;   // full tile: the hot path
+    case 0: mma_block<CF, MI, 1 * NQ>(acc, a, b); break;
+    case 1: mma_block<CF, MI, 2 * NQ>(acc, a, b); break;
+    case 2: mma_block<CF, MI, 3 * NQ>(acc, a, b); break;
+    case 4: mma_block<CF, MH, 1 * NQ>(acc, a, b); break;
+    case 5: mma_block<CF, MH, 2 * NQ>(acc, a, b); break;
+    case 6: mma_block<CF, MH, 3 * NQ>(acc, a, b); break;
+    default: mma_block<CF, MH, 4 * NQ>(acc, a, b); break;
+  }
+}
+
+// The k-loop of one work unit for one consumer warp.  Fragments are double-buffered across the four
+// k-steps of a tile and across the full-barrier wait of the next tile.
+template <class CF, bool TA, bool TB>
+__device__ __forceinline__ void consume_unit(double (&acc)[CF::MI][CF::NI][2], const double* smem,
+                                             uint64_t* full_bar, uint64_t* empty_bar, int& stage, uint32_t& phase,
+                                             int nkt, int code, int wm, int wn, int g, int q, int lane) {
+  double a0[CF::MI], b0[CF::NI], a1[CF::MI], b1[CF::NI];
+  if (nkt > 0) {
+    mbar_wait(full_bar + stage, phase);
+    load_frags<CF, TA, TB>(smem + stage * CF::STAGE, smem + stage * CF::STAGE + CF::TILE_A, 0, a0, b0, wm, wn, g, q);
+  }
+#define B200CC_KLOOP(MMA)                                                                              \
+  for (int t = 0; t < nkt; ++t) {                                                                      \
+    const double* As = smem + stage * CF::STAGE;                                                       \
+    const double* Bs = As + CF::TILE_A;                                                                \
+    load_frags<CF, TA, TB>(As, Bs, 1, a1, b1, wm, wn, g, q);                                           \
+    MMA(a0, b0);                                                                                       \
+    load_frags<CF, TA, TB>(As, Bs, 2, a0, b0, wm, wn, g, q);                                           \
+    MMA(a1, b1);                                                                                       \
+    load_frags<CF, TA, TB>(As, Bs, 3, a1, b1, wm, wn, g, q);                                           \
+    MMA(a0, b0);                                                                                       \
+    int nstage = stage + 1;                                                                            \
+    uint32_t nphase = phase;                                                                           \
+    if (nstage == STAGES) { nstage = 0; nphase ^= 1u; }                                                \
+    if (t + 1 < nkt) {                                                                                 \
+      mbar_wait(full_bar + nstage, nphase);                                                            \
+      load_frags<CF, TA, TB>(smem + nstage * CF::STAGE, smem + nstage * CF::STAGE + CF::TILE_A, 0, a0, b0, wm, \
+                             wn, g, q);                                                                \
+    }                                                                                                  \
+    MMA(a1, b1);                                                                                       \
+    /* every shared read of `stage` has been consumed by a DMMA above: hand the slot back */           \
+    __syncwarp();                                                                                      \
+    if (lane == 0) mbar_arrive(empty_bar + stage);                                                     \
+    stage = nstage;                                                                                    \
+    phase = nphase;                                                                                    \
+  }
+#define B200CC_MMA_FULL(A_, B_) mma_block<CF, CF::MI, CF::NI>(acc, A_, B_)
+#define B200CC_MMA_SEL(A_, B_) mma_select<CF>(acc, A_, B_, code)
+  if (code == 3) {
+    B200CC_KLOOP(B200CC_MMA_FULL)      // full tile: branch-free hot loop
+  } else {
+    B200CC_KLOOP(B200CC_MMA_SEL)
+  }
+#undef B200CC_KLOOP
+#undef B200CC_MMA_FULL
+#undef B200CC_MMA_SEL
+}
+
+// a warp with no in-range fragment in this unit still has to keep the barriers moving
+__device__ __forceinline__ void idle_unit(uint64_t* full_bar, uint64_t* empty_bar, int& stage, uint32_t& phase,
+                                          int nkt, int lane) {
+  for (int t = 0; t < nkt; ++t) {
+    mbar_wait(full_bar + stage, phase);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_bar + stage);
+    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
   }
 }
 
@@ -451,12 +527,12 @@ __global__ void __launch_bounds__(CF::NT + WS_PRODUCER_THREADS, 1) dgemm_ws_kern
   uint32_t phase = 0;
   for (int cu = blockIdx.x; cu < p.units; cu += G) {
     const Unit w = decode_unit<CF>(p, cu);
-    uint32_t mmask = 0, nmask = 0;
+    // in-range fragments of this warp form a prefix (fragments are interleaved over the warps)
+    int mc = 0, nc = 0;
 #pragma unroll
-    for (int i = 0; i < MI; ++i) mmask |= (w.m0 + 8 * (wm + CF::WARPS_M * i) < p.M) ? (1u << i) : 0u;
+    for (int i = 0; i < MI; ++i) mc += (w.m0 + 8 * (wm + CF::WARPS_M * i) < p.M) ? 1 : 0;
 #pragma unroll
-    for (int j = 0; j < NI; ++j) nmask |= (w.n0 + 8 * (wn + CF::WARPS_N * j) < p.N) ? (1u << j) : 0u;
-    const bool full = (w.m0 + CF::BM <= p.M) && (w.n0 + CF::BN <= p.N);
+    for (int j = 0; j < NI; ++j) nc += (w.n0 + 8 * (wn + CF::WARPS_N * j) < p.N) ? 1 : 0;
 
     double acc[MI][NI][2];
 #pragma unroll
@@ -464,38 +540,12 @@ __global__ void __launch_bounds__(CF::NT + WS_PRODUCER_THREADS, 1) dgemm_ws_kern
 #pragma unroll
       for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    double a0[MI], b0[NI], a1[MI], b1[NI];
-    if (w.nkt > 0) {
-      mbar_wait(full_bar + stage, phase);
-      load_frags<CF, TA, TB>(smem + stage * CF::STAGE, smem + stage * CF::STAGE + CF::TILE_A, 0, a0, b0, wm, wn, g, q);
-    }
-    for (int t = 0; t < w.nkt; ++t) {
-      const double* As = smem + stage * CF::STAGE;
-      const double* Bs = As + CF::TILE_A;
-      // ks = 0: prefetch ks = 1
-      load_frags<CF, TA, TB>(As, Bs, 1, a1, b1, wm, wn, g, q);
-      if (full) mma_frags<CF, false>(acc, a0, b0, mmask, nmask); else mma_frags<CF, true>(acc, a0, b0, mmask, nmask);
-      // ks = 1: prefetch ks = 2
-      load_frags<CF, TA, TB>(As, Bs, 2, a0, b0, wm, wn, g, q);
-      if (full) mma_frags<CF, false>(acc, a1, b1, mmask, nmask); else mma_frags<CF, true>(acc, a1, b1, mmask, nmask);
-      // ks = 2: prefetch ks = 3
-      load_frags<CF, TA, TB>(As, Bs, 3, a1, b1, wm, wn, g, q);
-      if (full) mma_frags<CF, false>(acc, a0, b0, mmask, nmask); else mma_frags<CF, true>(acc, a0, b0, mmask, nmask);
-      // ks = 3: prefetch ks = 0 of the next k-tile of this unit (its stage must be full first)
-      int nstage = stage + 1;
-      uint32_t nphase = phase;
-      if (nstage == STAGES) { nstage = 0; nphase ^= 1u; }
-      if (t + 1 < w.nkt) {
-        mbar_wait(full_bar + nstage, nphase);
-        load_frags<CF, TA, TB>(smem + nstage * CF::STAGE, smem + nstage * CF::STAGE + CF::TILE_A, 0, a0, b0, wm, wn,
-                               g, q);
-      }
-      if (full) mma_frags<CF, false>(acc, a1, b1, mmask, nmask); else mma_frags<CF, true>(acc, a1, b1, mmask, nmask);
-      // every shared read of `stage` has been consumed by a DMMA above: hand the slot back
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty_bar + stage);
-      stage = nstage;
-      phase = nphase;
+    if (mc == 0 || nc == 0) {
+      idle_unit(full_bar, empty_bar, stage, phase, w.nkt, lane);
+    } else {
+      constexpr int NQ = NI / 4, MH = (MI + 1) / 2;
+      const int code = (mc <= MH ? 4 : 0) + (nc + NQ - 1) / NQ - 1;
+      consume_unit<CF, TA, TB>(acc, smem, full_bar, empty_bar, stage, phase, w.nkt, code, wm, wn, g, q, lane);
     }
 
     // ---- epilogue (same as the plain kernel)
@@ -673,15 +723,21 @@ extern "C" int b200cc_dgemm(const b200cc_gemm_desc* d, void* stream) {
   // tile configuration: 0 = auto
   int cfg = d->config;
   if (cfg == 0) {
-    // warp-specialised kernels; the 80-row tile when it wastes clearly less of a ragged M (M = o^2 = 400, ...)
-    cfg = 4;
-    const double e128 = eff_extent(d->M, 128, 4), e80 = eff_extent(d->M, 80, 2);
-    if (d->M >= 80 && e80 < 0.93 * e128) cfg = 5;
+    // Warp-specialised kernels; pick the CTA tile by a small cost model: persistent CTAs do
+    // ceil(units / #SM) rounds of the average unit cost (ragged edges counted at fragment granularity).
+    // The 80x128 tile wins when M is ragged for 128 (M = o^2 = 400) or when it fills the last round better.
+    const int nsm = sm_count();
+    auto cost = [&](int bm, int wm, int bn, int wn, double eff) {
+      const double area = eff_extent(d->M, bm, wm) * eff_extent(d->N, bn, wn);
+      const double units = (double)((d->M + bm - 1) / bm) * ((d->N + bn - 1) / bn) * d->batch * ksplit;
+      const double rounds = (double)((i64)((units + nsm - 1) / nsm));
+      return rounds * (area * d->batch * ksplit / units) / eff;
+    };
+    const double c4 = cost(128, 4, 128, 2, 1.0), c5 = cost(80, 2, 128, 4, 0.97);
+    cfg = (d->M >= 80 && c5 < 0.97 * c4) ? 5 : 4;
   }
   int rc;
-  if (cfg == 1) rc = dispatch<CfgA, false>(p, ta, tb, v2, st);
-  else if (cfg == 2) rc = dispatch<CfgB, false>(p, ta, tb, v2, st);
-  else if (cfg == 3) rc = dispatch<CfgC, false>(p, ta, tb, v2, st);
+  if (cfg == 2) rc = dispatch<CfgB, false>(p, ta, tb, v2, st);
   else if (cfg == 4) rc = dispatch<CfgB, true>(p, ta, tb, v2, st);
   else if (cfg == 5) rc = dispatch<CfgC, true>(p, ta, tb, v2, st);
   else { set_error("b200cc_dgemm: unknown tile config %d", cfg); return 1; }

@@ -133,7 +133,7 @@ class BlockHamiltonian:
         return cls(F, blocks, no, nfzc, device)
 
     @classmethod
-    def from_factor(cls, syn, device="cuda", a_range=None, chunk_bytes=4 << 30):
+    def from_factor(cls, syn, device="cuda", a_range=None, chunk_bytes=4 << 30, names=STORED):
         """From a factorised synthetic problem (pycc_b200.synthetic): every block is contracted on the
         device with the package's own GEMM, <pq|rs> = scale * sum_P B[P,p,r] B[P,q,s]; `vvvv` in row
         chunks so no temporary larger than ``chunk_bytes`` exists."""
@@ -143,7 +143,7 @@ class BlockHamiltonian:
         ct = Contractor()
         sl = {"o": slice(0, no), "v": slice(no, no + nv)}
         blocks = {}
-        for name in STORED:
+        for name in names:
             p, q, r, s = (sl[c] for c in name)
             if name != "vvvv":
                 blocks[name] = ct("Ppr,Pqs->pqrs", B[:, p, r], B[:, q, s], alpha=syn.scale)

@@ -37,12 +37,22 @@ def _dev(x):
 
 
 def auto_ksplit(M, N, K, batch):
-    """Split-K factor for small-output / long-K shapes (Fae, Fmi, r1 terms, Wmnij): aim at ~2 CTAs per SM."""
+    """Split-K factor.  The GEMM is persistent (one CTA per SM doing ceil(units/148) rounds), so splitting K
+    pays when the output has too few tiles to fill the SMs (Fae, Fmi, r1 terms) or when it fills the last
+    round badly (Wmnij: 169 tiles = 2 rounds at 57 %); each split costs an extra M*N partial write + read."""
     tiles = ((M + 127) // 128) * ((N + 127) // 128) * batch
     kt = (K + 15) // 16
-    if tiles >= NSM or kt < 64:
+    if kt < 64 or tiles >= 8 * NSM:
         return 1
-    return int(max(1, min((2 * NSM + tiles - 1) // tiles, kt // 16, 256)))
+    best, best_t = 1, None
+    for s in (1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 24, 32, 48, 64, 96, 128, 192, 256):
+        if s > 1 and kt // s < 32:
+            break
+        rounds = -(-tiles * s // NSM)
+        t = rounds * (kt / s + 6.0)            # k-tiles per round + per-unit prologue/epilogue/partials
+        if best_t is None or t < 0.93 * best_t:
+            best, best_t = s, t
+    return best
 
 
 def dgemm(M, N, K, A, lda, transA, B, ldb, transB, Cmat, ldc, alpha=1.0, beta=0.0,
