@@ -12,6 +12,14 @@ from .contract import Contractor
 from .exceptions import InvalidKeywordError, PyCCError
 
 
+def _current_device():
+    """The reference pins 'cuda:0' (device.py:62,142); with one process per GPU the compute device is the
+    process's CURRENT CUDA device (torch.cuda.set_device(LOCAL_RANK)), which is cuda:0 in the single-GPU case."""
+    if torch.cuda.is_available():
+        return torch.device('cuda', torch.cuda.current_device())
+    return torch.device('cpu')
+
+
 class ContractionBackend(object):
     """``contract(subscripts, *operands)`` on the B200 kernels (reference: device.py:64-86).
 
@@ -24,8 +32,7 @@ class ContractionBackend(object):
         if device != 'GPU':
             raise PyCCError("pycc_b200 only implements device='GPU' (use pycc itself for the CPU path)")
         self.device = device
-        self.device1 = device1 if device1 is not None else torch.device(
-            'cuda:0' if torch.cuda.is_available() else 'cpu')
+        self.device1 = device1 if device1 is not None else _current_device()
         self.engine = Contractor()
 
     def _resident(self, x):
@@ -63,7 +70,7 @@ class DeviceManager(object):
         if self.precision != 'DP':
             raise NotImplementedError("precision='SP' (float32 / TF32-split) is not implemented yet; "
                                       "the FP64 DMMA path is precision='DP'")
-        self.device1 = torch.device('cuda:0' if torch.cuda.is_available() else 'cpu')
+        self.device1 = _current_device()
         self.device0 = self.device1
         self.real_dtype = np.float64
         self._torch_dtype = torch.float64

@@ -1,0 +1,55 @@
+"""N > 1 on real GPUs (NCCL): skipped unless at least two CUDA devices are visible.  Same checks as
+tests/test_multirank.py (gloo + numpy double), but through libb200cc.so on each rank's own GPU."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import pycc_b200
+        from pycc_b200.parallel import Comm
+        from pycc_b200.synthetic import make_synthetic, blocks_from_factor
+        from oracle import ccsd_oracle as co, triples_oracle as to
+        no, nv = 6, 26
+        syn = make_synthetic(no, nv, seed=3, fock_noise=0.01)
+        comm = Comm()
+        cc = pycc_b200.ccwfn(syn, model="CCSD(T)", device="GPU", quiet=True, comm=comm)
+        e = float(cc.solve_cc(1e-11, 1e-11))
+        b = blocks_from_factor(syn)
+        P = co.Problem(b, syn.F, no)
+        e_ref, t1, t2, trace = co.solve_cc(P, 1e-11, 1e-11)
+        et = to.t_tjl(t1, t2, syn.F, b["ovvv"], b["ooov"], b["oovv"])
+        q.put((rank, abs(e - (e_ref + et)), float(np.abs(cc.t2.cpu().numpy() - t2).max()), len(cc.trace), len(trace)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nccl_ranks_match_oracle():
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 200
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, de, dt, n, nref in res:
+        assert de < 1e-10 and dt < 1e-9 and n == nref, (rank, de, dt, n, nref)
