@@ -164,6 +164,8 @@ def main():
     comm = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # keep stdout to the single JSON line: NCCL_DEBUG=VERSION/INFO print there
+        os.environ["NCCL_DEBUG"] = os.environ.get("B200CC_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
         comm = Comm()
     o, v = args.o, args.v
