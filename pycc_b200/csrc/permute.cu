@@ -21,13 +21,30 @@ struct PermParams {
   i64 tiles_x, tiles_y, outer;
 };
 
+// One CTA per "row" (all dims but the last, grid-stride), threads along the last dimension: the 64-bit
+// div/mod index decode happens once per row per thread instead of once per element.
 __global__ void __launch_bounds__(256) permute_rowcopy_kernel(const PermParams p, const double* __restrict__ in,
                                                               double* __restrict__ out) {
-  for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < p.total; e += (i64)gridDim.x * blockDim.x) {
-    i64 r = e, oi = 0, oo = 0;
+  const i64 n_last = p.shape[p.rank - 1];
+  const i64 si_l = p.si[p.rank - 1], so_l = p.so[p.rank - 1];
+  if (p.rank == 1) {   // plain strided vector: grid-stride over the elements
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < n_last; e += (i64)gridDim.x * blockDim.x) {
+      const double v = p.alpha * in[e * si_l];
+      out[e * so_l] = (p.beta != 0.0) ? v + p.beta * out[e * so_l] : v;
+    }
+    return;
+  }
+  const i64 rows = p.total / n_last;
+  // rows are processed in chunks so that short rows still fill the CTA
+  const int rows_per_cta = n_last >= 256 ? 1 : (int)(256 / n_last);
+  const int sub = threadIdx.x / (int)(n_last >= 256 ? 256 : n_last);      // which row of the chunk
+  const i64 lane0 = n_last >= 256 ? threadIdx.x : threadIdx.x % n_last;
+  if (sub >= rows_per_cta) return;
+  for (i64 row = (i64)blockIdx.x * rows_per_cta + sub; row < rows; row += (i64)gridDim.x * rows_per_cta) {
+    i64 r = row, oi = 0, oo = 0;
 #pragma unroll
-    for (int d = MAXR - 1; d >= 0; --d) {
-      if (d < p.rank) {
+    for (int d = MAXR - 2; d >= 0; --d) {
+      if (d < p.rank - 1) {
         const i64 s = p.shape[d];
         const i64 qd = r / s;
         const i64 id = r - qd * s;
@@ -36,8 +53,13 @@ __global__ void __launch_bounds__(256) permute_rowcopy_kernel(const PermParams p
         oo += id * p.so[d];
       }
     }
-    const double v = p.alpha * in[oi];
-    out[oo] = (p.beta != 0.0) ? v + p.beta * out[oo] : v;
+    const double* src = in + oi;
+    double* dst = out + oo;
+    if (p.beta != 0.0) {
+      for (i64 e = lane0; e < n_last; e += 256) dst[e * so_l] = p.alpha * src[e * si_l] + p.beta * dst[e * so_l];
+    } else {
+      for (i64 e = lane0; e < n_last; e += 256) dst[e * so_l] = p.alpha * src[e * si_l];
+    }
   }
 }
 
@@ -136,8 +158,11 @@ extern "C" int b200cc_permute(int rank, const b200cc_i64* shape, const b200cc_i6
                               p.shape[dx] >= 8 && p.shape[last] >= 8;
   const int cap = sm_count() * 16;
   if (!need_transpose) {
-    i64 blocks = (p.total + 255) / 256;
+    const i64 n_last = p.shape[last];
+    const i64 rpc = n_last >= 256 ? 1 : 256 / n_last;
+    i64 blocks = p.rank == 1 ? (n_last + 255) / 256 : (p.total / n_last + rpc - 1) / rpc;
     if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
     permute_rowcopy_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, in, out);
     return check_launch("permute_rowcopy_kernel");
   }
