@@ -209,10 +209,16 @@ class CCwfn(object):
         t1 = t1.contiguous()
         t2 = t2.contiguous()
         I = self._intermediates(F, t1, t2)
-        r1 = self._r1(F, t1, t2, I)
-        half = self._r2_half(F, t1, t2, I)
+        # one flat buffer [ r2 half | rank-partial part of r1 ] so that ONE all-reduce carries both
+        n2, n1 = t2.numel(), t1.numel()
+        buf = torch.empty(n2 + n1, dtype=F64, device=self.device1)
+        half = buf[:n2].view(t2.shape)
+        r1p = buf[n2:].view(t1.shape)
+        r1 = self._r1(F, t1, t2, I, r1p)
+        self._r2_half(F, t1, t2, I, half)
         if self.part.size > 1:
-            self.part.all_reduce_sum(half)
+            self.part.all_reduce_sum(buf)
+        K.strided_axpby(r1, r1p, 1.0, 1.0)
         if self.model == 'CCD':
             r1.zero_()
         return r1, half
@@ -247,22 +253,28 @@ class CCwfn(object):
             ct("menf,nf->me", H.derived("Loovv_menf"), t1, out=Fme, alpha=1.0, beta=1.0)
         I["Fme"] = Fme
 
-        # ---------------- Fae                                            (ccwfn.py:495-497)
-        Fae = K.permuted(F[v, v], (0, 1))
+        # ---------------- Fae, Fmi (ccwfn.py:495-497, 531-533).  Their o^2v^3 / o^3v^2 sums run over an occupied
+        # index: each rank sums its slice m (resp. n) in [i0,i1) into a packed [Fae|Fmi] buffer, one small
+        # all-reduce (v^2 + o^2 doubles) completes them; the cheap t1 / Fock terms are added on every rank.
         tauh = K.build_tau(t1, t2, 1.0, 0.0 if ccd else 0.5)
-        ct("mnaf,mnef->ae", tauh, Loovv, out=Fae, alpha=-1.0, beta=1.0)
+        pk = torch.zeros(nv * nv + no * no, dtype=F64, device=self.device1)
+        Fae_p, Fmi_p = pk[:nv * nv].view(nv, nv), pk[nv * nv:].view(no, no)
+        if ni > 0:
+            ct("mnaf,emnf->ae", tauh[i0:i1], self._Loovv_emnf(i0, i1), out=Fae_p, alpha=-1.0, beta=1.0)
+            ct("inef,mnef->mi", tauh[:, i0:i1], Loovv[:, i0:i1], out=Fmi_p, alpha=1.0, beta=1.0)
+            if not ccd:
+                self._fae_ovvv(t1, Fae_p, i0, i1)
+        if self.part.size > 1 and not full:
+            self.part.all_reduce_sum(pk)
+        Fae = K.permuted(F[v, v], (0, 1))
+        K.strided_axpby(Fae, Fae_p, 1.0, 1.0)
+        Fmi = K.permuted(F[o, o], (0, 1))
+        K.strided_axpby(Fmi, Fmi_p, 1.0, 1.0)
         if not ccd:
             ct("me,ma->ae", Fov, t1, out=Fae, alpha=-0.5, beta=1.0)
-            self._fae_ovvv(t1, Fae)
-        I["Fae"] = Fae
-
-        # ---------------- Fmi                                            (ccwfn.py:531-533)
-        Fmi = K.permuted(F[o, o], (0, 1))
-        ct("inef,mnef->mi", tauh, Loovv, out=Fmi, alpha=1.0, beta=1.0)
-        if not ccd:
             ct("ie,me->mi", t1, Fov, out=Fmi, alpha=0.5, beta=1.0)
             ct("ne,mnie->mi", t1, H.derived("Looov"), out=Fmi, alpha=1.0, beta=1.0)
-        I["Fmi"] = Fmi
+        I["Fae"], I["Fmi"] = Fae, Fmi
         del tauh
         if ni == 0:
             return I
@@ -314,27 +326,40 @@ class CCwfn(object):
             I["Zijmb"] = ct("ijef,mbef->ijmb", A["tau"][i0:i1], H.block("ovvv"))
         return I
 
-    def _fae_ovvv(self, t1, Fae):
-        """Fae += sum_mf t_mf (2<ma|fe> - <ma|ef>)  (ccwfn.py:496): <mb|ef> streamed in place, twice."""
+    def _Loovv_emnf(self, m0, m1):
+        """Constant [e, m, n, f] copy of Loovv[m0:m1] (K-major operand of the Fae contraction), built once."""
+        key = ("Loovv_emnf", m0, m1)
+        if key not in self.H._derived:
+            self.H._derived[key] = K.permuted(self.H.derived("Loovv")[m0:m1], (2, 0, 1, 3))
+        return self.H._derived[key]
+
+    def _fae_ovvv(self, t1, Fae, m0, m1):
+        """Fae += sum_{m in [m0,m1)} sum_f t_mf (2<ma|fe> - <ma|ef>)  (ccwfn.py:496): <mb|ef> streamed in place."""
         no, nv = self.no, self.nv
+        nm = m1 - m0
         ovvv = self.H.block("ovvv")
-        tmp = torch.empty((no, nv, nv), dtype=F64, device=self.device1)
+        tmp = torch.empty((nm, nv, nv), dtype=F64, device=self.device1)
         # tmp[m,a,e] = - sum_f <ma|ef> t_mf : batch m, (a,e) x f  times  f x 1
-        K.dgemm(nv * nv, 1, nv, ovvv, nv, 0, t1, nv, 0, tmp, 1, -1.0, 0.0,
-                batch=no, sA=nv ** 3, sB=nv, sC=nv * nv)
+        K.dgemm(nv * nv, 1, nv, (ovvv, m0 * nv ** 3), nv, 0, (t1, m0 * nv), nv, 0, tmp, 1, -1.0, 0.0,
+                batch=nm, sA=nv ** 3, sB=nv, sC=nv * nv)
         # tmp[m,a,e] += 2 sum_f t_mf <ma|fe> : per m, batch a: (1 x f) times (f x e)
-        for m in range(no):
-            K.dgemm(1, nv, nv, (t1, m * nv), nv, 0, (ovvv, m * nv ** 3), nv, 1, (tmp, m * nv * nv), nv, 2.0, 1.0,
-                    batch=nv, sA=0, sB=nv * nv, sC=nv)
-        ones = torch.ones(no, dtype=F64, device=self.device1)
+        for m in range(m0, m1):
+            K.dgemm(1, nv, nv, (t1, m * nv), nv, 0, (ovvv, m * nv ** 3), nv, 1, (tmp, (m - m0) * nv * nv), nv,
+                    2.0, 1.0, batch=nv, sA=0, sB=nv * nv, sC=nv)
+        ones = torch.ones(nm, dtype=F64, device=self.device1)
         self._ct("m,mae->ae", ones, tmp, out=Fae, alpha=1.0, beta=1.0)
 
     # ---- r1 (ccwfn.py:754-760), replicated on every rank ------------------------------------------------
-    def _r1(self, F, t1, t2, I):
+    def _r1(self, F, t1, t2, I, r1p):
+        """Returns the replicated (cheap) part of r1; the two o^2v^3 / o^3v^2 sums over an occupied index m are
+        evaluated for this rank's m in [i0,i1) only and written to ``r1p`` (summed by the r2 all-reduce)."""
         H, ct = self.H, self._ct
         o, v, no, nv = self.o, self.v, self.no, self.nv
         A = I["amps"]
+        i0, i1 = I["occ"]
+        ni = i1 - i0
         r1 = K.permuted(F[v, o], (1, 0))                                        # f_ai
+        r1p.zero_()
         if self.model == 'CCD':
             return r1
         ct("ie,ae->ia", t1, I["Fae"], out=r1, alpha=1.0, beta=1.0)
@@ -346,22 +371,25 @@ class CCwfn(object):
         ovov = H.block("ovov")
         K.dgemm(nv, 1, nv * no, ovov, nv, 1, t1T, nv * no, 0, r1, 1, -1.0, 1.0,
                 batch=no, sA=nv * no * nv, sB=0, sC=nv)
-        # (2 t2 - t2^T)_mief <ma|ef> : per m a (o x v^2)(v^2 x v) product, summed over m
-        s_mief = torch.empty_like(t2)
-        K.strided_axpby(s_mief, t2, 2.0, 0.0)
-        K.strided_axpby(s_mief, t2.permute(0, 1, 3, 2), -1.0, 1.0)
-        tmp = torch.empty((no, no, nv), dtype=F64, device=self.device1)
-        K.dgemm(no, nv, nv * nv, s_mief, nv * nv, 0, H.block("ovvv"), nv * nv, 0, tmp, nv, 1.0, 0.0,
-                batch=no, sA=no * nv * nv, sB=nv ** 3, sC=no * nv)
-        ones = torch.ones(no, dtype=F64, device=self.device1)
-        ct("m,mia->ia", ones, tmp, out=r1, alpha=1.0, beta=1.0)
+        if ni == 0:
+            return r1
+        # (2 t2 - t2^T)_mief <ma|ef> : per m a (o x v^2)(v^2 x v) product, summed over this rank's m
+        t2m = t2[i0:i1]
+        s_mief = torch.empty_like(t2m)
+        K.strided_axpby(s_mief, t2m, 2.0, 0.0)
+        K.strided_axpby(s_mief, t2m.permute(0, 1, 3, 2), -1.0, 1.0)
+        tmp = torch.empty((ni, no, nv), dtype=F64, device=self.device1)
+        K.dgemm(no, nv, nv * nv, s_mief, nv * nv, 0, (H.block("ovvv"), i0 * nv ** 3), nv * nv, 0, tmp, nv, 1.0, 0.0,
+                batch=ni, sA=no * nv * nv, sB=nv ** 3, sC=no * nv)
+        ones = torch.ones(ni, dtype=F64, device=self.device1)
+        ct("m,mia->ia", ones, tmp, out=r1p, alpha=1.0, beta=1.0)
         del s_mief, tmp
         # - t2_mnae L_nmei,  L_nmei = 2<mn|ie> - <nm|ie> = Looov[m,n,i,e]
-        ct("mnae,mnie->ia", t2, H.derived("Looov"), out=r1, alpha=-1.0, beta=1.0)
+        ct("mnae,mnie->ia", t2m, H.derived("Looov")[i0:i1], out=r1p, alpha=-1.0, beta=1.0)
         return r1
 
     # ---- r2, unsymmetrised half (ccwfn.py:922-940): this rank's share -------------------------------------
-    def _r2_half(self, F, t1, t2, I):
+    def _r2_half(self, F, t1, t2, I, r2=None):
         H, ct = self.H, self._ct
         o, v, no, nv = self.o, self.v, self.no, self.nv
         A = I["amps"]
@@ -370,7 +398,10 @@ class CCwfn(object):
         ni = i1 - i0
         oovv = H.block("oovv")
         whole = ni == no
-        r2 = torch.empty_like(t2) if whole else torch.zeros_like(t2)
+        if r2 is None:
+            r2 = torch.empty_like(t2)
+        if not whole:
+            r2.zero_()
         # 1/2 tau_ijef <ab|ef>  -- the particle-particle ladder, local a rows, all (i,j)      931
         if ni > 0:
             K.strided_axpby(r2[i0:i1], oovv[i0:i1], 0.5, 0.0)                      # 1/2 <ab|ij>       922
@@ -492,7 +523,11 @@ class CCwfn(object):
         self._own(ERI, L)
         F = self._check_F(F)
         t1, t2 = t1.contiguous(), t2.contiguous()
-        r1 = self._r1(F, t1, t2, self._intermediates(F, t1, t2))
+        r1p = torch.empty_like(t1)
+        r1 = self._r1(F, t1, t2, self._intermediates(F, t1, t2), r1p)
+        if self.part.size > 1:
+            self.part.all_reduce_sum(r1p)
+        K.strided_axpby(r1, r1p, 1.0, 1.0)
         if self.model == 'CCD':
             r1.zero_()
         return r1
