@@ -15,6 +15,7 @@
 //     fragment load (LDS.64) is bank-conflict free; cp.async zero-fill handles all M/N/K tails.
 //   * Two K-segments can be chained into the same accumulators ((T): particle + hole term);
 //     split-K goes through a workspace and a deterministic reduction; batches by stride or address table.
+#include <cuda.h>
 #include "common.cuh"
 
 namespace b200cc {
@@ -600,6 +601,253 @@ static int launch_ws(const KParams& p, int grid, cudaStream_t st) {
   return check_launch("dgemm_ws_kernel");
 }
 
+// =====================================================================================================
+// TMA variant (config 6) of the warp-specialised kernel, for K-major x K-major operands (the ladder, the
+// W_mbej builds, Z_mbij, W_mnij): ONE producer thread issues two cp.async.bulk.tensor loads per stage
+// (128 rows x 16 doubles = 128-byte rows, CU_TENSOR_MAP_SWIZZLE_128B, out-of-range rows/k zero-filled by
+// the TMA unit) that complete on the stage's mbarrier (expect_tx); the 8 consumer warps are unchanged
+// except for the fragment addressing.  With 128-byte rows a naive fragment read would be an 8-way bank
+// conflict; the 128B swizzle XORs the 16-byte chunk index with (row & 7), and because the summation index
+// may be visited in any order, k-step s / lane q reads logical k = 8*(q>>1) + 2*s + (q&1): the half-warp
+// then covers all eight chunks x both halves -> conflict-free LDS.64 (same mapping for A and B).
+// =====================================================================================================
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::
+          "r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <class CF>
+__device__ __forceinline__ void load_frags_swz(const unsigned char* __restrict__ As, const unsigned char* __restrict__ Bs,
+                                               int off, double (&a)[CF::MI], double (&b)[CF::NI], int wm, int wn,
+                                               int g) {
+#pragma unroll
+  for (int i = 0; i < CF::MI; ++i)
+    a[i] = *reinterpret_cast<const double*>(As + (8 * (wm + CF::WARPS_M * i) + g) * 128 + off);
+#pragma unroll
+  for (int j = 0; j < CF::NI; ++j)
+    b[j] = *reinterpret_cast<const double*>(Bs + (8 * (wn + CF::WARPS_N * j) + g) * 128 + off);
+}
+
+template <class CF>
+__global__ void __launch_bounds__(CF::NT + WS_PRODUCER_THREADS, 1)
+    dgemm_tma_kernel(const KParams p, const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int MI = CF::MI, NI = CF::NI;
+  constexpr int A_BYTES = CF::BM * 128, B_BYTES = CF::BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  unsigned char* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte swizzle atoms
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int G = gridDim.x;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, CF::NT / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp >= CF::NT / 32) {
+    // ================================ producer: one thread drives the TMA unit ================================
+    // (a whole warpgroup is launched only so that setmaxnreg can hand its registers to the consumers)
+    reg_dec<40>();
+    if (warp == CF::NT / 32 && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < p.units; u += G) {
+        const Unit w = decode_unit<CF>(p, u);
+        const int bA1 = p.sA1 ? w.b : 0, bB1 = p.sB1 ? w.b : 0, bA2 = p.sA2 ? w.b : 0, bB2 = p.sB2 ? w.b : 0;
+        for (int t = 0; t < w.nkt; ++t) {
+          mbar_wait(empty_bar + stage, phase ^ 1u);
+          unsigned char* As = tiles + stage * STAGE_BYTES;
+          unsigned char* Bs = As + A_BYTES;
+          mbar_expect_tx(full_bar + stage, STAGE_BYTES);
+          const int kt = w.kt_begin + t;
+          if (kt < p.kt1) {
+            tma_load_3d(As, &tmA1, kt * BK, w.m0, bA1, full_bar + stage);
+            tma_load_3d(Bs, &tmB1, kt * BK, w.n0, bB1, full_bar + stage);
+          } else {
+            tma_load_3d(As, &tmA2, (kt - p.kt1) * BK, w.m0, bA2, full_bar + stage);
+            tma_load_3d(Bs, &tmB2, (kt - p.kt1) * BK, w.n0, bB2, full_bar + stage);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    return;
+  }
+
+  // ================================ consumers ================================
+  reg_inc<216>();
+  const int wn = warp % CF::WARPS_N, wm = warp / CF::WARPS_N;
+  const int g = lane >> 2, q = lane & 3;
+  int off[4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) off[s] = ((((q >> 1) * 4 + s) ^ g) << 4) + ((q & 1) << 3);
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int cu = blockIdx.x; cu < p.units; cu += G) {
+    const Unit w = decode_unit<CF>(p, cu);
+    int mc = 0, nc = 0;
+#pragma unroll
+    for (int i = 0; i < MI; ++i) mc += (w.m0 + 8 * (wm + CF::WARPS_M * i) < p.M) ? 1 : 0;
+#pragma unroll
+    for (int j = 0; j < NI; ++j) nc += (w.n0 + 8 * (wn + CF::WARPS_N * j) < p.N) ? 1 : 0;
+
+    double acc[MI][NI][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+      for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    if (mc == 0 || nc == 0) {
+      idle_unit(full_bar, empty_bar, stage, phase, w.nkt, lane);
+    } else {
+      constexpr int NQ = NI / 4, MH = (MI + 1) / 2;
+      const int code = (mc <= MH ? 4 : 0) + (nc + NQ - 1) / NQ - 1;
+      double a0[MI], b0[NI], a1[MI], b1[NI];
+      if (w.nkt > 0) {
+        mbar_wait(full_bar + stage, phase);
+        load_frags_swz<CF>(tiles + stage * STAGE_BYTES, tiles + stage * STAGE_BYTES + A_BYTES, off[0], a0, b0, wm, wn, g);
+      }
+      for (int t = 0; t < w.nkt; ++t) {
+        const unsigned char* As = tiles + stage * STAGE_BYTES;
+        const unsigned char* Bs = As + A_BYTES;
+        load_frags_swz<CF>(As, Bs, off[1], a1, b1, wm, wn, g);
+        mma_select<CF>(acc, a0, b0, code);
+        load_frags_swz<CF>(As, Bs, off[2], a0, b0, wm, wn, g);
+        mma_select<CF>(acc, a1, b1, code);
+        load_frags_swz<CF>(As, Bs, off[3], a1, b1, wm, wn, g);
+        mma_select<CF>(acc, a0, b0, code);
+        int nstage = stage + 1;
+        uint32_t nphase = phase;
+        if (nstage == STAGES) { nstage = 0; nphase ^= 1u; }
+        if (t + 1 < w.nkt) {
+          mbar_wait(full_bar + nstage, nphase);
+          load_frags_swz<CF>(tiles + nstage * STAGE_BYTES, tiles + nstage * STAGE_BYTES + A_BYTES, off[0], a0, b0, wm,
+                             wn, g);
+        }
+        mma_select<CF>(acc, a1, b1, code);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar + stage);
+        stage = nstage;
+        phase = nphase;
+      }
+    }
+
+    // ---- epilogue
+    const bool split = p.ksplit > 1;
+    double* C;
+    if (split) C = p.ws + ((i64)w.z * p.batch + w.b) * (i64)p.M * p.N;
+    else C = p.C + (i64)w.b * p.sC;
+    const i64 ldo = split ? (i64)p.N : p.ldc;
+    const double alpha = split ? 1.0 : p.alpha, beta = split ? 0.0 : p.beta;
+    const bool vec = split ? ((p.N & 1) == 0 && (((i64)p.M * p.N) & 1) == 0) : (p.cvec != 0);
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+      const int row = w.m0 + 8 * (wm + CF::WARPS_M * i) + g;
+      if (row >= p.M) continue;
+#pragma unroll
+      for (int j = 0; j < NI; ++j) {
+        const int col = w.n0 + 8 * (wn + CF::WARPS_N * j) + 2 * q;
+        if (col >= p.N) continue;
+        double* c = C + (i64)row * ldo + col;
+        double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
+        if (vec && col + 1 < p.N) {
+          if (beta != 0.0) {
+            const double2 o = *reinterpret_cast<const double2*>(c);
+            v0 += beta * o.x;
+            v1 += beta * o.y;
+          }
+          *reinterpret_cast<double2*>(c) = make_double2(v0, v1);
+        } else {
+          if (beta != 0.0) v0 += beta * c[0];
+          c[0] = v0;
+          if (col + 1 < p.N) {
+            if (beta != 0.0) v1 += beta * c[1];
+            c[1] = v1;
+          }
+        }
+      }
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// K-major operand (rows x K, pitch ld, `batch` copies `stride` apart) as a 3-D tensor map {K, rows, batch}
+static int make_tmap(CUtensorMap* tm, const double* base, int rows, int K, i64 ld, i64 stride, int batch, int box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available"); return 1; }
+  const bool batched = batch > 1 && stride != 0;
+  cuuint64_t gdim[3] = {(cuuint64_t)(K > 0 ? K : 1), (cuuint64_t)rows, (cuuint64_t)(batched ? batch : 1)};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 8, (cuuint64_t)(batched ? stride : ld * (i64)rows) * 8};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t est[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), gdim, gstr, box, est,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return 1; }
+  return 0;
+}
+
+template <class CF>
+static int launch_tma(KParams& p, cudaStream_t st) {
+  p.tiles_m = (p.M + CF::BM - 1) / CF::BM;
+  p.tiles_n = (p.N + CF::BN - 1) / CF::BN;
+  const i64 tiles = (i64)p.tiles_m * p.tiles_n;
+  const i64 units = tiles * p.batch * p.ksplit;
+  if (tiles > 2000000000LL || units > 2000000000LL) { set_error("b200cc_dgemm: too many tiles"); return 1; }
+  p.tiles = (int)tiles;
+  p.units = (int)units;
+  p.nfast = p.tiles_n < p.tiles_m ? 1 : 0;
+  CUtensorMap tA1, tB1, tA2, tB2;
+  if (make_tmap(&tA1, p.A1, p.M, p.K1, p.lda1, p.sA1, p.batch, CF::BM)) return 1;
+  if (make_tmap(&tB1, p.B1, p.N, p.K1, p.ldb1, p.sB1, p.batch, CF::BN)) return 1;
+  if (p.K2 > 0) {
+    if (make_tmap(&tA2, p.A2, p.M, p.K2, p.lda2, p.sA2, p.batch, CF::BM)) return 1;
+    if (make_tmap(&tB2, p.B2, p.N, p.K2, p.ldb2, p.sB2, p.batch, CF::BN)) return 1;
+  } else {
+    tA2 = tA1;
+    tB2 = tB1;
+  }
+  constexpr int SMEM = STAGES * (CF::BM + CF::BN) * 128 + 2 * STAGES * (int)sizeof(uint64_t) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    B200CC_CUDA_OK(cudaFuncSetAttribute(dgemm_tma_kernel<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  const int nsm = sm_count();
+  const int grid = units < nsm ? (int)units : nsm;
+  dgemm_tma_kernel<CF><<<grid, CF::NT + WS_PRODUCER_THREADS, SMEM, st>>>(p, tA1, tB1, tA2, tB2);
+  return check_launch("dgemm_tma_kernel");
+}
+
 // C[b] = alpha * sum_z ws[z][b] + beta * C[b]
 __global__ void splitk_reduce_kernel(const double* __restrict__ ws, int ksplit, int batch, int M, int N,
                                      double alpha, double beta, double* C, i64 ldc, i64 sC,
@@ -720,6 +968,7 @@ extern "C" int b200cc_dgemm(const b200cc_gemm_desc* d, void* stream) {
   const bool v2 = va && vb;
   const int ta = d->transA ? 1 : 0, tb = d->transB ? 1 : 0;
 
+  const bool tma_ok = !ta && !tb && !d->table && v2 && d->K1 > 0;
   // tile configuration: 0 = auto
   int cfg = d->config;
   if (cfg == 0) {
@@ -740,6 +989,10 @@ extern "C" int b200cc_dgemm(const b200cc_gemm_desc* d, void* stream) {
   if (cfg == 2) rc = dispatch<CfgB, false>(p, ta, tb, v2, st);
   else if (cfg == 4) rc = dispatch<CfgB, true>(p, ta, tb, v2, st);
   else if (cfg == 5) rc = dispatch<CfgC, true>(p, ta, tb, v2, st);
+  else if (cfg == 6) {
+    if (!tma_ok) { set_error("b200cc_dgemm: config 6 (TMA) needs K-major 16-byte aligned operands without an address table"); return 1; }
+    rc = launch_tma<CfgB>(p, st);
+  }
   else { set_error("b200cc_dgemm: unknown tile config %d", cfg); return 1; }
   if (rc) return rc;
   if (ksplit > 1) {

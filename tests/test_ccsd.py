@@ -244,3 +244,53 @@ def test_medium_size_vs_oracle(no, nv, seed, noise):
         assert np.abs(r2.cpu().numpy() - r2_ref).max() < 1e-11
     finally:
         DEV[0] = torch.device("cpu")
+
+
+def test_frozen_core_offsets(dev):
+    """nfzc > 0: the reference keeps the full MO space and offsets the o/v slices (wavefunction.py:293-332);
+    here the same F (full n x n) and a full-space ERI are given with nfzc = 2."""
+    from oracle import ccsd_oracle as co, triples_oracle as to
+    from pycc_b200.synthetic import make_synthetic
+    nfzc, no, nv = 2, 3, 6
+    syn = make_synthetic(nfzc + no, nv, seed=5, fock_noise=0.01)      # n = 11 orbitals, the first 2 frozen
+    ERI = full_eri(syn)
+    ref = IntegralReference.from_arrays(syn.F, ERI, no, nfzc, eref=-1.25)
+    cc = pycc_b200.ccwfn(ref, model="CCSD(T)", device="GPU", quiet=True)
+    assert (cc.nfzc, cc.no, cc.nv, cc.nmo) == (nfzc, no, nv, nfzc + no + nv)
+    assert cc.o == slice(nfzc, nfzc + no) and cc.v == slice(nfzc + no, cc.nmo)
+    e = cc.solve_cc(1e-11, 1e-11)
+    P = co.Problem(co.blocks_from_full(ERI, no, nfzc), syn.F, no, nfzc)
+    e_ref, t1, t2, trace = co.solve_cc(P, 1e-11, 1e-11)
+    et = to.t_tjl(t1, t2, syn.F, P.ovvv, P.ooov, P.oovv, nfzc=nfzc)
+    assert abs(float(e) - (e_ref + et)) < 1e-10
+    assert np.abs(cc.t2.cpu().numpy() - t2).max() < 1e-9
+    assert cc.eref == -1.25
+    # the block views follow the offset slices
+    assert np.abs(cc.H.ERI[cc.o, cc.v, cc.v, cc.o].cpu().numpy() - ERI[cc.o, cc.v, cc.v, cc.o]).max() < 1e-13
+
+
+def test_not_converged_returns_none(dev):
+    from pycc_b200.synthetic import make_synthetic
+    cc = make_wfn(make_synthetic(3, 5, seed=1), "CCSD")
+    assert cc.solve_cc(1e-12, 1e-12, maxiter=2) is None            # reference: falls off the loop (ccwfn.py:268-319)
+    cc2 = make_wfn(make_synthetic(3, 5, seed=1), "CCSD")
+    e_nodiis = cc2.solve_cc(1e-10, 1e-10, maxiter=200, max_diis=0)  # max_diis = 0 switches DIIS off (utils.py:311)
+    cc3 = make_wfn(make_synthetic(3, 5, seed=1), "CCSD")
+    e_diis = cc3.solve_cc(1e-10, 1e-10)
+    assert abs(float(e_nodiis) - float(e_diis)) < 1e-9
+    assert len(cc2.trace) > len(cc3.trace)
+
+
+def test_tiny_and_ragged_shapes(dev):
+    """o = 1 (no i>j>k triple survives), v = 1, and odd extents."""
+    from oracle import ccsd_oracle as co, triples_oracle as to
+    from pycc_b200.synthetic import make_synthetic, blocks_from_factor
+    for (no, nv) in ((1, 3), (2, 1), (5, 9)):
+        syn = make_synthetic(no, nv, seed=no + nv)
+        b = blocks_from_factor(syn)
+        P = co.Problem(b, syn.F, no)
+        e_ref, t1, t2, _ = co.solve_cc(P, 1e-11, 1e-11)
+        et = to.t_tjl(t1, t2, syn.F, b["ovvv"], b["ooov"], b["oovv"])
+        cc = make_wfn(syn, "CCSD(T)")
+        e = cc.solve_cc(1e-11, 1e-11)
+        assert abs(float(e) - (e_ref + et)) < 1e-10, (no, nv)

@@ -177,3 +177,33 @@ def test_diis_kernels():
     assert relerr(z, 2.0 * xs[0] - 3.0 * xs[1]) < 1e-15
     # determinism: identical bits on repeat
     assert torch.equal(K.multi_dot(xs[0], xs), d)
+
+
+@pytest.mark.parametrize("M,N,Kd", [(1, 1, 1), (37, 19, 53), (129, 130, 18), (300, 257, 1000), (400, 150, 334), (64, 513, 16)])
+def test_dgemm_tma_config(M, N, Kd):
+    """config 6: cp.async.bulk.tensor (TMA, 128B swizzle) operand staging; K-major operands with even pitches."""
+    lda, ldb = Kd + (Kd & 1) + 2, Kd + (Kd & 1)
+    A = rnd(M, lda, seed=1)[:, :Kd]
+    B = rnd(N, ldb, seed=2)[:, :Kd]
+    C0 = rnd(M, N + 3, seed=3)
+    C = C0.clone()
+    K.dgemm(M, N, Kd, A, lda, 0, B, ldb, 0, C, N + 3, alpha=0.75, beta=-0.5, ksplit=1, config=6)
+    ref = 0.75 * (A @ B.t()) - 0.5 * C0[:, :N]
+    assert relerr(C[:, :N], ref) < 1e-12
+    assert torch.equal(C[:, N:], C0[:, N:])
+
+
+def test_dgemm_tma_batch_segments_splitk():
+    nb, M, N, K1, K2 = 5, 150, 41, 64, 14
+    A1, B1 = rnd(nb, M, K1), rnd(N, K1)                      # B shared by all batches (stride 0)
+    A2, B2 = rnd(nb, M, K2, seed=5), rnd(nb, N, K2, seed=6)
+    C = torch.zeros(nb, M, N, dtype=torch.float64, device=DEV)
+    ref = torch.einsum("bmk,nk->bmn", A1, B1) + torch.einsum("bmk,bnk->bmn", A2, B2)
+    K.dgemm(M, N, K1, A1, K1, 0, B1, K1, 0, C, N, batch=nb, sA=M * K1, sB=0, sC=M * N,
+            seg2=(A2, K2, B2, K2, K2, M * K2, N * K2), ksplit=1, config=6)
+    assert relerr(C, ref) < 1e-12
+    M, N, Kd = 45, 70, 5000
+    A, B = rnd(M, Kd), rnd(N, Kd)
+    C = torch.empty(M, N, dtype=torch.float64, device=DEV)
+    K.dgemm(M, N, Kd, A, Kd, 0, B, Kd, 0, C, N, ksplit=7, config=6)
+    assert relerr(C, A @ B.t()) < 1e-12
