@@ -60,9 +60,10 @@ typedef struct {
   int table_align16;               /* table mode: caller vouches every address is 16-byte aligned */
   int ksplit;
   double* workspace;
-  int config;                      /* kernel: 0 auto (4 or 5 by a cost model); 2 = plain 128x128 multistage kernel (8 warps,
+  int config;                      /* kernel: 0 auto (tile by a cost model, TMA when eligible); 2 = plain 128x128 multistage kernel (8 warps,
                                       __syncthreads pipeline; kept as a cross-check); 4 = 128x128 warp-specialised
-                                      (8 DMMA warps + 4 cp.async producer warps, mbarrier pipeline); 5 = 80x128 ditto */
+                                      (8 DMMA warps + 4 cp.async producer warps, mbarrier pipeline); 5 = 80x128 ditto;
+                                      6 / 7 = as 4 / 5 with cp.async.bulk.tensor (TMA) operand staging, K-major aligned operands only */
 } b200cc_gemm_desc;
 
 int b200cc_dgemm(const b200cc_gemm_desc* d, void* stream);

@@ -290,35 +290,35 @@ class CCwfn(object):
         ct("ijef,mnef->mnij", A["tau"][i0:i1], H.block("oovv"), out=Wmnij, alpha=1.0, beta=1.0)
         I["Wmnij"] = Wmnij
 
-        # ---------------- ring intermediates in [m,e,j_g,b] layout
-        #   W1[m,e,j,b] = Wmbej[m,b,e,j]    (ccwfn.py:641-645)
-        #   W2[m,e,j,b] = Wmbje[m,b,j,e]    (ccwfn.py:680-683)
+        # ---------------- ring intermediates in [j_g,b,m,e] layout (every o^3v^3 GEMM is then K-major x K-major)
+        #   W1[j,b,m,e] = Wmbej[m,b,e,j]    (ccwfn.py:641-645)
+        #   W2[j,b,m,e] = Wmbje[m,b,j,e]    (ccwfn.py:680-683)
         taut = K.build_tau(t1, t2, 0.5, 0.0 if ccd else 1.0)
         taut_jbnf = K.permuted(taut[i0:i1], (0, 3, 1, 2))         # [j,b,n,f] = tau(1/2,1)[j,n,f,b]
         del taut
         t2_jbnf = K.permuted(t2[:, i0:i1], (1, 3, 0, 2))          # [j,b,n,f] = t2[n,j,f,b]
         oovv_menf = H.derived("oovv_menf")
-        W1 = K.permuted(oovv_menf[:, :, i0:i1, :], (0, 1, 2, 3))  # <mb|ej> = <mj|eb> -> [m,e,j,b]
-        ct("menf,jbnf->mejb", oovv_menf, taut_jbnf, out=W1, alpha=-1.0, beta=1.0)
-        ct("menf,jbnf->mejb", H.derived("Loovv_menf"), t2_jbnf, out=W1, alpha=0.5, beta=1.0)
+        W1 = K.permuted(oovv_menf[:, :, i0:i1, :], (2, 3, 0, 1))  # <mb|ej> = <mj|eb> -> [j,b,m,e]
+        ct("jbnf,menf->jbme", taut_jbnf, oovv_menf, out=W1, alpha=-1.0, beta=1.0)
+        ct("jbnf,menf->jbme", t2_jbnf, H.derived("Loovv_menf"), out=W1, alpha=0.5, beta=1.0)
         del t2_jbnf
-        W2 = K.permuted(H.derived("ovov_mejb")[:, :, i0:i1, :], (0, 1, 2, 3), -1.0)
-        ct("menf,jbnf->mejb", H.derived("oovv_mfne"), taut_jbnf, out=W2, alpha=1.0, beta=1.0)
+        W2 = K.permuted(H.derived("ovov_mejb")[:, :, i0:i1, :], (2, 3, 0, 1), -1.0)
+        ct("jbnf,menf->jbme", taut_jbnf, H.derived("oovv_mfne"), out=W2, alpha=1.0, beta=1.0)
         del taut_jbnf
         if not ccd:
             ovvv = H.block("ovvv")
             t1g = t1[i0:i1]
-            # + t_jf <mb|ef>: natural GEMM output is [m,b,e,j]; fold into [m,e,j,b]
+            # + t_jf <mb|ef>: natural GEMM output is [m,b,e,j]; fold into [j,b,m,e]
             tmp = ct("mbef,jf->mbej", ovvv, t1g)
-            K.strided_axpby(W1, tmp.permute(0, 2, 3, 1), 1.0, 1.0)
+            K.strided_axpby(W1, tmp.permute(3, 1, 0, 2), 1.0, 1.0)
             # - t_jf <mb|fe>: batch (m,b): C[j,e] = t1[j,:] . ovvv[m,b][f,e]   -> [m,b,j,e]
             K.dgemm(ni, nv, nv, t1g, nv, 0, ovvv, nv, 1, tmp, nv, 1.0, 0.0,
                     batch=no * nv, sA=0, sB=nv * nv, sC=ni * nv)
-            K.strided_axpby(W2, tmp.view(no, nv, ni, nv).permute(0, 3, 2, 1), -1.0, 1.0)
+            K.strided_axpby(W2, tmp.view(no, nv, ni, nv).permute(2, 1, 0, 3), -1.0, 1.0)
             del tmp
             # - t_nb <mn|ej> = - t_nb ooov[n,m,j,e]  and  + t_nb <mn|je>
-            ct("nb,nmje->mejb", t1, ooov[:, :, i0:i1, :], out=W1, alpha=-1.0, beta=1.0)
-            ct("nb,mnje->mejb", t1, ooov[:, :, i0:i1, :], out=W2, alpha=1.0, beta=1.0)
+            ct("nb,nmje->jbme", t1, ooov[:, :, i0:i1, :], out=W1, alpha=-1.0, beta=1.0)
+            ct("nb,mnje->jbme", t1, ooov[:, :, i0:i1, :], out=W2, alpha=1.0, beta=1.0)
         I["W1"], I["W2"] = W1, W2
 
         # ---------------- Z'[i_g,j,m,b] = Zmbij[m,b,i,j] = <mb|ef> tau_ijef   (ccwfn.py:715)
@@ -426,11 +426,11 @@ class CCwfn(object):
         # 1/2 tau_mnab W_mnij                                                       930
         ct("mnij,mnab->ijab", I["Wmnij"], A["tau"], out=rg, alpha=0.5, beta=1.0)
         # ring terms, columns j_g, in [i,a,j,b] layout                              933-935
-        R = ct("iame,mejb->iajb", A["s_iame"], I["W1"])          # (2t2 - t2^T) W_mbej
-        ct("iame,mejb->iajb", A["t2_iame"], I["W2"], out=R, alpha=1.0, beta=1.0)   # t2 W_mbje^T
+        R = ct("iame,jbme->iajb", A["s_iame"], I["W1"])          # (2t2 - t2^T) W_mbej
+        ct("iame,jbme->iajb", A["t2_iame"], I["W2"], out=R, alpha=1.0, beta=1.0)   # t2 W_mbje^T
         K.strided_axpby(r2[:, i0:i1], R.permute(0, 2, 1, 3), 1.0, 1.0)
         t2_jame = K.permuted(t2, (1, 2, 0, 3))                   # [j,a,m,e] = t2[m,j,a,e]
-        ct("jame,meib->jaib", t2_jame, I["W2"], out=R, alpha=1.0, beta=0.0)        # t2_mjae W_mbie
+        ct("jame,ibme->jaib", t2_jame, I["W2"], out=R, alpha=1.0, beta=0.0)        # t2_mjae W_mbie
         K.strided_axpby(rg, R.permute(2, 0, 1, 3), 1.0, 1.0)
         del R, t2_jame
         if not ccd:
@@ -505,11 +505,11 @@ class CCwfn(object):
 
     def build_Wmbej(self, o, v, ERI, L, t1, t2):
         self._own(ERI, L)
-        return K.permuted(self._I(self.H.F, t1, t2)["W1"], (0, 3, 1, 2))          # [m,e,j,b] -> [m,b,e,j]
+        return K.permuted(self._I(self.H.F, t1, t2)["W1"], (2, 1, 3, 0))          # [j,b,m,e] -> [m,b,e,j]
 
     def build_Wmbje(self, o, v, ERI, t1, t2):
         self._own(ERI)
-        return K.permuted(self._I(self.H.F, t1, t2)["W2"], (0, 3, 2, 1))          # [m,e,j,b] -> [m,b,j,e]
+        return K.permuted(self._I(self.H.F, t1, t2)["W2"], (2, 1, 0, 3))          # [j,b,m,e] -> [m,b,j,e]
 
     def build_Zmbij(self, o, v, ERI, t1, t2):
         self._own(ERI)

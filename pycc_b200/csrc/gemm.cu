@@ -984,6 +984,7 @@ extern "C" int b200cc_dgemm(const b200cc_gemm_desc* d, void* stream) {
     };
     const double c4 = cost(128, 4, 128, 2, 1.0), c5 = cost(80, 2, 128, 4, 0.97);
     cfg = (d->M >= 80 && c5 < 0.97 * c4) ? 5 : 4;
+    if (tma_ok) cfg += 2;   // same tiles, operands staged by the TMA unit instead of cp.async producer warps
   }
   int rc;
   if (cfg == 2) rc = dispatch<CfgB, false>(p, ta, tb, v2, st);
@@ -992,6 +993,9 @@ extern "C" int b200cc_dgemm(const b200cc_gemm_desc* d, void* stream) {
   else if (cfg == 6) {
     if (!tma_ok) { set_error("b200cc_dgemm: config 6 (TMA) needs K-major 16-byte aligned operands without an address table"); return 1; }
     rc = launch_tma<CfgB>(p, st);
+  } else if (cfg == 7) {
+    if (!tma_ok) { set_error("b200cc_dgemm: config 7 (TMA) needs K-major 16-byte aligned operands without an address table"); return 1; }
+    rc = launch_tma<CfgC>(p, st);
   }
   else { set_error("b200cc_dgemm: unknown tile config %d", cfg); return 1; }
   if (rc) return rc;
