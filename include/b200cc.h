@@ -60,6 +60,9 @@ typedef struct {
   int table_align16;               /* table mode: caller vouches every address is 16-byte aligned */
   int ksplit;
   double* workspace;
+  const int* bcoords;              /* device, [batch][4] or NULL: per-batch INDEX of {A1,B1,A2,B2} along each operand's own
+                                      batch stride (counts nbA1..nbB2); C stays strided.  K-major TMA kernels only ((T)) */
+  int nbA1, nbB1, nbA2, nbB2;
   int config;                      /* kernel: 0 auto (tile by a cost model, TMA when eligible); 2 = plain 128x128 multistage kernel (8 warps,
                                       __syncthreads pipeline; kept as a cross-check); 4 = 128x128 warp-specialised
                                       (8 DMMA warps + 4 cp.async producer warps, mbarrier pipeline); 5 = 80x128 ditto;

@@ -42,6 +42,8 @@ class GemmDesc(C.Structure):
         ("table_align16", C.c_int),
         ("ksplit", C.c_int),
         ("workspace", dptr),
+        ("bcoords", dptr),
+        ("nbA1", C.c_int), ("nbB1", C.c_int), ("nbA2", C.c_int), ("nbB2", C.c_int),
         ("config", C.c_int),
     ]
 

@@ -49,7 +49,7 @@ def triples_list(no):
 class TriplesEngine:
     """Owns the constant operands of the (T) GEMMs for one wavefunction state."""
 
-    def __init__(self, ccwfn, t1=None, t2=None, q_bytes=None):
+    def __init__(self, ccwfn, t1=None, t2=None, q_bytes=None, use_tma=True):
         self.w = ccwfn
         H = ccwfn.H
         self.no, self.nv = ccwfn.no, ccwfn.nv
@@ -61,6 +61,14 @@ class TriplesEngine:
         self.Y = K.permuted(H.block("ooov"), (0, 1, 3, 2), -1.0)
         self.fov = H.F[ccwfn.o, ccwfn.v]
         self.dev = self.t2.device
+        # TMA path (K-major operands for cp.async.bulk.tensor): needs even o, v (16-byte pitches) and one
+        # constant transposed copy of <mb|ef>,  G[i,a,b,e] = <ib|ea>-slab = ovvv[i,e,a,b], built once per H
+        self.tma = (self.nv % 2 == 0) and (self.no % 2 == 0) and use_tma
+        if self.tma:
+            if "ovvv_iabe" not in H._derived:
+                H._derived["ovvv_iabe"] = K.permuted(self.ovvv, (0, 2, 3, 1))
+            self.G = H._derived["ovvv_iabe"]
+            self.t2p = K.permuted(self.t2, (0, 2, 3, 1))          # [i,a,b,m] = t2[i,m,a,b]
         nv = self.nv
         per = 6 * nv ** 3 * 8
         if q_bytes is None:
@@ -103,8 +111,21 @@ class TriplesEngine:
         """Launch the 6*len(trip) two-segment GEMMs; returns the Q buffer ([nb][6][v^3])."""
         nb = len(trip)
         Q = self.qbuf(nb) if Q is None else Q
-        tab, aligned = self.table(trip, Q)
         no, nv = self.no, self.nv
+        if self.tma:
+            T = np.asarray(trip, dtype=np.int64).reshape(-1, 3)
+            co = np.empty((nb, 6, 4), dtype=np.int32)
+            for q, (x, (p1, q1), (p2, q2)) in enumerate(_TERMS):
+                co[:, q, 0] = T[:, x]
+                co[:, q, 1] = T[:, p1] * no + T[:, q1]
+                co[:, q, 2] = T[:, x]
+                co[:, q, 3] = T[:, p2] * no + T[:, q2]
+            co = torch.from_numpy(co.reshape(nb * 6, 4)).to(self.dev)
+            K.dgemm(nv * nv, nv, nv, self.G, nv, 0, self.t2, nv, 0, Q, nv, 1.0, 0.0, batch=6 * nb,
+                    sA=nv ** 3, sB=nv * nv, sC=nv ** 3, seg2=(self.t2p, no, self.Y, no, no, no * nv * nv, nv * no),
+                    bcoords=co, nbatch=(no, no * no, no, no * no), ksplit=1)
+            return Q
+        tab, aligned = self.table(trip, Q)
         K.dgemm(nv * nv, nv, nv, self.ovvv, nv * nv, 1, self.t2, nv, 0, Q, nv, 1.0, 0.0,
                 batch=6 * nb, seg2=(self.t2, nv * nv, self.Y, no, no, 0, 0),
                 table=tab, table_align16=aligned, ksplit=1)

@@ -48,6 +48,8 @@ struct KParams {
   int ksplit, batch, cvec, nfast;
   int units;
   double* ws;
+  const int* bcoords;
+  int nbA1, nbB1, nbA2, nbB2;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -667,7 +669,11 @@ __global__ void __launch_bounds__(CF::NT + WS_PRODUCER_THREADS, 1)
       uint32_t phase = 0;
       for (int u = blockIdx.x; u < p.units; u += G) {
         const Unit w = decode_unit<CF>(p, u);
-        const int bA1 = p.sA1 ? w.b : 0, bB1 = p.sB1 ? w.b : 0, bA2 = p.sA2 ? w.b : 0, bB2 = p.sB2 ? w.b : 0;
+        int bA1 = p.sA1 ? w.b : 0, bB1 = p.sB1 ? w.b : 0, bA2 = p.sA2 ? w.b : 0, bB2 = p.sB2 ? w.b : 0;
+        if (p.bcoords) {   // (T): each batch entry names its own slab of every operand
+          const int4 c = reinterpret_cast<const int4*>(p.bcoords)[w.b];
+          bA1 = c.x; bB1 = c.y; bA2 = c.z; bB2 = c.w;
+        }
         for (int t = 0; t < w.nkt; ++t) {
           mbar_wait(empty_bar + stage, phase ^ 1u);
           unsigned char* As = tiles + stage * STAGE_BYTES;
@@ -827,11 +833,12 @@ static int launch_tma(KParams& p, cudaStream_t st) {
   p.units = (int)units;
   p.nfast = p.tiles_n < p.tiles_m ? 1 : 0;
   CUtensorMap tA1, tB1, tA2, tB2;
-  if (make_tmap(&tA1, p.A1, p.M, p.K1, p.lda1, p.sA1, p.batch, CF::BM)) return 1;
-  if (make_tmap(&tB1, p.B1, p.N, p.K1, p.ldb1, p.sB1, p.batch, CF::BN)) return 1;
+  const bool bc = p.bcoords != nullptr;
+  if (make_tmap(&tA1, p.A1, p.M, p.K1, p.lda1, p.sA1, bc ? p.nbA1 : p.batch, CF::BM)) return 1;
+  if (make_tmap(&tB1, p.B1, p.N, p.K1, p.ldb1, p.sB1, bc ? p.nbB1 : p.batch, CF::BN)) return 1;
   if (p.K2 > 0) {
-    if (make_tmap(&tA2, p.A2, p.M, p.K2, p.lda2, p.sA2, p.batch, CF::BM)) return 1;
-    if (make_tmap(&tB2, p.B2, p.N, p.K2, p.ldb2, p.sB2, p.batch, CF::BN)) return 1;
+    if (make_tmap(&tA2, p.A2, p.M, p.K2, p.lda2, p.sA2, bc ? p.nbA2 : p.batch, CF::BM)) return 1;
+    if (make_tmap(&tB2, p.B2, p.N, p.K2, p.ldb2, p.sB2, bc ? p.nbB2 : p.batch, CF::BN)) return 1;
   } else {
     tA2 = tA1;
     tB2 = tB1;
@@ -946,6 +953,8 @@ extern "C" int b200cc_dgemm(const b200cc_gemm_desc* d, void* stream) {
   p.ksplit = ksplit; p.batch = d->batch; p.ws = d->workspace;
   p.kt_per_split = (p.kt_total + ksplit - 1) / ksplit;
   if (p.kt_per_split < 1) p.kt_per_split = 1;
+  p.bcoords = d->bcoords;
+  p.nbA1 = d->nbA1; p.nbB1 = d->nbB1; p.nbA2 = d->nbA2; p.nbB2 = d->nbB2;
 
   // 16-byte vector paths need every address/pitch/stride to be a multiple of 2 doubles.
   bool va, vb, vc;
@@ -969,6 +978,10 @@ extern "C" int b200cc_dgemm(const b200cc_gemm_desc* d, void* stream) {
   const int ta = d->transA ? 1 : 0, tb = d->transB ? 1 : 0;
 
   const bool tma_ok = !ta && !tb && !d->table && v2 && d->K1 > 0;
+  if (d->bcoords && !tma_ok) {
+    set_error("b200cc_dgemm: bcoords needs the TMA path (K-major, 16-byte aligned operands and strides)");
+    return 1;
+  }
   // tile configuration: 0 = auto
   int cfg = d->config;
   if (cfg == 0) {
@@ -986,6 +999,7 @@ extern "C" int b200cc_dgemm(const b200cc_gemm_desc* d, void* stream) {
     cfg = (d->M >= 80 && c5 < 0.97 * c4) ? 5 : 4;
     if (tma_ok) cfg += 2;   // same tiles, operands staged by the TMA unit instead of cp.async producer warps
   }
+  if (d->bcoords && cfg != 6 && cfg != 7) { set_error("b200cc_dgemm: bcoords is only implemented by the TMA kernels (config 6/7)"); return 1; }
   int rc;
   if (cfg == 2) rc = dispatch<CfgB, false>(p, ta, tb, v2, st);
   else if (cfg == 4) rc = dispatch<CfgB, true>(p, ta, tb, v2, st);

@@ -56,7 +56,8 @@ def auto_ksplit(M, N, K, batch):
 
 
 def dgemm(M, N, K, A, lda, transA, B, ldb, transB, Cmat, ldc, alpha=1.0, beta=0.0,
-          batch=1, sA=0, sB=0, sC=0, seg2=None, table=None, table_align16=False, ksplit=None, config=0):
+          batch=1, sA=0, sB=0, sC=0, seg2=None, table=None, table_align16=False, ksplit=None, config=0,
+          bcoords=None, nbatch=None):
     """C[b] = alpha * (opA[b] opB[b]^T [+ second K segment]) + beta * C[b]; see b200cc_dgemm.
 
     A, B, Cmat: tensor, (tensor, element offset) or raw address.  seg2 = (A2, lda2, B2, ldb2, K2, sA2, sB2).
@@ -81,6 +82,10 @@ def dgemm(M, N, K, A, lda, transA, B, ldb, transB, Cmat, ldc, alpha=1.0, beta=0.
         ksplit = auto_ksplit(M, N, K + K2, batch)
     d.ksplit = int(ksplit)
     d.config = int(config) if config else DEFAULT_GEMM_CONFIG
+    if bcoords is not None:
+        # per-batch operand indices (int32 [batch,4]) + the extent of each operand's batch dimension
+        d.bcoords = _lib.ptr(bcoords)
+        d.nbA1, d.nbB1, d.nbA2, d.nbB2 = (int(x) for x in nbatch)
     ws = None
     if ksplit > 1:
         dev = _dev(table if table is not None else Cmat)

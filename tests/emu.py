@@ -73,9 +73,18 @@ class EmuLib:
                 return np.zeros((rows, 0))
             return _arr(addr, (rows, K), (1, ld) if trans else (ld, 1))
 
+        bc = None
+        if d.bcoords:
+            bc = _ints(d.bcoords, 4 * d.batch).reshape(d.batch, 4)
         for b in range(d.batch):
             if tab is not None:
                 a1, b1, a2, b2, c = (int(x) for x in tab[b])
+            elif bc is not None:
+                a1 = d.A1 + 8 * int(bc[b, 0]) * d.strideA1
+                b1 = d.B1 + 8 * int(bc[b, 1]) * d.strideB1
+                a2 = (d.A2 or 0) + 8 * int(bc[b, 2]) * d.strideA2
+                b2 = (d.B2 or 0) + 8 * int(bc[b, 3]) * d.strideB2
+                c = d.C + 8 * b * d.strideC
             else:
                 a1 = d.A1 + 8 * b * d.strideA1
                 b1 = d.B1 + 8 * b * d.strideB1
