@@ -21,6 +21,7 @@
 namespace b200cc {
 
 constexpr int BK = 16, STAGES = 4;
+constexpr int FULL_CODE = 99;   // consume_unit: every fragment of the warp is in range
 constexpr int LDK = BK + 4;  // K-major shared row pitch (doubles): 160 B -> consecutive rows 32 B apart mod 128
 
 template <int WM_, int WN_, int MI_, int NI_>
@@ -358,9 +359,9 @@ __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.al
 // Ragged tiles: a predicated-off DMMA still occupies the tensor pipe for its 16 cycles (measured with ncu:
 // pipe-active time of the N = 280 (T) GEMM equalled 3 FULL N tiles), so out-of-range fragments must be
 // skipped by real, warp-uniform control flow.  In-range fragments of a warp form a prefix (fragments are
-// interleaved over the warps); `code` selects one of 8 straight-line DMMA blocks:
-//   rows  : all MI fragments, or the first ceil(MI/2)         (code >> 2)
-//   cols  : the first 1/4, 2/4, 3/4 or 4/4 of the NI fragments (code & 3)
+// interleaved over the warps); `code` selects one of 16 straight-line DMMA blocks:
+//   rows  : all MI fragments, or the first ceil(MI/2)   (code >> 3)
+//   cols  : the first 1 .. NI fragments                 ((code & 7) + 1)
 template <class CF, bool TA, bool TB>
 __device__ __forceinline__ void load_frags(const double* __restrict__ As, const double* __restrict__ Bs, int ks,
                                            double (&a)[CF::MI], double (&b)[CF::NI], int wm, int wn, int g, int q) {
@@ -388,18 +389,19 @@ __device__ __forceinline__ void mma_block(double (&acc)[CF::MI][CF::NI][2], cons
 template <class CF>
 __device__ __forceinline__ void mma_select(double (&acc)[CF::MI][CF::NI][2], const double (&a)[CF::MI],
                                            const double (&b)[CF::NI], int code) {
-  constexpr int MI = CF::MI, MH = (CF::MI + 1) / 2, NQ = CF::NI / 4;
-  static_assert(CF::NI % 4 == 0, "NI must be a multiple of 4");
+  constexpr int MI = CF::MI, MH = (CF::MI + 1) / 2, NI = CF::NI;
+  static_assert(NI == 4 || NI == 8, "mma_select is written for NI = 4 or 8");
+  // code = 8 * (rows: 0 = all MI, 1 = first ceil(MI/2)) + (in-range N fragments - 1)
+#define B200CC_ARM(C, MC, NC) \
+  case C: mma_block<CF, MC, (NC <= NI ? NC : NI)>(acc, a, b); break;
   switch (code) {
-    case 3: mma_block<CF, MI, 4 * NQ>(acc, a, b); break;   // full tile: the hot path
-    case 0: mma_block<CF, MI, 1 * NQ>(acc, a, b); break;
-    case 1: mma_block<CF, MI, 2 * NQ>(acc, a, b); break;
-    case 2: mma_block<CF, MI, 3 * NQ>(acc, a, b); break;
-    case 4: mma_block<CF, MH, 1 * NQ>(acc, a, b); break;
-    case 5: mma_block<CF, MH, 2 * NQ>(acc, a, b); break;
-    case 6: mma_block<CF, MH, 3 * NQ>(acc, a, b); break;
-    default: mma_block<CF, MH, 4 * NQ>(acc, a, b); break;
+    B200CC_ARM(0, MI, 1) B200CC_ARM(1, MI, 2) B200CC_ARM(2, MI, 3) B200CC_ARM(3, MI, 4)
+    B200CC_ARM(4, MI, 5) B200CC_ARM(5, MI, 6) B200CC_ARM(6, MI, 7) B200CC_ARM(7, MI, 8)
+    B200CC_ARM(8, MH, 1) B200CC_ARM(9, MH, 2) B200CC_ARM(10, MH, 3) B200CC_ARM(11, MH, 4)
+    B200CC_ARM(12, MH, 5) B200CC_ARM(13, MH, 6) B200CC_ARM(14, MH, 7)
+    default: mma_block<CF, MH, NI>(acc, a, b); break;
   }
+#undef B200CC_ARM
 }
 
 // The k-loop of one work unit for one consumer warp.  Fragments are double-buffered across the four
@@ -440,7 +442,7 @@ __device__ __forceinline__ void consume_unit(double (&acc)[CF::MI][CF::NI][2], c
   }
 #define B200CC_MMA_FULL(A_, B_) mma_block<CF, CF::MI, CF::NI>(acc, A_, B_)
 #define B200CC_MMA_SEL(A_, B_) mma_select<CF>(acc, A_, B_, code)
-  if (code == 3) {
+  if (code == FULL_CODE) {
     B200CC_KLOOP(B200CC_MMA_FULL)      // full tile: branch-free hot loop
   } else {
     B200CC_KLOOP(B200CC_MMA_SEL)
@@ -546,8 +548,8 @@ __global__ void __launch_bounds__(CF::NT + WS_PRODUCER_THREADS, 1) dgemm_ws_kern
     if (mc == 0 || nc == 0) {
       idle_unit(full_bar, empty_bar, stage, phase, w.nkt, lane);
     } else {
-      constexpr int NQ = NI / 4, MH = (MI + 1) / 2;
-      const int code = (mc <= MH ? 4 : 0) + (nc + NQ - 1) / NQ - 1;
+      constexpr int MH = (MI + 1) / 2;
+      const int code = (mc == MI && nc == NI) ? FULL_CODE : (mc <= MH ? 8 : 0) + nc - 1;
       consume_unit<CF, TA, TB>(acc, smem, full_bar, empty_bar, stage, phase, w.nkt, code, wm, wn, g, q, lane);
     }
 
@@ -720,8 +722,8 @@ __global__ void __launch_bounds__(CF::NT + WS_PRODUCER_THREADS, 1)
     if (mc == 0 || nc == 0) {
       idle_unit(full_bar, empty_bar, stage, phase, w.nkt, lane);
     } else {
-      constexpr int NQ = NI / 4, MH = (MI + 1) / 2;
-      const int code = (mc <= MH ? 4 : 0) + (nc + NQ - 1) / NQ - 1;
+      constexpr int MH = (MI + 1) / 2;
+      const int code = (mc <= MH ? 8 : 0) + nc - 1;
       double a0[MI], b0[NI], a1[MI], b1[NI];
       if (w.nkt > 0) {
         mbar_wait(full_bar + stage, phase);
