@@ -204,6 +204,46 @@ def t3d_ijk(o, v, i, j, k, t1, t2, Woovv, F, contract, WithDenom=True):
     return d3
 
 
+def _abc_denominator(t3, F, o, v, a, b, c):
+    """t3[i,j,k] / (e_i + e_j + e_k - e_a - e_b - e_c) through the d1 kernel on the (ij, k) view."""
+    no = t3.shape[0]
+    eo, ev = _eps(F, o, v)
+    dev = t3.device
+    rows = torch.empty((no, no), dtype=F64, device=dev)
+    K.strided_axpby(rows, eo.view(-1, 1).expand(no, no), 1.0, 0.0)
+    K.strided_axpby(rows, eo.view(1, -1).expand(no, no), 1.0, 1.0)
+    shift = float(ev[a] + ev[b] + ev[c])
+    ones = torch.ones(no * no, dtype=F64, device=dev)
+    rows = rows.view(-1)
+    K.axpbyz(1.0, rows, -shift, ones, rows)
+    negk = torch.empty(no, dtype=F64, device=dev)
+    K.axpbyz(-1.0, eo, 0.0, None, negk)
+    return K.div_d1(t3.contiguous().view(no * no, no), rows, negk).view(no, no, no)
+
+
+def t3c_abc(o, v, a, b, c, t2, Wvvvo, Wovoo, F, contract, WithDenom=True):
+    """Connected t3 for fixed (a,b,c), all (i,j,k) (reference: cctriples.py:75-105); generic in the W blocks."""
+    t3 = contract('ei,kje->ijk', Wvvvo[b, a], t2[:, :, c])
+    for sub, (x, y), z in (('ei,jke->ijk', (c, a), b), ('ek,jie->ijk', (a, c), b), ('ek,ije->ijk', (b, c), a),
+                           ('ej,ike->ijk', (c, b), a), ('ej,kie->ijk', (a, b), c)):
+        contract(sub, Wvvvo[x, y], t2[:, :, z], out=t3, alpha=1.0, beta=1.0)
+    for sub, x, (y, z) in (('mjk,im->ijk', c, (a, b)), ('mkj,im->ijk', b, (a, c)), ('mij,km->ijk', b, (c, a)),
+                           ('mji,km->ijk', a, (c, b)), ('mki,jm->ijk', a, (b, c)), ('mik,jm->ijk', c, (b, a))):
+        contract(sub, Wovoo[:, x], t2[:, :, y, z], out=t3, alpha=-1.0, beta=1.0)
+    return _abc_denominator(t3, F, o, v, a, b, c) if WithDenom else t3
+
+
+def t3d_abc(o, v, a, b, c, t1, t2, Woovv, F, contract, WithDenom=True):
+    """Disconnected t3 for fixed (a,b,c) (reference: cctriples.py:149-173)."""
+    Fov = F[o, v]
+    t3 = contract('ij,k->ijk', Woovv[:, :, a, b], t1[:, c])
+    for sub, X, y in (('ik,j->ijk', Woovv[:, :, a, c], t1[:, b]), ('jk,i->ijk', Woovv[:, :, b, c], t1[:, a]),
+                      ('ij,k->ijk', t2[:, :, a, b], Fov[:, c]), ('ik,j->ijk', t2[:, :, a, c], Fov[:, b]),
+                      ('jk,i->ijk', t2[:, :, b, c], Fov[:, a])):
+        contract(sub, X, y, out=t3, alpha=1.0, beta=1.0)
+    return _abc_denominator(t3, F, o, v, a, b, c) if WithDenom else t3
+
+
 def t_vikings(ccwfn):
     """E(T), Helgaker-Jorgensen-Olsen full-loop formulation (reference: cctriples.py:243-307).  Cross-check
     only (6x the work of t_tjl): t3 tiles come from the same GEMM + assemble kernels, the X1/X2
@@ -256,36 +296,13 @@ def t_vikings_inverted(ccwfn):
     Fov = K.permuted(H.F[o, v], (0, 1))
     X1 = torch.zeros((nv, no), dtype=F64, device=dev)
     X2 = torch.zeros((nv, nv, no, no), dtype=F64, device=dev)
-    # Wvvvo[x,y,e,i] = ovvv[i,e,y,x] -> Wv[x,y][e,i];  Wovoo[m,x,j,k] = ooov[j,k,m,x]
+    # Wvvvo[x,y,e,i] = ovvv[i,e,y,x];  Wovoo[m,x,j,k] = ooov[j,k,m,x]   (views, no copies)
     Wvvvo = ovvv.permute(3, 2, 1, 0)
     Wovoo = ooov.permute(2, 3, 0, 1)
-    t2v = K.permuted(t2, (2, 3, 0, 1))                 # [a,b,i,j]
-    # denominators through the d1 kernel on the (ij, k) view: t3[(i,j),k] / (rows[(i,j)] - negk[k]),
-    # rows = e_i + e_j - (e_a+e_b+e_c), negk = -e_k
-    eo, ev = ccwfn.eps_o, ccwfn.eps_v
-    rows0 = torch.empty((no, no), dtype=F64, device=dev)
-    K.strided_axpby(rows0, eo.view(-1, 1).expand(no, no), 1.0, 0.0)
-    K.strided_axpby(rows0, eo.view(1, -1).expand(no, no), 1.0, 1.0)
-    rows0 = rows0.view(-1)
-    ones = torch.ones(no * no, dtype=F64, device=dev)
-    rows = torch.empty(no * no, dtype=F64, device=dev)
-    negk = torch.empty(no, dtype=F64, device=dev)
-    K.axpbyz(-1.0, eo, 0.0, None, negk)
-    ev_h = ev.tolist()
     for a in range(nv):
         for b in range(nv):
             for c in range(nv):
-                t3 = ct('ei,kje->ijk', Wvvvo[b, a], t2[:, :, c])
-                for sub, (x, y), z in (('ei,jke->ijk', (c, a), b), ('ek,jie->ijk', (a, c), b),
-                                       ('ek,ije->ijk', (b, c), a), ('ej,ike->ijk', (c, b), a),
-                                       ('ej,kie->ijk', (a, b), c)):
-                    ct(sub, Wvvvo[x, y], t2[:, :, z], out=t3, alpha=1.0, beta=1.0)
-                for sub, x, (y, z) in (('mjk,im->ijk', c, (a, b)), ('mkj,im->ijk', b, (a, c)),
-                                       ('mij,km->ijk', b, (c, a)), ('mji,km->ijk', a, (c, b)),
-                                       ('mki,jm->ijk', a, (b, c)), ('mik,jm->ijk', c, (b, a))):
-                    ct(sub, Wovoo[:, x], t2v[y, z], out=t3, alpha=-1.0, beta=1.0)
-                K.axpbyz(1.0, rows0, -(ev_h[a] + ev_h[b] + ev_h[c]), ones, rows)
-                t3 = K.div_d1(t3.view(no * no, no), rows, negk).view(no, no, no)
+                t3 = t3c_abc(o, v, a, b, c, t2, Wvvvo, Wovoo, H.F, ct, True)
                 u = K.permuted(t3, (0, 1, 2))
                 K.strided_axpby(u, t3.permute(2, 1, 0), -1.0, 1.0)
                 w = K.permuted(t3, (0, 1, 2), 2.0)

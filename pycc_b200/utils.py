@@ -14,6 +14,58 @@ import torch
 from . import kernels as K
 
 
+# ---- tensor helpers with the reference's names (utils.py:14-191).  pycc dispatches these on numpy-vs-torch; here
+# every amplitude is a CUDA tensor, so they are thin plumbing over torch allocation / the package's own kernels.
+def zeros_like(a):
+    return torch.zeros_like(a)
+
+
+def zeros(shape, like):
+    return torch.zeros(shape, dtype=like.dtype, device=like.device)
+
+
+def real_zeros(shape, like):
+    return torch.zeros(shape, dtype=like.real.dtype, device=like.device)
+
+
+def clone(a, device=None):
+    out = torch.empty(tuple(a.shape), dtype=a.dtype, device=a.device)
+    K.strided_axpby(out, a, 1.0, 0.0)
+    return out.to(device) if device is not None else out
+
+
+def diag(a):
+    return torch.diagonal(a) if a.dim() == 2 else torch.diag(a)
+
+
+def dot(a, b):
+    """1-D dot product on the device (b200cc_multi_dot); returns a 0-d tensor."""
+    return K.multi_dot(a.contiguous().view(-1), [b.contiguous().view(-1)])[0]
+
+
+def sqrt(a):
+    return torch.sqrt(a) if isinstance(a, torch.Tensor) else np.sqrt(a)
+
+
+def absolute(a):
+    return torch.abs(a) if isinstance(a, torch.Tensor) else np.abs(a)
+
+
+def solve(A, b):
+    """(m+1)x(m+1) Pulay systems: solved on the host (utils.py:348 uses torch/np.linalg.solve)."""
+    if isinstance(A, torch.Tensor):
+        return torch.from_numpy(np.linalg.solve(A.cpu().numpy(), b.cpu().numpy())).to(A.device)
+    return np.linalg.solve(A, b)
+
+
+def reshape(a, shape):
+    return a.reshape(shape)
+
+
+def concatenate(arrays):
+    return torch.cat(arrays) if isinstance(arrays[0], torch.Tensor) else np.concatenate(arrays)
+
+
 class helper_diis(object):
     def __init__(self, t1, t2, max_diis, precision='DP'):
         self.max_diis = max_diis

@@ -294,3 +294,22 @@ def test_tiny_and_ragged_shapes(dev):
         cc = make_wfn(syn, "CCSD(T)")
         e = cc.solve_cc(1e-11, 1e-11)
         assert abs(float(e) - (e_ref + et)) < 1e-10, (no, nv)
+
+
+def test_abc_batched_t3_and_helpers(golden, dev):
+    """t3c_abc / t3d_abc (cctriples.py:75-105, 149-173) and the utils helpers keep the reference's results."""
+    from pycc_b200 import utils
+    g, syn = golden
+    cc = make_wfn(syn, "CCSD(T)")
+    cc.t1, cc.t2 = T(g["conv_t1"]), T(g["conv_t2"])
+    o, v, H = cc.o, cc.v, cc.H
+    a, b, c = 2, 1, 0
+    t3c = cctriples.t3c_abc(o, v, a, b, c, cc.t2, H.ERI[v, v, v, o], H.ERI[o, v, o, o], H.F, cc.contract, True)
+    t3d = cctriples.t3d_abc(o, v, a, b, c, cc.t1, cc.t2, H.ERI[o, o, v, v], H.F, cc.contract, True)
+    assert np.abs(t3c.cpu().numpy() - g["t3c_abc_210"]).max() < 1e-12
+    assert np.abs(t3d.cpu().numpy() - g["t3d_abc_210"]).max() < 1e-12
+    x = utils.clone(cc.t2)
+    assert x.data_ptr() != cc.t2.data_ptr() and torch.equal(x, cc.t2)
+    d = float(utils.dot(cc.t2.reshape(-1), cc.t2.reshape(-1)))
+    assert abs(d - float(np.sum(g["conv_t2"] ** 2))) < 1e-12
+    assert float(utils.zeros_like(cc.t1).abs().max()) == 0.0
