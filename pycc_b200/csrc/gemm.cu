@@ -16,6 +16,7 @@
 //   * Two K-segments can be chained into the same accumulators ((T): particle + hole term);
 //     split-K goes through a workspace and a deterministic reduction; batches by stride or address table.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace b200cc {
@@ -144,6 +145,20 @@ __device__ __forceinline__ void compute_tile(const double* __restrict__ As, cons
       }
     }
   }
+}
+
+// Persistent scheduling (one CTA per SM striding over the units) pipelines across tile boundaries, which pays
+// for short-K units.  For long-K units it buys nothing, and the fixed unit->CTA map lets co-running CTAs drift
+// apart in k, so operand panels shared by neighbouring tiles stop meeting in L2 (ncu: 1.09 TB of DRAM reads for the
+// o=40,v=300 ladder, 16x the algorithmic bytes).  Long-K GEMMs therefore launch one CTA per unit: the hardware
+// hands out units in order as SMs free up, so neighbouring units start together.
+static inline int pick_grid(const KParams& p) {
+  const int nsm = sm_count();
+  if (p.units <= nsm) return p.units;
+  const int force = getenv("B200CC_GEMM_PERSISTENT") ? atoi(getenv("B200CC_GEMM_PERSISTENT")) : -1;
+  if (force == 1) return nsm;
+  if (force == 0) return p.units;
+  return p.kt_per_split >= 512 ? p.units : nsm;
 }
 
 struct Unit {
@@ -851,8 +866,7 @@ static int launch_tma(KParams& p, cudaStream_t st) {
     B200CC_CUDA_OK(cudaFuncSetAttribute(dgemm_tma_kernel<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
-  const int nsm = sm_count();
-  const int grid = units < nsm ? (int)units : nsm;
+  const int grid = pick_grid(p);
   dgemm_tma_kernel<CF><<<grid, CF::NT + WS_PRODUCER_THREADS, SMEM, st>>>(p, tA1, tB1, tA2, tB2);
   return check_launch("dgemm_tma_kernel");
 }
@@ -897,8 +911,7 @@ static int dispatch(KParams& p, int ta, int tb, bool v2, cudaStream_t st) {
   p.units = (int)units;
   // raster: the index with FEWER tiles varies fastest, so co-running CTAs share the larger operand panel in L2
   p.nfast = p.tiles_n < p.tiles_m ? 1 : 0;
-  const int nsm = sm_count();
-  const int grid = units < nsm ? (int)units : nsm;
+  const int grid = pick_grid(p);
 #define B200CC_GO(TA, TB)                                                                         \
   do {                                                                                            \
     if constexpr (WS) return v2 ? launch_ws<CF, TA, TB, 2>(p, grid, st) : launch_ws<CF, TA, TB, 1>(p, grid, st); \

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Ladder GEMM (o=40, v=300 shape, a-slice of NA rows) with tile config 4 vs 5: time + (under ncu) DRAM traffic."""
+"""Ladder GEMM (o=40, v=300 shape, NA rows of a): time (and, under ncu, DRAM traffic) of the default kernel."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pycc_b200 import kernels as K
@@ -10,12 +10,10 @@ tau = torch.randn(o * o, v * v, dtype=torch.float64, device=dev)
 vvvv = torch.randn(na * v, v * v, dtype=torch.float64, device=dev)
 r2 = torch.zeros(o * o, v * v, dtype=torch.float64, device=dev)
 fl = 2.0 * o * o * na * v * v * v
-for cfg in (4, 5):
-    K.dgemm(o * o, na * v, v * v, tau, v * v, 0, vvvv, v * v, 0, r2, v * v, 0.5, 1.0, config=cfg, ksplit=1)
-    torch.cuda.synchronize()
+for rep in range(2):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    K.dgemm(o * o, na * v, v * v, tau, v * v, 0, vvvv, v * v, 0, r2, v * v, 0.5, 1.0, config=cfg, ksplit=1)
+    K.dgemm(o * o, na * v, v * v, tau, v * v, 0, vvvv, v * v, 0, r2, v * v, 0.5, 1.0, ksplit=1)
     b.record()
     torch.cuda.synchronize()
-    print("cfg", cfg, "na", na, "ms", a.elapsed_time(b), "TFLOP/s", fl / a.elapsed_time(b) / 1e9, flush=True)
+    print("persistent=%s" % os.environ.get("B200CC_GEMM_PERSISTENT", "auto"), "na", na, "ms", a.elapsed_time(b), "TFLOP/s", fl / a.elapsed_time(b) / 1e9, flush=True)
