@@ -60,6 +60,8 @@ typedef struct {
   int table_align16;               /* table mode: caller vouches every address is 16-byte aligned */
   int ksplit;
   double* workspace;
+  int out_cube_nv;                 /* > 0: C is written 8x8x8-cube-blocked with row = x*nv + y, col = z (see b200cc_t_q_size);
+                                      TMA kernels only, beta must be 0 */
   const int* bcoords;              /* device, [batch][4] or NULL: per-batch INDEX of {A1,B1,A2,B2} along each operand's own
                                       batch stride (counts nbA1..nbB2); C stays strided.  K-major TMA kernels only ((T)) */
   int nbA1, nbB1, nbA2, nbB2;
@@ -126,7 +128,10 @@ int b200cc_multi_axpy(b200cc_i64 n, int m, const double* c, const double* const*
  * et_out[0] (+)= sum over the batch (accumulate != 0 adds to the existing value).
  * scratch >= number of CTAs doubles (b200cc_t_energy_scratch).                                   */
 b200cc_i64 b200cc_t_energy_scratch(int nv, int ntrip);
-int b200cc_t_energy_batch(int no, int nv, int ntrip, const int* ijk, const double* Q,
+/* doubles per Q array: nv^3 (q_blocked = 0), or ceil(nv/8)^3 * 512 when the GEMM wrote it as contiguous 8x8x8 cubes
+ * (b200cc_gemm_desc.out_cube_nv): element (x,y,z) at cube (x/8,y/8,z/8), offset (x%8)*64 + (y%8)*8 + z%8. */
+b200cc_i64 b200cc_t_q_size(int nv, int blocked);
+int b200cc_t_energy_batch(int no, int nv, int ntrip, const int* ijk, const double* Q, int q_blocked,
                           const double* t1, const double* t2, const double* oovv,
                           const double* fov, b200cc_i64 ldf, const double* eo, const double* ev,
                           double* et_out, int accumulate, double* scratch, void* stream);
@@ -134,7 +139,7 @@ int b200cc_t_energy_batch(int no, int nv, int ntrip, const int* ijk, const doubl
 /* The connected (w3_out, = t3c_ijk) and disconnected (v3_out, = t3d_ijk) t3 numerators of ONE triple
  * as (nv,nv,nv) arrays, w3 assembled from Q1..Q6 -- the per-triple parity hook for
  * cctriples.py:27-72 and 108-147.  with_denom != 0 divides both by D_ijkabc.  v3_out may be NULL. */
-int b200cc_t3_assemble(int no, int nv, int i, int j, int k, const double* Q,
+int b200cc_t3_assemble(int no, int nv, int i, int j, int k, const double* Q, int q_blocked,
                        const double* t1, const double* t2, const double* oovv,
                        const double* fov, b200cc_i64 ldf, const double* eo, const double* ev,
                        int with_denom, double* w3_out, double* v3_out, void* stream);

@@ -42,6 +42,7 @@ class GemmDesc(C.Structure):
         ("table_align16", C.c_int),
         ("ksplit", C.c_int),
         ("workspace", dptr),
+        ("out_cube_nv", C.c_int),
         ("bcoords", dptr),
         ("nbA1", C.c_int), ("nbB1", C.c_int), ("nbA2", C.c_int), ("nbB2", C.c_int),
         ("config", C.c_int),
@@ -68,9 +69,10 @@ SIGNATURES = {
     "b200cc_multi_dot": (C.c_int, [i64, dptr, C.c_int, C.POINTER(dptr), dptr, dptr, C.c_void_p]),
     "b200cc_multi_axpy": (C.c_int, [i64, C.c_int, C.POINTER(C.c_double), C.POINTER(dptr), dptr, C.c_void_p]),
     "b200cc_t_energy_scratch": (i64, [C.c_int, C.c_int]),
-    "b200cc_t_energy_batch": (C.c_int, [C.c_int, C.c_int, C.c_int, dptr, dptr, dptr, dptr, dptr, dptr, i64,
+    "b200cc_t_q_size": (i64, [C.c_int, C.c_int]),
+    "b200cc_t_energy_batch": (C.c_int, [C.c_int, C.c_int, C.c_int, dptr, dptr, C.c_int, dptr, dptr, dptr, dptr, i64,
                                         dptr, dptr, dptr, C.c_int, dptr, C.c_void_p]),
-    "b200cc_t3_assemble": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, dptr, dptr, dptr, dptr,
+    "b200cc_t3_assemble": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, dptr, C.c_int, dptr, dptr, dptr,
                                      dptr, i64, dptr, dptr, C.c_int, dptr, dptr, C.c_void_p]),
 }
 

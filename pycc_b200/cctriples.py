@@ -70,7 +70,9 @@ class TriplesEngine:
             self.G = H._derived["ovvv_iabe"]
             self.t2p = K.permuted(self.t2, (0, 2, 3, 1))          # [i,a,b,m] = t2[i,m,a,b]
         nv = self.nv
-        per = 6 * nv ** 3 * 8
+        # with the TMA GEMM, Q is written as contiguous 8x8x8 cubes (the energy kernel then reads 4 KB runs)
+        self.qsz = K.q_size(nv, self.tma)
+        per = 6 * self.qsz * 8
         if q_bytes is None:
             q_bytes = 8 << 30
             if self.dev.type == "cuda":
@@ -81,7 +83,7 @@ class TriplesEngine:
     def qbuf(self, nb):
         """The Q workspace ([nb][6][v^3] doubles) is kept per device across engines (grow-only), so repeated
         (T) evaluations do not pay a multi-GB cudaMalloc each."""
-        need = nb * 6 * self.nv ** 3
+        need = nb * 6 * self.qsz
         buf = _QCACHE.get(self.dev)
         if buf is None or buf.numel() < need:
             _QCACHE.pop(self.dev, None)
@@ -103,7 +105,7 @@ class TriplesEngine:
             tab[:, q, 1] = p_t2 + 8 * (T[:, p1] * no + T[:, q1]) * v2
             tab[:, q, 2] = p_t2 + 8 * T[:, x] * no * v2
             tab[:, q, 3] = p_Y + 8 * (T[:, p2] * no + T[:, q2]) * nv * no
-            tab[:, q, 4] = p_Q + 8 * (np.arange(nb) * 6 + q) * v3
+            tab[:, q, 4] = p_Q + 8 * (np.arange(nb) * 6 + q) * self.qsz
         aligned = bool(np.all(tab % 16 == 0))
         return torch.from_numpy(tab.reshape(nb * 6, 5)).to(self.dev), aligned
 
@@ -122,8 +124,8 @@ class TriplesEngine:
                 co[:, q, 3] = T[:, p2] * no + T[:, q2]
             co = torch.from_numpy(co.reshape(nb * 6, 4)).to(self.dev)
             K.dgemm(nv * nv, nv, nv, self.G, nv, 0, self.t2, nv, 0, Q, nv, 1.0, 0.0, batch=6 * nb,
-                    sA=nv ** 3, sB=nv * nv, sC=nv ** 3, seg2=(self.t2p, no, self.Y, no, no, no * nv * nv, nv * no),
-                    bcoords=co, nbatch=(no, no * no, no, no * no), ksplit=1)
+                    sA=nv ** 3, sB=nv * nv, sC=self.qsz, seg2=(self.t2p, no, self.Y, no, no, no * nv * nv, nv * no),
+                    bcoords=co, nbatch=(no, no * no, no, no * no), ksplit=1, out_cube_nv=nv)
             return Q
         tab, aligned = self.table(trip, Q)
         K.dgemm(nv * nv, nv, nv, self.ovvv, nv * nv, 1, self.t2, nv, 0, Q, nv, 1.0, 0.0,
@@ -140,14 +142,14 @@ class TriplesEngine:
             Q = self.build_q(chunk)
             ijk = torch.tensor(np.asarray(chunk, dtype=np.int32).reshape(-1, 3), dtype=torch.int32).to(self.dev)
             K.t_energy_batch(self.no, self.nv, ijk, Q, self.t1, self.t2, self.oovv, self.fov,
-                             w.eps_o, w.eps_v, et, accumulate=True)
+                             w.eps_o, w.eps_v, et, accumulate=True, blocked=self.tma)
         return et
 
     def t3_parts(self, i, j, k, with_denom):
         """(connected, disconnected) t3 numerators of one triple as (v,v,v) tensors."""
         Q = self.build_q([(i, j, k)])
         return K.t3_assemble(self.no, self.nv, i, j, k, Q, self.t1, self.t2, self.oovv, self.fov,
-                             self.w.eps_o, self.w.eps_v, with_denom)
+                             self.w.eps_o, self.w.eps_v, with_denom, blocked=self.tma)
 
 
 def t_tjl(ccwfn, triples=None):

@@ -52,6 +52,7 @@ struct KParams {
   double* ws;
   const int* bcoords;
   int nbA1, nbB1, nbA2, nbB2;
+  int cube_nv;   // > 0: C written as contiguous 8x8x8 cubes of (x = row / nv, y = row % nv, z = col)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -300,16 +301,22 @@ __global__ void __launch_bounds__(CF::NT, 1) dgemm_kernel(const KParams p) {
     else C = p.C + (i64)w.b * p.sC;
     const i64 ldo = split ? (i64)p.N : p.ldc;
     const double alpha = split ? 1.0 : p.alpha, beta = split ? 0.0 : p.beta;
-    const bool vec = split ? ((p.N & 1) == 0 && (((i64)p.M * p.N) & 1) == 0) : (p.cvec != 0);
+    const bool cube = !split && p.cube_nv > 0;
+    const bool vec = split ? ((p.N & 1) == 0 && (((i64)p.M * p.N) & 1) == 0) : (p.cvec != 0 || cube);
+    const int nc8 = (p.cube_nv + 7) >> 3;
 #pragma unroll
     for (int i = 0; i < MI; ++i) {
       const int row = w.m0 + 8 * (wm + CF::WARPS_M * i) + g;
       if (row >= p.M) continue;
+      const int cx = cube ? row / p.cube_nv : 0, cy = cube ? row - cx * p.cube_nv : 0;
 #pragma unroll
       for (int j = 0; j < NI; ++j) {
         const int col = w.n0 + 8 * (wn + CF::WARPS_N * j) + 2 * q;
         if (col >= p.N) continue;
-        double* c = C + (i64)row * ldo + col;
+        // (T): Q stored as 4 KB cubes so that the energy kernel reads it in fully contiguous runs
+        double* c = cube ? C + ((((i64)(cx >> 3) * nc8 + (cy >> 3)) * nc8 + (col >> 3)) << 9) + ((cx & 7) << 6) +
+                               ((cy & 7) << 3) + (col & 7)
+                         : C + (i64)row * ldo + col;
         double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
         if (vec && col + 1 < p.N) {
           if (beta != 0.0) {
@@ -576,16 +583,22 @@ __global__ void __launch_bounds__(CF::NT + WS_PRODUCER_THREADS, 1) dgemm_ws_kern
     else C = p.C + (i64)w.b * p.sC;
     const i64 ldo = split ? (i64)p.N : p.ldc;
     const double alpha = split ? 1.0 : p.alpha, beta = split ? 0.0 : p.beta;
-    const bool vec = split ? ((p.N & 1) == 0 && (((i64)p.M * p.N) & 1) == 0) : (p.cvec != 0);
+    const bool cube = !split && p.cube_nv > 0;
+    const bool vec = split ? ((p.N & 1) == 0 && (((i64)p.M * p.N) & 1) == 0) : (p.cvec != 0 || cube);
+    const int nc8 = (p.cube_nv + 7) >> 3;
 #pragma unroll
     for (int i = 0; i < MI; ++i) {
       const int row = w.m0 + 8 * (wm + CF::WARPS_M * i) + g;
       if (row >= p.M) continue;
+      const int cx = cube ? row / p.cube_nv : 0, cy = cube ? row - cx * p.cube_nv : 0;
 #pragma unroll
       for (int j = 0; j < NI; ++j) {
         const int col = w.n0 + 8 * (wn + CF::WARPS_N * j) + 2 * q;
         if (col >= p.N) continue;
-        double* c = C + (i64)row * ldo + col;
+        // (T): Q stored as 4 KB cubes so that the energy kernel reads it in fully contiguous runs
+        double* c = cube ? C + ((((i64)(cx >> 3) * nc8 + (cy >> 3)) * nc8 + (col >> 3)) << 9) + ((cx & 7) << 6) +
+                               ((cy & 7) << 3) + (col & 7)
+                         : C + (i64)row * ldo + col;
         double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
         if (vec && col + 1 < p.N) {
           if (beta != 0.0) {
@@ -776,16 +789,22 @@ __global__ void __launch_bounds__(CF::NT + WS_PRODUCER_THREADS, 1)
     else C = p.C + (i64)w.b * p.sC;
     const i64 ldo = split ? (i64)p.N : p.ldc;
     const double alpha = split ? 1.0 : p.alpha, beta = split ? 0.0 : p.beta;
-    const bool vec = split ? ((p.N & 1) == 0 && (((i64)p.M * p.N) & 1) == 0) : (p.cvec != 0);
+    const bool cube = !split && p.cube_nv > 0;
+    const bool vec = split ? ((p.N & 1) == 0 && (((i64)p.M * p.N) & 1) == 0) : (p.cvec != 0 || cube);
+    const int nc8 = (p.cube_nv + 7) >> 3;
 #pragma unroll
     for (int i = 0; i < MI; ++i) {
       const int row = w.m0 + 8 * (wm + CF::WARPS_M * i) + g;
       if (row >= p.M) continue;
+      const int cx = cube ? row / p.cube_nv : 0, cy = cube ? row - cx * p.cube_nv : 0;
 #pragma unroll
       for (int j = 0; j < NI; ++j) {
         const int col = w.n0 + 8 * (wn + CF::WARPS_N * j) + 2 * q;
         if (col >= p.N) continue;
-        double* c = C + (i64)row * ldo + col;
+        // (T): Q stored as 4 KB cubes so that the energy kernel reads it in fully contiguous runs
+        double* c = cube ? C + ((((i64)(cx >> 3) * nc8 + (cy >> 3)) * nc8 + (col >> 3)) << 9) + ((cx & 7) << 6) +
+                               ((cy & 7) << 3) + (col & 7)
+                         : C + (i64)row * ldo + col;
         double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
         if (vec && col + 1 < p.N) {
           if (beta != 0.0) {
@@ -969,6 +988,7 @@ extern "C" int b200cc_dgemm(const b200cc_gemm_desc* d, void* stream) {
   p.kt_per_split = (p.kt_total + ksplit - 1) / ksplit;
   if (p.kt_per_split < 1) p.kt_per_split = 1;
   p.bcoords = d->bcoords;
+  p.cube_nv = d->out_cube_nv;
   p.nbA1 = d->nbA1; p.nbB1 = d->nbB1; p.nbA2 = d->nbA2; p.nbB2 = d->nbB2;
 
   // 16-byte vector paths need every address/pitch/stride to be a multiple of 2 doubles.
@@ -1013,6 +1033,10 @@ extern "C" int b200cc_dgemm(const b200cc_gemm_desc* d, void* stream) {
     const double c4 = cost(128, 4, 128, 2, 1.0), c5 = cost(80, 2, 128, 4, 0.97);
     cfg = (d->M >= 80 && c5 < 0.97 * c4) ? 5 : 4;
     if (tma_ok) cfg += 2;   // same tiles, operands staged by the TMA unit instead of cp.async producer warps
+  }
+  if (d->out_cube_nv > 0 && (cfg != 6 && cfg != 7 || d->beta != 0.0 || ksplit > 1)) {
+    set_error("b200cc_dgemm: out_cube_nv needs a TMA kernel (config 6/7), beta = 0 and no split-K");
+    return 1;
   }
   if (d->bcoords && cfg != 6 && cfg != 7) { set_error("b200cc_dgemm: bcoords is only implemented by the TMA kernels (config 6/7)"); return 1; }
   int rc;

@@ -16,17 +16,29 @@ constexpr int TT = 8;  // cube edge
 
 struct TArgs {
   int no, nv, nt;
+  int blocked;   // Q stored as contiguous 8x8x8 cubes (written so by the TMA GEMM epilogue), else plain (v,v,v)
   const int* ijk;
   const double* Q;
   const double *t1, *t2, *oovv, *fov, *eo, *ev;
   i64 ldf;
 };
 
-__device__ __forceinline__ double wsum(const double* __restrict__ Q, i64 v3, int nv, int x, int y, int z) {
-  const i64 xyz = ((i64)x * nv + y) * nv + z, xzy = ((i64)x * nv + z) * nv + y;
-  const i64 zxy = ((i64)z * nv + x) * nv + y, zyx = ((i64)z * nv + y) * nv + x;
-  const i64 yzx = ((i64)y * nv + z) * nv + x, yxz = ((i64)y * nv + x) * nv + z;
-  return Q[xyz] + Q[v3 + xzy] + Q[2 * v3 + zxy] + Q[3 * v3 + zyx] + Q[4 * v3 + yzx] + Q[5 * v3 + yxz];
+// element (x,y,z) of one Q array: plain row-major (v,v,v), or 8x8x8-cube-blocked with nc8 = ceil(v/8) cubes per edge
+__device__ __forceinline__ i64 qoff(int blocked, int nv, int x, int y, int z) {
+  if (!blocked) return ((i64)x * nv + y) * nv + z;
+  const int nc8 = (nv + 7) >> 3;
+  return ((((i64)(x >> 3) * nc8 + (y >> 3)) * nc8 + (z >> 3)) << 9) + ((x & 7) << 6) + ((y & 7) << 3) + (z & 7);
+}
+__host__ __device__ __forceinline__ i64 qsize(int blocked, int nv) {
+  if (!blocked) return (i64)nv * nv * nv;
+  const i64 nc8 = (nv + 7) >> 3;
+  return nc8 * nc8 * nc8 * 512;
+}
+
+__device__ __forceinline__ double wsum(const double* __restrict__ Q, i64 v3, int blocked, int nv, int x, int y, int z) {
+  return Q[qoff(blocked, nv, x, y, z)] + Q[v3 + qoff(blocked, nv, x, z, y)] + Q[2 * v3 + qoff(blocked, nv, z, x, y)] +
+         Q[3 * v3 + qoff(blocked, nv, z, y, x)] + Q[4 * v3 + qoff(blocked, nv, y, z, x)] +
+         Q[5 * v3 + qoff(blocked, nv, y, x, z)];
 }
 
 struct Disc {  // row pointers for the disconnected part of one (i,j,k)
@@ -74,7 +86,7 @@ __global__ void __launch_bounds__(512, 2) t_energy_kernel(const TArgs p, double*
   const int trip = blockIdx.y;
   const int i = p.ijk[3 * trip], j = p.ijk[3 * trip + 1], k = p.ijk[3 * trip + 2];
   const int nv = p.nv;
-  const i64 v3 = (i64)nv * nv * nv;
+  const i64 v3 = qsize(p.blocked, nv);
   const double* Q = p.Q + (i64)trip * 6 * v3;
   const int T[3] = {TA * TT, TB * TT, TC * TT};
   const int u[3] = {(int)(threadIdx.x >> 6), (int)((threadIdx.x >> 3) & 7), (int)(threadIdx.x & 7)};
@@ -91,7 +103,8 @@ __global__ void __launch_bounds__(512, 2) t_energy_kernel(const TArgs p, double*
       const int r0 = PERM[P][PI[n][0]], r1 = PERM[P][PI[n][1]], r2 = PERM[P][PI[n][2]];
       const int x = T[r0] + u[0], y = T[r1] + u[1], z = T[r2] + u[2];
       double val = 0.0;
-      if (x < nv && y < nv && z < nv) val = __ldg(Qn + ((i64)x * nv + y) * nv + z);
+      // blocked Q: the whole 8x8x8 source block is ONE contiguous 4 KB run (thread t reads element t)
+      if (x < nv && y < nv && z < nv) val = __ldg(Qn + qoff(p.blocked, nv, x, y, z));
       // cube-local coordinates of this element: l[rho_k] = u_k
       int l[3];
       l[r0] = u[0]; l[r1] = u[1]; l[r2] = u[2];
@@ -136,12 +149,13 @@ __global__ void __launch_bounds__(256) t3_assemble_kernel(const TArgs p, int i, 
                                                           double* w3, double* v3o) {
   const int nv = p.nv;
   const i64 v3 = (i64)nv * nv * nv;
+  const i64 qs = qsize(p.blocked, nv);
   const Disc D = make_disc(p, i, j, k);
   for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < v3; e += (i64)gridDim.x * blockDim.x) {
     const int c = (int)(e % nv);
     const int b = (int)((e / nv) % nv);
     const int a = (int)(e / ((i64)nv * nv));
-    double w = wsum(p.Q, v3, nv, a, b, c);   // t3c_ijk numerator
+    double w = wsum(p.Q, qs, p.blocked, nv, a, b, c);   // t3c_ijk numerator
     double v = D(a, b, c);                   // t3d_ijk numerator
     if (with_denom) {
       const double den = p.eo[i] + p.eo[j] + p.eo[k] - p.ev[a] - p.ev[b] - p.ev[c];
@@ -166,7 +180,10 @@ extern "C" b200cc_i64 b200cc_t_energy_scratch(int nv, int ntrip) {
   return (b200cc_i64)sorted_cubes(nv) * ntrip;
 }
 
-extern "C" int b200cc_t_energy_batch(int no, int nv, int ntrip, const int* ijk, const double* Q, const double* t1,
+extern "C" b200cc_i64 b200cc_t_q_size(int nv, int blocked) { return qsize(blocked, nv); }
+
+extern "C" int b200cc_t_energy_batch(int no, int nv, int ntrip, const int* ijk, const double* Q, int q_blocked,
+                                     const double* t1,
                                      const double* t2, const double* oovv, const double* fov, b200cc_i64 ldf,
                                      const double* eo, const double* ev, double* et_out, int accumulate,
                                      double* scratch, void* stream) {
@@ -174,7 +191,7 @@ extern "C" int b200cc_t_energy_batch(int no, int nv, int ntrip, const int* ijk, 
   if (ntrip > 65535) { set_error("b200cc_t_energy_batch: ntrip > 65535"); return 1; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TArgs p;
-  p.no = no; p.nv = nv; p.nt = (nv + TT - 1) / TT;
+  p.no = no; p.nv = nv; p.nt = (nv + TT - 1) / TT; p.blocked = q_blocked ? 1 : 0;
   p.ijk = ijk; p.Q = Q; p.t1 = t1; p.t2 = t2; p.oovv = oovv; p.fov = fov; p.eo = eo; p.ev = ev; p.ldf = ldf;
   const int ncube = sorted_cubes(nv);
   t_energy_kernel<<<dim3(ncube, ntrip), 512, 0, st>>>(p, scratch);
@@ -184,13 +201,14 @@ extern "C" int b200cc_t_energy_batch(int no, int nv, int ntrip, const int* ijk, 
   return launch_final_reduce(scratch, (int)nparts, 0, 1, et_out, accumulate, 1.0, st);
 }
 
-extern "C" int b200cc_t3_assemble(int no, int nv, int i, int j, int k, const double* Q, const double* t1,
+extern "C" int b200cc_t3_assemble(int no, int nv, int i, int j, int k, const double* Q, int q_blocked,
+                                  const double* t1,
                                   const double* t2, const double* oovv, const double* fov, b200cc_i64 ldf,
                                   const double* eo, const double* ev, int with_denom, double* w3_out,
                                   double* v3_out, void* stream) {
   if (nv <= 0) return 0;
   TArgs p;
-  p.no = no; p.nv = nv; p.nt = (nv + TT - 1) / TT;
+  p.no = no; p.nv = nv; p.nt = (nv + TT - 1) / TT; p.blocked = q_blocked ? 1 : 0;
   p.ijk = nullptr; p.Q = Q; p.t1 = t1; p.t2 = t2; p.oovv = oovv; p.fov = fov; p.eo = eo; p.ev = ev; p.ldf = ldf;
   const i64 v3 = (i64)nv * nv * nv;
   i64 blocks = (v3 + 255) / 256;

@@ -57,7 +57,7 @@ def auto_ksplit(M, N, K, batch):
 
 def dgemm(M, N, K, A, lda, transA, B, ldb, transB, Cmat, ldc, alpha=1.0, beta=0.0,
           batch=1, sA=0, sB=0, sC=0, seg2=None, table=None, table_align16=False, ksplit=None, config=0,
-          bcoords=None, nbatch=None):
+          bcoords=None, nbatch=None, out_cube_nv=0):
     """C[b] = alpha * (opA[b] opB[b]^T [+ second K segment]) + beta * C[b]; see b200cc_dgemm.
 
     A, B, Cmat: tensor, (tensor, element offset) or raw address.  seg2 = (A2, lda2, B2, ldb2, K2, sA2, sB2).
@@ -82,6 +82,7 @@ def dgemm(M, N, K, A, lda, transA, B, ldb, transB, Cmat, ldc, alpha=1.0, beta=0.
         ksplit = auto_ksplit(M, N, K + K2, batch)
     d.ksplit = int(ksplit)
     d.config = int(config) if config else DEFAULT_GEMM_CONFIG
+    d.out_cube_nv = int(out_cube_nv)
     if bcoords is not None:
         # per-batch operand indices (int32 [batch,4]) + the extent of each operand's batch dimension
         d.bcoords = _lib.ptr(bcoords)
@@ -231,11 +232,17 @@ def multi_axpy(coeffs, xs, out):
     return out
 
 
-def t_energy_batch(no, nv, ijk, Q, t1, t2, oovv, fov, eo, ev, et, accumulate=True):
+def q_size(nv, blocked):
+    """doubles per Q array (plain v^3, or padded to whole 8x8x8 cubes when blocked)"""
+    return int(_lib.get().b200cc_t_q_size(int(nv), int(bool(blocked))))
+
+
+def t_energy_batch(no, nv, ijk, Q, t1, t2, oovv, fov, eo, ev, et, accumulate=True, blocked=False):
     ntrip = ijk.shape[0]
     n = int(_lib.get().b200cc_t_energy_scratch(nv, ntrip))
     sc = _scratch(Q.device, max(n, 1))
-    _lib.check(_lib.get().b200cc_t_energy_batch(no, nv, ntrip, _lib.ptr(ijk), _lib.ptr(Q), _lib.ptr(_c(t1, "t1")),
+    _lib.check(_lib.get().b200cc_t_energy_batch(no, nv, ntrip, _lib.ptr(ijk), _lib.ptr(Q), int(bool(blocked)),
+                                                _lib.ptr(_c(t1, "t1")),
                                                 _lib.ptr(_c(t2, "t2")), _lib.ptr(_c(oovv, "oovv")), _lib.ptr(fov),
                                                 int(fov.stride(0)), _lib.ptr(eo), _lib.ptr(ev), _lib.ptr(et),
                                                 int(accumulate), _lib.ptr(sc), _lib.stream()),
@@ -243,10 +250,11 @@ def t_energy_batch(no, nv, ijk, Q, t1, t2, oovv, fov, eo, ev, et, accumulate=Tru
     return et
 
 
-def t3_assemble(no, nv, i, j, k, Q, t1, t2, oovv, fov, eo, ev, with_denom):
+def t3_assemble(no, nv, i, j, k, Q, t1, t2, oovv, fov, eo, ev, with_denom, blocked=False):
     w3 = torch.empty((nv, nv, nv), dtype=F64, device=Q.device)
     d3 = torch.empty((nv, nv, nv), dtype=F64, device=Q.device)
-    _lib.check(_lib.get().b200cc_t3_assemble(no, nv, int(i), int(j), int(k), _lib.ptr(Q), _lib.ptr(_c(t1, "t1")),
+    _lib.check(_lib.get().b200cc_t3_assemble(no, nv, int(i), int(j), int(k), _lib.ptr(Q), int(bool(blocked)),
+                                             _lib.ptr(_c(t1, "t1")),
                                              _lib.ptr(_c(t2, "t2")), _lib.ptr(_c(oovv, "oovv")), _lib.ptr(fov),
                                              int(fov.stride(0)), _lib.ptr(eo), _lib.ptr(ev), int(bool(with_denom)),
                                              _lib.ptr(w3), _lib.ptr(d3), _lib.stream()), "b200cc_t3_assemble")

@@ -94,6 +94,14 @@ class EmuLib:
             acc = mat(a1, M, d.K1, d.lda1, d.transA) @ mat(b1, N, d.K1, d.ldb1, d.transB).T
             if d.K2 > 0:
                 acc = acc + mat(a2, M, d.K2, d.lda2, d.transA) @ mat(b2, N, d.K2, d.ldb2, d.transB).T
+            if d.out_cube_nv > 0:        # (T): C written as contiguous 8x8x8 cubes, row = x*nv + y, col = z
+                nv = d.out_cube_nv
+                nc8 = (nv + 7) // 8
+                buf = _vec(c, nc8 ** 3 * 512).reshape(nc8, nc8, nc8, 8, 8, 8)
+                full = np.zeros((nc8 * 8, nc8 * 8, nc8 * 8))
+                full[:nv, :nv, :N] = (d.alpha * acc).reshape(nv, nv, N)
+                buf[...] = full.reshape(nc8, 8, nc8, 8, nc8, 8).transpose(0, 2, 4, 1, 3, 5)
+                continue
             Cm = _arr(c, (M, N), (d.ldc, 1))
             if d.beta != 0.0:
                 Cm[...] = d.alpha * acc + d.beta * Cm
@@ -198,13 +206,24 @@ class EmuLib:
         return 0
 
     # ---- (T) ------------------------------------------------------------------------------------------
+    def b200cc_t_q_size(self, nv, blocked):
+        return ((nv + 7) // 8) ** 3 * 512 if blocked else nv ** 3
+
+    @staticmethod
+    def _unblock(Q6, nv, blocked):
+        """[6][qsize] -> [6][nv^3] plain"""
+        if not blocked:
+            return Q6.reshape(6, nv, nv, nv)
+        nc8 = (nv + 7) // 8
+        q = Q6.reshape(6, nc8, nc8, nc8, 8, 8, 8).transpose(0, 1, 4, 2, 5, 3, 6).reshape(6, nc8 * 8, nc8 * 8, nc8 * 8)
+        return q[:, :nv, :nv, :nv]
+
     def b200cc_t_energy_scratch(self, nv, ntrip):
         nt = (nv + 7) // 8
         return nt * (nt + 1) * (nt + 2) // 6 * ntrip
 
     @staticmethod
     def _W(Q, nv):
-        Q = Q.reshape(6, nv, nv, nv)
         return (Q[0] + Q[1].transpose(0, 2, 1) + Q[2].transpose(1, 2, 0) + Q[3].transpose(2, 1, 0)
                 + Q[4].transpose(2, 0, 1) + Q[5].transpose(1, 0, 2))
 
@@ -224,11 +243,11 @@ class EmuLib:
         eo, ev = _vec(eo, no), _vec(ev, nv)
         return eo[i] + eo[j] + eo[k] - ev[:, None, None] - ev[None, :, None] - ev[None, None, :]
 
-    def b200cc_t_energy_batch(self, no, nv, ntrip, ijk, Q, t1, t2, oovv, fov, ldf, eo, ev, et, accumulate,
+    def b200cc_t_energy_batch(self, no, nv, ntrip, ijk, Q, blocked, t1, t2, oovv, fov, ldf, eo, ev, et, accumulate,
                               scratch, stream):
         self._count("t_energy", 2)
         trip = _ints(ijk, 3 * ntrip).reshape(ntrip, 3)
-        v3 = nv ** 3
+        v3 = self.b200cc_t_q_size(nv, blocked)
         a = np.arange(nv)
         eq = ((a[:, None, None] == a[None, :, None]).astype(float) + (a[:, None, None] == a[None, None, :])
               + (a[None, :, None] == a[None, None, :]))
@@ -236,7 +255,7 @@ class EmuLib:
         tot = 0.0
         for n in range(ntrip):
             i, j, k = (int(x) for x in trip[n])
-            W = self._W(_vec(Q + 8 * n * 6 * v3, 6 * v3), nv)
+            W = self._W(self._unblock(_vec(Q + 8 * n * 6 * v3, 6 * v3), nv, blocked), nv)
             V = (W + self._disc(no, nv, i, j, k, t1, t2, oovv, fov, ldf)) / (1.0 + eq)
             p = lambda X, *ax: X.transpose(*ax)
             X3 = (W * V + p(W, 0, 2, 1) * p(V, 0, 2, 1) + p(W, 1, 0, 2) * p(V, 1, 0, 2) + p(W, 1, 2, 0) * p(V, 1, 2, 0)
@@ -252,10 +271,12 @@ class EmuLib:
         o[0] = o[0] + tot if accumulate else tot
         return 0
 
-    def b200cc_t3_assemble(self, no, nv, i, j, k, Q, t1, t2, oovv, fov, ldf, eo, ev, with_denom, w3, d3, stream):
+    def b200cc_t3_assemble(self, no, nv, i, j, k, Q, blocked, t1, t2, oovv, fov, ldf, eo, ev, with_denom, w3, d3,
+                           stream):
         self._count("t3_assemble")
         v3 = nv ** 3
-        W = self._W(_vec(Q, 6 * v3), nv)
+        qs = self.b200cc_t_q_size(nv, blocked)
+        W = self._W(self._unblock(_vec(Q, 6 * qs), nv, blocked), nv)
         Dd = self._disc(no, nv, i, j, k, t1, t2, oovv, fov, ldf)
         if with_denom:
             den = self._den(no, nv, i, j, k, eo, ev)
