@@ -49,7 +49,7 @@ def triples_list(no):
 class TriplesEngine:
     """Owns the constant operands of the (T) GEMMs for one wavefunction state."""
 
-    def __init__(self, ccwfn, t1=None, t2=None, q_bytes=None, use_tma=True):
+    def __init__(self, ccwfn, t1=None, t2=None, q_bytes=None, use_tma=True, cube_q=False):
         self.w = ccwfn
         H = ccwfn.H
         self.no, self.nv = ccwfn.no, ccwfn.nv
@@ -70,8 +70,10 @@ class TriplesEngine:
             self.G = H._derived["ovvv_iabe"]
             self.t2p = K.permuted(self.t2, (0, 2, 3, 1))          # [i,a,b,m] = t2[i,m,a,b]
         nv = self.nv
-        # with the TMA GEMM, Q is written as contiguous 8x8x8 cubes (the energy kernel then reads 4 KB runs)
-        self.qsz = K.q_size(nv, self.tma)
+        # optional: the TMA GEMM can write Q as contiguous 8x8x8 cubes (4 KB runs for the energy kernel).  Measured
+        # on B200 this is SLOWER (1.35 vs 2.66 TB/s in the energy kernel), so the plain (v,v,v) layout is the default.
+        self.cube = bool(cube_q) and self.tma
+        self.qsz = K.q_size(nv, self.cube)
         per = 6 * self.qsz * 8
         if q_bytes is None:
             q_bytes = 8 << 30
@@ -125,7 +127,7 @@ class TriplesEngine:
             co = torch.from_numpy(co.reshape(nb * 6, 4)).to(self.dev)
             K.dgemm(nv * nv, nv, nv, self.G, nv, 0, self.t2, nv, 0, Q, nv, 1.0, 0.0, batch=6 * nb,
                     sA=nv ** 3, sB=nv * nv, sC=self.qsz, seg2=(self.t2p, no, self.Y, no, no, no * nv * nv, nv * no),
-                    bcoords=co, nbatch=(no, no * no, no, no * no), ksplit=1, out_cube_nv=nv)
+                    bcoords=co, nbatch=(no, no * no, no, no * no), ksplit=1, out_cube_nv=nv if self.cube else 0)
             return Q
         tab, aligned = self.table(trip, Q)
         K.dgemm(nv * nv, nv, nv, self.ovvv, nv * nv, 1, self.t2, nv, 0, Q, nv, 1.0, 0.0,
@@ -142,14 +144,14 @@ class TriplesEngine:
             Q = self.build_q(chunk)
             ijk = torch.tensor(np.asarray(chunk, dtype=np.int32).reshape(-1, 3), dtype=torch.int32).to(self.dev)
             K.t_energy_batch(self.no, self.nv, ijk, Q, self.t1, self.t2, self.oovv, self.fov,
-                             w.eps_o, w.eps_v, et, accumulate=True, blocked=self.tma)
+                             w.eps_o, w.eps_v, et, accumulate=True, blocked=self.cube)
         return et
 
     def t3_parts(self, i, j, k, with_denom):
         """(connected, disconnected) t3 numerators of one triple as (v,v,v) tensors."""
         Q = self.build_q([(i, j, k)])
         return K.t3_assemble(self.no, self.nv, i, j, k, Q, self.t1, self.t2, self.oovv, self.fov,
-                             self.w.eps_o, self.w.eps_v, with_denom, blocked=self.tma)
+                             self.w.eps_o, self.w.eps_v, with_denom, blocked=self.cube)
 
 
 def t_tjl(ccwfn, triples=None):

@@ -94,6 +94,20 @@ __global__ void __launch_bounds__(512, 2) t_energy_kernel(const TArgs p, double*
   // P (target permutation of (a,b,c)) and pi_n (index order of Q_n), as position tables
   constexpr int PERM[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
   constexpr int PI[6][3] = {{0, 1, 2}, {0, 2, 1}, {2, 0, 1}, {2, 1, 0}, {1, 2, 0}, {1, 0, 2}};
+  // Everything per-(n,P) that does not depend on the thread is hoisted: the source block origin is CTA-uniform, the
+  // thread's offset inside a source block is the same for all 36 blocks (= threadIdx.x for cube-blocked Q), and
+  // the shared-memory slot only depends on which of the 6 axis maps rho = P o pi_n applies (profiling showed this
+  // phase was issue-bound on index arithmetic, not DRAM-bound).
+  const bool interior = (T[0] + TT <= nv) && (T[1] + TT <= nv) && (T[2] + TT <= nv);
+  const i64 local = p.blocked ? (i64)threadIdx.x : ((i64)u[0] * nv + u[1]) * nv + u[2];
+  int dsto[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    int l[3];
+    l[PERM[r][0]] = u[0]; l[PERM[r][1]] = u[1]; l[PERM[r][2]] = u[2];
+    dsto[r] = l[0] * SA + l[1] * SB + l[2];
+  }
+  const int nc8 = (nv + 7) >> 3;
 #pragma unroll
   for (int n = 0; n < 6; ++n) {
     const double* Qn = Q + (i64)n * v3;
@@ -101,14 +115,12 @@ __global__ void __launch_bounds__(512, 2) t_energy_kernel(const TArgs p, double*
     for (int P = 0; P < 6; ++P) {
       // Q_n coordinate k of W[P(a,b,c)] is cube axis rho_k = PERM[P][PI[n][k]]
       const int r0 = PERM[P][PI[n][0]], r1 = PERM[P][PI[n][1]], r2 = PERM[P][PI[n][2]];
-      const int x = T[r0] + u[0], y = T[r1] + u[1], z = T[r2] + u[2];
-      double val = 0.0;
-      // blocked Q: the whole 8x8x8 source block is ONE contiguous 4 KB run (thread t reads element t)
-      if (x < nv && y < nv && z < nv) val = __ldg(Qn + qoff(p.blocked, nv, x, y, z));
-      // cube-local coordinates of this element: l[rho_k] = u_k
-      int l[3];
-      l[r0] = u[0]; l[r1] = u[1]; l[r2] = u[2];
-      double* dst = &Wsm[P][l[0] * SA + l[1] * SB + l[2]];
+      const int rid = r0 * 2 + (r1 > r2 ? 1 : 0);       // index of rho in PERM
+      const i64 origin = p.blocked ? ((((i64)(T[r0] >> 3) * nc8 + (T[r1] >> 3)) * nc8 + (T[r2] >> 3)) << 9)
+                                   : ((i64)T[r0] * nv + T[r1]) * nv + T[r2];
+      const bool ok = interior || (T[r0] + u[0] < nv && T[r1] + u[1] < nv && T[r2] + u[2] < nv);
+      const double val = ok ? __ldg(Qn + origin + local) : 0.0;
+      double* dst = &Wsm[P][dsto[rid]];
       if (n == 0) *dst = val;
       else *dst += val;
     }

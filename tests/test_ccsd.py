@@ -313,3 +313,20 @@ def test_abc_batched_t3_and_helpers(golden, dev):
     d = float(utils.dot(cc.t2.reshape(-1), cc.t2.reshape(-1)))
     assert abs(d - float(np.sum(g["conv_t2"] ** 2))) < 1e-12
     assert float(utils.zeros_like(cc.t1).abs().max()) == 0.0
+
+
+def test_cube_blocked_q_layout(golden, dev):
+    """The optional 8x8x8-cube-blocked Q layout (GEMM epilogue out_cube_nv + blocked energy / assemble kernels)
+    gives the same W3 and E(T) as the plain layout."""
+    g, syn = golden
+    if syn.no % 2 or syn.nv % 2:
+        pytest.skip("TMA path needs even o, v")
+    cc = make_wfn(syn, "CCSD(T)")
+    cc.t1, cc.t2 = T(g["conv_t1"]), T(g["conv_t2"])
+    eng = cctriples.TriplesEngine(cc, cube_q=True)
+    assert eng.cube
+    tl = [t for t in cctriples.triples_list(cc.no) if not (t[0] == t[1] == t[2])]
+    assert abs(float(eng.energy(tl)[0]) - float(g["e_t_tjl"])) < 1e-12
+    i, j, k = (int(x) for x in g["triples"][0])
+    w3, _ = eng.t3_parts(i, j, k, False)
+    assert np.abs(w3.cpu().numpy() - g["W3"][0]).max() < 1e-12
