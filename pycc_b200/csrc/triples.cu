@@ -73,6 +73,7 @@ __device__ __forceinline__ Disc make_disc(const TArgs& p, int i, int j, int k) {
 //  loads up front at one CTA per SM was slower, 2.04 TB/s.)
 constexpr int SA = 73, SB = 9, WTILE = 8 * SA;   // padded tile pitch (doubles)
 
+template <bool BLOCKED>
 __global__ void __launch_bounds__(512, 2) t_energy_kernel(const TArgs p, double* scratch) {
   __shared__ double Wsm[6][WTILE];
   __shared__ double red[16];
@@ -94,19 +95,8 @@ __global__ void __launch_bounds__(512, 2) t_energy_kernel(const TArgs p, double*
   // P (target permutation of (a,b,c)) and pi_n (index order of Q_n), as position tables
   constexpr int PERM[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
   constexpr int PI[6][3] = {{0, 1, 2}, {0, 2, 1}, {2, 0, 1}, {2, 1, 0}, {1, 2, 0}, {1, 0, 2}};
-  // Everything per-(n,P) that does not depend on the thread is hoisted: the source block origin is CTA-uniform, the
-  // thread's offset inside a source block is the same for all 36 blocks (= threadIdx.x for cube-blocked Q), and
-  // the shared-memory slot only depends on which of the 6 axis maps rho = P o pi_n applies (profiling showed this
-  // phase was issue-bound on index arithmetic, not DRAM-bound).
+  // cube-blocked Q: a source block is one contiguous 4 KB run (thread t reads element t); plain Q: 64-byte runs
   const bool interior = (T[0] + TT <= nv) && (T[1] + TT <= nv) && (T[2] + TT <= nv);
-  const i64 local = p.blocked ? (i64)threadIdx.x : ((i64)u[0] * nv + u[1]) * nv + u[2];
-  int dsto[6];
-#pragma unroll
-  for (int r = 0; r < 6; ++r) {
-    int l[3];
-    l[PERM[r][0]] = u[0]; l[PERM[r][1]] = u[1]; l[PERM[r][2]] = u[2];
-    dsto[r] = l[0] * SA + l[1] * SB + l[2];
-  }
   const int nc8 = (nv + 7) >> 3;
 #pragma unroll
   for (int n = 0; n < 6; ++n) {
@@ -115,12 +105,18 @@ __global__ void __launch_bounds__(512, 2) t_energy_kernel(const TArgs p, double*
     for (int P = 0; P < 6; ++P) {
       // Q_n coordinate k of W[P(a,b,c)] is cube axis rho_k = PERM[P][PI[n][k]]
       const int r0 = PERM[P][PI[n][0]], r1 = PERM[P][PI[n][1]], r2 = PERM[P][PI[n][2]];
-      const int rid = r0 * 2 + (r1 > r2 ? 1 : 0);       // index of rho in PERM
-      const i64 origin = p.blocked ? ((((i64)(T[r0] >> 3) * nc8 + (T[r1] >> 3)) * nc8 + (T[r2] >> 3)) << 9)
-                                   : ((i64)T[r0] * nv + T[r1]) * nv + T[r2];
-      const bool ok = interior || (T[r0] + u[0] < nv && T[r1] + u[1] < nv && T[r2] + u[2] < nv);
-      const double val = ok ? __ldg(Qn + origin + local) : 0.0;
-      double* dst = &Wsm[P][dsto[rid]];
+      const int x = T[r0] + u[0], y = T[r1] + u[1], z = T[r2] + u[2];
+      double val = 0.0;
+      if (interior || (x < nv && y < nv && z < nv)) {
+        if (BLOCKED)
+          val = __ldg(Qn + ((((i64)(T[r0] >> 3) * nc8 + (T[r1] >> 3)) * nc8 + (T[r2] >> 3)) << 9) + threadIdx.x);
+        else
+          val = __ldg(Qn + ((i64)x * nv + y) * nv + z);
+      }
+      // cube-local coordinates of this element: l[rho_k] = u_k
+      int l[3];
+      l[r0] = u[0]; l[r1] = u[1]; l[r2] = u[2];
+      double* dst = &Wsm[P][l[0] * SA + l[1] * SB + l[2]];
       if (n == 0) *dst = val;
       else *dst += val;
     }
@@ -206,7 +202,8 @@ extern "C" int b200cc_t_energy_batch(int no, int nv, int ntrip, const int* ijk, 
   p.no = no; p.nv = nv; p.nt = (nv + TT - 1) / TT; p.blocked = q_blocked ? 1 : 0;
   p.ijk = ijk; p.Q = Q; p.t1 = t1; p.t2 = t2; p.oovv = oovv; p.fov = fov; p.eo = eo; p.ev = ev; p.ldf = ldf;
   const int ncube = sorted_cubes(nv);
-  t_energy_kernel<<<dim3(ncube, ntrip), 512, 0, st>>>(p, scratch);
+  if (p.blocked) t_energy_kernel<true><<<dim3(ncube, ntrip), 512, 0, st>>>(p, scratch);
+  else t_energy_kernel<false><<<dim3(ncube, ntrip), 512, 0, st>>>(p, scratch);
   if (check_launch("t_energy_kernel")) return 1;
   const i64 nparts = (i64)ncube * ntrip;
   if (nparts > 2147483647LL) { set_error("b200cc_t_energy_batch: too many partials"); return 1; }
