@@ -143,6 +143,7 @@ def main():
     ap.add_argument("--cpu-v", type=int, default=120)
     ap.add_argument("--t-triples", type=int, default=48, help="(T) sample: triples timed per rank-set")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-mp", action="store_true", help="skip the mixed-precision (precision='MP') leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -183,9 +184,12 @@ def main():
     sync()
     t_setup = time.time() - t_setup
 
+    energies = []                                   # E after every iteration (warm-up included): the MP leg repeats them
+
     def step():
         ecc, rms = cc.iterate()
         cc.diis_step(diis, True)
+        energies.append(ecc)
         return ecc, rms
 
     for _ in range(max(3, args.warmup)):
@@ -305,6 +309,87 @@ def main():
     e2e = {"value": t_e2e, "unit": "s/iter", "h2d_bytes_per_step": int((h_t1.numel() + h_t2.numel() + h_F.numel()) * 8),
            "d2h_bytes_per_step": 16}
 
+    # ---- BASELINE configs[4]: the same iterations with precision='MP' (split-TF32 contractions on tcgen05, FP64
+    # accumulation) from the same starting guess: s/iter, |E_MP - E_FP64| after each iteration, and the ladder GEMM
+    # against the TF32 tensor peak (cuBLAS TF32 SGEMM 8192^3 measured live).  The FP64 objects are released first
+    # (<ab|ef> FP64 + its TF32 planes do not fit together at v=300).
+    mp = None
+    if not args.no_mp:
+        n_dp = len(energies)
+        del cc, diis, h_t1, h_t2, h_F, d_F
+        cctriples._QCACHE.clear()
+        import gc
+        gc.collect()                                # the Hamiltonian <-> its ERI/L views form reference cycles
+        torch.cuda.empty_cache()
+        ccm = pycc_b200.ccwfn(syn, model="CCSD", device="GPU", precision="MP", quiet=True, comm=comm)
+        diism = pycc_b200.helper_diis(ccm.t1, ccm.t2, 8)
+        e_mp = []
+
+        def mstep():
+            e, r = ccm.iterate()
+            ccm.diis_step(diism, True)
+            e_mp.append(e)
+
+        for _ in range(max(3, args.warmup)):
+            mstep()
+        sync()
+        l0 = K.launch_count()
+        ma, mb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ma.record()
+        for _ in range(args.steps):
+            mstep()
+        mb.record()
+        sync()
+        mp_launches = K.launch_count() - l0
+        t_mp = ma.elapsed_time(mb) * 1e-3 / args.steps
+        if comm is not None:
+            t_mp = comm.all_reduce_max_scalar(t_mp)
+        nmp = min(n_dp, len(e_mp))
+        de = max(abs(a - b) for a, b in zip(energies[:nmp], e_mp[:nmp]))
+        tau = K.build_tau(ccm.t1, ccm.t2)
+        r2 = torch.zeros_like(ccm.t2)
+        with K.mixed_mode(True):
+            ccm._ladder(tau, r2)
+            torch.cuda.synchronize()
+            la, lb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            la.record()
+            for _ in range(3):
+                ccm._ladder(tau, r2)
+            lb.record()
+            torch.cuda.synchronize()
+        t_lad_mp = la.elapsed_time(lb) * 1e-3 / 3
+        del tau, r2
+        tf32_peak, tf32_src = 1130.0, "nominal dense TF32 (no measured entry in MEASURED_PEAKS.json)"
+        try:
+            torch.backends.cuda.matmul.allow_tf32 = True
+            A = torch.randn(8192, 8192, dtype=torch.float32, device=dev)
+            C = torch.empty_like(A)
+            for _ in range(2):
+                torch.matmul(A, A, out=C)
+            torch.cuda.synchronize()
+            best = 0.0
+            for _ in range(5):
+                pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                pa.record()
+                torch.matmul(A, A, out=C)
+                pb.record()
+                torch.cuda.synchronize()
+                best = max(best, 2.0 * 8192**3 / (pa.elapsed_time(pb) * 1e-3) / 1e12)
+            tf32_peak, tf32_src = best, "cuBLAS TF32 SGEMM 8192^3, best of 5, measured live in this run"
+            torch.backends.cuda.matmul.allow_tf32 = False
+            del A, C
+        except Exception:
+            pass
+        mp = {"value": t_mp, "unit": "s/iter", "speedup_vs_fp64": s_iter / t_mp, "dtype": "tf32x3 products, f64 accumulate",
+              "max_abs_dE_vs_fp64_same_iteration": de, "iterations_compared": nmp, "ecc_last": e_mp[-1],
+              "gpu_launches": int(mp_launches), "stats": dict(K.MIXED.stats),
+              "roofline": {"bound": "tensor", "kernel": "tf32x3_gemm_r_kernel (ladder, ccwfn.py:931)",
+                           "achieved": 3.0 * lad_flops / t_lad_mp / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                           "frac": 3.0 * lad_flops / t_lad_mp / 1e12 / tf32_peak, "peak_source": tf32_src,
+                           "fp64_equivalent_tflops": lad_flops / t_lad_mp / 1e12, "launch_ms": t_lad_mp * 1e3,
+                           "note": "achieved counts the three TF32 products actually executed per FP64-equivalent flop"}}
+        del ccm, diism
+
     if rank == 0:
         cpu = None
         if not args.no_cpu and world >= 1:
@@ -318,7 +403,7 @@ def main():
                                        "(75 GB of integrals streamed per step)" % (o, v),
                            "parallelism": "a-sharded ladder + occupied-sliced ring terms, 1 all-reduce/iter" if world > 1 else "single GPU",
                            "diis": 8, "setup_s": t_setup},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "t": t_info, "clocks": clocks,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "t": t_info, "mp": mp, "clocks": clocks,
                 "gpu_launches": int(launches), "ecc_last": ecc, "rms_last": rms}
         print(json.dumps(line), flush=True)
     if comm is not None:

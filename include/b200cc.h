@@ -73,6 +73,44 @@ typedef struct {
 
 int b200cc_dgemm(const b200cc_gemm_desc* d, void* stream);
 
+/* ---- mixed precision: split-TF32 GEMM on the tcgen05 tensor cores, FP64 accumulation -------------
+ * precision='MP' replacement for the large K-major x K-major contractions of b200cc_dgemm (same reference
+ * lines: ccwfn.py:931 ladder, 644-645/683/715/933-935 ring terms, 603 Wmnij).  The reference has only
+ * whole-calculation float32 ('SP', device.py:147-151); this mode keeps every tensor FP64 and evaluates
+ *
+ *   C[b](m,n) = alpha * sum_k A[b](m,k) B[b](n,k) + beta * C[b](m,n)
+ *
+ * as Ahi.Bhi + Ahi.Blo + Alo.Bhi with TF32 operands (hi + lo ~= the FP64 value to 2^-22), FP32 accumulation in
+ * TMEM over at most `kchunk` summation indices at a time and FP64 accumulation of the chunks in C.
+ *
+ * b200cc_split_tf32: src (rows x K, pitch ld doubles, `batch` copies `stride` doubles apart) ->
+ * hi/lo FP32 planes [batch][rows][ldp], ldp % 4 == 0, ldp >= K, columns K..ldp zeroed, 16-byte aligned.
+ * b200cc_gemm_tf32x3: planes are K-major: A element (m,k) at Ahi[b*strideA + m*lda + k] (floats; lda, ldb,
+ * strideA, strideB multiples of 4; stride 0 = one operand shared by the whole batch); C row-major FP64.        */
+typedef struct {
+  int M, N, K;
+  const float *Ahi, *Alo, *Bhi, *Blo;
+  b200cc_i64 lda, ldb, strideA, strideB;
+  double* C;
+  b200cc_i64 ldc, strideC;
+  double alpha, beta;
+  int batch;
+  int kchunk;                      /* summation indices per FP32 (TMEM) accumulation chunk; 0 = 256 (configs 5/6) / 2048 (1..4) */
+  int config;                      /* 0 auto = 5; 5 / 6 = 128x128 tile, FP64 running sums in registers, separate TMEM accumulators
+                                      for the hi.hi and the cross products, 32- / 16-wide k-blocks (3 / 6 stages);
+                                      1..4 = one shared accumulator drained into C in global memory:
+                                      1 = 128x256 tile, 32-wide k-blocks, 2 stages; 2 = 128x128, 32, 3 stages;
+                                      3 = 128x256, 16-wide k-blocks (64-byte swizzle), 4 stages; 4 = 128x128, 16, 6 stages */
+  int lockstep;                    /* configs 5/6: leader/follower tile schedule -- a CTA requests an operand tile only after the
+                                      CTA that leads its row / column of the tile block has received it, so every tile is read from
+                                      DRAM once and served from L2 afterwards.  > 0: on, followers run this many k-blocks behind;
+                                      <= 0: off (default: measured to cut DRAM traffic but not run time, see mixed.cu) */
+} b200cc_gemm3_desc;
+
+int b200cc_split_tf32(const double* src, b200cc_i64 ld, b200cc_i64 stride, int rows, int K, int batch,
+                      float* hi, float* lo, b200cc_i64 ldp, void* stream);
+int b200cc_gemm_tf32x3(const b200cc_gemm3_desc* d, void* stream);
+
 /* ---- tensor permutation / strided axpby -------------------------------------------------------
  * out[sum_d i_d*so[d]] = alpha * in[sum_d i_d*si[d]] + beta * out[...]  for i_d < shape[d], rank <= 6.
  * Replaces tensordot's permute+contiguous copies and swapaxes/clone/+ ATen passes

@@ -49,6 +49,22 @@ class GemmDesc(C.Structure):
     ]
 
 
+class Gemm3Desc(C.Structure):
+    """Mirror of ``b200cc_gemm3_desc`` (include/b200cc.h)."""
+    _fields_ = [
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+        ("Ahi", dptr), ("Alo", dptr), ("Bhi", dptr), ("Blo", dptr),
+        ("lda", i64), ("ldb", i64), ("strideA", i64), ("strideB", i64),
+        ("C", dptr),
+        ("ldc", i64), ("strideC", i64),
+        ("alpha", C.c_double), ("beta", C.c_double),
+        ("batch", C.c_int),
+        ("kchunk", C.c_int),
+        ("config", C.c_int),
+        ("lockstep", C.c_int),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/b200cc.h declares
 SIGNATURES = {
     "b200cc_version": (C.c_int, []),
@@ -56,6 +72,8 @@ SIGNATURES = {
     "b200cc_launch_count": (i64, []),
     "b200cc_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3 + [C.POINTER(i64)] * 2),
     "b200cc_dgemm": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
+    "b200cc_split_tf32": (C.c_int, [dptr, i64, i64, C.c_int, C.c_int, C.c_int, dptr, dptr, i64, C.c_void_p]),
+    "b200cc_gemm_tf32x3": (C.c_int, [C.POINTER(Gemm3Desc), C.c_void_p]),
     "b200cc_permute": (C.c_int, [C.c_int, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64),
                                  C.c_double, dptr, C.c_double, dptr, C.c_void_p]),
     "b200cc_axpbyz": (C.c_int, [i64, C.c_double, dptr, C.c_double, dptr, dptr, C.c_void_p]),

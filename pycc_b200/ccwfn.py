@@ -86,7 +86,8 @@ class CCwfn(object):
         ref = resolve_reference(scf_wfn)
         self.ref = scf_wfn
         self.eref = ref.eref
-        self.H = ref.hamiltonian(self.device1, comm=self.comm)
+        self.mixed = mgr.mixed
+        self.H = ref.hamiltonian(self.device1, comm=self.comm, mixed=self.mixed)
         self.nfzc, self.no, self.nv, self.nmo = self.H.nfzc, self.H.no, self.H.nv, self.H.nmo
         self.nact = self.no + self.nv
         self.o, self.v = self.H.o, self.H.v
@@ -204,7 +205,12 @@ class CCwfn(object):
 
     def _residuals_half(self, F, t1, t2):
         """r1 and the UNsymmetrised half of r2 (ccwfn.py:922-940), fused formulation.  With several ranks
-        each computes its share of r2 (see parallel.py) and ONE all-reduce sums them."""
+        each computes its share of r2 (see parallel.py) and ONE all-reduce sums them.  precision='MP': the large
+        K-major contractions inside run on the split-TF32 tcgen05 kernel (kernels.mixed_mode)."""
+        with K.mixed_mode(self.mixed):
+            return self._residuals_half_impl(F, t1, t2)
+
+    def _residuals_half_impl(self, F, t1, t2):
         F = self._check_F(F)
         t1 = t1.contiguous()
         t2 = t2.contiguous()
@@ -457,13 +463,21 @@ class CCwfn(object):
         """r2[i,j,a,b] += 1/2 sum_ef tau[i,j,e,f] <ab|ef>  (ccwfn.py:931): M=o^2, N=K=v^2, <ab|ef> streamed
         once, in place.  With an a-sharded <ab|ef> only the local rows a_g are touched."""
         no, nv = self.no, self.nv
-        vvvv = self.H.block("vvvv")
+        vvvv = None if K.MIXED.on else self.H.block("vvvv")
         r_lo, r_hi = self.H.a_range                 # rows resident on this device
         a_lo, a_hi = self.part.a_range(nv)          # rows this rank is responsible for
         if a_lo < r_lo or a_hi > r_hi:
             raise B200ccError("<ab|ef> rows [%d,%d) needed but only [%d,%d) are resident" % (a_lo, a_hi, r_lo, r_hi))
         na = a_hi - a_lo
         if na == 0:
+            return
+        if K.MIXED.on:
+            # precision='MP': <ab|ef> lives as TF32 planes [(a,b), ldp]; tau is split per iteration (1.15 GB pass)
+            hi, lo, ldp = self.H.to_mixed(drop=False)
+            th, tl, lpt = K.split_tf32(tau, no * no, nv * nv, nv * nv)
+            off = (a_lo - r_lo) * nv * ldp
+            K.gemm_tf32x3(no * no, na * nv, nv * nv, th, tl, lpt, (hi, off), (lo, off), ldp, (r2, a_lo * nv), nv * nv,
+                          0.5, 1.0)
             return
         K.dgemm(no * no, na * nv, nv * nv, tau, nv * nv, 0, (vvvv, (a_lo - r_lo) * nv ** 3), nv * nv, 0,
                 (r2, a_lo * nv), nv * nv, 0.5, 1.0)
@@ -480,7 +494,8 @@ class CCwfn(object):
                                       "use the wavefunction's own H.ERI / H.L")
 
     def _I(self, F, t1, t2):
-        return self._intermediates(self._check_F(F), t1.contiguous(), t2.contiguous(), full=True)
+        with K.mixed_mode(self.mixed):
+            return self._intermediates(self._check_F(F), t1.contiguous(), t2.contiguous(), full=True)
 
     def build_Fae(self, o, v, F, L, t1, t2):
         self._own(L=L)
@@ -524,7 +539,8 @@ class CCwfn(object):
         F = self._check_F(F)
         t1, t2 = t1.contiguous(), t2.contiguous()
         r1p = torch.empty_like(t1)
-        r1 = self._r1(F, t1, t2, self._intermediates(F, t1, t2), r1p)
+        with K.mixed_mode(self.mixed):
+            r1 = self._r1(F, t1, t2, self._intermediates(F, t1, t2), r1p)
         if self.part.size > 1:
             self.part.all_reduce_sum(r1p)
         K.strided_axpby(r1, r1p, 1.0, 1.0)
@@ -538,7 +554,8 @@ class CCwfn(object):
         self._own(ERI)
         F = self._check_F(F)
         t1, t2 = t1.contiguous(), t2.contiguous()
-        half = self._r2_half(F, t1, t2, self._intermediates(F, t1, t2))
+        with K.mixed_mode(self.mixed):
+            half = self._r2_half(F, t1, t2, self._intermediates(F, t1, t2))
         if self.part.size > 1:
             self.part.all_reduce_sum(half)
         return K.symmetrize_r2(half)

@@ -87,6 +87,18 @@ class _BlockView:
         return self._cache[pat]
 
 
+class _ConstDict(dict):
+    """``H._derived``: every tensor stored here is registered as a constant GEMM operand (its TF32 planes are cached)."""
+
+    def __init__(self, H):
+        super().__init__()
+        self._H = H
+
+    def __setitem__(self, key, t):
+        super().__setitem__(key, t)
+        K.register_constant(t, self._H._split_cache)
+
+
 class BlockHamiltonian:
     """F, eps and the six integral blocks on one device (float64)."""
 
@@ -111,13 +123,39 @@ class BlockHamiltonian:
                 self._blocks[name] = t.to(self.device, dtype=torch.float64).contiguous()
         self.ERI = _BlockView(self, "ERI")
         self.L = _BlockView(self, "L")
-        self._derived = {}
+        self._derived = _ConstDict(self)
+        # precision='MP': TF32 (hi, lo) planes of constant GEMM operands, computed once (kernels._split_operand);
+        # <ab|ef> as planes [(a,b), ldp] (the FP64 block may then be released, see to_mixed)
+        self._split_cache = {}
+        self.vvvv_planes = None
+        for t in self._blocks.values():
+            K.register_constant(t, self._split_cache)
+
+    def __del__(self):
+        try:
+            K.unregister_constants(self._split_cache)
+        except Exception:
+            pass
 
     def block(self, name):
         try:
             return self._blocks[name]
         except KeyError:
+            if name == "vvvv" and self.vvvv_planes is not None:
+                raise B200ccError("the FP64 <ab|ef> block was released for precision='MP' (only its TF32 planes are "
+                                  "resident)")
             raise B200ccError("integral block %r is not resident" % name)
+
+    def to_mixed(self, drop=True):
+        """Split <ab|ef> into TF32 planes (precision='MP'); ``drop`` releases the FP64 block (64.8 GB at v=300)."""
+        if self.vvvv_planes is None:
+            vvvv = self.block("vvvv")
+            na, nv = vvvv.shape[0], self.nv
+            hi, lo, ldp = K.split_tf32(vvvv, na * nv, nv * nv, nv * nv)
+            self.vvvv_planes = (hi[0], lo[0], ldp)
+        if drop and "vvvv" in self._blocks:
+            del self._blocks["vvvv"]
+        return self.vvvv_planes
 
     def has(self, name):
         return name in self._blocks
@@ -133,7 +171,7 @@ class BlockHamiltonian:
         return cls(F, blocks, no, nfzc, device)
 
     @classmethod
-    def from_factor(cls, syn, device="cuda", a_range=None, chunk_bytes=4 << 30, names=STORED):
+    def from_factor(cls, syn, device="cuda", a_range=None, chunk_bytes=4 << 30, names=STORED, mixed=False):
         """From a factorised synthetic problem (pycc_b200.synthetic): every block is contracted on the
         device with the package's own GEMM, <pq|rs> = scale * sum_P B[P,p,r] B[P,q,s]; `vvvv` in row
         chunks so no temporary larger than ``chunk_bytes`` exists."""
@@ -150,17 +188,34 @@ class BlockHamiltonian:
                 continue
             a_lo, a_hi = (0, nv) if a_range is None else a_range
             na = a_hi - a_lo
-            out = torch.empty((na, nv, nv, nv), dtype=torch.float64, device=dev)
             Bqs = K.permuted(B[:, q, s], (1, 2, 0))                  # [(b,f), P]  K-major
             rows = max(1, min(na, int(chunk_bytes // (8 * nv ** 3))))
+            if mixed:
+                # precision='MP': the FP64 block is never materialised, each row chunk goes straight to TF32 planes
+                ldp = (nv * nv + 3) // 4 * 4
+                hi = torch.empty((na * nv, ldp), dtype=torch.float32, device=dev)
+                lo = torch.empty((na * nv, ldp), dtype=torch.float32, device=dev)
+                out = torch.empty((min(rows, na), nv, nv, nv), dtype=torch.float64, device=dev)
+                planes = (hi, lo, ldp)
+            else:
+                out = torch.empty((na, nv, nv, nv), dtype=torch.float64, device=dev)
             for a0 in range(0, na, rows):
                 a1 = min(na, a0 + rows)
                 Bpr = K.permuted(B[:, no + a_lo + a0:no + a_lo + a1, r], (1, 2, 0))   # [(a,e), P]
                 tmp = ct("aeP,bfP->aebf", Bpr, Bqs, alpha=syn.scale)
-                K.strided_axpby(out[a0:a1], tmp.permute(0, 2, 1, 3), 1.0, 0.0)
+                dst = out[:a1 - a0] if mixed else out[a0:a1]
+                K.strided_axpby(dst, tmp.permute(0, 2, 1, 3), 1.0, 0.0)
                 del tmp, Bpr
-            blocks[name] = out
-        return cls(syn.F, blocks, no, 0, dev, a_range)
+                if mixed:
+                    K.split_tf32(dst, (a1 - a0) * nv, nv * nv, nv * nv,
+                                 out=((hi, a0 * nv * ldp), (lo, a0 * nv * ldp), ldp))
+            if not mixed:
+                blocks[name] = out
+            del out
+        H = cls(syn.F, blocks, no, 0, dev, a_range)
+        if mixed and "vvvv" in names:
+            H.vvvv_planes = planes
+        return H
 
     # ---- derived constant layouts (built once, cached) ---------------------------------------------
     def derived(self, key):

@@ -12,7 +12,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import GemmDesc, B200ccError, i64
+from ._lib import GemmDesc, Gemm3Desc, B200ccError, i64
 
 NSM = 148                   # B200
 # tile-config override for experiments (0 = library heuristic); see b200cc_gemm_desc.config
@@ -55,6 +55,120 @@ def auto_ksplit(M, N, K, batch):
     return best
 
 
+# ---- mixed precision (precision='MP'): large K-major x K-major products go to the tcgen05 split-TF32 GEMM --------
+class _Mixed:
+    """Process-wide switch set by DeviceManager(precision='MP').  ``min_flops``: smaller products stay on the FP64
+    DMMA kernel (they are a few % of an iteration and keep full precision); ``kchunk``: summation indices accumulated
+    in FP32 (TMEM) before the FP64 drain; ``config``: b200cc_gemm3_desc.config."""
+    on = False
+    min_flops = 1.0e9
+    min_dim = 32
+    kchunk = int(os.environ.get("B200CC_MP_KCHUNK", "0"))       # 0 = library default (256 for the default kernel)
+    config = int(os.environ.get("B200CC_MP_CONFIG", "0"))
+    lockstep = int(os.environ.get("B200CC_MP_LOCKSTEP", "0"))   # leader/follower tile schedule: >0 skew in k-blocks, <=0 off
+    min_tiles = 74        # fewer 128x128 output tiles than this: the split-K FP64 kernel fills the SMs better
+    stats = {"gemm": 0, "split": 0, "split_cached": 0}
+
+
+MIXED = _Mixed()
+
+
+class mixed_mode:
+    """``with mixed_mode(flag):`` -- route eligible dgemm calls to the split-TF32 kernel inside the block."""
+
+    def __init__(self, flag):
+        self.flag = bool(flag)
+
+    def __enter__(self):
+        self.prev = MIXED.on
+        MIXED.on = self.flag
+        return self
+
+    def __exit__(self, *exc):
+        MIXED.on = self.prev
+        return False
+
+
+_CONST = {}       # storage address of a constant tensor (integral block / derived layout) -> its owner's split cache
+
+
+def register_constant(t, cache):
+    """Mark ``t`` as constant: its TF32 planes are computed once and kept in ``cache`` (owned by the Hamiltonian)."""
+    _CONST[t.untyped_storage().data_ptr()] = cache
+
+
+def unregister_constants(cache):
+    for k in [k for k, v in _CONST.items() if v is cache]:
+        del _CONST[k]
+
+
+def _faddr(x):
+    """float32 tensor | (tensor, float offset) -> address"""
+    if isinstance(x, tuple):
+        return _lib.ptr(x[0]) + 4 * int(x[1])
+    return _lib.ptr(x)
+
+
+def split_tf32(src, rows, K, ld, batch=1, stride=0, out=None):
+    """FP64 operand (rows x K, pitch ld, batch entries `stride` apart) -> (hi, lo, ldp): FP32 planes
+    [batch][rows][ldp] with x ~= hi + lo, both TF32-representable (b200cc_split_tf32).  ``out=(hi, lo, ldp)``
+    writes into existing planes (tensors or (tensor, float offset))."""
+    nb = int(batch) if (batch > 1 and stride != 0) else 1
+    if out is None:
+        ldp = (int(K) + 3) // 4 * 4
+        dev = _dev(src)
+        hi = torch.empty((nb, rows, ldp), dtype=torch.float32, device=dev)
+        lo = torch.empty((nb, rows, ldp), dtype=torch.float32, device=dev)
+    else:
+        hi, lo, ldp = out
+    _lib.check(_lib.get().b200cc_split_tf32(_addr(src), int(ld), int(stride), int(rows), int(K), nb, _faddr(hi),
+                                            _faddr(lo), int(ldp), _lib.stream()), "b200cc_split_tf32")
+    MIXED.stats["split"] += 1
+    return hi, lo, ldp
+
+
+def _split_operand(X, rows, K, ld, batch, stride):
+    t = X[0] if isinstance(X, tuple) else X
+    cache = _CONST.get(t.untyped_storage().data_ptr())
+    if cache is None:
+        return split_tf32(X, rows, K, ld, batch, stride)
+    key = (_addr(X), int(rows), int(K), int(ld), int(batch) if stride else 1, int(stride))
+    r = cache.get(key)
+    if r is None:
+        r = cache[key] = split_tf32(X, rows, K, ld, batch, stride)
+    else:
+        MIXED.stats["split_cached"] += 1
+    return r
+
+
+def gemm_tf32x3(M, N, K, Ahi, Alo, lda, Bhi, Blo, ldb, Cmat, ldc, alpha=1.0, beta=0.0, batch=1, sA=0, sB=0, sC=0,
+                kchunk=None, config=None, lockstep=None):
+    """C[b] = alpha * A[b] B[b]^T + beta * C[b] from split-TF32 planes (b200cc_gemm_tf32x3); plane operands may be
+    tensors or (tensor, float offset)."""
+    if M == 0 or N == 0 or batch == 0:
+        return
+
+    fa = _faddr
+    d = Gemm3Desc()
+    d.M, d.N, d.K = int(M), int(N), int(K)
+    d.Ahi, d.Alo, d.Bhi, d.Blo = fa(Ahi), fa(Alo), fa(Bhi), fa(Blo)
+    d.lda, d.ldb, d.strideA, d.strideB = int(lda), int(ldb), int(sA), int(sB)
+    d.C, d.ldc, d.strideC = _addr(Cmat), int(ldc), int(sC)
+    d.alpha, d.beta, d.batch = float(alpha), float(beta), int(batch)
+    d.kchunk = int(MIXED.kchunk if kchunk is None else kchunk)
+    d.config = int(MIXED.config if config is None else config)
+    d.lockstep = int(MIXED.lockstep if lockstep is None else lockstep)
+    _lib.check(_lib.get().b200cc_gemm_tf32x3(C.byref(d), _lib.stream()), "b200cc_gemm_tf32x3")
+    MIXED.stats["gemm"] += 1
+
+
+def _mixed_eligible(M, N, K, A, B, transA, transB, batch, seg2, table, bcoords, out_cube_nv):
+    return (MIXED.on and not transA and not transB and seg2 is None and table is None and bcoords is None
+            and not out_cube_nv and not isinstance(A, int) and not isinstance(B, int)
+            and min(M, N, K) >= MIXED.min_dim and 2.0 * M * N * K * batch >= MIXED.min_flops
+            and ((M + 127) // 128) * ((N + 127) // 128) * batch >= MIXED.min_tiles)
+
+
 def dgemm(M, N, K, A, lda, transA, B, ldb, transB, Cmat, ldc, alpha=1.0, beta=0.0,
           batch=1, sA=0, sB=0, sC=0, seg2=None, table=None, table_align16=False, ksplit=None, config=0,
           bcoords=None, nbatch=None, out_cube_nv=0):
@@ -64,6 +178,11 @@ def dgemm(M, N, K, A, lda, transA, B, ldb, transB, Cmat, ldc, alpha=1.0, beta=0.
     """
     if M == 0 or N == 0 or batch == 0:
         return
+    if _mixed_eligible(M, N, K, A, B, transA, transB, batch, seg2, table, bcoords, out_cube_nv):
+        Ah, Al, lpa = _split_operand(A, M, K, lda, batch, sA)
+        Bh, Bl, lpb = _split_operand(B, N, K, ldb, batch, sB)
+        return gemm_tf32x3(M, N, K, Ah, Al, lpa, Bh, Bl, lpb, Cmat, ldc, alpha, beta, batch,
+                           M * lpa if (batch > 1 and sA) else 0, N * lpb if (batch > 1 and sB) else 0, sC)
     d = GemmDesc()
     d.M, d.N, d.transA, d.transB = int(M), int(N), int(bool(transA)), int(bool(transB))
     d.K1 = int(K)

@@ -22,32 +22,37 @@ class IntegralReference:
     def __init__(self, eref=0.0):
         self.eref = float(eref)
         self._make = None
+        self._owns = True          # the Hamiltonian is built for this wavefunction (False: a caller's object)
 
     def energy(self):
         return self.eref
 
-    def hamiltonian(self, device, comm=None):
-        return self._make(device, comm)
+    def hamiltonian(self, device, comm=None, mixed=False):
+        """``mixed``: the Hamiltonian will be used by precision='MP' -- <ab|ef> is kept as TF32 planes only."""
+        H = self._make(device, comm, mixed)
+        if mixed and H.vvvv_planes is None and H.has("vvvv"):
+            H.to_mixed(drop=self._owns)
+        return H
 
     @classmethod
     def from_arrays(cls, F, ERI, no, nfzc=0, eref=0.0):
         r = cls(eref)
-        r._make = lambda device, comm: BlockHamiltonian.from_full(F, ERI, no, nfzc, device)
+        r._make = lambda device, comm, mixed: BlockHamiltonian.from_full(F, ERI, no, nfzc, device)
         return r
 
     @classmethod
     def from_blocks(cls, F, blocks, no, nfzc=0, eref=0.0):
         r = cls(eref)
-        r._make = lambda device, comm: BlockHamiltonian(F, blocks, no, nfzc, device)
+        r._make = lambda device, comm, mixed: BlockHamiltonian(F, blocks, no, nfzc, device)
         return r
 
     @classmethod
     def from_synthetic(cls, syn):
         r = cls(syn.eref)
 
-        def make(device, comm):
+        def make(device, comm, mixed):
             a_range = None if comm is None else comm.a_range(syn.nv)
-            return BlockHamiltonian.from_factor(syn, device, a_range=a_range)
+            return BlockHamiltonian.from_factor(syn, device, a_range=a_range, mixed=mixed)
         r._make = make
         return r
 
@@ -71,7 +76,8 @@ def resolve_reference(x):
         return IntegralReference.from_synthetic(x)
     if isinstance(x, BlockHamiltonian):
         r = IntegralReference(0.0)
-        r._make = lambda device, comm: x
+        r._make = lambda device, comm, mixed: x
+        r._owns = False
         return r
     if hasattr(x, "frzcpi") and hasattr(x, "Ca_subset"):
         return IntegralReference.from_psi4(x)

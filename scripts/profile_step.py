@@ -23,10 +23,13 @@ ap.add_argument("--o", type=int, default=20)
 ap.add_argument("--v", type=int, default=150)
 ap.add_argument("--only", default="step", choices=["step", "ladder", "t"])
 ap.add_argument("--triples", type=int, default=4)
+ap.add_argument("--precision", default="DP", choices=["DP", "MP"])
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 syn = make_synthetic(args.o, args.v, seed=0, device=dev)
-cc = pycc_b200.ccwfn(syn, model="CCSD(T)", device="GPU", quiet=True)
+cc = pycc_b200.ccwfn(syn, model="CCSD(T)", device="GPU", quiet=True, precision=args.precision)
+mixed = K.mixed_mode(args.precision == "MP")
+mixed.__enter__()
 diis = pycc_b200.helper_diis(cc.t1, cc.t2, 8)
 for _ in range(2):
     cc.iterate()

@@ -29,6 +29,21 @@ def _arr(addr, shape, strides):
     return as_strided(base, shape, tuple(8 * st for st in strides))
 
 
+def _f32(addr, shape):
+    """contiguous float32 view of raw memory"""
+    if isinstance(addr, C.c_void_p):
+        addr = addr.value
+    n = int(np.prod(shape))
+    buf = (C.c_float * n).from_address(int(addr))
+    return np.frombuffer(buf, dtype=np.float32).reshape(shape)
+
+
+def tf32_rna(f):
+    """cvt.rna.tf32.f32: round a float32 array to 10 explicit mantissa bits, ties away from zero"""
+    u = np.ascontiguousarray(f, dtype=np.float32).view(np.uint32)
+    return ((u + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
 def _vec(addr, n):
     return _arr(addr, (n,), (1,))
 
@@ -103,6 +118,39 @@ class EmuLib:
                 buf[...] = full.reshape(nc8, 8, nc8, 8, nc8, 8).transpose(0, 2, 4, 1, 3, 5)
                 continue
             Cm = _arr(c, (M, N), (d.ldc, 1))
+            if d.beta != 0.0:
+                Cm[...] = d.alpha * acc + d.beta * Cm
+            else:
+                Cm[...] = d.alpha * acc
+        return 0
+
+    # ---- mixed precision: TF32 split + 3-product GEMM (FP64 arithmetic on the split values) ---------
+    def b200cc_split_tf32(self, src, ld, stride, rows, K, batch, hi, lo, ldp, stream):
+        self._count("split_tf32")
+        if rows <= 0 or K <= 0 or batch <= 0:
+            return 0
+        x = _arr(src, (batch, rows, K), (stride, ld, 1))
+        H = _f32(hi, (batch, rows, ldp))
+        L = _f32(lo, (batch, rows, ldp))
+        h = tf32_rna(x.astype(np.float32))
+        H[...] = 0.0
+        L[...] = 0.0
+        H[:, :, :K] = h
+        L[:, :, :K] = tf32_rna((x - h.astype(np.float64)).astype(np.float32))
+        return 0
+
+    def b200cc_gemm_tf32x3(self, dref, stream):
+        d = dref._obj
+        self._count("gemm_tf32x3")
+        if d.M <= 0 or d.N <= 0 or d.batch <= 0:
+            return 0
+        for b in range(d.batch):
+            def pl(addr, rows, ld, st):
+                return _f32(addr + 4 * b * st, (rows, ld))[:, :d.K].astype(np.float64)
+            ah, al = pl(d.Ahi, d.M, d.lda, d.strideA), pl(d.Alo, d.M, d.lda, d.strideA)
+            bh, bl = pl(d.Bhi, d.N, d.ldb, d.strideB), pl(d.Blo, d.N, d.ldb, d.strideB)
+            acc = ah @ bh.T + ah @ bl.T + al @ bh.T
+            Cm = _arr(d.C + 8 * b * d.strideC, (d.M, d.N), (d.ldc, 1))
             if d.beta != 0.0:
                 Cm[...] = d.alpha * acc + d.beta * Cm
             else:

@@ -183,6 +183,51 @@ def test_ccd_is_ccsd_without_singles(dev):
     assert abs(float(e) - ecc) < 1e-10
 
 
+@pytest.mark.parametrize("precision", ["MP", "SP"])
+def test_mixed_precision_energy(golden, dev, precision):
+    """precision='MP' (split-TF32 contractions on tcgen05, FP64 accumulation; 'SP' is served by the same path):
+    converged E(CCSD) and E(CCSD(T)) within 1e-6 Eh of the reference's FP64 values (north_star tolerance), amplitudes
+    within 1e-6; <ab|ef> is resident as TF32 planes only and constant operands are split once."""
+    from pycc_b200 import kernels as K
+    g, syn = golden
+    keep = (K.MIXED.min_flops, K.MIXED.min_dim, K.MIXED.min_tiles)
+    K.MIXED.min_flops, K.MIXED.min_dim, K.MIXED.min_tiles = 0.0, 1, 1      # golden cases are tiny: force every K-major GEMM onto the mixed kernel
+    try:
+        cc = pycc_b200.ccwfn(IntegralReference.from_synthetic(syn), model="CCSD(T)", device='GPU',
+                             precision=precision, quiet=True)
+        assert cc.precision == precision and cc.mixed
+        assert cc.H.vvvv_planes is not None and not cc.H.has("vvvv")
+        before = dict(K.MIXED.stats)
+        # the split contractions carry ~2^-22 relative jitter: rms stalls near 3e-9, so converge to the reference's
+        # default thresholds (1e-7), not to 1e-10
+        e = cc.solve_cc(1e-7, 1e-7, 100)
+        assert e is not None
+        assert K.MIXED.stats["gemm"] > before["gemm"] + 3 * len(cc.trace)
+        assert K.MIXED.stats["split_cached"] > before["split_cached"]
+        assert not K.MIXED.on                              # the switch is scoped to the residual evaluation
+        assert abs(cc.trace[-1][0] - float(g["trace_ecc_rms"][-1, 0])) < 1e-6
+        assert abs(float(e) - float(g["e_total_ccsd_t"])) < 1e-6
+        assert np.abs(cc.t2.cpu().numpy() - g["conv_t2"]).max() < 1e-6
+        assert np.abs(cc.t1.cpu().numpy() - g["conv_t1"]).max() < 1e-6
+        # not silently the FP64 path
+        assert np.abs(cc.t2.cpu().numpy() - g["conv_t2"]).max() > 1e-13
+    finally:
+        K.MIXED.min_flops, K.MIXED.min_dim, K.MIXED.min_tiles = keep
+
+
+def test_mixed_precision_keeps_callers_hamiltonian(dev):
+    """A BlockHamiltonian handed in by the caller keeps its FP64 <ab|ef> (it may serve a 'DP' wavefunction too)."""
+    from pycc_b200.hamiltonian import BlockHamiltonian
+    from pycc_b200.synthetic import make_synthetic
+    syn = make_synthetic(3, 6, seed=5)
+    H = BlockHamiltonian.from_factor(syn, DEV[0])
+    mp = pycc_b200.ccwfn(H, model="CCSD", precision="MP", quiet=True)
+    dp = pycc_b200.ccwfn(H, model="CCSD", precision="DP", quiet=True)
+    assert H.has("vvvv") and H.vvvv_planes is not None
+    e_mp, e_dp = mp.solve_cc(1e-8, 1e-7), dp.solve_cc(1e-10, 1e-10)
+    assert 1e-14 < abs(float(e_mp) - float(e_dp)) < 1e-6
+
+
 def test_keyword_errors():
     from pycc_b200.exceptions import InvalidKeywordError, PyCCError
     from pycc_b200.synthetic import make_synthetic
@@ -243,6 +288,41 @@ def test_medium_size_vs_oracle(no, nv, seed, noise):
         assert np.abs(r1.cpu().numpy() - r1_ref).max() < 1e-11
         assert np.abs(r2.cpu().numpy() - r2_ref).max() < 1e-11
     finally:
+        DEV[0] = torch.device("cpu")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("no,nv,seed,force", [(8, 40, 0, True), (10, 64, 2, True), (12, 72, 3, False)])
+def test_medium_size_mixed_vs_oracle(no, nv, seed, force):
+    """precision='MP' on the GPU (tcgen05 split-TF32 GEMMs) vs the FP64 numpy oracle on the same inputs:
+    E(CCSD) and E(CCSD(T)) within 1e-6 Eh (north_star tolerance for mixed precision), amplitudes within 1e-6.
+    ``force``: every K-major GEMM goes through the mixed kernel regardless of size; otherwise the product
+    thresholds apply (ladder always mixed)."""
+    from oracle import ccsd_oracle as co, triples_oracle as to
+    from pycc_b200 import kernels as K
+    from pycc_b200.synthetic import make_synthetic, blocks_from_factor
+    assert torch.cuda.is_available()
+    DEV[0] = torch.device("cuda:0")
+    keep = (K.MIXED.min_flops, K.MIXED.min_dim, K.MIXED.min_tiles)
+    if force:
+        K.MIXED.min_flops, K.MIXED.min_dim, K.MIXED.min_tiles = 0.0, 1, 1
+    try:
+        syn = make_synthetic(no, nv, seed=seed)
+        b = blocks_from_factor(syn)
+        P = co.Problem(b, syn.F, no)
+        e_ref, t1_ref, t2_ref, trace = co.solve_cc(P, 1e-10, 1e-10, 100)
+        et_ref = to.t_tjl(t1_ref, t2_ref, syn.F, b["ovvv"], b["ooov"], b["oovv"])
+        before = K.MIXED.stats["gemm"]
+        cc = pycc_b200.ccwfn(IntegralReference.from_synthetic(syn), model="CCSD(T)", device='GPU', precision="MP",
+                             quiet=True)
+        e = cc.solve_cc(1e-7, 1e-7, 100)
+        assert e is not None and K.MIXED.stats["gemm"] > before
+        assert abs(cc.trace[-1][0] - e_ref) < 1e-6
+        assert abs(float(e) - (e_ref + et_ref)) < 1e-6
+        assert np.abs(cc.t1.cpu().numpy() - t1_ref).max() < 1e-6
+        assert np.abs(cc.t2.cpu().numpy() - t2_ref).max() < 1e-6
+    finally:
+        K.MIXED.min_flops, K.MIXED.min_dim, K.MIXED.min_tiles = keep
         DEV[0] = torch.device("cpu")
 
 

@@ -1,0 +1,125 @@
+"""Mixed-precision (split-TF32 on tcgen05, FP64 accumulation) kernels through the C ABI against torch float64 on the
+same device.  All `-m gpu`.
+
+Tolerance (written out in ``tol``): the tensor core's FP32 accumulate truncates, so an accumulator that receives
+n MMAs is off by at most n ulp = n * 1.2e-7 of its magnitude (measured mean: n * 1.6e-8, a systematic shrink);
+n = MMAs per K chunk into the large accumulator (3 per 8 summation indices for the shared-accumulator kernels,
+configs 1-4; 1 per 8 for the register-accumulating kernel, configs 0/5/6).  On top: the 2^-22 split error and one
+FP32 rounding per chunk -> 1e-6.  Everything relative to the largest |result|.
+"""
+import numpy as np
+import pytest
+import torch
+
+from pycc_b200 import kernels as K
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+
+
+def rnd(*shape, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed + sum(shape))
+    return torch.randn(*shape, dtype=torch.float64, generator=g).to(DEV)
+
+
+def tf32_rna_torch(x32):
+    u = x32.view(torch.int32)
+    return ((u + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def test_split_tf32_planes():
+    rows, Kd, ld = 37, 53, 61
+    buf = rnd(2, rows, ld) * 3.0
+    hi, lo, ldp = K.split_tf32(buf, rows, Kd, ld, batch=2, stride=rows * ld)
+    assert ldp == 56 and tuple(hi.shape) == (2, rows, ldp)
+    x = buf[:, :, :Kd]
+    h = tf32_rna_torch(x.to(torch.float32))
+    l = tf32_rna_torch((x - h.double()).to(torch.float32))
+    assert torch.equal(hi[:, :, :Kd], h) and torch.equal(lo[:, :, :Kd], l)
+    assert float(hi[:, :, Kd:].abs().max()) == 0.0 and float(lo[:, :, Kd:].abs().max()) == 0.0
+    # hi + lo reproduces the double to ~2^-22
+    assert float(((hi.double() + lo.double())[:, :, :Kd] - x).abs().max() / x.abs().max()) < 2.0 ** -21
+    # low 13 mantissa bits are clear: the tensor core reads exactly these values
+    assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0 and int((lo.view(torch.int32) & 0x1FFF).abs().max()) == 0
+
+
+SHAPES = [(128, 256, 32), (128, 256, 64), (128, 128, 256), (256, 512, 2048), (37, 19, 53), (129, 300, 1000),
+          (400, 513, 333), (1, 300, 77), (257, 1, 40), (1600, 1200, 4096)]
+
+
+def tol(config, kchunk, Kd, ref):
+    per8 = 1 if config in (0, 5, 6) else 3
+    nops = per8 * (min(kchunk, Kd) + 7) // 8
+    return (nops * 1.2e-7 + 1e-6) * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("config", [5, 6, 1, 2, 3, 4])
+@pytest.mark.parametrize("M,N,Kd", SHAPES)
+def test_gemm_tf32x3(M, N, Kd, config):
+    A, B = rnd(M, Kd, seed=1), rnd(N, Kd, seed=2)
+    C0 = rnd(M, N + 3, seed=3)
+    C = C0.clone()
+    Ah, Al, lpa = K.split_tf32(A, M, Kd, Kd)
+    Bh, Bl, lpb = K.split_tf32(B, N, Kd, Kd)
+    K.gemm_tf32x3(M, N, Kd, Ah, Al, lpa, Bh, Bl, lpb, C, N + 3, alpha=0.75, beta=-0.5, kchunk=256, config=config)
+    ref = 0.75 * (A @ B.t()) - 0.5 * C0[:, :N]
+    assert float((C[:, :N] - ref).abs().max()) < tol(config, 256, Kd, ref)
+    assert torch.equal(C[:, N:], C0[:, N:])            # nothing written past column N
+
+
+@pytest.mark.parametrize("config", [0, 1])
+@pytest.mark.parametrize("kchunk", [32, 256, 100000])
+def test_gemm_tf32x3_chunked_accumulation(kchunk, config):
+    """Many FP64 drains (kchunk=32: one per k-block), few, and none: same answer; beta applied exactly once."""
+    M, N, Kd = 300, 520, 6000
+    A, B = rnd(M, Kd, seed=4), rnd(N, Kd, seed=5)
+    C0 = rnd(M, N, seed=6)
+    C = C0.clone()
+    Ah, Al, lpa = K.split_tf32(A, M, Kd, Kd)
+    Bh, Bl, lpb = K.split_tf32(B, N, Kd, Kd)
+    K.gemm_tf32x3(M, N, Kd, Ah, Al, lpa, Bh, Bl, lpb, C, N, alpha=-1.25, beta=2.0, kchunk=kchunk, config=config)
+    ref = -1.25 * (A @ B.t()) + 2.0 * C0
+    assert float((C - ref).abs().max()) < tol(config, kchunk, Kd, ref)
+
+
+def test_gemm_tf32x3_batched_and_shared_operand():
+    nb, M, N, Kd = 5, 150, 260, 700
+    A, B = rnd(nb, M, Kd, seed=7), rnd(N, Kd, seed=8)
+    C = torch.zeros(nb, M, N, dtype=torch.float64, device=DEV)
+    Ah, Al, lpa = K.split_tf32(A, M, Kd, Kd, batch=nb, stride=M * Kd)
+    Bh, Bl, lpb = K.split_tf32(B, N, Kd, Kd)
+    K.gemm_tf32x3(M, N, Kd, Ah, Al, lpa, Bh, Bl, lpb, C, N, batch=nb, sA=M * lpa, sB=0, sC=M * N)
+    ref = torch.einsum("bmk,nk->bmn", A, B)
+    assert float((C - ref).abs().max()) < tol(0, 256, Kd, ref)
+
+
+@pytest.mark.parametrize("lockstep", [-1, 0, 1, 4, 7])
+@pytest.mark.parametrize("M,N,Kd,nb", [(19 * 128 - 50, 11 * 128 + 5, 1536, 1), (13 * 128 - 64, 30 * 128, 800, 1),
+                                       (5 * 128, 3 * 128 + 1, 640, 3)])
+def test_gemm_tf32x3_leader_follower_schedule(M, N, Kd, nb, lockstep):
+    """Plain unit schedule (-1 / auto at these sizes) vs the leader/follower block schedule (skew 1, 4, 7): ragged bands of
+    m-tiles (19 -> 12 + 7 with idle CTAs in the second band), several rounds of n-blocks, batches."""
+    A, B = rnd(nb, M, Kd, seed=11), rnd(N, Kd, seed=12)
+    C = torch.zeros(nb, M, N, dtype=torch.float64, device=DEV)
+    Ah, Al, lpa = K.split_tf32(A, M, Kd, Kd, batch=nb, stride=M * Kd)
+    Bh, Bl, lpb = K.split_tf32(B, N, Kd, Kd)
+    K.gemm_tf32x3(M, N, Kd, Ah, Al, lpa, Bh, Bl, lpb, C, N, batch=nb, sA=M * lpa if nb > 1 else 0, sB=0, sC=M * N,
+                  lockstep=lockstep)
+    ref = torch.einsum("bmk,nk->bmn", A, B)
+    assert float((C - ref).abs().max()) < tol(0, 256, Kd, ref)
+
+
+def test_dgemm_routes_to_mixed_when_enabled():
+    M, N, Kd = 1280, 1024, 2048
+    A, B = rnd(M, Kd, seed=9), rnd(N, Kd, seed=10)
+    C = torch.zeros(M, N, dtype=torch.float64, device=DEV)
+    before = dict(K.MIXED.stats)
+    K.MIXED.on = True
+    try:
+        K.dgemm(M, N, Kd, A, Kd, 0, B, Kd, 0, C, N)
+    finally:
+        K.MIXED.on = False
+    assert K.MIXED.stats["gemm"] == before["gemm"] + 1
+    ref = A @ B.t()
+    err = float((C - ref).abs().max())
+    assert 0.0 < err < tol(0, 256, Kd, ref)      # TF32-split, not bitwise FP64
