@@ -321,7 +321,7 @@ def main():
         import gc
         gc.collect()                                # the Hamiltonian <-> its ERI/L views form reference cycles
         torch.cuda.empty_cache()
-        ccm = pycc_b200.ccwfn(syn, model="CCSD", device="GPU", precision="MP", quiet=True, comm=comm)
+        ccm = pycc_b200.ccwfn(syn, model="CCSD(T)", device="GPU", precision="MP", quiet=True, comm=comm)
         diism = pycc_b200.helper_diis(ccm.t1, ccm.t2, 8)
         e_mp = []
 
@@ -359,6 +359,17 @@ def main():
             torch.cuda.synchronize()
         t_lad_mp = la.elapsed_time(lb) * 1e-3 / 3
         del tau, r2
+        # (T) in MP mode: the same sample of triples, t3 build on the split-TF32 kernel (two K segments per GEMM)
+        cctriples.t_tjl(ccm, sample_trip)
+        sync()
+        tma_, tmb_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tma_.record()
+        et_mp = cctriples.t_tjl(ccm, sample_trip)
+        tmb_.record()
+        sync()
+        t_t_mp = tma_.elapsed_time(tmb_) * 1e-3
+        if comm is not None:
+            t_t_mp = comm.all_reduce_max_scalar(t_t_mp)
         tf32_peak, tf32_src = 1130.0, "nominal dense TF32 (no measured entry in MEASURED_PEAKS.json)"
         try:
             torch.backends.cuda.matmul.allow_tf32 = True
@@ -383,6 +394,10 @@ def main():
         mp = {"value": t_mp, "unit": "s/iter", "speedup_vs_fp64": s_iter / t_mp, "dtype": "tf32x3 products, f64 accumulate",
               "max_abs_dE_vs_fp64_same_iteration": de, "iterations_compared": nmp, "ecc_last": e_mp[-1],
               "gpu_launches": int(mp_launches), "stats": dict(K.MIXED.stats),
+              "t": {"tflops_fp64_equivalent": t_flops_per_triple(o, v) * len(sample_trip) / t_t_mp / 1e12,
+                    "seconds": t_t_mp, "speedup_vs_fp64": t_t / t_t_mp, "triples_timed": len(sample_trip),
+                    "full_t_seconds_est": t_t_mp * len(trip) / len(sample_trip),
+                    "e_t_sample": float(et_mp), "abs_dE_vs_fp64": abs(float(et_mp) - float(et))},
               "roofline": {"bound": "tensor", "kernel": "tf32x3_gemm_r_kernel (ladder, ccwfn.py:931)",
                            "achieved": 3.0 * lad_flops / t_lad_mp / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
                            "frac": 3.0 * lad_flops / t_lad_mp / 1e12 / tf32_peak, "peak_source": tf32_src,

@@ -101,6 +101,13 @@ typedef struct {
                                       1..4 = one shared accumulator drained into C in global memory:
                                       1 = 128x256 tile, 32-wide k-blocks, 2 stages; 2 = 128x128, 32, 3 stages;
                                       3 = 128x256, 16-wide k-blocks (64-byte swizzle), 4 stages; 4 = 128x128, 16, 6 stages */
+  /* optional second K segment accumulated into the same tile (the (T) hole term), configs 0/5/6 only; K2 = 0: none */
+  int K2;
+  const float *A2hi, *A2lo, *B2hi, *B2lo;
+  b200cc_i64 lda2, ldb2, strideA2, strideB2;
+  const int* bcoords;              /* device, [batch][4] or NULL: per-batch slab INDEX of {A1,B1,A2,B2} along each operand's own
+                                      stride (slab counts nbA1..nbB2); C stays strided (as b200cc_gemm_desc.bcoords) */
+  int nbA1, nbB1, nbA2, nbB2;
   int lockstep;                    /* configs 5/6: leader/follower tile schedule -- a CTA requests an operand tile only after the
                                       CTA that leads its row / column of the tile block has received it, so every tile is read from
                                       DRAM once and served from L2 afterwards.  > 0: on, followers run this many k-blocks behind;

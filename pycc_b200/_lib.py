@@ -61,6 +61,11 @@ class Gemm3Desc(C.Structure):
         ("batch", C.c_int),
         ("kchunk", C.c_int),
         ("config", C.c_int),
+        ("K2", C.c_int),
+        ("A2hi", dptr), ("A2lo", dptr), ("B2hi", dptr), ("B2lo", dptr),
+        ("lda2", i64), ("ldb2", i64), ("strideA2", i64), ("strideB2", i64),
+        ("bcoords", dptr),
+        ("nbA1", C.c_int), ("nbB1", C.c_int), ("nbA2", C.c_int), ("nbB2", C.c_int),
         ("lockstep", C.c_int),
     ]
 

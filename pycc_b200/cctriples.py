@@ -69,10 +69,18 @@ class TriplesEngine:
                 H._derived["ovvv_iabe"] = K.permuted(self.ovvv, (0, 2, 3, 1))
             self.G = H._derived["ovvv_iabe"]
             self.t2p = K.permuted(self.t2, (0, 2, 3, 1))          # [i,a,b,m] = t2[i,m,a,b]
+        # precision='MP': the (T) GEMMs run on the split-TF32 tcgen05 kernel.  Amplitudes and <mc|jk> are constant for
+        # the lifetime of this engine, so their TF32 planes are split once (kernels._split_operand cache); close()
+        # drops them -- t2 is updated in place by the next CCSD iteration.
+        self.mixed = bool(getattr(ccwfn, "mixed", False)) and self.tma
+        self._planes = {}
+        if self.mixed:
+            for t in (self.t2, self.t2p, self.Y):
+                K.register_constant(t, self._planes)
         nv = self.nv
         # optional: the TMA GEMM can write Q as contiguous 8x8x8 cubes (4 KB runs for the energy kernel).  Measured
         # on B200 this is SLOWER (1.35 vs 2.66 TB/s in the energy kernel), so the plain (v,v,v) layout is the default.
-        self.cube = bool(cube_q) and self.tma
+        self.cube = bool(cube_q) and self.tma and not self.mixed
         self.qsz = K.q_size(nv, self.cube)
         per = 6 * self.qsz * 8
         if q_bytes is None:
@@ -81,6 +89,16 @@ class TriplesEngine:
                 free, _ = torch.cuda.mem_get_info(self.dev)
                 q_bytes = max(per, min(q_bytes * 2, int(free * 0.5)))
         self.nb_max = int(max(1, min(q_bytes // max(per, 1), 65535 // 6, 4096)))
+
+    def close(self):
+        K.unregister_constants(self._planes)
+        self._planes.clear()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def qbuf(self, nb):
         """The Q workspace ([nb][6][v^3] doubles) is kept per device across engines (grow-only), so repeated
@@ -125,9 +143,10 @@ class TriplesEngine:
                 co[:, q, 2] = T[:, x]
                 co[:, q, 3] = T[:, p2] * no + T[:, q2]
             co = torch.from_numpy(co.reshape(nb * 6, 4)).to(self.dev)
-            K.dgemm(nv * nv, nv, nv, self.G, nv, 0, self.t2, nv, 0, Q, nv, 1.0, 0.0, batch=6 * nb,
-                    sA=nv ** 3, sB=nv * nv, sC=self.qsz, seg2=(self.t2p, no, self.Y, no, no, no * nv * nv, nv * no),
-                    bcoords=co, nbatch=(no, no * no, no, no * no), ksplit=1, out_cube_nv=nv if self.cube else 0)
+            with K.mixed_mode(self.mixed):
+                K.dgemm(nv * nv, nv, nv, self.G, nv, 0, self.t2, nv, 0, Q, nv, 1.0, 0.0, batch=6 * nb,
+                        sA=nv ** 3, sB=nv * nv, sC=self.qsz, seg2=(self.t2p, no, self.Y, no, no, no * nv * nv, nv * no),
+                        bcoords=co, nbatch=(no, no * no, no, no * no), ksplit=1, out_cube_nv=nv if self.cube else 0)
             return Q
         tab, aligned = self.table(trip, Q)
         K.dgemm(nv * nv, nv, nv, self.ovvv, nv * nv, 1, self.t2, nv, 0, Q, nv, 1.0, 0.0,
@@ -163,7 +182,10 @@ def t_tjl(ccwfn, triples=None):
     trip = [t for t in trip if not (t[0] == t[1] == t[2])]
     if comm is not None and comm.size > 1:
         trip = trip[comm.rank::comm.size]
-    et = eng.energy(trip)
+    try:
+        et = eng.energy(trip)
+    finally:
+        eng.close()
     if comm is not None and comm.size > 1:
         comm.all_reduce_sum(et)
     return et[0]

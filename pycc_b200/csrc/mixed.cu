@@ -139,7 +139,10 @@ __host__ __device__ constexpr uint32_t make_idesc() {
 struct MxParams {
   int M, N, batch;
   int tiles_m, tiles_n, units;
-  int nkb;           // k-blocks (of BK) in the summation
+  int nkb;           // k-blocks (of BK) in the summation (both segments)
+  int nkb1;          // k-blocks of the first K segment (kernel R: an optional second segment follows, own operands)
+  const int* bcoords;  // [batch][4] per-batch slab index of {A1, B1, A2, B2}, or nullptr (batch index / shared operand)
+  int bA2, bB2;
   int kc;            // k-blocks accumulated in FP32 before a drain into FP64
   int bA, bB;        // operand has its own batch dimension (else shared by all batch entries)
   double* C;
@@ -401,7 +404,10 @@ constexpr int RBN = 128;
 template <int BK, int NSTAGE>
 __global__ void __launch_bounds__(MXR_THREADS, 1)
     tf32x3_gemm_r_kernel(const MxParams p, const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
-                         const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl) {
+                         const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                         const __grid_constant__ CUtensorMap tmA2h, const __grid_constant__ CUtensorMap tmA2l,
+                         const __grid_constant__ CUtensorMap tmB2h, const __grid_constant__ CUtensorMap tmB2l) {
+
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   constexpr int BN = RBN;
   constexpr int ROW_BYTES = BK * 4;
@@ -452,7 +458,11 @@ __global__ void __launch_bounds__(MXR_THREADS, 1)
         if (w == 0) break;
         if (w == 2) continue;
         const int m0 = tm * BM, n0 = tn * BN;
-        const int ba = p.bA ? b : 0, bb = p.bB ? b : 0;
+        int ba = p.bA ? b : 0, bb = p.bB ? b : 0, ba2 = p.bA2 ? b : 0, bb2 = p.bB2 ? b : 0;
+        if (p.bcoords) {     // (T): each batch entry names its own slab of every operand
+          const int4 co = reinterpret_cast<const int4*>(p.bcoords)[b];
+          ba = co.x; bb = co.y; ba2 = co.z; bb2 = co.w;
+        }
         for (int kb = 0; kb < p.nkb; ++kb) {
           if (lf && kb % p.skew == 0) {
             const int need = it * p.nkb + min(kb + p.skew, p.nkb);
@@ -462,10 +472,18 @@ __global__ void __launch_bounds__(MXR_THREADS, 1)
           mbar_wait(empty_bar + stage, phase ^ 1u);
           unsigned char* s = tiles + stage * STAGE_BYTES;
           mbar_expect_tx(full_bar + stage, STAGE_BYTES);
-          tma_load_3d(s, &tmAh, kb * BK, m0, ba, full_bar + stage);
-          tma_load_3d(s + 2 * A_BYTES, &tmBh, kb * BK, n0, bb, full_bar + stage);
-          tma_load_3d(s + A_BYTES, &tmAl, kb * BK, m0, ba, full_bar + stage);
-          tma_load_3d(s + 2 * A_BYTES + B_BYTES, &tmBl, kb * BK, n0, bb, full_bar + stage);
+          if (kb < p.nkb1) {
+            tma_load_3d(s, &tmAh, kb * BK, m0, ba, full_bar + stage);
+            tma_load_3d(s + 2 * A_BYTES, &tmBh, kb * BK, n0, bb, full_bar + stage);
+            tma_load_3d(s + A_BYTES, &tmAl, kb * BK, m0, ba, full_bar + stage);
+            tma_load_3d(s + 2 * A_BYTES + B_BYTES, &tmBl, kb * BK, n0, bb, full_bar + stage);
+          } else {           // second K segment (its own operands), accumulated into the same tile
+            const int k2 = (kb - p.nkb1) * BK;
+            tma_load_3d(s, &tmA2h, k2, m0, ba2, full_bar + stage);
+            tma_load_3d(s + 2 * A_BYTES, &tmB2h, k2, n0, bb2, full_bar + stage);
+            tma_load_3d(s + A_BYTES, &tmA2l, k2, m0, ba2, full_bar + stage);
+            tma_load_3d(s + 2 * A_BYTES + B_BYTES, &tmB2l, k2, n0, bb2, full_bar + stage);
+          }
           if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
         }
       }
@@ -585,6 +603,233 @@ __global__ void __launch_bounds__(MXR_THREADS, 1)
   }
 }
 
+// =====================================================================================================
+// Kernel R2: kernel R on CTA PAIRS (tcgen05 cta_group::2).  The kernel above is bound by operand delivery
+// (L2 -> shared memory: a 128x128 tile needs 64 KB per 32-k stage, tensor pipe 59-70 % active).  Two CTAs of a
+// cluster compute ONE 256x128 tile: each loads its own 128 rows of A but only HALF (64 rows) of B, so a stage is 48 KB
+// per CTA (25 % less traffic per MMA, and 4 stages fit instead of 3).  The leader CTA's MMA thread issues
+// tcgen05.mma.cta_group::2 (M = 256: rows 0-127 accumulate in the leader's TMEM, 128-255 in the peer's; B is read from
+// both CTAs' shared memory); both CTAs' TMA loads signal the LEADER's full barrier (.cta_group::2 loads, barrier
+// address with the peer bit cleared); tcgen05.commit multicasts the "slot free" / "chunk finished" arrivals to both
+// CTAs; each CTA's epilogue warps drain their own TMEM half and arrive remotely on the leader's "buffer drained"
+// barrier (mapa + mbarrier.arrive.shared::cluster).
+// =====================================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the pair's even CTA
+__device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::
+          "r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(leader_bar) & PEER_BIT_MASK)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(slot)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      " setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs of the pair once all MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(ra) : "r"(smem_u32(bar)), "r"(0));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(ra) : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc_2sm_256x128() {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(128 >> 3) << 17) | (static_cast<uint32_t>(256 >> 4) << 24);
+}
+
+template <int BK, int NSTAGE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MXR_THREADS, 1)
+    tf32x3_gemm_r2_kernel(const MxParams p, const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                          const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int BN = RBN, BNH = RBN / 2;
+  constexpr int ROW_BYTES = BK * 4;
+  constexpr int A_BYTES = BM * ROW_BYTES, B_BYTES = BNH * ROW_BYTES, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  constexpr uint32_t TMEM_COLS = 512;
+  constexpr uint32_t IDESC = make_idesc_2sm_256x128();
+  unsigned char* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + NSTAGE * STAGE_BYTES);   // used in the leader CTA only
+  uint64_t* empty_bar = full_bar + NSTAGE;
+  uint64_t* tfull_bar = empty_bar + NSTAGE;
+  uint64_t* tempty_bar = tfull_bar + 2;                                              // used in the leader CTA only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rank = static_cast<int>(cluster_ctarank());
+  const int pair = static_cast<int>(blockIdx.x) >> 1, npairs = static_cast<int>(gridDim.x) >> 1;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    mbar_init(tfull_bar + 0, 1);
+    mbar_init(tfull_bar + 1, 1);
+    mbar_init(tempty_bar + 0, 16);      // 8 epilogue warps x 2 CTAs
+    mbar_init(tempty_bar + 1, 16);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  const int nchunks = (p.nkb + p.kc - 1) / p.kc;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = pair; u < p.units; u += npairs) {
+        int tm, tn, b;
+        decode_unit(p, u, tm, tn, b);
+        const int m0 = tm * 2 * BM + rank * BM, n0 = tn * BN + rank * BNH;
+        const int ba = p.bA ? b : 0, bb = p.bB ? b : 0;
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait(empty_bar + stage, phase ^ 1u);
+          unsigned char* s = tiles + stage * STAGE_BYTES;
+          if (rank == 0) mbar_expect_tx(full_bar + stage, 2 * STAGE_BYTES);      // both CTAs' bytes land on this barrier
+          tma_load_3d_2sm(s, &tmAh, kb * BK, m0, ba, full_bar + stage);
+          tma_load_3d_2sm(s + 2 * A_BYTES, &tmBh, kb * BK, n0, bb, full_bar + stage);
+          tma_load_3d_2sm(s + A_BYTES, &tmAl, kb * BK, m0, ba, full_bar + stage);
+          tma_load_3d_2sm(s + 2 * A_BYTES + B_BYTES, &tmBl, kb * BK, n0, bb, full_bar + stage);
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t acc_it = 0;
+      for (int u = pair; u < p.units; u += npairs) {
+        for (int c = 0; c < nchunks; ++c, ++acc_it) {
+          const uint32_t buf = acc_it & 1u, aphase = (acc_it >> 1) & 1u;
+          mbar_wait(tempty_bar + buf, aphase ^ 1u);
+          tc_fence_after();
+          const uint32_t d_hh = tmem_base + buf * BN, d_x = tmem_base + 2 * BN + buf * BN;
+          const int kb0 = c * p.kc, kb1 = min(p.nkb, kb0 + p.kc);
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(full_bar + stage, phase);
+            tc_fence_after();
+            const uint32_t s = smem_u32(tiles + stage * STAGE_BYTES);
+            const uint64_t ah = make_sdesc<ROW_BYTES>(s), al = make_sdesc<ROW_BYTES>(s + A_BYTES);
+            const uint64_t bh = make_sdesc<ROW_BYTES>(s + 2 * A_BYTES), bl = make_sdesc<ROW_BYTES>(s + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+            for (int j = 0; j < BK / 8; ++j) {
+              const uint64_t o = static_cast<uint64_t>(2 * j);
+              const uint32_t cont = (kb > kb0 || j > 0) ? 1u : 0u;
+              umma_tf32_2sm(d_hh, ah + o, bh + o, IDESC, cont);
+              umma_tf32_2sm(d_x, ah + o, bl + o, IDESC, cont);
+              umma_tf32_2sm(d_x, al + o, bh + o, IDESC, 1u);
+            }
+            umma_commit_2sm(empty_bar + stage);
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+          }
+          umma_commit_2sm(tfull_bar + buf);
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const int rloc = quarter * 32 + lane;
+    uint32_t acc_it = 0;
+    double acc[64];
+    for (int u = pair; u < p.units; u += npairs) {
+      int tm, tn, b;
+      decode_unit(p, u, tm, tn, b);
+      const int row = tm * 2 * BM + rank * BM + rloc;
+      const int n0 = tn * BN + half * 64;
+#pragma unroll
+      for (int t = 0; t < 64; ++t) acc[t] = 0.0;
+      for (int c = 0; c < nchunks; ++c, ++acc_it) {
+        const uint32_t buf = acc_it & 1u, aphase = (acc_it >> 1) & 1u;
+        mbar_wait(tfull_bar + buf, aphase);
+        tc_fence_after();
+        const uint32_t t_hh = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BN + half * 64;
+        const uint32_t t_x = t_hh + 2 * BN;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t v[16], w[16];
+          tmem_ld16(t_hh + q * 16, v);
+          tmem_ld16(t_x + q * 16, w);
+          tmem_wait_ld();
+#pragma unroll
+          for (int t = 0; t < 16; ++t)
+            acc[q * 16 + t] += static_cast<double>(__uint_as_float(v[t]) + __uint_as_float(w[t]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(tempty_bar + buf);
+      }
+      if (row < p.M && n0 < p.N) {
+        double* cp = p.C + (i64)b * p.sC + (i64)row * p.ldc + n0;
+        const bool rd = p.beta != 0.0;
+        if (p.vec && n0 + 64 <= p.N) {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            double x = p.alpha * acc[2 * t], y = p.alpha * acc[2 * t + 1];
+            if (rd) {
+              const double2 o = *reinterpret_cast<const double2*>(cp + 2 * t);
+              x += p.beta * o.x;
+              y += p.beta * o.y;
+            }
+            *reinterpret_cast<double2*>(cp + 2 * t) = make_double2(x, y);
+          }
+        } else {
+#pragma unroll
+          for (int t = 0; t < 64; ++t) {
+            if (n0 + t < p.N) {
+              double x = p.alpha * acc[t];
+              if (rd) x += p.beta * cp[t];
+              cp[t] = x;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // the peer's shared memory / TMEM must stay alive until the leader's last MMA has completed: both CTAs' epilogues
+  // have seen the last "chunk finished" arrival before they get here
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  }
+}
+
 // ---- FP64 -> (hi, lo) TF32 planes --------------------------------------------------------------------
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
@@ -678,7 +923,11 @@ static int launch(const b200cc_gemm3_desc* d, cudaStream_t st) {
   const i64 units = (i64)p.tiles_m * p.tiles_n * d->batch;
   if (units > 2000000000LL) { set_error("b200cc_gemm_tf32x3: too many tiles"); return 1; }
   p.units = (int)units;
-  p.nkb = (d->K + BK - 1) / BK;
+  p.nkb1 = (d->K + BK - 1) / BK;
+  p.nkb = p.nkb1 + (d->K2 > 0 ? (d->K2 + BK - 1) / BK : 0);
+  p.bcoords = d->bcoords;
+  p.bA2 = (d->batch > 1 && d->strideA2 != 0) ? 1 : 0;
+  p.bB2 = (d->batch > 1 && d->strideB2 != 0) ? 1 : 0;
   const int kchunk = d->kchunk > 0 ? d->kchunk : (REG ? 256 : 2048);
   p.kc = kchunk / BK > 0 ? kchunk / BK : 1;
   p.bA = (d->batch > 1 && d->strideA != 0) ? 1 : 0;
@@ -692,10 +941,23 @@ static int launch(const b200cc_gemm3_desc* d, cudaStream_t st) {
   p.skew = 4;
 
   CUtensorMap tAh, tAl, tBh, tBl;
-  if (make_tmap(&tAh, d->Ahi, d->M, d->K, d->lda, d->strideA, d->batch, BK, BM)) return 1;
-  if (make_tmap(&tAl, d->Alo, d->M, d->K, d->lda, d->strideA, d->batch, BK, BM)) return 1;
-  if (make_tmap(&tBh, d->Bhi, d->N, d->K, d->ldb, d->strideB, d->batch, BK, BN)) return 1;
-  if (make_tmap(&tBl, d->Blo, d->N, d->K, d->ldb, d->strideB, d->batch, BK, BN)) return 1;
+  const bool bc = d->bcoords != nullptr;
+  if (make_tmap(&tAh, d->Ahi, d->M, d->K, d->lda, d->strideA, bc ? d->nbA1 : d->batch, BK, BM)) return 1;
+  if (make_tmap(&tAl, d->Alo, d->M, d->K, d->lda, d->strideA, bc ? d->nbA1 : d->batch, BK, BM)) return 1;
+  if (make_tmap(&tBh, d->Bhi, d->N, d->K, d->ldb, d->strideB, bc ? d->nbB1 : d->batch, BK, BN)) return 1;
+  if (make_tmap(&tBl, d->Blo, d->N, d->K, d->ldb, d->strideB, bc ? d->nbB1 : d->batch, BK, BN)) return 1;
+  CUtensorMap tA2h = tAh, tA2l = tAl, tB2h = tBh, tB2l = tBl;
+  if (d->K2 > 0) {
+    if (!REG) { set_error("b200cc_gemm_tf32x3: a second K segment needs config 0/5/6"); return 1; }
+    if (make_tmap(&tA2h, d->A2hi, d->M, d->K2, d->lda2, d->strideA2, bc ? d->nbA2 : d->batch, BK, BM)) return 1;
+    if (make_tmap(&tA2l, d->A2lo, d->M, d->K2, d->lda2, d->strideA2, bc ? d->nbA2 : d->batch, BK, BM)) return 1;
+    if (make_tmap(&tB2h, d->B2hi, d->N, d->K2, d->ldb2, d->strideB2, bc ? d->nbB2 : d->batch, BK, BN)) return 1;
+    if (make_tmap(&tB2l, d->B2lo, d->N, d->K2, d->ldb2, d->strideB2, bc ? d->nbB2 : d->batch, BK, BN)) return 1;
+  }
+  if (bc) {
+    if (!REG) { set_error("b200cc_gemm_tf32x3: bcoords need config 0/5/6"); return 1; }
+    p.bA = p.bB = p.bA2 = p.bB2 = 1;
+  }
   constexpr int SMEM = NSTAGE * (2 * BM + 2 * BN) * BK * 4 + (2 * NSTAGE + 4) * (int)sizeof(uint64_t) + 16 + 1024;
   static bool configured = false;
   const int nsm = sm_count();
@@ -718,7 +980,7 @@ static int launch(const b200cc_gemm3_desc* d, cudaStream_t st) {
       B200CC_CUDA_OK(cudaFuncSetAttribute(tf32x3_gemm_r_kernel<BK, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
       configured = true;
     }
-    tf32x3_gemm_r_kernel<BK, NSTAGE><<<grid, MXR_THREADS, SMEM, st>>>(p, tAh, tAl, tBh, tBl);
+    tf32x3_gemm_r_kernel<BK, NSTAGE><<<grid, MXR_THREADS, SMEM, st>>>(p, tAh, tAl, tBh, tBl, tA2h, tA2l, tB2h, tB2l);
     return check_launch("tf32x3_gemm_r_kernel");
   } else {
     if (!configured) {
@@ -728,6 +990,46 @@ static int launch(const b200cc_gemm3_desc* d, cudaStream_t st) {
     tf32x3_gemm_kernel<BN, BK, NSTAGE><<<grid, MX_THREADS, SMEM, st>>>(p, tAh, tAl, tBh, tBl);
     return check_launch("tf32x3_gemm_kernel");
   }
+}
+
+template <int BK, int NSTAGE>
+static int launch_r2(const b200cc_gemm3_desc* d, cudaStream_t st) {
+  MxParams p;
+  p.M = d->M; p.N = d->N; p.batch = d->batch;
+  if (d->K2 > 0 || d->bcoords) { set_error("b200cc_gemm_tf32x3: config 7 takes one K segment and strided batches only"); return 1; }
+  p.bcoords = nullptr; p.bA2 = p.bB2 = 0;
+  p.tiles_m = (d->M + 2 * BM - 1) / (2 * BM);          // 256-row pair tiles
+  p.tiles_n = (d->N + RBN - 1) / RBN;
+  const i64 units = (i64)p.tiles_m * p.tiles_n * d->batch;
+  if (units > 2000000000LL) { set_error("b200cc_gemm_tf32x3: too many tiles"); return 1; }
+  p.units = (int)units;
+  p.nkb = p.nkb1 = (d->K + BK - 1) / BK;
+  const int kchunk = d->kchunk > 0 ? d->kchunk : 256;
+  p.kc = kchunk / BK > 0 ? kchunk / BK : 1;
+  p.bA = (d->batch > 1 && d->strideA != 0) ? 1 : 0;
+  p.bB = (d->batch > 1 && d->strideB != 0) ? 1 : 0;
+  p.C = d->C; p.ldc = d->ldc; p.sC = d->strideC;
+  p.alpha = d->alpha; p.beta = d->beta;
+  p.vec = (al16(d->C) && (d->ldc & 1) == 0 && (d->strideC & 1) == 0) ? 1 : 0;
+  p.gm = p.tiles_m <= 10 ? p.tiles_m : 8;
+  p.prog = nullptr;
+  p.gn = p.nmb = p.nnb = p.nrounds = 0;
+  p.skew = 4;
+  CUtensorMap tAh, tAl, tBh, tBl;
+  if (make_tmap(&tAh, d->Ahi, d->M, d->K, d->lda, d->strideA, d->batch, BK, BM)) return 1;
+  if (make_tmap(&tAl, d->Alo, d->M, d->K, d->lda, d->strideA, d->batch, BK, BM)) return 1;
+  if (make_tmap(&tBh, d->Bhi, d->N, d->K, d->ldb, d->strideB, d->batch, BK, RBN / 2)) return 1;
+  if (make_tmap(&tBl, d->Blo, d->N, d->K, d->ldb, d->strideB, d->batch, BK, RBN / 2)) return 1;
+  constexpr int SMEM = NSTAGE * (2 * BM + RBN) * BK * 4 + (2 * NSTAGE + 4) * (int)sizeof(uint64_t) + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    B200CC_CUDA_OK(cudaFuncSetAttribute(tf32x3_gemm_r2_kernel<BK, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  const int maxpairs = sm_count() / 2;
+  const int npairs = p.units < maxpairs ? p.units : maxpairs;
+  tf32x3_gemm_r2_kernel<BK, NSTAGE><<<2 * npairs, MXR_THREADS, SMEM, st>>>(p, tAh, tAl, tBh, tBl);
+  return check_launch("tf32x3_gemm_r2_kernel");
 }
 
 }  // namespace mx
@@ -762,11 +1064,18 @@ extern "C" int b200cc_gemm_tf32x3(const b200cc_gemm3_desc* d, void* stream) {
     set_error("b200cc_gemm_tf32x3: planes must be 16-byte aligned with pitches / strides that are multiples of 4 floats");
     return 1;
   }
+  if (d->K2 > 0 && (!d->A2hi || !d->A2lo || !d->B2hi || !d->B2lo || !mx::al16(d->A2hi) || !mx::al16(d->A2lo) ||
+                    !mx::al16(d->B2hi) || !mx::al16(d->B2lo) || (d->lda2 & 3) || (d->ldb2 & 3) || (d->strideA2 & 3) ||
+                    (d->strideB2 & 3) || d->lda2 < d->K2 || d->ldb2 < d->K2)) {
+    set_error("b200cc_gemm_tf32x3: bad second-segment planes");
+    return 1;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   switch (d->config) {
     case 0:
     case 5: return mx::launch<128, 32, 3, true>(d, st);
     case 6: return mx::launch<128, 16, 6, true>(d, st);
+    case 7: return mx::launch_r2<32, 4>(d, st);
     case 1: return mx::launch<256, 32, 2, false>(d, st);
     case 2: return mx::launch<128, 32, 3, false>(d, st);
     case 3: return mx::launch<256, 16, 4, false>(d, st);

@@ -142,9 +142,10 @@ def _split_operand(X, rows, K, ld, batch, stride):
 
 
 def gemm_tf32x3(M, N, K, Ahi, Alo, lda, Bhi, Blo, ldb, Cmat, ldc, alpha=1.0, beta=0.0, batch=1, sA=0, sB=0, sC=0,
-                kchunk=None, config=None, lockstep=None):
-    """C[b] = alpha * A[b] B[b]^T + beta * C[b] from split-TF32 planes (b200cc_gemm_tf32x3); plane operands may be
-    tensors or (tensor, float offset)."""
+                kchunk=None, config=None, lockstep=None, seg2=None, bcoords=None, nbatch=None):
+    """C[b] = alpha * (A[b] B[b]^T [+ A2[b] B2[b]^T]) + beta * C[b] from split-TF32 planes (b200cc_gemm_tf32x3); plane
+    operands may be tensors or (tensor, float offset).  seg2 = (A2hi, A2lo, lda2, B2hi, B2lo, ldb2, K2, sA2, sB2);
+    bcoords / nbatch as in dgemm."""
     if M == 0 or N == 0 or batch == 0:
         return
 
@@ -158,12 +159,21 @@ def gemm_tf32x3(M, N, K, Ahi, Alo, lda, Bhi, Blo, ldb, Cmat, ldc, alpha=1.0, bet
     d.kchunk = int(MIXED.kchunk if kchunk is None else kchunk)
     d.config = int(MIXED.config if config is None else config)
     d.lockstep = int(MIXED.lockstep if lockstep is None else lockstep)
+    if seg2 is not None:
+        A2h, A2l, lda2, B2h, B2l, ldb2, K2, sA2, sB2 = seg2
+        d.K2, d.A2hi, d.A2lo, d.B2hi, d.B2lo = int(K2), fa(A2h), fa(A2l), fa(B2h), fa(B2l)
+        d.lda2, d.ldb2, d.strideA2, d.strideB2 = int(lda2), int(ldb2), int(sA2), int(sB2)
+    if bcoords is not None:
+        d.bcoords = _lib.ptr(bcoords)
+        d.nbA1, d.nbB1, d.nbA2, d.nbB2 = (int(x) for x in nbatch)
     _lib.check(_lib.get().b200cc_gemm_tf32x3(C.byref(d), _lib.stream()), "b200cc_gemm_tf32x3")
     MIXED.stats["gemm"] += 1
 
 
 def _mixed_eligible(M, N, K, A, B, transA, transB, batch, seg2, table, bcoords, out_cube_nv):
-    return (MIXED.on and not transA and not transB and seg2 is None and table is None and bcoords is None
+    if seg2 is not None and (isinstance(seg2[0], int) or isinstance(seg2[2], int)):
+        return False
+    return (MIXED.on and not transA and not transB and table is None
             and not out_cube_nv and not isinstance(A, int) and not isinstance(B, int)
             and min(M, N, K) >= MIXED.min_dim and 2.0 * M * N * K * batch >= MIXED.min_flops
             and ((M + 127) // 128) * ((N + 127) // 128) * batch >= MIXED.min_tiles)
@@ -179,10 +189,20 @@ def dgemm(M, N, K, A, lda, transA, B, ldb, transB, Cmat, ldc, alpha=1.0, beta=0.
     if M == 0 or N == 0 or batch == 0:
         return
     if _mixed_eligible(M, N, K, A, B, transA, transB, batch, seg2, table, bcoords, out_cube_nv):
-        Ah, Al, lpa = _split_operand(A, M, K, lda, batch, sA)
-        Bh, Bl, lpb = _split_operand(B, N, K, ldb, batch, sB)
+        # with bcoords every operand is a stack of slabs (counts in nbatch) that the batch entries index
+        nA1, nB1, nA2, nB2 = (int(x) for x in nbatch) if bcoords is not None else (batch,) * 4
+        Ah, Al, lpa = _split_operand(A, M, K, lda, nA1, sA)
+        Bh, Bl, lpb = _split_operand(B, N, K, ldb, nB1, sB)
+        s2 = None
+        if seg2 is not None:
+            A2, lda2, B2, ldb2, K2, sA2, sB2 = seg2
+            A2h, A2l, lpa2 = _split_operand(A2, M, K2, lda2, nA2, sA2)
+            B2h, B2l, lpb2 = _split_operand(B2, N, K2, ldb2, nB2, sB2)
+            s2 = (A2h, A2l, lpa2, B2h, B2l, lpb2, K2, M * lpa2 if (nA2 > 1 and sA2) else 0,
+                  N * lpb2 if (nB2 > 1 and sB2) else 0)
         return gemm_tf32x3(M, N, K, Ah, Al, lpa, Bh, Bl, lpb, Cmat, ldc, alpha, beta, batch,
-                           M * lpa if (batch > 1 and sA) else 0, N * lpb if (batch > 1 and sB) else 0, sC)
+                           M * lpa if (nA1 > 1 and sA) else 0, N * lpb if (nB1 > 1 and sB) else 0, sC,
+                           seg2=s2, bcoords=bcoords, nbatch=nbatch)
     d = GemmDesc()
     d.M, d.N, d.transA, d.transB = int(M), int(N), int(bool(transA)), int(bool(transB))
     d.K1 = int(K)

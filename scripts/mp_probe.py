@@ -58,6 +58,8 @@ def run(name, M, N, Kd, configs, kchunks, locksteps=(0,)):
 if quick:
     run("small", 1600, 2048, 8192, [5, 6, 1, 3], [256, 2048])
 else:
-    run("ladder_slice", 1600, 36000, 90000, [5], [256], [int(x) for x in os.environ.get("LS", "-1,4,8").split(",")])
+    run("ladder_slice", 1600, 36000, 90000, [5, 7], [256])
+    run("ladder_slice_T", 36000, 1600, 90000, [5, 7], [256])
+    run("ring", 12000, 12000, 12000, [5, 7], [256])
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/mp_probe.json", "w"), indent=1)

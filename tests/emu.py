@@ -144,12 +144,20 @@ class EmuLib:
         self._count("gemm_tf32x3")
         if d.M <= 0 or d.N <= 0 or d.batch <= 0:
             return 0
+        bc = _ints(d.bcoords, 4 * d.batch).reshape(d.batch, 4) if d.bcoords else None
+
+        def pl(addr, rows, ld, st, b, Kd):
+            return _f32(addr + 4 * b * st, (rows, ld))[:, :Kd].astype(np.float64)
+
         for b in range(d.batch):
-            def pl(addr, rows, ld, st):
-                return _f32(addr + 4 * b * st, (rows, ld))[:, :d.K].astype(np.float64)
-            ah, al = pl(d.Ahi, d.M, d.lda, d.strideA), pl(d.Alo, d.M, d.lda, d.strideA)
-            bh, bl = pl(d.Bhi, d.N, d.ldb, d.strideB), pl(d.Blo, d.N, d.ldb, d.strideB)
+            i1, j1, i2, j2 = (int(x) for x in bc[b]) if bc is not None else (b, b, b, b)
+            ah, al = pl(d.Ahi, d.M, d.lda, d.strideA, i1, d.K), pl(d.Alo, d.M, d.lda, d.strideA, i1, d.K)
+            bh, bl = pl(d.Bhi, d.N, d.ldb, d.strideB, j1, d.K), pl(d.Blo, d.N, d.ldb, d.strideB, j1, d.K)
             acc = ah @ bh.T + ah @ bl.T + al @ bh.T
+            if d.K2 > 0:
+                ah, al = pl(d.A2hi, d.M, d.lda2, d.strideA2, i2, d.K2), pl(d.A2lo, d.M, d.lda2, d.strideA2, i2, d.K2)
+                bh, bl = pl(d.B2hi, d.N, d.ldb2, d.strideB2, j2, d.K2), pl(d.B2lo, d.N, d.ldb2, d.strideB2, j2, d.K2)
+                acc = acc + ah @ bh.T + ah @ bl.T + al @ bh.T
             Cm = _arr(d.C + 8 * b * d.strideC, (d.M, d.N), (d.ldc, 1))
             if d.beta != 0.0:
                 Cm[...] = d.alpha * acc + d.beta * Cm

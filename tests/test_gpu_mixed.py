@@ -48,12 +48,12 @@ SHAPES = [(128, 256, 32), (128, 256, 64), (128, 128, 256), (256, 512, 2048), (37
 
 
 def tol(config, kchunk, Kd, ref):
-    per8 = 1 if config in (0, 5, 6) else 3
+    per8 = 1 if config in (0, 5, 6, 7) else 3
     nops = per8 * (min(kchunk, Kd) + 7) // 8
     return (nops * 1.2e-7 + 1e-6) * float(ref.abs().max())
 
 
-@pytest.mark.parametrize("config", [5, 6, 1, 2, 3, 4])
+@pytest.mark.parametrize("config", [7, 5, 6, 1, 2, 3, 4])
 @pytest.mark.parametrize("M,N,Kd", SHAPES)
 def test_gemm_tf32x3(M, N, Kd, config):
     A, B = rnd(M, Kd, seed=1), rnd(N, Kd, seed=2)
@@ -67,7 +67,7 @@ def test_gemm_tf32x3(M, N, Kd, config):
     assert torch.equal(C[:, N:], C0[:, N:])            # nothing written past column N
 
 
-@pytest.mark.parametrize("config", [0, 1])
+@pytest.mark.parametrize("config", [0, 1, 7])
 @pytest.mark.parametrize("kchunk", [32, 256, 100000])
 def test_gemm_tf32x3_chunked_accumulation(kchunk, config):
     """Many FP64 drains (kchunk=32: one per k-block), few, and none: same answer; beta applied exactly once."""
@@ -82,13 +82,14 @@ def test_gemm_tf32x3_chunked_accumulation(kchunk, config):
     assert float((C - ref).abs().max()) < tol(config, kchunk, Kd, ref)
 
 
-def test_gemm_tf32x3_batched_and_shared_operand():
+@pytest.mark.parametrize("config", [0, 7])
+def test_gemm_tf32x3_batched_and_shared_operand(config):
     nb, M, N, Kd = 5, 150, 260, 700
     A, B = rnd(nb, M, Kd, seed=7), rnd(N, Kd, seed=8)
     C = torch.zeros(nb, M, N, dtype=torch.float64, device=DEV)
     Ah, Al, lpa = K.split_tf32(A, M, Kd, Kd, batch=nb, stride=M * Kd)
     Bh, Bl, lpb = K.split_tf32(B, N, Kd, Kd)
-    K.gemm_tf32x3(M, N, Kd, Ah, Al, lpa, Bh, Bl, lpb, C, N, batch=nb, sA=M * lpa, sB=0, sC=M * N)
+    K.gemm_tf32x3(M, N, Kd, Ah, Al, lpa, Bh, Bl, lpb, C, N, batch=nb, sA=M * lpa, sB=0, sC=M * N, config=config)
     ref = torch.einsum("bmk,nk->bmn", A, B)
     assert float((C - ref).abs().max()) < tol(0, 256, Kd, ref)
 
@@ -107,6 +108,48 @@ def test_gemm_tf32x3_leader_follower_schedule(M, N, Kd, nb, lockstep):
                   lockstep=lockstep)
     ref = torch.einsum("bmk,nk->bmn", A, B)
     assert float((C - ref).abs().max()) < tol(0, 256, Kd, ref)
+
+
+def test_gemm_tf32x3_pairs_many_tiles():
+    """CTA-pair kernel: several 256x128 tiles per pair, ragged M (last pair tile half empty) and N."""
+    M, N, Kd = 9 * 256 + 100, 21 * 128 + 70, 1100
+    A, B = rnd(M, Kd, seed=13), rnd(N, Kd, seed=14)
+    C0 = rnd(M, N, seed=15)
+    C = C0.clone()
+    Ah, Al, lpa = K.split_tf32(A, M, Kd, Kd)
+    Bh, Bl, lpb = K.split_tf32(B, N, Kd, Kd)
+    K.gemm_tf32x3(M, N, Kd, Ah, Al, lpa, Bh, Bl, lpb, C, N, alpha=0.5, beta=1.0, config=7)
+    ref = 0.5 * (A @ B.t()) + C0
+    assert float((C - ref).abs().max()) < tol(7, 256, Kd, ref)
+
+
+def test_two_segment_slab_indexed_gemm_matches_fp64():
+    """The (T) launch shape: batch entries pick operand slabs by index (bcoords) and chain a second K segment into the
+    same tile; mixed kernel vs the FP64 DMMA kernel on identical arguments."""
+    nsA, nsB, M, N, K1, K2, nb = 4, 6, 700, 136, 136, 12, 9
+    A1, B1 = rnd(nsA, M, K1, seed=21), rnd(nsB, N, K1, seed=22)
+    A2, B2 = rnd(nsA, M, K2, seed=23), rnd(nsB, N, K2, seed=24)
+    g = torch.Generator().manual_seed(5)
+    co = torch.stack([torch.randint(0, nsA, (nb,), generator=g), torch.randint(0, nsB, (nb,), generator=g),
+                      torch.randint(0, nsA, (nb,), generator=g), torch.randint(0, nsB, (nb,), generator=g)], 1)
+    co = co.to(torch.int32).to(DEV)
+    out = {}
+    for mixed in (False, True):
+        C = torch.zeros(nb, M, N, dtype=torch.float64, device=DEV)
+        keep = (K.MIXED.min_flops, K.MIXED.min_tiles)
+        K.MIXED.min_flops, K.MIXED.min_tiles = 0.0, 1
+        try:
+            with K.mixed_mode(mixed):
+                K.dgemm(M, N, K1, A1, K1, 0, B1, K1, 0, C, N, 1.0, 0.0, batch=nb, sA=M * K1, sB=N * K1, sC=M * N,
+                        seg2=(A2, K2, B2, K2, K2, M * K2, N * K2), bcoords=co, nbatch=(nsA, nsB, nsA, nsB), ksplit=1)
+        finally:
+            K.MIXED.min_flops, K.MIXED.min_tiles = keep
+        out[mixed] = C
+    c = co.cpu().numpy()
+    ref = torch.stack([A1[c[b, 0]] @ B1[c[b, 1]].t() + A2[c[b, 2]] @ B2[c[b, 3]].t() for b in range(nb)])
+    assert float((out[False] - ref).abs().max()) < 1e-11 * float(ref.abs().max())
+    err = float((out[True] - ref).abs().max())
+    assert 0.0 < err < tol(0, 256, K1 + K2, ref)
 
 
 def test_dgemm_routes_to_mixed_when_enabled():
