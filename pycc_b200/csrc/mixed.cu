@@ -118,6 +118,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): a thread that owns a run of a row moves one full 32-byte sector
+// per instruction
+__device__ __forceinline__ void ld_global_v4(const double* p, double (&v)[4]) {
+  asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];\n" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void st_global_v4(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
 // Shared-memory matrix descriptor of a K-major operand tile whose rows are ROW_BYTES (= the swizzle span) long:
 // 8-row groups are 8*ROW_BYTES apart (stride byte offset); start address / offsets in 16-byte units;
 // bits [46,48) = descriptor version 1 (sm_100); bits [61,64) = swizzle mode (2 = 128 B, 4 = 64 B).
@@ -148,7 +157,7 @@ struct MxParams {
   double* C;
   i64 ldc, sC;
   double alpha, beta;
-  int vec;           // 16-byte vector access to C is legal
+  int vec;           // widest legal vector access to C in doubles: 4 (256-bit LDG/STG, one full sector per thread), 2, or 0
   int gm;            // rasterisation: units sweep the n-tiles inside bands of gm m-tiles (one wave ~ gm x 148/gm tiles)
   // leader/follower schedule (kernel R, prog != nullptr): the grid is a gm x gn block of CTAs, CTA c = (i = c % gm,
   // g = c / gm) computes tile (mb*gm + i, nb*gn + g) of block (mb, nb) in round R = (b*nmb + mb)*nnb + nb
@@ -569,7 +578,15 @@ __global__ void __launch_bounds__(MXR_THREADS, 1)
       if (row < p.M && n0 < p.N) {
         double* cp = p.C + (i64)b * p.sC + (i64)row * p.ldc + n0;
         const bool rd = p.beta != 0.0;
-        if (p.vec && n0 + 64 <= p.N) {
+        if (p.vec == 4 && n0 + 64 <= p.N) {
+#pragma unroll
+          for (int t = 0; t < 16; ++t) {
+            double o[4] = {0.0, 0.0, 0.0, 0.0};
+            if (rd) ld_global_v4(cp + 4 * t, o);
+            st_global_v4(cp + 4 * t, p.alpha * acc[4 * t] + p.beta * o[0], p.alpha * acc[4 * t + 1] + p.beta * o[1],
+                         p.alpha * acc[4 * t + 2] + p.beta * o[2], p.alpha * acc[4 * t + 3] + p.beta * o[3]);
+          }
+        } else if (p.vec && n0 + 64 <= p.N) {
 #pragma unroll
           for (int t = 0; t < 32; ++t) {
             double x = p.alpha * acc[2 * t], y = p.alpha * acc[2 * t + 1];
@@ -794,7 +811,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MXR_THREADS, 1)
       if (row < p.M && n0 < p.N) {
         double* cp = p.C + (i64)b * p.sC + (i64)row * p.ldc + n0;
         const bool rd = p.beta != 0.0;
-        if (p.vec && n0 + 64 <= p.N) {
+        if (p.vec == 4 && n0 + 64 <= p.N) {
+#pragma unroll
+          for (int t = 0; t < 16; ++t) {
+            double o[4] = {0.0, 0.0, 0.0, 0.0};
+            if (rd) ld_global_v4(cp + 4 * t, o);
+            st_global_v4(cp + 4 * t, p.alpha * acc[4 * t] + p.beta * o[0], p.alpha * acc[4 * t + 1] + p.beta * o[1],
+                         p.alpha * acc[4 * t + 2] + p.beta * o[2], p.alpha * acc[4 * t + 3] + p.beta * o[3]);
+          }
+        } else if (p.vec && n0 + 64 <= p.N) {
 #pragma unroll
           for (int t = 0; t < 32; ++t) {
             double x = p.alpha * acc[2 * t], y = p.alpha * acc[2 * t + 1];
@@ -934,7 +959,8 @@ static int launch(const b200cc_gemm3_desc* d, cudaStream_t st) {
   p.bB = (d->batch > 1 && d->strideB != 0) ? 1 : 0;
   p.C = d->C; p.ldc = d->ldc; p.sC = d->strideC;
   p.alpha = d->alpha; p.beta = d->beta;
-  p.vec = (al16(d->C) && (d->ldc & 1) == 0 && (d->strideC & 1) == 0) ? 1 : 0;
+  p.vec = (al16(d->C) && (d->ldc & 1) == 0 && (d->strideC & 1) == 0) ? 2 : 0;
+  if (p.vec && (reinterpret_cast<uintptr_t>(d->C) & 31) == 0 && (d->ldc & 3) == 0 && (d->strideC & 3) == 0) p.vec = 4;
   p.gm = p.tiles_m <= 16 ? p.tiles_m : 12;
   p.prog = nullptr;
   p.gn = p.nmb = p.nnb = p.nrounds = 0;
@@ -1010,7 +1036,8 @@ static int launch_r2(const b200cc_gemm3_desc* d, cudaStream_t st) {
   p.bB = (d->batch > 1 && d->strideB != 0) ? 1 : 0;
   p.C = d->C; p.ldc = d->ldc; p.sC = d->strideC;
   p.alpha = d->alpha; p.beta = d->beta;
-  p.vec = (al16(d->C) && (d->ldc & 1) == 0 && (d->strideC & 1) == 0) ? 1 : 0;
+  p.vec = (al16(d->C) && (d->ldc & 1) == 0 && (d->strideC & 1) == 0) ? 2 : 0;
+  if (p.vec && (reinterpret_cast<uintptr_t>(d->C) & 31) == 0 && (d->ldc & 3) == 0 && (d->strideC & 3) == 0) p.vec = 4;
   p.gm = p.tiles_m <= 10 ? p.tiles_m : 8;
   p.prog = nullptr;
   p.gn = p.nmb = p.nnb = p.nrounds = 0;

@@ -8,6 +8,7 @@
 // blocks that make W at the six permutations of (a,b,c) are summed in shared memory, then each thread adds the
 // disconnected part on the fly from t1/t2/<ij|ab>/f_ov (cctriples.py:131-137), applies the
 // 1/(1+delta) factor (210-213), forms the Lee-Rendell bracket (215-237) and reduces.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace b200cc {
@@ -73,7 +74,7 @@ __device__ __forceinline__ Disc make_disc(const TArgs& p, int i, int j, int k) {
 //  loads up front at one CTA per SM was slower, 2.04 TB/s.)
 constexpr int SA = 73, SB = 9, WTILE = 8 * SA;   // padded tile pitch (doubles)
 
-template <bool BLOCKED>
+template <bool BLOCKED, bool HOIST>
 __global__ void __launch_bounds__(512, 2) t_energy_kernel(const TArgs p, double* scratch) {
   __shared__ double Wsm[6][WTILE];
   __shared__ double red[16];
@@ -97,6 +98,17 @@ __global__ void __launch_bounds__(512, 2) t_energy_kernel(const TArgs p, double*
   constexpr int PI[6][3] = {{0, 1, 2}, {0, 2, 1}, {2, 0, 1}, {2, 1, 0}, {1, 2, 0}, {1, 0, 2}};
   // cube-blocked Q: a source block is one contiguous 4 KB run (thread t reads element t); plain Q: 64-byte runs
   const int nc8 = (nv + 7) >> 3;
+  // HOIST: everything per-(n,P) that does not depend on the thread (block origin, bounds) is CTA-uniform, the thread's
+  // offset inside a source block is the same for all 36 blocks, and the shared slot only depends on which of the six
+  // axis maps rho applies.  Loads stay PREDICATED (bitwise conditions, no short-circuit branches).
+  const i64 tpart = BLOCKED ? (i64)threadIdx.x : ((i64)u[0] * nv + u[1]) * nv + u[2];
+  int dsto[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    int l[3];
+    l[PERM[r][0]] = u[0]; l[PERM[r][1]] = u[1]; l[PERM[r][2]] = u[2];
+    dsto[r] = l[0] * SA + l[1] * SB + l[2];
+  }
 #pragma unroll
   for (int n = 0; n < 6; ++n) {
     const double* Qn = Q + (i64)n * v3;
@@ -104,17 +116,26 @@ __global__ void __launch_bounds__(512, 2) t_energy_kernel(const TArgs p, double*
     for (int P = 0; P < 6; ++P) {
       // Q_n coordinate k of W[P(a,b,c)] is cube axis rho_k = PERM[P][PI[n][k]]
       const int r0 = PERM[P][PI[n][0]], r1 = PERM[P][PI[n][1]], r2 = PERM[P][PI[n][2]];
-      const int x = T[r0] + u[0], y = T[r1] + u[1], z = T[r2] + u[2];
-      // keep this a single PREDICATED load: with a branch per load (e.g. an `interior ||` short-circuit) the compiler
-      // wraps each of the 36 loads in BSSY/BSYNC and they no longer overlap -- measured 1.9x slower (1.4 vs 2.7 TB/s)
-      const i64 off = BLOCKED ? (((((i64)(T[r0] >> 3) * nc8 + (T[r1] >> 3)) * nc8 + (T[r2] >> 3)) << 9) + threadIdx.x)
-                              : (((i64)x * nv + y) * nv + z);
       double val = 0.0;
-      if (x < nv && y < nv && z < nv) val = __ldg(Qn + off);
-      // cube-local coordinates of this element: l[rho_k] = u_k
-      int l[3];
-      l[r0] = u[0]; l[r1] = u[1]; l[r2] = u[2];
-      double* dst = &Wsm[P][l[0] * SA + l[1] * SB + l[2]];
+      double* dst;
+      if (HOIST) {
+        const i64 origin = BLOCKED ? ((((i64)(T[r0] >> 3) * nc8 + (T[r1] >> 3)) * nc8 + (T[r2] >> 3)) << 9)
+                                   : ((i64)T[r0] * nv + T[r1]) * nv + T[r2];
+        const bool ok = (u[0] < nv - T[r0]) & (u[1] < nv - T[r1]) & (u[2] < nv - T[r2]);
+        if (ok) val = __ldg(Qn + origin + tpart);
+        dst = &Wsm[P][dsto[r0 * 2 + (r1 > r2 ? 1 : 0)]];
+      } else {
+        const int x = T[r0] + u[0], y = T[r1] + u[1], z = T[r2] + u[2];
+        // keep this a single PREDICATED load: with a branch per load (e.g. an `interior ||` short-circuit) the compiler
+        // wraps each of the 36 loads in BSSY/BSYNC and they no longer overlap -- measured 1.9x slower (1.4 vs 2.7 TB/s)
+        const i64 off = BLOCKED ? (((((i64)(T[r0] >> 3) * nc8 + (T[r1] >> 3)) * nc8 + (T[r2] >> 3)) << 9) + threadIdx.x)
+                                : (((i64)x * nv + y) * nv + z);
+        if (x < nv && y < nv && z < nv) val = __ldg(Qn + off);
+        // cube-local coordinates of this element: l[rho_k] = u_k
+        int l[3];
+        l[r0] = u[0]; l[r1] = u[1]; l[r2] = u[2];
+        dst = &Wsm[P][l[0] * SA + l[1] * SB + l[2]];
+      }
       if (n == 0) *dst = val;
       else *dst += val;
     }
@@ -200,8 +221,12 @@ extern "C" int b200cc_t_energy_batch(int no, int nv, int ntrip, const int* ijk, 
   p.no = no; p.nv = nv; p.nt = (nv + TT - 1) / TT; p.blocked = q_blocked ? 1 : 0;
   p.ijk = ijk; p.Q = Q; p.t1 = t1; p.t2 = t2; p.oovv = oovv; p.fov = fov; p.eo = eo; p.ev = ev; p.ldf = ldf;
   const int ncube = sorted_cubes(nv);
-  if (p.blocked) t_energy_kernel<true><<<dim3(ncube, ntrip), 512, 0, st>>>(p, scratch);
-  else t_energy_kernel<false><<<dim3(ncube, ntrip), 512, 0, st>>>(p, scratch);
+  // hoisted index arithmetic measured 2.47 vs 2.03 TB/s on B200 (profiles/t_probe_r01_hoist.log); B200CC_T_HOIST=0 selects
+  // the per-element form
+  static const bool hoist = [] { const char* e = getenv("B200CC_T_HOIST"); return !(e && e[0] == '0'); }();
+  if (p.blocked) t_energy_kernel<true, false><<<dim3(ncube, ntrip), 512, 0, st>>>(p, scratch);
+  else if (hoist) t_energy_kernel<false, true><<<dim3(ncube, ntrip), 512, 0, st>>>(p, scratch);
+  else t_energy_kernel<false, false><<<dim3(ncube, ntrip), 512, 0, st>>>(p, scratch);
   if (check_launch("t_energy_kernel")) return 1;
   const i64 nparts = (i64)ncube * ntrip;
   if (nparts > 2147483647LL) { set_error("b200cc_t_energy_batch: too many partials"); return 1; }

@@ -181,8 +181,9 @@ def _mixed_eligible(M, N, K, A, B, transA, transB, batch, seg2, table, bcoords, 
 
 def dgemm(M, N, K, A, lda, transA, B, ldb, transB, Cmat, ldc, alpha=1.0, beta=0.0,
           batch=1, sA=0, sB=0, sC=0, seg2=None, table=None, table_align16=False, ksplit=None, config=0,
-          bcoords=None, nbatch=None, out_cube_nv=0):
+          bcoords=None, nbatch=None, out_cube_nv=0, mp_kchunk=None):
     """C[b] = alpha * (opA[b] opB[b]^T [+ second K segment]) + beta * C[b]; see b200cc_dgemm.
+    ``mp_kchunk``: FP32 accumulation run when the product is routed to the mixed-precision kernel.
 
     A, B, Cmat: tensor, (tensor, element offset) or raw address.  seg2 = (A2, lda2, B2, ldb2, K2, sA2, sB2).
     """
@@ -202,7 +203,7 @@ def dgemm(M, N, K, A, lda, transA, B, ldb, transB, Cmat, ldc, alpha=1.0, beta=0.
                   N * lpb2 if (nB2 > 1 and sB2) else 0)
         return gemm_tf32x3(M, N, K, Ah, Al, lpa, Bh, Bl, lpb, Cmat, ldc, alpha, beta, batch,
                            M * lpa if (nA1 > 1 and sA) else 0, N * lpb if (nB1 > 1 and sB) else 0, sC,
-                           seg2=s2, bcoords=bcoords, nbatch=nbatch)
+                           seg2=s2, bcoords=bcoords, nbatch=nbatch, kchunk=mp_kchunk)
     d = GemmDesc()
     d.M, d.N, d.transA, d.transB = int(M), int(N), int(bool(transA)), int(bool(transB))
     d.K1 = int(K)
