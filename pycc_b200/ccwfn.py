@@ -475,9 +475,18 @@ class CCwfn(object):
             # precision='MP': <ab|ef> lives as TF32 planes [(a,b), ldp]; tau is split per iteration (1.15 GB pass)
             hi, lo, ldp = self.H.to_mixed(drop=False)
             th, tl, lpt = K.split_tf32(tau, no * no, nv * nv, nv * nv)
-            off = (a_lo - r_lo) * nv * ldp
-            K.gemm_tf32x3(no * no, na * nv, nv * nv, th, tl, lpt, (hi, off), (lo, off), ldp, (r2, a_lo * nv), nv * nv,
-                          0.5, 1.0)
+            # One launch over all na*nv rows of <ab|ef> runs 26 % slower than the same work in row slices of a few
+            # thousand rows (192 vs 142 ms at o=40,v=300, profiles/mp_ladder_slices_r01.json): a launch then touches
+            # a few GB of address space instead of 65 GB.  Slices of ~44 n-tiles still give every SM ~4 tiles.
+            rows_total = na * nv
+            nsl = max(1, min(16, rows_total // 4096))
+            rows = -(-rows_total // nsl)
+            rows = -(-rows // 128) * 128
+            for r0 in range(0, rows_total, rows):
+                n = min(rows, rows_total - r0)
+                off = ((a_lo - r_lo) * nv + r0) * ldp
+                K.gemm_tf32x3(no * no, n, nv * nv, th, tl, lpt, (hi, off), (lo, off), ldp, (r2, a_lo * nv + r0), nv * nv,
+                              0.5, 1.0)
             return
         K.dgemm(no * no, na * nv, nv * nv, tau, nv * nv, 0, (vvvv, (a_lo - r_lo) * nv ** 3), nv * nv, 0,
                 (r2, a_lo * nv), nv * nv, 0.5, 1.0)

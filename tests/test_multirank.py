@@ -65,6 +65,53 @@ def test_two_ranks_match_reference(world):
     assert len(iters) == 1
 
 
+def _worker_mp(rank, world, port, golden_path, q):
+    """precision='MP' with two ranks: <ab|ef> planes a-sharded, mixed GEMMs on the rank-local slices."""
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import pycc_b200
+        from pycc_b200 import kernels as K
+        from pycc_b200.parallel import Comm
+        from tests import emu
+        from tests.conftest import load_golden
+        g, syn = load_golden(golden_path)
+        K.MIXED.min_flops, K.MIXED.min_dim, K.MIXED.min_tiles = 0.0, 1, 1
+        with emu.install():
+            comm = Comm()
+            cc = pycc_b200.ccwfn(syn, model="CCSD(T)", device="GPU", quiet=True, comm=comm, precision="MP")
+            a0, a1 = comm.a_range(syn.nv)
+            assert not cc.H.has("vvvv") and cc.H.vvvv_planes[0].shape[0] == (a1 - a0) * syn.nv
+            g0 = K.MIXED.stats["gemm"]
+            ecc = cc.solve_cc(1e-7, 1e-7)
+            ee = abs(float(ecc) - float(g["e_total_ccsd_t"]))
+            dt = float(np.abs(cc.t2.numpy() - g["conv_t2"]).max())
+            q.put((rank, ee, dt, len(cc.trace), K.MIXED.stats["gemm"] - g0, float(ecc)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_mixed_precision():
+    from tests.conftest import GOLDEN
+    path = [p for p in GOLDEN if "o4v10_s1" in p][0]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 500) + 7
+    procs = [ctx.Process(target=_worker_mp, args=(r, 2, port, path, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, ee, dt, n, ngemm, e in res:
+        assert ee < 1e-6 and dt < 1e-6, (rank, ee, dt)
+        assert ngemm > 0
+    assert res[0][3] == res[1][3] and res[0][5] == res[1][5]        # replicated state stays identical
+
+
 def test_split_is_a_partition():
     from pycc_b200.parallel import split
     for n in (0, 1, 7, 40, 300):
