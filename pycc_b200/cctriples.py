@@ -302,6 +302,7 @@ def t_vikings(ccwfn):
                 ct('abc,c->ab', u, Fov[k], out=X2[i, j], alpha=1.0, beta=1.0)
     s = K.permuted(t2, (0, 1, 2, 3), 4.0)
     K.strided_axpby(s, t2.permute(0, 1, 3, 2), -2.0, 1.0)
+    eng.close()
     d1 = K.multi_dot(t1.reshape(-1), [X1.reshape(-1)])
     d2 = K.multi_dot(s.reshape(-1), [X2.reshape(-1)])
     out = torch.empty(1, dtype=F64, device=dev)

@@ -154,6 +154,10 @@ class BlockHamiltonian:
             hi, lo, ldp = K.split_tf32(vvvv, na * nv, nv * nv, nv * nv)
             self.vvvv_planes = (hi[0], lo[0], ldp)
         if drop and "vvvv" in self._blocks:
+            # the released storage may be handed to a per-iteration tensor next: it must not look constant any more
+            K.unregister_tensor(self._blocks["vvvv"])
+            for key in [k for k in self._split_cache if k[0] == self._blocks["vvvv"].data_ptr()]:
+                del self._split_cache[key]
             del self._blocks["vvvv"]
         return self.vvvv_planes
 

@@ -97,6 +97,11 @@ def register_constant(t, cache):
     _CONST[t.untyped_storage().data_ptr()] = cache
 
 
+def unregister_tensor(t):
+    """Forget one constant (its storage is about to be released and may be reused by a non-constant tensor)."""
+    _CONST.pop(t.untyped_storage().data_ptr(), None)
+
+
 def unregister_constants(cache):
     for k in [k for k, v in _CONST.items() if v is cache]:
         del _CONST[k]

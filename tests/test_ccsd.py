@@ -215,6 +215,30 @@ def test_mixed_precision_energy(golden, dev, precision):
         K.MIXED.min_flops, K.MIXED.min_dim, K.MIXED.min_tiles = keep
 
 
+def test_mixed_precision_from_host_arrays_releases_fp64_ladder_block(dev):
+    """from_arrays + 'MP': <ab|ef> is converted to planes, the FP64 block is released AND forgotten as a constant
+    (its storage can be reused by per-iteration tensors, whose TF32 planes must never be cached)."""
+    from pycc_b200 import kernels as K
+    from pycc_b200.synthetic import make_synthetic
+    syn = make_synthetic(4, 8, seed=3)
+    ref = IntegralReference.from_arrays(syn.F, full_eri(syn), syn.no)
+    keep = (K.MIXED.min_flops, K.MIXED.min_dim, K.MIXED.min_tiles)
+    K.MIXED.min_flops, K.MIXED.min_dim, K.MIXED.min_tiles = 0.0, 1, 1
+    try:
+        n0 = len(K._CONST)
+        mp = pycc_b200.ccwfn(ref, model="CCSD", precision="MP", quiet=True)
+        assert not mp.H.has("vvvv") and mp.H.vvvv_planes is not None
+        live = {t.untyped_storage().data_ptr() for t in list(mp.H._blocks.values()) + list(mp.H._derived.values())}
+        assert set(K._CONST) - live == set() or len(K._CONST) - n0 <= len(live)
+        dp = pycc_b200.ccwfn(IntegralReference.from_arrays(syn.F, full_eri(syn), syn.no), model="CCSD", quiet=True)
+        e_mp, e_dp = mp.solve_cc(1e-8, 1e-7), dp.solve_cc(1e-10, 1e-10)
+        assert abs(float(e_mp) - float(e_dp)) < 1e-6
+        for (a, _), (b, _) in zip(mp.trace, dp.trace):          # every iteration, not only the converged value
+            assert abs(a - b) < 1e-6
+    finally:
+        K.MIXED.min_flops, K.MIXED.min_dim, K.MIXED.min_tiles = keep
+
+
 def test_mixed_precision_keeps_callers_hamiltonian(dev):
     """A BlockHamiltonian handed in by the caller keeps its FP64 <ab|ef> (it may serve a 'DP' wavefunction too)."""
     from pycc_b200.hamiltonian import BlockHamiltonian
