@@ -10,12 +10,14 @@ raises if it (or a CUDA device) is missing -- there is no CPU fallback.
 from .exceptions import PyCCError, PyCCWarning, InvalidKeywordError
 from .ccwfn import CCwfn, ccwfn
 from . import cctriples
+from .cchbar import cchbar
+from .cclambda import cclambda
 from .utils import helper_diis
 from .device import DeviceManager, ContractionBackend
 from .wavefunction import IntegralReference
 from .hamiltonian import BlockHamiltonian
 from .synthetic import make_synthetic
 
-__all__ = ["CCwfn", "ccwfn", "cctriples", "helper_diis", "DeviceManager", "ContractionBackend",
+__all__ = ["CCwfn", "ccwfn", "cctriples", "cchbar", "cclambda", "helper_diis", "DeviceManager", "ContractionBackend",
            "IntegralReference", "BlockHamiltonian", "make_synthetic", "PyCCError", "PyCCWarning",
            "InvalidKeywordError"]

@@ -1,0 +1,195 @@
+"""Similarity-transformed Hamiltonian (HBAR) for closed-shell CCSD / CCD on B200 -- drop-in for ``pycc.cchbar``
+(reference: pycc/cchbar.py:24-110 and the spatial-orbital ``build_*`` methods 128-823).  SURVEY 8(f) "next" #1.
+
+Same eleven blocks with the reference's names and index orders (``Hov, Hvv, Hoo, Hoooo, Hvvvv, Hvovv, Hooov,
+Hovvo, Hovov, Hvvvo, Hovoo``), same ``build_*`` signatures.  Underneath, each block is a TERM TABLE
+``(alpha, subscripts, operand, operand)`` accumulated IN PLACE into one output tensor by the contraction backend
+(``Contractor``: TTGT planning on strides -> ``b200cc_dgemm`` / ``b200cc_permute``), so no ``X = X + contract(...)``
+temporaries exist, and every <pq|rs> / L_pqrs operand is a permuted VIEW of one of the six device-resident integral
+blocks (``BlockHamiltonian.ERI`` / ``.L``), never an n^4 array.  The reference's ``tmp + tmp.swapaxes(0,1).swapaxes(2,3)``
+pairs are written as the two contractions they are.
+
+This is the correctness-first slice of the row (parity against the reference's golden vectors and the numpy oracle);
+the products go through the generic planner, not yet through fused layouts as the CCSD residual does.
+CC2 / CC3 / spin-orbital branches of the reference are outside the accelerated path.
+"""
+from __future__ import annotations
+
+import time
+
+import torch
+
+from . import kernels as K
+from .utils import timing
+
+F64 = torch.float64
+
+
+def _view(H, name):
+    """'E:vovv' -> <am|ef> view, 'L:vovv' -> 2<am|ef> - <am|fe> (materialised once per Hamiltonian)."""
+    kind, pat = name.split(":")
+    key = tuple(H.o if c == "o" else H.v for c in pat)
+    return (H.ERI if kind == "E" else H.L)[key]
+
+
+# block -> (initial value, terms for every model, extra terms when singles are present (CCSD))
+# operands: t1, t2, tau (= t2 + t1 t1; t2 itself for CCD), Fov, previously built blocks, 'E:pqrs' / 'L:pqrs' integrals
+_TABLE = {
+    # H_me = f_me + t_nf L_mnef                                                  cchbar.py:147-153
+    "Hov": ("F:ov", [], [(1.0, "nf,mnef->me", "t1", "L:oovv")]),
+    # H_ae = f_ae - f_me t_ma + t_mf L_amef - tau_mnfa L_mnfe                      cchbar.py:201-210
+    "Hvv": ("F:vv", [(-1.0, "mnfa,mnfe->ae", "tau", "L:oovv")],
+            [(-1.0, "me,ma->ae", "Fov", "t1"), (1.0, "mf,amef->ae", "t1", "L:vovv")]),
+    # H_mi = f_mi + t_ie f_me + t_ne L_mnie + tau_inef L_mnef                      cchbar.py:264-273
+    "Hoo": ("F:oo", [(1.0, "inef,mnef->mi", "tau", "L:oovv")],
+            [(1.0, "ie,me->mi", "t1", "Fov"), (1.0, "ne,mnie->mi", "t1", "L:ooov")]),
+    # H_mnij = <mn|ij> + t_je <mn|ie> + t_ie <nm|je> + tau_ijef <mn|ef>            cchbar.py:330-339
+    "Hoooo": ("E:oooo", [(1.0, "ijef,mnef->mnij", "tau", "E:oovv")],
+              [(1.0, "je,mnie->mnij", "t1", "E:ooov"), (1.0, "ie,nmje->mnij", "t1", "E:ooov")]),
+    # H_abef = <ab|ef> - t_mb <am|ef> - t_ma <bm|fe> + tau_mnab <mn|ef>            cchbar.py:394-403
+    "Hvvvv": ("E:vvvv", [(1.0, "mnab,mnef->abef", "tau", "E:oovv")],
+              [(-1.0, "mb,amef->abef", "t1", "E:vovv"), (-1.0, "ma,bmfe->abef", "t1", "E:vovv")]),
+    # H_amef = <am|ef> - t_na <nm|ef>                                            cchbar.py:450-458
+    "Hvovv": ("E:vovv", [], [(-1.0, "na,nmef->amef", "t1", "E:oovv")]),
+    # H_mnie = <mn|ie> + t_if <nm|ef>                                            cchbar.py:500-508
+    "Hooov": ("E:ooov", [], [(1.0, "if,nmef->mnie", "t1", "E:oovv")]),
+    # H_mbej = <mb|ej> + t_jf <mb|ef> - t_nb <mn|ej> - tau_jnfb <mn|ef> + t2_njfb L_mnef     cchbar.py:554-569
+    "Hovvo": ("E:ovvo", [(-1.0, "jnfb,mnef->mbej", "tau", "E:oovv"), (1.0, "njfb,mnef->mbej", "t2", "L:oovv")],
+              [(1.0, "jf,mbef->mbej", "t1", "E:ovvv"), (-1.0, "nb,mnej->mbej", "t1", "E:oovo")]),
+    # H_mbje = <mb|je> + t_jf <bm|ef> - t_nb <mn|je> - tau_jnfb <nm|ef>            cchbar.py:617-630
+    "Hovov": ("E:ovov", [(-1.0, "jnfb,nmef->mbje", "tau", "E:oovv")],
+              [(1.0, "jf,bmef->mbje", "t1", "E:vovv"), (-1.0, "nb,mnje->mbje", "t1", "E:ooov")]),
+    # H_abei                                                                     cchbar.py:662-698
+    "Hvvvo": ("E:vvvo", [(-1.0, "me,miab->abei", "Hov", "t2"), (1.0, "mnab,mnei->abei", "tau", "E:oovo"),
+                         (-1.0, "imfa,bmfe->abei", "t2", "E:vovv"), (-1.0, "imfb,amef->abei", "t2", "E:vovv"),
+                         (1.0, "mifb,amef->abei", "t2", "L:vovv")],
+              [(1.0, "if,abef->abei", "t1", "Hvvvv"), (-1.0, "mb,amei->abei", "t1", "X:vovo"),
+               (-1.0, "ma,bmie->abei", "t1", "X:voov")]),
+    # H_mbij                                                                     cchbar.py:785-823
+    "Hovoo": ("E:ovoo", [(1.0, "me,ijeb->mbij", "Hov", "t2"), (1.0, "ijef,mbef->mbij", "tau", "E:ovvv"),
+                         (-1.0, "ineb,nmje->mbij", "t2", "E:ooov"), (-1.0, "jneb,mnie->mbij", "t2", "E:ooov"),
+                         (1.0, "njeb,mnie->mbij", "t2", "L:ooov")],
+              [(-1.0, "nb,mnij->mbij", "t1", "Hoooo"), (1.0, "je,mbie->mbij", "t1", "X:ovov"),
+               (1.0, "ie,bmje->mbij", "t1", "X:voov2")]),
+}
+# t2-dressed integrals used only inside Hvvvo / Hovoo (the reference's `tmp`, cchbar.py:689-696, 812-820)
+_DRESSED = {
+    "X:vovo": ("E:vovo", [(-1.0, "infa,mnfe->amei", "t2", "E:oovv")]),
+    "X:voov": ("E:voov", [(-1.0, "infb,mnef->bmie", "t2", "E:oovv"), (1.0, "nifb,mnef->bmie", "t2", "L:oovv")]),
+    "X:ovov": ("E:ovov", [(-1.0, "infb,mnfe->mbie", "t2", "E:oovv")]),
+    "X:voov2": ("E:voov", [(-1.0, "jnfb,mnef->bmje", "t2", "E:oovv"), (1.0, "njfb,mnef->bmje", "t2", "L:oovv")]),
+}
+ORDER = ("Hov", "Hvv", "Hoo", "Hoooo", "Hvvvv", "Hvovv", "Hooov", "Hovvo", "Hovov", "Hvvvo", "Hovoo")
+
+
+class cchbar(object):
+    """See module docstring.  ``cchbar(ccwfn)`` builds all blocks from the wavefunction's current amplitudes."""
+
+    def __init__(self, ccwfn):
+        t0 = time.time()
+        if ccwfn.model not in ("CCSD", "CCD", "CCSD(T)"):
+            raise NotImplementedError("HBAR is accelerated for the closed-shell CCD / CCSD amplitudes only")
+        self.ccwfn = ccwfn
+        self.contract = ccwfn.contract
+        self.o, self.v = ccwfn.o, ccwfn.v
+        self.no, self.nv = ccwfn.no, ccwfn.nv
+        blocks = self.build_all(ccwfn.H.F, ccwfn.t1, ccwfn.t2)
+        for k in ORDER:
+            setattr(self, k, blocks[k])
+        if not getattr(ccwfn, "quiet", False):
+            print(timing("HBAR", time.time() - t0))
+
+    # ---- evaluation of the tables -----------------------------------------------------------------------
+    def _env(self, F, t1, t2):
+        w = self.ccwfn
+        F = w._check_F(F)
+        ccd = w.model == "CCD"
+        t1, t2 = t1.contiguous(), t2.contiguous()
+        env = {"t1": t1, "t2": t2, "F": F, "Fov": F[self.o, self.v]}
+        env["tau"] = t2 if ccd else K.build_tau(t1, t2, 1.0, 1.0)
+        return env
+
+    def _operand(self, env, name):
+        if name in env:
+            return env[name]
+        if name.startswith("X:"):
+            init, terms = _DRESSED[name]
+            x = K.permuted(_view(self.ccwfn.H, init), (0, 1, 2, 3))
+            for alpha, sub, a, b in terms:
+                self.ccwfn._ct(sub, self._operand(env, a), self._operand(env, b), out=x, alpha=alpha, beta=1.0)
+            return x                       # not cached: used once
+        return _view(self.ccwfn.H, name)
+
+    def _build(self, key, env):
+        init, terms, singles = _TABLE[key]
+        w = self.ccwfn
+        if init.startswith("F:"):
+            sl = {"o": self.o, "v": self.v}
+            out = K.permuted(env["F"][sl[init[2]], sl[init[3]]], (0, 1))
+        else:
+            src = _view(w.H, init)
+            out = K.permuted(src, tuple(range(src.dim())))
+        todo = list(terms) + ([] if w.model == "CCD" else list(singles))
+        with K.mixed_mode(getattr(w, "mixed", False)):
+            for alpha, sub, a, b in todo:
+                w._ct(sub, self._operand(env, a), self._operand(env, b), out=out, alpha=alpha, beta=1.0)
+        env[key] = out
+        return out
+
+    def build_all(self, F, t1, t2):
+        """Every block, in dependency order (Hvvvo needs Hov and Hvvvv, Hovoo needs Hov and Hoooo)."""
+        env = self._env(F, t1, t2)
+        return {k: self._build(k, env) for k in ORDER}
+
+    # ---- the reference's builders (signatures of cchbar.py:128-823; integrals must be the wavefunction's own) ----
+    def _one(self, key, F, t1, t2, **have):
+        env = self._env(F, t1, t2)
+        env.update({k: x for k, x in have.items() if x is not None})
+        for dep in ("Hov", "Hoooo", "Hvvvv"):
+            if dep not in env and any(dep in (a, b) for _, _, a, b in _TABLE[key][1] + _TABLE[key][2]):
+                self._build(dep, env)
+        return self._build(key, env)
+
+    def build_Hov(self, o, v, F, L, t1):
+        self.ccwfn._own(L=L)
+        return self._one("Hov", F, t1, self.ccwfn.t2)
+
+    def build_Hvv(self, o, v, F, L, t1, t2):
+        self.ccwfn._own(L=L)
+        return self._one("Hvv", F, t1, t2)
+
+    def build_Hoo(self, o, v, F, L, t1, t2):
+        self.ccwfn._own(L=L)
+        return self._one("Hoo", F, t1, t2)
+
+    def build_Hoooo(self, o, v, ERI, t1, t2):
+        self.ccwfn._own(ERI)
+        return self._one("Hoooo", self.ccwfn.H.F, t1, t2)
+
+    def build_Hvvvv(self, o, v, ERI, t1, t2):
+        self.ccwfn._own(ERI)
+        return self._one("Hvvvv", self.ccwfn.H.F, t1, t2)
+
+    def build_Hvovv(self, o, v, ERI, t1):
+        self.ccwfn._own(ERI)
+        return self._one("Hvovv", self.ccwfn.H.F, t1, self.ccwfn.t2)
+
+    def build_Hooov(self, o, v, ERI, t1):
+        self.ccwfn._own(ERI)
+        return self._one("Hooov", self.ccwfn.H.F, t1, self.ccwfn.t2)
+
+    def build_Hovvo(self, o, v, ERI, L, t1, t2):
+        self.ccwfn._own(ERI, L)
+        return self._one("Hovvo", self.ccwfn.H.F, t1, t2)
+
+    def build_Hovov(self, o, v, ERI, t1, t2):
+        self.ccwfn._own(ERI)
+        return self._one("Hovov", self.ccwfn.H.F, t1, t2)
+
+    def build_Hvvvo(self, o, v, ERI, L, Hov, Hvvvv, t1, t2):
+        self.ccwfn._own(ERI, L)
+        return self._one("Hvvvo", self.ccwfn.H.F, t1, t2, Hov=Hov, Hvvvv=Hvvvv)
+
+    def build_Hovoo(self, o, v, ERI, L, Hov, Hoooo, t1, t2):
+        self.ccwfn._own(ERI, L)
+        return self._one("Hovoo", self.ccwfn.H.F, t1, t2, Hov=Hov, Hoooo=Hoooo)

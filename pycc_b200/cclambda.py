@@ -1,0 +1,151 @@
+"""Closed-shell CCSD / CCD Lambda-amplitude solver on B200 -- drop-in for ``pycc.cclambda`` on the spatial-orbital
+path (reference: pycc/cclambda.py:27-66 ctor/guess, 69-200 solve_lambda, 202-256 residuals, 258-306 Goo/Gvv,
+308-370 r_L1, 408-497 r_L2, 547-570 pseudoenergy).  SURVEY 8(f) "next" #1.
+
+Same surface: ``cclambda(ccwfn, hbar).solve_lambda(e_conv, r_conv, maxiter, max_diis, start_diis)``, ``residuals``,
+``build_Goo``, ``build_Gvv``, ``r_L1``, ``r_L2``, ``pseudoenergy``, attributes ``l1``, ``l2``.  The loop skeleton is
+the one of ``solve_cc`` and reuses its kernels: residual terms accumulate in place through the contraction backend
+(term tables, see cchbar.py), the r2 symmetrisation + Jacobi update + sum((r/D)^2) is the ONE fused pass
+``b200cc_update_amps`` (cclambda.py:496 + 163-168), the pseudo-energy is a ``b200cc_multi_dot`` and DIIS is the shared
+``helper_diis``.  One device->host sync per iteration.
+"""
+from __future__ import annotations
+
+import time
+
+import torch
+
+from . import kernels as K
+from .utils import helper_diis, title, iteration, converged
+
+F64 = torch.float64
+
+# r_l1_ia = 2 H_ia + l1_ie H_ea - l1_ma H_im + l2_imef H_efam - l2_mnae H_iemn + l1_me (2 H_ieam - H_iema)
+#           - 2 G_ef H_eifa + G_ef H_eiaf - 2 G_mn H_mina + G_mn H_imna                      cclambda.py:344-370
+_R1 = [(1.0, "ie,ea->ia", "l1", "Hvv"), (-1.0, "ma,im->ia", "l1", "Hoo"),
+       (1.0, "imef,efam->ia", "l2", "Hvvvo"), (-1.0, "mnae,iemn->ia", "l2", "Hovoo"),
+       (1.0, "me,ieam->ia", "l1", "W"),
+       (-2.0, "ef,eifa->ia", "Gvv", "Hvovv"), (1.0, "ef,eiaf->ia", "Gvv", "Hvovv"),
+       (-2.0, "mn,mina->ia", "Goo", "Hooov"), (1.0, "mn,imna->ia", "Goo", "Hooov")]
+# unsymmetrised half of r_l2 (cclambda.py:447-495); the l1 terms only with singles
+_R2_SINGLES = [(2.0, "ia,jb->ijab", "l1", "Hov"), (-1.0, "ja,ib->ijab", "l1", "Hov"),
+               (2.0, "ie,ejab->ijab", "l1", "Hvovv"), (-1.0, "ie,ejba->ijab", "l1", "Hvovv"),
+               (-2.0, "mb,jima->ijab", "l1", "Hooov"), (1.0, "mb,ijma->ijab", "l1", "Hooov")]
+_R2 = [(1.0, "ijeb,ea->ijab", "l2", "Hvv"), (-1.0, "mjab,im->ijab", "l2", "Hoo"),
+       (0.5, "mnab,ijmn->ijab", "l2", "Hoooo"), (0.5, "ijef,efab->ijab", "l2", "Hvvvv"),
+       (1.0, "mjeb,ieam->ijab", "l2", "W"), (-1.0, "mibe,jema->ijab", "l2", "Hovov"),
+       (-1.0, "mieb,jeam->ijab", "l2", "Hovvo"),
+       (1.0, "ae,ijeb->ijab", "Gvv", "Loovv"), (-1.0, "mi,mjab->ijab", "Goo", "Loovv")]
+
+
+class cclambda(object):
+    def __init__(self, ccwfn, hbar):
+        if ccwfn.model not in ("CCSD", "CCD"):
+            raise NotImplementedError("the Lambda equations are accelerated for closed-shell CCD / CCSD; the (T) "
+                                      "sources S1/S2 and CC2/CC3 stay with the reference implementation")
+        self.ccwfn, self.hbar = ccwfn, hbar
+        self.contract = ccwfn.contract
+        t1, t2 = ccwfn.t1, ccwfn.t2
+        # l1 = 2 t1, l2 = 2 (2 t2 - t2^T)                                              cclambda.py:65-66
+        self.l1 = torch.empty_like(t1)
+        K.strided_axpby(self.l1, t1, 2.0, 0.0)
+        self.l2 = torch.empty_like(t2)
+        K.strided_axpby(self.l2, t2, 4.0, 0.0)
+        K.strided_axpby(self.l2, t2.permute(0, 1, 3, 2), -2.0, 1.0)
+
+    # ---- building blocks with the reference's signatures ----------------------------------------------------
+    def build_Goo(self, t2, l2):
+        return self.ccwfn._ct("mjab,ijab->mi", t2.contiguous(), l2.contiguous())            # cclambda.py:281
+
+    def build_Gvv(self, t2, l2):
+        return self.ccwfn._ct("ijeb,ijab->ae", t2.contiguous(), l2.contiguous(), alpha=-1.0)  # cclambda.py:306
+
+    @staticmethod
+    def _w(Hovvo, Hovov):
+        """2 H_ieam - H_iema (used by r_L1 and r_L2; constant during a solve)"""
+        W = K.permuted(Hovvo, (0, 1, 2, 3), 2.0)
+        return K.strided_axpby(W, Hovov.permute(0, 1, 3, 2), -1.0, 1.0)
+
+    def _accumulate(self, out, terms, env):
+        ct = self.ccwfn._ct
+        with K.mixed_mode(getattr(self.ccwfn, "mixed", False)):
+            for alpha, sub, a, b in terms:
+                ct(sub, env[a], env[b], out=out, alpha=alpha, beta=1.0)
+        return out
+
+    def r_L1(self, o, v, l1, l2, Hov, Hvv, Hoo, Hovvo, Hovov, Hvvvo, Hovoo, Hvovv, Hooov, Gvv, Goo, s1=None, W=None):
+        if s1 is not None:
+            raise NotImplementedError("(T) lambda sources are outside the accelerated path")
+        if self.ccwfn.model == "CCD":
+            return torch.zeros_like(l1)
+        env = dict(l1=l1.contiguous(), l2=l2.contiguous(), Hvv=Hvv, Hoo=Hoo, Hvvvo=Hvvvo, Hovoo=Hovoo, Hvovv=Hvovv,
+                   Hooov=Hooov, Gvv=Gvv, Goo=Goo, W=W if W is not None else self._w(Hovvo, Hovov))
+        return self._accumulate(K.permuted(Hov, (0, 1), 2.0), _R1, env)
+
+    def _r_L2_half(self, l1, l2, Hov, Hvv, Hoo, Hoooo, Hvvvv, Hovvo, Hovov, Hvovv, Hooov, Gvv, Goo, W):
+        Loovv = self.ccwfn.H.derived("Loovv")
+        env = dict(l1=l1.contiguous(), l2=l2.contiguous(), Hov=Hov, Hvv=Hvv, Hoo=Hoo, Hoooo=Hoooo, Hvvvv=Hvvvv,
+                   Hovvo=Hovvo, Hovov=Hovov, Hvovv=Hvovv, Hooov=Hooov, Gvv=Gvv, Goo=Goo, W=W, Loovv=Loovv)
+        terms = _R2 if self.ccwfn.model == "CCD" else _R2_SINGLES + _R2
+        return self._accumulate(K.permuted(Loovv, (0, 1, 2, 3)), terms, env)
+
+    def r_L2(self, o, v, l1, l2, L, Hov, Hvv, Hoo, Hoooo, Hvvvv, Hovvo, Hovov, Hvvvo, Hovoo, Hvovv, Hooov, Gvv, Goo,
+             s2=None):
+        if s2 is not None:
+            raise NotImplementedError("(T) lambda sources are outside the accelerated path")
+        self.ccwfn._own(L=L)
+        half = self._r_L2_half(l1, l2, Hov, Hvv, Hoo, Hoooo, Hvvvv, Hovvo, Hovov, Hvovv, Hooov, Gvv, Goo,
+                               self._w(Hovvo, Hovov))
+        return K.symmetrize_r2(half)                                                       # cclambda.py:496
+
+    def pseudoenergy(self, o, v, ERI, l2):
+        """1/2 <ij|ab> l2_ijab as a 0-d device tensor                                       cclambda.py:570"""
+        self.ccwfn._own(ERI)
+        oovv = self.ccwfn.H.block("oovv")
+        return 0.5 * K.multi_dot(oovv.reshape(-1), [l2.contiguous().reshape(-1)])[0]
+
+    def residuals(self, F, t1, t2, l1, l2):
+        """(r1, r2) with HBAR rebuilt from (F, t1, t2)                                      cclambda.py:202-256"""
+        hb = self.hbar.build_all(F, t1, t2)
+        Goo, Gvv = self.build_Goo(t2, l2), self.build_Gvv(t2, l2)
+        W = self._w(hb["Hovvo"], hb["Hovov"])
+        r1 = self.r_L1(self.ccwfn.o, self.ccwfn.v, l1, l2, hb["Hov"], hb["Hvv"], hb["Hoo"], hb["Hovvo"], hb["Hovov"],
+                       hb["Hvvvo"], hb["Hovoo"], hb["Hvovv"], hb["Hooov"], Gvv, Goo, W=W)
+        half = self._r_L2_half(l1, l2, hb["Hov"], hb["Hvv"], hb["Hoo"], hb["Hoooo"], hb["Hvvvv"], hb["Hovvo"],
+                               hb["Hovov"], hb["Hvovv"], hb["Hooov"], Gvv, Goo, W)
+        return r1, K.symmetrize_r2(half)
+
+    # ---- solve_lambda (cclambda.py:69-200) -------------------------------------------------------------------
+    def solve_lambda(self, e_conv=1e-7, r_conv=1e-7, maxiter=100, max_diis=8, start_diis=1):
+        t0 = time.time()
+        w, hb = self.ccwfn, self.hbar
+        o, v = w.o, w.v
+        say = (lambda *a: None) if getattr(w, "quiet", False) else print
+        lecc = float(self.pseudoenergy(o, v, w.H.ERI, self.l2))
+        name = "Lambda-amplitudes (%s)" % w.model
+        say(title(name))
+        say(iteration(0, energy=lecc, de=-lecc, e_label="LCC PseudoE"))
+        diis = helper_diis(self.l1, self.l2, max_diis, w.precision)
+        W = self._w(hb.Hovvo, hb.Hovov)
+        self.trace = []
+        for niter in range(1, maxiter + 1):
+            last = lecc
+            Goo, Gvv = self.build_Goo(w.t2, self.l2), self.build_Gvv(w.t2, self.l2)
+            r1 = self.r_L1(o, v, self.l1, self.l2, hb.Hov, hb.Hvv, hb.Hoo, hb.Hovvo, hb.Hovov, hb.Hvvvo, hb.Hovoo,
+                           hb.Hvovv, hb.Hooov, Gvv, Goo, W=W)
+            half = self._r_L2_half(self.l1, self.l2, hb.Hov, hb.Hvv, hb.Hoo, hb.Hoooo, hb.Hvvvv, hb.Hovvo, hb.Hovov,
+                                   hb.Hvovv, hb.Hooov, Gvv, Goo, W)
+            # r2 = half + half^T, l += r/D, sum (r/D)^2 in one pass; then the pseudo-energy
+            ssq = K.update_amps(r1, half, w.eps_o, w.eps_v, self.l1, self.l2, symmetrize=True, write_r2=False)
+            e_dev = self.pseudoenergy(o, v, w.H.ERI, self.l2)
+            ssq_h, lecc = torch.stack((ssq[0], e_dev)).tolist()
+            rms = ssq_h ** 0.5
+            self.trace.append((lecc, rms))
+            say(iteration(niter, energy=lecc, de=lecc - last, rms=rms, e_label="LCC PseudoE"))
+            if abs(lecc - last) < e_conv and abs(rms) < r_conv:
+                say(converged(name, time.time() - t0))
+                return torch.tensor(lecc, dtype=F64, device=self.l2.device)
+            diis.add_error_vector(self.l1, self.l2)
+            if niter >= start_diis:
+                self.l1, self.l2 = diis.extrapolate(self.l1, self.l2)
+        return None          # the reference falls off the loop (cclambda.py:69-200)
