@@ -189,6 +189,39 @@ int b200cc_t3_assemble(int no, int nv, int i, int j, int k, const double* Q, int
                        const double* fov, b200cc_i64 ldf, const double* eo, const double* ev,
                        int with_denom, double* w3_out, double* v3_out, void* stream);
 
+/* ---- (T) densities and Lambda sources (cctriples.py:1063-1157, t3_density) --------------
+ * Step 1: connected t3 WITH denominators for a batch of triples, from the six GEMM outputs per triple:
+ *   m3_out[t][a,b,c] = (Q1[a,b,c]+Q2[a,c,b]+Q3[c,a,b]+Q4[c,b,a]+Q5[b,c,a]+Q6[b,a,c]) / D_ijkabc   (= t3c_ijk,
+ *   cctriples.py:50-70).  Q: [ntrip][6][nv^3] (plain layout), ijk: device int32 [ntrip][3].                  */
+int b200cc_t3_connected_batch(int no, int nv, int ntrip, const int* ijk, const double* Q, const double* eo,
+                              const double* ev, double* m3_out, void* stream);
+
+/* Step 2: for fixed (i,j) and k = k0 .. k0+nk-1, everything of the loop body of t3_density (cctriples.py:1121-1148)
+ * that is not a GEMM.  With M3 from step 1, N3 = t3d_ijk/D formed on the fly, X3 = sym(M3), Y3 = sym(N3):
+ *   GEMM operands (written, not accumulated):
+ *     W2 = 2 X3 + Y3  ->  W2ab[(a,b)][kk][c]  and  W2n[a][kk][(b,c)]        (kk = k - k0)
+ *     P  = 2 M3 - M3[a,c,b] - M3[c,b,a]  ->  Pab, Pn  (same two layouts)
+ *   accumulated in place:
+ *     Gij[a,b] += 4 t1[k,c] Z3[a,b,c]            (Goovv[i,j], line 1141)
+ *     Xij[a,b] += (M3 - M3[c,b,a]) f[k,c]        (X2[i,j], line 1128)
+ *     dvv[a]   += 1/2 M3 (X3 + Y3)               (line 1133; doo[i] = - sum_a of the same, line 1134)
+ *     Dov[a]   += (M3 - M3[c,b,a]) (4 t2[j,k,b,c] - 2 t2[j,k,c,b])          (Dov[i], line 1137)
+ *     S1[a]    += 2 (M3 - M3[b,a,c]) (2<jk|bc> - <jk|cb>)                   (S1[i], line 1146)
+ * scratch: >= b200cc_t3_density_scratch(nv) doubles.  Deterministic (no atomics).                            */
+typedef struct {
+  int no, nv, i, j, k0, nk;
+  const double* M3;                    /* [nk][nv^3] */
+  const double *t1, *t2, *oovv, *fov;  /* fov: (no,nv) view, leading dimension ldf */
+  b200cc_i64 ldf;
+  const double *eo, *ev;
+  double *W2ab, *W2n, *Pab, *Pn;       /* nk*nv^3 each */
+  double *Gij, *Xij;                   /* (nv,nv) */
+  double *dvv, *Dov, *S1;              /* nv each */
+  double* scratch;
+} b200cc_t3d_desc;
+b200cc_i64 b200cc_t3_density_scratch(int nv);
+int b200cc_t3_density_forms(const b200cc_t3d_desc* d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,20 @@ class Gemm3Desc(C.Structure):
     ]
 
 
+class T3dDesc(C.Structure):
+    """Mirror of ``b200cc_t3d_desc`` (include/b200cc.h)."""
+    _fields_ = [
+        ("no", C.c_int), ("nv", C.c_int), ("i", C.c_int), ("j", C.c_int), ("k0", C.c_int), ("nk", C.c_int),
+        ("M3", dptr), ("t1", dptr), ("t2", dptr), ("oovv", dptr), ("fov", dptr),
+        ("ldf", i64),
+        ("eo", dptr), ("ev", dptr),
+        ("W2ab", dptr), ("W2n", dptr), ("Pab", dptr), ("Pn", dptr),
+        ("Gij", dptr), ("Xij", dptr),
+        ("dvv", dptr), ("Dov", dptr), ("S1", dptr),
+        ("scratch", dptr),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/b200cc.h declares
 SIGNATURES = {
     "b200cc_version": (C.c_int, []),
@@ -97,6 +111,9 @@ SIGNATURES = {
                                         dptr, dptr, dptr, C.c_int, dptr, C.c_void_p]),
     "b200cc_t3_assemble": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, dptr, C.c_int, dptr, dptr, dptr,
                                      dptr, i64, dptr, dptr, C.c_int, dptr, dptr, C.c_void_p]),
+    "b200cc_t3_connected_batch": (C.c_int, [C.c_int, C.c_int, C.c_int, dptr, dptr, dptr, dptr, dptr, C.c_void_p]),
+    "b200cc_t3_density_scratch": (i64, [C.c_int]),
+    "b200cc_t3_density_forms": (C.c_int, [C.POINTER(T3dDesc), C.c_void_p]),
 }
 
 _LIB = None

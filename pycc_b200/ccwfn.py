@@ -56,8 +56,8 @@ class CCwfn(object):
         self.e_conv, self.r_conv, self.maxiter = 1e-7, 1e-7, 100
         self.need_singles = ['CCSD', 'CCSD(T)', 'CC2', 'CC3']
         self.make_t3_density = kwargs.pop('make_t3_density', False)
-        if self.make_t3_density:
-            raise NotImplementedError("(T) densities are outside the accelerated path (SURVEY 8f, next #2)")
+        if self.make_t3_density not in (True, False):
+            raise InvalidKeywordError('make_t3_density', self.make_t3_density, [True, False])
         local = kwargs.pop('local', None)
         if local is not None:
             raise NotImplementedError("local correlation is CPU-only in the reference and not accelerated")
@@ -156,7 +156,8 @@ class CCwfn(object):
                 if self.model == 'CCSD(T)':
                     say("E(CCSD) = %20.15f" % ecc)
                     from .cctriples import t_tjl
-                    et = t_tjl(self)
+                    # ccwfn.py:300-308: the density-producing (T) when make_t3_density is set, else Lee-Rendell
+                    et = self.t3_density() if self.make_t3_density is True else t_tjl(self)
                     say("E(T)    = %20.15f" % float(et))
                     ecc_t = ecc_t + et
                 else:
@@ -167,6 +168,17 @@ class CCwfn(object):
             self.diis_step(diis, niter >= start_diis)
         # not converged: the reference falls off the loop and returns None (ccwfn.py:268-319)
         return None
+
+    def t3_density(self):
+        """(T) contributions to the Lambda residuals and the one-/two-particle densities (ccwfn.py:1819-1829):
+        delegates to cctriples.t3_density, caches the returned pieces on the wavefunction (Doo, Dvv, Dov, Goovv,
+        Gooov, Gvvvo, S1, S2) and returns the (T) energy."""
+        from . import cctriples
+        et, dens = cctriples.t3_density(self.o, self.v, self.no, self.nv, self.t1, self.t2, self.H.F, self.H.ERI,
+                                        self.H.L, self.contract, comm=self.comm)
+        for name, value in dens.items():
+            setattr(self, name, value)
+        return et
 
     def iterate(self, F=None):
         """One Jacobi step of solve_cc (ccwfn.py:272-286): residuals, then ONE fused pass doing

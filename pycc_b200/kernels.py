@@ -12,7 +12,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import GemmDesc, Gemm3Desc, B200ccError, i64
+from ._lib import GemmDesc, Gemm3Desc, T3dDesc, B200ccError, i64
 
 NSM = 148                   # B200
 # tile-config override for experiments (0 = library heuristic); see b200cc_gemm_desc.config
@@ -404,6 +404,41 @@ def t3_assemble(no, nv, i, j, k, Q, t1, t2, oovv, fov, eo, ev, with_denom, block
                                              int(fov.stride(0)), _lib.ptr(eo), _lib.ptr(ev), int(bool(with_denom)),
                                              _lib.ptr(w3), _lib.ptr(d3), _lib.stream()), "b200cc_t3_assemble")
     return w3, d3
+
+
+def t3_connected_batch(no, nv, ijk, Q, eo, ev, out):
+    """out[t] = connected t3 of triple t WITH denominators, from the six GEMM outputs Q[t] (b200cc_t3_connected_batch)."""
+    ntrip = ijk.shape[0]
+    if out.numel() < ntrip * nv ** 3:
+        raise B200ccError("t3_connected_batch: output too small")
+    _lib.check(_lib.get().b200cc_t3_connected_batch(int(no), int(nv), int(ntrip), _lib.ptr(ijk), _lib.ptr(Q),
+                                                    _lib.ptr(eo), _lib.ptr(ev), _lib.ptr(_c(out, "out")),
+                                                    _lib.stream()), "b200cc_t3_connected_batch")
+    return out
+
+
+def t3_density_forms(no, nv, i, j, k0, nk, M3, t1, t2, oovv, fov, eo, ev, W2ab, W2n, Pab, Pn, Gij, Xij, dvv, Dov, S1):
+    """The non-GEMM part of the t3_density loop body for fixed (i,j) and k0 <= k < k0+nk (b200cc_t3_density_forms)."""
+    need = nk * nv ** 3
+    for t in (M3, W2ab, W2n, Pab, Pn):
+        if t.numel() < need or not t.is_contiguous():
+            raise B200ccError("t3_density_forms: work arrays must be contiguous with >= nk*nv^3 elements")
+    for t, n in ((Gij, nv * nv), (Xij, nv * nv), (dvv, nv), (Dov, nv), (S1, nv)):
+        if t.numel() != n or not t.is_contiguous():
+            raise B200ccError("t3_density_forms: accumulators must be contiguous (nv,nv) / (nv,) tensors")
+    if fov.stride(1) != 1 and nv > 1:
+        raise B200ccError("t3_density_forms: fov must be unit-stride along the virtual index")
+    sc = _scratch(M3.device, max(1, int(_lib.get().b200cc_t3_density_scratch(int(nv)))))
+    d = T3dDesc()
+    d.no, d.nv, d.i, d.j, d.k0, d.nk = int(no), int(nv), int(i), int(j), int(k0), int(nk)
+    d.M3, d.t1, d.t2, d.oovv = _lib.ptr(M3), _lib.ptr(_c(t1, "t1")), _lib.ptr(_c(t2, "t2")), _lib.ptr(_c(oovv, "oovv"))
+    d.fov, d.ldf = _lib.ptr(fov), int(fov.stride(0))
+    d.eo, d.ev = _lib.ptr(eo), _lib.ptr(ev)
+    d.W2ab, d.W2n, d.Pab, d.Pn = _lib.ptr(W2ab), _lib.ptr(W2n), _lib.ptr(Pab), _lib.ptr(Pn)
+    d.Gij, d.Xij = _lib.ptr(Gij), _lib.ptr(Xij)
+    d.dvv, d.Dov, d.S1 = _lib.ptr(dvv), _lib.ptr(Dov), _lib.ptr(S1)
+    d.scratch = _lib.ptr(sc)
+    _lib.check(_lib.get().b200cc_t3_density_forms(C.byref(d), _lib.stream()), "b200cc_t3_density_forms")
 
 
 def launch_count():

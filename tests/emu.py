@@ -343,6 +343,63 @@ class EmuLib:
         return 0
 
 
+    # ---- (T) densities -------------------------------------------------------------------------------
+    def b200cc_t3_connected_batch(self, no, nv, ntrip, ijk, Q, eo, ev, m3, stream):
+        self._count("t3_connected")
+        trip = _ints(ijk, 3 * ntrip).reshape(ntrip, 3)
+        v3 = nv ** 3
+        out = _vec(m3, ntrip * v3).reshape(ntrip, nv, nv, nv)
+        for n in range(ntrip):
+            i, j, k = (int(x) for x in trip[n])
+            W = self._W(_vec(Q + 8 * n * 6 * v3, 6 * v3).reshape(6, nv, nv, nv), nv)
+            out[n] = W / self._den(no, nv, i, j, k, eo, ev)
+        return 0
+
+    def b200cc_t3_density_scratch(self, nv):
+        return 3 * nv * ((nv + 7) // 8)
+
+    def b200cc_t3_density_forms(self, dref, stream):
+        d = dref._obj
+        self._count("t3_density_forms", 4)
+        no, nv, i, j, nk = d.no, d.nv, d.i, d.j, d.nk
+        v3 = nv ** 3
+        M = _vec(d.M3, nk * v3).reshape(nk, nv, nv, nv)
+        T1 = _arr(d.t1, (no, nv), (nv, 1))
+        T2 = _vec(d.t2, no * no * nv * nv).reshape(no, no, nv, nv)
+        Kv = _vec(d.oovv, no * no * nv * nv).reshape(no, no, nv, nv)
+        f = _arr(d.fov, (no, nv), (d.ldf, 1))
+        W2ab = _vec(d.W2ab, nk * v3).reshape(nv, nv, nk, nv)
+        W2n = _vec(d.W2n, nk * v3).reshape(nv, nk, nv, nv)
+        Pab = _vec(d.Pab, nk * v3).reshape(nv, nv, nk, nv)
+        Pn = _vec(d.Pn, nk * v3).reshape(nv, nk, nv, nv)
+        Gij, Xij = _vec(d.Gij, nv * nv).reshape(nv, nv), _vec(d.Xij, nv * nv).reshape(nv, nv)
+        dvv, Dov, S1 = _vec(d.dvv, nv), _vec(d.Dov, nv), _vec(d.S1, nv)
+
+        def sym(A):
+            return (8.0 * A - 4.0 * A.transpose(1, 0, 2) - 4.0 * A.transpose(0, 2, 1) - 4.0 * A.transpose(2, 1, 0)
+                    + 2.0 * A.transpose(2, 0, 1) + 2.0 * A.transpose(1, 2, 0))
+        e = np.einsum
+        for kk in range(nk):
+            k = d.k0 + kk
+            M3 = M[kk]
+            N3 = self._disc(no, nv, i, j, k, d.t1, d.t2, d.oovv, d.fov, d.ldf) / self._den(no, nv, i, j, k, d.eo, d.ev)
+            X3, Y3 = sym(M3), sym(N3)
+            W2 = 2.0 * X3 + Y3
+            P = 2.0 * M3 - M3.transpose(0, 2, 1) - M3.transpose(2, 1, 0)
+            U = M3 - M3.transpose(2, 1, 0)
+            Z3 = 2.0 * (M3 - M3.transpose(0, 2, 1)) - (M3.transpose(1, 0, 2) - M3.transpose(2, 0, 1))
+            W2ab[:, :, kk, :] = W2
+            W2n[:, kk] = W2
+            Pab[:, :, kk, :] = P
+            Pn[:, kk] = P
+            Gij += 4.0 * e("c,abc->ab", T1[k], Z3)
+            Xij += e("abc,c->ab", U, f[k])
+            dvv += 0.5 * e("abc,abc->a", M3, X3 + Y3)
+            Dov += e("abc,bc->a", U, 4.0 * T2[j, k] - 2.0 * T2[j, k].T)
+            S1 += e("abc,bc->a", 2.0 * (M3 - M3.transpose(1, 0, 2)), 2.0 * Kv[j, k] - Kv[j, k].T)
+        return 0
+
+
 class install:
     """Context manager / fixture helper: route pycc_b200 through the numpy double on CPU tensors."""
 
