@@ -207,11 +207,14 @@ int b200cc_t3_connected_batch(int no, int nv, int ntrip, const int* ijk, const d
  *     dvv[a]   += 1/2 M3 (X3 + Y3)               (line 1133; doo[i] = - sum_a of the same, line 1134)
  *     Dov[a]   += (M3 - M3[c,b,a]) (4 t2[j,k,b,c] - 2 t2[j,k,c,b])          (Dov[i], line 1137)
  *     S1[a]    += 2 (M3 - M3[b,a,c]) (2<jk|bc> - <jk|cb>)                   (S1[i], line 1146)
- * scratch: >= b200cc_t3_density_scratch(nv) doubles.  Deterministic (no atomics).                            */
+ * t2s = 4 t2 - 2 t2.swapaxes(2,3) and oovvs = 4<ij|ab> - 2<ij|ba> are (no,no,nv,nv) arrays built once by the caller
+ * (sym() of the disconnected t3 needs only these combinations, see triples.cu).
+ * swap_ab != 0: M3 holds the run of the transposed pair, M3[kk][b,a,c] = t3c(i,j,k)[a,b,c] (one t3 build serves
+ * (i,j) and (j,i)).  scratch: >= b200cc_t3_density_scratch(nv) doubles.  Deterministic (no atomics).            */
 typedef struct {
-  int no, nv, i, j, k0, nk;
+  int no, nv, i, j, k0, nk, swap_ab;
   const double* M3;                    /* [nk][nv^3] */
-  const double *t1, *t2, *oovv, *fov;  /* fov: (no,nv) view, leading dimension ldf */
+  const double *t1, *t2s, *oovvs, *fov; /* fov: (no,nv) view, leading dimension ldf */
   b200cc_i64 ldf;
   const double *eo, *ev;
   double *W2ab, *W2n, *Pab, *Pn;       /* nk*nv^3 each */

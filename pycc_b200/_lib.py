@@ -74,7 +74,8 @@ class T3dDesc(C.Structure):
     """Mirror of ``b200cc_t3d_desc`` (include/b200cc.h)."""
     _fields_ = [
         ("no", C.c_int), ("nv", C.c_int), ("i", C.c_int), ("j", C.c_int), ("k0", C.c_int), ("nk", C.c_int),
-        ("M3", dptr), ("t1", dptr), ("t2", dptr), ("oovv", dptr), ("fov", dptr),
+        ("swap_ab", C.c_int),
+        ("M3", dptr), ("t1", dptr), ("t2s", dptr), ("oovvs", dptr), ("fov", dptr),
         ("ldf", i64),
         ("eo", dptr), ("ev", dptr),
         ("W2ab", dptr), ("W2n", dptr), ("Pab", dptr), ("Pn", dptr),

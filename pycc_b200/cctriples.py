@@ -357,19 +357,21 @@ T3D_NAMES = ("Doo", "Dvv", "Dov", "Goovv", "Gooov", "Gvvvo", "S1", "S2")
 
 
 def t3_density(o, v, no, nv, t1, t2, F, ERI, L, contract, comm=None, k_batch=None, work_bytes=None, prof=None,
-               js=None):
+               pairs=None):
     """(T) energy plus the (T) increments {Doo, Dvv, Dov, Goovv, Gooov, Gvvvo, S1, S2} to the one-/two-particle
     densities and the Lambda residuals; reference: cctriples.py:1063-1157, same signature and return value
     (``ERI`` must be the ``H.ERI`` block view of a :class:`BlockHamiltonian`; ``L`` is derived from it).
 
-    The reference's o^3 loop body is 13 einsums on (v,v,v) tiles.  Here, for fixed (j, i) and a run of k:
+    The reference's o^3 loop body is 13 einsums on (v,v,v) tiles.  Here, for a pair i >= j and a run of k:
 
     1. the t3 numerators of all k are six two-segment GEMMs per triple in ONE launch (TriplesEngine.build_q, the
-       kernel of t_tjl); ``b200cc_t3_connected_batch`` assembles M3 = t3c/D (every Q element read once);
-    2. ``b200cc_t3_density_forms`` forms N3 = t3d/D on the fly and writes the two GEMM operands W2 = 2 sym(M3) +
+       kernel of t_tjl); ``b200cc_t3_connected_batch`` assembles M3 = t3c/D (every Q element read once).  Because
+       t3c(j,i,k)[b,a,c] = t3c(i,j,k)[a,b,c], the same M3 run serves the loop bodies of (i,j) AND (j,i): the t3 build,
+       70 % of the reference's flops, is done for o(o+1)/2 pairs instead of o^2;
+    2. ``b200cc_t3_density_forms`` forms sym(t3d/D) on the fly and writes the two GEMM operands W2 = 2 sym(M3) +
        sym(N3) and P = 2 M3 - M3[acb] - M3[cba], each in the two K-major layouts the products below need, and keeps
        every matrix-vector shaped term (Goovv, the Fock part of X2, dvv/doo, Dov, S1) as in-register running sums;
-    3. the run index k is folded into the SUMMATION index of five long-K GEMMs (no per-triple launches, no permuted
+    3. the run index k is folded into the SUMMATION index of six long-K GEMMs (no per-triple launches, no permuted
        copies of <mb|ef>):
          Gvvvo[:,:,:,j] [(a,b),d] += W2ab[(a,b),(k,c)] t2[i,k,d,c]          K = o v          (line 1143)
          S2[i] [(a,b),l]          -= W2ab[(a,b),(k,c)] <jk|lc>              K = o v          (line 1147)
@@ -379,9 +381,9 @@ def t3_density(o, v, no, nv, t1, t2, F, ERI, L, contract, comm=None, k_batch=Non
          Gooov[j,i] [l,a]         -= t2[l,(k,b,c)] W2n[a,(k,b,c)]                            (line 1142)
        (<dk|bc> = <kd|cb> = <kb|cd> = ovvv[k,b,c,d], so the natural layout of <mb|ef> IS the [(k,b,c), d] matrix).
 
-    With a ``comm`` the middle loop index j is dealt round-robin to the ranks and the pieces are summed with
-    all-reduces at the end.  Returns ``(ET, dict)``; ET is a 0-d device tensor.  ``prof`` (a dict) collects CUDA-event
-    times per phase in ms; ``js`` restricts the j loop (timing probes only: the result is then a partial sum).
+    With a ``comm`` the (i >= j) pairs are dealt round-robin to the ranks and the pieces are summed with all-reduces
+    at the end.  Returns ``(ET, dict)``; ET is a 0-d device tensor.  ``prof`` (a dict) collects CUDA-event times per
+    phase in ms; ``pairs`` restricts the pair loop (timing probes only: the result is then a partial sum).
     """
     import types
     H = getattr(ERI, "H", None)
@@ -394,30 +396,35 @@ def t3_density(o, v, no, nv, t1, t2, F, ERI, L, contract, comm=None, k_batch=Non
     eo, ev = _eps(F, o, v)
     shim = types.SimpleNamespace(H=H, no=no, nv=nv, t1=t1, t2=t2, o=o, v=v, eps_o=eo, eps_v=ev, mixed=False)
     v2, v3 = nv * nv, nv ** 3
+    z = lambda *shape: torch.zeros(shape, dtype=F64, device=dev)
+    ovvv, ooov, oovv = H.block("ovvv"), H.block("ooov"), H.block("oovv")
+    t2q = K.permuted(t2, (0, 2, 1, 3))               # [i,d,k,c] = t2[i,k,d,c]
+    ooovq = K.permuted(ooov, (0, 2, 1, 3))           # [j,l,k,c] = <jk|lc>
+    t2s = K.permuted(t2, (0, 1, 2, 3), 4.0)          # 4 t2 - 2 t2.swapaxes(2,3)
+    K.strided_axpby(t2s, t2.permute(0, 1, 3, 2), -2.0, 1.0)
+    oovvs = K.permuted(oovv, (0, 1, 2, 3), 4.0)      # 4 <ij|ab> - 2 <ij|ba>
+    K.strided_axpby(oovvs, oovv.permute(0, 1, 3, 2), -2.0, 1.0)
+    dvv_i, Dov, S1 = z(no, nv), z(no, nv), z(no, nv)
+    Goovv, X2, S2 = z(no, no, nv, nv), z(no, no, nv, nv), z(no, no, nv, nv)
+    S2T, X2T = z(no, v2, no), z(no, v2, no)         # [i][(a,b)][l]
+    Gooov = z(no, no, no, nv)
+    Gall = z(no, v2, nv)                            # [j][(a,b)][d]
     # work arrays per k of a run: Q (6 v^3) + M3 + W2ab + W2n + Pab + Pn = 11 v^3 doubles
     if work_bytes is None:
         work_bytes = 24 << 30
         if dev.type == "cuda":
             free, _ = torch.cuda.mem_get_info(dev)
-            work_bytes = int(free * 0.6)
+            work_bytes = int((free - 8 * no * v3) * 0.6)          # Gvvvo itself is still to be allocated
     kb = int(max(1, min(no, work_bytes // (11 * 8 * v3)))) if k_batch is None else int(max(1, min(no, k_batch)))
     kb = -(-no // -(-no // kb))                      # equal-sized runs
     eng = TriplesEngine(shim, t1, t2, q_bytes=kb * 6 * v3 * 8)
     eng.fov = F[o, v]
     fov = eng.fov
-    ovvv, ooov, oovv = H.block("ovvv"), H.block("ooov"), H.block("oovv")
-    t2q = K.permuted(t2, (0, 2, 1, 3))               # [i,d,k,c] = t2[i,k,d,c]
-    ooovq = K.permuted(ooov, (0, 2, 1, 3))           # [j,l,k,c] = <jk|lc>
-    z = lambda *shape: torch.zeros(shape, dtype=F64, device=dev)
     M3 = torch.empty(kb * v3, dtype=F64, device=dev)
     W2ab, W2n, Pab, Pn = (torch.empty(kb * v3, dtype=F64, device=dev) for _ in range(4))
-    dvv_i, Dov, S1 = z(no, nv), z(no, nv), z(no, nv)
-    Goovv, X2, S2 = z(no, no, nv, nv), z(no, no, nv, nv), z(no, no, nv, nv)
-    S2T, X2T = z(no, v2, no), z(no, v2, no)         # [i][(a,b)][l]
-    Gooov = z(no, no, no, nv)
-    Gvvvo = z(nv, nv, nv, no)
-    Gj = torch.empty((v2, nv), dtype=F64, device=dev)
     size, rank = (comm.size, comm.rank) if comm is not None else (1, 0)
+    if pairs is None:
+        pairs = [(i, j) for j in range(no) for i in range(j, no)][rank::size]
     marks = []
 
     def mark(name):
@@ -427,31 +434,35 @@ def t3_density(o, v, no, nv, t1, t2, F, ERI, L, contract, comm=None, k_batch=Non
             marks.append((name, e))
 
     try:
-        for j in (range(rank, no, size) if js is None else js):
-            Gj.zero_()
-            for i in range(no):
-                for k0 in range(0, no, kb):
-                    nk = min(kb, no - k0)
-                    trip = [(i, j, k) for k in range(k0, k0 + nk)]
-                    ijk = torch.tensor(np.asarray(trip, dtype=np.int32), dtype=torch.int32).to(dev)
+        for (i0, j0) in pairs:
+            for k0 in range(0, no, kb):
+                nk = min(kb, no - k0)
+                trip = [(i0, j0, k) for k in range(k0, k0 + nk)]
+                ijk = torch.tensor(np.asarray(trip, dtype=np.int32), dtype=torch.int32).to(dev)
+                mark("start")
+                Q = eng.build_q(trip)
+                mark("t3_gemm")
+                K.t3_connected_batch(no, nv, ijk, Q, eo, ev, M3)
+                mark("connected")
+                for (i, j, swap) in (((i0, j0, False),) if i0 == j0 else ((i0, j0, False), (j0, i0, True))):
                     mark("start")
-                    Q = eng.build_q(trip)
-                    mark("t3_gemm")
-                    K.t3_connected_batch(no, nv, ijk, Q, eo, ev, M3)
-                    mark("connected")
-                    K.t3_density_forms(no, nv, i, j, k0, nk, M3, t1, t2, oovv, fov, eo, ev, W2ab, W2n, Pab, Pn,
-                                       Goovv[i, j], X2[i, j], dvv_i[i], Dov[i], S1[i])
+                    K.t3_density_forms(no, nv, i, j, k0, nk, M3, t1, t2s, oovvs, fov, eo, ev, W2ab, W2n, Pab, Pn,
+                                       Goovv[i, j], X2[i, j], dvv_i[i], Dov[i], S1[i], swap_ab=swap)
                     mark("forms")
                     kc, kbc = nk * nv, nk * v2
-                    K.dgemm(v2, nv, kc, W2ab, kc, 0, (t2q, (i * nv * no + k0) * nv), no * nv, 0, Gj, nv, 1.0, 1.0)
+                    K.dgemm(v2, nv, kc, W2ab, kc, 0, (t2q, (i * nv * no + k0) * nv), no * nv, 0, Gall[j], nv, 1.0, 1.0)
+                    mark("gemm_Gvvvo")
                     qoff = (j * no * no + k0) * nv
                     K.dgemm(v2, no, kc, W2ab, kc, 0, (ooovq, qoff), no * nv, 0, S2T[i], no, -1.0, 1.0)
                     K.dgemm(v2, no, kc, Pab, kc, 0, (ooovq, qoff), no * nv, 0, X2T[i], no, -1.0, 1.0)
-                    K.dgemm(nv, nv, kbc, W2n, kbc, 0, (ovvv, k0 * v3), nv, 1, S2[i, j], nv, 1.0, 1.0)
-                    K.dgemm(nv, nv, kbc, Pn, kbc, 0, (ovvv, k0 * v3), nv, 1, X2[i, j], nv, 1.0, 1.0)
-                    K.dgemm(no, nv, kbc, (t2, k0 * v2), no * v2, 0, W2n, kbc, 0, Gooov[j, i], nv, -1.0, 1.0)
-                    mark("density_gemm")
-            K.strided_axpby(Gvvvo[:, :, :, j], Gj.view(nv, nv, nv), 1.0, 0.0)
+                    mark("gemm_ooov")
+                    ks = K.balanced_ksplit(nv, nv, kbc)
+                    K.dgemm(nv, nv, kbc, W2n, kbc, 0, (ovvv, k0 * v3), nv, 1, S2[i, j], nv, 1.0, 1.0, ksplit=ks)
+                    K.dgemm(nv, nv, kbc, Pn, kbc, 0, (ovvv, k0 * v3), nv, 1, X2[i, j], nv, 1.0, 1.0, ksplit=ks)
+                    mark("gemm_ovvv")
+                    K.dgemm(no, nv, kbc, (t2, k0 * v2), no * v2, 0, W2n, kbc, 0, Gooov[j, i], nv, -1.0, 1.0,
+                            ksplit=K.balanced_ksplit(no, nv, kbc))
+                    mark("gemm_Gooov")
     finally:
         eng.close()
     if prof is not None:
@@ -459,11 +470,14 @@ def t3_density(o, v, no, nv, t1, t2, F, ERI, L, contract, comm=None, k_batch=Non
         for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
             if name != "start":
                 prof[name] = prof.get(name, 0.0) + e0.elapsed_time(e1)
-    del M3, W2ab, W2n, Pab, Pn, Gj
-    # [i][(a,b)][l] -> [i,l,a,b]
+    del M3, W2ab, W2n, Pab, Pn
+    _QCACHE.pop(dev, None)                           # release the Q workspace before the o v^3 output is allocated
+    # [i][(a,b)][l] -> [i,l,a,b];  [j][a,b,d] -> [a,b,d,j]
     K.strided_axpby(S2, S2T.view(no, nv, nv, no).permute(0, 3, 1, 2), 1.0, 1.0)
     K.strided_axpby(X2, X2T.view(no, nv, nv, no).permute(0, 3, 1, 2), 1.0, 1.0)
     del S2T, X2T
+    Gvvvo = K.permuted(Gall.view(no, nv, nv, nv), (1, 2, 3, 0))
+    del Gall
     if size > 1:
         for t in (dvv_i, Dov, S1, Goovv, X2, S2, Gooov, Gvvvo):
             comm.all_reduce_sum(t)
@@ -473,10 +487,8 @@ def t3_density(o, v, no, nv, t1, t2, F, ERI, L, contract, comm=None, k_batch=Non
     ct('ia,i->a', dvv_i, torch.ones(no, dtype=F64, device=dev), out=torch.diagonal(Dvv), alpha=1.0, beta=0.0)
     ct('ia,a->i', dvv_i, torch.ones(nv, dtype=F64, device=dev), out=torch.diagonal(Doo), alpha=-1.0, beta=0.0)
     # ET = t1.S1 + (4 t2 - 2 t2.swapaxes(2,3)).X2                                                         (1153-1154)
-    s = K.permuted(t2, (0, 1, 2, 3), 4.0)
-    K.strided_axpby(s, t2.permute(0, 1, 3, 2), -2.0, 1.0)
     d1 = K.multi_dot(t1.reshape(-1), [S1.reshape(-1)])
-    d2 = K.multi_dot(s.reshape(-1), [X2.reshape(-1)])
+    d2 = K.multi_dot(t2s.reshape(-1), [X2.reshape(-1)])
     et = torch.empty(1, dtype=F64, device=dev)
     K.axpbyz(1.0, d1, 1.0, d2, et)
     return et[0], {'Doo': Doo, 'Dvv': Dvv, 'Dov': Dov, 'Goovv': Goovv, 'Gooov': Gooov, 'Gvvvo': Gvvvo,

@@ -194,6 +194,16 @@ __global__ void __launch_bounds__(256) t3_assemble_kernel(const TArgs p, int i, 
   }
 }
 
+// Conflict-free 8x8x8 shared tile: element (l0,l1,l2) lives at ((l0,l1,l2) as 9 bits) ^ h(l0,l1) with
+//   h = 9 (l0 & 1) ^ (l0 & 6) ^ (l1 & 6),
+// a GF(2)-linear swizzle of the low four address bits (= the 64-bit bank).  For EVERY assignment of the thread
+// coordinates (la,lb,lc) to (l0,l1,l2) the 16 lanes of a half-warp (lc = 0..7, two lb) hit 16 distinct banks, so the
+// six permuted scatter-stores and the natural-order loads are all single-wavefront (the padded 73/9 pitches of the
+// energy kernel are 2-way conflicted on every pattern; ncu: 1.5 extra wavefronts per shared instruction).
+__device__ __forceinline__ int swz(int l0, int l1, int l2) {
+  return ((l0 << 6) | (l1 << 3) | l2) ^ (((l0 & 1) * 9) ^ (l0 & 6) ^ (l1 & 6));
+}
+
 // ---- (T) densities (cctriples.py:1063-1157) ---------------------------------------------------------------------
 // Step 1: connected t3 WITH denominators of a batch of triples, M3[t][a,b,c] = (Q1[a,b,c] + Q2[a,c,b] + Q3[c,a,b] +
 // Q4[c,b,a] + Q5[b,c,a] + Q6[b,a,c]) / D.  One CTA per 8x8x8 cube of the FULL (a,b,c) space; the six source blocks are
@@ -203,7 +213,7 @@ __global__ void __launch_bounds__(512, 2) t3_connected_kernel(int no, int nv, in
                                                               const double* __restrict__ Q,
                                                               const double* __restrict__ eo,
                                                               const double* __restrict__ ev, double* __restrict__ M3) {
-  __shared__ double Wsm[WTILE];
+  __shared__ double Wsm[512];
   int rem = blockIdx.x;
   const int TC = rem % nt; rem /= nt;
   const int TB = rem % nt;
@@ -223,7 +233,7 @@ __global__ void __launch_bounds__(512, 2) t3_connected_kernel(int no, int nv, in
     if (x < nv && y < nv && z < nv) val = __ldg(Qt + (i64)n * v3 + ((i64)x * nv + y) * nv + z);
     int l[3];
     l[r0] = u[0]; l[r1] = u[1]; l[r2] = u[2];
-    double* dst = &Wsm[l[0] * SA + l[1] * SB + l[2]];
+    double* dst = &Wsm[swz(l[0], l[1], l[2])];
     if (n == 0) *dst = val;
     else *dst += val;
     __syncthreads();
@@ -231,14 +241,13 @@ __global__ void __launch_bounds__(512, 2) t3_connected_kernel(int no, int nv, in
   const int a = T[0] + u[0], b = T[1] + u[1], c = T[2] + u[2];
   if (a < nv && b < nv && c < nv) {
     const double den = eo[i] + eo[j] + eo[k] - ev[a] - ev[b] - ev[c];
-    M3[(i64)trip * v3 + ((i64)a * nv + b) * nv + c] = Wsm[u[0] * SA + u[1] * SB + u[2]] / den;
+    M3[(i64)trip * v3 + ((i64)a * nv + b) * nv + c] = Wsm[swz(u[0], u[1], u[2])] / den;
   }
 }
 
 // Step 2: everything of the (i,j,k) loop body of t3_density that is not a GEMM, for fixed (i,j) and a run of k.
-// A CTA owns the 8x8 tile (TA,TB) of (a,b) and sweeps all k of the run and all c cubes: per cube the six permuted
-// blocks of M3 are staged in shared memory (coalesced), the disconnected t3 N3 is formed on the fly at the six
-// permutations, and the thread at (a,b,c) produces
+// A CTA owns the 8x8 tile (TA,TB) of (a,b) and sweeps all k of the run and all c cubes.  Per cube the six permuted
+// blocks of M3 are staged in shared memory (coalesced 64-byte runs) and the thread at (a,b,c) produces
 //   W2 = 2 sym(M3) + sym(N3)   and   P = 2 M3 - M3[acb] - M3[cba]         (GEMM operands, written in TWO layouts each:
 //                                        [(a,b)][k][c] for the contractions over (k,c), [a][k][(b,c)] for those over (k,b,c))
 // and keeps in registers the running sums of the matrix-vector shaped terms (lines 1128, 1133-1137, 1141, 1146):
@@ -247,16 +256,29 @@ __global__ void __launch_bounds__(512, 2) t3_connected_kernel(int no, int nv, in
 //   S1[i,a] += 2 (M3 - M3[bac]) (2<jk|bc> - <jk|cb>)                                             (sum over k, b, c)
 // (a,b) sums are written by their owner CTA (no atomics); per-a sums go to scratch[q][a][TB] and a second-stage
 // reduction, so the result is deterministic.
+//
+// The disconnected t3 is never formed per permutation.  With A~[x,y] = 4 A[x,y] - 2 A[y,x] the symmetriser of
+// cctriples.py:1125 applied to the three outer-product shapes of t3d_ijk (cctriples.py:131-137) collapses to
+//   sym(A[x,y] w[z]) = 2 A~[a,b] w[c] -   A~[a,c] w[b] -   A~[c,b] w[a]
+//   sym(A[x,z] w[y]) = 2 A~[a,c] w[b] -   A~[b,c] w[a] -   A~[a,b] w[c]
+//   sym(A[y,z] w[x]) = 2 A~[b,c] w[a] -   A~[a,c] w[b] -   A~[b,a] w[c]
+// so per cube only twelve 8x8 tiles of K~ = 4<pq|ab> - 2<pq|ba> and T~ = 4 t2 - 2 t2^T (both built once by the host)
+// are staged next to the M3 blocks; the (a,b)-only factors live in registers.  K~[j,k][b,c] and T~[j,k][b,c] are also
+// exactly the weights of the S1 (x 1/2) and Dov sums.  Loads of the next cube are issued before the arithmetic of the
+// current one (register prefetch).  swap_ab: M3 holds the run of the TRANSPOSED pair, M3(j,i,k)[b,a,c] = M3(i,j,k)[a,b,c]
+// (cctriples.py:50-62 is symmetric under simultaneous permutation of (i,j,k) and (a,b,c)), so one t3 build serves both.
 struct T3dArgs {
-  int no, nv, nt, i, j, k0, nk;
+  int no, nv, nt, i, j, k0, nk, swap_ab;
   const double* M3;
-  const double *t1, *t2, *oovv, *fov, *eo, *ev;
+  const double *t1, *Ts, *Ks, *fov, *eo, *ev;
   i64 ldf;
   double *W2ab, *W2n, *Pab, *Pn, *Gij, *Xij, *scratch;
 };
 
+template <bool SWAP>
 __global__ void __launch_bounds__(512, 1) t3_density_forms_kernel(const T3dArgs p) {
-  __shared__ double Wsm[6][WTILE];
+  __shared__ double Wsm[6][512];
+  __shared__ double Tl[12][64];
   __shared__ double red[16][3];
   const int nv = p.nv, nt = p.nt, no = p.no;
   const int TA = blockIdx.y, TB = blockIdx.x;
@@ -265,61 +287,157 @@ __global__ void __launch_bounds__(512, 1) t3_density_forms_kernel(const T3dArgs 
   const int a = TA * TT + la, b = TB * TT + lb;
   const i64 vv = (i64)nv * nv, v3 = vv * nv;
   constexpr int PERM[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+  const int TAB[2] = {TA * TT, TB * TT};
+
+  // ---- prefetch state: everything advances by constant pointer steps per c-cube / per k -------------------------
+  // M3 block of target permutation r: source coordinates (x,y,z) = (X[PERM[r][0]] + u0, X[PERM[r][1]] + u1, X[PERM[r][2]] + u2)
+  // with X = (A origin, B origin, C origin); the C origin moves by 8 per iteration along the source axis holding c.
+  unsigned moff[6];          // element offsets into M3 (the host keeps nk * nv^3 < 2^32)
+  unsigned mstep[6];
   int dsto[6];
+  unsigned abok = 0;         // bit r: the two non-c source coordinates are in range
+  int ucp[6];                // thread coordinate that sits on the c axis of block r
 #pragma unroll
   for (int r = 0; r < 6; ++r) {
     int l[3];
     l[PERM[r][0]] = u[0]; l[PERM[r][1]] = u[1]; l[PERM[r][2]] = u[2];
-    dsto[r] = l[0] * SA + l[1] * SB + l[2];
-  }
-  const int s = la * SA + lb * SB + lc;
-  TArgs q;
-  q.no = no; q.nv = nv; q.t1 = p.t1; q.t2 = p.t2; q.oovv = p.oovv; q.fov = p.fov; q.ldf = p.ldf;
-  double accG = 0.0, accX = 0.0, accD = 0.0, accO = 0.0, accS = 0.0;
-  const bool ab_ok = (a < nv) & (b < nv);
-  const double evab = ab_ok ? p.ev[a] + p.ev[b] : 0.0;
-  for (int kk = 0; kk < p.nk; ++kk) {
-    const int k = p.k0 + kk;
-    const Disc D = make_disc(q, p.i, p.j, k);
-    const double eijk = p.eo[p.i] + p.eo[p.j] + p.eo[k];
-    const double* Mk = p.M3 + (i64)kk * v3;
-    const double* Tjk = p.t2 + ((i64)p.j * no + k) * vv;
-    const double* Kjk = p.oovv + ((i64)p.j * no + k) * vv;
-    const double* t1k = p.t1 + (i64)k * nv;
-    const double* fk = p.fov + (i64)k * p.ldf;
-    for (int TC = 0; TC < nt; ++TC) {
-      const int T[3] = {TA * TT, TB * TT, TC * TT};
+    dsto[r] = swz(l[0], l[1], l[2]);
+    unsigned off = 0;
+    bool ok = true;
+    const unsigned st[3] = {(unsigned)vv, (unsigned)nv, 1u};
+    mstep[r] = 0; ucp[r] = 0;
 #pragma unroll
-      for (int r = 0; r < 6; ++r) {
-        const int x = T[PERM[r][0]] + u[0], y = T[PERM[r][1]] + u[1], z = T[PERM[r][2]] + u[2];
-        double val = 0.0;
-        if ((x < nv) & (y < nv) & (z < nv)) val = __ldg(Mk + ((i64)x * nv + y) * nv + z);
-        Wsm[r][dsto[r]] = val;
-      }
+    for (int n = 0; n < 3; ++n) {
+      if (PERM[r][n] == 2) { mstep[r] = TT * st[n]; ucp[r] = u[n]; off += (unsigned)u[n] * st[n]; }
+      else { const int x = TAB[PERM[r][n]] + u[n]; ok = ok && (x < nv); off += (unsigned)(ok ? x : 0) * st[n]; }
+    }
+    moff[r] = off;
+    if (ok) abok |= 1u << r;
+  }
+  // the tile(s) this thread stages: tile t = tid/64 (and 8 + tid/64 for tid < 256), as 8x8 elements (lb, lc)
+  //   t % 6:  0 ij[a,c]  1 ij[c,b]  2 ik[a,c]  3 ik[b,c]  4 jk[b,c]  5 jk[a,c];   t / 6: 0 = K~, 1 = T~
+  // every tile is stored [row = its a- or b-coordinate][col = c]; for tile 1 (source rows = c) the thread reads the
+  // source element (c = C + lc, b = B + lb) -- strided in global memory, conflict-free in shared memory.
+  const int tl[2] = {(int)(threadIdx.x >> 6), 8 + (int)(threadIdx.x >> 6)};
+  const bool has1 = threadIdx.x < 256;
+  const double* tbase[2];
+  unsigned toff[2], tstep[2], tkstep[2];     // element offsets into K~ / T~ (no^2 nv^2 < 2^32, checked by the host)
+  bool tok[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int m = tl[h] % 6;
+    tbase[h] = tl[h] >= 6 ? p.Ts : p.Ks;
+    const unsigned base = (unsigned)(m < 2 ? (p.i * no + p.j) : (m < 4 ? (p.i * no + p.k0) : (p.j * no + p.k0))) * (unsigned)vv;
+    tkstep[h] = m < 2 ? 0u : (unsigned)vv;
+    const int rowo = (m == 3 || m == 4 || m == 1) ? TAB[1] : TAB[0];       // b-rows for bc / cb tiles, else a-rows
+    const int x = rowo + lb;
+    tok[h] = (x < nv) && (h == 0 || has1);
+    const unsigned xs = tok[h] ? (unsigned)x : 0u;
+    if (m == 1) { toff[h] = base + (unsigned)lc * nv + xs; tstep[h] = (unsigned)TT * nv; }
+    else { toff[h] = base + xs * nv + lc; tstep[h] = TT; }
+  }
+  int nTC = 0, nkk = 0;      // (k, c-cube) of the NEXT iteration to load
+  double nm[6], ntl[2];
+  auto load_next = [&]() {
+    const int c0 = nTC * TT;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      nm[r] = 0.0;
+      if (((abok >> r) & 1u) && (c0 + ucp[r] < nv)) nm[r] = __ldg(p.M3 + moff[r]);
+      moff[r] += mstep[r];
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      ntl[h] = 0.0;
+      if (tok[h] && (c0 + lc < nv)) ntl[h] = __ldg(tbase[h] + toff[h]);
+      toff[h] += tstep[h];
+    }
+    if (++nTC == nt) {
+      nTC = 0; ++nkk;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) moff[r] += (unsigned)v3 - (unsigned)nt * mstep[r];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) toff[h] += tkstep[h] - (unsigned)nt * tstep[h];
+    }
+  };
+
+  // ---- (a,b)-only factors ---------------------------------------------------------------------------------------
+  const bool ab_ok = (a < nv) & (b < nv);
+  const int ac = a < nv ? a : 0, bc = b < nv ? b : 0;
+  const i64 pij = ((i64)p.i * no + p.j) * vv;
+  const double* t1i = p.t1 + (i64)p.i * nv;
+  const double* t1j = p.t1 + (i64)p.j * nv;
+  const double* fi = p.fov + (i64)p.i * p.ldf;
+  const double* fj = p.fov + (i64)p.j * p.ldf;
+  const double t1ia = t1i[ac], t1ib = t1i[bc], t1ja = t1j[ac], t1jb = t1j[bc];
+  const double fia = fi[ac], fib = fi[bc], fja = fj[ac], fjb = fj[bc];
+  const double Kij_ab = p.Ks[pij + (i64)ac * nv + bc], Tij_ab = p.Ts[pij + (i64)ac * nv + bc];
+  const double evab = p.ev[ac] + p.ev[bc];
+  const double eij = p.eo[p.i] + p.eo[p.j];
+  // M3 of the transposed pair: target permutation r reads the tile of r with its first two source axes exchanged
+  const int s = swz(la, lb, lc);
+  const int ac_ = la * 8 + lc, bc_ = lb * 8 + lc;
+  // output cursors: W2ab/Pab [(a,b)][kk][c], W2n/Pn [a][kk][b][c]
+  i64 oab = ((i64)ac * nv + bc) * p.nk * nv + lc;
+  i64 on = (i64)ac * p.nk * vv + (i64)bc * nv + lc;
+
+  double accG = 0.0, accX = 0.0, accD = 0.0, accO = 0.0, accS = 0.0;
+  double Kik_ab = 0.0, Tik_ab = 0.0, Kjk_ba = 0.0, Tjk_ba = 0.0, t1ka = 0.0, t1kb = 0.0, fka = 0.0, fkb = 0.0, eabk = 0.0;
+  const double *t1k = p.t1, *fk = p.fov;
+  load_next();
+  for (int kk = 0; kk < p.nk; ++kk) {
+    {
+      const int k = p.k0 + kk;
+      const i64 pik = ((i64)p.i * no + k) * vv, pjk = ((i64)p.j * no + k) * vv;
+      Kik_ab = p.Ks[pik + (i64)ac * nv + bc]; Tik_ab = p.Ts[pik + (i64)ac * nv + bc];
+      Kjk_ba = p.Ks[pjk + (i64)bc * nv + ac]; Tjk_ba = p.Ts[pjk + (i64)bc * nv + ac];
+      t1k = p.t1 + (i64)k * nv; fk = p.fov + (i64)k * p.ldf;
+      t1ka = t1k[ac]; t1kb = t1k[bc]; fka = fk[ac]; fkb = fk[bc];
+      eabk = eij + p.eo[k] - evab;
+    }
+    for (int TC = 0; TC < nt; ++TC) {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) Wsm[r][dsto[r]] = nm[r];
+      Tl[tl[0]][bc_] = ntl[0];
+      if (has1) Tl[tl[1]][bc_] = ntl[1];
       __syncthreads();
+      if (nkk < p.nk) load_next();
       const int c = TC * TT + lc;
       if (ab_ok && c < nv) {
-        const double m0 = Wsm[0][s], m1 = Wsm[1][s], m2 = Wsm[2][s], m3 = Wsm[3][s], m4 = Wsm[4][s], m5 = Wsm[5][s];
-        const double rden = 1.0 / (eijk - evab - p.ev[c]);
-        const double n0 = D(a, b, c), n1 = D(a, c, b), n2 = D(b, a, c), n3 = D(b, c, a), n4 = D(c, a, b), n5 = D(c, b, a);
+        const double m0 = Wsm[SWAP ? 2 : 0][s], m1 = Wsm[SWAP ? 4 : 1][s], m2 = Wsm[SWAP ? 0 : 2][s];
+        const double m3 = Wsm[SWAP ? 5 : 3][s], m4 = Wsm[SWAP ? 1 : 4][s], m5 = Wsm[SWAP ? 3 : 5][s];
+        const double Kij_ac = Tl[0][ac_], Kij_cb = Tl[1][bc_], Kik_ac = Tl[2][ac_], Kik_bc = Tl[3][bc_];
+        const double Kjk_bc = Tl[4][bc_], Kjk_ac = Tl[5][ac_];
+        const double Tij_ac = Tl[6][ac_], Tij_cb = Tl[7][bc_], Tik_ac = Tl[8][ac_], Tik_bc = Tl[9][bc_];
+        const double Tjk_bc = Tl[10][bc_], Tjk_ac = Tl[11][ac_];
+        const double t1kc = __ldg(t1k + c), t1jc = __ldg(t1j + c), t1ic = __ldg(t1i + c);
+        const double fkc = __ldg(fk + c), fjc = __ldg(fj + c), fic = __ldg(fi + c);
+        const double rden = 1.0 / (eabk - __ldg(p.ev + c));
+        const double Yn = (2.0 * Kij_ab * t1kc - Kij_ac * t1kb - Kij_cb * t1ka)
+                          + (2.0 * Kik_ac * t1jb - Kik_bc * t1ja - Kik_ab * t1jc)
+                          + (2.0 * Kjk_bc * t1ia - Kjk_ac * t1ib - Kjk_ba * t1ic)
+                          + (2.0 * Tij_ab * fkc - Tij_ac * fkb - Tij_cb * fka)
+                          + (2.0 * Tik_ac * fjb - Tik_bc * fja - Tik_ab * fjc)
+                          + (2.0 * Tjk_bc * fia - Tjk_ac * fib - Tjk_ba * fic);
         const double X3 = 8.0 * m0 - 4.0 * (m1 + m2 + m5) + 2.0 * (m3 + m4);
-        const double Y3 = (8.0 * n0 - 4.0 * (n1 + n2 + n5) + 2.0 * (n3 + n4)) * rden;
+        const double Y3 = Yn * rden;
         const double W2 = 2.0 * X3 + Y3;
         const double P = 2.0 * m0 - m1 - m5;
         const double U = m0 - m5;
         const double Z3 = 2.0 * (m0 - m1) - (m2 - m3);
-        const i64 iab = (((i64)a * nv + b) * p.nk + kk) * nv + c;
-        const i64 in = (((i64)a * p.nk + kk) * nv + b) * nv + c;
-        p.W2ab[iab] = W2; p.W2n[in] = W2;
-        p.Pab[iab] = P;   p.Pn[in] = P;
-        accG += 4.0 * t1k[c] * Z3;
-        accX += U * fk[c];
+        p.W2ab[oab] = W2; p.W2n[on] = W2;
+        p.Pab[oab] = P;   p.Pn[on] = P;
+        accG += 4.0 * t1kc * Z3;
+        accX += U * fkc;
         accD += 0.5 * m0 * (X3 + Y3);
-        accO += U * (4.0 * Tjk[(i64)b * nv + c] - 2.0 * Tjk[(i64)c * nv + b]);
-        accS += 2.0 * (m0 - m2) * (2.0 * Kjk[(i64)b * nv + c] - Kjk[(i64)c * nv + b]);
+        accO += U * Tjk_bc;
+        accS += (m0 - m2) * Kjk_bc;
       }
+      oab += TT; on += TT;
       __syncthreads();
     }
+    oab += nv - (i64)nt * TT;
+    on += vv - (i64)nt * TT;
   }
   // (a,b) sums: reduce over the 8 lanes that share (la,lb)
 #pragma unroll
@@ -422,10 +540,16 @@ extern "C" int b200cc_t3_density_forms(const b200cc_t3d_desc* d, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   T3dArgs p;
   p.no = d->no; p.nv = d->nv; p.nt = (d->nv + TT - 1) / TT; p.i = d->i; p.j = d->j; p.k0 = d->k0; p.nk = d->nk;
-  p.M3 = d->M3; p.t1 = d->t1; p.t2 = d->t2; p.oovv = d->oovv; p.fov = d->fov; p.eo = d->eo; p.ev = d->ev;
+  p.swap_ab = d->swap_ab ? 1 : 0;
+  p.M3 = d->M3; p.t1 = d->t1; p.Ts = d->t2s; p.Ks = d->oovvs; p.fov = d->fov; p.eo = d->eo; p.ev = d->ev;
   p.ldf = d->ldf; p.W2ab = d->W2ab; p.W2n = d->W2n; p.Pab = d->Pab; p.Pn = d->Pn; p.Gij = d->Gij; p.Xij = d->Xij;
   p.scratch = d->scratch;
-  t3_density_forms_kernel<<<dim3(p.nt, p.nt), 512, 0, st>>>(p);
+  if ((double)d->nk * d->nv * d->nv * d->nv >= 4294967296.0 || (double)d->no * d->no * d->nv * d->nv >= 4294967296.0) {
+    set_error("b200cc_t3_density_forms: nk*nv^3 and no^2*nv^2 must stay below 2^32 (shorten the k run)");
+    return 1;
+  }
+  if (p.swap_ab) t3_density_forms_kernel<true><<<dim3(p.nt, p.nt), 512, 0, st>>>(p);
+  else t3_density_forms_kernel<false><<<dim3(p.nt, p.nt), 512, 0, st>>>(p);
   if (check_launch("t3_density_forms_kernel")) return 1;
   const i64 stride = (i64)d->nv * p.nt;
   if (launch_final_reduce(d->scratch, p.nt, p.nt, d->nv, d->dvv, 1, 1.0, st)) return 1;

@@ -55,6 +55,17 @@ def auto_ksplit(M, N, K, batch):
     return best
 
 
+def balanced_ksplit(M, N, K, batch=1, rounds=12):
+    """Split-K factor for long-K products with FEW, RAGGED output tiles (the o v^2-long contractions of t3_density,
+    M = N = v): units are scheduled dynamically, so a ragged 128x128 tiling only balances when every SM gets many
+    units -- aim at ``rounds`` units per SM, but keep >= 64 k-tiles per unit."""
+    tiles = ((M + 127) // 128) * ((N + 127) // 128) * batch
+    kt = (K + 15) // 16
+    if tiles >= rounds * NSM or kt < 128:
+        return auto_ksplit(M, N, K, batch)
+    return int(max(1, min(-(-rounds * NSM // tiles), kt // 64, 4096)))
+
+
 # ---- mixed precision (precision='MP'): large K-major x K-major products go to the tcgen05 split-TF32 GEMM --------
 class _Mixed:
     """Process-wide switch set by DeviceManager(precision='MP').  ``min_flops``: smaller products stay on the FP64
@@ -417,8 +428,10 @@ def t3_connected_batch(no, nv, ijk, Q, eo, ev, out):
     return out
 
 
-def t3_density_forms(no, nv, i, j, k0, nk, M3, t1, t2, oovv, fov, eo, ev, W2ab, W2n, Pab, Pn, Gij, Xij, dvv, Dov, S1):
-    """The non-GEMM part of the t3_density loop body for fixed (i,j) and k0 <= k < k0+nk (b200cc_t3_density_forms)."""
+def t3_density_forms(no, nv, i, j, k0, nk, M3, t1, t2s, oovvs, fov, eo, ev, W2ab, W2n, Pab, Pn, Gij, Xij, dvv, Dov, S1,
+                     swap_ab=False):
+    """The non-GEMM part of the t3_density loop body for fixed (i,j) and k0 <= k < k0+nk (b200cc_t3_density_forms).
+    t2s = 4 t2 - 2 t2^T(ab), oovvs = 4<ij|ab> - 2<ij|ba>; swap_ab: M3 is the run of the transposed pair (j,i)."""
     need = nk * nv ** 3
     for t in (M3, W2ab, W2n, Pab, Pn):
         if t.numel() < need or not t.is_contiguous():
@@ -431,7 +444,8 @@ def t3_density_forms(no, nv, i, j, k0, nk, M3, t1, t2, oovv, fov, eo, ev, W2ab, 
     sc = _scratch(M3.device, max(1, int(_lib.get().b200cc_t3_density_scratch(int(nv)))))
     d = T3dDesc()
     d.no, d.nv, d.i, d.j, d.k0, d.nk = int(no), int(nv), int(i), int(j), int(k0), int(nk)
-    d.M3, d.t1, d.t2, d.oovv = _lib.ptr(M3), _lib.ptr(_c(t1, "t1")), _lib.ptr(_c(t2, "t2")), _lib.ptr(_c(oovv, "oovv"))
+    d.swap_ab = int(bool(swap_ab))
+    d.M3, d.t1, d.t2s, d.oovvs = _lib.ptr(M3), _lib.ptr(_c(t1, "t1")), _lib.ptr(_c(t2s, "t2s")), _lib.ptr(_c(oovvs, "oovvs"))
     d.fov, d.ldf = _lib.ptr(fov), int(fov.stride(0))
     d.eo, d.ev = _lib.ptr(eo), _lib.ptr(ev)
     d.W2ab, d.W2n, d.Pab, d.Pn = _lib.ptr(W2ab), _lib.ptr(W2n), _lib.ptr(Pab), _lib.ptr(Pn)

@@ -365,8 +365,8 @@ class EmuLib:
         v3 = nv ** 3
         M = _vec(d.M3, nk * v3).reshape(nk, nv, nv, nv)
         T1 = _arr(d.t1, (no, nv), (nv, 1))
-        T2 = _vec(d.t2, no * no * nv * nv).reshape(no, no, nv, nv)
-        Kv = _vec(d.oovv, no * no * nv * nv).reshape(no, no, nv, nv)
+        Ts = _vec(d.t2s, no * no * nv * nv).reshape(no, no, nv, nv)
+        Ks = _vec(d.oovvs, no * no * nv * nv).reshape(no, no, nv, nv)
         f = _arr(d.fov, (no, nv), (d.ldf, 1))
         W2ab = _vec(d.W2ab, nk * v3).reshape(nv, nv, nk, nv)
         W2n = _vec(d.W2n, nk * v3).reshape(nv, nk, nv, nv)
@@ -378,12 +378,20 @@ class EmuLib:
         def sym(A):
             return (8.0 * A - 4.0 * A.transpose(1, 0, 2) - 4.0 * A.transpose(0, 2, 1) - 4.0 * A.transpose(2, 1, 0)
                     + 2.0 * A.transpose(2, 0, 1) + 2.0 * A.transpose(1, 2, 0))
+
+        def symd(Aij, Aik, Ajk, wi, wj, wk):
+            """sym() of  Aij[x,y] wk[z] + Aik[x,z] wj[y] + Ajk[y,z] wi[x]  from the A~ = 4A - 2A^T combinations"""
+            e = np.einsum
+            return (2.0 * e("ab,c->abc", Aij, wk) - e("ac,b->abc", Aij, wk) - e("cb,a->abc", Aij, wk)
+                    + 2.0 * e("ac,b->abc", Aik, wj) - e("bc,a->abc", Aik, wj) - e("ab,c->abc", Aik, wj)
+                    + 2.0 * e("bc,a->abc", Ajk, wi) - e("ac,b->abc", Ajk, wi) - e("ba,c->abc", Ajk, wi))
         e = np.einsum
         for kk in range(nk):
             k = d.k0 + kk
-            M3 = M[kk]
-            N3 = self._disc(no, nv, i, j, k, d.t1, d.t2, d.oovv, d.fov, d.ldf) / self._den(no, nv, i, j, k, d.eo, d.ev)
-            X3, Y3 = sym(M3), sym(N3)
+            M3 = M[kk].transpose(1, 0, 2) if d.swap_ab else M[kk]
+            Y3 = (symd(Ks[i, j], Ks[i, k], Ks[j, k], T1[i], T1[j], T1[k])
+                  + symd(Ts[i, j], Ts[i, k], Ts[j, k], f[i], f[j], f[k])) / self._den(no, nv, i, j, k, d.eo, d.ev)
+            X3 = sym(M3)
             W2 = 2.0 * X3 + Y3
             P = 2.0 * M3 - M3.transpose(0, 2, 1) - M3.transpose(2, 1, 0)
             U = M3 - M3.transpose(2, 1, 0)
@@ -395,8 +403,8 @@ class EmuLib:
             Gij += 4.0 * e("c,abc->ab", T1[k], Z3)
             Xij += e("abc,c->ab", U, f[k])
             dvv += 0.5 * e("abc,abc->a", M3, X3 + Y3)
-            Dov += e("abc,bc->a", U, 4.0 * T2[j, k] - 2.0 * T2[j, k].T)
-            S1 += e("abc,bc->a", 2.0 * (M3 - M3.transpose(1, 0, 2)), 2.0 * Kv[j, k] - Kv[j, k].T)
+            Dov += e("abc,bc->a", U, Ts[j, k])
+            S1 += e("abc,bc->a", M3 - M3.transpose(1, 0, 2), Ks[j, k])
         return 0
 
 
