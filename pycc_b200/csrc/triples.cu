@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(512, 2) t3_connected_kernel(int no, int nv, in
                                                               const double* __restrict__ Q,
                                                               const double* __restrict__ eo,
                                                               const double* __restrict__ ev, double* __restrict__ M3) {
-  __shared__ double Wsm[512];
+  __shared__ double Wsm[WTILE];
   int rem = blockIdx.x;
   const int TC = rem % nt; rem /= nt;
   const int TB = rem % nt;
@@ -225,23 +225,26 @@ __global__ void __launch_bounds__(512, 2) t3_connected_kernel(int no, int nv, in
   const int T[3] = {TA * TT, TB * TT, TC * TT};
   const int u[3] = {(int)(threadIdx.x >> 6), (int)((threadIdx.x >> 3) & 7), (int)(threadIdx.x & 7)};
   constexpr int PI[6][3] = {{0, 1, 2}, {0, 2, 1}, {2, 0, 1}, {2, 1, 0}, {1, 2, 0}, {1, 0, 2}};
+  double val[6];               // all six loads in flight before the first barrier
 #pragma unroll
   for (int n = 0; n < 6; ++n) {
-    const int r0 = PI[n][0], r1 = PI[n][1], r2 = PI[n][2];
-    const int x = T[r0] + u[0], y = T[r1] + u[1], z = T[r2] + u[2];
-    double val = 0.0;
-    if (x < nv && y < nv && z < nv) val = __ldg(Qt + (i64)n * v3 + ((i64)x * nv + y) * nv + z);
+    const int x = T[PI[n][0]] + u[0], y = T[PI[n][1]] + u[1], z = T[PI[n][2]] + u[2];
+    val[n] = 0.0;
+    if ((x < nv) & (y < nv) & (z < nv)) val[n] = __ldg(Qt + (i64)n * v3 + ((i64)x * nv + y) * nv + z);
+  }
+#pragma unroll
+  for (int n = 0; n < 6; ++n) {
     int l[3];
-    l[r0] = u[0]; l[r1] = u[1]; l[r2] = u[2];
-    double* dst = &Wsm[swz(l[0], l[1], l[2])];
-    if (n == 0) *dst = val;
-    else *dst += val;
+    l[PI[n][0]] = u[0]; l[PI[n][1]] = u[1]; l[PI[n][2]] = u[2];
+    double* dst = &Wsm[l[0] * SA + l[1] * SB + l[2]];
+    if (n == 0) *dst = val[n];
+    else *dst += val[n];
     __syncthreads();
   }
   const int a = T[0] + u[0], b = T[1] + u[1], c = T[2] + u[2];
   if (a < nv && b < nv && c < nv) {
     const double den = eo[i] + eo[j] + eo[k] - ev[a] - ev[b] - ev[c];
-    M3[(i64)trip * v3 + ((i64)a * nv + b) * nv + c] = Wsm[swz(u[0], u[1], u[2])] / den;
+    M3[(i64)trip * v3 + ((i64)a * nv + b) * nv + c] = Wsm[u[0] * SA + u[1] * SB + u[2]] / den;
   }
 }
 
@@ -275,10 +278,25 @@ struct T3dArgs {
   double *W2ab, *W2n, *Pab, *Pn, *Gij, *Xij, *scratch;
 };
 
+constexpr int T3D_NST = 4;                    // ring depth
+constexpr int T3D_STAGE = 6 * 512 + 12 * 64 + 64;  // doubles per stage: M3 blocks, K~/T~ tiles, seven c-vectors
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool pred) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = pred ? 8 : 0;            // src-size 0: nothing is read, the 8 bytes are zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
 template <bool SWAP>
 __global__ void __launch_bounds__(512, 1) t3_density_forms_kernel(const T3dArgs p) {
-  __shared__ double Wsm[6][512];
-  __shared__ double Tl[12][64];
+  // NST-deep ring of stages filled by cp.async (8-byte copies straight into the swizzled slots, zero-fill out of range):
+  // stage = six 8x8x8 M3 blocks + twelve 8x8 K~/T~ tiles = 30 KB.  With one CTA per SM and ~2 us of loaded DRAM latency a
+  // single register-prefetched stage kept only 32 KB per SM in flight (measured 1.9 TB/s of DRAM traffic); the ring
+  // keeps NST-1 stages in flight and needs ONE __syncthreads per cube.
+  extern __shared__ double dsm[];
   __shared__ double red[16][3];
   const int nv = p.nv, nt = p.nt, no = p.no;
   const int TA = blockIdx.y, TB = blockIdx.x;
@@ -337,20 +355,31 @@ __global__ void __launch_bounds__(512, 1) t3_density_forms_kernel(const T3dArgs 
     else { toff[h] = base + xs * nv + lc; tstep[h] = TT; }
   }
   int nTC = 0, nkk = 0;      // (k, c-cube) of the NEXT iteration to load
-  double nm[6], ntl[2];
-  auto load_next = [&]() {
+  auto issue_next = [&](int stage) {
+    double* Ws = dsm + stage * T3D_STAGE;
     const int c0 = nTC * TT;
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
-      nm[r] = 0.0;
-      if (((abok >> r) & 1u) && (c0 + ucp[r] < nv)) nm[r] = __ldg(p.M3 + moff[r]);
+      const bool ok = ((abok >> r) & 1u) && (c0 + ucp[r] < nv);
+      cp_async8(Ws + r * 512 + dsto[r], p.M3 + (ok ? moff[r] : 0u), ok);
       moff[r] += mstep[r];
     }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      ntl[h] = 0.0;
-      if (tok[h] && (c0 + lc < nv)) ntl[h] = __ldg(tbase[h] + toff[h]);
+      if (h == 0 || has1) {
+        const bool ok = tok[h] && (c0 + lc < nv);
+        cp_async8(Ws + 3072 + tl[h] * 64 + lb * 8 + lc, tbase[h] + (ok ? toff[h] : 0u), ok);
+      }
       toff[h] += tstep[h];
+    }
+    if (threadIdx.x < 56) {
+      // the c-dependent vectors of this cube: t1[k], t1[j], t1[i], f[k], f[j], f[i], eps_v  (vector q = tid / 8)
+      const int q = (int)(threadIdx.x >> 3), k = p.k0 + nkk;
+      const double* src = q == 6 ? p.ev
+                                 : (q < 3 ? p.t1 + (i64)(q == 0 ? k : (q == 1 ? p.j : p.i)) * nv
+                                          : p.fov + (i64)(q == 3 ? k : (q == 4 ? p.j : p.i)) * p.ldf);
+      const bool ok = c0 + lc < nv;
+      cp_async8(Ws + 3840 + threadIdx.x, src + (ok ? c0 + lc : 0), ok);
     }
     if (++nTC == nt) {
       nTC = 0; ++nkk;
@@ -384,7 +413,12 @@ __global__ void __launch_bounds__(512, 1) t3_density_forms_kernel(const T3dArgs 
   double accG = 0.0, accX = 0.0, accD = 0.0, accO = 0.0, accS = 0.0;
   double Kik_ab = 0.0, Tik_ab = 0.0, Kjk_ba = 0.0, Tjk_ba = 0.0, t1ka = 0.0, t1kb = 0.0, fka = 0.0, fkb = 0.0, eabk = 0.0;
   const double *t1k = p.t1, *fk = p.fov;
-  load_next();
+#pragma unroll
+  for (int st0 = 0; st0 < T3D_NST - 1; ++st0) {
+    if (nkk < p.nk) issue_next(st0);
+    cp_async_commit();
+  }
+  int stage = 0;
   for (int kk = 0; kk < p.nk; ++kk) {
     {
       const int k = p.k0 + kk;
@@ -396,23 +430,28 @@ __global__ void __launch_bounds__(512, 1) t3_density_forms_kernel(const T3dArgs 
       eabk = eij + p.eo[k] - evab;
     }
     for (int TC = 0; TC < nt; ++TC) {
-#pragma unroll
-      for (int r = 0; r < 6; ++r) Wsm[r][dsto[r]] = nm[r];
-      Tl[tl[0]][bc_] = ntl[0];
-      if (has1) Tl[tl[1]][bc_] = ntl[1];
-      __syncthreads();
-      if (nkk < p.nk) load_next();
+      cp_async_wait<T3D_NST - 2>();
+      __syncthreads();          // stage `stage` has landed for everyone; everyone is done with the stage refilled next
+      {
+        const int fill = stage == 0 ? T3D_NST - 1 : stage - 1;
+        if (nkk < p.nk) issue_next(fill);
+        cp_async_commit();
+      }
+      const double* Wsm = dsm + stage * T3D_STAGE;
+      const double* Tl = Wsm + 3072;
+      stage = stage + 1 == T3D_NST ? 0 : stage + 1;
       const int c = TC * TT + lc;
       if (ab_ok && c < nv) {
-        const double m0 = Wsm[SWAP ? 2 : 0][s], m1 = Wsm[SWAP ? 4 : 1][s], m2 = Wsm[SWAP ? 0 : 2][s];
-        const double m3 = Wsm[SWAP ? 5 : 3][s], m4 = Wsm[SWAP ? 1 : 4][s], m5 = Wsm[SWAP ? 3 : 5][s];
-        const double Kij_ac = Tl[0][ac_], Kij_cb = Tl[1][bc_], Kik_ac = Tl[2][ac_], Kik_bc = Tl[3][bc_];
-        const double Kjk_bc = Tl[4][bc_], Kjk_ac = Tl[5][ac_];
-        const double Tij_ac = Tl[6][ac_], Tij_cb = Tl[7][bc_], Tik_ac = Tl[8][ac_], Tik_bc = Tl[9][bc_];
-        const double Tjk_bc = Tl[10][bc_], Tjk_ac = Tl[11][ac_];
-        const double t1kc = __ldg(t1k + c), t1jc = __ldg(t1j + c), t1ic = __ldg(t1i + c);
-        const double fkc = __ldg(fk + c), fjc = __ldg(fj + c), fic = __ldg(fi + c);
-        const double rden = 1.0 / (eabk - __ldg(p.ev + c));
+        const double m0 = Wsm[(SWAP ? 2 : 0) * 512 + s], m1 = Wsm[(SWAP ? 4 : 1) * 512 + s];
+        const double m2 = Wsm[(SWAP ? 0 : 2) * 512 + s], m3 = Wsm[(SWAP ? 5 : 3) * 512 + s];
+        const double m4 = Wsm[(SWAP ? 1 : 4) * 512 + s], m5 = Wsm[(SWAP ? 3 : 5) * 512 + s];
+        const double Kij_ac = Tl[0 * 64 + ac_], Kij_cb = Tl[1 * 64 + bc_], Kik_ac = Tl[2 * 64 + ac_];
+        const double Kik_bc = Tl[3 * 64 + bc_], Kjk_bc = Tl[4 * 64 + bc_], Kjk_ac = Tl[5 * 64 + ac_];
+        const double Tij_ac = Tl[6 * 64 + ac_], Tij_cb = Tl[7 * 64 + bc_], Tik_ac = Tl[8 * 64 + ac_];
+        const double Tik_bc = Tl[9 * 64 + bc_], Tjk_bc = Tl[10 * 64 + bc_], Tjk_ac = Tl[11 * 64 + ac_];
+        const double* Vs = Wsm + 3840 + lc;
+        const double t1kc = Vs[0], t1jc = Vs[8], t1ic = Vs[16], fkc = Vs[24], fjc = Vs[32], fic = Vs[40];
+        const double rden = 1.0 / (eabk - Vs[48]);
         const double Yn = (2.0 * Kij_ab * t1kc - Kij_ac * t1kb - Kij_cb * t1ka)
                           + (2.0 * Kik_ac * t1jb - Kik_bc * t1ja - Kik_ab * t1jc)
                           + (2.0 * Kjk_bc * t1ia - Kjk_ac * t1ib - Kjk_ba * t1ic)
@@ -434,7 +473,6 @@ __global__ void __launch_bounds__(512, 1) t3_density_forms_kernel(const T3dArgs 
         accS += (m0 - m2) * Kjk_bc;
       }
       oab += TT; on += TT;
-      __syncthreads();
     }
     oab += nv - (i64)nt * TT;
     on += vv - (i64)nt * TT;
@@ -548,8 +586,15 @@ extern "C" int b200cc_t3_density_forms(const b200cc_t3d_desc* d, void* stream) {
     set_error("b200cc_t3_density_forms: nk*nv^3 and no^2*nv^2 must stay below 2^32 (shorten the k run)");
     return 1;
   }
-  if (p.swap_ab) t3_density_forms_kernel<true><<<dim3(p.nt, p.nt), 512, 0, st>>>(p);
-  else t3_density_forms_kernel<false><<<dim3(p.nt, p.nt), 512, 0, st>>>(p);
+  constexpr int SMEM = T3D_NST * T3D_STAGE * (int)sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    B200CC_CUDA_OK(cudaFuncSetAttribute(t3_density_forms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    B200CC_CUDA_OK(cudaFuncSetAttribute(t3_density_forms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  if (p.swap_ab) t3_density_forms_kernel<true><<<dim3(p.nt, p.nt), 512, SMEM, st>>>(p);
+  else t3_density_forms_kernel<false><<<dim3(p.nt, p.nt), 512, SMEM, st>>>(p);
   if (check_launch("t3_density_forms_kernel")) return 1;
   const i64 stride = (i64)d->nv * p.nt;
   if (launch_final_reduce(d->scratch, p.nt, p.nt, d->nv, d->dvv, 1, 1.0, st)) return 1;
