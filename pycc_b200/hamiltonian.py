@@ -221,6 +221,73 @@ class BlockHamiltonian:
             H.vvvv_planes = planes
         return H
 
+    @classmethod
+    def from_ao(cls, F_ao, eri_ao, C, no, nfzc=0, device="cuda", a_range=None, chunk_bytes=4 << 30):
+        """AO -> MO integral staging straight into the six device blocks (reference:
+        hamiltonian.py:54-70, which asks psi4 for the full n^4 MO array on the host and forms ERI and L there).
+
+        ``F_ao`` (nbf,nbf) AO Fock matrix, ``eri_ao`` (nbf,)*4 AO repulsion integrals in CHEMIST order (mu lam|nu sig)
+        (psi4 ``MintsHelper.ao_eri()``), ``C`` (nbf,nmo) MO coefficients in energy order with the frozen core in
+        columns [0:nfzc] (wavefunction.py:304-315).  Computes, with the package's own GEMM kernel only,
+
+            F_pq    = C_mu,p F_mu,nu C_nu,q                                            (hamiltonian.py:55-56)
+            <pq|rs> = (pr|qs) = C_mu,p C_lam,r C_nu,q C_sig,s (mu lam|nu sig)          (hamiltonian.py:67-68)
+
+        as four quarter transformations per block family.  The first two indices (p,r) are transformed once per
+        family -- (o,o) feeds oooo/ooov/ovov, (o,v) feeds oovv/ovvv -- and <ab|ef> is produced in row chunks of a
+        (``chunk_bytes``), directly for this rank's ``a_range``: neither the n^4 MO array nor L ever exists, on
+        the host or on the device.  The AO array itself is held on the device (nbf^4 doubles)."""
+        dev = torch.device(device)
+        ct = Contractor()
+        as_dev = lambda x: torch.as_tensor(np.ascontiguousarray(np.asarray(x), dtype=np.float64)).to(dev)
+        C = as_dev(C)
+        nbf, nmo = C.shape
+        nv = nmo - no - nfzc
+        Co = K.permuted(C[:, nfzc:nfzc + no], (0, 1))
+        Cv = K.permuted(C[:, nfzc + no:], (0, 1))
+        F = ct("mp,mn,nq->pq", C, as_dev(F_ao), C)
+        AO = as_dev(eri_ao)
+        if tuple(AO.shape) != (nbf,) * 4:
+            raise B200ccError("from_ao: eri_ao must have shape (nbf,nbf,nbf,nbf) = %r" % ((nbf,) * 4,))
+
+        def finish(X2, Cq, Cs):
+            """X2[p,r,nu,sig] -> <pq|rs>[p,q,r,s]"""
+            Y = ct("prns,nq->prqs", X2, Cq)
+            Z = ct("prqs,st->prqt", Y, Cs)
+            del Y
+            return K.permuted(Z, (0, 2, 1, 3))
+
+        blocks = {}
+        X1 = ct("mp,mlns->plns", Co, AO)                        # first index -> occupied
+        X2 = ct("plns,lr->prns", X1, Co)                        # (p,r) = (o,o)
+        blocks["oooo"] = finish(X2, Co, Co)
+        blocks["ooov"] = finish(X2, Co, Cv)                     # <mn|ie> = (mi|ne)
+        blocks["ovov"] = finish(X2, Cv, Cv)                     # <mb|je> = (mj|be)
+        X2 = ct("plns,lr->prns", X1, Cv)                        # (p,r) = (o,v)
+        del X1
+        blocks["oovv"] = finish(X2, Co, Cv)                     # <mn|ef> = (me|nf)
+        blocks["ovvv"] = finish(X2, Cv, Cv)                     # <mb|ef> = (me|bf)
+        del X2
+        a_lo, a_hi = (0, nv) if a_range is None else (int(a_range[0]), int(a_range[1]))
+        na = a_hi - a_lo
+        vvvv = torch.empty((na, nv, nv, nv), dtype=torch.float64, device=dev)
+        rows = max(1, min(max(na, 1), int(chunk_bytes // (8 * max(nbf, 1) ** 3))))
+        for a0 in range(0, na, rows):
+            a1 = min(na, a0 + rows)
+            Ca = K.permuted(Cv[:, a_lo + a0:a_lo + a1], (0, 1))
+            X1 = ct("mp,mlns->plns", Ca, AO)
+            X2 = ct("plns,lr->prns", X1, Cv)                    # (a,e)
+            del X1
+            Y = ct("prns,nq->prqs", X2, Cv)
+            del X2
+            Z = ct("prqs,st->prqt", Y, Cv)                      # [a,e,b,f]
+            del Y
+            K.strided_axpby(vvvv[a0:a1], Z.permute(0, 2, 1, 3), 1.0, 0.0)
+            del Z
+        blocks["vvvv"] = vvvv
+        del AO
+        return cls(F, blocks, no, nfzc, dev, a_range)
+
     # ---- derived constant layouts (built once, cached) ---------------------------------------------
     def derived(self, key):
         """Constant rearrangements of the blocks used by the fused residual (see ccwfn.py):

@@ -7,6 +7,8 @@ nfzc, E_ref) works, through :class:`IntegralReference`:
 * ``IntegralReference.from_arrays(F, ERI, no, nfzc, eref)`` -- host arrays (e.g. dumped from psi4);
 * ``IntegralReference.from_synthetic(syn)``                 -- factorised synthetic integrals, contracted
                                                               into blocks on the device;
+* ``IntegralReference.from_ao(F_ao, eri_ao, C, no, nfzc)``    -- AO-basis arrays; the AO -> MO transformation runs on
+                                                              the device, block by block (hamiltonian.py:54-70);
 * ``IntegralReference.from_psi4(scf_wfn)``                  -- same calls as pycc/hamiltonian.py:58-68.
 A raw psi4 wavefunction or a ``Synthetic`` passed to ``CCwfn`` is converted automatically.
 """
@@ -53,6 +55,19 @@ class IntegralReference:
         def make(device, comm, mixed):
             a_range = None if comm is None else comm.a_range(syn.nv)
             return BlockHamiltonian.from_factor(syn, device, a_range=a_range, mixed=mixed)
+        r._make = make
+        return r
+
+    @classmethod
+    def from_ao(cls, F_ao, eri_ao, C, no, nfzc=0, eref=0.0):
+        """AO-basis inputs (Fock matrix, chemist-order repulsion integrals, MO coefficients): the AO -> MO
+        transformation runs on the device, straight into the six blocks (BlockHamiltonian.from_ao)."""
+        r = cls(eref)
+
+        def make(device, comm, mixed):
+            nv = np.asarray(C).shape[1] - no - nfzc
+            a_range = None if comm is None else comm.a_range(nv)
+            return BlockHamiltonian.from_ao(F_ao, eri_ao, C, no, nfzc, device, a_range=a_range)
         r._make = make
         return r
 
