@@ -85,16 +85,14 @@ class Problem:
     # ---- one-body intermediates ---------------------------------------------
     def Fae(self, F, t1, t2):
         o, v = self.o, self.v
-        X = F[v, v].copy()
-        X -= 0.5 * es("me,ma->ae", F[o, v], t1)
+        X = F[v, v] - 0.5 * es("me,ma->ae", F[o, v], t1)
         X += es("mf,mafe->ae", t1, self.Lovvv)
         X -= es("mnaf,mnef->ae", self.tau(t1, t2, 1.0, 0.5), self.Loovv)
         return X
 
     def Fmi(self, F, t1, t2):
         o, v = self.o, self.v
-        X = F[o, o].copy()
-        X += 0.5 * es("ie,me->mi", t1, F[o, v])
+        X = F[o, o] + 0.5 * es("ie,me->mi", t1, F[o, v])
         X += es("ne,mnie->mi", t1, self.Looov)
         X += es("inef,mnef->mi", self.tau(t1, t2, 1.0, 0.5), self.Loovv)
         return X
@@ -104,23 +102,21 @@ class Problem:
 
     # ---- two-body intermediates ---------------------------------------------
     def Wmnij(self, t1, t2):
-        X = self.oooo.copy()
-        X += es("je,mnie->mnij", t1, self.ooov)
+        X = self.oooo + es("je,mnie->mnij", t1, self.ooov)
         X += es("ie,nmje->mnij", t1, self.ooov)          # <mn|ej> = ooov[n,m,j,e]
         X += es("ijef,mnef->mnij", self.tau(t1, t2), self.oovv)
         return X
 
     def Wmbej(self, t1, t2):
-        X = self.oovv.transpose(0, 3, 2, 1).copy()       # <mb|ej> = oovv[m,j,e,b]
-        X += es("jf,mbef->mbej", t1, self.ovvv)
+        # <mb|ej> = oovv[m,j,e,b]   (out-of-place first term: the result takes the amplitudes' dtype, real or complex)
+        X = self.oovv.transpose(0, 3, 2, 1) + es("jf,mbef->mbej", t1, self.ovvv)
         X -= es("nb,nmje->mbej", t1, self.ooov)          # <mn|ej> = ooov[n,m,j,e]
         X -= es("jnfb,mnef->mbej", self.tau(t1, t2, 0.5, 1.0), self.oovv)
         X += 0.5 * es("njfb,mnef->mbej", t2, self.Loovv)
         return X
 
     def Wmbje(self, t1, t2):
-        X = -self.ovov.copy()
-        X -= es("jf,mbfe->mbje", t1, self.ovvv)
+        X = -self.ovov - es("jf,mbfe->mbje", t1, self.ovvv)
         X += es("nb,mnje->mbje", t1, self.ooov)
         X += es("jnfb,mnfe->mbje", self.tau(t1, t2, 0.5, 1.0), self.oovv)
         return X
@@ -132,8 +128,7 @@ class Problem:
     def r1(self, F, t1, t2, Fae, Fme, Fmi):
         o, v = self.o, self.v
         s = 2.0 * t2 - t2.transpose(0, 1, 3, 2)
-        X = F[v, o].T.copy()
-        X += es("ie,ae->ia", t1, Fae)
+        X = F[v, o].T + es("ie,ae->ia", t1, Fae)
         X -= es("mi,ma->ia", Fmi, t1)
         X += es("imae,me->ia", s, Fme)
         # L[n,a,f,i] = 2<na|fi> - <na|if> = 2 oovv[n,i,f,a] - ovov[n,a,i,f]

@@ -239,7 +239,10 @@ class BlockHamiltonian:
         the host or on the device.  The AO array itself is held on the device (nbf^4 doubles)."""
         dev = torch.device(device)
         ct = Contractor()
-        as_dev = lambda x: torch.as_tensor(np.ascontiguousarray(np.asarray(x), dtype=np.float64)).to(dev)
+        def as_dev(x):
+            if isinstance(x, torch.Tensor):
+                return x.to(dev, dtype=torch.float64).contiguous()
+            return torch.as_tensor(np.ascontiguousarray(np.asarray(x), dtype=np.float64)).to(dev)
         C = as_dev(C)
         nbf, nmo = C.shape
         nv = nmo - no - nfzc
