@@ -204,6 +204,154 @@ __device__ __forceinline__ int swz(int l0, int l1, int l2) {
   return ((l0 << 6) | (l1 << 3) | l2) ^ (((l0 & 1) * 9) ^ (l0 & 6) ^ (l1 & 6));
 }
 
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool pred) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = pred ? 8 : 0;            // src-size 0: nothing is read, the 8 bytes are zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// cp.async-staged variant of the (T) energy kernel (plain Q layout).  Two things bound the classic kernel above
+// (2.5 TB/s): its six load / barrier rounds keep only ~50 KB per SM in flight, and -- mostly -- phase 2 evaluates the
+// disconnected t3 at the six permutations with 72 scattered global loads per thread (54 distinct), twice the number of
+// Q loads.  Here
+//  * the 36 (Q_n, permutation) blocks of a cube are copied asynchronously, 18 at a time (72 KB), straight into
+//    conflict-free swizzled slots (element l of target permutation P from Q_n lands in raw[n%3][P][swz(l)]); each thread
+//    then adds its six W values out of shared memory;
+//  * the 36 8x8 tiles of <ij|..>, <ik|..>, <jk|..>, t2[ij], t2[ik], t2[jk] over the ordered pairs of (A,B,C), and the
+//    t1 / f_ov / eps_v segments of the three ranges, ride in the first copy group (4.5 + 0.33 copies per thread), so the
+//    disconnected part is formed from shared memory only.
+// Two CTAs per SM overlap one CTA's copies with the other's arithmetic.
+constexpr int TE_ROUND = 18 * 512;          // doubles staged per round
+constexpr int TE_TP = 9;                    // tile pitch
+constexpr int TE_TILES = 36 * 8 * TE_TP;    // [mat 6][ordered pair 6][8][pitch]
+constexpr int TE_VECS = 7 * 24;             // t1[i], t1[j], t1[k], f[i], f[j], f[k], eps_v  x  ranges A, B, C  x  8
+constexpr int TE_DOUBLES = TE_ROUND + TE_TILES + TE_VECS;
+
+// ordered pair (X,Y), X != Y, of the axes {0:a, 1:b, 2:c}  ->  0..5
+__host__ __device__ constexpr int te_pair(int X, int Y) { return X == 0 ? (Y == 1 ? 0 : 2) : (X == 1 ? (Y == 0 ? 1 : 4) : (Y == 0 ? 3 : 5)); }
+
+// disconnected t3 numerator (cctriples.py:131-137) at the permutation (x,y,z) = (axis X, axis Y, axis Z) of this
+// thread's (a,b,c), from the staged tiles: mat 0..2 = <ij|, <ik|, <jk|; 3..5 = t2[ij], t2[ik], t2[jk]; vec 0..2 = t1[i],
+// t1[j], t1[k]; 3..5 = f[i], f[j], f[k]
+template <int X, int Y, int Z>
+__device__ __forceinline__ double te_disc(const double* tiles, const double* vecs, const int (&l)[3]) {
+  auto tl = [&](int mat, int P, int Q) { return tiles[((mat * 6 + te_pair(P, Q)) * 8 + l[P]) * TE_TP + l[Q]]; };
+  auto vc = [&](int vec, int P) { return vecs[(vec * 3 + P) * 8 + l[P]]; };
+  return tl(0, X, Y) * vc(2, Z) + tl(1, X, Z) * vc(1, Y) + tl(2, Y, Z) * vc(0, X) +
+         tl(3, X, Y) * vc(5, Z) + tl(4, X, Z) * vc(4, Y) + tl(5, Y, Z) * vc(3, X);
+}
+
+__global__ void __launch_bounds__(512, 2) t_energy_cp_kernel(const TArgs p, double* scratch) {
+  extern __shared__ double raw[];    // [3][6][512] | tiles | vecs
+  __shared__ double red[16];
+  double* tiles = raw + TE_ROUND;
+  double* vecs = tiles + TE_TILES;
+  int rem = blockIdx.x, TA = 0;
+  while ((TA + 1) * (TA + 2) * (TA + 3) / 6 <= rem) ++TA;
+  rem -= TA * (TA + 1) * (TA + 2) / 6;
+  int TB = 0;
+  while ((TB + 1) * (TB + 2) / 2 <= rem) ++TB;
+  const int TC = rem - TB * (TB + 1) / 2;
+  const int trip = blockIdx.y;
+  const int i = p.ijk[3 * trip], j = p.ijk[3 * trip + 1], k = p.ijk[3 * trip + 2];
+  const int nv = p.nv, no = p.no;
+  const i64 vv = (i64)nv * nv, v3 = vv * nv;
+  const double* Q = p.Q + (i64)trip * 6 * v3;
+  const int T[3] = {TA * TT, TB * TT, TC * TT};
+  const int u[3] = {(int)(threadIdx.x >> 6), (int)((threadIdx.x >> 3) & 7), (int)(threadIdx.x & 7)};
+  constexpr int PERM[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+  constexpr int PI[6][3] = {{0, 1, 2}, {0, 2, 1}, {2, 0, 1}, {2, 1, 0}, {1, 2, 0}, {1, 0, 2}};
+  const i64 tpart = ((i64)u[0] * nv + u[1]) * nv + u[2];
+  // shared slot of this thread's element for each of the six axis maps rho (index r0*2 + (r1 > r2)), see classic kernel
+  int dsto[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    int l[3];
+    l[PERM[r][0]] = u[0]; l[PERM[r][1]] = u[1]; l[PERM[r][2]] = u[2];
+    dsto[r] = swz(l[0], l[1], l[2]);
+  }
+  const int s = swz(u[0], u[1], u[2]);
+  // ---- tiles and vectors of the disconnected part (first copy group) --------------------------------------------
+  {
+    const i64 pij = ((i64)i * no + j) * vv, pik = ((i64)i * no + k) * vv, pjk = ((i64)j * no + k) * vv;
+    const int row = u[1], col = u[2];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      const int t = (int)(threadIdx.x >> 6) + 8 * q;          // tile 0..35 (q = 4: only tiles 32..35)
+      if (t < 36) {
+        const int mat = t / 6, pr = t - mat * 6;
+        // ordered pair pr -> (X,Y):  0 (a,b)  1 (b,a)  2 (a,c)  3 (c,a)  4 (b,c)  5 (c,b)
+        const int X = pr == 0 || pr == 2 ? 0 : (pr == 1 || pr == 4 ? 1 : 2);
+        const int Y = pr == 1 || pr == 3 ? 0 : (pr == 0 || pr == 5 ? 1 : 2);
+        const int m3 = mat % 3;
+        const double* base = (mat < 3 ? p.oovv : p.t2) + (m3 == 0 ? pij : (m3 == 1 ? pik : pjk));
+        const int x = T[X] + row, y = T[Y] + col;
+        const bool ok = (x < nv) & (y < nv);
+        cp_async8(tiles + (t * 8 + row) * TE_TP + col, base + (ok ? (i64)x * nv + y : 0), ok);
+      }
+    }
+    if (threadIdx.x < TE_VECS) {
+      const int vec = (int)threadIdx.x / 24, rg = ((int)threadIdx.x % 24) >> 3, el = (int)threadIdx.x & 7;
+      const int occ = vec % 3 == 0 ? i : (vec % 3 == 1 ? j : k);
+      const double* src = vec == 6 ? p.ev : (vec < 3 ? p.t1 + (i64)occ * nv : p.fov + (i64)occ * p.ldf);
+      const int x = T[rg] + el;
+      const bool ok = x < nv;
+      cp_async8(vecs + threadIdx.x, src + (ok ? x : 0), ok);
+    }
+  }
+  double W[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+#pragma unroll
+    for (int nn = 0; nn < 3; ++nn) {
+      const int n = half * 3 + nn;
+      const double* Qn = Q + (i64)n * v3;
+#pragma unroll
+      for (int P = 0; P < 6; ++P) {
+        const int r0 = PERM[P][PI[n][0]], r1 = PERM[P][PI[n][1]], r2 = PERM[P][PI[n][2]];
+        const i64 origin = ((i64)T[r0] * nv + T[r1]) * nv + T[r2];
+        const bool ok = (u[0] < nv - T[r0]) & (u[1] < nv - T[r1]) & (u[2] < nv - T[r2]);
+        cp_async8(raw + (nn * 6 + P) * 512 + dsto[r0 * 2 + (r1 > r2 ? 1 : 0)], Qn + (ok ? origin + tpart : 0), ok);
+      }
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+#pragma unroll
+    for (int P = 0; P < 6; ++P) W[P] += raw[P * 512 + s] + raw[(6 + P) * 512 + s] + raw[(12 + P) * 512 + s];
+    if (half == 0) __syncthreads();   // everyone has read round 0 before round 1 overwrites it
+  }
+
+  const int l[3] = {u[0], u[1], u[2]};
+  const int a = T[0] + l[0], b = T[1] + l[1], c = T[2] + l[2];
+  double e = 0.0;
+  if (a < nv && b <= a && c <= b) {
+    const double sc = 1.0 / (1.0 + (a == b ? 1.0 : 0.0) + (a == c ? 1.0 : 0.0) + (b == c ? 1.0 : 0.0));
+    const double Wabc = W[0], Wacb = W[1], Wbac = W[2], Wbca = W[3], Wcab = W[4], Wcba = W[5];
+    const double Vabc = (Wabc + te_disc<0, 1, 2>(tiles, vecs, l)) * sc, Vacb = (Wacb + te_disc<0, 2, 1>(tiles, vecs, l)) * sc;
+    const double Vbac = (Wbac + te_disc<1, 0, 2>(tiles, vecs, l)) * sc, Vbca = (Wbca + te_disc<1, 2, 0>(tiles, vecs, l)) * sc;
+    const double Vcab = (Wcab + te_disc<2, 0, 1>(tiles, vecs, l)) * sc, Vcba = (Wcba + te_disc<2, 1, 0>(tiles, vecs, l)) * sc;
+    const double X = Wabc * Vabc + Wacb * Vacb + Wbac * Vbac + Wbca * Vbca + Wcab * Vcab + Wcba * Vcba;
+    const double Y = Vabc + Vbca + Vcab, Z = Vacb + Vbac + Vcba;
+    const double Wc = Wabc + Wbca + Wcab, Wo = Wacb + Wbac + Wcba;
+    const double den = p.eo[i] + p.eo[j] + p.eo[k] - vecs[(6 * 3 + 0) * 8 + l[0]] - vecs[(6 * 3 + 1) * 8 + l[1]] -
+                       vecs[(6 * 3 + 2) * 8 + l[2]];
+    const double occ = 2.0 - ((i == j ? 1.0 : 0.0) + (i == k ? 1.0 : 0.0) + (j == k ? 1.0 : 0.0));
+    e = ((Y - 2.0 * Z) * Wc + (Z - 2.0 * Y) * Wo + 3.0 * X) * occ / den;
+  }
+  e = warp_sum(e);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double s2 = threadIdx.x < 16 ? red[threadIdx.x] : 0.0;
+    s2 = warp_sum(s2);
+    if (threadIdx.x == 0) scratch[(i64)trip * gridDim.x + blockIdx.x] = s2;
+  }
+}
+
 // ---- (T) densities (cctriples.py:1063-1157) ---------------------------------------------------------------------
 // Step 1: connected t3 WITH denominators of a batch of triples, M3[t][a,b,c] = (Q1[a,b,c] + Q2[a,c,b] + Q3[c,a,b] +
 // Q4[c,b,a] + Q5[b,c,a] + Q6[b,a,c]) / D.  One CTA per 8x8x8 cube of the FULL (a,b,c) space; the six source blocks are
@@ -280,15 +428,6 @@ struct T3dArgs {
 
 constexpr int T3D_NST = 4;                    // ring depth
 constexpr int T3D_STAGE = 6 * 512 + 12 * 64 + 64;  // doubles per stage: M3 blocks, K~/T~ tiles, seven c-vectors
-
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool pred) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-  const int sz = pred ? 8 : 0;            // src-size 0: nothing is read, the 8 bytes are zero-filled
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(gsrc), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 template <bool SWAP>
 __global__ void __launch_bounds__(512, 1) t3_density_forms_kernel(const T3dArgs p) {
@@ -532,7 +671,17 @@ extern "C" int b200cc_t_energy_batch(int no, int nv, int ntrip, const int* ijk, 
   // hoisted index arithmetic measured 2.47 vs 2.03 TB/s on B200 (profiles/t_probe_r01_hoist.log); B200CC_T_HOIST=0 selects
   // the per-element form
   static const bool hoist = [] { const char* e = getenv("B200CC_T_HOIST"); return !(e && e[0] == '0'); }();
+  // cp.async-staged kernel (plain Q layout): B200CC_T_ENERGY=classic selects the register-load kernels below
+  static const bool use_cp = [] { const char* e = getenv("B200CC_T_ENERGY"); return !(e && e[0] == 'c'); }();
+  constexpr int TE_SMEM = TE_DOUBLES * (int)sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    B200CC_CUDA_OK(cudaFuncSetAttribute(t_energy_cp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TE_SMEM));
+    // (forcing the largest shared-memory carve-out was measured much SLOWER, 1.86 vs 2.88 TB/s: cp.async.ca wants its L1)
+    configured = true;
+  }
   if (p.blocked) t_energy_kernel<true, false><<<dim3(ncube, ntrip), 512, 0, st>>>(p, scratch);
+  else if (use_cp) t_energy_cp_kernel<<<dim3(ncube, ntrip), 512, TE_SMEM, st>>>(p, scratch);
   else if (hoist) t_energy_kernel<false, true><<<dim3(ncube, ntrip), 512, 0, st>>>(p, scratch);
   else t_energy_kernel<false, false><<<dim3(ncube, ntrip), 512, 0, st>>>(p, scratch);
   if (check_launch("t_energy_kernel")) return 1;
