@@ -10,7 +10,8 @@ blocks (``BlockHamiltonian.ERI`` / ``.L``), never an n^4 array.  The reference's
 pairs are written as the two contractions they are.
 
 This is the correctness-first slice of the row (parity against the reference's golden vectors and the numpy oracle);
-the products go through the generic planner, not yet through fused layouts as the CCSD residual does.
+the products go through the generic planner, not yet through fused layouts as the CCSD residual does.  ``Hvvvv`` (v^4
+doubles, 64.8 GB at v=300) is never needed as a tensor on the Lambda path and is materialised lazily, see EAGER.
 CC2 / CC3 / spin-orbital branches of the reference are outside the accelerated path.
 """
 from __future__ import annotations
@@ -63,8 +64,11 @@ _TABLE = {
     "Hvvvo": ("E:vvvo", [(-1.0, "me,miab->abei", "Hov", "t2"), (1.0, "mnab,mnei->abei", "tau", "E:oovo"),
                          (-1.0, "imfa,bmfe->abei", "t2", "E:vovv"), (-1.0, "imfb,amef->abei", "t2", "E:vovv"),
                          (1.0, "mifb,amef->abei", "t2", "L:vovv")],
-              [(1.0, "if,abef->abei", "t1", "Hvvvv"), (-1.0, "mb,amei->abei", "t1", "X:vovo"),
-               (-1.0, "ma,bmie->abei", "t1", "X:voov")]),
+              # t_if H_abef without H_abef (64.8 GB at v=300): t_if <ab|ef> - t_mb (t_if <am|ef>) - t_ma (t_if <bm|fe>)
+              # + tau_mnab (t_if <mn|ef>); the three small products are the single-term intermediates I:* below
+              [(1.0, "if,abef->abei", "t1", "E:vvvv"), (-1.0, "mb,amei->abei", "t1", "I:amei"),
+               (-1.0, "ma,bmei->abei", "t1", "I:bmei"), (1.0, "mnab,mnei->abei", "tau", "I:mnei"),
+               (-1.0, "mb,amei->abei", "t1", "X:vovo"), (-1.0, "ma,bmie->abei", "t1", "X:voov")]),
     # H_mbij                                                                     cchbar.py:785-823
     "Hovoo": ("E:ovoo", [(1.0, "me,ijeb->mbij", "Hov", "t2"), (1.0, "ijef,mbef->mbij", "tau", "E:ovvv"),
                          (-1.0, "ineb,nmje->mbij", "t2", "E:ooov"), (-1.0, "jneb,mnie->mbij", "t2", "E:ooov"),
@@ -79,7 +83,17 @@ _DRESSED = {
     "X:ovov": ("E:ovov", [(-1.0, "infb,mnfe->mbie", "t2", "E:oovv")]),
     "X:voov2": ("E:voov", [(-1.0, "jnfb,mnef->bmje", "t2", "E:oovv"), (1.0, "njfb,mnef->bmje", "t2", "L:oovv")]),
 }
+# single-term intermediates of the factorised t1.Hvvvv (singles only)
+_INTER = {
+    "I:amei": (1.0, "if,amef->amei", "t1", "E:vovv"),
+    "I:bmei": (1.0, "if,bmfe->bmei", "t1", "E:vovv"),
+    "I:mnei": (1.0, "if,mnef->mnei", "t1", "E:oovv"),
+}
 ORDER = ("Hov", "Hvv", "Hoo", "Hoooo", "Hvvvv", "Hvovv", "Hooov", "Hovvo", "Hovov", "Hvvvo", "Hovoo")
+# H_abef is v^4 doubles -- as large as <ab|ef> itself.  Nothing on the Lambda path needs it as a tensor (cclambda
+# applies it to l2 as one ladder GEMM against <ab|ef> plus three o^3v^3 / o^4v^2 corrections; Hvvvo uses the same
+# factorisation), so it is built only when somebody reads ``hbar.Hvvvv`` / calls ``build_Hvvvv``.
+EAGER = tuple(k for k in ORDER if k != "Hvvvv")
 
 
 class cchbar(object):
@@ -94,10 +108,19 @@ class cchbar(object):
         self.o, self.v = ccwfn.o, ccwfn.v
         self.no, self.nv = ccwfn.no, ccwfn.nv
         blocks = self.build_all(ccwfn.H.F, ccwfn.t1, ccwfn.t2)
-        for k in ORDER:
+        for k in EAGER:
             setattr(self, k, blocks[k])
+        self._Hvvvv = None
+        self._amps = (ccwfn.H.F, ccwfn.t1, ccwfn.t2)
         if not getattr(ccwfn, "quiet", False):
             print(timing("HBAR", time.time() - t0))
+
+    @property
+    def Hvvvv(self):
+        """H_abef (cchbar.py:394-403), materialised on first access (v^4 doubles)."""
+        if self._Hvvvv is None:
+            self._Hvvvv = self._one("Hvvvv", *self._amps)
+        return self._Hvvvv
 
     # ---- evaluation of the tables -----------------------------------------------------------------------
     def _env(self, F, t1, t2):
@@ -112,6 +135,9 @@ class cchbar(object):
     def _operand(self, env, name):
         if name in env:
             return env[name]
+        if name.startswith("I:"):
+            alpha, sub, a, b = _INTER[name]
+            return self.ccwfn._ct(sub, self._operand(env, a), self._operand(env, b), alpha=alpha)
         if name.startswith("X:"):
             init, terms = _DRESSED[name]
             x = K.permuted(_view(self.ccwfn.H, init), (0, 1, 2, 3))
@@ -136,16 +162,16 @@ class cchbar(object):
         env[key] = out
         return out
 
-    def build_all(self, F, t1, t2):
-        """Every block, in dependency order (Hvvvo needs Hov and Hvvvv, Hovoo needs Hov and Hoooo)."""
+    def build_all(self, F, t1, t2, with_vvvv=False):
+        """Every block in dependency order (Hvvvo needs Hov, Hovoo needs Hov and Hoooo); H_abef only on request."""
         env = self._env(F, t1, t2)
-        return {k: self._build(k, env) for k in ORDER}
+        return {k: self._build(k, env) for k in (ORDER if with_vvvv else EAGER)}
 
     # ---- the reference's builders (signatures of cchbar.py:128-823; integrals must be the wavefunction's own) ----
     def _one(self, key, F, t1, t2, **have):
         env = self._env(F, t1, t2)
         env.update({k: x for k, x in have.items() if x is not None})
-        for dep in ("Hov", "Hoooo", "Hvvvv"):
+        for dep in ("Hov", "Hoooo"):
             if dep not in env and any(dep in (a, b) for _, _, a, b in _TABLE[key][1] + _TABLE[key][2]):
                 self._build(dep, env)
         return self._build(key, env)
@@ -187,8 +213,10 @@ class cchbar(object):
         return self._one("Hovov", self.ccwfn.H.F, t1, t2)
 
     def build_Hvvvo(self, o, v, ERI, L, Hov, Hvvvv, t1, t2):
+        """``Hvvvv`` is accepted for signature compatibility (cchbar.py:632) and not read: t1.Hvvvv is evaluated from
+        <ab|ef> directly."""
         self.ccwfn._own(ERI, L)
-        return self._one("Hvvvo", self.ccwfn.H.F, t1, t2, Hov=Hov, Hvvvv=Hvvvv)
+        return self._one("Hvvvo", self.ccwfn.H.F, t1, t2, Hov=Hov)
 
     def build_Hovoo(self, o, v, ERI, L, Hov, Hoooo, t1, t2):
         self.ccwfn._own(ERI, L)

@@ -32,7 +32,7 @@ _R2_SINGLES = [(2.0, "ia,jb->ijab", "l1", "Hov"), (-1.0, "ja,ib->ijab", "l1", "H
                (2.0, "ie,ejab->ijab", "l1", "Hvovv"), (-1.0, "ie,ejba->ijab", "l1", "Hvovv"),
                (-2.0, "mb,jima->ijab", "l1", "Hooov"), (1.0, "mb,ijma->ijab", "l1", "Hooov")]
 _R2 = [(1.0, "ijeb,ea->ijab", "l2", "Hvv"), (-1.0, "mjab,im->ijab", "l2", "Hoo"),
-       (0.5, "mnab,ijmn->ijab", "l2", "Hoooo"), (0.5, "ijef,efab->ijab", "l2", "Hvvvv"),
+       (0.5, "mnab,ijmn->ijab", "l2", "Hoooo"),
        (1.0, "mjeb,ieam->ijab", "l2", "W"), (-1.0, "mibe,jema->ijab", "l2", "Hovov"),
        (-1.0, "mieb,jeam->ijab", "l2", "Hovvo"),
        (1.0, "ae,ijeb->ijab", "Gvv", "Loovv"), (-1.0, "mi,mjab->ijab", "Goo", "Loovv")]
@@ -43,6 +43,8 @@ class cclambda(object):
         if ccwfn.model not in ("CCSD", "CCD"):
             raise NotImplementedError("the Lambda equations are accelerated for closed-shell CCD / CCSD; the (T) "
                                       "sources S1/S2 and CC2/CC3 stay with the reference implementation")
+        if getattr(ccwfn, "part", None) is not None and ccwfn.part.size > 1:
+            raise NotImplementedError("the Lambda solver is single-GPU (its terms are not rank-partitioned yet)")
         self.ccwfn, self.hbar = ccwfn, hbar
         self.contract = ccwfn.contract
         t1, t2 = ccwfn.t1, ccwfn.t2
@@ -82,12 +84,38 @@ class cclambda(object):
                    Hooov=Hooov, Gvv=Gvv, Goo=Goo, W=W if W is not None else self._w(Hovvo, Hovov))
         return self._accumulate(K.permuted(Hov, (0, 1), 2.0), _R1, env)
 
+    def _ladder(self, half, l2, Hvvvv=None):
+        """half += 1/2 l2_ijef H_efab (cclambda.py:468) WITHOUT the v^4 tensor H_efab:
+             1/2 l2_ijef <ef|ab>                      the ladder GEMM of the CCSD residual on <ab|ef> in place
+           - 1/2 (l2_ijef t_mf) <em|ab> - 1/2 (l2_ijef t_me) <fm|ba>                     two o^3v^3 products
+           + 1/2 (l2_ijef tau_mnef) <mn|ab>                                              two o^4v^2 products
+        (cchbar.py:394-403 substituted).  A caller that hands in a materialised ``Hvvvv`` gets the literal term."""
+        w, ct = self.ccwfn, self.ccwfn._ct
+        if Hvvvv is not None:
+            return ct("ijef,efab->ijab", l2, Hvvvv, out=half, alpha=0.5, beta=1.0)
+        with K.mixed_mode(getattr(w, "mixed", False)):
+            w._ladder(l2, half)
+            o, v = w.o, w.v
+            oovv = w.H.ERI[o, o, v, v]
+            if w.model == "CCD":
+                tau = w.t2.contiguous()
+            else:
+                t1 = w.t1.contiguous()
+                vovv = w.H.ERI[v, o, v, v]
+                ct("ijem,emab->ijab", ct("ijef,mf->ijem", l2, t1), vovv, out=half, alpha=-0.5, beta=1.0)
+                ct("ijfm,fmba->ijab", ct("ijef,me->ijfm", l2, t1), vovv, out=half, alpha=-0.5, beta=1.0)
+                tau = K.build_tau(t1, w.t2.contiguous(), 1.0, 1.0)
+            ct("ijmn,mnab->ijab", ct("ijef,mnef->ijmn", l2, tau), oovv, out=half, alpha=0.5, beta=1.0)
+        return half
+
     def _r_L2_half(self, l1, l2, Hov, Hvv, Hoo, Hoooo, Hvvvv, Hovvo, Hovov, Hvovv, Hooov, Gvv, Goo, W):
         Loovv = self.ccwfn.H.derived("Loovv")
-        env = dict(l1=l1.contiguous(), l2=l2.contiguous(), Hov=Hov, Hvv=Hvv, Hoo=Hoo, Hoooo=Hoooo, Hvvvv=Hvvvv,
+        l2 = l2.contiguous()
+        env = dict(l1=l1.contiguous(), l2=l2, Hov=Hov, Hvv=Hvv, Hoo=Hoo, Hoooo=Hoooo,
                    Hovvo=Hovvo, Hovov=Hovov, Hvovv=Hvovv, Hooov=Hooov, Gvv=Gvv, Goo=Goo, W=W, Loovv=Loovv)
         terms = _R2 if self.ccwfn.model == "CCD" else _R2_SINGLES + _R2
-        return self._accumulate(K.permuted(Loovv, (0, 1, 2, 3)), terms, env)
+        half = self._accumulate(K.permuted(Loovv, (0, 1, 2, 3)), terms, env)
+        return self._ladder(half, l2, Hvvvv)
 
     def r_L2(self, o, v, l1, l2, L, Hov, Hvv, Hoo, Hoooo, Hvvvv, Hovvo, Hovov, Hvvvo, Hovoo, Hvovv, Hooov, Gvv, Goo,
              s2=None):
@@ -111,7 +139,7 @@ class cclambda(object):
         W = self._w(hb["Hovvo"], hb["Hovov"])
         r1 = self.r_L1(self.ccwfn.o, self.ccwfn.v, l1, l2, hb["Hov"], hb["Hvv"], hb["Hoo"], hb["Hovvo"], hb["Hovov"],
                        hb["Hvvvo"], hb["Hovoo"], hb["Hvovv"], hb["Hooov"], Gvv, Goo, W=W)
-        half = self._r_L2_half(l1, l2, hb["Hov"], hb["Hvv"], hb["Hoo"], hb["Hoooo"], hb["Hvvvv"], hb["Hovvo"],
+        half = self._r_L2_half(l1, l2, hb["Hov"], hb["Hvv"], hb["Hoo"], hb["Hoooo"], None, hb["Hovvo"],
                                hb["Hovov"], hb["Hvovv"], hb["Hooov"], Gvv, Goo, W)
         return r1, K.symmetrize_r2(half)
 
@@ -133,7 +161,7 @@ class cclambda(object):
             Goo, Gvv = self.build_Goo(w.t2, self.l2), self.build_Gvv(w.t2, self.l2)
             r1 = self.r_L1(o, v, self.l1, self.l2, hb.Hov, hb.Hvv, hb.Hoo, hb.Hovvo, hb.Hovov, hb.Hvvvo, hb.Hovoo,
                            hb.Hvovv, hb.Hooov, Gvv, Goo, W=W)
-            half = self._r_L2_half(self.l1, self.l2, hb.Hov, hb.Hvv, hb.Hoo, hb.Hoooo, hb.Hvvvv, hb.Hovvo, hb.Hovov,
+            half = self._r_L2_half(self.l1, self.l2, hb.Hov, hb.Hvv, hb.Hoo, hb.Hoooo, None, hb.Hovvo, hb.Hovov,
                                    hb.Hvovv, hb.Hooov, Gvv, Goo, W)
             # r2 = half + half^T, l += r/D, sum (r/D)^2 in one pass; then the pseudo-energy
             ssq = K.update_amps(r1, half, w.eps_o, w.eps_v, self.l1, self.l2, symmetrize=True, write_r2=False)

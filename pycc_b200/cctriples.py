@@ -379,6 +379,7 @@ def t3_density(o, v, no, nv, t1, t2, F, ERI, L, contract, comm=None, k_batch=Non
          S2[i,j] [a,d]            += W2n[a,(k,b,c)] <kb|cd>                 K = o v^2        (line 1148)
          X2[i,j] [a,d]            += Pn [a,(k,b,c)] <kb|cd>                                  (line 1129)
          Gooov[j,i] [l,a]         -= t2[l,(k,b,c)] W2n[a,(k,b,c)]                            (line 1142)
+       (the last three are issued once per t3 build for BOTH bodies: their left operands are stacked along M)
        (<dk|bc> = <kd|cb> = <kb|cd> = ovvv[k,b,c,d], so the natural layout of <mb|ef> IS the [(k,b,c), d] matrix).
 
     With a ``comm`` the (i >= j) pairs are dealt round-robin to the ranks and the pieces are summed with all-reduces
@@ -409,19 +410,26 @@ def t3_density(o, v, no, nv, t1, t2, F, ERI, L, contract, comm=None, k_batch=Non
     S2T, X2T = z(no, v2, no), z(no, v2, no)         # [i][(a,b)][l]
     Gooov = z(no, no, no, nv)
     Gall = z(no, v2, nv)                            # [j][(a,b)][d]
-    # work arrays per k of a run: Q (6 v^3) + M3 + W2ab + W2n + Pab + Pn = 11 v^3 doubles
+    # work arrays per k of a run: Q (6 v^3) + M3 + two bodies x (W2ab, W2n, Pab, Pn) = 15 v^3 doubles
     if work_bytes is None:
         work_bytes = 24 << 30
         if dev.type == "cuda":
             free, _ = torch.cuda.mem_get_info(dev)
             work_bytes = int((free - 8 * no * v3) * 0.6)          # Gvvvo itself is still to be allocated
-    kb = int(max(1, min(no, work_bytes // (11 * 8 * v3)))) if k_batch is None else int(max(1, min(no, k_batch)))
+    kb = int(max(1, min(no, work_bytes // (15 * 8 * v3)))) if k_batch is None else int(max(1, min(no, k_batch)))
     kb = -(-no // -(-no // kb))                      # equal-sized runs
     eng = TriplesEngine(shim, t1, t2, q_bytes=kb * 6 * v3 * 8)
     eng.fov = F[o, v]
     fov = eng.fov
     M3 = torch.empty(kb * v3, dtype=F64, device=dev)
-    W2ab, W2n, Pab, Pn = (torch.empty(kb * v3, dtype=F64, device=dev) for _ in range(4))
+    # operands of the two loop bodies (i,j), (j,i) served by one t3 build.  The K = (k,b,c) operands of both bodies live
+    # in ONE buffer [W2n(0) | W2n(1) | Pn(0) | Pn(1)] so that the products against the common <kb|cd> matrix are a single
+    # GEMM with M = 4v (a v x v output tiles raggedly and is too small to amortise its operand traffic)
+    W2ab = [torch.empty(kb * v3, dtype=F64, device=dev) for _ in range(2)]
+    Pab = [torch.empty(kb * v3, dtype=F64, device=dev) for _ in range(2)]
+    NB = torch.empty(4 * kb * v3, dtype=F64, device=dev)
+    Ctmp = torch.empty(4 * v2, dtype=F64, device=dev)
+    Gtmp = torch.empty(no * 2 * nv, dtype=F64, device=dev)
     size, rank = (comm.size, comm.rank) if comm is not None else (1, 0)
     if pairs is None:
         pairs = [(i, j) for j in range(no) for i in range(j, no)][rank::size]
@@ -435,6 +443,8 @@ def t3_density(o, v, no, nv, t1, t2, F, ERI, L, contract, comm=None, k_batch=Non
 
     try:
         for (i0, j0) in pairs:
+            bodies = ((i0, j0, False),) if i0 == j0 else ((i0, j0, False), (j0, i0, True))
+            nb = len(bodies)
             for k0 in range(0, no, kb):
                 nk = min(kb, no - k0)
                 trip = [(i0, j0, k) for k in range(k0, k0 + nk)]
@@ -444,25 +454,36 @@ def t3_density(o, v, no, nv, t1, t2, F, ERI, L, contract, comm=None, k_batch=Non
                 mark("t3_gemm")
                 K.t3_connected_batch(no, nv, ijk, Q, eo, ev, M3)
                 mark("connected")
-                for (i, j, swap) in (((i0, j0, False),) if i0 == j0 else ((i0, j0, False), (j0, i0, True))):
+                kc, kbc, seg = nk * nv, nk * v2, nk * v3
+                for q, (i, j, swap) in enumerate(bodies):
                     mark("start")
-                    K.t3_density_forms(no, nv, i, j, k0, nk, M3, t1, t2s, oovvs, fov, eo, ev, W2ab, W2n, Pab, Pn,
+                    K.t3_density_forms(no, nv, i, j, k0, nk, M3, t1, t2s, oovvs, fov, eo, ev, W2ab[q],
+                                       NB[q * seg:(q + 1) * seg], Pab[q], NB[(nb + q) * seg:(nb + q + 1) * seg],
                                        Goovv[i, j], X2[i, j], dvv_i[i], Dov[i], S1[i], swap_ab=swap)
                     mark("forms")
-                    kc, kbc = nk * nv, nk * v2
-                    K.dgemm(v2, nv, kc, W2ab, kc, 0, (t2q, (i * nv * no + k0) * nv), no * nv, 0, Gall[j], nv, 1.0, 1.0)
+                    K.dgemm(v2, nv, kc, W2ab[q], kc, 0, (t2q, (i * nv * no + k0) * nv), no * nv, 0, Gall[j], nv, 1.0, 1.0)
                     mark("gemm_Gvvvo")
                     qoff = (j * no * no + k0) * nv
-                    K.dgemm(v2, no, kc, W2ab, kc, 0, (ooovq, qoff), no * nv, 0, S2T[i], no, -1.0, 1.0)
-                    K.dgemm(v2, no, kc, Pab, kc, 0, (ooovq, qoff), no * nv, 0, X2T[i], no, -1.0, 1.0)
+                    K.dgemm(v2, no, kc, W2ab[q], kc, 0, (ooovq, qoff), no * nv, 0, S2T[i], no, -1.0, 1.0)
+                    K.dgemm(v2, no, kc, Pab[q], kc, 0, (ooovq, qoff), no * nv, 0, X2T[i], no, -1.0, 1.0)
                     mark("gemm_ooov")
-                    ks = K.balanced_ksplit(nv, nv, kbc)
-                    K.dgemm(nv, nv, kbc, W2n, kbc, 0, (ovvv, k0 * v3), nv, 1, S2[i, j], nv, 1.0, 1.0, ksplit=ks)
-                    K.dgemm(nv, nv, kbc, Pn, kbc, 0, (ovvv, k0 * v3), nv, 1, X2[i, j], nv, 1.0, 1.0, ksplit=ks)
-                    mark("gemm_ovvv")
-                    K.dgemm(no, nv, kbc, (t2, k0 * v2), no * v2, 0, W2n, kbc, 0, Gooov[j, i], nv, -1.0, 1.0,
-                            ksplit=K.balanced_ksplit(no, nv, kbc))
-                    mark("gemm_Gooov")
+                mark("start")
+                # [W2n(q); Pn(q)] (2 nb v rows) x <kb|cd>  ->  S2[i,j] / X2[i,j] increments of every body
+                M = 2 * nb * nv
+                K.dgemm(M, nv, kbc, NB, kbc, 0, (ovvv, k0 * v3), nv, 1, Ctmp, nv, 1.0, 0.0,
+                        ksplit=K.balanced_ksplit(M, nv, kbc))
+                for q, (i, j, _) in enumerate(bodies):
+                    K.axpbyz(1.0, S2[i, j].view(-1), 1.0, Ctmp[q * v2:(q + 1) * v2], S2[i, j].view(-1))
+                    K.axpbyz(1.0, X2[i, j].view(-1), 1.0, Ctmp[(nb + q) * v2:(nb + q + 1) * v2], X2[i, j].view(-1))
+                mark("gemm_ovvv")
+                # t2[l,(k,b,c)] x W2n(q)[a,(k,b,c)]  ->  Gooov[j,i][l,a] increments of every body
+                N = nb * nv
+                K.dgemm(no, N, kbc, (t2, k0 * v2), no * v2, 0, NB, kbc, 0, Gtmp, N, 1.0, 0.0,
+                        ksplit=K.balanced_ksplit(no, N, kbc))
+                Gv = Gtmp[:no * N].view(no, nb, nv)
+                for q, (i, j, _) in enumerate(bodies):
+                    K.strided_axpby(Gooov[j, i], Gv[:, q, :], -1.0, 1.0)
+                mark("gemm_Gooov")
     finally:
         eng.close()
     if prof is not None:
@@ -470,7 +491,7 @@ def t3_density(o, v, no, nv, t1, t2, F, ERI, L, contract, comm=None, k_batch=Non
         for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
             if name != "start":
                 prof[name] = prof.get(name, 0.0) + e0.elapsed_time(e1)
-    del M3, W2ab, W2n, Pab, Pn
+    del M3, W2ab, Pab, NB, Ctmp, Gtmp
     _QCACHE.pop(dev, None)                           # release the Q workspace before the o v^3 output is allocated
     # [i][(a,b)][l] -> [i,l,a,b];  [j][a,b,d] -> [a,b,d,j]
     K.strided_axpby(S2, S2T.view(no, nv, nv, no).permute(0, 3, 1, 2), 1.0, 1.0)

@@ -13,12 +13,13 @@ from pycc_b200 import kernels as K  # noqa: E402
 from pycc_b200.synthetic import make_synthetic  # noqa: E402
 
 o, v = int(sys.argv[1]), int(sys.argv[2])
+conv = float(sys.argv[3]) if len(sys.argv) > 3 else 1e-10
 dev = torch.device("cuda:0")
 syn = make_synthetic(o, v, seed=0, device=dev)
 cc = pycc_b200.ccwfn(syn, model="CCSD", device="GPU", quiet=True)
 torch.cuda.synchronize()
 t0 = time.time()
-ecc = cc.solve_cc(1e-10, 1e-10, 60)
+ecc = cc.solve_cc(conv, conv, 60)
 torch.cuda.synchronize()
 t_cc = time.time() - t0
 l0 = K.launch_count()
@@ -30,13 +31,14 @@ n_hbar = K.launch_count() - l0
 lm = pycc_b200.cclambda(cc, hb)
 l0 = K.launch_count()
 t0 = time.time()
-lecc = lm.solve_lambda(1e-10, 1e-10, 60)
+lecc = lm.solve_lambda(conv, conv, 60)
 torch.cuda.synchronize()
 t_lam = time.time() - t0
 iters = len(lm.trace)
 # dominant terms of one Lambda iteration: Hvvvv ladder, Hoooo, three o^3v^3 ring terms, l2.Hvvvo / l2.Hovoo, Goo/Gvv
 fl = 2 * o**2 * v**4 + 2 * o**4 * v**2 + 3 * 2 * o**3 * v**3 + 2 * o**2 * v**3 * 2 + 2 * o**3 * v**2 * 2 + 2 * o**2 * v**3 + 2 * o**3 * v**2
-out = {"o": o, "v": v, "ecc": float(ecc), "ccsd_s_per_iter": t_cc / len(cc.trace), "hbar_s": t_hbar, "hbar_launches": n_hbar,
+out = {"o": o, "v": v, "conv": conv, "hvvvv_materialised": hb._Hvvvv is not None,
+       "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9, "ecc": float(ecc), "ccsd_s_per_iter": t_cc / len(cc.trace), "hbar_s": t_hbar, "hbar_launches": n_hbar,
        "lambda_pseudoE": float(lecc) if lecc is not None else None, "lambda_iters": iters,
        "lambda_s_per_iter": t_lam / iters, "lambda_launches_per_iter": (K.launch_count() - l0) / iters,
        "lambda_tflops": fl / (t_lam / iters) / 1e12}
