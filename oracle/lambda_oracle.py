@@ -64,7 +64,7 @@ class Hbar:
     """All eleven HBAR blocks for amplitudes (t1, t2); model 'CCSD' or 'CCD' (cchbar.py:54-99)."""
 
     def __init__(self, P, t1, t2, model="CCSD"):
-        ccd = model == "CCD"
+        ccd = model == "CCD"                      # 'CCSD(T)' builds the CCSD blocks (cchbar.py has no (T) branch)
         o, v, F = P.o, P.v, P.F
         tt = tau(t1, t2)
         oovv, Loovv = eri(P, "oovv"), lint(P, "oovv")
@@ -140,11 +140,13 @@ def Gvv(t2, l2):
     return -es("ijeb,ijab->ae", t2, l2)                     # cclambda.py:306
 
 
-def r_L1(H, l1, l2, gvv, goo, model="CCSD"):
-    """cclambda.py:344-370 (s1 = None)"""
+def r_L1(H, l1, l2, gvv, goo, model="CCSD", s1=None):
+    """cclambda.py:344-370; ``s1``: the (T) source cc.S1 of a CCSD(T) wavefunction (350-352)"""
     if model == "CCD":
         return np.zeros_like(l1)
     r = 2.0 * H.Hov
+    if s1 is not None:
+        r = r + s1
     r = r + es("ie,ea->ia", l1, H.Hvv) - es("ma,im->ia", l1, H.Hoo)
     r = r + es("imef,efam->ia", l2, H.Hvvvo) - es("mnae,iemn->ia", l2, H.Hovoo)
     r = r + es("me,ieam->ia", l1, 2.0 * H.Hovvo - H.Hovov.transpose(0, 1, 3, 2))
@@ -153,10 +155,12 @@ def r_L1(H, l1, l2, gvv, goo, model="CCSD"):
     return r
 
 
-def r_L2(P, H, l1, l2, gvv, goo, model="CCSD"):
-    """cclambda.py:447-497 (s2 = None); symmetrised on return"""
+def r_L2(P, H, l1, l2, gvv, goo, model="CCSD", s2=None):
+    """cclambda.py:447-497; ``s2``: the (T) source cc.S2, added as 1/2 s2 before the symmetrisation (470-474)"""
     Loovv = lint(P, "oovv")
     r = Loovv.copy()
+    if s2 is not None:
+        r = r + 0.5 * s2
     if model != "CCD":
         r = r + 2.0 * es("ia,jb->ijab", l1, H.Hov) - es("ja,ib->ijab", l1, H.Hov)
         r = r + 2.0 * es("ie,ejab->ijab", l1, H.Hvovv) - es("ie,ejba->ijab", l1, H.Hvovv)
@@ -173,14 +177,15 @@ def pseudoenergy(P, l2):
     return 0.5 * es("ijab,ijab->", eri(P, "oovv"), l2)      # cclambda.py:570
 
 
-def residuals(P, t1, t2, l1, l2, model="CCSD"):
+def residuals(P, t1, t2, l1, l2, model="CCSD", s1=None, s2=None):
     """cclambda.py:202-256: HBAR rebuilt from (t1, t2), then r_L1 / r_L2"""
     H = Hbar(P, t1, t2, model)
     gvv, goo = Gvv(t2, l2), Goo(t2, l2)
-    return r_L1(H, l1, l2, gvv, goo, model), r_L2(P, H, l1, l2, gvv, goo, model)
+    return r_L1(H, l1, l2, gvv, goo, model, s1), r_L2(P, H, l1, l2, gvv, goo, model, s2)
 
 
-def solve_lambda(P, t1, t2, e_conv=1e-7, r_conv=1e-7, maxiter=100, max_diis=8, start_diis=1, model="CCSD"):
+def solve_lambda(P, t1, t2, e_conv=1e-7, r_conv=1e-7, maxiter=100, max_diis=8, start_diis=1, model="CCSD", s1=None,
+                 s2=None):
     """cclambda.py:69-200.  Returns (pseudo-energy, l1, l2, trace[(lecc, rms)]); None as energy if not converged."""
     H = Hbar(P, t1, t2, model)
     l1, l2 = guess(t1, t2)
@@ -190,8 +195,8 @@ def solve_lambda(P, t1, t2, e_conv=1e-7, r_conv=1e-7, maxiter=100, max_diis=8, s
     for niter in range(1, maxiter + 1):
         last = lecc
         gvv, goo = Gvv(t2, l2), Goo(t2, l2)
-        r1 = r_L1(H, l1, l2, gvv, goo, model)
-        r2 = r_L2(P, H, l1, l2, gvv, goo, model)
+        r1 = r_L1(H, l1, l2, gvv, goo, model, s1)
+        r2 = r_L2(P, H, l1, l2, gvv, goo, model, s2)
         l1 = l1 + r1 / P.Dia
         l2 = l2 + r2 / P.Dijab
         rms = np.sqrt(es("ia,ia->", r1 / P.Dia, r1 / P.Dia) + es("ijab,ijab->", r2 / P.Dijab, r2 / P.Dijab))

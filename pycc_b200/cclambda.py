@@ -1,4 +1,4 @@
-"""Closed-shell CCSD / CCD Lambda-amplitude solver on B200 -- drop-in for ``pycc.cclambda`` on the spatial-orbital
+"""Closed-shell CCSD / CCD / CCSD(T) Lambda-amplitude solver on B200 -- drop-in for ``pycc.cclambda`` on the spatial-orbital
 path (reference: pycc/cclambda.py:27-66 ctor/guess, 69-200 solve_lambda, 202-256 residuals, 258-306 Goo/Gvv,
 308-370 r_L1, 408-497 r_L2, 547-570 pseudoenergy).  SURVEY 8(f) "next" #1.
 
@@ -16,6 +16,7 @@ import time
 import torch
 
 from . import kernels as K
+from .exceptions import PyCCError
 from .utils import helper_diis, title, iteration, converged
 
 F64 = torch.float64
@@ -40,9 +41,12 @@ _R2 = [(1.0, "ijeb,ea->ijab", "l2", "Hvv"), (-1.0, "mjab,im->ijab", "l2", "Hoo")
 
 class cclambda(object):
     def __init__(self, ccwfn, hbar):
-        if ccwfn.model not in ("CCSD", "CCD"):
-            raise NotImplementedError("the Lambda equations are accelerated for closed-shell CCD / CCSD; the (T) "
-                                      "sources S1/S2 and CC2/CC3 stay with the reference implementation")
+        if ccwfn.model not in ("CCSD", "CCD", "CCSD(T)"):
+            raise NotImplementedError("the Lambda equations are accelerated for closed-shell CCD / CCSD / CCSD(T); "
+                                      "CC2/CC3 stay with the reference implementation")
+        if ccwfn.model == "CCSD(T)" and not (hasattr(ccwfn, "S1") and hasattr(ccwfn, "S2")):
+            raise PyCCError("CCSD(T) Lambda needs the (T) sources S1/S2: solve the amplitudes with "
+                            "make_t3_density=True (or call ccwfn.t3_density()) first")
         if getattr(ccwfn, "part", None) is not None and ccwfn.part.size > 1:
             raise NotImplementedError("the Lambda solver is single-GPU (its terms are not rank-partitioned yet)")
         self.ccwfn, self.hbar = ccwfn, hbar
@@ -76,13 +80,14 @@ class cclambda(object):
         return out
 
     def r_L1(self, o, v, l1, l2, Hov, Hvv, Hoo, Hovvo, Hovov, Hvvvo, Hovoo, Hvovv, Hooov, Gvv, Goo, s1=None, W=None):
-        if s1 is not None:
-            raise NotImplementedError("(T) lambda sources are outside the accelerated path")
         if self.ccwfn.model == "CCD":
             return torch.zeros_like(l1)
         env = dict(l1=l1.contiguous(), l2=l2.contiguous(), Hvv=Hvv, Hoo=Hoo, Hvvvo=Hvvvo, Hovoo=Hovoo, Hvovv=Hvovv,
                    Hooov=Hooov, Gvv=Gvv, Goo=Goo, W=W if W is not None else self._w(Hovvo, Hovov))
-        return self._accumulate(K.permuted(Hov, (0, 1), 2.0), _R1, env)
+        out = K.permuted(Hov, (0, 1), 2.0)
+        if s1 is not None:                                   # (T) source cc.S1          cclambda.py:350-352
+            K.strided_axpby(out, s1, 1.0, 1.0)
+        return self._accumulate(out, _R1, env)
 
     def _ladder(self, half, l2, Hvvvv=None):
         """half += 1/2 l2_ijef H_efab (cclambda.py:468) WITHOUT the v^4 tensor H_efab:
@@ -108,23 +113,29 @@ class cclambda(object):
             ct("ijmn,mnab->ijab", ct("ijef,mnef->ijmn", l2, tau), oovv, out=half, alpha=0.5, beta=1.0)
         return half
 
-    def _r_L2_half(self, l1, l2, Hov, Hvv, Hoo, Hoooo, Hvvvv, Hovvo, Hovov, Hvovv, Hooov, Gvv, Goo, W):
+    def _r_L2_half(self, l1, l2, Hov, Hvv, Hoo, Hoooo, Hvvvv, Hovvo, Hovov, Hvovv, Hooov, Gvv, Goo, W, s2=None):
         Loovv = self.ccwfn.H.derived("Loovv")
         l2 = l2.contiguous()
         env = dict(l1=l1.contiguous(), l2=l2, Hov=Hov, Hvv=Hvv, Hoo=Hoo, Hoooo=Hoooo,
                    Hovvo=Hovvo, Hovov=Hovov, Hvovv=Hvovv, Hooov=Hooov, Gvv=Gvv, Goo=Goo, W=W, Loovv=Loovv)
         terms = _R2 if self.ccwfn.model == "CCD" else _R2_SINGLES + _R2
-        half = self._accumulate(K.permuted(Loovv, (0, 1, 2, 3)), terms, env)
+        half = K.permuted(Loovv, (0, 1, 2, 3))
+        if s2 is not None:                                   # (T) source: + 1/2 cc.S2 before P_ij^ab   cclambda.py:470-474
+            K.strided_axpby(half, s2, 0.5, 1.0)
+        self._accumulate(half, terms, env)
         return self._ladder(half, l2, Hvvvv)
 
     def r_L2(self, o, v, l1, l2, L, Hov, Hvv, Hoo, Hoooo, Hvvvv, Hovvo, Hovov, Hvvvo, Hovoo, Hvovv, Hooov, Gvv, Goo,
              s2=None):
-        if s2 is not None:
-            raise NotImplementedError("(T) lambda sources are outside the accelerated path")
         self.ccwfn._own(L=L)
         half = self._r_L2_half(l1, l2, Hov, Hvv, Hoo, Hoooo, Hvvvv, Hovvo, Hovov, Hvovv, Hooov, Gvv, Goo,
-                               self._w(Hovvo, Hovov))
+                               self._w(Hovvo, Hovov), s2=s2)
         return K.symmetrize_r2(half)                                                       # cclambda.py:496
+
+    def _sources(self):
+        """(S1, S2) of a CCSD(T) wavefunction (cclambda.py:145-146), else (None, None)"""
+        w = self.ccwfn
+        return (w.S1, w.S2) if w.model == "CCSD(T)" else (None, None)
 
     def pseudoenergy(self, o, v, ERI, l2):
         """1/2 <ij|ab> l2_ijab as a 0-d device tensor                                       cclambda.py:570"""
@@ -137,6 +148,7 @@ class cclambda(object):
         hb = self.hbar.build_all(F, t1, t2)
         Goo, Gvv = self.build_Goo(t2, l2), self.build_Gvv(t2, l2)
         W = self._w(hb["Hovvo"], hb["Hovov"])
+        # as in the reference, this entry point never adds the (T) sources (only solve_lambda does, cclambda.py:145-148)
         r1 = self.r_L1(self.ccwfn.o, self.ccwfn.v, l1, l2, hb["Hov"], hb["Hvv"], hb["Hoo"], hb["Hovvo"], hb["Hovov"],
                        hb["Hvvvo"], hb["Hovoo"], hb["Hvovv"], hb["Hooov"], Gvv, Goo, W=W)
         half = self._r_L2_half(l1, l2, hb["Hov"], hb["Hvv"], hb["Hoo"], hb["Hoooo"], None, hb["Hovvo"],
@@ -155,14 +167,15 @@ class cclambda(object):
         say(iteration(0, energy=lecc, de=-lecc, e_label="LCC PseudoE"))
         diis = helper_diis(self.l1, self.l2, max_diis, w.precision)
         W = self._w(hb.Hovvo, hb.Hovov)
+        s1, s2 = self._sources()
         self.trace = []
         for niter in range(1, maxiter + 1):
             last = lecc
             Goo, Gvv = self.build_Goo(w.t2, self.l2), self.build_Gvv(w.t2, self.l2)
             r1 = self.r_L1(o, v, self.l1, self.l2, hb.Hov, hb.Hvv, hb.Hoo, hb.Hovvo, hb.Hovov, hb.Hvvvo, hb.Hovoo,
-                           hb.Hvovv, hb.Hooov, Gvv, Goo, W=W)
+                           hb.Hvovv, hb.Hooov, Gvv, Goo, s1=s1, W=W)
             half = self._r_L2_half(self.l1, self.l2, hb.Hov, hb.Hvv, hb.Hoo, hb.Hoooo, None, hb.Hovvo, hb.Hovov,
-                                   hb.Hvovv, hb.Hooov, Gvv, Goo, W)
+                                   hb.Hvovv, hb.Hooov, Gvv, Goo, W, s2=s2)
             # r2 = half + half^T, l += r/D, sum (r/D)^2 in one pass; then the pseudo-energy
             ssq = K.update_amps(r1, half, w.eps_o, w.eps_v, self.l1, self.l2, symmetrize=True, write_r2=False)
             e_dev = self.pseudoenergy(o, v, w.H.ERI, self.l2)

@@ -40,9 +40,13 @@ def case(mods, tag, model):
             w.t1, w.t2 = g["conv_t1"].copy(), g["conv_t2"].copy()
             ecc = float(g["e_ccsd"])
         else:
+            # CCSD(T): the (T) step of solve_cc is t3_density, which leaves the Lambda sources S1 / S2 on the wavefunction
+            w.make_t3_density = model == "CCSD(T)"
             ecc = float(w.solve_cc(1e-12, 1e-12, 100))
         hbar = cchbar(w)
     out = dict(model=np.array(model), t1=w.t1.copy(), t2=w.t2.copy(), ecc=ecc)
+    if model == "CCSD(T)":
+        out["S1"], out["S2"] = np.array(w.S1), np.array(w.S2)
     for k in HBAR:
         out[k] = np.array(getattr(hbar, k))
     lam = cclambda(w, hbar)
@@ -68,7 +72,7 @@ def case(mods, tag, model):
     out["trace_lecc_rms"] = np.array(trace)
     out["lecc"] = float(lecc)
     out["conv_l1"], out["conv_l2"] = np.array(lam.l1), np.array(lam.l2)
-    path = os.path.join(HERE, "lam_%s_%s.npz" % (tag, model.lower()))
+    path = os.path.join(HERE, "lam_%s_%s.npz" % (tag, {"CCSD(T)": "ccsdpt"}.get(model, model.lower())))
     np.savez_compressed(path, **out)
     print("wrote %s  pseudo-E = %.15f  iters = %d" % (path, out["lecc"], len(trace)))
 
@@ -79,6 +83,7 @@ def main():
     case(mods, "o4v10_s1_noise", "CCSD")
     case(mods, "o3v7_s2", "CCSD")
     case(mods, "o4v10_s0", "CCD")
+    case(mods, "o4v10_s1_noise", "CCSD(T)")
 
 
 if __name__ == "__main__":

@@ -55,6 +55,7 @@ def test_oracle_lambda_residuals(lam):
     assert np.abs(l1 - g["guess_l1"]).max() < 1e-14 and np.abs(l2 - g["guess_l2"]).max() < 1e-14
     assert np.abs(lo.Goo(g["t2"], g["rand_l2"]) - g["rand_Goo"]).max() < 1e-13
     assert np.abs(lo.Gvv(g["t2"], g["rand_l2"]) - g["rand_Gvv"]).max() < 1e-13
+    # cclambda.residuals (202-256) never adds the (T) sources -- only solve_lambda does (145-148)
     r1, r2 = lo.residuals(P, g["t1"], g["t2"], g["rand_l1"], g["rand_l2"], model)
     assert np.abs(r1 - g["rand_r1"]).max() < 1e-12
     assert np.abs(r2 - g["rand_r2"]).max() < 1e-12
@@ -63,7 +64,8 @@ def test_oracle_lambda_residuals(lam):
 
 def test_oracle_solve_lambda_trace(lam):
     g, syn, model = lam
-    lecc, l1, l2, trace = lo.solve_lambda(problem(syn), g["t1"], g["t2"], 1e-12, 1e-12, 100, model=model)
+    lecc, l1, l2, trace = lo.solve_lambda(problem(syn), g["t1"], g["t2"], 1e-12, 1e-12, 100, model=model,
+                                          s1=g.get("S1"), s2=g.get("S2"))
     ref = g["trace_lecc_rms"]
     assert len(trace) == len(ref)
     tr = np.array(trace)
@@ -95,6 +97,8 @@ def T(x):
 def wfn(syn, model, g):
     cc = pycc_b200.ccwfn(IntegralReference.from_synthetic(syn), model=model, device='GPU', quiet=True)
     cc.t1, cc.t2 = T(g["t1"]), T(g["t2"])
+    if "S1" in g:                                  # CCSD(T): the (T) Lambda sources that t3_density leaves on the wfn
+        cc.S1, cc.S2 = T(g["S1"]), T(g["S2"])
     return cc
 
 
@@ -150,9 +154,28 @@ def test_lambda_not_converged_and_unsupported(dev):
     cc.solve_cc(1e-10, 1e-10)
     lm = pycc_b200.cclambda(cc, pycc_b200.cchbar(cc))
     assert lm.solve_lambda(1e-12, 1e-12, maxiter=2) is None
+    from pycc_b200.exceptions import PyCCError
     cct = pycc_b200.ccwfn(syn, model="CCSD(T)", quiet=True)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(PyCCError):                 # CCSD(T) Lambda needs S1 / S2 (make_t3_density=True)
         pycc_b200.cclambda(cct, pycc_b200.cchbar(cct))
+
+
+def test_ccsd_t_chain_solve_cc_t3_density_lambda(dev):
+    """The whole CCSD(T) chain of the reference (ccwfn.py:300-304 -> cchbar -> cclambda.py:145-148): amplitudes with
+    make_t3_density=True, HBAR, Lambda with the (T) sources -- against the reference's own pseudo-energy / amplitudes."""
+    path = [p for p in LAM if p.endswith("ccsdpt.npz")][0]
+    g, syn, model = load(path)
+    assert model == "CCSD(T)"
+    cc = pycc_b200.ccwfn(IntegralReference.from_synthetic(syn), model="CCSD(T)", device='GPU', quiet=True,
+                         make_t3_density=True)
+    e = cc.solve_cc(1e-12, 1e-12)
+    assert abs(float(e) - float(g["ecc"])) < 1e-10
+    assert np.abs(cc.S1.cpu().numpy() - g["S1"]).max() < 1e-9 and np.abs(cc.S2.cpu().numpy() - g["S2"]).max() < 1e-9
+    lm = pycc_b200.cclambda(cc, pycc_b200.cchbar(cc))
+    lecc = lm.solve_lambda(1e-12, 1e-12, 100)
+    assert abs(float(lecc) - float(g["lecc"])) < 1e-10
+    assert np.abs(lm.l1.cpu().numpy() - g["conv_l1"]).max() < 1e-9
+    assert np.abs(lm.l2.cpu().numpy() - g["conv_l2"]).max() < 1e-9
 
 
 @pytest.mark.gpu
