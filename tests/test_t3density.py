@@ -133,6 +133,26 @@ def test_odd_sizes_and_fock_noise(dev):
         assert worst({k: getattr(cc, k) for k in do.NAMES}, want) < 1e-12, (no, nv)
 
 
+def test_frozen_core_offsets(dev):
+    """nfzc > 0: o / v are offset slices of the full MO space (wavefunction.py:304-315); eps and f_ov must follow"""
+    from pycc_b200.synthetic import full_eri
+    from pycc_b200.wavefunction import IntegralReference
+    nf, no, nv = 2, 3, 6
+    syn = make_synthetic(nf + no, nv, seed=9, fock_noise=0.01)
+    ERI = full_eri(syn)
+    n = nf + no + nv
+    o, v = slice(nf, nf + no), slice(nf + no, n)
+    rng = np.random.default_rng(3)
+    t1 = 0.05 * rng.standard_normal((no, nv))
+    t2 = 0.05 * rng.standard_normal((no, no, nv, nv))
+    t2 = t2 + t2.transpose(1, 0, 3, 2)
+    et, want = do.t3_density(t1, t2, syn.F, ERI[o, v, v, v], ERI[o, o, o, v], ERI[o, o, v, v], nfzc=nf)
+    cc = pycc_b200.ccwfn(IntegralReference.from_arrays(syn.F, ERI, no, nf), model="CCSD(T)", device="GPU", quiet=True)
+    cc.t1, cc.t2 = T(t1), T(t2)
+    assert abs(float(cc.t3_density()) - et) < 1e-12
+    assert worst({k: getattr(cc, k) for k in do.NAMES}, want) < 1e-12
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("no,nv,seed,noise,kb", [(6, 26, 0, 0.01, None), (8, 40, 1, 0.0, 3), (5, 33, 2, 0.01, 2)])
 def test_medium_size_vs_oracle(no, nv, seed, noise, kb):
