@@ -453,7 +453,7 @@ def main():
 
     if rank == 0:
         cpu = None
-        if not args.no_cpu and world >= 1:
+        if not args.no_cpu and world == 1:          # reported at N=1 only (rank 0)
             cores = os.cpu_count() or 1
             est, t_s, sample = cpu_sample_fullsize(o, v, cores)
             cpu = {"value": est, "unit": "s/iter", "cores": cores, "kind": "port", "sample": sample}

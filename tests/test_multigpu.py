@@ -32,7 +32,13 @@ def _worker(rank, world, port, q):
         P = co.Problem(b, syn.F, no)
         e_ref, t1, t2, trace = co.solve_cc(P, 1e-11, 1e-11)
         et = to.t_tjl(t1, t2, syn.F, b["ovvv"], b["ooov"], b["oovv"])
-        q.put((rank, abs(e - (e_ref + et)), float(np.abs(cc.t2.cpu().numpy() - t2).max()), len(cc.trace), len(trace)))
+        # (T) densities: (i >= j) pairs dealt over the ranks, pieces all-reduced (NCCL)
+        from oracle import t3density_oracle as do
+        et_d, want = do.t3_density(t1, t2, syn.F, b["ovvv"], b["ooov"], b["oovv"])
+        e_d = float(cc.t3_density())
+        dd = max(float(np.abs(getattr(cc, k).cpu().numpy() - want[k]).max()) for k in do.NAMES)
+        q.put((rank, abs(e - (e_ref + et)), float(np.abs(cc.t2.cpu().numpy() - t2).max()), len(cc.trace), len(trace),
+               abs(e_d - et_d), dd))
     finally:
         dist.destroy_process_group()
 
@@ -51,5 +57,6 @@ def test_nccl_ranks_match_oracle():
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    for rank, de, dt, n, nref in res:
+    for rank, de, dt, n, nref, ded, dd in res:
         assert de < 1e-10 and dt < 1e-9 and n == nref, (rank, de, dt, n, nref)
+        assert ded < 1e-10 and dd < 1e-9, (rank, ded, dd)
