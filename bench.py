@@ -211,8 +211,10 @@ def main():
     comm = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # keep stdout to the single JSON line: NCCL_DEBUG=VERSION/INFO print there
+        # keep stdout to the single JSON line: NCCL writes its banner ("NCCL version ...", printed from VERSION up,
+        # i.e. also at WARN) and debug lines to stdout unless NCCL_DEBUG_FILE points elsewhere
         os.environ["NCCL_DEBUG"] = os.environ.get("B200CC_NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
         comm = Comm()
     o, v = args.o, args.v
