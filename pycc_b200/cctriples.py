@@ -417,6 +417,7 @@ def t3_density(o, v, no, nv, t1, t2, F, ERI, L, contract, comm=None, k_batch=Non
             free, _ = torch.cuda.mem_get_info(dev)
             work_bytes = int((free - 8 * no * v3) * 0.6)          # Gvvvo itself is still to be allocated
     kb = int(max(1, min(no, work_bytes // (15 * 8 * v3)))) if k_batch is None else int(max(1, min(no, k_batch)))
+    kb = max(1, min(kb, (2 ** 32 - 1) // v3))        # the forms kernel indexes a run with 32-bit element offsets
     kb = -(-no // -(-no // kb))                      # equal-sized runs
     eng = TriplesEngine(shim, t1, t2, q_bytes=kb * 6 * v3 * 8)
     eng.fov = F[o, v]
