@@ -357,7 +357,7 @@ T3D_NAMES = ("Doo", "Dvv", "Dov", "Goovv", "Gooov", "Gvvvo", "S1", "S2")
 
 
 def t3_density(o, v, no, nv, t1, t2, F, ERI, L, contract, comm=None, k_batch=None, work_bytes=None, prof=None,
-               pairs=None):
+               pairs=None, mixed=False):
     """(T) energy plus the (T) increments {Doo, Dvv, Dov, Goovv, Gooov, Gvvvo, S1, S2} to the one-/two-particle
     densities and the Lambda residuals; reference: cctriples.py:1063-1157, same signature and return value
     (``ERI`` must be the ``H.ERI`` block view of a :class:`BlockHamiltonian`; ``L`` is derived from it).
@@ -385,6 +385,10 @@ def t3_density(o, v, no, nv, t1, t2, F, ERI, L, contract, comm=None, k_batch=Non
     With a ``comm`` the (i >= j) pairs are dealt round-robin to the ranks and the pieces are summed with all-reduces
     at the end.  Returns ``(ET, dict)``; ET is a 0-d device tensor.  ``prof`` (a dict) collects CUDA-event times per
     phase in ms; ``pairs`` restricts the pair loop (timing probes only: the result is then a partial sum).
+    ``mixed`` (precision='MP'): the t3 build and the Gvvvo product run as split-TF32 products on the tcgen05 kernel with
+    FP64 accumulation (105 / 90 TFLOP/s FP64-equivalent at o=40,v=300); the stacked <kb|cd> product has too few output
+    tiles (4v x v) for that kernel, which has no split-K, and the N = o products are bound by streaming their operand:
+    both stay on the FP64 DMMA kernel.
     """
     import types
     H = getattr(ERI, "H", None)
@@ -395,10 +399,18 @@ def t3_density(o, v, no, nv, t1, t2, F, ERI, L, contract, comm=None, k_batch=Non
     t2 = t2.contiguous()
     dev = t2.device
     eo, ev = _eps(F, o, v)
-    shim = types.SimpleNamespace(H=H, no=no, nv=nv, t1=t1, t2=t2, o=o, v=v, eps_o=eo, eps_v=ev, mixed=False)
+    shim = types.SimpleNamespace(H=H, no=no, nv=nv, t1=t1, t2=t2, o=o, v=v, eps_o=eo, eps_v=ev, mixed=bool(mixed))
     v2, v3 = nv * nv, nv ** 3
     z = lambda *shape: torch.zeros(shape, dtype=F64, device=dev)
     ovvv, ooov, oovv = H.block("ovvv"), H.block("ooov"), H.block("oovv")
+    # <kb|cd> with d slowest, [d,k,b,c] = ovvv[k,b,c,d]: a constant K-major copy (o v^3 doubles, built once per
+    # Hamiltonian when it fits) puts the [W2n;Pn] x <kb|cd> products on the TMA kernel -- and, with precision='MP', on
+    # the tcgen05 kernel; without it <mb|ef> is streamed in place as an N-major operand (cp.async kernel)
+    ovvv_d = H._derived.get("ovvv_dkbc")
+    if ovvv_d is None and nv % 2 == 0:
+        free = torch.cuda.mem_get_info(dev)[0] if dev.type == "cuda" else 1 << 62
+        if free > 6 * 8 * no * v3:
+            ovvv_d = H._derived["ovvv_dkbc"] = K.permuted(ovvv, (3, 0, 1, 2))
     t2q = K.permuted(t2, (0, 2, 1, 3))               # [i,d,k,c] = t2[i,k,d,c]
     ooovq = K.permuted(ooov, (0, 2, 1, 3))           # [j,l,k,c] = <jk|lc>
     t2s = K.permuted(t2, (0, 1, 2, 3), 4.0)          # 4 t2 - 2 t2.swapaxes(2,3)
@@ -462,8 +474,11 @@ def t3_density(o, v, no, nv, t1, t2, F, ERI, L, contract, comm=None, k_batch=Non
                                        NB[q * seg:(q + 1) * seg], Pab[q], NB[(nb + q) * seg:(nb + q + 1) * seg],
                                        Goovv[i, j], X2[i, j], dvv_i[i], Dov[i], S1[i], swap_ab=swap)
                     mark("forms")
-                    K.dgemm(v2, nv, kc, W2ab[q], kc, 0, (t2q, (i * nv * no + k0) * nv), no * nv, 0, Gall[j], nv, 1.0, 1.0)
+                    with K.mixed_mode(mixed):
+                        K.dgemm(v2, nv, kc, W2ab[q], kc, 0, (t2q, (i * nv * no + k0) * nv), no * nv, 0, Gall[j], nv,
+                                1.0, 1.0)
                     mark("gemm_Gvvvo")
+                    # N = o columns only: bound by streaming W2ab / Pab, stays on the FP64 kernel in every mode
                     qoff = (j * no * no + k0) * nv
                     K.dgemm(v2, no, kc, W2ab[q], kc, 0, (ooovq, qoff), no * nv, 0, S2T[i], no, -1.0, 1.0)
                     K.dgemm(v2, no, kc, Pab[q], kc, 0, (ooovq, qoff), no * nv, 0, X2T[i], no, -1.0, 1.0)
@@ -471,8 +486,13 @@ def t3_density(o, v, no, nv, t1, t2, F, ERI, L, contract, comm=None, k_batch=Non
                 mark("start")
                 # [W2n(q); Pn(q)] (2 nb v rows) x <kb|cd>  ->  S2[i,j] / X2[i,j] increments of every body
                 M = 2 * nb * nv
-                K.dgemm(M, nv, kbc, NB, kbc, 0, (ovvv, k0 * v3), nv, 1, Ctmp, nv, 1.0, 0.0,
-                        ksplit=K.balanced_ksplit(M, nv, kbc))
+                if ovvv_d is not None:
+                    with K.mixed_mode(mixed):
+                        K.dgemm(M, nv, kbc, NB, kbc, 0, (ovvv_d, k0 * v2), no * v2, 0, Ctmp, nv, 1.0, 0.0,
+                                ksplit=K.balanced_ksplit(M, nv, kbc))
+                else:
+                    K.dgemm(M, nv, kbc, NB, kbc, 0, (ovvv, k0 * v3), nv, 1, Ctmp, nv, 1.0, 0.0,
+                            ksplit=K.balanced_ksplit(M, nv, kbc))
                 for q, (i, j, _) in enumerate(bodies):
                     K.axpbyz(1.0, S2[i, j].view(-1), 1.0, Ctmp[q * v2:(q + 1) * v2], S2[i, j].view(-1))
                     K.axpbyz(1.0, X2[i, j].view(-1), 1.0, Ctmp[(nb + q) * v2:(nb + q + 1) * v2], X2[i, j].view(-1))

@@ -179,7 +179,7 @@ class CCwfn(object):
         Gooov, Gvvvo, S1, S2) and returns the (T) energy."""
         from . import cctriples
         et, dens = cctriples.t3_density(self.o, self.v, self.no, self.nv, self.t1, self.t2, self.H.F, self.H.ERI,
-                                        self.H.L, self.contract, comm=self.comm)
+                                        self.H.L, self.contract, comm=self.comm, mixed=self.mixed)
         for name, value in dens.items():
             setattr(self, name, value)
         return et

@@ -17,6 +17,7 @@ import types  # noqa: E402
 
 o, v = int(sys.argv[1]), int(sys.argv[2])
 npair = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+mixed = len(sys.argv) > 4 and sys.argv[4].upper() == "MP"
 dev = torch.device("cuda:0")
 syn = make_synthetic(o, v, seed=0, device=dev)
 H = BlockHamiltonian.from_factor(syn, dev, names=("ooov", "oovv", "ovvv"))
@@ -27,12 +28,12 @@ ct = pycc_b200.device.DeviceManager(device="GPU", precision="DP").contract
 allp = [(i, j) for j in range(o) for i in range(j, o)]
 pairs = allp if not npair else [(o - 1 - n, n) for n in range(npair)]          # i > j: both loop bodies per t3 build
 # warm-up on one pair (allocations, derived layouts), then the timed run
-cctriples.t3_density(H.o, H.v, o, v, t1, t2, H.F, H.ERI, H.L, ct, pairs=pairs[:1])
+cctriples.t3_density(H.o, H.v, o, v, t1, t2, H.F, H.ERI, H.L, ct, pairs=pairs[:1], mixed=mixed)
 torch.cuda.synchronize()
 prof = {}
 l0 = K.launch_count()
 t0 = time.time()
-et, dens = cctriples.t3_density(H.o, H.v, o, v, t1, t2, H.F, H.ERI, H.L, ct, pairs=pairs, prof=prof)
+et, dens = cctriples.t3_density(H.o, H.v, o, v, t1, t2, H.F, H.ERI, H.L, ct, pairs=pairs, prof=prof, mixed=mixed)
 torch.cuda.synchronize()
 wall = time.time() - t0
 nbuild = len(pairs) * o                                   # t3 tiles built
@@ -42,7 +43,7 @@ ntrip = sum(1 if i == j else 2 for i, j in pairs) * o     # loop bodies of the r
 fl_build = nbuild * (12 * v**4 + 12 * o * v**3)
 fl_dens = ntrip * (6 * v**4 + 6 * o * v**3)
 dens_ms = sum(prof[k] for k in prof if k.startswith("gemm_"))
-out = {"o": o, "v": v, "pairs": len(pairs), "t3_tiles_built": nbuild, "loop_bodies": ntrip, "wall_s": wall,
+out = {"o": o, "v": v, "precision": "MP" if mixed else "DP", "pairs": len(pairs), "t3_tiles_built": nbuild, "loop_bodies": ntrip, "wall_s": wall,
        "tflops_executed": (fl_build + fl_dens) / wall / 1e12,
        "tflops_reference_formulation": ntrip * (18 * v**4 + 18 * o * v**3) / wall / 1e12,
        "full_o3_s_est": wall * o * o * o / ntrip, "launches": K.launch_count() - l0, "phase_ms": prof,
@@ -55,4 +56,4 @@ out = {"o": o, "v": v, "pairs": len(pairs), "t3_tiles_built": nbuild, "loop_bodi
        "et_partial": float(et)}
 print(json.dumps(out))
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(out, open("gpurun_out/t3d_probe_o%dv%d.json" % (o, v), "w"), indent=1)
+json.dump(out, open("gpurun_out/t3d_probe_o%dv%d%s.json" % (o, v, "_mp" if mixed else ""), "w"), indent=1)

@@ -133,6 +133,26 @@ def test_odd_sizes_and_fock_noise(dev):
         assert worst({k: getattr(cc, k) for k in do.NAMES}, want) < 1e-12, (no, nv)
 
 
+def test_mixed_precision_t3_density(t3d, dev):
+    """precision='MP': t3 build and the K-major density products as split-TF32 GEMMs with FP64 accumulation; E(T) to
+    1e-6 Eh (north_star), the pieces to 1e-6 relative to their largest element"""
+    from pycc_b200 import kernels as K
+    g, r, syn = t3d
+    keep = (K.MIXED.min_flops, K.MIXED.min_dim, K.MIXED.min_tiles)
+    K.MIXED.min_flops, K.MIXED.min_dim, K.MIXED.min_tiles = 0.0, 1, 1
+    try:
+        cc = pycc_b200.ccwfn(syn, model="CCSD(T)", device="GPU", quiet=True, precision="MP")
+        cc.t1, cc.t2 = T(g["t1"]), T(g["t2"])
+        g0 = K.MIXED.stats["gemm"]
+        e = float(cc.t3_density())
+        assert K.MIXED.stats["gemm"] > g0
+    finally:
+        K.MIXED.min_flops, K.MIXED.min_dim, K.MIXED.min_tiles = keep
+    assert abs(e - float(g["et"])) < 1e-6
+    for k in do.NAMES:
+        assert np.abs(getattr(cc, k).cpu().numpy() - g[k]).max() < 1e-6 * max(1.0, np.abs(g[k]).max()), k
+
+
 def test_frozen_core_offsets(dev):
     """nfzc > 0: o / v are offset slices of the full MO space (wavefunction.py:304-315); eps and f_ov must follow"""
     from pycc_b200.synthetic import full_eri
