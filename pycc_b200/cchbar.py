@@ -119,6 +119,8 @@ class cchbar(object):
     def Hvvvv(self):
         """H_abef (cchbar.py:394-403), materialised on first access (v^4 doubles)."""
         if self._Hvvvv is None:
+            if self.ccwfn.part.size > 1:
+                raise NotImplementedError("H_abef is not materialised when <ab|ef> is sharded over ranks")
             self._Hvvvv = self._one("Hvvvv", *self._amps)
         return self._Hvvvv
 
@@ -156,11 +158,31 @@ class cchbar(object):
             src = _view(w.H, init)
             out = K.permuted(src, tuple(range(src.dim())))
         todo = list(terms) + ([] if w.model == "CCD" else list(singles))
+        sharded = w.part.size > 1
         with K.mixed_mode(getattr(w, "mixed", False)):
             for alpha, sub, a, b in todo:
+                if sharded and "E:vvvv" in (a, b):
+                    self._vvvv_term_sharded(out, alpha, sub, a, b, env)
+                    continue
                 w._ct(sub, self._operand(env, a), self._operand(env, b), out=out, alpha=alpha, beta=1.0)
         env[key] = out
         return out
+
+    def _vvvv_term_sharded(self, out, alpha, sub, a, b, env):
+        """A term whose integral operand is <ab|ef> when that block is a-sharded over the ranks (parallel.py): each
+        rank contracts its rows a, the pieces are summed with one all-reduce and added to the (replicated) block.
+        Only 't_if <ab|ef> -> abei' (Hvvvo) occurs; both tensors have a as their slowest index."""
+        w = self.ccwfn
+        if sub != "if,abef->abei" or b != "E:vvvv":
+            raise NotImplementedError("a-sharded <ab|ef> in HBAR term %r" % sub)
+        if w.H.a_range != tuple(w.part.a_range(w.nv)):
+            raise NotImplementedError("<ab|ef> rows resident on this rank differ from its share")
+        a_lo, a_hi = w.H.a_range
+        piece = torch.zeros_like(out)
+        if a_hi > a_lo:
+            w._ct(sub, self._operand(env, a), w.H.block("vvvv"), out=piece[a_lo:a_hi], alpha=alpha, beta=0.0)
+        w.part.all_reduce_sum(piece)
+        K.strided_axpby(out, piece, 1.0, 1.0)
 
     def build_all(self, F, t1, t2, with_vvvv=False):
         """Every block in dependency order (Hvvvo needs Hov, Hovoo needs Hov and Hoooo); H_abef only on request."""

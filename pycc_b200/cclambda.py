@@ -47,8 +47,6 @@ class cclambda(object):
         if ccwfn.model == "CCSD(T)" and not (hasattr(ccwfn, "S1") and hasattr(ccwfn, "S2")):
             raise PyCCError("CCSD(T) Lambda needs the (T) sources S1/S2: solve the amplitudes with "
                             "make_t3_density=True (or call ccwfn.t3_density()) first")
-        if getattr(ccwfn, "part", None) is not None and ccwfn.part.size > 1:
-            raise NotImplementedError("the Lambda solver is single-GPU (its terms are not rank-partitioned yet)")
         self.ccwfn, self.hbar = ccwfn, hbar
         self.contract = ccwfn.contract
         t1, t2 = ccwfn.t1, ccwfn.t2
@@ -99,7 +97,15 @@ class cclambda(object):
         if Hvvvv is not None:
             return ct("ijef,efab->ijab", l2, Hvvvv, out=half, alpha=0.5, beta=1.0)
         with K.mixed_mode(getattr(w, "mixed", False)):
-            w._ladder(l2, half)
+            if w.part.size > 1:
+                # <ab|ef> is a-sharded: every rank adds the rows it holds, one all-reduce (o^2v^2) sums the pieces;
+                # all other terms are replicated, so l1 / l2 stay identical on all ranks
+                piece = torch.zeros_like(half)
+                w._ladder(l2, piece)
+                w.part.all_reduce_sum(piece)
+                K.strided_axpby(half, piece, 1.0, 1.0)
+            else:
+                w._ladder(l2, half)
             o, v = w.o, w.v
             oovv = w.H.ERI[o, o, v, v]
             if w.model == "CCD":

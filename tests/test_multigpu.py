@@ -37,8 +37,15 @@ def _worker(rank, world, port, q):
         et_d, want = do.t3_density(t1, t2, syn.F, b["ovvv"], b["ooov"], b["oovv"])
         e_d = float(cc.t3_density())
         dd = max(float(np.abs(getattr(cc, k).cpu().numpy() - want[k]).max()) for k in do.NAMES)
+        # HBAR + Lambda with the (T) sources, <ab|ef> a-sharded (rank-local ladder pieces + all-reduce)
+        from oracle import lambda_oracle as lo
+        lecc_ref, l1_ref, l2_ref, ltrace = lo.solve_lambda(P, t1, t2, 1e-11, 1e-11, 100, model="CCSD(T)",
+                                                           s1=want["S1"], s2=want["S2"])
+        lm = pycc_b200.cclambda(cc, pycc_b200.cchbar(cc))
+        lecc = float(lm.solve_lambda(1e-11, 1e-11, 100))
+        dl = float(np.abs(lm.l2.cpu().numpy() - l2_ref).max())
         q.put((rank, abs(e - (e_ref + et)), float(np.abs(cc.t2.cpu().numpy() - t2).max()), len(cc.trace), len(trace),
-               abs(e_d - et_d), dd))
+               abs(e_d - et_d), dd, abs(lecc - lecc_ref), dl))
     finally:
         dist.destroy_process_group()
 
@@ -57,6 +64,7 @@ def test_nccl_ranks_match_oracle():
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    for rank, de, dt, n, nref, ded, dd in res:
+    for rank, de, dt, n, nref, ded, dd, dle, dl in res:
         assert de < 1e-10 and dt < 1e-9 and n == nref, (rank, de, dt, n, nref)
         assert ded < 1e-10 and dd < 1e-9, (rank, ded, dd)
+        assert dle < 1e-10 and dl < 1e-9, (rank, dle, dl)

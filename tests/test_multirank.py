@@ -120,3 +120,47 @@ def test_split_is_a_partition():
             assert parts[0][0] == 0 and parts[-1][1] == n
             assert all(parts[r][1] == parts[r + 1][0] for r in range(size - 1))
             assert max(hi - lo for lo, hi in parts) - min(hi - lo for lo, hi in parts) <= 1
+
+
+def _worker_lambda(rank, world, port, lam_path, q):
+    """HBAR + Lambda with an a-sharded <ab|ef>: the t1.<ab|ef> term of Hvvvo and the Lambda ladder are rank-local pieces
+    summed by all-reduces, everything else is replicated."""
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import pycc_b200
+        from pycc_b200.parallel import Comm
+        from tests import emu
+        from tests.test_lambda import load
+        g, syn, model = load(lam_path)
+        with emu.install():
+            cc = pycc_b200.ccwfn(syn, model=model, device="GPU", quiet=True, comm=Comm())
+            cc.t1, cc.t2 = torch.from_numpy(g["t1"].copy()), torch.from_numpy(g["t2"].copy())
+            hb = pycc_b200.cchbar(cc)
+            dh = float(np.abs(hb.Hvvvo.numpy() - g["Hvvvo"]).max())
+            lm = pycc_b200.cclambda(cc, hb)
+            lecc = lm.solve_lambda(1e-12, 1e-12, 100)
+            q.put((rank, dh, abs(float(lecc) - float(g["lecc"])), float(np.abs(lm.l2.numpy() - g["conv_l2"]).max()),
+                   len(lm.trace), len(g["trace_lecc_rms"])))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_lambda_with_sharded_vvvv(world):
+    import glob
+    path = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "lam_o4v10_s1_noise_ccsd.npz")))[0]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 500) + 20 + world
+    procs = [ctx.Process(target=_worker_lambda, args=(r, world, port, path, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, dh, de, dl, n, nref in res:
+        assert dh < 1e-12 and de < 1e-11 and dl < 1e-10 and n == nref, (rank, dh, de, dl, n, nref)
