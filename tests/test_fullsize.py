@@ -26,6 +26,17 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.fixture(autouse=True)
+def _release_device_memory():
+    """these tests hold up to ~70 GB: hand cached blocks back before and after each of them"""
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    yield
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
 @pytest.fixture(scope="module")
 def config1():
     """o=20, v=150 solved to 1e-10 (BASELINE configs[1])"""
