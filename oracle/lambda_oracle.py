@@ -63,9 +63,10 @@ def tau(t1, t2):
 class Hbar:
     """All eleven HBAR blocks for amplitudes (t1, t2); model 'CCSD' or 'CCD' (cchbar.py:54-99)."""
 
-    def __init__(self, P, t1, t2, model="CCSD"):
+    def __init__(self, P, t1, t2, model="CCSD", F=None):
         ccd = model == "CCD"                      # 'CCSD(T)' builds the CCSD blocks (cchbar.py has no (T) branch)
-        o, v, F = P.o, P.v, P.F
+        o, v = P.o, P.v
+        F = P.F if F is None else F               # cclambda.residuals rebuilds HBAR with the passed (field-dressed) F
         tt = tau(t1, t2)
         oovv, Loovv = eri(P, "oovv"), lint(P, "oovv")
         # ---- one-body (cchbar.py:147-153, 201-210, 264-273)
@@ -177,9 +178,9 @@ def pseudoenergy(P, l2):
     return 0.5 * es("ijab,ijab->", eri(P, "oovv"), l2)      # cclambda.py:570
 
 
-def residuals(P, t1, t2, l1, l2, model="CCSD", s1=None, s2=None):
-    """cclambda.py:202-256: HBAR rebuilt from (t1, t2), then r_L1 / r_L2"""
-    H = Hbar(P, t1, t2, model)
+def residuals(P, t1, t2, l1, l2, model="CCSD", s1=None, s2=None, F=None):
+    """cclambda.py:202-256: HBAR rebuilt from (F, t1, t2), then r_L1 / r_L2 (amplitudes may be complex: RT-CC)"""
+    H = Hbar(P, t1, t2, model, F)
     gvv, goo = Gvv(t2, l2), Goo(t2, l2)
     return r_L1(H, l1, l2, gvv, goo, model, s1), r_L2(P, H, l1, l2, gvv, goo, model, s2)
 

@@ -87,13 +87,16 @@ class cclambda(object):
             K.strided_axpby(out, s1, 1.0, 1.0)
         return self._accumulate(out, _R1, env)
 
-    def _ladder(self, half, l2, Hvvvv=None):
+    def _ladder(self, half, l2, Hvvvv=None, t1=None, t2=None):
         """half += 1/2 l2_ijef H_efab (cclambda.py:468) WITHOUT the v^4 tensor H_efab:
              1/2 l2_ijef <ef|ab>                      the ladder GEMM of the CCSD residual on <ab|ef> in place
            - 1/2 (l2_ijef t_mf) <em|ab> - 1/2 (l2_ijef t_me) <fm|ba>                     two o^3v^3 products
            + 1/2 (l2_ijef tau_mnef) <mn|ab>                                              two o^4v^2 products
-        (cchbar.py:394-403 substituted).  A caller that hands in a materialised ``Hvvvv`` gets the literal term."""
+        (cchbar.py:394-403 substituted).  A caller that hands in a materialised ``Hvvvv`` gets the literal term.
+        ``t1, t2``: the amplitudes HBAR is built from (default: the wavefunction's)."""
         w, ct = self.ccwfn, self.ccwfn._ct
+        t1 = w.t1 if t1 is None else t1
+        t2 = w.t2 if t2 is None else t2
         if Hvvvv is not None:
             return ct("ijef,efab->ijab", l2, Hvvvv, out=half, alpha=0.5, beta=1.0)
         with K.mixed_mode(getattr(w, "mixed", False)):
@@ -109,17 +112,18 @@ class cclambda(object):
             o, v = w.o, w.v
             oovv = w.H.ERI[o, o, v, v]
             if w.model == "CCD":
-                tau = w.t2.contiguous()
+                tau = t2.contiguous()
             else:
-                t1 = w.t1.contiguous()
+                t1 = t1.contiguous()
                 vovv = w.H.ERI[v, o, v, v]
                 ct("ijem,emab->ijab", ct("ijef,mf->ijem", l2, t1), vovv, out=half, alpha=-0.5, beta=1.0)
                 ct("ijfm,fmba->ijab", ct("ijef,me->ijfm", l2, t1), vovv, out=half, alpha=-0.5, beta=1.0)
-                tau = K.build_tau(t1, w.t2.contiguous(), 1.0, 1.0)
+                tau = K.build_tau(t1, t2.contiguous(), 1.0, 1.0)
             ct("ijmn,mnab->ijab", ct("ijef,mnef->ijmn", l2, tau), oovv, out=half, alpha=0.5, beta=1.0)
         return half
 
-    def _r_L2_half(self, l1, l2, Hov, Hvv, Hoo, Hoooo, Hvvvv, Hovvo, Hovov, Hvovv, Hooov, Gvv, Goo, W, s2=None):
+    def _r_L2_half(self, l1, l2, Hov, Hvv, Hoo, Hoooo, Hvvvv, Hovvo, Hovov, Hvovv, Hooov, Gvv, Goo, W, s2=None,
+                   t1=None, t2=None):
         Loovv = self.ccwfn.H.derived("Loovv")
         l2 = l2.contiguous()
         env = dict(l1=l1.contiguous(), l2=l2, Hov=Hov, Hvv=Hvv, Hoo=Hoo, Hoooo=Hoooo,
@@ -129,7 +133,7 @@ class cclambda(object):
         if s2 is not None:                                   # (T) source: + 1/2 cc.S2 before P_ij^ab   cclambda.py:470-474
             K.strided_axpby(half, s2, 0.5, 1.0)
         self._accumulate(half, terms, env)
-        return self._ladder(half, l2, Hvvvv)
+        return self._ladder(half, l2, Hvvvv, t1, t2)
 
     def r_L2(self, o, v, l1, l2, L, Hov, Hvv, Hoo, Hoooo, Hvvvv, Hovvo, Hovov, Hvvvo, Hovoo, Hvovv, Hooov, Gvv, Goo,
              s2=None):
@@ -150,7 +154,12 @@ class cclambda(object):
         return 0.5 * K.multi_dot(oovv.reshape(-1), [l2.contiguous().reshape(-1)])[0]
 
     def residuals(self, F, t1, t2, l1, l2):
-        """(r1, r2) with HBAR rebuilt from (F, t1, t2)                                      cclambda.py:202-256"""
+        """(r1, r2) with HBAR rebuilt from (F, t1, t2)                                      cclambda.py:202-256
+        Complex amplitudes / a complex Hermitian F (the Lambda half of rtcc.f, rt/rtcc.py:143-147) are evaluated from
+        five real samples (utils.complex_from_real_samples; the residual is exactly quartic in the joint scaling)."""
+        from .utils import complex_from_real_samples, is_complex
+        if any(is_complex(x) for x in (F, t1, t2, l1, l2)):
+            return tuple(complex_from_real_samples(self.residuals, (F, t1, t2, l1, l2), self.l2.device))
         hb = self.hbar.build_all(F, t1, t2)
         Goo, Gvv = self.build_Goo(t2, l2), self.build_Gvv(t2, l2)
         W = self._w(hb["Hovvo"], hb["Hovov"])
@@ -158,7 +167,7 @@ class cclambda(object):
         r1 = self.r_L1(self.ccwfn.o, self.ccwfn.v, l1, l2, hb["Hov"], hb["Hvv"], hb["Hoo"], hb["Hovvo"], hb["Hovov"],
                        hb["Hvvvo"], hb["Hovoo"], hb["Hvovv"], hb["Hooov"], Gvv, Goo, W=W)
         half = self._r_L2_half(l1, l2, hb["Hov"], hb["Hvv"], hb["Hoo"], hb["Hoooo"], None, hb["Hovvo"],
-                               hb["Hovov"], hb["Hvovv"], hb["Hooov"], Gvv, Goo, W)
+                               hb["Hovov"], hb["Hvovv"], hb["Hooov"], Gvv, Goo, W, t1=t1, t2=t2)
         return r1, K.symmetrize_r2(half)
 
     # ---- solve_lambda (cclambda.py:69-200) -------------------------------------------------------------------

@@ -213,63 +213,20 @@ class CCwfn(object):
         K.symmetrize_r2(half)
         return r1, half
 
-    # ---- complex amplitudes / field-dressed Fock matrix: the RT-CC right-hand side (rt/rtcc.py:136-141) ----------
-    # sample points s and the weights that turn {R(s)} into Re R(i), Im R(i) for a polynomial R of degree <= 4
-    _CPTS = (-2.0, -1.0, 0.0, 1.0, 2.0)
-    _CRE = (1.0 / 12.0, -5.0 / 6.0, 2.5, -5.0 / 6.0, 1.0 / 12.0)
-    _CIM = (1.0 / 6.0, -5.0 / 6.0, 0.0, 5.0 / 6.0, -1.0 / 6.0)
-
     def _residuals_complex(self, F, t1, t2):
-        """(r1, r2) for COMPLEX t1, t2 (and optionally a complex Hermitian F) as torch.complex128 tensors.
+        """(r1, r2) for COMPLEX t1, t2 (and optionally a complex Hermitian F) as torch.complex128 tensors: the RT-CC
+        right-hand side (rt/rtcc.py:136-141).  Five fused real residuals, see utils.complex_from_real_samples -- a
+        complex right-hand side costs 5 real residuals where complex arithmetic would cost 4 (3 with the 3M trick)
+        real GEMMs per contraction, with the same kernels and the same sharding over ranks."""
+        from .utils import complex_from_real_samples
 
-        The CCSD residual is a polynomial of total degree <= 4 in (F, t1, t2) when all three are scaled together
-        (quartic in t1; every Fock term carries at most two amplitudes).  Hence for x = x_re + s x_im the map
-        s -> R(F(s), t1(s), t2(s)) is a real polynomial of degree <= 4 in the REAL parameter s, and its value at
-        s = i follows exactly from five real evaluations:
-            Re R(i) = 5/2 R(0) - 5/6 [R(1) + R(-1)] + 1/12 [R(2) + R(-2)]
-            Im R(i) = 5/6 [R(1) - R(-1)] - 1/6 [R(2) - R(-2)]
-        Each evaluation is the fused FP64 residual of the energy path (same kernels, same sharding over ranks), so
-        the complex right-hand side costs 5 real residuals -- against 4 (3 with the 3M trick) real GEMMs per
-        contraction for complex arithmetic -- and needs no complex kernels; the weights sum to |w| = 4.3, so
-        round-off is amplified by less than one digit."""
-        dev = self.device1
-
-        def planes(x):
-            if not isinstance(x, torch.Tensor):
-                x = torch.from_numpy(np.ascontiguousarray(np.asarray(x)))
-            x = x.to(dev)
-            ident = tuple(range(x.dim()))
-            if x.is_complex():
-                xr = torch.view_as_real(x.to(torch.complex128))
-                return K.permuted(xr[..., 0], ident), K.permuted(xr[..., 1], ident)
-            return K.permuted(x.to(F64), ident), None
-
-        def at(re, im, s):
-            if im is None or s == 0.0:
-                return re
-            out = torch.empty_like(re)
-            return K.axpbyz(1.0, re, s, im, out)
-
-        (Fr, Fi), (t1r, t1i), (t2r, t2i) = planes(F), planes(t1), planes(t2)
-        R1, R2 = [], []
-        for s in self._CPTS:
-            r1, half = self._residuals_half(at(Fr, Fi, s), at(t1r, t1i, s), at(t2r, t2i, s))
+        def real_residual(Fs, t1s, t2s):
+            r1, half = self._residuals_half(Fs, t1s, t2s)
             K.symmetrize_r2(half)
-            R1.append(r1.contiguous())
-            R2.append(half.view(t2r.shape))
-        out = []
-        for R, shape in ((R1, t1r.shape), (R2, t2r.shape)):
-            z = torch.empty(tuple(shape), dtype=torch.complex128, device=dev)
-            zr = torch.view_as_real(z)
-            tmp = torch.empty(tuple(shape), dtype=F64, device=dev)
-            flat = [r.reshape(-1) for r in R]
-            K.multi_axpy(self._CRE, flat, tmp.view(-1))
-            K.strided_axpby(zr[..., 0], tmp, 1.0, 0.0)
-            K.multi_axpy([w for w in self._CIM if w != 0.0], [r for r, w in zip(flat, self._CIM) if w != 0.0],
-                         tmp.view(-1))
-            K.strided_axpby(zr[..., 1], tmp, 1.0, 0.0)
-            out.append(z)
-        return out[0], out[1]
+            return r1, half.view(t2s.shape)
+
+        r1, r2 = complex_from_real_samples(real_residual, (F, t1, t2), self.device1)
+        return r1, r2
 
     def _check_F(self, F):
         if not isinstance(F, torch.Tensor):

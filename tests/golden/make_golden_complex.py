@@ -43,6 +43,23 @@ def case(mods, tag):
     for name, F in (("el", F_el), ("mag", F_mag)):
         r1, r2 = w.residuals(F, t1, t2, real_time=True)
         out["r1_" + name], out["r2_" + name] = np.array(r1), np.array(r2)
+    # the Lambda half of rtcc.f (rt/rtcc.py:143-147): cclambda.residuals with complex t AND complex lambda amplitudes
+    import contextlib
+    import importlib
+    import io
+    cchbar = importlib.import_module("pycc.cchbar").cchbar
+    cclambda = importlib.import_module("pycc.cclambda").cclambda
+    w.t1, w.t2 = g["conv_t1"].copy(), g["conv_t2"].copy()
+    with contextlib.redirect_stdout(io.StringIO()):
+        lam = cclambda(w, cchbar(w))
+    l1 = 2.0 * g["conv_t1"] + 0.03 * (rng.standard_normal((no, nv)) + 1j * rng.standard_normal((no, nv)))
+    l2 = 0.03 * (rng.standard_normal((no, no, nv, nv)) + 1j * rng.standard_normal((no, no, nv, nv)))
+    l2 = l2 + 2.0 * (2.0 * g["conv_t2"] - g["conv_t2"].swapaxes(2, 3))
+    out["l1"], out["l2"] = l1, l2
+    for name, F in (("el", F_el), ("mag", F_mag)):
+        with contextlib.redirect_stdout(io.StringIO()):
+            q1, q2 = lam.residuals(F, t1, t2, l1, l2)
+        out["rl1_" + name], out["rl2_" + name] = np.array(q1), np.array(q2)
     # real amplitudes in a complex container must reproduce the real path
     r1, r2 = w.residuals(syn.F, g["conv_t1"].astype(complex), g["conv_t2"].astype(complex), real_time=True)
     out["r1_realamps"], out["r2_realamps"] = np.array(r1), np.array(r2)

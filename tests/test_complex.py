@@ -12,7 +12,7 @@ import torch
 
 import pycc_b200
 from pycc_b200.synthetic import Synthetic, blocks_from_factor, make_synthetic
-from oracle import ccsd_oracle as co
+from oracle import ccsd_oracle as co, lambda_oracle as lo
 from tests import emu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -100,3 +100,25 @@ def test_medium_size_complex_vs_oracle(no, nv, seed):
         assert np.abs(q2.cpu().numpy() - r2).max() < 1e-9
     finally:
         DEV[0] = torch.device("cpu")
+
+
+# ---- the Lambda half of rtcc.f: cclambda.residuals(F, t1, t2, l1, l2) with complex t and complex lambda ------------
+def test_oracle_complex_lambda_residuals(cplx):
+    g, r, syn = cplx
+    P = co.Problem(blocks_from_factor(syn), syn.F, syn.no)
+    for name in ("el", "mag"):
+        q1, q2 = lo.residuals(P, g["t1"], g["t2"], g["l1"], g["l2"], F=g["F_" + name])
+        assert np.abs(q1 - g["rl1_" + name]).max() < 1e-12, name
+        assert np.abs(q2 - g["rl2_" + name]).max() < 1e-12, name
+
+
+@pytest.mark.parametrize("field", ["el", "mag"])
+def test_complex_lambda_residuals_match_reference(cplx, dev, field):
+    g, r, syn = cplx
+    cc = pycc_b200.ccwfn(syn, model="CCSD", device="GPU", quiet=True)
+    cc.t1, cc.t2 = T(r["conv_t1"]), T(r["conv_t2"])
+    lm = pycc_b200.cclambda(cc, pycc_b200.cchbar(cc))
+    q1, q2 = lm.residuals(T(g["F_" + field]), T(g["t1"]), T(g["t2"]), T(g["l1"]), T(g["l2"]))
+    assert q1.is_complex() and q2.is_complex()
+    assert np.abs(q1.cpu().numpy() - g["rl1_" + field]).max() < 1e-10
+    assert np.abs(q2.cpu().numpy() - g["rl2_" + field]).max() < 1e-10
