@@ -49,25 +49,37 @@ def triples_list(no):
 class TriplesEngine:
     """Owns the constant operands of the (T) GEMMs for one wavefunction state."""
 
-    def __init__(self, ccwfn, t1=None, t2=None, q_bytes=None, use_tma=True, cube_q=False):
+    def __init__(self, ccwfn, t1=None, t2=None, q_bytes=None, use_tma=True, cube_q=False, dressed=None):
+        """``dressed = (Wvvvo, Wovoo)``: build the t3 numerators of cctriples.py:50-62 from these blocks ([a,b,e,i] and
+        [m,b,i,j], no permutational symmetry assumed -- the T1-dressed CC3 intermediates) instead of the integrals."""
         self.w = ccwfn
         H = ccwfn.H
         self.no, self.nv = ccwfn.no, ccwfn.nv
         self.t1 = (ccwfn.t1 if t1 is None else t1).contiguous()
         self.t2 = (ccwfn.t2 if t2 is None else t2).contiguous()
-        self.ovvv = H.block("ovvv")
         self.oovv = H.block("oovv")
-        # Y[j,k,c,m] = -<mc|jk> = -ooov[j,k,m,c]
-        self.Y = K.permuted(H.block("ooov"), (0, 1, 3, 2), -1.0)
         self.fov = H.F[ccwfn.o, ccwfn.v]
         self.dev = self.t2.device
         # TMA path (K-major operands for cp.async.bulk.tensor): needs even o, v (16-byte pitches) and one
-        # constant transposed copy of <mb|ef>,  G[i,a,b,e] = <ib|ea>-slab = ovvv[i,e,a,b], built once per H
+        # transposed copy of the particle-term operand,  G[i,a,b,e] = Wvvvo[b,a,e,i]  (= ovvv[i,e,a,b] for the
+        # integrals: constant, built once per H)
         self.tma = (self.nv % 2 == 0) and (self.no % 2 == 0) and use_tma
+        if dressed is None:
+            self.ovvv = H.block("ovvv")
+            # Y[j,k,c,m] = -<mc|jk> = -ooov[j,k,m,c]
+            self.Y = K.permuted(H.block("ooov"), (0, 1, 3, 2), -1.0)
+        else:
+            Wvvvo, Wovoo = dressed
+            # the natural-layout operand of the non-TMA path is [i][e][(a,b)] = Wvvvo[b,a,e,i]
+            self.ovvv = None if self.tma else K.permuted(Wvvvo, (3, 2, 1, 0))
+            self.Y = K.permuted(Wovoo, (2, 3, 1, 0), -1.0)        # Y[j,k,c,m] = -Wovoo[m,c,j,k]
         if self.tma:
-            if "ovvv_iabe" not in H._derived:
-                H._derived["ovvv_iabe"] = K.permuted(self.ovvv, (0, 2, 3, 1))
-            self.G = H._derived["ovvv_iabe"]
+            if dressed is not None:
+                self.G = K.permuted(dressed[0], (3, 1, 0, 2))
+            else:
+                if "ovvv_iabe" not in H._derived:
+                    H._derived["ovvv_iabe"] = K.permuted(self.ovvv, (0, 2, 3, 1))
+                self.G = H._derived["ovvv_iabe"]
             self.t2p = K.permuted(self.t2, (0, 2, 3, 1))          # [i,a,b,m] = t2[i,m,a,b]
         # precision='MP': the (T) GEMMs run on the split-TF32 tcgen05 kernel.  Amplitudes and <mc|jk> are constant for
         # the lifetime of this engine, so their TF32 planes are split once (kernels._split_operand cache); close()
@@ -535,3 +547,75 @@ def t3_density(o, v, no, nv, t1, t2, F, ERI, L, contract, comm=None, k_batch=Non
     K.axpbyz(1.0, d1, 1.0, d2, et)
     return et[0], {'Doo': Doo, 'Dvv': Dvv, 'Dov': Dov, 'Goovv': Goovv, 'Gooov': Gooov, 'Gvvvo': Gvvvo,
                    'S1': S1, 'S2': S2}
+
+
+# ---- CC3: connected-triples contribution to the T residuals ----------------------------------
+def cc3_t_residual(ccwfn, F, t1, t2, Fme, W, k_batch=None, work_bytes=None):
+    """(X1, X2) of ``CCwfn._cc3_t_residual`` (reference: ccwfn.py:374-430, real_time = False) from the T1-dressed
+    intermediates ``W`` (dict with Wabei, Wmbij, Wmnie, Wamef in the reference's index orders).
+
+    Same machinery as :func:`t3_density`, fed with dressed operands: for a pair i >= j and a run of k the t3
+    numerators are the batched two-segment GEMMs of the (T) engine on (Wabei, Wmbij); ``b200cc_t3_connected_batch``
+    applies the denominators; because t3(j,i,k)[b,a,c] = t3(i,j,k)[a,b,c] holds for ANY W, one build serves the loop
+    bodies (i,j) and (j,i).  ``b200cc_t3_density_forms`` then delivers, with its weight arrays pointed at L_jkbc and
+    H_me,  P = 2 t3 - t3[acb] - t3[cba]  in both K-major layouts,  X1[i] += (t3 - t3[cba]) L_jkbc  and the H_me part of
+    X2[i,j]; the two remaining terms are long-K GEMMs with k folded into the summation index:
+        X2[i,j][a,d] += P[a,(k,b,c)] W_amef[d,k,b,c]        X2[i][(a,b),l] -= P[(a,b),(k,c)] W_mnie[j,k,l,c]."""
+    import types
+    H = ccwfn.H
+    no, nv, o, v = ccwfn.no, ccwfn.nv, ccwfn.o, ccwfn.v
+    t1, t2 = t1.contiguous(), t2.contiguous()
+    dev = t2.device
+    eo, ev = _eps(F, o, v)
+    shim = types.SimpleNamespace(H=H, no=no, nv=nv, t1=t1, t2=t2, o=o, v=v, eps_o=eo, eps_v=ev, mixed=False)
+    v2, v3 = nv * nv, nv ** 3
+    z = lambda *shape: torch.zeros(shape, dtype=F64, device=dev)
+    if work_bytes is None:
+        work_bytes = 24 << 30
+        if dev.type == "cuda":
+            work_bytes = int(torch.cuda.mem_get_info(dev)[0] * 0.6)
+    # per k of a run: Q (6 v^3) + M3 + (unused W2 operands written by the forms kernel: 2) + two bodies x (Pab, Pn)
+    kb = int(max(1, min(no, work_bytes // (13 * 8 * v3)))) if k_batch is None else int(max(1, min(no, k_batch)))
+    kb = max(1, min(kb, (2 ** 32 - 1) // v3))
+    kb = -(-no // -(-no // kb))
+    eng = TriplesEngine(shim, t1, t2, q_bytes=kb * 6 * v3 * 8, dressed=(W["Wabei"], W["Wmbij"]))
+    Wamef = W["Wamef"].contiguous()                               # [d,k,b,c]: K-major in (k,b,c) as stored
+    Wq = K.permuted(W["Wmnie"], (0, 2, 1, 3))                      # [j,l,k,c]
+    Loovv = H.derived("Loovv")
+    Fme = Fme.contiguous()
+    X1, X2 = z(no, nv), z(no, no, nv, nv)
+    X2T = z(no, v2, no)                                           # [i][(a,b)][l]
+    M3 = torch.empty(kb * v3, dtype=F64, device=dev)
+    junk = [torch.empty(kb * v3, dtype=F64, device=dev) for _ in range(2)]       # W2 outputs of the forms kernel
+    Pab = [torch.empty(kb * v3, dtype=F64, device=dev) for _ in range(2)]
+    NB = torch.empty(2 * kb * v3, dtype=F64, device=dev)         # [Pn(0) | Pn(1)]
+    Ctmp = torch.empty(2 * v2, dtype=F64, device=dev)
+    gij, dv, s1 = z(nv, nv), z(nv), z(nv)                         # accumulators of the forms kernel that CC3 ignores
+    try:
+        for j0 in range(no):
+            for i0 in range(j0, no):
+                bodies = ((i0, j0, False),) if i0 == j0 else ((i0, j0, False), (j0, i0, True))
+                nb = len(bodies)
+                for k0 in range(0, no, kb):
+                    nk = min(kb, no - k0)
+                    trip = [(i0, j0, k) for k in range(k0, k0 + nk)]
+                    ijk = torch.tensor(np.asarray(trip, dtype=np.int32), dtype=torch.int32).to(dev)
+                    Q = eng.build_q(trip)
+                    K.t3_connected_batch(no, nv, ijk, Q, eo, ev, M3)
+                    kc, kbc, seg = nk * nv, nk * v2, nk * v3
+                    for q, (i, j, swap) in enumerate(bodies):
+                        # weights: "t2s" -> L_jkbc (its Dov output is the X1[i] increment), "fov" -> H_me
+                        K.t3_density_forms(no, nv, i, j, k0, nk, M3, t1, Loovv, Loovv, Fme, eo, ev, junk[0], junk[1],
+                                           Pab[q], NB[q * seg:(q + 1) * seg], gij, X2[i, j], dv, X1[i], s1,
+                                           swap_ab=swap)
+                        K.dgemm(v2, no, kc, Pab[q], kc, 0, (Wq, (j * no * no + k0) * nv), no * nv, 0, X2T[i], no,
+                                -1.0, 1.0)
+                    M = nb * nv
+                    K.dgemm(M, nv, kbc, NB, kbc, 0, (Wamef, k0 * v2), no * v2, 0, Ctmp, nv, 1.0, 0.0,
+                            ksplit=K.balanced_ksplit(M, nv, kbc))
+                    for q, (i, j, _) in enumerate(bodies):
+                        K.axpbyz(1.0, X2[i, j].view(-1), 1.0, Ctmp[q * v2:(q + 1) * v2], X2[i, j].view(-1))
+    finally:
+        eng.close()
+    K.strided_axpby(X2, X2T.view(no, nv, nv, no).permute(0, 3, 1, 2), 1.0, 1.0)
+    return X1, X2

@@ -46,7 +46,7 @@ class CCwfn(object):
     """See module docstring.  Constructor mirrors pycc/ccwfn.py:76-213 for the closed-shell path."""
 
     VALID_MODELS = ['CCD', 'CC2', 'CCSD', 'CCSD(T)', 'CC3']
-    SUPPORTED_MODELS = ['CCD', 'CCSD', 'CCSD(T)']
+    SUPPORTED_MODELS = ['CCD', 'CCSD', 'CCSD(T)', 'CC3']
 
     def __init__(self, scf_wfn, **kwargs):
         t0 = time.time()
@@ -54,7 +54,7 @@ class CCwfn(object):
         if model not in self.VALID_MODELS:
             raise InvalidKeywordError('model', model, self.VALID_MODELS)
         if model not in self.SUPPORTED_MODELS:
-            raise NotImplementedError("pycc_b200 accelerates the closed-shell CCD/CCSD/CCSD(T) energy path; "
+            raise NotImplementedError("pycc_b200 accelerates the closed-shell CCD/CCSD/CCSD(T)/CC3 energy path; "
                                       "model %r stays with the reference implementation" % model)
         self.model = self.method = model
         self.e_conv, self.r_conv, self.maxiter = 1e-7, 1e-7, 100
@@ -184,6 +184,81 @@ class CCwfn(object):
             setattr(self, name, value)
         return et
 
+    # =============================================================================================
+    # CC3 (ccwfn.py:374-430, 947-1120): T1-dressed intermediates and the connected-triples terms
+    # =============================================================================================
+    def _E(self, pat):
+        return self.H.ERI[tuple(self.o if c == 'o' else self.v for c in pat)]
+
+    def build_cc3_Wmnij(self, o, v, ERI, t1):
+        """W_mnij = <mn|ij> + t_ja <mn|ia> + t_ia <nm|ja> + t_ie t_jf <mn|ef>          (ccwfn.py:947-977)"""
+        self._own(ERI)
+        ct, t1 = self._ct, t1.contiguous()
+        W = K.permuted(self._E('oooo'), (0, 1, 2, 3))
+        tmp = ct('ijma,na->ijmn', self._E('ooov'), t1)
+        K.strided_axpby(W, tmp, 1.0, 1.0)
+        K.strided_axpby(W, tmp.permute(1, 0, 3, 2), 1.0, 1.0)
+        ct('mnif,jf->mnij', ct('ia,mnaf->mnif', t1, self._E('oovv')), t1, out=W, alpha=1.0, beta=1.0)
+        return W
+
+    def build_cc3_Wmbij(self, o, v, ERI, t1, Wmnij):
+        """W_mbij = <mb|ij> - W_mnij t_nb + t_je <mb|ie> + t_ie (<mb|ej> + t_jf <mb|ef>)   (ccwfn.py:979-1008)"""
+        self._own(ERI)
+        ct, t1 = self._ct, t1.contiguous()
+        W = K.permuted(self._E('ovoo'), (0, 1, 2, 3))
+        ct('mnij,nb->mbij', Wmnij, t1, out=W, alpha=-1.0, beta=1.0)
+        ct('mbie,je->mbij', self._E('ovov'), t1, out=W, alpha=1.0, beta=1.0)
+        tmp = K.permuted(self._E('ovvo'), (0, 1, 2, 3))
+        ct('mbef,jf->mbej', self._E('ovvv'), t1, out=tmp, alpha=1.0, beta=1.0)
+        ct('ie,mbej->mbij', t1, tmp, out=W, alpha=1.0, beta=1.0)
+        return W
+
+    def build_cc3_Wmnie(self, o, v, ERI, t1):
+        """W_mnie = <mn|ie> + t_if <mn|fe>                                           (ccwfn.py:1010-1031)"""
+        self._own(ERI)
+        W = K.permuted(self._E('ooov'), (0, 1, 2, 3))
+        return self._ct('if,mnfe->mnie', t1.contiguous(), self._E('oovv'), out=W, alpha=1.0, beta=1.0)
+
+    def build_cc3_Wamef(self, o, v, ERI, t1):
+        """W_amef = <am|ef> - t_na <nm|ef>                                           (ccwfn.py:1033-1052)"""
+        self._own(ERI)
+        W = K.permuted(self._E('vovv'), (0, 1, 2, 3))
+        return self._ct('na,nmef->amef', t1.contiguous(), self._E('oovv'), out=W, alpha=-1.0, beta=1.0)
+
+    def build_cc3_Wabei(self, o, v, ERI, t1):
+        """W_abei = Z_abei + Z_eiab^T with                                           (ccwfn.py:1054-1120)
+             Z_eiab = <ei|ab> + t_if <ab|ef> - t_mb (<ei|am> + t_if <am|ef>) + t_ma t_nb (<mn|ei> + t_if <mn|ef>)
+             Z_abei = -t_ma (<mb|ei> + t_if <mb|ef>)
+        (the reference's symmetric + antisymmetric split of <ab|ef> sums back to the block: ONE pass over <ab|ef>)."""
+        self._own(ERI)
+        if self.part.size > 1:
+            raise NotImplementedError("CC3 intermediates need the whole <ab|ef> block on this rank")
+        ct, t1 = self._ct, t1.contiguous()
+        Z = K.permuted(self._E('vovv'), (0, 1, 2, 3))                                   # [e,i,a,b]
+        ct('if,abef->eiab', t1, self._E('vvvv'), out=Z, alpha=1.0, beta=1.0)
+        Zeiam = K.permuted(self._E('vovo'), (0, 1, 2, 3))
+        K.strided_axpby(Zeiam, ct('amef,if->amei', self._E('vovv'), t1).permute(2, 3, 0, 1), 1.0, 1.0)
+        ct('eiam,mb->eiab', Zeiam, t1, out=Z, alpha=-1.0, beta=1.0)
+        Zmnei = K.permuted(self._E('oovo'), (0, 1, 2, 3))
+        ct('mnef,if->mnei', self._E('oovv'), t1, out=Zmnei, alpha=1.0, beta=1.0)
+        ct('anei,nb->eiab', ct('ma,mnei->anei', t1, Zmnei), t1, out=Z, alpha=1.0, beta=1.0)
+        Zmbei = K.permuted(self._E('ovvo'), (0, 1, 2, 3))
+        ct('mbef,if->mbei', self._E('ovvv'), t1, out=Zmbei, alpha=1.0, beta=1.0)
+        W = ct('ma,mbei->abei', t1, Zmbei, alpha=-1.0)
+        return K.strided_axpby(W, Z.permute(2, 3, 0, 1), 1.0, 1.0)
+
+    def _cc3_t_residual(self, o, v, F, ERI, L, t1, t2, Fme, real_time=False):
+        """(X1, X2): the connected-triples contributions to the T1 / T2 residuals (ccwfn.py:374-430)."""
+        if real_time:
+            raise NotImplementedError("the explicit-field (real-time) CC3 triples are outside the accelerated path")
+        self._own(ERI, L)
+        from . import cctriples
+        t1 = t1.contiguous()
+        Wmnij = self.build_cc3_Wmnij(o, v, ERI, t1)
+        W = {"Wmbij": self.build_cc3_Wmbij(o, v, ERI, t1, Wmnij), "Wmnie": self.build_cc3_Wmnie(o, v, ERI, t1),
+             "Wamef": self.build_cc3_Wamef(o, v, ERI, t1), "Wabei": self.build_cc3_Wabei(o, v, ERI, t1)}
+        return cctriples.cc3_t_residual(self, self._check_F(F), t1, t2, Fme, W)
+
     def iterate(self, F=None):
         """One Jacobi step of solve_cc (ccwfn.py:272-286): residuals, then ONE fused pass doing
         r2 = half + half^T (790), t += r/D and sum (r/D)^2 (281-284), then the energy (286).
@@ -258,6 +333,12 @@ class CCwfn(object):
         K.strided_axpby(r1, r1p, 1.0, 1.0)
         if self.model == 'CCD':
             r1.zero_()
+        if self.model == 'CC3':
+            # connected triples (ccwfn.py:364-367): r1 += X1, r2 += X2 + X2^T -- X2 joins the unsymmetrised half
+            Fme = self.build_Fme(self.o, self.v, F, self.H.L, t1)
+            X1, X2 = self._cc3_t_residual(self.o, self.v, F, self.H.ERI, self.H.L, t1, t2, Fme)
+            K.strided_axpby(r1, X1, 1.0, 1.0)
+            K.strided_axpby(half, X2, 1.0, 1.0)
         return r1, half
 
     # ---- shared per-iteration rearrangements of the amplitudes -----------------------------------
