@@ -46,7 +46,7 @@ class CCwfn(object):
     """See module docstring.  Constructor mirrors pycc/ccwfn.py:76-213 for the closed-shell path."""
 
     VALID_MODELS = ['CCD', 'CC2', 'CCSD', 'CCSD(T)', 'CC3']
-    SUPPORTED_MODELS = ['CCD', 'CCSD', 'CCSD(T)', 'CC3']
+    SUPPORTED_MODELS = ['CCD', 'CC2', 'CCSD', 'CCSD(T)', 'CC3']
 
     def __init__(self, scf_wfn, **kwargs):
         t0 = time.time()
@@ -54,7 +54,7 @@ class CCwfn(object):
         if model not in self.VALID_MODELS:
             raise InvalidKeywordError('model', model, self.VALID_MODELS)
         if model not in self.SUPPORTED_MODELS:
-            raise NotImplementedError("pycc_b200 accelerates the closed-shell CCD/CCSD/CCSD(T)/CC3 energy path; "
+            raise NotImplementedError("pycc_b200 accelerates the closed-shell CCD/CC2/CCSD/CCSD(T)/CC3 energy path; "
                                       "model %r stays with the reference implementation" % model)
         self.model = self.method = model
         self.e_conv, self.r_conv, self.maxiter = 1e-7, 1e-7, 100
@@ -320,14 +320,18 @@ class CCwfn(object):
         F = self._check_F(F)
         t1 = t1.contiguous()
         t2 = t2.contiguous()
-        I = self._intermediates(F, t1, t2)
+        cc2 = self.model == 'CC2'
+        I = self._intermediates(F, t1, t2, rings=not cc2)
         # one flat buffer [ r2 half | rank-partial part of r1 ] so that ONE all-reduce carries both
         n2, n1 = t2.numel(), t1.numel()
         buf = torch.empty(n2 + n1, dtype=F64, device=self.device1)
         half = buf[:n2].view(t2.shape)
         r1p = buf[n2:].view(t1.shape)
         r1 = self._r1(F, t1, t2, I, r1p)
-        self._r2_half(F, t1, t2, I, half)
+        if cc2:
+            self._r2_half_cc2(F, t1, t2, half)
+        else:
+            self._r2_half(F, t1, t2, I, half)
         if self.part.size > 1:
             self.part.all_reduce_sum(buf)
         K.strided_axpby(r1, r1p, 1.0, 1.0)
@@ -352,7 +356,7 @@ class CCwfn(object):
         A["s_iame"] = s
         return A
 
-    def _intermediates(self, F, t1, t2, full=False):
+    def _intermediates(self, F, t1, t2, full=False, rings=True):
         """Fae, Fmi, Fme (replicated) and the LOCAL slices of Wmnij (rows i_g), W1/W2 (columns j_g) and
         Z' (rows i_g).  ``full=True`` ignores the rank partition (public build_* methods)."""
         H, ct = self.H, self._ct
@@ -394,7 +398,7 @@ class CCwfn(object):
             ct("ne,mnie->mi", t1, H.derived("Looov"), out=Fmi, alpha=1.0, beta=1.0)
         I["Fae"], I["Fmi"] = Fae, Fmi
         del tauh
-        if ni == 0:
+        if ni == 0 or not rings:           # rings=False: the one-body intermediates only (CC2's r1)
             return I
 
         # ---------------- Wmnij[m,n,i_g,j]                               (ccwfn.py:596-603)
@@ -505,6 +509,47 @@ class CCwfn(object):
         # - t2_mnae L_nmei,  L_nmei = 2<mn|ie> - <nm|ie> = Looov[m,n,i,e]
         ct("mnae,mnie->ia", t2m, H.derived("Looov")[i0:i1], out=r1p, alpha=-1.0, beta=1.0)
         return r1
+
+    # ---- CC2 (ccwfn.py:596-602, 711-713, 832-884): doubles residual with bare-Fock Fae/Fmi and t1-only W / Z ----------
+    def _cc2_Wmnij(self, t1):
+        """<mn|ij> + t_je <mn|ie> + t_ie <mn|ej> + t_ie t_jf <mn|ef>                      (ccwfn.py:596-602)"""
+        ct = self._ct
+        W = K.permuted(self._E('oooo'), (0, 1, 2, 3))
+        ct('je,mnie->mnij', t1, self._E('ooov'), out=W, alpha=1.0, beta=1.0)
+        ct('ie,mnej->mnij', t1, self._E('oovo'), out=W, alpha=1.0, beta=1.0)
+        return ct('mnif,jf->mnij', ct('mnef,ie->mnif', self._E('oovv'), t1), t1, out=W, alpha=1.0, beta=1.0)
+
+    def _cc2_Zmbij(self, t1):
+        """<mb|ef> t_ie t_jf                                                              (ccwfn.py:711-713)"""
+        return self._ct('mbif,jf->mbij', self._ct('mbef,ie->mbif', self._E('ovvv'), t1), t1)
+
+    def _r2_half_cc2(self, F, t1, t2, half):
+        """The unsymmetrised CC2 doubles residual (ccwfn.py:868-881), term by term through the contraction backend.
+        t_ie t_jf <ab|ef> is ONE pass over <ab|ef> (M = v^3, N = o, K = v) followed by an o^2v^3 product -- 2 o v^4
+        flop, not the 2 o^2 v^4 of the CCSD ladder."""
+        ct = self._ct
+        o, v = self.o, self.v
+        if self.part.size > 1:
+            raise NotImplementedError("CC2 is single-GPU: its doubles terms are not rank-partitioned and t_ie t_jf <ab|ef> "
+                                      "needs the whole <ab|ef> block")
+        Fov = F[o, v]
+        K.strided_axpby(half, self.H.block("oovv"), 0.5, 0.0)                       # 1/2 <ab|ij>
+        # t2_ijae (f_be - 1/2 f_me t_mb) - 1/2 t2_ijae f_me t_mb  =  t2_ijae (f_be - f_me t_mb)
+        Y = K.permuted(F[v, v], (0, 1))
+        ct('mb,me->be', t1, Fov, out=Y, alpha=-1.0, beta=1.0)
+        ct('ijae,be->ijab', t2, Y, out=half, alpha=1.0, beta=1.0)
+        # - t2_imab (f_mj + 1/2 f_me t_je) - 1/2 t2_imab f_me t_je  =  - t2_imab (f_mj + f_me t_je)
+        X = K.permuted(F[o, o], (0, 1))
+        ct('me,je->mj', Fov, t1, out=X, alpha=1.0, beta=1.0)
+        ct('imab,mj->ijab', t2, X, out=half, alpha=-1.0, beta=1.0)
+        ct('ma,mbij->ijab', t1, ct('nb,mnij->mbij', t1, self._cc2_Wmnij(t1)), out=half, alpha=0.5, beta=1.0)
+        ct('jf,abif->ijab', t1, ct('ie,abef->abif', t1, self._E('vvvv')), out=half, alpha=0.5, beta=1.0)
+        ct('ma,mbij->ijab', t1, self._cc2_Zmbij(t1), out=half, alpha=-1.0, beta=1.0)
+        ct('ma,mbij->ijab', t1, ct('ie,mbej->mbij', t1, self._E('ovvo')), out=half, alpha=-1.0, beta=1.0)
+        ct('mb,maji->ijab', t1, ct('ie,maje->maji', t1, self._E('ovov')), out=half, alpha=-1.0, beta=1.0)
+        ct('ie,abej->ijab', t1, self._E('vvvo'), out=half, alpha=1.0, beta=1.0)
+        ct('ma,mbij->ijab', t1, self._E('ovoo'), out=half, alpha=-1.0, beta=1.0)
+        return half
 
     # ---- r2, unsymmetrised half (ccwfn.py:922-940): this rank's share -------------------------------------
     def _r2_half(self, F, t1, t2, I, r2=None):
@@ -637,20 +682,28 @@ class CCwfn(object):
 
     def build_Wmnij(self, o, v, ERI, t1, t2):
         self._own(ERI)
+        if self.model == 'CC2':
+            return self._cc2_Wmnij(t1.contiguous())
         return self._I(self.H.F, t1, t2)["Wmnij"]
 
     def build_Wmbej(self, o, v, ERI, L, t1, t2):
         self._own(ERI, L)
+        if self.model == 'CC2':
+            return None                                                           # ccwfn.py:638-639
         return K.permuted(self._I(self.H.F, t1, t2)["W1"], (2, 1, 3, 0))          # [j,b,m,e] -> [m,b,e,j]
 
     def build_Wmbje(self, o, v, ERI, t1, t2):
         self._own(ERI)
+        if self.model == 'CC2':
+            return None                                                           # ccwfn.py:677-678
         return K.permuted(self._I(self.H.F, t1, t2)["W2"], (2, 1, 0, 3))          # [j,b,m,e] -> [m,b,j,e]
 
     def build_Zmbij(self, o, v, ERI, t1, t2):
         self._own(ERI)
         if self.model == 'CCD':
             return None
+        if self.model == 'CC2':
+            return self._cc2_Zmbij(t1.contiguous())
         return K.permuted(self._I(self.H.F, t1, t2)["Zijmb"], (2, 3, 0, 1))       # [i,j,m,b] -> [m,b,i,j]
 
     def r_T1(self, o, v, F, ERI, L, t1, t2, Fae=None, Fme=None, Fmi=None):
