@@ -51,6 +51,11 @@ def absolute(a):
     return torch.abs(a) if isinstance(a, torch.Tensor) else np.abs(a)
 
 
+def conj(a):
+    """complex conjugate (utils.py:157-161); a view flip for torch tensors, no arithmetic kernel involved"""
+    return torch.conj(a) if isinstance(a, torch.Tensor) else np.conj(a)
+
+
 def solve(A, b):
     """(m+1)x(m+1) Pulay systems: solved on the host (utils.py:348 uses torch/np.linalg.solve)."""
     if isinstance(A, torch.Tensor):
