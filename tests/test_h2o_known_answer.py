@@ -1,9 +1,14 @@
-"""Known-answer tests on a real molecule: H2O / STO-3G, frozen core -- the numbers the reference's own hot-path tests
-hard-code (pycc/tests/test_002_ccsd_energy.py:22-31, test_005_ccsd_t_energy.py:21-36, test_044_ccsd_t_gpu.py:21-38).
+"""Known-answer tests on a real molecule: H2O in STO-3G and cc-pVDZ (BASELINE.json configs[0]) -- the numbers the
+reference's own tests hard-code for this path:
 
-The AO integrals come from tests/golden/h2o_sto3g.npz (tests/golden/make_h2o_sto3g.py: s/p McMurchie-Davidson integrals +
-RHF in numpy, since psi4 is not installable offline; the unmodified reference, fed with them, reproduces its hard-coded
-energies to 1e-14).  Tolerance 1e-11 Eh as in the reference tests.  `emu` / `cuda` as in test_ccsd.py."""
+    test_002_ccsd_energy.py:31,38   test_003_ccsd_lambda.py:49,61   test_005_ccsd_t_energy.py:33,44
+    test_017_ccd.py:19,25           test_020_cc2.py:19              test_030_sp.py:30
+    test_031_cc3.py:31              test_044_ccsd_t_gpu.py:37
+
+The AO integrals come from tests/golden/h2o_*.npz (tests/golden/make_h2o.py: McMurchie-Davidson integrals + RHF in
+numpy, since psi4 is not installable offline; the unmodified reference, fed with them, reproduces every one of its
+hard-coded energies to <= 1e-13, recorded as ``dev_*`` in the fixtures).  Tolerance 1e-11 Eh as in the reference's
+tests.  Oracle tests run on the CPU; product tests through `emu` / `cuda` as in test_ccsd.py."""
 import os
 
 import numpy as np
@@ -15,16 +20,36 @@ from pycc_b200 import cctriples
 from pycc_b200.wavefunction import IntegralReference
 from oracle import aomo_oracle as ao
 from oracle import ccsd_oracle as co
+from oracle import cc2_oracle, cc3_oracle
+from oracle import lambda_oracle as lo
 from oracle import triples_oracle as to
 from tests import emu
+from tests.golden import gto
 
-ECCSD = -0.070616830152761        # test_002_ccsd_energy.py:31
-ET = -0.000099957499645           # test_005_ccsd_t_energy.py:33
-ECCSD_T = -0.0707167876524093     # test_044_ccsd_t_gpu.py:37
 TOL = 1e-11
+ECCSD_T_STO3G = -0.0707167876524093     # test_044_ccsd_t_gpu.py:37
 
-G = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "h2o_sto3g.npz")))
-NO, NV, NFZC = int(G["no"]), int(G["nv"]), int(G["nfzc"])
+
+def load(tag):
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "h2o_%s.npz" % tag)))
+    g["eri_ao"] = gto.unpack_eri(g["eri_packed"], g["S"].shape[0])
+    return g
+
+
+FIX = {tag: load(tag) for tag in ("sto3g", "ccpvdz", "teach_ccpvdz")}
+
+
+def hard(tag, core, model, what):
+    return float(FIX[tag]["hardcoded_%s_%s_%s" % (core, model.lower(), what)])
+
+
+def ref(tag, core, model, what):
+    return FIX[tag]["ref_%s_%s_%s" % (core, model.lower(), what)]
+
+
+def sizes(tag, core):
+    nfzc = 1 if core == "fc" else 0
+    return 5 - nfzc, nfzc
 
 
 @pytest.fixture(params=[pytest.param("emu"), pytest.param("cuda", marks=pytest.mark.gpu)])
@@ -37,77 +62,171 @@ def dev(request):
         yield torch.device("cuda:0")
 
 
-def test_fixture_is_a_converged_rhf():
-    S, C, F_ao, eps = G["S"], G["C"], G["F_ao"], G["eps"]
-    assert S.shape == (7, 7) and (NO, NV, NFZC) == (4, 2, 1)
-    assert np.abs(C.T @ S @ C - np.eye(7)).max() < 1e-12
-    assert np.abs(F_ao @ C - S @ C * eps).max() < 1e-11
-    # the Fock matrix is the one of its own density
+# ---------------------------------------------------------------------------------------------- fixtures themselves
+@pytest.mark.parametrize("tag", sorted(FIX))
+def test_fixture_is_a_converged_rhf(tag):
+    g = FIX[tag]
+    S, C, F_ao, eps, eri = g["S"], g["C"], g["F_ao"], g["eps"], g["eri_ao"]
+    n = S.shape[0]
+    assert n == {"sto3g": 7}.get(tag, 24)
+    assert np.abs(C.T @ S @ C - np.eye(n)).max() < 1e-11
+    assert np.abs(F_ao @ C - S @ C * eps).max() < 1e-10
     D = C[:, :5] @ C[:, :5].T
-    eri = G["eri_ao"]
-    F = G["Hcore"] + 2 * np.einsum("pqrs,rs->pq", eri, D) - np.einsum("prqs,rs->pq", eri, D)
-    assert np.abs(F - F_ao).max() < 1e-11
-    assert abs(np.sum(D * (G["Hcore"] + F)) + float(G["enuc"]) - float(G["escf"])) < 1e-11
-    # 8-fold symmetry of (pq|rs)
+    F = g["Hcore"] + 2 * np.einsum("pqrs,rs->pq", eri, D) - np.einsum("prqs,rs->pq", eri, D)
+    assert np.abs(F - F_ao).max() < 1e-10                                   # the Fock matrix of its own density
+    assert abs(np.sum(D * (g["Hcore"] + F)) + float(g["enuc"]) - float(g["escf"])) < 1e-10
     for perm in ((1, 0, 2, 3), (0, 1, 3, 2), (2, 3, 0, 1)):
-        assert np.abs(eri - eri.transpose(perm)).max() < 1e-14
+        assert np.abs(eri - eri.transpose(perm)).max() == 0.0
 
 
 def test_reference_outputs_match_its_hardcoded_numbers():
-    """What make_h2o_sto3g.py recorded from the unmodified reference on these integrals."""
-    assert abs(float(G["ref_eccsd"]) - ECCSD) < TOL
-    assert abs(float(G["ref_et"]) - ET) < TOL
-    assert abs(ECCSD + ET - ECCSD_T) < TOL
+    """What make_h2o.py recorded from the unmodified reference on these integrals."""
+    n = 0
+    for tag, g in FIX.items():
+        for k in g:
+            if k.startswith("dev_"):
+                assert abs(float(g[k])) < (1e-7 if k == "dev_ae_ccsd_ecc" else TOL), (tag, k)
+                n += 1
+    assert n == 11                      # + the CCSD(T) total of test_044 below = the twelve known answers
+    assert abs(hard("sto3g", "fc", "CCSD", "ecc") + hard("sto3g", "fc", "CCSD", "et") - ECCSD_T_STO3G) < TOL
 
 
-def test_oracle_known_answer():
-    F, ERI, _ = ao.mo_hamiltonian(G["F_ao"], G["eri_ao"], G["C"])
-    blocks = co.blocks_from_full(ERI, NO, NFZC)
-    P = co.Problem(blocks, F, NO, NFZC)
+# ---------------------------------------------------------------------------------------------------------- oracle
+def oracle_problem(tag, core):
+    g = FIX[tag]
+    no, nfzc = sizes(tag, core)
+    F, ERI, _ = ao.mo_hamiltonian(g["F_ao"], g["eri_ao"], g["C"])
+    blocks = co.blocks_from_full(ERI, no, nfzc)
+    return co.Problem(blocks, F, no, nfzc), blocks, F, nfzc
+
+
+def oracle_ccd(P, F):
+    """CCSD equations with t1 pinned to zero (the CCD branches of ccwfn.py drop every t1 term)."""
+    t1, t2 = P.guess()
+    ecc = P.cc_energy(F, t1, t2)
+    diis = co.Diis(t1, t2, 8)
+    for it in range(75):
+        last = ecc
+        _, r2 = P.residuals(F, t1, t2)
+        t2 = t2 + r2 / P.Dijab
+        rms = np.sqrt(np.sum((r2 / P.Dijab) ** 2))
+        ecc = P.cc_energy(F, t1, t2)
+        if abs(ecc - last) < 1e-12 and rms < 1e-12:
+            return ecc, t1, t2
+        diis.add_error_vector(t1, t2)
+        _, t2 = diis.extrapolate(t1, t2)
+    raise AssertionError("CCD oracle did not converge")
+
+
+@pytest.mark.parametrize("tag", ["sto3g", "ccpvdz"])
+def test_oracle_ccsd_t_lambda(tag):
+    P, b, F, nfzc = oracle_problem(tag, "fc")
     ecc, t1, t2, _ = co.solve_cc(P, 1e-12, 1e-12, 75)
-    assert abs(ecc - ECCSD) < TOL
-    assert np.abs(t1 - G["ref_t1"]).max() < 1e-10 and np.abs(t2 - G["ref_t2"]).max() < 1e-10
-    et = to.t_tjl(t1, t2, F, blocks["ovvv"], blocks["ooov"], blocks["oovv"], NFZC)
-    assert abs(et - ET) < TOL
-    assert abs(to.t_vikings(t1, t2, F, blocks["ovvv"], blocks["ooov"], blocks["oovv"], NFZC) - ET) < TOL
+    assert abs(ecc - hard(tag, "fc", "CCSD", "ecc")) < TOL
+    assert np.abs(t1 - ref(tag, "fc", "CCSD", "t1")).max() < 1e-10
+    assert np.abs(t2 - ref(tag, "fc", "CCSD", "t2")).max() < 1e-10
+    et = to.t_tjl(t1, t2, F, b["ovvv"], b["ooov"], b["oovv"], nfzc)
+    assert abs(et - hard(tag, "fc", "CCSD", "et")) < TOL
+    assert abs(to.t_vikings(t1, t2, F, b["ovvv"], b["ooov"], b["oovv"], nfzc) - et) < 1e-12
+    lecc, l1, l2, _ = lo.solve_lambda(P, t1, t2, 1e-12, 1e-12, 75)
+    assert abs(lecc - hard(tag, "fc", "CCSD", "lecc")) < TOL
+    assert np.abs(l2 - ref(tag, "fc", "CCSD", "l2")).max() < 1e-10
 
 
-def h2o_reference(kind):
+def test_oracle_all_electron_ccsd_ccd_cc2():
+    P, b, F, nfzc = oracle_problem("ccpvdz", "ae")
+    ecc = co.solve_cc(P, 1e-12, 1e-12, 75)[0]
+    assert abs(ecc - hard("ccpvdz", "ae", "CCSD", "ecc")) < 1e-7          # the reference's SP test
+    assert abs(ecc - float(ref("ccpvdz", "ae", "CCSD", "ecc"))) < TOL
+    eccd, t1, t2 = oracle_ccd(P, F)
+    assert abs(eccd - hard("ccpvdz", "ae", "CCD", "ecc")) < TOL
+    lecc = lo.solve_lambda(P, t1, t2, 1e-12, 1e-12, 75, model="CCD")[0]
+    assert abs(lecc - hard("ccpvdz", "ae", "CCD", "lecc")) < TOL
+    assert abs(cc2_oracle.solve_cc(P, 1e-12, 1e-12, 75)[0] - hard("ccpvdz", "ae", "CC2", "ecc")) < TOL
+
+
+def test_oracle_cc3():
+    P, b, F, nfzc = oracle_problem("teach_ccpvdz", "ae")
+    assert abs(cc3_oracle.solve_cc(P, 1e-12, 1e-12, 75)[0] - hard("teach_ccpvdz", "ae", "CC3", "ecc")) < TOL
+
+
+# --------------------------------------------------------------------------------------------------------- product
+def h2o_reference(tag, core, kind="ao"):
+    g = FIX[tag]
+    no, nfzc = sizes(tag, core)
     if kind == "ao":
-        return IntegralReference.from_ao(G["F_ao"], G["eri_ao"], G["C"], NO, NFZC)
-    F, ERI, _ = ao.mo_hamiltonian(G["F_ao"], G["eri_ao"], G["C"])
-    return IntegralReference.from_arrays(F, ERI, NO, NFZC)
+        return IntegralReference.from_ao(g["F_ao"], g["eri_ao"], g["C"], no, nfzc)
+    F, ERI, _ = ao.mo_hamiltonian(g["F_ao"], g["eri_ao"], g["C"])
+    return IntegralReference.from_arrays(F, ERI, no, nfzc)
 
 
-@pytest.mark.parametrize("kind", ["ao", "mo"])
-def test_ccsd_energy(dev, kind):
-    """test_002_ccsd_energy.py:22-31"""
-    cc = pycc_b200.ccwfn(h2o_reference(kind), quiet=True)
+@pytest.mark.parametrize("tag,kind", [("sto3g", "ao"), ("sto3g", "mo"), ("ccpvdz", "ao")])
+def test_ccsd_energy(dev, tag, kind):
+    """test_002_ccsd_energy.py:22-39"""
+    cc = pycc_b200.ccwfn(h2o_reference(tag, "fc", kind), quiet=True)
     eccsd = cc.solve_cc(1e-12, 1e-12, 75)
-    assert abs(float(eccsd) - ECCSD) < TOL
-    assert np.abs(cc.t2.cpu().numpy() - G["ref_t2"]).max() < 1e-10
-    assert np.abs(cc.t1.cpu().numpy() - G["ref_t1"]).max() < 1e-10
+    assert abs(float(eccsd) - hard(tag, "fc", "CCSD", "ecc")) < TOL
+    assert np.abs(cc.t2.cpu().numpy() - ref(tag, "fc", "CCSD", "t2")).max() < 1e-10
+    assert np.abs(cc.t1.cpu().numpy() - ref(tag, "fc", "CCSD", "t1")).max() < 1e-10
 
 
-def test_ccsd_t_three_formulations(dev):
-    """test_005_ccsd_t_energy.py:21-36"""
-    cc = pycc_b200.ccwfn(h2o_reference("ao"), model="ccsd(t)", quiet=True)
+@pytest.mark.parametrize("tag", ["sto3g", "ccpvdz"])
+def test_ccsd_t_three_formulations(dev, tag):
+    """test_005_ccsd_t_energy.py:21-47"""
+    cc = pycc_b200.ccwfn(h2o_reference(tag, "fc"), model="ccsd(t)", quiet=True)
     total = cc.solve_cc(1e-12, 1e-12, 75)
-    assert abs(float(total) - ECCSD_T) < TOL
+    et = hard(tag, "fc", "CCSD", "et")
+    assert abs(float(total) - hard(tag, "fc", "CCSD", "ecc") - et) < TOL
     for fn in (cctriples.t_vikings, cctriples.t_vikings_inverted, cctriples.t_tjl):
-        assert abs(float(fn(cc)) - ET) < TOL, fn.__name__
+        assert abs(float(fn(cc)) - et) < TOL, fn.__name__
 
 
 def test_ccsd_t_gpu_total(dev):
     """test_044_ccsd_t_gpu.py:21-38: device='GPU', the return value must be float()-able."""
-    cc = pycc_b200.ccwfn(h2o_reference("ao"), model="CCSD(T)", device="GPU", quiet=True)
+    cc = pycc_b200.ccwfn(h2o_reference("sto3g", "fc"), model="CCSD(T)", device="GPU", quiet=True)
     ecc = cc.solve_cc(1e-12, 1e-12, 75)
-    assert abs(float(ecc) - ECCSD_T) < TOL
+    assert abs(float(ecc) - ECCSD_T_STO3G) < TOL
 
 
-def test_mixed_precision_within_1e6(dev):
-    """BASELINE north_star: mixed precision within 1e-6 Eh (the reference's SP test, test_030_sp.py:26-31, uses 1e-7 on
-    another basis)."""
-    cc = pycc_b200.ccwfn(h2o_reference("ao"), model="CCSD(T)", device="GPU", precision="MP", quiet=True)
-    ecc = cc.solve_cc(1e-9, 1e-9, 75)
-    assert abs(float(ecc) - ECCSD_T) < 1e-6
+@pytest.mark.parametrize("tag", ["sto3g", "ccpvdz"])
+def test_ccsd_lambda(dev, tag):
+    """test_003_ccsd_lambda.py:36-63"""
+    cc = pycc_b200.ccwfn(h2o_reference(tag, "fc"), quiet=True)
+    cc.solve_cc(1e-12, 1e-12, 75)
+    lecc = pycc_b200.cclambda(cc, pycc_b200.cchbar(cc)).solve_lambda(1e-12, 1e-12)
+    assert abs(float(lecc) - hard(tag, "fc", "CCSD", "lecc")) < TOL
+
+
+def test_ccd_and_its_lambda(dev):
+    """test_017_ccd.py:11-26 (all-electron)"""
+    cc = pycc_b200.ccwfn(h2o_reference("ccpvdz", "ae"), model="CCD", quiet=True)
+    assert abs(float(cc.solve_cc(1e-12, 1e-12, 75)) - hard("ccpvdz", "ae", "CCD", "ecc")) < TOL
+    lecc = pycc_b200.cclambda(cc, pycc_b200.cchbar(cc)).solve_lambda(1e-12, 1e-12)
+    assert abs(float(lecc) - hard("ccpvdz", "ae", "CCD", "lecc")) < TOL
+
+
+def test_cc2(dev):
+    """test_020_cc2.py:11-20 (all-electron)"""
+    cc = pycc_b200.ccwfn(h2o_reference("ccpvdz", "ae"), model="CC2", quiet=True)
+    assert abs(float(cc.solve_cc(1e-12, 1e-12, 75)) - hard("ccpvdz", "ae", "CC2", "ecc")) < TOL
+
+
+def test_cc3(dev):
+    """test_031_cc3.py:24-32 (H2O_Teach geometry, all-electron)"""
+    cc = pycc_b200.ccwfn(h2o_reference("teach_ccpvdz", "ae"), model="CC3", quiet=True)
+    assert abs(float(cc.solve_cc(1e-12, 1e-12, 75)) - hard("teach_ccpvdz", "ae", "CC3", "ecc")) < TOL
+
+
+def test_sp_all_electron(dev):
+    """test_030_sp.py:17-31: precision='SP', all-electron cc-pVDZ, 1e-7."""
+    cc = pycc_b200.ccwfn(h2o_reference("ccpvdz", "ae"), precision="SP", quiet=True)
+    ecc = cc.solve_cc(1e-7, 1e-7)
+    assert abs(float(ecc) - hard("ccpvdz", "ae", "CCSD", "ecc")) < 1e-7
+
+
+@pytest.mark.parametrize("tag", ["sto3g", "ccpvdz"])
+def test_mixed_precision_within_1e6(dev, tag):
+    """BASELINE north_star: mixed precision within 1e-6 Eh of the FP64 reference."""
+    cc = pycc_b200.ccwfn(h2o_reference(tag, "fc"), model="CCSD(T)", device="GPU", precision="MP", quiet=True)
+    ecc = cc.solve_cc(1e-7, 1e-7, 75)      # the reference's defaults; the split-TF32 products leave rms ~1e-8
+    assert abs(float(ecc) - hard(tag, "fc", "CCSD", "ecc") - hard(tag, "fc", "CCSD", "et")) < 1e-6
