@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Known-answer fixtures on the molecule of the reference's hot-path tests: H2O in STO-3G and cc-pVDZ.
 
-    python tests/golden/make_h2o.py        # rewrites tests/golden/h2o_{sto3g,ccpvdz,teach_ccpvdz}.npz
+    python tests/golden/make_h2o.py        # rewrites tests/golden/h2o_*.npz (all, or the tags given)
 
 The reference's tests pin the path on this molecule with hard-coded numbers (geometry ``moldict["H2O"]`` =
 pycc/data/molecules.py:42-46, frozen core, SCF converged to 1e-12 -- pycc/tests/conftest.py:28-36):
@@ -70,7 +70,11 @@ HARDCODED = {
                ("ae", "CCD"): dict(ecc=-0.222559319034, lecc=-0.218758826700),      # test_017_ccd.py:19,25
                ("ae", "CC2"): dict(ecc=-0.215857544656)},                            # test_020_cc2.py:19
     "teach_ccpvdz": {("ae", "CC3"): dict(ecc=-0.227888246840310)},                   # test_031_cc3.py:31
+    # test_034_ccsd_t_density.py:19-68: CCSD(T) with make_t3_density=True, then Lambda with the (T) sources
+    "t034_sto3g": {("ae", "CCSD(T)"): dict(lecc=-0.069084521221746)},                # max_diis=0 (test_034:32,36)
+    "t034_ccpvdz": {("ae", "CCSD(T)"): dict(lecc=-0.227199866607450)},
 }
+MAX_DIIS = {"t034_sto3g": 0}
 ECCSD_T_STO3G = -0.0707167876524093      # test_044_ccsd_t_gpu.py:37
 TOL = {("ae", "CCSD"): 1e-7}             # everything else 1e-10 here (1e-11 in the reference's tests)
 
@@ -80,13 +84,17 @@ def geometry(tag):
         return [("O", np.array([0.0, -0.143225816552, 0.0])),
                 ("H", np.array([1.638036840407, 1.136548822547, 0.0])),
                 ("H", np.array([-1.638036840407, 1.136548822547, 0.0]))]
+    if tag.startswith("t034"):           # pycc/tests/test_034_ccsd_t_density.py:19-25, bohr
+        return [("O", np.array([0.0, 0.0, 0.143225857166674])),
+                ("H", np.array([0.0, -1.638037301628121, -1.136549142277225])),
+                ("H", np.array([0.0, 1.638037301628121, -1.136549142277225]))]
     r = 1.1 / gto.BOHR                   # moldict["H2O"], pycc/data/molecules.py:42-46, Angstrom
     th = math.radians(104.0)
     return [("O", np.zeros(3)), ("H", np.array([0.0, 0.0, r])),
             ("H", np.array([r * math.sin(th), 0.0, r * math.cos(th)]))]
 
 
-def run_reference(mods, F, ERI, no, nfzc, model, want):
+def run_reference(mods, F, ERI, no, nfzc, model, want, max_diis=8):
     import importlib
     from make_golden import reference_wfn
     ccwfn_mod, cctriples, utils, device_mod = mods
@@ -95,9 +103,10 @@ def run_reference(mods, F, ERI, no, nfzc, model, want):
                                 o=slice(nfzc, nfzc + no), v=slice(nfzc + no, n))
     w = reference_wfn(ccwfn_mod, device_mod, syn, ERI, model=model)
     w.nfzc = nfzc
+    w.make_t3_density = model == "CCSD(T)"        # solve_cc then runs t3_density, which leaves S1/S2 for Lambda
     out = {}
     with contextlib.redirect_stdout(io.StringIO()):
-        out["ecc"] = float(w.solve_cc(1e-12, 1e-12, 75))
+        out["ecc"] = float(w.solve_cc(1e-12, 1e-12, 75, max_diis=max_diis))
         out["t1"], out["t2"] = np.array(w.t1), np.array(w.t2)
         if "et" in want:
             out["et"] = float(cctriples.t_tjl(w))
@@ -106,7 +115,7 @@ def run_reference(mods, F, ERI, no, nfzc, model, want):
         if "lecc" in want:
             hbar = importlib.import_module("pycc.cchbar").cchbar(w)
             lam = importlib.import_module("pycc.cclambda").cclambda(w, hbar)
-            out["lecc"] = float(lam.solve_lambda(1e-12, 1e-12, 75))
+            out["lecc"] = float(lam.solve_lambda(1e-12, 1e-12, 75, max_diis=max_diis))
             out["l1"], out["l2"] = np.array(lam.l1), np.array(lam.l2)
     return out
 
@@ -123,8 +132,8 @@ def make(tag, shells, mods):
                ndocc=5)
     for (core, model), hard in HARDCODED[tag].items():
         nfzc = 1 if core == "fc" else 0
-        out = run_reference(mods, F, ERI, 5 - nfzc, nfzc, model, hard)
-        key = "%s_%s" % (core, model.lower())
+        out = run_reference(mods, F, ERI, 5 - nfzc, nfzc, model, hard, MAX_DIIS.get(tag, 8))
+        key = "%s_%s" % (core, model.lower().replace("(t)", "pt"))
         for k, val in out.items():
             rec["ref_%s_%s" % (key, k)] = val
         for k, val in hard.items():
@@ -139,9 +148,8 @@ def make(tag, shells, mods):
 def main():
     from make_golden import load_reference
     mods = load_reference()
-    make("sto3g", STO3G, mods)
-    make("ccpvdz", CCPVDZ, mods)
-    make("teach_ccpvdz", CCPVDZ, mods)
+    for tag in (sys.argv[1:] or sorted(HARDCODED)):
+        make(tag, STO3G if tag.endswith("sto3g") else CCPVDZ, mods)
 
 
 if __name__ == "__main__":

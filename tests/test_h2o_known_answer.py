@@ -3,7 +3,7 @@ reference's own tests hard-code for this path:
 
     test_002_ccsd_energy.py:31,38   test_003_ccsd_lambda.py:49,61   test_005_ccsd_t_energy.py:33,44
     test_017_ccd.py:19,25           test_020_cc2.py:19              test_030_sp.py:30
-    test_031_cc3.py:31              test_044_ccsd_t_gpu.py:37
+    test_031_cc3.py:31              test_044_ccsd_t_gpu.py:37       test_034_ccsd_t_density.py:44,68
 
 The AO integrals come from tests/golden/h2o_*.npz (tests/golden/make_h2o.py: McMurchie-Davidson integrals + RHF in
 numpy, since psi4 is not installable offline; the unmodified reference, fed with them, reproduces every one of its
@@ -36,15 +36,15 @@ def load(tag):
     return g
 
 
-FIX = {tag: load(tag) for tag in ("sto3g", "ccpvdz", "teach_ccpvdz")}
+FIX = {tag: load(tag) for tag in ("sto3g", "ccpvdz", "teach_ccpvdz", "t034_sto3g", "t034_ccpvdz")}
 
 
 def hard(tag, core, model, what):
-    return float(FIX[tag]["hardcoded_%s_%s_%s" % (core, model.lower(), what)])
+    return float(FIX[tag]["hardcoded_%s_%s_%s" % (core, model.lower().replace("(t)", "pt"), what)])
 
 
 def ref(tag, core, model, what):
-    return FIX[tag]["ref_%s_%s_%s" % (core, model.lower(), what)]
+    return FIX[tag]["ref_%s_%s_%s" % (core, model.lower().replace("(t)", "pt"), what)]
 
 
 def sizes(tag, core):
@@ -68,7 +68,7 @@ def test_fixture_is_a_converged_rhf(tag):
     g = FIX[tag]
     S, C, F_ao, eps, eri = g["S"], g["C"], g["F_ao"], g["eps"], g["eri_ao"]
     n = S.shape[0]
-    assert n == {"sto3g": 7}.get(tag, 24)
+    assert n == (7 if tag.endswith("sto3g") else 24)
     assert np.abs(C.T @ S @ C - np.eye(n)).max() < 1e-11
     assert np.abs(F_ao @ C - S @ C * eps).max() < 1e-10
     D = C[:, :5] @ C[:, :5].T
@@ -87,7 +87,7 @@ def test_reference_outputs_match_its_hardcoded_numbers():
             if k.startswith("dev_"):
                 assert abs(float(g[k])) < (1e-7 if k == "dev_ae_ccsd_ecc" else TOL), (tag, k)
                 n += 1
-    assert n == 11                      # + the CCSD(T) total of test_044 below = the twelve known answers
+    assert n == 13                      # + the CCSD(T) total of test_044 below = fourteen known answers
     assert abs(hard("sto3g", "fc", "CCSD", "ecc") + hard("sto3g", "fc", "CCSD", "et") - ECCSD_T_STO3G) < TOL
 
 
@@ -150,6 +150,20 @@ def test_oracle_cc3():
     assert abs(cc3_oracle.solve_cc(P, 1e-12, 1e-12, 75)[0] - hard("teach_ccpvdz", "ae", "CC3", "ecc")) < TOL
 
 
+@pytest.mark.parametrize("tag", ["t034_sto3g", "t034_ccpvdz"])
+def test_oracle_ccsd_t_density_lambda(tag):
+    """CCSD -> t3_density ((T) energy + Lambda sources S1/S2) -> Lambda, all-electron; max_diis=0 in STO-3G as in
+    test_034_ccsd_t_density.py:32,36."""
+    from oracle import t3density_oracle as td
+    P, b, F, nfzc = oracle_problem(tag, "ae")
+    md = 0 if tag == "t034_sto3g" else 8
+    ecc, t1, t2, _ = co.solve_cc(P, 1e-12, 1e-12, 75, max_diis=md)
+    et, d = td.t3_density(t1, t2, F, b["ovvv"], b["ooov"], b["oovv"], nfzc)
+    assert abs(ecc + et - float(ref(tag, "ae", "CCSD(T)", "ecc"))) < TOL
+    lecc = lo.solve_lambda(P, t1, t2, 1e-12, 1e-12, 75, max_diis=md, model="CCSD(T)", s1=d["S1"], s2=d["S2"])[0]
+    assert abs(lecc - hard(tag, "ae", "CCSD(T)", "lecc")) < TOL
+
+
 # --------------------------------------------------------------------------------------------------------- product
 def h2o_reference(tag, core, kind="ao"):
     g = FIX[tag]
@@ -195,6 +209,17 @@ def test_ccsd_lambda(dev, tag):
     cc.solve_cc(1e-12, 1e-12, 75)
     lecc = pycc_b200.cclambda(cc, pycc_b200.cchbar(cc)).solve_lambda(1e-12, 1e-12)
     assert abs(float(lecc) - hard(tag, "fc", "CCSD", "lecc")) < TOL
+
+
+@pytest.mark.parametrize("tag", ["t034_sto3g", "t034_ccpvdz"])
+def test_ccsd_t_density_lambda(dev, tag):
+    """test_034_ccsd_t_density.py:13-68: make_t3_density=True, then Lambda with the (T) sources (all-electron)."""
+    md = 0 if tag == "t034_sto3g" else 8
+    cc = pycc_b200.ccwfn(h2o_reference(tag, "ae"), model="ccsd(t)", make_t3_density=True, quiet=True)
+    ecc = cc.solve_cc(1e-12, 1e-12, 75, max_diis=md)
+    assert abs(float(ecc) - float(ref(tag, "ae", "CCSD(T)", "ecc"))) < TOL
+    lecc = pycc_b200.cclambda(cc, pycc_b200.cchbar(cc)).solve_lambda(1e-12, 1e-12, 75, max_diis=md)
+    assert abs(float(lecc) - hard(tag, "ae", "CCSD(T)", "lecc")) < TOL
 
 
 def test_ccd_and_its_lambda(dev):
