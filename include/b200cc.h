@@ -117,6 +117,12 @@ typedef struct {
 int b200cc_split_tf32(const double* src, b200cc_i64 ld, b200cc_i64 stride, int rows, int K, int batch,
                       float* hi, float* lo, b200cc_i64 ldp, void* stream);
 int b200cc_gemm_tf32x3(const b200cc_gemm3_desc* d, void* stream);
+/* b200cc_merge_tf32: the inverse of b200cc_split_tf32 for one batch entry -- dst (rows x K doubles, pitch ld) = hi + lo.
+ * Used where precision='MP' has released the FP64 <ab|ef> block and an FP64-only consumer needs rows of it back
+ * (t_if <ab|ef> inside HBAR's Hvvvo, cchbar.py:632-688; the CC2 / CC3 t1-dressed <ab|ef> terms, ccwfn.py:880, 1104);
+ * the result carries the 2^-22 relative accuracy of the planes, i.e. that of the mode.                          */
+int b200cc_merge_tf32(const float* hi, const float* lo, b200cc_i64 ldp, b200cc_i64 rows, int K, double* dst,
+                      b200cc_i64 ld, void* stream);
 
 /* ---- tensor permutation / strided axpby -------------------------------------------------------
  * out[sum_d i_d*so[d]] = alpha * in[sum_d i_d*si[d]] + beta * out[...]  for i_d < shape[d], rank <= 6.

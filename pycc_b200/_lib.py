@@ -94,6 +94,7 @@ SIGNATURES = {
     "b200cc_dgemm": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
     "b200cc_split_tf32": (C.c_int, [dptr, i64, i64, C.c_int, C.c_int, C.c_int, dptr, dptr, i64, C.c_void_p]),
     "b200cc_gemm_tf32x3": (C.c_int, [C.POINTER(Gemm3Desc), C.c_void_p]),
+    "b200cc_merge_tf32": (C.c_int, [dptr, dptr, i64, i64, C.c_int, dptr, i64, C.c_void_p]),
     "b200cc_permute": (C.c_int, [C.c_int, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64),
                                  C.c_double, dptr, C.c_double, dptr, C.c_void_p]),
     "b200cc_axpbyz": (C.c_int, [i64, C.c_double, dptr, C.c_double, dptr, dptr, C.c_void_p]),

@@ -164,6 +164,13 @@ class cchbar(object):
                 if sharded and "E:vvvv" in (a, b):
                     self._vvvv_term_sharded(out, alpha, sub, a, b, env)
                     continue
+                if "E:vvvv" in (a, b) and w._vvvv_released():
+                    # precision='MP' / 'SP': only the TF32 planes of <ab|ef> are resident
+                    if sub != "if,abef->abei" or b != "E:vvvv":
+                        raise NotImplementedError("HBAR term %r needs the FP64 <ab|ef> block (precision='MP' released "
+                                                  "it); read hbar.Hvvvv in double precision" % sub)
+                    w._t1_vvvv(self._operand(env, a), out, alpha)
+                    continue
                 w._ct(sub, self._operand(env, a), self._operand(env, b), out=out, alpha=alpha, beta=1.0)
         env[key] = out
         return out
@@ -179,7 +186,9 @@ class cchbar(object):
             raise NotImplementedError("<ab|ef> rows resident on this rank differ from its share")
         a_lo, a_hi = w.H.a_range
         piece = torch.zeros_like(out)
-        if a_hi > a_lo:
+        if a_hi > a_lo and w._vvvv_released():
+            w._t1_vvvv(self._operand(env, a), piece[a_lo:a_hi], alpha)       # rebuilt from the MP planes
+        elif a_hi > a_lo:
             w._ct(sub, self._operand(env, a), w.H.block("vvvv"), out=piece[a_lo:a_hi], alpha=alpha, beta=0.0)
         w.part.all_reduce_sum(piece)
         K.strided_axpby(out, piece, 1.0, 1.0)

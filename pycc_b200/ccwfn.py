@@ -190,6 +190,21 @@ class CCwfn(object):
     def _E(self, pat):
         return self.H.ERI[tuple(self.o if c == 'o' else self.v for c in pat)]
 
+    def _vvvv_released(self):
+        """precision='MP' / 'SP': the FP64 <ab|ef> block has been released, only its TF32 planes are resident."""
+        return (not self.H.has("vvvv")) and self.H.vvvv_planes is not None
+
+    def _t1_vvvv(self, t1, out_abei, alpha=1.0):
+        """out_abei[a,b,e,i] += alpha * sum_f t_if <ab|ef> over the RESIDENT rows a of <ab|ef> (``out_abei``: any
+        strided view with that index order, first extent = resident rows).  FP64 rows come from
+        ``H.vvvv_fp64_chunks`` -- the block itself, or chunks rebuilt from the TF32 planes when precision='MP' has
+        released it (cchbar.py:654 / ccwfn.py:880, 1104 in that mode)."""
+        t1 = t1.contiguous()
+        with K.mixed_mode(False):                       # the rebuilt chunks are temporaries: no second split
+            for a0, a1, blk in self.H.vvvv_fp64_chunks():
+                K.strided_axpby(out_abei[a0:a1], self._ct('if,abef->abei', t1, blk), alpha, 1.0)
+        return out_abei
+
     def build_cc3_Wmnij(self, o, v, ERI, t1):
         """W_mnij = <mn|ij> + t_ja <mn|ia> + t_ia <nm|ja> + t_ie t_jf <mn|ef>          (ccwfn.py:947-977)"""
         self._own(ERI)
@@ -235,7 +250,10 @@ class CCwfn(object):
             raise NotImplementedError("CC3 intermediates need the whole <ab|ef> block on this rank")
         ct, t1 = self._ct, t1.contiguous()
         Z = K.permuted(self._E('vovv'), (0, 1, 2, 3))                                   # [e,i,a,b]
-        ct('if,abef->eiab', t1, self._E('vvvv'), out=Z, alpha=1.0, beta=1.0)
+        if self._vvvv_released():
+            self._t1_vvvv(t1, Z.permute(2, 3, 0, 1))
+        else:
+            ct('if,abef->eiab', t1, self._E('vvvv'), out=Z, alpha=1.0, beta=1.0)
         Zeiam = K.permuted(self._E('vovo'), (0, 1, 2, 3))
         K.strided_axpby(Zeiam, ct('amef,if->amei', self._E('vovv'), t1).permute(2, 3, 0, 1), 1.0, 1.0)
         ct('eiam,mb->eiab', Zeiam, t1, out=Z, alpha=-1.0, beta=1.0)
@@ -543,7 +561,13 @@ class CCwfn(object):
         ct('me,je->mj', Fov, t1, out=X, alpha=1.0, beta=1.0)
         ct('imab,mj->ijab', t2, X, out=half, alpha=-1.0, beta=1.0)
         ct('ma,mbij->ijab', t1, ct('nb,mnij->mbij', t1, self._cc2_Wmnij(t1)), out=half, alpha=0.5, beta=1.0)
-        ct('jf,abif->ijab', t1, ct('ie,abef->abif', t1, self._E('vvvv')), out=half, alpha=0.5, beta=1.0)
+        if self._vvvv_released():
+            # sum_e t_ie <ab|ef> = X[b,a,f,i] with X_abei = sum_f t_if <ab|ef>   (<ab|ef> = <ba|fe>)
+            Y = torch.zeros((self.nv, self.nv, self.no, self.nv), dtype=F64, device=self.device1)       # [a,b,i,f]
+            self._t1_vvvv(t1, Y.permute(1, 0, 3, 2))
+        else:
+            Y = ct('ie,abef->abif', t1, self._E('vvvv'))
+        ct('jf,abif->ijab', t1, Y, out=half, alpha=0.5, beta=1.0)
         ct('ma,mbij->ijab', t1, self._cc2_Zmbij(t1), out=half, alpha=-1.0, beta=1.0)
         ct('ma,mbij->ijab', t1, ct('ie,mbej->mbij', t1, self._E('ovvo')), out=half, alpha=-1.0, beta=1.0)
         ct('mb,maji->ijab', t1, ct('ie,maje->maji', t1, self._E('ovov')), out=half, alpha=-1.0, beta=1.0)

@@ -886,6 +886,25 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const double* __restric
   }
 }
 
+// inverse of split_tf32_kernel: dst (rows x K doubles, pitch ld) = hi + lo, planes with pitch Kp (Kp % 4 == 0)
+__global__ void __launch_bounds__(256) merge_tf32_kernel(const float* __restrict__ hi, const float* __restrict__ lo,
+                                                         int Kp, i64 rows, int K, double* __restrict__ dst, i64 ld) {
+  const i64 q4 = Kp >> 2;
+  const i64 total = rows * q4;
+  for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+    const i64 r = e / q4;
+    const int k0 = static_cast<int>(e - r * q4) * 4;
+    const float4 h = __ldg(reinterpret_cast<const float4*>(hi + r * Kp + k0));
+    const float4 l = __ldg(reinterpret_cast<const float4*>(lo + r * Kp + k0));
+    const double v[4] = {(double)h.x + (double)l.x, (double)h.y + (double)l.y, (double)h.z + (double)l.z,
+                         (double)h.w + (double)l.w};
+    double* d = dst + r * ld + k0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (k0 + t < K) d[t] = v[t];
+  }
+}
+
 // ---- host side ----------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1079,6 +1098,25 @@ extern "C" int b200cc_split_tf32(const double* src, b200cc_i64 ld, b200cc_i64 st
   if (blocks > cap) blocks = cap;
   mx::split_tf32_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, ld, stride, rows, K, (int)ldp, batch, hi, lo);
   return check_launch("split_tf32_kernel");
+}
+
+extern "C" int b200cc_merge_tf32(const float* hi, const float* lo, b200cc_i64 ldp, b200cc_i64 rows, int K, double* dst,
+                                 b200cc_i64 ld, void* stream) {
+  if (rows <= 0 || K <= 0) return 0;
+  if (ldp < K || (ldp & 3) != 0 || ldp > 2147483647LL || ld < K) {
+    set_error("b200cc_merge_tf32: plane pitch must be a multiple of 4 and >= K, ld >= K");
+    return 1;
+  }
+  if (!dst || !hi || !lo || (reinterpret_cast<uintptr_t>(hi) & 15) || (reinterpret_cast<uintptr_t>(lo) & 15)) {
+    set_error("b200cc_merge_tf32: null or misaligned plane");
+    return 1;
+  }
+  const i64 total = rows * (ldp >> 2);
+  i64 blocks = (total + 255) / 256;
+  const i64 cap = (i64)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  mx::merge_tf32_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(hi, lo, (int)ldp, rows, K, dst, ld);
+  return check_launch("merge_tf32_kernel");
 }
 
 extern "C" int b200cc_gemm_tf32x3(const b200cc_gemm3_desc* d, void* stream) {

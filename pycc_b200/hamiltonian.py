@@ -164,6 +164,27 @@ class BlockHamiltonian:
     def has(self, name):
         return name in self._blocks
 
+    def vvvv_fp64_chunks(self, chunk_bytes=2 << 30):
+        """(a0, a1, FP64 [a1-a0, v, v, v]) over the RESIDENT rows of <ab|ef> (local row numbers): the block itself, or --
+        precision='MP' after the FP64 block was released -- chunks rebuilt from its TF32 planes (hi + lo: 2^-22
+        relative, the accuracy of the mode).  For the few FP64-only consumers of <ab|ef> outside the ladder
+        (t_if <ab|ef> in HBAR / CC2 / CC3: 2ov^4 flop, one pass per call)."""
+        if "vvvv" in self._blocks:
+            blk = self._blocks["vvvv"]
+            yield 0, blk.shape[0], blk
+            return
+        if self.vvvv_planes is None:
+            raise B200ccError("integral block 'vvvv' is not resident")
+        hi, lo, ldp = self.vvvv_planes
+        nv = self.nv
+        na = hi.shape[0] // nv
+        step = int(max(1, min(na, chunk_bytes // max(8 * nv ** 3, 1))))
+        for a0 in range(0, na, step):
+            a1 = min(na, a0 + step)
+            rows = (a1 - a0) * nv
+            blk = K.merge_tf32((hi, a0 * nv * ldp), (lo, a0 * nv * ldp), ldp, rows, nv * nv)
+            yield a0, a1, blk.view(a1 - a0, nv, nv, nv)
+
     # ---- constructors ---------------------------------------------------------------------------
     @classmethod
     def from_full(cls, F, ERI, no, nfzc=0, device="cuda"):

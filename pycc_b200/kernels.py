@@ -143,6 +143,16 @@ def split_tf32(src, rows, K, ld, batch=1, stride=0, out=None):
     return hi, lo, ldp
 
 
+def merge_tf32(hi, lo, ldp, rows, K, out=None):
+    """FP64 (rows x K, contiguous) = hi + lo from split-TF32 planes of pitch ldp (b200cc_merge_tf32); plane operands
+    may be tensors or (tensor, float offset)."""
+    if out is None:
+        out = torch.empty((int(rows), int(K)), dtype=torch.float64, device=_dev(hi))
+    _lib.check(_lib.get().b200cc_merge_tf32(_faddr(hi), _faddr(lo), int(ldp), int(rows), int(K), _lib.ptr(out), int(K),
+                                            _lib.stream()), "b200cc_merge_tf32")
+    return out
+
+
 def _split_operand(X, rows, K, ld, batch, stride):
     t = X[0] if isinstance(X, tuple) else X
     cache = _CONST.get(t.untyped_storage().data_ptr())

@@ -139,6 +139,15 @@ class EmuLib:
         L[:, :, :K] = tf32_rna((x - h.astype(np.float64)).astype(np.float32))
         return 0
 
+    def b200cc_merge_tf32(self, hi, lo, ldp, rows, K, dst, ld, stream):
+        self._count("merge_tf32")
+        if rows <= 0 or K <= 0:
+            return 0
+        H = _f32(hi, (rows, ldp))
+        L = _f32(lo, (rows, ldp))
+        _arr(dst, (rows, K), (ld, 1))[...] = H[:, :K].astype(np.float64) + L[:, :K].astype(np.float64)
+        return 0
+
     def b200cc_gemm_tf32x3(self, dref, stream):
         d = dref._obj
         self._count("gemm_tf32x3")

@@ -66,13 +66,14 @@ CHARGE = {"H": 1.0, "O": 8.0}
 HARDCODED = {
     "sto3g": {("fc", "CCSD"): dict(ecc=-0.070616830152761, et=-0.000099957499645, lecc=-0.068826452648939)},
     "ccpvdz": {("fc", "CCSD"): dict(ecc=-0.222029814166783, et=-0.003861236558801, lecc=-0.217838951550509),
-               ("ae", "CCSD"): dict(ecc=-0.223910018703551),           # test_030_sp.py:30, precision='SP', 1e-7
+               ("ae", "CCSD"): dict(ecc=-0.223910018703551, lecc=-0.219688229733875),   # test_030_sp.py:30,39 ('SP', 1e-7)
                ("ae", "CCD"): dict(ecc=-0.222559319034, lecc=-0.218758826700),      # test_017_ccd.py:19,25
                ("ae", "CC2"): dict(ecc=-0.215857544656)},                            # test_020_cc2.py:19
     "teach_ccpvdz": {("ae", "CC3"): dict(ecc=-0.227888246840310)},                   # test_031_cc3.py:31
     # test_034_ccsd_t_density.py:19-68: CCSD(T) with make_t3_density=True, then Lambda with the (T) sources
     "t034_sto3g": {("ae", "CCSD(T)"): dict(lecc=-0.069084521221746)},                # max_diis=0 (test_034:32,36)
     "t034_ccpvdz": {("ae", "CCSD(T)"): dict(lecc=-0.227199866607450)},
+    "h2_ccpvdz": {("ae", "CC2"): dict(ecc=-0.026445902512140185)},                   # test_020_cc2.py:40 (no = 1)
 }
 MAX_DIIS = {"t034_sto3g": 0}
 ECCSD_T_STO3G = -0.0707167876524093      # test_044_ccsd_t_gpu.py:37
@@ -84,6 +85,8 @@ def geometry(tag):
         return [("O", np.array([0.0, -0.143225816552, 0.0])),
                 ("H", np.array([1.638036840407, 1.136548822547, 0.0])),
                 ("H", np.array([-1.638036840407, 1.136548822547, 0.0]))]
+    if tag.startswith("h2_"):            # moldict["H2"], pycc/data/molecules.py:2-6, bohr
+        return [("H", np.zeros(3)), ("H", np.array([0.0, 0.0, 1.4]))]
     if tag.startswith("t034"):           # pycc/tests/test_034_ccsd_t_density.py:19-25, bohr
         return [("O", np.array([0.0, 0.0, 0.143225857166674])),
                 ("H", np.array([0.0, -1.638037301628121, -1.136549142277225])),
@@ -121,18 +124,20 @@ def run_reference(mods, F, ERI, no, nfzc, model, want, max_diis=8):
 
 
 def make(tag, shells, mods):
-    S, H, eri, enuc = gto.integrals(geometry(tag), shells, CHARGE)
-    escf_el, eps, C, F_ao = gto.rhf(S, H, eri, ndocc=5)
+    atoms = geometry(tag)
+    ndocc = int(sum(CHARGE[sym] for sym, _ in atoms)) // 2
+    S, H, eri, enuc = gto.integrals(atoms, shells, CHARGE)
+    escf_el, eps, C, F_ao = gto.rhf(S, H, eri, ndocc=ndocc)
     n = S.shape[0]
     print("%s: n = %d  E_nuc = %.12f  E_SCF = %.12f" % (tag, n, enuc, escf_el + enuc))
     mo = np.einsum("pqrs,pi,qj,rk,sl->ijkl", eri, C, C, C, C, optimize=True)
     ERI = np.ascontiguousarray(mo.swapaxes(1, 2))          # Dirac <pq|rs>, hamiltonian.py:67
     F = C.T @ F_ao @ C
     rec = dict(S=S, Hcore=H, eri_packed=gto.pack_eri(eri), C=C, eps=eps, F_ao=F_ao, enuc=enuc, escf=escf_el + enuc,
-               ndocc=5)
+               ndocc=ndocc)
     for (core, model), hard in HARDCODED[tag].items():
         nfzc = 1 if core == "fc" else 0
-        out = run_reference(mods, F, ERI, 5 - nfzc, nfzc, model, hard, MAX_DIIS.get(tag, 8))
+        out = run_reference(mods, F, ERI, ndocc - nfzc, nfzc, model, hard, MAX_DIIS.get(tag, 8))
         key = "%s_%s" % (core, model.lower().replace("(t)", "pt"))
         for k, val in out.items():
             rec["ref_%s_%s" % (key, k)] = val

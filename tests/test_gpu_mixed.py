@@ -43,6 +43,25 @@ def test_split_tf32_planes():
     assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0 and int((lo.view(torch.int32) & 0x1FFF).abs().max()) == 0
 
 
+def test_merge_tf32_is_the_inverse_of_split():
+    """b200cc_merge_tf32: dst = hi + lo, exactly (both planes are FP32, their sum is exact in FP64), with a row offset into
+    the planes and an odd K (scalar tail), untouched columns beyond K."""
+    rows, Kd = 45, 361                                        # 19^2: the cc-pVDZ water case
+    x = rnd(rows, Kd) * 2.0
+    hi, lo, ldp = K.split_tf32(x, rows, Kd, Kd)
+    hi, lo = hi[0], lo[0]
+    want = hi.double() + lo.double()
+    got = K.merge_tf32(hi, lo, ldp, rows, Kd)
+    assert tuple(got.shape) == (rows, Kd) and torch.equal(got, want[:, :Kd])
+    assert float((got - x).abs().max() / x.abs().max()) < 2.0 ** -21
+    r0 = 7
+    part = K.merge_tf32((hi, r0 * ldp), (lo, r0 * ldp), ldp, rows - r0, Kd)
+    assert torch.equal(part, want[r0:, :Kd])
+    out = torch.full((rows, Kd), -7.0, dtype=torch.float64, device=x.device)
+    K.merge_tf32(hi, lo, ldp, rows, Kd - 3, out=out[:, :Kd - 3].contiguous())      # K < ldp - 3: whole float4 groups skipped
+    assert float(out.min()) == -7.0
+
+
 SHAPES = [(128, 256, 32), (128, 256, 64), (128, 128, 256), (256, 512, 2048), (37, 19, 53), (129, 300, 1000),
           (400, 513, 333), (1, 300, 77), (257, 1, 40), (1600, 1200, 4096)]
 

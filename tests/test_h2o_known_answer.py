@@ -36,7 +36,7 @@ def load(tag):
     return g
 
 
-FIX = {tag: load(tag) for tag in ("sto3g", "ccpvdz", "teach_ccpvdz", "t034_sto3g", "t034_ccpvdz")}
+FIX = {tag: load(tag) for tag in ("sto3g", "ccpvdz", "teach_ccpvdz", "t034_sto3g", "t034_ccpvdz", "h2_ccpvdz")}
 
 
 def hard(tag, core, model, what):
@@ -49,7 +49,7 @@ def ref(tag, core, model, what):
 
 def sizes(tag, core):
     nfzc = 1 if core == "fc" else 0
-    return 5 - nfzc, nfzc
+    return int(FIX[tag]["ndocc"]) - nfzc, nfzc
 
 
 @pytest.fixture(params=[pytest.param("emu"), pytest.param("cuda", marks=pytest.mark.gpu)])
@@ -68,10 +68,11 @@ def test_fixture_is_a_converged_rhf(tag):
     g = FIX[tag]
     S, C, F_ao, eps, eri = g["S"], g["C"], g["F_ao"], g["eps"], g["eri_ao"]
     n = S.shape[0]
-    assert n == (7 if tag.endswith("sto3g") else 24)
+    nd = int(g["ndocc"])
+    assert n == (7 if tag.endswith("sto3g") else 10 if tag.startswith("h2_") else 24)
     assert np.abs(C.T @ S @ C - np.eye(n)).max() < 1e-11
     assert np.abs(F_ao @ C - S @ C * eps).max() < 1e-10
-    D = C[:, :5] @ C[:, :5].T
+    D = C[:, :nd] @ C[:, :nd].T
     F = g["Hcore"] + 2 * np.einsum("pqrs,rs->pq", eri, D) - np.einsum("prqs,rs->pq", eri, D)
     assert np.abs(F - F_ao).max() < 1e-10                                   # the Fock matrix of its own density
     assert abs(np.sum(D * (g["Hcore"] + F)) + float(g["enuc"]) - float(g["escf"])) < 1e-10
@@ -85,9 +86,9 @@ def test_reference_outputs_match_its_hardcoded_numbers():
     for tag, g in FIX.items():
         for k in g:
             if k.startswith("dev_"):
-                assert abs(float(g[k])) < (1e-7 if k == "dev_ae_ccsd_ecc" else TOL), (tag, k)
+                assert abs(float(g[k])) < TOL, (tag, k)
                 n += 1
-    assert n == 13                      # + the CCSD(T) total of test_044 below = fourteen known answers
+    assert n == 15                      # + the CCSD(T) total of test_044 below = sixteen known answers
     assert abs(hard("sto3g", "fc", "CCSD", "ecc") + hard("sto3g", "fc", "CCSD", "et") - ECCSD_T_STO3G) < TOL
 
 
@@ -135,14 +136,20 @@ def test_oracle_ccsd_t_lambda(tag):
 
 def test_oracle_all_electron_ccsd_ccd_cc2():
     P, b, F, nfzc = oracle_problem("ccpvdz", "ae")
-    ecc = co.solve_cc(P, 1e-12, 1e-12, 75)[0]
-    assert abs(ecc - hard("ccpvdz", "ae", "CCSD", "ecc")) < 1e-7          # the reference's SP test
-    assert abs(ecc - float(ref("ccpvdz", "ae", "CCSD", "ecc"))) < TOL
+    ecc, t1, t2, _ = co.solve_cc(P, 1e-12, 1e-12, 75)
+    assert abs(ecc - hard("ccpvdz", "ae", "CCSD", "ecc")) < TOL           # the reference's SP test asks for 1e-7
+    assert abs(lo.solve_lambda(P, t1, t2, 1e-12, 1e-12, 75)[0] - hard("ccpvdz", "ae", "CCSD", "lecc")) < TOL
     eccd, t1, t2 = oracle_ccd(P, F)
     assert abs(eccd - hard("ccpvdz", "ae", "CCD", "ecc")) < TOL
     lecc = lo.solve_lambda(P, t1, t2, 1e-12, 1e-12, 75, model="CCD")[0]
     assert abs(lecc - hard("ccpvdz", "ae", "CCD", "lecc")) < TOL
     assert abs(cc2_oracle.solve_cc(P, 1e-12, 1e-12, 75)[0] - hard("ccpvdz", "ae", "CC2", "ecc")) < TOL
+
+
+def test_oracle_cc2_h2():
+    """no = 1"""
+    P, b, F, nfzc = oracle_problem("h2_ccpvdz", "ae")
+    assert abs(cc2_oracle.solve_cc(P, 1e-12, 1e-12, 75)[0] - hard("h2_ccpvdz", "ae", "CC2", "ecc")) < TOL
 
 
 def test_oracle_cc3():
@@ -222,6 +229,14 @@ def test_ccsd_t_density_lambda(dev, tag):
     assert abs(float(lecc) - hard(tag, "ae", "CCSD(T)", "lecc")) < TOL
 
 
+def test_all_electron_ccsd_lambda(dev):
+    """test_030_sp.py:26-40 in double precision (the hard-coded numbers are good to 1e-14)."""
+    cc = pycc_b200.ccwfn(h2o_reference("ccpvdz", "ae"), quiet=True)
+    assert abs(float(cc.solve_cc(1e-12, 1e-12, 75)) - hard("ccpvdz", "ae", "CCSD", "ecc")) < TOL
+    lecc = pycc_b200.cclambda(cc, pycc_b200.cchbar(cc)).solve_lambda(1e-12, 1e-12)
+    assert abs(float(lecc) - hard("ccpvdz", "ae", "CCSD", "lecc")) < TOL
+
+
 def test_ccd_and_its_lambda(dev):
     """test_017_ccd.py:11-26 (all-electron)"""
     cc = pycc_b200.ccwfn(h2o_reference("ccpvdz", "ae"), model="CCD", quiet=True)
@@ -236,6 +251,24 @@ def test_cc2(dev):
     assert abs(float(cc.solve_cc(1e-12, 1e-12, 75)) - hard("ccpvdz", "ae", "CC2", "ecc")) < TOL
 
 
+def test_cc2_h2(dev):
+    """test_020_cc2.py:32-41: one occupied orbital."""
+    cc = pycc_b200.ccwfn(h2o_reference("h2_ccpvdz", "ae"), model="CC2", quiet=True)
+    assert abs(float(cc.solve_cc(1e-12, 1e-12, 75)) - hard("h2_ccpvdz", "ae", "CC2", "ecc")) < TOL
+
+
+def test_ccsd_h2_one_occupied(dev):
+    """Edge case no = 1 through CCSD(T) + Lambda (no reference number: oracle on the same integrals)."""
+    P, b, F, nfzc = oracle_problem("h2_ccpvdz", "ae")
+    ecc, t1, t2, _ = co.solve_cc(P, 1e-12, 1e-12, 75)
+    cc = pycc_b200.ccwfn(h2o_reference("h2_ccpvdz", "ae"), model="CCSD(T)", quiet=True)
+    assert abs(float(cc.solve_cc(1e-12, 1e-12, 75)) - ecc) < TOL          # E(T) = 0 with one occupied orbital
+    cc2 = pycc_b200.ccwfn(h2o_reference("h2_ccpvdz", "ae"), quiet=True)
+    cc2.solve_cc(1e-12, 1e-12, 75)
+    lecc = pycc_b200.cclambda(cc2, pycc_b200.cchbar(cc2)).solve_lambda(1e-12, 1e-12)
+    assert abs(float(lecc) - lo.solve_lambda(P, t1, t2, 1e-12, 1e-12, 75)[0]) < TOL
+
+
 def test_cc3(dev):
     """test_031_cc3.py:24-32 (H2O_Teach geometry, all-electron)"""
     cc = pycc_b200.ccwfn(h2o_reference("teach_ccpvdz", "ae"), model="CC3", quiet=True)
@@ -247,6 +280,8 @@ def test_sp_all_electron(dev):
     cc = pycc_b200.ccwfn(h2o_reference("ccpvdz", "ae"), precision="SP", quiet=True)
     ecc = cc.solve_cc(1e-7, 1e-7)
     assert abs(float(ecc) - hard("ccpvdz", "ae", "CCSD", "ecc")) < 1e-7
+    lecc = pycc_b200.cclambda(cc, pycc_b200.cchbar(cc)).solve_lambda(1e-7, 1e-7)
+    assert abs(float(lecc) - hard("ccpvdz", "ae", "CCSD", "lecc")) < 1e-7
 
 
 @pytest.mark.parametrize("tag", ["sto3g", "ccpvdz"])
@@ -255,3 +290,17 @@ def test_mixed_precision_within_1e6(dev, tag):
     cc = pycc_b200.ccwfn(h2o_reference(tag, "fc"), model="CCSD(T)", device="GPU", precision="MP", quiet=True)
     ecc = cc.solve_cc(1e-7, 1e-7, 75)      # the reference's defaults; the split-TF32 products leave rms ~1e-8
     assert abs(float(ecc) - hard(tag, "fc", "CCSD", "ecc") - hard(tag, "fc", "CCSD", "et")) < 1e-6
+
+
+def test_mixed_precision_lambda_cc2_cc3(dev):
+    """precision='MP' releases the FP64 <ab|ef> block; HBAR / CC2 / CC3 rebuild the rows they need from its TF32 planes
+    (b200cc_merge_tf32).  Within 1e-6 Eh of the reference's FP64 numbers."""
+    cc = pycc_b200.ccwfn(h2o_reference("ccpvdz", "fc"), precision="MP", quiet=True)
+    assert abs(float(cc.solve_cc(1e-7, 1e-7, 75)) - hard("ccpvdz", "fc", "CCSD", "ecc")) < 1e-6
+    assert cc._vvvv_released()
+    lecc = pycc_b200.cclambda(cc, pycc_b200.cchbar(cc)).solve_lambda(1e-7, 1e-7)
+    assert abs(float(lecc) - hard("ccpvdz", "fc", "CCSD", "lecc")) < 1e-6
+    cc = pycc_b200.ccwfn(h2o_reference("ccpvdz", "ae"), model="CC2", precision="MP", quiet=True)
+    assert abs(float(cc.solve_cc(1e-7, 1e-7, 75)) - hard("ccpvdz", "ae", "CC2", "ecc")) < 1e-6
+    cc = pycc_b200.ccwfn(h2o_reference("teach_ccpvdz", "ae"), model="CC3", precision="MP", quiet=True)
+    assert abs(float(cc.solve_cc(1e-7, 1e-7, 75)) - hard("teach_ccpvdz", "ae", "CC3", "ecc")) < 1e-6
