@@ -122,7 +122,7 @@ def test_split_is_a_partition():
             assert max(hi - lo for lo, hi in parts) - min(hi - lo for lo, hi in parts) <= 1
 
 
-def _worker_lambda(rank, world, port, lam_path, q):
+def _worker_lambda(rank, world, port, lam_path, q, precision="DP"):
     """HBAR + Lambda with an a-sharded <ab|ef>: the t1.<ab|ef> term of Hvvvo and the Lambda ladder are rank-local pieces
     summed by all-reduces, everything else is replicated."""
     sys.path.insert(0, ROOT)
@@ -136,12 +136,13 @@ def _worker_lambda(rank, world, port, lam_path, q):
         from tests.test_lambda import load
         g, syn, model = load(lam_path)
         with emu.install():
-            cc = pycc_b200.ccwfn(syn, model=model, device="GPU", quiet=True, comm=Comm())
+            cc = pycc_b200.ccwfn(syn, model=model, device="GPU", quiet=True, comm=Comm(), precision=precision)
+            assert cc._vvvv_released() == (precision == "MP")
             cc.t1, cc.t2 = torch.from_numpy(g["t1"].copy()), torch.from_numpy(g["t2"].copy())
             hb = pycc_b200.cchbar(cc)
             dh = float(np.abs(hb.Hvvvo.numpy() - g["Hvvvo"]).max())
             lm = pycc_b200.cclambda(cc, hb)
-            lecc = lm.solve_lambda(1e-12, 1e-12, 100)
+            lecc = lm.solve_lambda(*((1e-12, 1e-12, 100) if precision == "DP" else (1e-8, 1e-8, 100)))
             q.put((rank, dh, abs(float(lecc) - float(g["lecc"])), float(np.abs(lm.l2.numpy() - g["conv_l2"]).max()),
                    len(lm.trace), len(g["trace_lecc_rms"])))
     finally:
@@ -164,3 +165,22 @@ def test_lambda_with_sharded_vvvv(world):
         assert p.exitcode == 0
     for rank, dh, de, dl, n, nref in res:
         assert dh < 1e-12 and de < 1e-11 and dl < 1e-10 and n == nref, (rank, dh, de, dl, n, nref)
+
+
+def test_lambda_with_sharded_vvvv_mixed_precision():
+    """precision='MP' on two ranks: the a-sharded <ab|ef> exists only as TF32 planes; the t1.<ab|ef> piece of Hvvvo is
+    rebuilt from them (b200cc_merge_tf32), the Lambda ladder uses them directly.  Within 1e-6 of the FP64 reference."""
+    import glob
+    path = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "lam_o4v10_s1_noise_ccsd.npz")))[0]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 500) + 31
+    procs = [ctx.Process(target=_worker_lambda, args=(r, 2, port, path, q, "MP")) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, dh, de, dl, n, nref in res:
+        assert dh < 1e-6 and de < 1e-6 and dl < 1e-6, (rank, dh, de, dl)
