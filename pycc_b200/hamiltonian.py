@@ -164,7 +164,9 @@ class BlockHamiltonian:
     def has(self, name):
         return name in self._blocks
 
-    def vvvv_fp64_chunks(self, chunk_bytes=2 << 30):
+    merge_chunk_bytes = 2 << 30        # size of the FP64 row chunks rebuilt from the TF32 planes of <ab|ef>
+
+    def vvvv_fp64_chunks(self, chunk_bytes=None):
         """(a0, a1, FP64 [a1-a0, v, v, v]) over the RESIDENT rows of <ab|ef> (local row numbers): the block itself, or --
         precision='MP' after the FP64 block was released -- chunks rebuilt from its TF32 planes (hi + lo: 2^-22
         relative, the accuracy of the mode).  For the few FP64-only consumers of <ab|ef> outside the ladder
@@ -178,6 +180,7 @@ class BlockHamiltonian:
         hi, lo, ldp = self.vvvv_planes
         nv = self.nv
         na = hi.shape[0] // nv
+        chunk_bytes = self.merge_chunk_bytes if chunk_bytes is None else chunk_bytes
         step = int(max(1, min(na, chunk_bytes // max(8 * nv ** 3, 1))))
         for a0 in range(0, na, step):
             a1 = min(na, a0 + step)

@@ -1,5 +1,6 @@
-"""HBAR build + Lambda iteration on the GPU: wall times and FP64 rate.  python scripts/lambda_probe.py O V
-Writes gpurun_out/lambda_probe_o<O>v<V>.json"""
+"""HBAR build + Lambda iteration on the GPU: wall times and FP64 rate.
+    python scripts/lambda_probe.py O V [conv] [DP|MP]
+Writes gpurun_out/lambda_probe_o<O>v<V>[_mp].json"""
 import json
 import os
 import sys
@@ -14,9 +15,10 @@ from pycc_b200.synthetic import make_synthetic  # noqa: E402
 
 o, v = int(sys.argv[1]), int(sys.argv[2])
 conv = float(sys.argv[3]) if len(sys.argv) > 3 else 1e-10
+prec = sys.argv[4] if len(sys.argv) > 4 else "DP"
 dev = torch.device("cuda:0")
 syn = make_synthetic(o, v, seed=0, device=dev)
-cc = pycc_b200.ccwfn(syn, model="CCSD", device="GPU", quiet=True)
+cc = pycc_b200.ccwfn(syn, model="CCSD", device="GPU", quiet=True, precision=prec)
 torch.cuda.synchronize()
 t0 = time.time()
 ecc = cc.solve_cc(conv, conv, 60)
@@ -37,11 +39,11 @@ t_lam = time.time() - t0
 iters = len(lm.trace)
 # dominant terms of one Lambda iteration: Hvvvv ladder, Hoooo, three o^3v^3 ring terms, l2.Hvvvo / l2.Hovoo, Goo/Gvv
 fl = 2 * o**2 * v**4 + 2 * o**4 * v**2 + 3 * 2 * o**3 * v**3 + 2 * o**2 * v**3 * 2 + 2 * o**3 * v**2 * 2 + 2 * o**2 * v**3 + 2 * o**3 * v**2
-out = {"o": o, "v": v, "conv": conv, "hvvvv_materialised": hb._Hvvvv is not None,
+out = {"o": o, "v": v, "conv": conv, "precision": prec, "mixed_stats": dict(K.MIXED.stats), "hvvvv_materialised": hb._Hvvvv is not None,
        "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9, "ecc": float(ecc), "ccsd_s_per_iter": t_cc / len(cc.trace), "hbar_s": t_hbar, "hbar_launches": n_hbar,
        "lambda_pseudoE": float(lecc) if lecc is not None else None, "lambda_iters": iters,
        "lambda_s_per_iter": t_lam / iters, "lambda_launches_per_iter": (K.launch_count() - l0) / iters,
        "lambda_tflops": fl / (t_lam / iters) / 1e12}
 print(json.dumps(out))
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(out, open("gpurun_out/lambda_probe_o%dv%d.json" % (o, v), "w"), indent=1)
+json.dump(out, open("gpurun_out/lambda_probe_o%dv%d%s.json" % (o, v, "" if prec == "DP" else "_" + prec.lower()), "w"), indent=1)

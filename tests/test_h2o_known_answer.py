@@ -298,7 +298,10 @@ def test_mixed_precision_lambda_cc2_cc3(dev):
     cc = pycc_b200.ccwfn(h2o_reference("ccpvdz", "fc"), precision="MP", quiet=True)
     assert abs(float(cc.solve_cc(1e-7, 1e-7, 75)) - hard("ccpvdz", "fc", "CCSD", "ecc")) < 1e-6
     assert cc._vvvv_released()
-    lecc = pycc_b200.cclambda(cc, pycc_b200.cchbar(cc)).solve_lambda(1e-7, 1e-7)
+    hb = pycc_b200.cchbar(cc)
+    cc.H.merge_chunk_bytes = 8 * 19 ** 3 * 3                    # three rows a of <ab|ef> per rebuilt chunk: same block
+    assert float((pycc_b200.cchbar(cc).Hvvvo - hb.Hvvvo).abs().max()) < 1e-13
+    lecc = pycc_b200.cclambda(cc, hb).solve_lambda(1e-7, 1e-7)
     assert abs(float(lecc) - hard("ccpvdz", "fc", "CCSD", "lecc")) < 1e-6
     cc = pycc_b200.ccwfn(h2o_reference("ccpvdz", "ae"), model="CC2", precision="MP", quiet=True)
     assert abs(float(cc.solve_cc(1e-7, 1e-7, 75)) - hard("ccpvdz", "ae", "CC2", "ecc")) < 1e-6
