@@ -307,3 +307,25 @@ def test_mixed_precision_lambda_cc2_cc3(dev):
     assert abs(float(cc.solve_cc(1e-7, 1e-7, 75)) - hard("ccpvdz", "ae", "CC2", "ecc")) < 1e-6
     cc = pycc_b200.ccwfn(h2o_reference("teach_ccpvdz", "ae"), model="CC3", precision="MP", quiet=True)
     assert abs(float(cc.solve_cc(1e-7, 1e-7, 75)) - hard("teach_ccpvdz", "ae", "CC3", "ecc")) < 1e-6
+
+
+def test_h2_minimal_basis_one_occupied_one_virtual(dev):
+    """Smallest closed-shell problem there is: H2 / STO-3G (no = nv = 1), integrals computed on the fly.  CCSD is exact
+    here (two electrons); Szabo & Ostlund quote E_SCF = -1.1167 and E_corr = -0.0206 Eh at R = 1.4 bohr.  The product
+    must equal the oracle through CCSD(T) (E(T) = 0) and Lambda.  max_diis=0: with a single non-zero amplitude the DIIS
+    error vectors are collinear and the B matrix of utils.py:330-348 is singular (in the reference as well)."""
+    sto3g_h = {"H": [(0, [3.42525091, 0.62391373, 0.16885540], [0.15432897, 0.53532814, 0.44463454])]}
+    atoms = [("H", np.zeros(3)), ("H", np.array([0.0, 0.0, 1.4]))]
+    S, Hc, eri, enuc = gto.integrals(atoms, sto3g_h, {"H": 1.0})
+    eel, eps, C, F_ao = gto.rhf(S, Hc, eri, ndocc=1)
+    assert abs(eel + enuc + 1.1167) < 1e-4
+    F, ERI, _ = ao.mo_hamiltonian(F_ao, eri, C)
+    P = co.Problem(co.blocks_from_full(ERI, 1, 0), F, 1, 0)
+    ecc, t1, t2, _ = co.solve_cc(P, 1e-12, 1e-12, 200, max_diis=0)
+    assert abs(ecc + 0.0206) < 1e-4
+    cc = pycc_b200.ccwfn(IntegralReference.from_ao(F_ao, eri, C, 1, 0), model="CCSD(T)", quiet=True)
+    assert abs(float(cc.solve_cc(1e-12, 1e-12, 200, max_diis=0)) - ecc) < TOL
+    cc = pycc_b200.ccwfn(IntegralReference.from_ao(F_ao, eri, C, 1, 0), quiet=True)
+    cc.solve_cc(1e-12, 1e-12, 200, max_diis=0)
+    lecc = pycc_b200.cclambda(cc, pycc_b200.cchbar(cc)).solve_lambda(1e-12, 1e-12, 200, max_diis=0)
+    assert abs(float(lecc) - lo.solve_lambda(P, t1, t2, 1e-12, 1e-12, 200, max_diis=0)[0]) < TOL
