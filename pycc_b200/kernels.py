@@ -78,7 +78,11 @@ class _Mixed:
     config = int(os.environ.get("B200CC_MP_CONFIG", "0"))
     lockstep = int(os.environ.get("B200CC_MP_LOCKSTEP", "0"))   # leader/follower tile schedule: >0 skew in k-blocks, <=0 off
     min_tiles = 74        # fewer 128x128 output tiles than this: the split-K FP64 kernel fills the SMs better
-    stats = {"gemm": 0, "split": 0, "split_cached": 0}
+    # Upper bound on the TF32 planes kept per owner (Hamiltonian / (T) engine) for constant operands.  Beyond it a
+    # constant is split per use like any other operand (an 8.6 GB block: ~3 ms) instead of doubling its footprint:
+    # HBAR + Lambda touch three permuted copies of <ma|ef>, whose cached planes put the o=40,v=300 peak at 179.6 GB.
+    cache_bytes = int(float(os.environ.get("B200CC_MP_CACHE_GB", "32")) * (1 << 30))
+    stats = {"gemm": 0, "split": 0, "split_cached": 0, "split_uncached_over_budget": 0}
 
 
 MIXED = _Mixed()
@@ -161,7 +165,12 @@ def _split_operand(X, rows, K, ld, batch, stride):
     key = (_addr(X), int(rows), int(K), int(ld), int(batch) if stride else 1, int(stride))
     r = cache.get(key)
     if r is None:
-        r = cache[key] = split_tf32(X, rows, K, ld, batch, stride)
+        r = split_tf32(X, rows, K, ld, batch, stride)
+        held = sum(2 * 4 * v[0].numel() for v in cache.values())
+        if held + 2 * 4 * r[0].numel() <= MIXED.cache_bytes:
+            cache[key] = r
+        else:
+            MIXED.stats["split_uncached_over_budget"] += 1
     else:
         MIXED.stats["split_cached"] += 1
     return r

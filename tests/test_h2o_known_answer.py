@@ -329,3 +329,25 @@ def test_h2_minimal_basis_one_occupied_one_virtual(dev):
     cc.solve_cc(1e-12, 1e-12, 200, max_diis=0)
     lecc = pycc_b200.cclambda(cc, pycc_b200.cchbar(cc)).solve_lambda(1e-12, 1e-12, 200, max_diis=0)
     assert abs(float(lecc) - lo.solve_lambda(P, t1, t2, 1e-12, 1e-12, 200, max_diis=0)[0]) < TOL
+
+
+def test_split_plane_cache_budget(dev):
+    """kernels.MIXED.cache_bytes bounds the cached TF32 planes of constant operands; past it a constant is split per
+    use.  Same numbers either way."""
+    from pycc_b200 import kernels as K
+    keep = (K.MIXED.min_flops, K.MIXED.min_dim, K.MIXED.min_tiles, K.MIXED.cache_bytes)
+    K.MIXED.min_flops, K.MIXED.min_dim, K.MIXED.min_tiles = 0.0, 1, 1       # tiny problem: force the mixed kernel
+    try:
+        res = []
+        for budget in (keep[3], 0):
+            K.MIXED.cache_bytes = budget
+            n0 = K.MIXED.stats["split_uncached_over_budget"]
+            cc = pycc_b200.ccwfn(h2o_reference("ccpvdz", "fc"), precision="MP", quiet=True)
+            e = float(cc.solve_cc(1e-7, 1e-7, 75))
+            lecc = float(pycc_b200.cclambda(cc, pycc_b200.cchbar(cc)).solve_lambda(1e-7, 1e-7))
+            res.append((e, lecc, K.MIXED.stats["split_uncached_over_budget"] - n0))
+    finally:
+        K.MIXED.min_flops, K.MIXED.min_dim, K.MIXED.min_tiles, K.MIXED.cache_bytes = keep
+    assert res[0][2] == 0 and res[1][2] > 0
+    assert abs(res[0][0] - res[1][0]) < 1e-10 and abs(res[0][1] - res[1][1]) < 1e-10
+    assert abs(res[0][0] - hard("ccpvdz", "fc", "CCSD", "ecc")) < 1e-6
