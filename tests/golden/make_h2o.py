@@ -4,14 +4,23 @@
     python tests/golden/make_h2o.py        # rewrites tests/golden/h2o_*.npz (all, or the tags given)
 
 The reference's tests pin the path on this molecule with hard-coded numbers (geometry ``moldict["H2O"]`` =
-pycc/data/molecules.py:42-46, frozen core, SCF converged to 1e-12 -- pycc/tests/conftest.py:28-36):
+pycc/data/molecules.py:42-46 unless noted, SCF converged to 1e-12 -- pycc/tests/conftest.py:28-36); "fc" = frozen core,
+"ae" = all-electron:
 
-                      STO-3G                  cc-pVDZ
-    E_corr(CCSD)      -0.070616830152761      -0.222029814166783     test_002_ccsd_energy.py:31,38
-    E(T)              -0.000099957499645      -0.003861236558801     test_005_ccsd_t_energy.py:33,44
-    E_corr(CCSD(T))   -0.0707167876524093                            test_044_ccsd_t_gpu.py:37
-    E_corr(CCD)                               -0.222559319034        test_017_ccd.py:19
-    E_corr(CCSD), all-electron                -0.223910018703551     test_030_sp.py:30 (precision='SP', 1e-7)
+    tag            what                          STO-3G                cc-pVDZ               reference test
+    sto3g/ccpvdz   fc E_corr(CCSD)               -0.070616830152761    -0.222029814166783    test_002:31,38
+                   fc E(T)                       -0.000099957499645    -0.003861236558801    test_005:33,44
+                   fc Lambda pseudo-energy       -0.068826452648939    -0.217838951550509    test_003:49,61
+                   fc E_corr(CCSD(T))            -0.0707167876524093                         test_044:37 (device='GPU')
+    ccpvdz         ae E_corr(CCSD), its Lambda                         -0.223910018703551    test_030:30,39 ('SP', 1e-7)
+                                                                       -0.219688229733875
+                   ae E_corr(CCD), its Lambda                          -0.222559319034       test_017:19,25
+                                                                       -0.218758826700
+                   ae E_corr(CC2)                                      -0.215857544656       test_020:19
+    teach_ccpvdz   ae E_corr(CC3), moldict["H2O_Teach"]                -0.227888246840310    test_031:31
+    t034_*         ae Lambda of CCSD(T) with the     -0.069084521221746    -0.227199866607450    test_034:44,68
+                   t3_density sources (geometry of test_034:19-25; STO-3G with max_diis=0)
+    h2_ccpvdz      ae E_corr(CC2), moldict["H2"] (no = 1)              -0.026445902512140185 test_020:40
 
 cc-pVDZ is BASELINE.json configs[0].  psi4 (which supplies the integrals to the reference, hamiltonian.py:58-68) is
 not installable offline, so the integrals are computed by tests/golden/gto.py (McMurchie-Davidson in numpy), RHF is
