@@ -107,6 +107,9 @@ class cchbar(object):
         self.contract = ccwfn.contract
         self.o, self.v = ccwfn.o, ccwfn.v
         self.no, self.nv = ccwfn.no, ccwfn.nv
+        if getattr(ccwfn, "mixed", False):
+            # the planes the CCSD iterations cached (33 GB at o=40,v=300) are of no use to HBAR / Lambda
+            ccwfn.H.release_split_cache()
         blocks = self.build_all(ccwfn.H.F, ccwfn.t1, ccwfn.t2)
         for k in EAGER:
             setattr(self, k, blocks[k])
@@ -159,7 +162,7 @@ class cchbar(object):
             out = K.permuted(src, tuple(range(src.dim())))
         todo = list(terms) + ([] if w.model == "CCD" else list(singles))
         sharded = w.part.size > 1
-        with K.mixed_mode(getattr(w, "mixed", False)):
+        with K.mixed_mode(getattr(w, "mixed", False), cache=False):
             for alpha, sub, a, b in todo:
                 if sharded and "E:vvvv" in (a, b):
                     self._vvvv_term_sharded(out, alpha, sub, a, b, env)

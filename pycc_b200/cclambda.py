@@ -72,7 +72,7 @@ class cclambda(object):
 
     def _accumulate(self, out, terms, env):
         ct = self.ccwfn._ct
-        with K.mixed_mode(getattr(self.ccwfn, "mixed", False)):
+        with K.mixed_mode(getattr(self.ccwfn, "mixed", False), cache=False):
             for alpha, sub, a, b in terms:
                 ct(sub, env[a], env[b], out=out, alpha=alpha, beta=1.0)
         return out
@@ -99,7 +99,7 @@ class cclambda(object):
         t2 = w.t2 if t2 is None else t2
         if Hvvvv is not None:
             return ct("ijef,efab->ijab", l2, Hvvvv, out=half, alpha=0.5, beta=1.0)
-        with K.mixed_mode(getattr(w, "mixed", False)):
+        with K.mixed_mode(getattr(w, "mixed", False), cache=False):
             if w.part.size > 1:
                 # <ab|ef> is a-sharded: every rank adds the rows it holds, one all-reduce (o^2v^2) sums the pieces;
                 # all other terms are replicated, so l1 / l2 stay identical on all ranks

@@ -164,6 +164,10 @@ class BlockHamiltonian:
     def has(self, name):
         return name in self._blocks
 
+    def release_split_cache(self):
+        """Drop the cached TF32 planes of the constant operands (precision='MP'); they are rebuilt on demand."""
+        self._split_cache.clear()
+
     merge_chunk_bytes = 2 << 30        # size of the FP64 row chunks rebuilt from the TF32 planes of <ab|ef>
 
     def vvvv_fp64_chunks(self, chunk_bytes=None):

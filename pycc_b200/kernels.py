@@ -89,18 +89,24 @@ MIXED = _Mixed()
 
 
 class mixed_mode:
-    """``with mixed_mode(flag):`` -- route eligible dgemm calls to the split-TF32 kernel inside the block."""
+    """``with mixed_mode(flag):`` -- route eligible dgemm calls to the split-TF32 kernel inside the block.
+    ``cache=False``: planes of constant operands met inside the block are not added to the cache (entries already
+    there are still used).  HBAR / Lambda run this way: measured at o=40,v=300 the cache buys them nothing (0.380 vs
+    0.382 s per Lambda iteration) and costs 33 GB (profiles/lambda_probe_r01_o40v300_mp_cache{0,32}.json)."""
 
-    def __init__(self, flag):
+    def __init__(self, flag, cache=True):
         self.flag = bool(flag)
+        self.cache = bool(cache)
 
     def __enter__(self):
-        self.prev = MIXED.on
+        self.prev = (MIXED.on, MIXED.cache_bytes)
         MIXED.on = self.flag
+        if not self.cache:
+            MIXED.cache_bytes = 0
         return self
 
     def __exit__(self, *exc):
-        MIXED.on = self.prev
+        MIXED.on, MIXED.cache_bytes = self.prev
         return False
 
 

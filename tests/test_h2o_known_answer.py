@@ -344,8 +344,12 @@ def test_split_plane_cache_budget(dev):
             n0 = K.MIXED.stats["split_uncached_over_budget"]
             cc = pycc_b200.ccwfn(h2o_reference("ccpvdz", "fc"), precision="MP", quiet=True)
             e = float(cc.solve_cc(1e-7, 1e-7, 75))
-            lecc = float(pycc_b200.cclambda(cc, pycc_b200.cchbar(cc)).solve_lambda(1e-7, 1e-7))
-            res.append((e, lecc, K.MIXED.stats["split_uncached_over_budget"] - n0))
+            n_ccsd = K.MIXED.stats["split_uncached_over_budget"] - n0
+            held = len(cc.H._split_cache)
+            hb = pycc_b200.cchbar(cc)                 # HBAR / Lambda never add to the cache and drop what CCSD left
+            lecc = float(pycc_b200.cclambda(cc, hb).solve_lambda(1e-7, 1e-7))
+            assert (held > 0) == (budget > 0) and len(cc.H._split_cache) == 0
+            res.append((e, lecc, n_ccsd))
     finally:
         K.MIXED.min_flops, K.MIXED.min_dim, K.MIXED.min_tiles, K.MIXED.cache_bytes = keep
     assert res[0][2] == 0 and res[1][2] > 0
