@@ -23,10 +23,25 @@ import sys
 import threading
 import time
 
-import numpy as np
-
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# BLAS thread count for the host legs (--impl reference, cpu_baseline) -- fixed BEFORE numpy / torch are imported, and
+# regardless of torchrun, which exports OMP_NUM_THREADS=1 to every rank: the reference arm always gets all host cores.
+_REFERENCE_ARM = any(a == "reference" or a == "--impl=reference" for a in sys.argv[1:])
+if _REFERENCE_ARM or int(os.environ.get("WORLD_SIZE", "1")) == 1:
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(host_cores())
+
+import numpy as np  # noqa: E402
 
 METRIC = "CCSD s/iter + (T) FP64 TFLOP/s at o=40 v=300, 1/2/4/8 B200 vs host CPU"
 FP64_PEAK_FALLBACK = 36.18     # TFLOP/s, cuBLAS DGEMM 8192^3 measured on this pool's B200 (profiles/probe_r01_first.json)
@@ -81,99 +96,122 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_sample(o_s, v_s, o, v, threads, reps=1):
-    """The oracle (numpy restatement of the reference algorithm) timed on the host cores for one full
-    CCSD iteration at the reduced size (o_s, v_s), scaled to (o, v) by the reference's algorithmic flops."""
-    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
-    from oracle import ccsd_oracle as co
-    from pycc_b200.synthetic import make_synthetic, blocks_from_factor
+def blas_threads(n):
+    """Pin the BLAS pool to n threads at run time as well (threadpoolctl) and report what the pools say."""
+    info = []
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=int(n))
+        info = [{"api": d.get("internal_api"), "threads": d.get("num_threads")} for d in threadpoolctl.threadpool_info()]
+    except Exception as exc:                              # the env variables above still apply
+        info = [{"api": "threadpoolctl unavailable: %s" % exc, "threads": None}]
+    return info
+
+
+FULLSIZE_RECORD = os.path.join(ROOT, "profiles", "reference_fullsize_r02.json")
+
+
+def reference_iterations(o_s, v_s, n_warm, n_timed, log=None):
+    """Real CCSD iterations of the reference's own CPU path on the host cores at (o_s, v_s).
+
+    With the reference available (baseline/_ref, see baseline/install_ref.py): its UNMODIFIED ``CCwfn.solve_cc`` loop --
+    ``residuals`` (ccwfn.py:321-372), Jacobi update + rms (281-284), ``cc_energy`` (286), ``helper_diis`` (317-319) -- on
+    integrals held in the memory layout its Hamiltonian uses, timed per iteration from its own prints.  Without it
+    (kind 'port'): the numpy oracle, which restates the same equations.  Returns (seconds per timed iteration, kind,
+    energies)."""
+    from pycc_b200.synthetic import make_synthetic
     syn = make_synthetic(o_s, v_s, seed=0)
+    n = n_warm + n_timed
+    try:
+        from baseline import refload
+        ref = refload.load_reference()
+    except ImportError:
+        ref = None
+    if ref is not None:
+        w = refload.reference_wfn(ref, syn.F, syn.no, None, blocks=refload.host_blocks(syn, log=log))
+        secs, en = refload.timed_solve_cc(w, n, echo=log)
+        return secs[n_warm:], "reference", en
+    from oracle import ccsd_oracle as co
+    from pycc_b200.synthetic import blocks_from_factor
     P = co.Problem(blocks_from_factor(syn), syn.F, o_s)
     t1, t2 = P.guess()
     diis = co.Diis(t1, t2, 8)
-    times = []
-    for _ in range(reps + 1):                       # first pass warms BLAS / einsum paths
+    secs, en = [], []
+    for _ in range(n):
         t0 = time.perf_counter()
         r1, r2 = P.residuals(syn.F, t1, t2)
         t1 = t1 + r1 / P.Dia
         t2 = t2 + r2 / P.Dijab
-        P.cc_energy(syn.F, t1, t2)
+        en.append(float(P.cc_energy(syn.F, t1, t2)))
         diis.add_error_vector(t1, t2)
         t1, t2 = diis.extrapolate(t1, t2)
-        times.append(time.perf_counter() - t0)
-    t_s = min(times[1:])
-    scale = ccsd_flops(o, v, False) / ccsd_flops(o_s, v_s, False)
-    sample = ("oracle (numpy port of ccwfn.py:321-372 + update/energy/DIIS) full CCSD iteration at o=%d,v=%d: %.3f s; "
-              "scaled to o=%d,v=%d by reference algorithmic flops x%.1f (estimate)" % (o_s, v_s, t_s, o, v, scale))
-    return t_s * scale, t_s, sample
+        secs.append(time.perf_counter() - t0)
+    return secs[n_warm:], "port", en
 
 
-def cpu_sample_fullsize(o, v, threads, na=None, budget_s=8.0):
-    """Bounded sample of the SAME workload on the host cores: the reference's two dominant contraction shapes evaluated
-    with the reference's own backend call (an exact einsum -> tensordot -> BLAS, device.py:84) on arrays of the real
-    (o, v) shape:
-      * the ladder 'ijef,abef->ijab' (ccwfn.py:931) on ``na`` of the v rows a of <ab|ef> (the full block is 64.8 GB);
-      * ONE of the nine o^3v^3 contractions, 'imae,mbej->ijab' (ccwfn.py:933), at full size.
-    The iteration is then  ladder_time * v/na + ring_time * (9 + the o^4v^2 / o^2v^3 terms at the ring's flop rate);
-    HBM-bound passes (tau, update, DIIS) are not counted, which favours the CPU."""
-    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
-    rng = np.random.default_rng(0)
-    # size both slices from a quick BLAS rate probe: ~budget_s/3 for the ladder rows, ~2 budget_s/3 for the ring columns
-    a = rng.standard_normal((1536, 1536))
-    a @ a
-    t0 = time.perf_counter()
-    a @ a
-    rate = 2 * 1536**3 / max(time.perf_counter() - t0, 1e-4)
-    if na is None:
-        na = int(max(1, min(v, (budget_s / 3.0) * rate / (2.0 * o * o * v**3))))
-    nj = int(max(1, min(o, (2.0 * budget_s / 3.0) * rate / (2.0 * o * o * v**3))))
-    tau = rng.standard_normal((o, o, v, v))
-    vslice = rng.standard_normal((na, v, v, v))
-    t0 = time.perf_counter()
-    np.einsum("ijef,abef->ijab", tau, vslice, optimize=True)
-    t_lad = time.perf_counter() - t0
-    del vslice
-    W = rng.standard_normal((o, v, v, nj))
-    t0 = time.perf_counter()
-    np.einsum("imae,mbej->ijab", tau, W, optimize=True)
-    t_ring = time.perf_counter() - t0
-    del W, tau
-    ring_fl = 2.0 * o**3 * v**3
-    other = (2 * 2 * o**4 * v**2 + 8 * 2 * o**2 * v**3) / ring_fl
-    est = t_lad * v / na + t_ring * (o / nj) * (9.0 + other)
-    sample = ("same shapes as the workload, reference backend call (einsum->tensordot->BLAS): ladder ijef,abef->ijab on "
-              "%d of %d rows a of <ab|ef>: %.2f s (%.0f GFLOP/s); one of the nine o^3v^3 terms imae,mbej->ijab on %d of "
-              "%d columns j: %.2f s (%.0f GFLOP/s); iteration = ladder*v/na + ring*(o/nj)*(9 + %.2f for the "
-              "o^4v^2/o^2v^3 terms); HBM-bound passes not counted"
-              % (na, v, t_lad, 2.0 * o * o * na * v**3 / t_lad / 1e9, nj, o, t_ring,
-                 ring_fl * nj / o / t_ring / 1e9, other))
-    return est, t_lad + t_ring, sample
+def reference_scale(o_s, v_s, o, v):
+    """Factor from a measured (o_s, v_s) iteration of the reference to one at (o, v), and where it comes from.
+    Preferred: the ratio MEASURED on this pool's host by running the reference itself once at both sizes
+    (profiles/reference_fullsize_r02.json, scripts/reference_fullsize.py).  Fallback: the reference's algorithmic flop
+    count (9 o^3v^3 terms as written), which ignores that its transposition copies grow more slowly than its flops."""
+    flop = ccsd_flops(o, v, False) / ccsd_flops(o_s, v_s, False)
+    try:
+        rec = json.load(open(FULLSIZE_RECORD))
+        if (rec["o"], rec["v"], rec["o_s"], rec["v_s"]) == (o, v, o_s, v_s):
+            return float(rec["seconds_full"]) / float(rec["seconds_small"]), (
+                "ratio measured with the reference itself on this pool's host: one real iteration at o=%d,v=%d took %.1f s, "
+                "at o=%d,v=%d %.2f s (%d cores, %s)" % (o, v, rec["seconds_full"], o_s, v_s, rec["seconds_small"],
+                                                        rec["cores"], os.path.relpath(FULLSIZE_RECORD, ROOT)))
+    except Exception:
+        pass
+    return flop, "the reference's algorithmic flop ratio (9 o^3v^3 terms), no full-size measurement on record"
+
+
+def cpu_leg(args, n_warm, n_timed, log=None):
+    """The host-CPU measurement shared by --impl reference and the cpu_baseline key: real iterations of the reference
+    at BASELINE configs[1] (o=20, v=150 -- the largest config it finishes in seconds per iteration), scaled to the
+    bench workload (o, v).  A full (o=40, v=300) iteration of the reference needs ~165 GB of host memory and minutes of
+    strided copies per step, so it cannot be repeated --steps times; it is measured once by scripts/reference_fullsize.py
+    and its record calibrates the scale factor."""
+    cores = host_cores()
+    pools = blas_threads(cores)
+    o_s, v_s = args.cpu_o, args.cpu_v
+    secs, kind, en = reference_iterations(o_s, v_s, n_warm, n_timed, log)
+    t_small = float(np.median(secs))
+    scale, how = reference_scale(o_s, v_s, args.o, args.v)
+    sample = ("%d real CCSD iterations (%d warm-up) of %s at o=%d,v=%d (BASELINE configs[1]) on %d host cores: median "
+              "%.3f s/iter (min %.3f, max %.3f); value = median x %.2f -- %s [estimate for o=%d,v=%d]"
+              % (n_timed, n_warm,
+                 "the unmodified reference (baseline/_ref: CCwfn.solve_cc loop = residuals + update + cc_energy + helper_diis)"
+                 if kind == "reference" else "the numpy oracle port of the reference (baseline/_ref absent)",
+                 o_s, v_s, cores, t_small, min(secs), max(secs), scale, how, args.o, args.v))
+    return {"value": t_small * scale, "unit": "s/iter", "cores": cores, "blas_threads": pools, "kind": kind,
+            "estimate": True, "measured_small": {"o": o_s, "v": v_s, "s_per_iter": t_small, "iterations": n_timed,
+                                                 "all": [round(x, 4) for x in secs], "ecc_last": en[-1]},
+            "scale": scale, "sample": sample}
 
 
 def run_reference(args):
-    """--impl reference: the reference's own algorithm on the host cores (oracle port; the reference is
-    pure Python + psi4 and cannot travel to the GPU box)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores, all BLAS threads.
+    Under torchrun rank 0 alone runs it; the other ranks exit 0 without work."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    cores = os.cpu_count() or 1
-    vals = []
-    sample = ""
-    nwarm = min(1, max(0, args.warmup))              # one untimed sample warms BLAS threads / page cache
-    for _ in range(max(1, args.steps) + nwarm):
-        est, t_s, sample = cpu_sample_fullsize(args.o, args.v, cores)
-        vals.append(est)
-    vals = vals[nwarm:]
-    v = float(np.median(vals))
+    log = (lambda m: print(m, file=sys.stderr, flush=True)) if args.verbose else None
+    t0 = time.time()
+    cpu = cpu_leg(args, max(1, args.warmup), max(1, args.steps), log)
+    v = cpu["value"]
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "s/iter", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": v * 1e3, "higher_is_better": False,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "RHF-CCSD iteration o=%d v=%d FP64 (synthetic integrals, seed 0); inputs >> L2 "
-                                   "(75 GB of integrals streamed per step)" % (args.o, args.v),
-                       "parallelism": "host cores, all BLAS threads"},
-            "cpu_baseline": {"value": v, "unit": "s/iter", "cores": cores, "kind": "port", "sample": sample},
+            "config": workload_config(args.o, args.v, "host cores, all BLAS threads"),
+            "cpu_baseline": cpu, "wall_s": time.time() - t0,
             "e2e": {"value": v, "unit": "s/iter", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def workload_config(o, v, parallelism):
+    return {"workload": "RHF-CCSD iteration o=%d v=%d FP64 (synthetic integrals, seed 0); inputs >> L2 "
+                        "(integral blocks streamed from HBM every step)" % (o, v), "parallelism": parallelism}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -185,8 +223,9 @@ def main():
     ap.add_argument("--impl", default="b200cc", choices=["b200cc", "reference"])
     ap.add_argument("--o", type=int, default=40)
     ap.add_argument("--v", type=int, default=300)
-    ap.add_argument("--cpu-o", type=int, default=16)
-    ap.add_argument("--cpu-v", type=int, default=120)
+    ap.add_argument("--cpu-o", type=int, default=20, help="size of the real reference iterations (configs[1])")
+    ap.add_argument("--cpu-v", type=int, default=150)
+    ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--t-triples", type=int, default=48, help="(T) sample: triples timed per rank-set")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-mp", action="store_true", help="skip the mixed-precision (precision='MP') leg")
@@ -211,9 +250,11 @@ def main():
     comm = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # keep stdout to the single JSON line: NCCL writes its banner ("NCCL version ...", printed from VERSION up,
-        # i.e. also at WARN) and debug lines to stdout unless NCCL_DEBUG_FILE points elsewhere
-        os.environ["NCCL_DEBUG"] = os.environ.get("B200CC_NCCL_DEBUG", "WARN")
+        # NCCL_DEBUG / NCCL_DEBUG_FILE are the caller's (the driver reads NCCL's own log to count ranks).  Only when
+        # nobody set them: keep stdout to the single JSON line -- NCCL prints its banner and debug lines to stdout
+        # unless NCCL_DEBUG_FILE points elsewhere.
+        if "NCCL_DEBUG" not in os.environ:
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
         comm = Comm()
@@ -456,12 +497,7 @@ def main():
     if rank == 0:
         cpu = None
         if not args.no_cpu and world == 1:          # reported at N=1 only (rank 0)
-            cores = os.cpu_count() or 1
-            est, t_s, sample = cpu_sample_fullsize(o, v, cores)
-            cpu = {"value": est, "unit": "s/iter", "cores": cores, "kind": "port", "sample": sample}
-            # cross-check: the whole oracle iteration (residuals + update + energy + DIIS) at a reduced size, flop-scaled
-            est_s, t_small, sample_s = cpu_sample(args.cpu_o, args.cpu_v, o, v, cores)
-            cpu["cross_check"] = {"value": est_s, "sample": sample_s}
+            cpu = cpu_leg(args, 1, 2)               # ~3 real reference iterations at configs[1]: 10-30 s of CPU work
         line = {"metric": METRIC, "value": s_iter, "unit": "s/iter", "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": s_iter * 1e3, "higher_is_better": False,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

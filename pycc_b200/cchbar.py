@@ -110,11 +110,16 @@ class cchbar(object):
         if getattr(ccwfn, "mixed", False):
             # the planes the CCSD iterations cached (33 GB at o=40,v=300) are of no use to HBAR / Lambda
             ccwfn.H.release_split_cache()
-        blocks = self.build_all(ccwfn.H.F, ccwfn.t1, ccwfn.t2)
+        # HBAR belongs to the amplitudes it was built from: keep a snapshot, not references -- solve_cc / update_amps
+        # mutate ccwfn.t1 / t2 in place, and the lazily built Hvvvv and the Lambda ladder (which substitutes Hvvvv by
+        # its definition in t1, t2) must see the same amplitudes as the eagerly built blocks
+        self.t1 = K.permuted(ccwfn.t1, (0, 1))
+        self.t2 = K.permuted(ccwfn.t2, (0, 1, 2, 3))
+        blocks = self.build_all(ccwfn.H.F, self.t1, self.t2)
         for k in EAGER:
             setattr(self, k, blocks[k])
         self._Hvvvv = None
-        self._amps = (ccwfn.H.F, ccwfn.t1, ccwfn.t2)
+        self._amps = (K.permuted(ccwfn.H.F, (0, 1)), self.t1, self.t2)
         if not getattr(ccwfn, "quiet", False):
             print(timing("HBAR", time.time() - t0))
 
@@ -212,7 +217,7 @@ class cchbar(object):
 
     def build_Hov(self, o, v, F, L, t1):
         self.ccwfn._own(L=L)
-        return self._one("Hov", F, t1, self.ccwfn.t2)
+        return self._one("Hov", F, t1, self.t2)
 
     def build_Hvv(self, o, v, F, L, t1, t2):
         self.ccwfn._own(L=L)
@@ -232,11 +237,11 @@ class cchbar(object):
 
     def build_Hvovv(self, o, v, ERI, t1):
         self.ccwfn._own(ERI)
-        return self._one("Hvovv", self.ccwfn.H.F, t1, self.ccwfn.t2)
+        return self._one("Hvovv", self.ccwfn.H.F, t1, self.t2)
 
     def build_Hooov(self, o, v, ERI, t1):
         self.ccwfn._own(ERI)
-        return self._one("Hooov", self.ccwfn.H.F, t1, self.ccwfn.t2)
+        return self._one("Hooov", self.ccwfn.H.F, t1, self.t2)
 
     def build_Hovvo(self, o, v, ERI, L, t1, t2):
         self.ccwfn._own(ERI, L)

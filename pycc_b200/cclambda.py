@@ -49,7 +49,9 @@ class cclambda(object):
                             "make_t3_density=True (or call ccwfn.t3_density()) first")
         self.ccwfn, self.hbar = ccwfn, hbar
         self.contract = ccwfn.contract
-        t1, t2 = ccwfn.t1, ccwfn.t2
+        # the amplitudes HBAR was built from (its snapshot), not whatever the wavefunction holds by now
+        t1, t2 = getattr(hbar, "t1", ccwfn.t1), getattr(hbar, "t2", ccwfn.t2)
+        self.t1, self.t2 = t1, t2
         # l1 = 2 t1, l2 = 2 (2 t2 - t2^T)                                              cclambda.py:65-66
         self.l1 = torch.empty_like(t1)
         K.strided_axpby(self.l1, t1, 2.0, 0.0)
@@ -93,10 +95,10 @@ class cclambda(object):
            - 1/2 (l2_ijef t_mf) <em|ab> - 1/2 (l2_ijef t_me) <fm|ba>                     two o^3v^3 products
            + 1/2 (l2_ijef tau_mnef) <mn|ab>                                              two o^4v^2 products
         (cchbar.py:394-403 substituted).  A caller that hands in a materialised ``Hvvvv`` gets the literal term.
-        ``t1, t2``: the amplitudes HBAR is built from (default: the wavefunction's)."""
+        ``t1, t2``: the amplitudes HBAR is built from (default: HBAR's own snapshot)."""
         w, ct = self.ccwfn, self.ccwfn._ct
-        t1 = w.t1 if t1 is None else t1
-        t2 = w.t2 if t2 is None else t2
+        t1 = self.t1 if t1 is None else t1
+        t2 = self.t2 if t2 is None else t2
         if Hvvvv is not None:
             return ct("ijef,efab->ijab", l2, Hvvvv, out=half, alpha=0.5, beta=1.0)
         with K.mixed_mode(getattr(w, "mixed", False), cache=False):
@@ -186,7 +188,7 @@ class cclambda(object):
         self.trace = []
         for niter in range(1, maxiter + 1):
             last = lecc
-            Goo, Gvv = self.build_Goo(w.t2, self.l2), self.build_Gvv(w.t2, self.l2)
+            Goo, Gvv = self.build_Goo(self.t2, self.l2), self.build_Gvv(self.t2, self.l2)
             r1 = self.r_L1(o, v, self.l1, self.l2, hb.Hov, hb.Hvv, hb.Hoo, hb.Hovvo, hb.Hovov, hb.Hvvvo, hb.Hovoo,
                            hb.Hvovv, hb.Hooov, Gvv, Goo, s1=s1, W=W)
             half = self._r_L2_half(self.l1, self.l2, hb.Hov, hb.Hvv, hb.Hoo, hb.Hoooo, None, hb.Hovvo, hb.Hovov,

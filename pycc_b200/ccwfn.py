@@ -302,6 +302,9 @@ class CCwfn(object):
         """(r1, r2) for the given Fock matrix and amplitudes; r2 symmetrised as in r_T2 (ccwfn.py:790)."""
         if _is_complex(t1) or _is_complex(t2) or _is_complex(F):
             return self._residuals_complex(F, t1, t2)
+        if real_time and self.model == 'CC3':
+            # ccwfn.py:399-404: with real_time the CC3 triples use the explicit-field intermediates
+            raise NotImplementedError("the explicit-field (real-time) CC3 triples are outside the accelerated path")
         r1, half = self._residuals_half(F, t1, t2)
         K.symmetrize_r2(half)
         return r1, half
@@ -312,6 +315,10 @@ class CCwfn(object):
         complex right-hand side costs 5 real residuals where complex arithmetic would cost 4 (3 with the 3M trick)
         real GEMMs per contraction, with the same kernels and the same sharding over ranks."""
         from .utils import complex_from_real_samples
+        if self.model == 'CC3':
+            # the CC3 triples terms are of degree 5 in (F, t1, t2) scaled together (t3 ~ Wabei(t1^3) t2, contracted
+            # with Wamef(t1) / Fme): the five-sample quartic interpolation below would be silently wrong (~1e-4)
+            raise NotImplementedError("complex amplitudes with model='CC3' (RT-CC3) are outside the accelerated path")
 
         def real_residual(Fs, t1s, t2s):
             r1, half = self._residuals_half(Fs, t1s, t2s)
@@ -738,7 +745,7 @@ class CCwfn(object):
         t1, t2 = t1.contiguous(), t2.contiguous()
         r1p = torch.empty_like(t1)
         with K.mixed_mode(self.mixed):
-            r1 = self._r1(F, t1, t2, self._intermediates(F, t1, t2), r1p)
+            r1 = self._r1(F, t1, t2, self._intermediates(F, t1, t2, rings=self.model != 'CC2'), r1p)
         if self.part.size > 1:
             self.part.all_reduce_sum(r1p)
         K.strided_axpby(r1, r1p, 1.0, 1.0)
@@ -753,7 +760,10 @@ class CCwfn(object):
         F = self._check_F(F)
         t1, t2 = t1.contiguous(), t2.contiguous()
         with K.mixed_mode(self.mixed):
-            half = self._r2_half(F, t1, t2, self._intermediates(F, t1, t2))
+            if self.model == 'CC2':                     # ccwfn.py:786-787 -> _r_T2_cc2 (832-884)
+                half = self._r2_half_cc2(F, t1, t2, torch.empty_like(t2))
+            else:
+                half = self._r2_half(F, t1, t2, self._intermediates(F, t1, t2))
         if self.part.size > 1:
             self.part.all_reduce_sum(half)
         return K.symmetrize_r2(half)

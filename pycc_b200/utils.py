@@ -116,11 +116,13 @@ class helper_diis(object):
         self._ids.append(self._next_id)
         self._next_id += 1
         self.old = self._clone(val)
-        # new row of B in one pass over the newest error vector
-        dots = K.multi_dot(err, self.errors[-16:]).tolist()
+        # new row of B: one pass over the newest error vector per 16 stored ones (the kernel's limit; the history can
+        # be longer -- max_diis > 16, or start_diis > max_diis, which the reference accepts, utils.py:317-320)
         new = self._ids[-1]
-        for eid, d in zip(self._ids[-16:], dots):
-            self._dots[(eid, new)] = self._dots[(new, eid)] = d
+        for c0 in range(0, len(self.errors), 16):
+            dots = K.multi_dot(err, self.errors[c0:c0 + 16]).tolist()
+            for eid, d in zip(self._ids[c0:c0 + 16], dots):
+                self._dots[(eid, new)] = self._dots[(new, eid)] = d
 
     def extrapolate(self, t1, t2):
         """Pulay extrapolation (utils.py:297-361); returns (t1, t2) unchanged when max_diis == 0."""
@@ -146,7 +148,11 @@ class helper_diis(object):
             c = np.linalg.lstsq(B, rhs, rcond=None)[0]
         self.last_coefficients = c[:m].copy()
         new = torch.empty_like(self.old)
-        K.multi_axpy(c[:m], self.vals[1:m + 1], new)
+        K.multi_axpy(c[:min(m, 16)], self.vals[1:min(m, 16) + 1], new)
+        for c0 in range(16, m, 16):                      # more than 16 vectors: further chunks are added on
+            part = torch.empty_like(new)
+            K.multi_axpy(c[c0:min(m, c0 + 16)], self.vals[1 + c0:min(m, c0 + 16) + 1], part)
+            K.axpbyz(1.0, new, 1.0, part, new)
         self.old = self._clone(new)
         return self._split(new)
 

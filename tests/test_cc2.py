@@ -69,6 +69,9 @@ def test_cc2_residuals_and_solve(cc2, dev):
     r1, r2 = cc.residuals(H.F, t1, t2)
     assert np.abs(r1.cpu().numpy() - g["r1"]).max() < 1e-12
     assert np.abs(r2.cpu().numpy() - g["r2"]).max() < 1e-12
+    # the public r_T1 / r_T2 dispatch on the model like the reference's (ccwfn.py:786-787 -> _r_T2_cc2)
+    assert np.abs(cc.r_T2(o, v, H.F, H.ERI, t1, t2).cpu().numpy() - g["r2"]).max() < 1e-12
+    assert np.abs(cc.r_T1(o, v, H.F, H.ERI, H.L, t1, t2).cpu().numpy() - g["r1"]).max() < 1e-12
     e = cc.solve_cc(1e-12, 1e-12)
     ref = g["trace_ecc_rms"]
     tr = np.array(cc.trace)

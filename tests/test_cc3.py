@@ -123,6 +123,19 @@ def test_cc3_odd_sizes(dev):
         assert np.abs(Y2.cpu().numpy() - X2).max() < 1e-12, (no, nv)
 
 
+def test_cc3_complex_and_real_time_refused(dev):
+    """The five-sample complex evaluation is exact for quartic residuals only; the CC3 triples terms are of degree 5, so
+    complex CC3 amplitudes (and real_time=True, whose explicit-field triples are not built) must raise, not return a
+    silently wrong residual."""
+    syn = make_synthetic(3, 5, seed=3, fock_noise=0.01)
+    cc = pycc_b200.ccwfn(syn, model="CC3", device="GPU", quiet=True)
+    t1, t2 = cc.t1.clone(), cc.t2.clone()
+    with pytest.raises(NotImplementedError):
+        cc.residuals(cc.H.F, t1.to(torch.complex128), t2.to(torch.complex128))
+    with pytest.raises(NotImplementedError):
+        cc.residuals(cc.H.F, t1, t2, real_time=True)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("no,nv,seed", [(6, 26, 0), (7, 33, 1)])
 def test_medium_size_cc3_vs_oracle(no, nv, seed):

@@ -122,6 +122,29 @@ def test_diis_matches_reference(golden, dev):
     assert np.array_equal(a.cpu().numpy(), d1[1]) and np.array_equal(b.cpu().numpy(), d2[1])
 
 
+def test_diis_history_longer_than_16(dev):
+    """max_diis > 16, and start_diis > max_diis (the history then holds more vectors than max_diis: the reference trims
+    one per extrapolate call, utils.py:317-320) -- both beyond the 16-vector limit of the multi_dot / multi_axpy kernels."""
+    rng = np.random.default_rng(5)
+    no, nv = 2, 3
+    for max_diis, quiet_steps, steps in ((20, 0, 24), (8, 19, 24)):
+        x1, x2 = rng.standard_normal((no, nv)), rng.standard_normal((no, no, nv, nv))
+        ours = pycc_b200.helper_diis(T(x1), T(x2), max_diis)
+        from oracle import ccsd_oracle as co
+        ref = co.Diis(x1, x2, max_diis)
+        for n in range(steps):
+            x1 = x1 + 0.5 ** n * rng.standard_normal((no, nv))
+            x2 = x2 + 0.5 ** n * rng.standard_normal((no, no, nv, nv))
+            ours.add_error_vector(T(x1), T(x2))
+            ref.add_error_vector(x1, x2)
+            if n >= quiet_steps:
+                y1, y2 = ours.extrapolate(T(x1), T(x2))
+                r1, r2 = ref.extrapolate(x1, x2)
+                assert np.abs(y1.cpu().numpy() - r1).max() < 1e-8 and np.abs(y2.cpu().numpy() - r2).max() < 1e-8
+                x1, x2 = r1, r2
+        assert ours.diis_size > 16
+
+
 def test_triples(golden, dev):
     g, syn = golden
     cc = make_wfn(syn, "CCSD(T)")
