@@ -54,6 +54,13 @@ def ccsd_flops(o, v, factorised=True):
     return 2 * o**2 * v**4 + n33 * 2 * o**3 * v**3 + 2 * 2 * o**4 * v**2 + 8 * 2 * o**2 * v**3
 
 
+def ccsd_flops_executed(o, v):
+    """Flop one iteration of THIS package executes (solve_cc path): the ladder in pair form on rows (i >= j) --
+    2 x 2 x o(o+1)/2 x (v(v+1)/2)^2 -- plus seven o^3v^3 terms, two o^4v^2 and eight o^2v^3."""
+    nq, m = v * (v + 1) // 2, o * (o + 1) // 2
+    return 2 * 2 * m * nq * nq + 7 * 2 * o**3 * v**3 + 2 * 2 * o**4 * v**2 + 8 * 2 * o**2 * v**3
+
+
 def t_flops_per_triple(o, v):
     return 12 * v**4 + 12 * o * v**3
 
@@ -215,6 +222,40 @@ def workload_config(o, v, parallelism):
 
 
 # ------------------------------------------------------------------------------------------------
+def cuda_time(fn, reps=1, sync=None):
+    """Seconds per call of fn(), CUDA events on the current stream, synchronised on both sides."""
+    import torch
+    (sync or torch.cuda.synchronize)()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        out = fn()
+    b.record()
+    (sync or torch.cuda.synchronize)()
+    return a.elapsed_time(b) * 1e-3 / reps, out
+
+
+def library_peak(dev, dtype, allow_tf32=False):
+    """cuBLAS GEMM 8192^3, best of 5: the denominator of the tensor rooflines (not on the product path)."""
+    import torch
+    torch.backends.cuda.matmul.allow_tf32 = bool(allow_tf32)
+    try:
+        A = torch.randn(8192, 8192, dtype=dtype, device=dev)
+        C = torch.empty_like(A)
+        for _ in range(2):
+            torch.matmul(A, A, out=C)
+        best = 0.0
+        for _ in range(5):
+            t, _ = cuda_time(lambda: torch.matmul(A, A, out=C))
+            best = max(best, 2.0 * 8192**3 / t / 1e12)
+        return best
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = False
+
+
+PARITY_RECORD = os.path.join(ROOT, "profiles", "parity_r02.json")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -226,13 +267,15 @@ def main():
     ap.add_argument("--cpu-o", type=int, default=20, help="size of the real reference iterations (configs[1])")
     ap.add_argument("--cpu-v", type=int, default=150)
     ap.add_argument("--verbose", action="store_true")
-    ap.add_argument("--t-triples", type=int, default=48, help="(T) sample: triples timed per rank-set")
+    ap.add_argument("--t-triples", type=int, default=0, help="(T): time only this many triples per rank (0 = the full job)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-mp", action="store_true", help="skip the mixed-precision (precision='MP') leg")
+    ap.add_argument("--no-c4", action="store_true", help="skip BASELINE configs[3]: the full (T) at o=30, v=280")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
+    import gc
     import torch
     import torch.distributed as dist
     import pycc_b200
@@ -259,17 +302,27 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         comm = Comm()
     o, v = args.o, args.v
+    nwarm = max(3, args.warmup)
 
     def sync():
         if comm is not None:
             comm.barrier()
         torch.cuda.synchronize()
 
+    def rmax(x):
+        return comm.all_reduce_max_scalar(x) if comm is not None else x
+
+    def release():
+        cctriples._QCACHE.clear()
+        gc.collect()                                # the Hamiltonian <-> its ERI/L views form reference cycles
+        torch.cuda.empty_cache()
+
     # ---- problem: synthetic factor on the host (seeded), integral blocks contracted on the device
     t_setup = time.time()
     syn = make_synthetic(o, v, seed=0, device=dev)
     cc = pycc_b200.ccwfn(syn, model="CCSD(T)", device="GPU", quiet=True, comm=comm)
     diis = pycc_b200.helper_diis(cc.t1, cc.t2, 8)
+    e_mp2 = float(cc.cc_energy(cc.o, cc.v, cc.H.F, cc.H.L, cc.t1, cc.t2))
     sync()
     t_setup = time.time() - t_setup
 
@@ -281,10 +334,10 @@ def main():
         energies.append(ecc)
         return ecc, rms
 
-    for _ in range(max(3, args.warmup)):
+    for _ in range(nwarm):
         step()
     # ---- timed region: exactly K steps; inputs (integral blocks, amplitudes) resident in HBM.
-    # The working set of one step (>= 75 GB of integrals streamed) is far larger than the 126 MB L2.
+    # The working set of one step (> 40 GB of integrals streamed) is far larger than the 126 MB L2.
     sampler = ClockSampler(local)
     sync()
     sampler.start()
@@ -297,82 +350,85 @@ def main():
     sync()
     clocks = sampler.stop()
     launches = K.launch_count() - l0
-    sec = ev0.elapsed_time(ev1) * 1e-3
-    if comm is not None:
-        sec = comm.all_reduce_max_scalar(sec)
-    s_iter = sec / args.steps
+    s_iter = rmax(ev0.elapsed_time(ev1) * 1e-3) / args.steps
 
-    # ---- roofline of the dominant kernel, timed live: the ladder GEMM (this rank's a-slice)
+    # ---- parity at the FULL size, in this very run: the first iterations against the energies the unmodified
+    # reference printed when it was run once at this size on this pool's host (profiles/reference_fullsize_r02.json)
+    parity = {"e_mp2": e_mp2, "ecc_iter1": energies[0], "ecc_iter2": energies[1]}
+    try:
+        rec = json.load(open(FULLSIZE_RECORD))
+        if (rec["o"], rec["v"]) == (o, v):
+            want = rec["energies_full"]
+            devs = [abs(e_mp2 - want[0])] + [abs(a - b) for a, b in zip(energies, want[1:])]
+            parity.update({"reference_energies": want, "max_abs_dE_vs_reference": max(devs), "tolerance": 1e-10,
+                           "ok": bool(max(devs) < 1e-10),
+                           "what": "MP2 + first %d CCSD iteration energies of the unmodified reference at this size" % (len(want) - 1)})
+            if not parity["ok"]:
+                raise SystemExit("PARITY FAILURE vs the reference at o=%d,v=%d: %r" % (o, v, parity))
+    except (OSError, KeyError, ValueError):
+        pass
+
+    # ---- roofline of the dominant kernel, timed live: the ladder GEMM (this rank's share of the pair rows)
     tau = K.build_tau(cc.t1, cc.t2)
     r2 = torch.zeros_like(cc.t2)
+    cc._ladder(tau, r2, symmetric=True)
+    t_lad, _ = cuda_time(lambda: cc._ladder(tau, r2, symmetric=True), 3)
+    lad_exec = cc.ladder_flops
     a_lo, a_hi = cc.part.a_range(v)
-    lad_flops = 2.0 * o * o * (a_hi - a_lo) * v * v * v
-    cc._ladder(tau, r2)
-    torch.cuda.synchronize()
-    la, lb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    nl = 3
-    la.record()
-    for _ in range(nl):
-        cc._ladder(tau, r2)
-    lb.record()
-    torch.cuda.synchronize()
-    t_lad = la.elapsed_time(lb) * 1e-3 / nl
-    del tau, r2
-    peak = FP64_PEAK_FALLBACK
-    peak_src = "cuBLAS DGEMM 8192^3 measured on this pool (profiles/probe_r01_first.json); MEASURED_PEAKS.json has no FP64 entry"
-    try:   # live re-measurement of the denominator on this very GPU (library GEMM, not on the product path)
-        A = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
-        C = torch.empty_like(A)
-        for _ in range(2):
-            torch.matmul(A, A, out=C)
-        torch.cuda.synchronize()
-        best = 0.0
-        for _ in range(5):
-            pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            pa.record()
-            torch.matmul(A, A, out=C)
-            pb.record()
-            torch.cuda.synchronize()
-            best = max(best, 2.0 * 8192**3 / (pa.elapsed_time(pb) * 1e-3) / 1e12)
-        peak = best
+    npl, nq = K.pair_count(a_hi) - K.pair_count(a_lo), K.pair_count(v)
+    M_tri = K.pair_count(o)
+    # the GEMM alone (same operands, same launch as inside _ladder)
+    T = K.pack_tau(tau, True)
+    V, ldv = cc.H.packed()
+    lds = (npl + 1) // 2 * 2
+    SA = torch.empty((2, M_tri, lds), dtype=torch.float64, device=dev)
+    row0 = K.pair_count(a_lo) - K.pair_count(cc.H.a_range[0])
+
+    def ladder_gemm():
+        K.dgemm(M_tri, npl, nq, T, T.shape[2], 0, (V, row0 * ldv), ldv, 0, SA, lds, 1.0, 0.0, batch=2,
+                sA=M_tri * T.shape[2], sB=cc.H.npairs_local * ldv, sC=M_tri * lds)
+    ladder_gemm()
+    t_gemm, _ = cuda_time(ladder_gemm, 3)
+    del tau, r2, T, SA
+    try:
+        peak = library_peak(dev, torch.float64)
         peak_src = "cuBLAS DGEMM 8192^3, best of 5, measured live in this run (MEASURED_PEAKS.json has no FP64 entry)"
-        del A, C
     except Exception:
-        pass
-    # DRAM bytes of the ladder launch from the committed ncu --set full capture (profiles/), if it is this shape
+        peak, peak_src = FP64_PEAK_FALLBACK, "cuBLAS DGEMM 8192^3 measured on this pool (profiles/probe_r01_first.json)"
     traffic = None
     try:
         rec = json.load(open(os.path.join(ROOT, "profiles", "ladder_traffic.json")))
-        key = "o%dv%d_n%d" % (o, v, world)
+        key = "r02_o%dv%d_n%d" % (o, v, world)
         if key in rec:
             traffic = rec[key]["dram_bytes"]
     except Exception:
         pass
-    roofline = {"bound": "tensor", "kernel": "dgemm_kernel (ladder, ccwfn.py:931)", "achieved": lad_flops / t_lad / 1e12,
-                "peak": peak, "unit": "TFLOP/s", "frac": lad_flops / t_lad / 1e12 / peak, "traffic": traffic,
-                "algorithmic_bytes": 8.0 * ((a_hi - a_lo) * v ** 3 + 2 * o * o * v * v),
-                "peak_source": peak_src, "launch_ms": t_lad * 1e3,
-                "share_of_step": t_lad / s_iter,
-                "whole_step_tflops_per_gpu": ccsd_flops(o, v) / world / s_iter / 1e12}
+    lad_dense = 2.0 * o * o * v * v * (2.0 * npl)          # 2 o^2 v^2 x (this rank's share of the v^2 (a,b) columns)
+    roofline = {"bound": "tensor", "kernel": "dgemm_tma_kernel: the ladder as S = T+ V+^T, A = T- V-^T (ccwfn.py:931 in pair form)",
+                "achieved": lad_exec / t_gemm / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": lad_exec / t_gemm / 1e12 / peak,
+                "traffic": traffic, "algorithmic_bytes": 8.0 * 2 * (npl * nq + 2 * M_tri * nq),
+                "executed_flop": lad_exec, "dense_equivalent_flop": lad_dense,
+                "dense_equivalent_tflops": lad_dense / t_lad / 1e12,
+                "peak_source": peak_src, "launch_ms": t_gemm * 1e3, "ladder_ms_with_pack_unpack": t_lad * 1e3,
+                "share_of_step": t_gemm / s_iter,
+                "whole_step_tflops_per_gpu": ccsd_flops_executed(o, v) / world / s_iter / 1e12,
+                "note": "achieved counts EXECUTED flop (pair-packed: 1/4 of the dense 2 o^2 v^4); dense_equivalent_* "
+                        "is the reference's flop count for the same term over the time of the whole ladder"}
 
-    # ---- (T): FP64 TFLOP/s on a bounded sample of (i>=j>=k) triples, sharded round-robin over the ranks
-    trip = [t for t in cctriples.triples_list(o) if not (t[0] == t[1] == t[2])]
-    nt = min(len(trip), args.t_triples * world)
-    sample_trip = trip[:: max(1, len(trip) // nt)][:nt]
-    cctriples.t_tjl(cc, sample_trip)                       # warm-up (allocates the Q workspace once)
-    sync()
-    ta, tb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ta.record()
-    et = cctriples.t_tjl(cc, sample_trip)
-    tb.record()
-    sync()
-    t_t = ta.elapsed_time(tb) * 1e-3
-    if comm is not None:
-        t_t = comm.all_reduce_max_scalar(t_t)
-    t_rate = t_flops_per_triple(o, v) * len(sample_trip) / t_t / 1e12
-    t_info = {"tflops": t_rate, "unit": "TFLOP/s (FP64, whole job)", "triples_timed": len(sample_trip),
-              "triples_total": len(trip), "seconds": t_t, "full_t_seconds_est": t_t * len(trip) / len(sample_trip),
-              "frac_of_fp64_peak_per_gpu": t_rate / world / peak, "e_t_sample": float(et)}
+    # ---- (T): the FULL job at this size, all (i>=j>=k) triples dealt round-robin to the ranks
+    def t_job(wfn, nsample):
+        trip = [t for t in cctriples.triples_list(wfn.no) if not (t[0] == t[1] == t[2])]
+        run = trip if not nsample else trip[:: max(1, len(trip) // (nsample * world))][:nsample * world]
+        cctriples.t_tjl(wfn, run[:2 * world])                      # warm-up (allocates the Q workspace once)
+        t_t, et = cuda_time(lambda: cctriples.t_tjl(wfn, run), 1, sync)
+        t_t = rmax(t_t)
+        rate = t_flops_per_triple(wfn.no, wfn.nv) * len(run) / t_t / 1e12
+        return {"o": wfn.no, "v": wfn.nv, "tflops": rate, "unit": "TFLOP/s (FP64, whole job over all GPUs)",
+                "triples_timed": len(run), "triples_total": len(trip), "seconds": t_t,
+                "frac_of_fp64_peak_per_gpu": rate / world / peak, "e_t": float(et)}, run
+
+    t_info, t_run = t_job(cc, args.t_triples)
+    t_info["amplitudes"] = "after %d CCSD iterations" % len(energies)
 
     # ---- e2e: the same step through the public API with HOST amplitudes: every step uploads t1, t2 (and F)
     # from pinned host memory, runs the iteration, and reads (ecc, rms) back
@@ -381,35 +437,66 @@ def main():
     h_F = cc.H.F.cpu().pin_memory()
     d_F = torch.empty_like(cc.H.F)
     e2e_steps = max(2, min(args.steps, 3))
-    sync()
-    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ea.record()
-    for _ in range(e2e_steps):
+
+    def e2e_step():
         cc.t1.copy_(h_t1, non_blocking=True)
         cc.t2.copy_(h_t2, non_blocking=True)
         d_F.copy_(h_F, non_blocking=True)
-        ecc2, rms2 = cc.iterate(d_F)                     # returns host floats (D2H of 2 doubles)
+        out = cc.iterate(d_F)                              # returns host floats (D2H of 2 doubles)
         cc.diis_step(diis, True)
-    eb.record()
-    sync()
-    t_e2e = ea.elapsed_time(eb) * 1e-3 / e2e_steps
-    if comm is not None:
-        t_e2e = comm.all_reduce_max_scalar(t_e2e)
+        return out
+    t_e2e, _ = cuda_time(e2e_step, e2e_steps, sync)
+    t_e2e = rmax(t_e2e)
     e2e = {"value": t_e2e, "unit": "s/iter", "h2d_bytes_per_step": int((h_t1.numel() + h_t2.numel() + h_F.numel()) * 8),
            "d2h_bytes_per_step": 16}
+    n_dp = len(energies)
+    del cc, diis, h_t1, h_t2, h_F, d_F, V
+    release()
+
+    # ---- BASELINE configs[3]: RHF-CCSD(T) o=30 v=280, the full (T) job sharded over (i,j,k) on all ranks; the
+    # amplitudes are those after exactly three CCSD iterations (the (T) cost does not depend on convergence), so E(T)
+    # is a fixed number that every N must reproduce
+    c4 = None
+    if not args.no_c4:
+        syn4 = make_synthetic(30, 280, seed=0, device=dev)
+        cc4 = pycc_b200.ccwfn(syn4, model="CCSD(T)", device="GPU", quiet=True, comm=comm)
+        d4 = pycc_b200.helper_diis(cc4.t1, cc4.t2, 8)
+        for _ in range(3):
+            e4, _ = cc4.iterate()
+            cc4.diis_step(d4, True)
+        del d4
+        c4, _ = t_job(cc4, args.t_triples)
+        c4["ecc_after_3_iterations"] = e4
+        del cc4, syn4
+        release()
+
+    # ---- driver-visible multi-GPU parity: energies that every N must reproduce, recorded at N = 1
+    # (profiles/parity_r02.json, written by `bench.py --record-parity` runs at N=1; compared here at any N)
+    checks = {}
+    try:
+        rec = json.load(open(PARITY_RECORD))
+        key = "o%dv%d" % (o, v)
+        if key in rec:
+            for k_it, e_ref in rec[key].get("ecc_by_iteration", {}).items():
+                if int(k_it) <= len(energies):
+                    checks["ecc_iter%s" % k_it] = abs(energies[int(k_it) - 1] - e_ref)
+            e_t_ref = rec[key].get("e_t_by_iteration", {}).get(str(n_dp))
+            if e_t_ref is not None and t_info["triples_timed"] == t_info["triples_total"]:
+                checks["e_t_full_o%dv%d" % (o, v)] = abs(t_info["e_t"] - e_t_ref)
+        if c4 is not None and "o30v280" in rec and c4["triples_timed"] == c4["triples_total"]:
+            checks["c4_ecc_after_3_iterations"] = abs(c4["ecc_after_3_iterations"] - rec["o30v280"]["ecc_after_3_iterations"])
+            checks["c4_e_t_full"] = abs(c4["e_t"] - rec["o30v280"]["e_t"])
+    except (OSError, ValueError, KeyError):
+        pass
+    parity["vs_n1_record"] = {"max_abs_dE": max(checks.values()) if checks else None, "checks": checks, "tolerance": 1e-10}
+    if checks and max(checks.values()) >= 1e-10:
+        raise SystemExit("PARITY FAILURE vs the N=1 record (profiles/parity_r02.json): %r" % checks)
 
     # ---- BASELINE configs[4]: the same iterations with precision='MP' (split-TF32 contractions on tcgen05, FP64
     # accumulation) from the same starting guess: s/iter, |E_MP - E_FP64| after each iteration, and the ladder GEMM
-    # against the TF32 tensor peak (cuBLAS TF32 SGEMM 8192^3 measured live).  The FP64 objects are released first
-    # (<ab|ef> FP64 + its TF32 planes do not fit together at v=300).
+    # against the TF32 tensor peak (cuBLAS TF32 SGEMM 8192^3 measured live).
     mp = None
     if not args.no_mp:
-        n_dp = len(energies)
-        del cc, diis, h_t1, h_t2, h_F, d_F
-        cctriples._QCACHE.clear()
-        import gc
-        gc.collect()                                # the Hamiltonian <-> its ERI/L views form reference cycles
-        torch.cuda.empty_cache()
         ccm = pycc_b200.ccwfn(syn, model="CCSD(T)", device="GPU", precision="MP", quiet=True, comm=comm)
         diism = pycc_b200.helper_diis(ccm.t1, ccm.t2, 8)
         e_mp = []
@@ -419,94 +506,55 @@ def main():
             ccm.diis_step(diism, True)
             e_mp.append(e)
 
-        for _ in range(max(3, args.warmup)):
+        for _ in range(nwarm):
             mstep()
-        sync()
         l0 = K.launch_count()
-        ma, mb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ma.record()
-        for _ in range(args.steps):
-            mstep()
-        mb.record()
-        sync()
+        t_mp, _ = cuda_time(mstep, args.steps, sync)
+        t_mp = rmax(t_mp)
         mp_launches = K.launch_count() - l0
-        t_mp = ma.elapsed_time(mb) * 1e-3 / args.steps
-        if comm is not None:
-            t_mp = comm.all_reduce_max_scalar(t_mp)
         nmp = min(n_dp, len(e_mp))
         de = max(abs(a - b) for a, b in zip(energies[:nmp], e_mp[:nmp]))
         tau = K.build_tau(ccm.t1, ccm.t2)
         r2 = torch.zeros_like(ccm.t2)
         with K.mixed_mode(True):
-            ccm._ladder(tau, r2)
-            torch.cuda.synchronize()
-            la, lb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            la.record()
-            for _ in range(3):
-                ccm._ladder(tau, r2)
-            lb.record()
-            torch.cuda.synchronize()
-        t_lad_mp = la.elapsed_time(lb) * 1e-3 / 3
+            ccm._ladder(tau, r2, symmetric=True)
+            t_lad_mp, _ = cuda_time(lambda: ccm._ladder(tau, r2, symmetric=True), 3)
+        mp_exec = ccm.ladder_flops
         del tau, r2
-        # (T) in MP mode: the same sample of triples, t3 build on the split-TF32 kernel (two K segments per GEMM)
-        cctriples.t_tjl(ccm, sample_trip)
-        sync()
-        tma_, tmb_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        tma_.record()
-        et_mp = cctriples.t_tjl(ccm, sample_trip)
-        tmb_.record()
-        sync()
-        t_t_mp = tma_.elapsed_time(tmb_) * 1e-3
-        if comm is not None:
-            t_t_mp = comm.all_reduce_max_scalar(t_t_mp)
-        tf32_peak, tf32_src = 1130.0, "nominal dense TF32 (no measured entry in MEASURED_PEAKS.json)"
+        # (T) in MP mode: a bounded sample of the triples, t3 build on the split-TF32 kernel (two K segments per GEMM)
+        mt, _ = t_job(ccm, args.t_triples or 48)
         try:
-            torch.backends.cuda.matmul.allow_tf32 = True
-            A = torch.randn(8192, 8192, dtype=torch.float32, device=dev)
-            C = torch.empty_like(A)
-            for _ in range(2):
-                torch.matmul(A, A, out=C)
-            torch.cuda.synchronize()
-            best = 0.0
-            for _ in range(5):
-                pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                pa.record()
-                torch.matmul(A, A, out=C)
-                pb.record()
-                torch.cuda.synchronize()
-                best = max(best, 2.0 * 8192**3 / (pa.elapsed_time(pb) * 1e-3) / 1e12)
-            tf32_peak, tf32_src = best, "cuBLAS TF32 SGEMM 8192^3, best of 5, measured live in this run"
-            torch.backends.cuda.matmul.allow_tf32 = False
-            del A, C
+            tf32_peak, tf32_src = library_peak(dev, torch.float32, True), "cuBLAS TF32 SGEMM 8192^3, best of 5, measured live in this run"
         except Exception:
-            pass
+            tf32_peak, tf32_src = 1130.0, "nominal dense TF32 (no measured entry in MEASURED_PEAKS.json)"
         mp = {"value": t_mp, "unit": "s/iter", "speedup_vs_fp64": s_iter / t_mp, "dtype": "tf32x3 products, f64 accumulate",
               "max_abs_dE_vs_fp64_same_iteration": de, "iterations_compared": nmp, "ecc_last": e_mp[-1],
               "gpu_launches": int(mp_launches), "stats": dict(K.MIXED.stats),
-              "t": {"tflops_fp64_equivalent": t_flops_per_triple(o, v) * len(sample_trip) / t_t_mp / 1e12,
-                    "seconds": t_t_mp, "speedup_vs_fp64": t_t / t_t_mp, "triples_timed": len(sample_trip),
-                    "full_t_seconds_est": t_t_mp * len(trip) / len(sample_trip),
-                    "e_t_sample": float(et_mp), "abs_dE_vs_fp64": abs(float(et_mp) - float(et))},
-              "roofline": {"bound": "tensor", "kernel": "tf32x3_gemm_r_kernel (ladder, ccwfn.py:931)",
-                           "achieved": 3.0 * lad_flops / t_lad_mp / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
-                           "frac": 3.0 * lad_flops / t_lad_mp / 1e12 / tf32_peak, "peak_source": tf32_src,
-                           "fp64_equivalent_tflops": lad_flops / t_lad_mp / 1e12, "launch_ms": t_lad_mp * 1e3,
-                           "note": "achieved counts the three TF32 products actually executed per FP64-equivalent flop"}}
+              "t": {"tflops_fp64_equivalent": mt["tflops"], "seconds": mt["seconds"], "triples_timed": mt["triples_timed"],
+                    "triples_total": mt["triples_total"], "e_t_sample": mt["e_t"]},
+              "roofline": {"bound": "tensor", "kernel": "tf32x3_gemm_r_kernel (ladder in pair form, ccwfn.py:931)",
+                           "achieved": 3.0 * mp_exec / t_lad_mp / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                           "frac": 3.0 * mp_exec / t_lad_mp / 1e12 / tf32_peak, "peak_source": tf32_src,
+                           "fp64_equivalent_tflops": mp_exec / t_lad_mp / 1e12,
+                           "dense_equivalent_tflops": lad_dense / t_lad_mp / 1e12, "launch_ms": t_lad_mp * 1e3,
+                           "note": "achieved counts the three TF32 products actually executed per FP64-equivalent flop; "
+                                   "launch_ms includes the pack / split / unpack passes around the GEMM"}}
         del ccm, diism
+        release()
 
     if rank == 0:
         cpu = None
         if not args.no_cpu and world == 1:          # reported at N=1 only (rank 0)
             cpu = cpu_leg(args, 1, 2)               # ~3 real reference iterations at configs[1]: 10-30 s of CPU work
+        cfg = workload_config(o, v, "pair-packed ladder a-sharded by pair count + occupied-sliced ring terms, 1 all-reduce/iter"
+                              if world > 1 else "single GPU")
+        cfg.update({"diis": 8, "setup_s": t_setup})
         line = {"metric": METRIC, "value": s_iter, "unit": "s/iter", "n_gpus": world, "steps": args.steps,
-                "warmup": max(3, args.warmup), "ms_per_step": s_iter * 1e3, "higher_is_better": False,
+                "warmup": nwarm, "ms_per_step": s_iter * 1e3, "higher_is_better": False,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "RHF-CCSD iteration o=%d v=%d FP64 (synthetic integrals, seed 0); inputs >> L2 "
-                                       "(75 GB of integrals streamed per step)" % (o, v),
-                           "parallelism": "a-sharded ladder + occupied-sliced ring terms, 1 all-reduce/iter" if world > 1 else "single GPU",
-                           "diis": 8, "setup_s": t_setup},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "t": t_info, "mp": mp, "clocks": clocks,
-                "gpu_launches": int(launches), "ecc_last": ecc, "rms_last": rms}
+                "config": cfg, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "t": t_info, "t_c4": c4, "mp": mp,
+                "parity": parity, "clocks": clocks, "gpu_launches": int(launches), "ecc_last": ecc, "rms_last": rms,
+                "energies": energies}
         print(json.dumps(line), flush=True)
     if comm is not None:
         dist.destroy_process_group()

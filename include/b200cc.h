@@ -24,7 +24,7 @@ extern "C" {
 
 typedef long long b200cc_i64;
 
-int b200cc_version(void);
+int b200cc_version(void);          /* 200 = this header (round 2: struct_size fields, pair-packed ladder entries) */
 const char* b200cc_last_error(void);
 /* number of kernels launched by this library in this process (for bench.py's gpu_launches) */
 b200cc_i64 b200cc_launch_count(void);
@@ -46,6 +46,8 @@ int b200cc_device_info(int* sm_count, int* cc_major, int* cc_minor, b200cc_i64* 
  * ksplit > 1 splits the K loop over gridDim.z and reduces through `workspace`
  * (>= ksplit*batch*M*N doubles); deterministic (no atomics).                                    */
 typedef struct {
+  int struct_size;                 /* = sizeof(b200cc_gemm_desc): a binding built against another layout of this struct
+                                      is refused with an error instead of being mis-read */
   int M, N;
   int transA, transB;
   int K1, K2;                      /* K2 = 0: single segment */
@@ -88,6 +90,7 @@ int b200cc_dgemm(const b200cc_gemm_desc* d, void* stream);
  * b200cc_gemm_tf32x3: planes are K-major: A element (m,k) at Ahi[b*strideA + m*lda + k] (floats; lda, ldb,
  * strideA, strideB multiples of 4; stride 0 = one operand shared by the whole batch); C row-major FP64.        */
 typedef struct {
+  int struct_size;                 /* = sizeof(b200cc_gemm3_desc), checked like b200cc_gemm_desc.struct_size */
   int M, N, K;
   const float *Ahi, *Alo, *Bhi, *Blo;
   b200cc_i64 lda, ldb, strideA, strideB;
@@ -123,6 +126,36 @@ int b200cc_gemm_tf32x3(const b200cc_gemm3_desc* d, void* stream);
  * the result carries the 2^-22 relative accuracy of the planes, i.e. that of the mode.                          */
 int b200cc_merge_tf32(const float* hi, const float* lo, b200cc_i64 ldp, b200cc_i64 rows, int K, double* dst,
                       b200cc_i64 ld, void* stream);
+
+/* ---- the particle-particle ladder in symmetric / antisymmetric pair form ------------------------------------
+ * Replaces 'ijef,abef->ijab' (ccwfn.py:931; the Lambda ladder cclambda.py:468 likewise) as written -- a GEMM with
+ * N = K = v^2 over the v^4 block <ab|ef> -- by the split the reference itself uses for W_abei (ccwfn.py:1054-1120).
+ * With pair(x,y) = x(x+1)/2 + y, P = pair(a,b) (a >= b), Q = pair(e,f) (e >= f), nq = v(v+1)/2:
+ *   V+[P,Q] = <ab|ef> + <ab|fe> (e > f), <ab|ee> (e = f);      V-[P,Q] = <ab|ef> - <ab|fe>   (zero for a = b, e = f)
+ *   T+[m,Q] = (tau[m,e,f] + tau[m,f,e]) / 2 (tau[m,e,e]);      T-[m,Q] = (tau[m,e,f] - tau[m,f,e]) / 2
+ *   S = T+ V+^T,  A = T- V-^T  (b200cc_dgemm / b200cc_gemm_tf32x3, batch of 2, N = K = nq),
+ *   sum_ef tau[m,e,f] <ab|ef> = S[m,P] + A[m,P],   sum_ef tau[m,e,f] <ba|ef> = S[m,P] - A[m,P].
+ * `tri` != 0: tau has the pair symmetry tau[i,j,e,f] = tau[j,i,f,e] (the amplitudes solve_cc iterates), rows are
+ * m = pair(i,j), i >= j only, and the (j,i) results follow from (i,j): o^2 v^4 / 2 executed flop instead of 2 o^2 v^4.
+ * `tri` == 0: m = i*no + j over all (i,j), any tau (o^2 v^4 executed flop).
+ * All matrices are row-major with pitch ldq (>= nq; the columns nq..ldq of packed rows are written as zeros).
+ *
+ * b200cc_pack_pairs: rows of <ab|ef> for a in [a0,a1) -> V+ / V- rows pair(a,b) - pair(a0,0), b <= a.  The source is
+ *   addressed by element strides, slab(a,b)[e,f] = src[(a-a0)*sa + b*sb + e*se + f*sf] (so the output of the
+ *   integral-generating GEMM is packed in whatever index order it was produced, no permuted copy).  Once per Hamiltonian.
+ * b200cc_unpack_pairs: the inverse for `npairs` consecutive rows: dst[p][e][f] = <ab|ef> of the p-th given pair (FP64,
+ *   v^2 per pair) -- for the few other consumers of <ab|ef> (t_if<ab|ef> in HBAR / CC2 / CC3, H.ERI[v,v,v,v]).
+ * b200cc_pack_tau: tau (no,no,nv,nv) -> T+ / T- (every iteration; also used for lambda_2 by the Lambda ladder).
+ * b200cc_ladder_unpack: r2[i,j,a,b] += alpha (S+A), r2[i,j,b,a] += alpha (S-A) [and the (j,i) images when tri] for the
+ *   columns pair(a,b) - pair(a0,0), a in [a0,a1) of S / A (pitch lds): each r2 element is updated by exactly one thread. */
+b200cc_i64 b200cc_pair_count(int n);          /* n(n+1)/2 */
+int b200cc_pack_pairs(const double* src, b200cc_i64 sa, b200cc_i64 sb, b200cc_i64 se, b200cc_i64 sf, int nv,
+                      int a0, int a1, double* vp, double* vm, b200cc_i64 ldq, void* stream);
+int b200cc_unpack_pairs(const double* vp, const double* vm, b200cc_i64 ldq, int nv, b200cc_i64 npairs,
+                        double* dst, void* stream);
+int b200cc_pack_tau(const double* tau, int no, int nv, int tri, double* tp, double* tm, b200cc_i64 ldq, void* stream);
+int b200cc_ladder_unpack(const double* S, const double* A, b200cc_i64 lds, int no, int nv, int tri, int a0, int a1,
+                         double alpha, double* r2, void* stream);
 
 /* ---- tensor permutation / strided axpby -------------------------------------------------------
  * out[sum_d i_d*so[d]] = alpha * in[sum_d i_d*si[d]] + beta * out[...]  for i_d < shape[d], rank <= 6.

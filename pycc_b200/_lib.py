@@ -28,6 +28,7 @@ class B200ccError(PyCCError, RuntimeError):
 class GemmDesc(C.Structure):
     """Mirror of ``b200cc_gemm_desc`` (include/b200cc.h)."""
     _fields_ = [
+        ("struct_size", C.c_int),
         ("M", C.c_int), ("N", C.c_int),
         ("transA", C.c_int), ("transB", C.c_int),
         ("K1", C.c_int), ("K2", C.c_int),
@@ -52,6 +53,7 @@ class GemmDesc(C.Structure):
 class Gemm3Desc(C.Structure):
     """Mirror of ``b200cc_gemm3_desc`` (include/b200cc.h)."""
     _fields_ = [
+        ("struct_size", C.c_int),
         ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
         ("Ahi", dptr), ("Alo", dptr), ("Bhi", dptr), ("Blo", dptr),
         ("lda", i64), ("ldb", i64), ("strideA", i64), ("strideB", i64),
@@ -95,6 +97,12 @@ SIGNATURES = {
     "b200cc_split_tf32": (C.c_int, [dptr, i64, i64, C.c_int, C.c_int, C.c_int, dptr, dptr, i64, C.c_void_p]),
     "b200cc_gemm_tf32x3": (C.c_int, [C.POINTER(Gemm3Desc), C.c_void_p]),
     "b200cc_merge_tf32": (C.c_int, [dptr, dptr, i64, i64, C.c_int, dptr, i64, C.c_void_p]),
+    "b200cc_pair_count": (i64, [C.c_int]),
+    "b200cc_pack_pairs": (C.c_int, [dptr, i64, i64, i64, i64, C.c_int, C.c_int, C.c_int, dptr, dptr, i64, C.c_void_p]),
+    "b200cc_unpack_pairs": (C.c_int, [dptr, dptr, i64, C.c_int, i64, dptr, C.c_void_p]),
+    "b200cc_pack_tau": (C.c_int, [dptr, C.c_int, C.c_int, C.c_int, dptr, dptr, i64, C.c_void_p]),
+    "b200cc_ladder_unpack": (C.c_int, [dptr, dptr, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, dptr,
+                                       C.c_void_p]),
     "b200cc_permute": (C.c_int, [C.c_int, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64),
                                  C.c_double, dptr, C.c_double, dptr, C.c_void_p]),
     "b200cc_axpbyz": (C.c_int, [i64, C.c_double, dptr, C.c_double, dptr, dptr, C.c_void_p]),

@@ -184,21 +184,24 @@ class cchbar(object):
         return out
 
     def _vvvv_term_sharded(self, out, alpha, sub, a, b, env):
-        """A term whose integral operand is <ab|ef> when that block is a-sharded over the ranks (parallel.py): each
-        rank contracts its rows a, the pieces are summed with one all-reduce and added to the (replicated) block.
-        Only 't_if <ab|ef> -> abei' (Hvvvo) occurs; both tensors have a as their slowest index."""
+        """A term whose integral operand is <ab|ef> when that block is sharded over the ranks (parallel.py): each rank
+        contracts the pairs (a >= b) it holds -- giving the (a,b) and (b,a) elements -- the pieces are summed with one
+        all-reduce and added to the (replicated) block.  Only 't_if <ab|ef> -> abei' (Hvvvo) occurs."""
         w = self.ccwfn
         if sub != "if,abef->abei" or b != "E:vvvv":
-            raise NotImplementedError("a-sharded <ab|ef> in HBAR term %r" % sub)
-        if w.H.a_range != tuple(w.part.a_range(w.nv)):
-            raise NotImplementedError("<ab|ef> rows resident on this rank differ from its share")
-        a_lo, a_hi = w.H.a_range
+            raise NotImplementedError("sharded <ab|ef> in HBAR term %r" % sub)
+        a_lo, a_hi = w.part.a_range(w.nv)
+        r_lo, r_hi = w.H.a_range
+        if (r_lo, r_hi) != (a_lo, a_hi) and (r_lo, r_hi) != (0, w.nv):
+            raise NotImplementedError("<ab|ef> rows resident on this rank are neither its share nor the whole block")
         piece = torch.zeros_like(out)
-        if a_hi > a_lo and w._vvvv_released():
-            w._t1_vvvv(self._operand(env, a), piece[a_lo:a_hi], alpha)       # rebuilt from the MP planes
-        elif a_hi > a_lo:
-            w._ct(sub, self._operand(env, a), w.H.block("vvvv"), out=piece[a_lo:a_hi], alpha=alpha, beta=0.0)
-        w.part.all_reduce_sum(piece)
+        if (r_lo, r_hi) == (a_lo, a_hi):
+            w._t1_vvvv(self._operand(env, a), piece, alpha)                  # this rank's pairs, from the packed form
+            w.part.all_reduce_sum(piece)
+        elif w.H.has("vvvv"):                                                # every rank holds the whole FP64 block
+            w._ct(sub, self._operand(env, a), w.H.block("vvvv"), out=piece, alpha=alpha, beta=0.0)
+        else:
+            w._t1_vvvv(self._operand(env, a), piece, alpha)                  # whole packed form on every rank
         K.strided_axpby(out, piece, 1.0, 1.0)
 
     def build_all(self, F, t1, t2, with_vvvv=False):

@@ -89,7 +89,7 @@ class cclambda(object):
             K.strided_axpby(out, s1, 1.0, 1.0)
         return self._accumulate(out, _R1, env)
 
-    def _ladder(self, half, l2, Hvvvv=None, t1=None, t2=None):
+    def _ladder(self, half, l2, Hvvvv=None, t1=None, t2=None, symmetric=False):
         """half += 1/2 l2_ijef H_efab (cclambda.py:468) WITHOUT the v^4 tensor H_efab:
              1/2 l2_ijef <ef|ab>                      the ladder GEMM of the CCSD residual on <ab|ef> in place
            - 1/2 (l2_ijef t_mf) <em|ab> - 1/2 (l2_ijef t_me) <fm|ba>                     two o^3v^3 products
@@ -106,11 +106,11 @@ class cclambda(object):
                 # <ab|ef> is a-sharded: every rank adds the rows it holds, one all-reduce (o^2v^2) sums the pieces;
                 # all other terms are replicated, so l1 / l2 stay identical on all ranks
                 piece = torch.zeros_like(half)
-                w._ladder(l2, piece)
+                w._ladder(l2, piece, symmetric=symmetric)
                 w.part.all_reduce_sum(piece)
                 K.strided_axpby(half, piece, 1.0, 1.0)
             else:
-                w._ladder(l2, half)
+                w._ladder(l2, half, symmetric=symmetric)
             o, v = w.o, w.v
             oovv = w.H.ERI[o, o, v, v]
             if w.model == "CCD":
@@ -125,7 +125,7 @@ class cclambda(object):
         return half
 
     def _r_L2_half(self, l1, l2, Hov, Hvv, Hoo, Hoooo, Hvvvv, Hovvo, Hovov, Hvovv, Hooov, Gvv, Goo, W, s2=None,
-                   t1=None, t2=None):
+                   t1=None, t2=None, symmetric=False):
         Loovv = self.ccwfn.H.derived("Loovv")
         l2 = l2.contiguous()
         env = dict(l1=l1.contiguous(), l2=l2, Hov=Hov, Hvv=Hvv, Hoo=Hoo, Hoooo=Hoooo,
@@ -135,7 +135,7 @@ class cclambda(object):
         if s2 is not None:                                   # (T) source: + 1/2 cc.S2 before P_ij^ab   cclambda.py:470-474
             K.strided_axpby(half, s2, 0.5, 1.0)
         self._accumulate(half, terms, env)
-        return self._ladder(half, l2, Hvvvv, t1, t2)
+        return self._ladder(half, l2, Hvvvv, t1, t2, symmetric=symmetric)
 
     def r_L2(self, o, v, l1, l2, L, Hov, Hvv, Hoo, Hoooo, Hvvvv, Hovvo, Hovov, Hvvvo, Hovoo, Hvovv, Hooov, Gvv, Goo,
              s2=None):
@@ -192,7 +192,7 @@ class cclambda(object):
             r1 = self.r_L1(o, v, self.l1, self.l2, hb.Hov, hb.Hvv, hb.Hoo, hb.Hovvo, hb.Hovov, hb.Hvvvo, hb.Hovoo,
                            hb.Hvovv, hb.Hooov, Gvv, Goo, s1=s1, W=W)
             half = self._r_L2_half(self.l1, self.l2, hb.Hov, hb.Hvv, hb.Hoo, hb.Hoooo, None, hb.Hovvo, hb.Hovov,
-                                   hb.Hvovv, hb.Hooov, Gvv, Goo, W, s2=s2)
+                                   hb.Hvovv, hb.Hooov, Gvv, Goo, W, s2=s2, symmetric=True)   # l2[i,j,a,b] = l2[j,i,b,a]
             # r2 = half + half^T, l += r/D, sum (r/D)^2 in one pass; then the pseudo-energy
             ssq = K.update_amps(r1, half, w.eps_o, w.eps_v, self.l1, self.l2, symmetrize=True, write_r2=False)
             e_dev = self.pseudoenergy(o, v, w.H.ERI, self.l2)

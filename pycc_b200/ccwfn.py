@@ -191,18 +191,28 @@ class CCwfn(object):
         return self.H.ERI[tuple(self.o if c == 'o' else self.v for c in pat)]
 
     def _vvvv_released(self):
-        """precision='MP' / 'SP': the FP64 <ab|ef> block has been released, only its TF32 planes are resident."""
-        return (not self.H.has("vvvv")) and self.H.vvvv_planes is not None
+        """The full FP64 <ab|ef> block is not resident: only its pair-packed form (or the TF32 planes of that,
+        precision='MP' / 'SP') is."""
+        return not self.H.has("vvvv")
 
     def _t1_vvvv(self, t1, out_abei, alpha=1.0):
-        """out_abei[a,b,e,i] += alpha * sum_f t_if <ab|ef> over the RESIDENT rows a of <ab|ef> (``out_abei``: any
-        strided view with that index order, first extent = resident rows).  FP64 rows come from
-        ``H.vvvv_fp64_chunks`` -- the block itself, or chunks rebuilt from the TF32 planes when precision='MP' has
-        released it (cchbar.py:654 / ccwfn.py:880, 1104 in that mode)."""
+        """out_abei[a,b,e,i] += alpha * sum_f t_if <ab|ef> from the pair-packed <ab|ef> (cchbar.py:654 / ccwfn.py:880,
+        1104 when the full block is not resident).  ``out_abei``: any strided (v,v,v,o) view with that index order.
+        Every RESIDENT pair (a >= b) contributes its (a,b) element and, through <ba|ef> = <ab|fe>, its (b,a) image --
+        with <ab|ef> sharded over ranks the result is this rank's piece (the caller all-reduces)."""
         t1 = t1.contiguous()
-        with K.mixed_mode(False):                       # the rebuilt chunks are temporaries: no second split
-            for a0, a1, blk in self.H.vvvv_fp64_chunks():
-                K.strided_axpby(out_abei[a0:a1], self._ct('if,abef->abei', t1, blk), alpha, 1.0)
+        ct = self._ct
+        with K.mixed_mode(False):                       # the rebuilt chunks are temporaries: no TF32 split of them
+            for a0, a1, X in self.H.vvvv_pair_chunks():
+                d1 = ct('pef,if->pei', X, t1)
+                d2 = ct('pfe,if->pei', X, t1)
+                off = 0
+                for a in range(a0, a1):
+                    K.strided_axpby(out_abei[a, 0:a + 1], d1[off:off + a + 1], alpha, 1.0)
+                    if a > 0:
+                        K.strided_axpby(out_abei[0:a, a], d2[off:off + a], alpha, 1.0)
+                    off += a + 1
+                del X, d1, d2
         return out_abei
 
     def build_cc3_Wmnij(self, o, v, ERI, t1):
@@ -282,7 +292,9 @@ class CCwfn(object):
         r2 = half + half^T (790), t += r/D and sum (r/D)^2 (281-284), then the energy (286).
         Returns (ecc, rms) as host floats -- the single device->host sync of the iteration."""
         F = self.H.F if F is None else F
-        r1, half = self._residuals_half(F, self.t1, self.t2)
+        # the amplitudes solve_cc iterates are pair-symmetric, t2[i,j,a,b] = t2[j,i,b,a] (the guess <ij|ab>/D is, the
+        # update adds a symmetrised residual, DIIS mixes iterates linearly): the ladder runs on rows (i >= j) only
+        r1, half = self._residuals_half(F, self.t1, self.t2, symmetric=True)
         ssq = K.update_amps(r1, half, self.eps_o, self.eps_v, self.t1, self.t2, symmetrize=True,
                             write_r2=False)
         e_dev = self.cc_energy(self.o, self.v, F, self.H.L, self.t1, self.t2)
@@ -334,14 +346,15 @@ class CCwfn(object):
         F = F.to(self.device1, dtype=F64)
         return F if F.is_contiguous() else F.contiguous()
 
-    def _residuals_half(self, F, t1, t2):
+    def _residuals_half(self, F, t1, t2, symmetric=False):
         """r1 and the UNsymmetrised half of r2 (ccwfn.py:922-940), fused formulation.  With several ranks
         each computes its share of r2 (see parallel.py) and ONE all-reduce sums them.  precision='MP': the large
-        K-major contractions inside run on the split-TF32 tcgen05 kernel (kernels.mixed_mode)."""
+        K-major contractions inside run on the split-TF32 tcgen05 kernel (kernels.mixed_mode).
+        ``symmetric``: the caller vouches that t2[i,j,a,b] = t2[j,i,b,a] (halves the ladder once more)."""
         with K.mixed_mode(self.mixed):
-            return self._residuals_half_impl(F, t1, t2)
+            return self._residuals_half_impl(F, t1, t2, symmetric)
 
-    def _residuals_half_impl(self, F, t1, t2):
+    def _residuals_half_impl(self, F, t1, t2, symmetric=False):
         F = self._check_F(F)
         t1 = t1.contiguous()
         t2 = t2.contiguous()
@@ -356,7 +369,7 @@ class CCwfn(object):
         if cc2:
             self._r2_half_cc2(F, t1, t2, half)
         else:
-            self._r2_half(F, t1, t2, I, half)
+            self._r2_half(F, t1, t2, I, half, symmetric=symmetric)
         if self.part.size > 1:
             self.part.all_reduce_sum(buf)
         K.strided_axpby(r1, r1p, 1.0, 1.0)
@@ -583,7 +596,7 @@ class CCwfn(object):
         return half
 
     # ---- r2, unsymmetrised half (ccwfn.py:922-940): this rank's share -------------------------------------
-    def _r2_half(self, F, t1, t2, I, r2=None):
+    def _r2_half(self, F, t1, t2, I, r2=None, symmetric=False):
         H, ct = self.H, self._ct
         o, v, no, nv = self.o, self.v, self.no, self.nv
         A = I["amps"]
@@ -599,7 +612,7 @@ class CCwfn(object):
         # 1/2 tau_ijef <ab|ef>  -- the particle-particle ladder, local a rows, all (i,j)      931
         if ni > 0:
             K.strided_axpby(r2[i0:i1], oovv[i0:i1], 0.5, 0.0)                      # 1/2 <ab|ij>       922
-        self._ladder(A["tau"], r2)
+        self._ladder(A["tau"], r2, symmetric=symmetric)
         if ni == 0:
             return r2
         rg = r2[i0:i1]                                                             # rows i_g (contiguous)
@@ -647,37 +660,50 @@ class CCwfn(object):
             ct("ie,jabe->ijab", t1g, H.block("ovvv"), out=rg, alpha=1.0, beta=1.0)
         return r2
 
-    def _ladder(self, tau, r2):
-        """r2[i,j,a,b] += 1/2 sum_ef tau[i,j,e,f] <ab|ef>  (ccwfn.py:931): M=o^2, N=K=v^2, <ab|ef> streamed
-        once, in place.  With an a-sharded <ab|ef> only the local rows a_g are touched."""
+    def _ladder(self, tau, r2, symmetric=False):
+        """r2[i,j,a,b] += 1/2 sum_ef tau[i,j,e,f] <ab|ef>  (ccwfn.py:931) in symmetric / antisymmetric pair form
+        (csrc/pairs.cu): T+- = (tau_ef +- tau_fe)/2 over pairs (e >= f), S = T+ V+^T and A = T- V-^T as ONE batched
+        GEMM (batch 2, N = K = v(v+1)/2), then r2[..,a,b] += (S+A)/2, r2[..,b,a] += (S-A)/2.  ``symmetric``: tau is
+        pair-symmetric, rows (i >= j) only.  Executed flop: o^2 v^4 (general) or o^2 v^4 / 2 instead of 2 o^2 v^4;
+        V+- (v^4/2 doubles, a-sharded over ranks by pair count) is streamed once, in place."""
         no, nv = self.no, self.nv
-        vvvv = None if K.MIXED.on else self.H.block("vvvv")
-        r_lo, r_hi = self.H.a_range                 # rows resident on this device
+        H = self.H
+        r_lo, r_hi = H.a_range                      # rows resident on this device
         a_lo, a_hi = self.part.a_range(nv)          # rows this rank is responsible for
         if a_lo < r_lo or a_hi > r_hi:
             raise B200ccError("<ab|ef> rows [%d,%d) needed but only [%d,%d) are resident" % (a_lo, a_hi, r_lo, r_hi))
-        na = a_hi - a_lo
-        if na == 0:
+        if a_hi == a_lo:
             return
+        nq = K.pair_count(nv)
+        npl = K.pair_count(a_hi) - K.pair_count(a_lo)           # pairs (columns of S / A) this rank computes
+        row0 = K.pair_count(a_lo) - K.pair_count(r_lo)           # first of them among the resident packed rows
+        nres = H.npairs_local
+        tri = bool(symmetric)
+        T = K.pack_tau(tau, tri)                                 # [2, M, ldq]
+        M, ldq = T.shape[1], T.shape[2]
+        lds = (npl + 1) // 2 * 2
+        SA = torch.empty((2, M, lds), dtype=F64, device=self.device1)
+        self.ladder_flops = 2.0 * 2 * M * npl * nq               # executed by the last call (bench roofline)
         if K.MIXED.on:
-            # precision='MP': <ab|ef> lives as TF32 planes [(a,b), ldp]; tau is split per iteration (1.15 GB pass)
-            hi, lo, ldp = self.H.to_mixed(drop=False)
-            th, tl, lpt = K.split_tf32(tau, no * no, nv * nv, nv * nv)
-            # One launch over all na*nv rows of <ab|ef> runs 26 % slower than the same work in row slices of a few
-            # thousand rows (192 vs 142 ms at o=40,v=300, profiles/mp_ladder_slices_r01.json): a launch then touches
-            # a few GB of address space instead of 65 GB.  Slices of ~44 n-tiles still give every SM ~4 tiles.
-            rows_total = na * nv
-            nsl = max(1, min(16, rows_total // 4096))
-            rows = -(-rows_total // nsl)
+            # precision='MP': V+- live as TF32 planes [2, nres, ldp]; T+- are split per call (a 0.6-1.2 GB pass)
+            hi, lo, ldp = H.to_mixed(drop=False)
+            th, tl, lpt = K.split_tf32(T, 2 * M, nq, ldq)
+            del T
+            # One launch over all rows of a 30+ GB operand runs ~25 % slower than the same work in row slices of a few
+            # thousand rows (profiles/mp_ladder_slices_r01.json): a launch then sweeps a few GB of address space.
+            nsl = max(1, min(16, npl // 4096))
+            rows = -(-npl // nsl)
             rows = -(-rows // 128) * 128
-            for r0 in range(0, rows_total, rows):
-                n = min(rows, rows_total - r0)
-                off = ((a_lo - r_lo) * nv + r0) * ldp
-                K.gemm_tf32x3(no * no, n, nv * nv, th, tl, lpt, (hi, off), (lo, off), ldp, (r2, a_lo * nv + r0), nv * nv,
-                              0.5, 1.0)
-            return
-        K.dgemm(no * no, na * nv, nv * nv, tau, nv * nv, 0, (vvvv, (a_lo - r_lo) * nv ** 3), nv * nv, 0,
-                (r2, a_lo * nv), nv * nv, 0.5, 1.0)
+            for r0 in range(0, npl, rows):
+                n = min(rows, npl - r0)
+                off = (row0 + r0) * ldp
+                K.gemm_tf32x3(M, n, nq, th, tl, lpt, (hi, off), (lo, off), ldp, (SA, r0), lds, 1.0, 0.0,
+                              batch=2, sA=M * lpt, sB=nres * ldp, sC=M * lds)
+        else:
+            V, ldv = H.packed()
+            K.dgemm(M, npl, nq, T, ldq, 0, (V, row0 * ldv), ldv, 0, SA, lds, 1.0, 0.0,
+                    batch=2, sA=M * ldq, sB=nres * ldv, sC=M * lds)
+        K.ladder_unpack(SA[0], SA[1], lds, no, nv, tri, a_lo, a_hi, 0.5, r2)
 
     # =============================================================================================
     # the reference's public building blocks, reference layouts (used by tests and downstream code)

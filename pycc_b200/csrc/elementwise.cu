@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(256) multi_axpy_kernel(i64 n, PtrPack xs, doub
 
 using namespace b200cc;
 
-extern "C" int b200cc_version(void) { return 100; }
+extern "C" int b200cc_version(void) { return 200; }
 extern "C" const char* b200cc_last_error(void) { return g_err; }
 extern "C" b200cc_i64 b200cc_launch_count(void) { return g_launches.load(); }
 

@@ -962,6 +962,11 @@ using namespace b200cc;
 
 extern "C" int b200cc_dgemm(const b200cc_gemm_desc* d, void* stream) {
   if (!d) { set_error("b200cc_dgemm: null descriptor"); return 1; }
+  if (d->struct_size != (int)sizeof(b200cc_gemm_desc)) {
+    set_error("b200cc_dgemm: descriptor is %d bytes, this library's b200cc_gemm_desc is %d (stale binding? see include/b200cc.h)",
+              d->struct_size, (int)sizeof(b200cc_gemm_desc));
+    return 1;
+  }
   if (d->M < 0 || d->N < 0 || d->K1 < 0 || d->K2 < 0 || d->batch < 0) {
     set_error("b200cc_dgemm: negative dimension"); return 1;
   }

@@ -1121,6 +1121,11 @@ extern "C" int b200cc_merge_tf32(const float* hi, const float* lo, b200cc_i64 ld
 
 extern "C" int b200cc_gemm_tf32x3(const b200cc_gemm3_desc* d, void* stream) {
   if (!d) { set_error("b200cc_gemm_tf32x3: null descriptor"); return 1; }
+  if (d->struct_size != (int)sizeof(b200cc_gemm3_desc)) {
+    set_error("b200cc_gemm_tf32x3: descriptor is %d bytes, this library's b200cc_gemm3_desc is %d (stale binding? see include/b200cc.h)",
+              d->struct_size, (int)sizeof(b200cc_gemm3_desc));
+    return 1;
+  }
   if (d->M <= 0 || d->N <= 0 || d->batch <= 0) return 0;
   if (d->K <= 0) { set_error("b200cc_gemm_tf32x3: K must be positive"); return 1; }
   if (!d->Ahi || !d->Alo || !d->Bhi || !d->Blo || !d->C) { set_error("b200cc_gemm_tf32x3: null operand"); return 1; }

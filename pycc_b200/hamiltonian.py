@@ -14,6 +14,7 @@ symmetry relations <pq|rs> = <qp|sr> = <rs|pq> = <rq|ps> = <ps|rq> (+ products).
 from __future__ import annotations
 
 import itertools
+import os
 
 import numpy as np
 import torch
@@ -127,9 +128,57 @@ class BlockHamiltonian:
         # precision='MP': TF32 (hi, lo) planes of constant GEMM operands, computed once (kernels._split_operand);
         # <ab|ef> as planes [(a,b), ldp] (the FP64 block may then be released, see to_mixed)
         self._split_cache = {}
+        # <ab|ef> in pair-packed form (csrc/pairs.cu): FP64 [2, npl, ldq] (V+, V-) over the pairs (a >= b) of the
+        # resident rows a, and / or its TF32 planes (hi, lo: FP32 [2, npl, ldp]) for precision='MP'.  The ladder only
+        # ever reads these; the full FP64 block is optional (kept when small, see keep_vvvv_bytes).
+        self.vvvv_packed = None
         self.vvvv_planes = None
+        self.owned = True          # False: a caller's object (wavefunction.resolve_reference) -- never release its blocks
         for t in self._blocks.values():
             K.register_constant(t, self._split_cache)
+
+    # FP64 <ab|ef> blocks up to this size stay resident next to the packed form (small molecules: ``H.ERI[v,v,v,v]``
+    # and the other direct consumers keep working on it); larger ones are released once packed when the Hamiltonian
+    # belongs to the wavefunction.  B200CC_VVVV_KEEP_GB overrides.
+    keep_vvvv_bytes = int(float(os.environ.get("B200CC_VVVV_KEEP_GB", "4")) * (1 << 30))
+
+    @property
+    def npairs_local(self):
+        a_lo, a_hi = self.a_range
+        return K.pair_count(a_hi) - K.pair_count(a_lo)
+
+    def packed(self, drop=None):
+        """(V [2, npl, ldq], ldq): the pair-packed FP64 <ab|ef> of the resident rows, built on first use from the FP64
+        block in row chunks.  ``drop``: release the FP64 block afterwards (default: when it exceeds keep_vvvv_bytes)."""
+        if self.vvvv_packed is None:
+            if self.vvvv_planes is not None:
+                raise B200ccError("<ab|ef> is resident as TF32 planes only (precision='MP')")
+            vvvv = self.block("vvvv")
+            nv = self.nv
+            a_lo, a_hi = self.a_range
+            ldq = K.pair_ld(nv)
+            V = torch.empty((2, self.npairs_local, ldq), dtype=torch.float64, device=self.device)
+            step = max(1, int((1 << 30) // max(8 * nv ** 3, 1)))
+            for a0 in range(a_lo, a_hi, step):
+                a1 = min(a_hi, a0 + step)
+                row = K.pair_count(a0) - K.pair_count(a_lo)
+                K.pack_pairs(vvvv[a0 - a_lo:a1 - a_lo], nv, a0, a1, (V[0], row * ldq), (V[1], row * ldq), ldq)
+            self.vvvv_packed = (V, ldq)
+            K.register_constant(V, self._split_cache)
+        if drop is None:
+            drop = (self.owned and "vvvv" in self._blocks
+                    and self._blocks["vvvv"].numel() * 8 > self.keep_vvvv_bytes)
+        if drop:
+            self._release_fp64_vvvv()
+        return self.vvvv_packed
+
+    def _release_fp64_vvvv(self):
+        if "vvvv" in self._blocks:
+            # the released storage may be handed to a per-iteration tensor next: it must not look constant any more
+            K.unregister_tensor(self._blocks["vvvv"])
+            for key in [k for k in self._split_cache if k[0] == self._blocks["vvvv"].data_ptr()]:
+                del self._split_cache[key]
+            del self._blocks["vvvv"]
 
     def __del__(self):
         try:
@@ -141,24 +190,46 @@ class BlockHamiltonian:
         try:
             return self._blocks[name]
         except KeyError:
-            if name == "vvvv" and self.vvvv_planes is not None:
-                raise B200ccError("the FP64 <ab|ef> block was released for precision='MP' (only its TF32 planes are "
-                                  "resident)")
+            if name == "vvvv" and (self.vvvv_planes is not None or self.vvvv_packed is not None):
+                return self.materialize_vvvv()
             raise B200ccError("integral block %r is not resident" % name)
 
+    def materialize_vvvv(self):
+        """The full FP64 <ab|ef> block rebuilt from the pair-packed form (or its TF32 planes) -- for callers that index
+        ``H.ERI[v,v,v,v]`` directly.  Only when every row is resident and the block fits keep_vvvv_bytes; the ladder and
+        the t1-dressed consumers never need it (they work on pair chunks, vvvv_pair_chunks)."""
+        nv = self.nv
+        if self.a_range != (0, nv):
+            raise B200ccError("<ab|ef> is sharded over ranks (rows %r of %d): the full block is not available"
+                              % (self.a_range, nv))
+        if 8 * nv ** 4 > self.keep_vvvv_bytes:
+            raise B200ccError("the full FP64 <ab|ef> block (%.1f GB) is not kept resident: only its pair-packed form "
+                              "is (raise B200CC_VVVV_KEEP_GB, or use H.vvvv_pair_chunks())" % (8 * nv ** 4 / 2 ** 30))
+        out = torch.empty((nv, nv, nv, nv), dtype=torch.float64, device=self.device)
+        for a0, a1, X in self.vvvv_pair_chunks():
+            off = 0
+            for a in range(a0, a1):
+                K.strided_axpby(out[a, 0:a + 1], X[off:off + a + 1], 1.0, 0.0)
+                if a > 0:                                   # <ba|ef> = <ab|fe>
+                    K.strided_axpby(out[0:a, a], X[off:off + a].permute(0, 2, 1), 1.0, 0.0)
+                off += a + 1
+        self._blocks["vvvv"] = out
+        K.register_constant(out, self._split_cache)
+        return out
+
     def to_mixed(self, drop=True):
-        """Split <ab|ef> into TF32 planes (precision='MP'); ``drop`` releases the FP64 block (64.8 GB at v=300)."""
+        """TF32 planes (hi, lo, ldp), each FP32 [2, npl, ldp], of the pair-packed <ab|ef> (precision='MP'); ``drop``
+        releases the FP64 forms (block and packed)."""
         if self.vvvv_planes is None:
-            vvvv = self.block("vvvv")
-            na, nv = vvvv.shape[0], self.nv
-            hi, lo, ldp = K.split_tf32(vvvv, na * nv, nv * nv, nv * nv)
-            self.vvvv_planes = (hi[0], lo[0], ldp)
-        if drop and "vvvv" in self._blocks:
-            # the released storage may be handed to a per-iteration tensor next: it must not look constant any more
-            K.unregister_tensor(self._blocks["vvvv"])
-            for key in [k for k in self._split_cache if k[0] == self._blocks["vvvv"].data_ptr()]:
-                del self._split_cache[key]
-            del self._blocks["vvvv"]
+            V, ldq = self.packed(drop=drop)
+            npl, nq = V.shape[1], K.pair_count(self.nv)
+            hi, lo, ldp = K.split_tf32(V, 2 * npl, nq, ldq)
+            self.vvvv_planes = (hi[0].view(2, npl, ldp), lo[0].view(2, npl, ldp), ldp)
+        if drop:
+            self._release_fp64_vvvv()
+            if self.vvvv_packed is not None:
+                K.unregister_tensor(self.vvvv_packed[0])
+                self.vvvv_packed = None
         return self.vvvv_planes
 
     def has(self, name):
@@ -168,29 +239,40 @@ class BlockHamiltonian:
         """Drop the cached TF32 planes of the constant operands (precision='MP'); they are rebuilt on demand."""
         self._split_cache.clear()
 
-    merge_chunk_bytes = 2 << 30        # size of the FP64 row chunks rebuilt from the TF32 planes of <ab|ef>
+    merge_chunk_bytes = 2 << 30        # size of the FP64 pair chunks rebuilt from the packed form / its TF32 planes
 
-    def vvvv_fp64_chunks(self, chunk_bytes=None):
-        """(a0, a1, FP64 [a1-a0, v, v, v]) over the RESIDENT rows of <ab|ef> (local row numbers): the block itself, or --
-        precision='MP' after the FP64 block was released -- chunks rebuilt from its TF32 planes (hi + lo: 2^-22
-        relative, the accuracy of the mode).  For the few FP64-only consumers of <ab|ef> outside the ladder
-        (t_if <ab|ef> in HBAR / CC2 / CC3: 2ov^4 flop, one pass per call)."""
-        if "vvvv" in self._blocks:
-            blk = self._blocks["vvvv"]
-            yield 0, blk.shape[0], blk
-            return
-        if self.vvvv_planes is None:
-            raise B200ccError("integral block 'vvvv' is not resident")
-        hi, lo, ldp = self.vvvv_planes
+    def vvvv_pair_chunks(self, chunk_bytes=None):
+        """(a0, a1, X) over the RESIDENT rows a of <ab|ef> in chunks of whole rows: X[p, e, f] = <ab|ef> (FP64) for the
+        pairs p = pair(a,b) - pair(a0,0), a0 <= a < a1, b <= a.  Built from the pair-packed form (exact up to one
+        rounding), or -- precision='MP' -- from its TF32 planes (hi + lo: 2^-22 relative, the accuracy of the mode).
+        For the FP64 consumers of <ab|ef> outside the ladder (t_if <ab|ef> in HBAR / CC2 / CC3: 2ov^4 flop, one pass per
+        call); the (b, a) image of a pair follows from <ba|ef> = <ab|fe>."""
         nv = self.nv
-        na = hi.shape[0] // nv
+        a_lo, a_hi = self.a_range
+        nq = K.pair_count(nv)
+        if self.vvvv_packed is None and self.vvvv_planes is None:
+            self.packed()
         chunk_bytes = self.merge_chunk_bytes if chunk_bytes is None else chunk_bytes
-        step = int(max(1, min(na, chunk_bytes // max(8 * nv ** 3, 1))))
-        for a0 in range(0, na, step):
-            a1 = min(na, a0 + step)
-            rows = (a1 - a0) * nv
-            blk = K.merge_tf32((hi, a0 * nv * ldp), (lo, a0 * nv * ldp), ldp, rows, nv * nv)
-            yield a0, a1, blk.view(a1 - a0, nv, nv, nv)
+        budget = max(1, chunk_bytes // max(8 * nv * nv, 1))           # pairs per chunk
+        a0 = a_lo
+        while a0 < a_hi:
+            a1 = a0 + 1
+            while a1 < a_hi and K.pair_count(a1 + 1) - K.pair_count(a0) <= budget:
+                a1 += 1
+            row = K.pair_count(a0) - K.pair_count(a_lo)
+            n = K.pair_count(a1) - K.pair_count(a0)
+            if self.vvvv_packed is not None:
+                V, ldq = self.vvvv_packed
+                X = K.unpack_pairs((V[0], row * ldq), (V[1], row * ldq), ldq, nv, n)
+            else:
+                hi, lo, ldp = self.vvvv_planes
+                tmp = torch.empty((2, n, nq), dtype=torch.float64, device=self.device)
+                for s_ in (0, 1):
+                    K.merge_tf32((hi[s_], row * ldp), (lo[s_], row * ldp), ldp, n, nq, out=tmp[s_])
+                X = K.unpack_pairs(tmp[0], tmp[1], nq, nv, n)
+                del tmp
+            yield a0, a1, X
+            a0 = a1
 
     # ---- constructors ---------------------------------------------------------------------------
     @classmethod
@@ -221,32 +303,47 @@ class BlockHamiltonian:
             a_lo, a_hi = (0, nv) if a_range is None else a_range
             na = a_hi - a_lo
             Bqs = K.permuted(B[:, q, s], (1, 2, 0))                  # [(b,f), P]  K-major
-            rows = max(1, min(na, int(chunk_bytes // (8 * nv ** 3))))
+            rows = max(1, min(max(na, 1), int(chunk_bytes // (8 * nv ** 3))))
+            # <ab|ef> goes straight into its pair-packed form (FP64 V+/V-, or TF32 planes of them for precision='MP'):
+            # each row chunk of the generating GEMM ([a,e,b,f] order) is packed in place through a strided view.  The
+            # full FP64 block is kept as well only while it is small (keep_vvvv_bytes).
+            nq, ldq = K.pair_count(nv), K.pair_ld(nv)
+            npl = K.pair_count(a_hi) - K.pair_count(a_lo)
+            keep_full = (not mixed) and 8 * na * nv ** 3 <= cls.keep_vvvv_bytes
+            full = torch.empty((na, nv, nv, nv), dtype=torch.float64, device=dev) if keep_full else None
             if mixed:
-                # precision='MP': the FP64 block is never materialised, each row chunk goes straight to TF32 planes
-                ldp = (nv * nv + 3) // 4 * 4
-                hi = torch.empty((na * nv, ldp), dtype=torch.float32, device=dev)
-                lo = torch.empty((na * nv, ldp), dtype=torch.float32, device=dev)
-                out = torch.empty((min(rows, na), nv, nv, nv), dtype=torch.float64, device=dev)
-                planes = (hi, lo, ldp)
+                ldp = (nq + 3) // 4 * 4
+                hi = torch.empty((2, npl, ldp), dtype=torch.float32, device=dev)
+                lo = torch.empty((2, npl, ldp), dtype=torch.float32, device=dev)
             else:
-                out = torch.empty((na, nv, nv, nv), dtype=torch.float64, device=dev)
-            for a0 in range(0, na, rows):
-                a1 = min(na, a0 + rows)
-                Bpr = K.permuted(B[:, no + a_lo + a0:no + a_lo + a1, r], (1, 2, 0))   # [(a,e), P]
+                V = torch.empty((2, npl, ldq), dtype=torch.float64, device=dev)
+            for a0 in range(a_lo, a_hi, rows):
+                a1 = min(a_hi, a0 + rows)
+                Bpr = K.permuted(B[:, no + a0:no + a1, r], (1, 2, 0))   # [(a,e), P]
                 tmp = ct("aeP,bfP->aebf", Bpr, Bqs, alpha=syn.scale)
-                dst = out[:a1 - a0] if mixed else out[a0:a1]
-                K.strided_axpby(dst, tmp.permute(0, 2, 1, 3), 1.0, 0.0)
-                del tmp, Bpr
+                view = tmp.permute(0, 2, 1, 3)                              # indexed [a, b, e, f]
+                row = K.pair_count(a0) - K.pair_count(a_lo)
+                n = K.pair_count(a1) - K.pair_count(a0)
                 if mixed:
-                    K.split_tf32(dst, (a1 - a0) * nv, nv * nv, nv * nv,
-                                 out=((hi, a0 * nv * ldp), (lo, a0 * nv * ldp), ldp))
-            if not mixed:
-                blocks[name] = out
-            del out
+                    Vc = torch.empty((2, n, ldq), dtype=torch.float64, device=dev)
+                    K.pack_pairs(view, nv, a0, a1, Vc[0], Vc[1], ldq)
+                    for s_ in (0, 1):
+                        K.split_tf32(Vc[s_], n, nq, ldq, out=((hi[s_], row * ldp), (lo[s_], row * ldp), ldp))
+                    del Vc
+                else:
+                    K.pack_pairs(view, nv, a0, a1, (V[0], row * ldq), (V[1], row * ldq), ldq)
+                if full is not None:
+                    K.strided_axpby(full[a0 - a_lo:a1 - a_lo], view, 1.0, 0.0)
+                del tmp, Bpr, view
+            if full is not None:
+                blocks[name] = full
         H = cls(syn.F, blocks, no, 0, dev, a_range)
-        if mixed and "vvvv" in names:
-            H.vvvv_planes = planes
+        if "vvvv" in names:
+            if mixed:
+                H.vvvv_planes = (hi, lo, ldp)
+            else:
+                H.vvvv_packed = (V, ldq)
+                K.register_constant(V, H._split_cache)
         return H
 
     @classmethod

@@ -192,6 +192,7 @@ def gemm_tf32x3(M, N, K, Ahi, Alo, lda, Bhi, Blo, ldb, Cmat, ldc, alpha=1.0, bet
 
     fa = _faddr
     d = Gemm3Desc()
+    d.struct_size = C.sizeof(Gemm3Desc)
     d.M, d.N, d.K = int(M), int(N), int(K)
     d.Ahi, d.Alo, d.Bhi, d.Blo = fa(Ahi), fa(Alo), fa(Bhi), fa(Blo)
     d.lda, d.ldb, d.strideA, d.strideB = int(lda), int(ldb), int(sA), int(sB)
@@ -246,6 +247,7 @@ def dgemm(M, N, K, A, lda, transA, B, ldb, transB, Cmat, ldc, alpha=1.0, beta=0.
                            M * lpa if (nA1 > 1 and sA) else 0, N * lpb if (nB1 > 1 and sB) else 0, sC,
                            seg2=s2, bcoords=bcoords, nbatch=nbatch, kchunk=mp_kchunk)
     d = GemmDesc()
+    d.struct_size = C.sizeof(GemmDesc)
     d.M, d.N, d.transA, d.transB = int(M), int(N), int(bool(transA)), int(bool(transB))
     d.K1 = int(K)
     d.A1, d.B1, d.C = _addr(A), _addr(B), _addr(Cmat)
@@ -275,6 +277,58 @@ def dgemm(M, N, K, A, lda, transA, B, ldb, transB, Cmat, ldc, alpha=1.0, beta=0.
         d.workspace = _lib.ptr(ws)
     _lib.check(_lib.get().b200cc_dgemm(C.byref(d), _lib.stream()), "b200cc_dgemm")
     del ws
+
+
+# ---- the ladder in symmetric / antisymmetric pair form (csrc/pairs.cu) ------------------------------------------
+def pair_count(n):
+    """number of pairs (x >= y) of n indices; pair(x, y) = x(x+1)/2 + y"""
+    return int(n) * (int(n) + 1) // 2
+
+
+def pair_ld(nv):
+    """row pitch of packed pair matrices: v(v+1)/2 rounded up to 16 doubles (128-byte rows for TMA boxes)"""
+    return (pair_count(nv) + 15) // 16 * 16
+
+
+def pack_pairs(src, nv, a0, a1, vp, vm, ldq):
+    """Rows a in [a0,a1) of <ab|ef> -> V+ / V- rows pair(a,b) - pair(a0,0), b <= a (b200cc_pack_pairs).
+    ``src``: a 4-D strided view indexed [a - a0, b, e, f] (any memory order); ``vp``, ``vm``: tensor or
+    (tensor, element offset) of the first output row."""
+    if src.dim() != 4 or tuple(src.shape) != (a1 - a0, nv, nv, nv):
+        raise B200ccError("pack_pairs: src must be a [a1-a0, v, v, v] view (got %s)" % (tuple(src.shape),))
+    sa, sb, se, sf = (int(x) for x in src.stride())
+    _lib.check(_lib.get().b200cc_pack_pairs(_lib.ptr(src), sa, sb, se, sf, int(nv), int(a0), int(a1), _addr(vp),
+                                            _addr(vm), int(ldq), _lib.stream()), "b200cc_pack_pairs")
+
+
+def unpack_pairs(vp, vm, ldq, nv, npairs, out=None):
+    """FP64 slabs <ab|ef>[p, e, f] of ``npairs`` consecutive packed rows starting at ``vp`` / ``vm`` (b200cc_unpack_pairs)."""
+    if out is None:
+        out = torch.empty((int(npairs), nv, nv), dtype=F64, device=_dev(vp))
+    _lib.check(_lib.get().b200cc_unpack_pairs(_addr(vp), _addr(vm), int(ldq), int(nv), int(npairs), _lib.ptr(out),
+                                              _lib.stream()), "b200cc_unpack_pairs")
+    return out
+
+
+def pack_tau(tau, tri, out=None):
+    """tau (no,no,nv,nv) -> [2, M, ldq]: T+ and T- over the pairs (e >= f); M = o(o+1)/2 rows (i >= j) when ``tri``
+    (tau pair-symmetric), else o^2 (b200cc_pack_tau)."""
+    no, nv = tau.shape[0], tau.shape[2]
+    M = pair_count(no) if tri else no * no
+    ldq = pair_ld(nv)
+    if out is None:
+        out = torch.empty((2, M, ldq), dtype=F64, device=tau.device)
+    _lib.check(_lib.get().b200cc_pack_tau(_lib.ptr(_c(tau, "tau")), int(no), int(nv), int(bool(tri)), _lib.ptr(out[0]),
+                                          _lib.ptr(out[1]), int(ldq), _lib.stream()), "b200cc_pack_tau")
+    return out
+
+
+def ladder_unpack(S, A, lds, no, nv, tri, a0, a1, alpha, r2):
+    """r2 += alpha * (the ladder held as S / A over the pairs of rows a in [a0,a1)) (b200cc_ladder_unpack)."""
+    _lib.check(_lib.get().b200cc_ladder_unpack(_addr(S), _addr(A), int(lds), int(no), int(nv), int(bool(tri)), int(a0),
+                                               int(a1), float(alpha), _lib.ptr(_c(r2, "r2")), _lib.stream()),
+               "b200cc_ladder_unpack")
+    return r2
 
 
 def strided_axpby(out, inp, alpha=1.0, beta=0.0):

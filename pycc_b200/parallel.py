@@ -4,8 +4,9 @@ The reference has no distributed code at all.  Here ``torch.distributed`` (NCCL 
 B200; gloo in the CPU tests) is plumbing only -- ONE all-reduce of the half-residual r2 (o^2 v^2
 doubles) per CCSD iteration and ONE scalar all-reduce for E(T):
 
-* <ab|ef> is held a-sharded: rank g owns rows a in ``a_range(nv)`` and computes the ladder
-  contribution to r2[:, :, a_g, :] from the (replicated) tau;
+* <ab|ef> is held a-sharded in its pair-packed form (rows (a >= b), see csrc/pairs.cu): rank g owns the pairs of
+  the rows a in ``a_range(nv)`` -- boundaries chosen for equal PAIR counts -- and computes the ladder contribution to
+  r2[:, :, a_g, b <= a] and its (b, a) image from the (replicated) tau;
 * every other o^3v^3 / o^4v^2 / o^2v^3 term of r2 is split over an occupied index -- rank g computes
   r2[i_g] rows (F/W_mnij/Z/t1-driven terms) and r2[:, j_g] columns (ring terms, whose W_mbej/W_mbje
   intermediates are built only for the local j_g, so they are never gathered);
@@ -27,6 +28,24 @@ def split(n, size, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def split_pairs(n, size, rank):
+    """Contiguous partition of range(n) into ``size`` parts with (nearly) equal numbers of PAIRS (a >= b): part
+    boundaries at a_k ~ n sqrt(k / size).  <ab|ef> is held as its pair-packed rows (a >= b), so equal work per rank
+    means equal pair counts, not equal row counts."""
+    total = n * (n + 1) // 2
+
+    def bound(k):
+        if k <= 0:
+            return 0
+        if k >= size:
+            return n
+        target = total * k / size
+        a = int((2.0 * target) ** 0.5)
+        best = min(range(max(0, a - 2), min(n, a + 3) + 1), key=lambda x: abs(x * (x + 1) // 2 - target))
+        return best
+    return bound(rank), bound(rank + 1)
+
+
 class Comm:
     """Rank / size and the two collectives the path needs."""
 
@@ -38,7 +57,7 @@ class Comm:
         self.size = dist.get_world_size(group)
 
     def a_range(self, nv):
-        return split(nv, self.size, self.rank)
+        return split_pairs(nv, self.size, self.rank)
 
     def occ_range(self, no):
         return split(no, self.size, self.rank)

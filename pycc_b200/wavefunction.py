@@ -32,8 +32,11 @@ class IntegralReference:
     def hamiltonian(self, device, comm=None, mixed=False):
         """``mixed``: the Hamiltonian will be used by precision='MP' -- <ab|ef> is kept as TF32 planes only."""
         H = self._make(device, comm, mixed)
-        if mixed and H.vvvv_planes is None and H.has("vvvv"):
+        H.owned = self._owns
+        if mixed and H.vvvv_planes is None and (H.has("vvvv") or H.vvvv_packed is not None):
             H.to_mixed(drop=self._owns)
+        elif not mixed and self._owns and H.has("vvvv"):
+            H.packed()                     # pack now; a large FP64 block is released (BlockHamiltonian.keep_vvvv_bytes)
         return H
 
     @classmethod

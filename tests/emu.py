@@ -64,7 +64,7 @@ class EmuLib:
         self.calls[name] = self.calls.get(name, 0) + 1
 
     def b200cc_version(self):
-        return 100
+        return 200
 
     def b200cc_last_error(self):
         return self.err
@@ -172,6 +172,103 @@ class EmuLib:
                 Cm[...] = d.alpha * acc + d.beta * Cm
             else:
                 Cm[...] = d.alpha * acc
+        return 0
+
+    # ---- ladder in pair form (csrc/pairs.cu) ------------------------------------------------------------
+    @staticmethod
+    def _pairs(n):
+        """(x, y) index arrays of the pairs x >= y in pair(x,y) = x(x+1)/2 + y order"""
+        x, y = np.tril_indices(n)
+        return x, y
+
+    def b200cc_pair_count(self, n):
+        return n * (n + 1) // 2
+
+    def b200cc_pack_pairs(self, src, sa, sb, se, sf, nv, a0, a1, vp, vm, ldq, stream):
+        self._count("pack_pairs")
+        na = a1 - a0
+        if na <= 0:
+            return 0
+        X = _arr(src, (na, nv, nv, nv), (sa, sb, se, sf))
+        e, f = self._pairs(nv)
+        nq = len(e)
+        npairs = a1 * (a1 + 1) // 2 - a0 * (a0 + 1) // 2
+        P = _arr(vp, (npairs, ldq), (ldq, 1))
+        Mn = _arr(vm, (npairs, ldq), (ldq, 1))
+        P[...] = 0.0
+        Mn[...] = 0.0
+        row = 0
+        for a in range(a0, a1):
+            for b in range(a + 1):
+                S = X[a - a0, b]
+                x, y = S[e, f], S[f, e]
+                P[row, :nq] = np.where(e == f, x, x + y)
+                Mn[row, :nq] = 0.0 if a == b else np.where(e == f, 0.0, x - y)
+                row += 1
+        return 0
+
+    def b200cc_unpack_pairs(self, vp, vm, ldq, nv, npairs, dst, stream):
+        self._count("unpack_pairs")
+        if npairs <= 0:
+            return 0
+        P = _arr(vp, (npairs, ldq), (ldq, 1))
+        Mn = _arr(vm, (npairs, ldq), (ldq, 1))
+        D = _vec(dst, npairs * nv * nv).reshape(npairs, nv, nv)
+        e, f = self._pairs(nv)
+        nq = len(e)
+        lower = 0.5 * (P[:, :nq] + Mn[:, :nq])
+        upper = 0.5 * (P[:, :nq] - Mn[:, :nq])
+        D[:, f, e] = upper
+        D[:, e, f] = lower
+        dg = e == f
+        D[:, e[dg], f[dg]] = P[:, :nq][:, dg]
+        return 0
+
+    def _rows(self, no, tri):
+        if tri:
+            i, j = self._pairs(no)
+        else:
+            i, j = np.divmod(np.arange(no * no), no)
+        return i, j
+
+    def b200cc_pack_tau(self, tau, no, nv, tri, tp, tm, ldq, stream):
+        self._count("pack_tau")
+        T = _vec(tau, no * no * nv * nv).reshape(no, no, nv, nv)
+        i, j = self._rows(no, tri)
+        e, f = self._pairs(nv)
+        nq, M = len(e), len(i)
+        P = _arr(tp, (M, ldq), (ldq, 1))
+        Mn = _arr(tm, (M, ldq), (ldq, 1))
+        P[...] = 0.0
+        Mn[...] = 0.0
+        x = T[i[:, None], j[:, None], e[None, :], f[None, :]]
+        y = T[i[:, None], j[:, None], f[None, :], e[None, :]]
+        P[:, :nq] = np.where(e == f, x, 0.5 * (x + y))
+        Mn[:, :nq] = np.where(e == f, 0.0, 0.5 * (x - y))
+        return 0
+
+    def b200cc_ladder_unpack(self, S, A, lds, no, nv, tri, a0, a1, alpha, r2, stream):
+        self._count("ladder_unpack")
+        if a1 <= a0:
+            return 0
+        R = _vec(r2, no * no * nv * nv).reshape(no, no, nv, nv)
+        i, j = self._rows(no, tri)
+        M = len(i)
+        npl = a1 * (a1 + 1) // 2 - a0 * (a0 + 1) // 2
+        Sm = _arr(S, (M, npl), (lds, 1))
+        Am = _arr(A, (M, npl), (lds, 1))
+        a, b = self._pairs(a1)
+        keep = a >= a0
+        a, b = a[keep], b[keep]
+        off = a != b
+        for m in range(M):
+            u = alpha * (Sm[m] + Am[m])
+            w = alpha * (Sm[m] - Am[m])
+            R[i[m], j[m], a, b] += u
+            R[i[m], j[m], b[off], a[off]] += w[off]
+            if tri and i[m] != j[m]:
+                R[j[m], i[m], a, b] += w
+                R[j[m], i[m], b[off], a[off]] += u[off]
         return 0
 
     # ---- permute / axpby ---------------------------------------------------------------------------

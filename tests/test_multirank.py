@@ -83,7 +83,9 @@ def _worker_mp(rank, world, port, golden_path, q):
             comm = Comm()
             cc = pycc_b200.ccwfn(syn, model="CCSD(T)", device="GPU", quiet=True, comm=comm, precision="MP")
             a0, a1 = comm.a_range(syn.nv)
-            assert not cc.H.has("vvvv") and cc.H.vvvv_planes[0].shape[0] == (a1 - a0) * syn.nv
+            # only the TF32 planes of this rank's pair-packed rows (a >= b, a in its range) are resident
+            assert not cc.H.has("vvvv") and cc.H.vvvv_packed is None
+            assert cc.H.vvvv_planes[0].shape[:2] == (2, a1 * (a1 + 1) // 2 - a0 * (a0 + 1) // 2)
             g0 = K.MIXED.stats["gemm"]
             ecc = cc.solve_cc(1e-7, 1e-7)
             ee = abs(float(ecc) - float(g["e_total_ccsd_t"]))
