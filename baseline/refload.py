@@ -196,6 +196,13 @@ def reference_wfn(ref, F, no, ERI, L=None, blocks=None, nfzc=0, model="CCSD", de
     w.Dia = eo.reshape(-1, 1) - ev
     w.t1 = np.zeros((w.no, w.nv))
     w.t2 = np.array(ERI[w.o, w.o, w.v, w.v]) / w.Dijab
+    if device == "GPU":
+        # what wavefunction.py:165-169 and ccwfn.py:195-211 do for device='GPU': F / eps / denominators / amplitudes
+        # become torch tensors on the compute device, the n^4 ERI / L torch tensors on the storage device (host)
+        H.F, H.eps = mgr.seed_compute(H.F), mgr.seed_compute(H.eps)
+        H.ERI, H.L = mgr.seed_store(np.ascontiguousarray(H.ERI)), mgr.seed_store(np.ascontiguousarray(H.L))
+        w.Dijab, w.Dia = mgr.seed_compute(w.Dijab), mgr.seed_compute(w.Dia)
+        w.t1, w.t2 = mgr.seed_compute(w.t1), mgr.seed_compute(w.t2)
     return w
 
 

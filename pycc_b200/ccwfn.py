@@ -30,7 +30,7 @@ from ._lib import B200ccError
 from .contract import Contractor
 from .device import DeviceManager
 from .exceptions import InvalidKeywordError, PyCCError
-from .hamiltonian import BlockHamiltonian
+from .hamiltonian import BlockHamiltonian, _BlockView
 from .utils import helper_diis, title, iteration, converged, timing, solve_params
 from .wavefunction import resolve_reference
 from .parallel import Serial
@@ -317,6 +317,10 @@ class CCwfn(object):
         if real_time and self.model == 'CC3':
             # ccwfn.py:399-404: with real_time the CC3 triples use the explicit-field intermediates
             raise NotImplementedError("the explicit-field (real-time) CC3 triples are outside the accelerated path")
+        if self._foreign():
+            # someone swapped H.ERI / H.L (perturbed integrals, ccderiv.py:250-259): term-by-term generic evaluation
+            r1, half = self._generic().residuals(F, t1, t2)
+            return r1, K.symmetrize_r2(half)
         r1, half = self._residuals_half(F, t1, t2)
         K.symmetrize_r2(half)
         return r1, half
@@ -712,53 +716,91 @@ class CCwfn(object):
         return K.build_tau(t1.contiguous(), t2.contiguous(), fact1, fact2)
 
     def _own(self, ERI=None, L=None):
-        if (ERI is not None and ERI is not self.H.ERI) or (L is not None and L is not self.H.L):
-            raise NotImplementedError("swapped-in (perturbed) integrals are outside the accelerated path; "
-                                      "use the wavefunction's own H.ERI / H.L")
+        """The fused (block) formulation only applies to the wavefunction's own integrals; CC2 / CC3 have no generic
+        path (the CCSD / CCD methods dispatch on ``_foreign`` before they get here)."""
+        if self._foreign(ERI, L):
+            raise NotImplementedError("swapped-in (perturbed) integrals with model %r are outside the accelerated path; "
+                                      "use the wavefunction's own H.ERI / H.L" % self.model)
+
+    def _foreign(self, ERI=None, L=None):
+        """True when the integrals to use are not this wavefunction's own block views: a caller passed other objects,
+        or swapped ``self.H.ERI`` / ``self.H.L`` (ccderiv.py:250-259 does, around ``residuals``)."""
+        H = self.H
+        for given, kind in ((ERI, "ERI"), (L, "L")):
+            cur = getattr(H, kind)
+            own = isinstance(cur, _BlockView) and cur.H is H and cur.kind == kind
+            if not own or (given is not None and given is not cur):
+                return True
+        return False
+
+    def _generic(self, ERI=None, L=None):
+        """The term-by-term evaluator for foreign integrals (generic.py); L defaults to 2 ERI - ERI^T(rs) of the ERI in
+        use when only ERI is foreign (hamiltonian.py:70)."""
+        from .generic import GenericResidual
+        if self.model not in ('CCSD', 'CCSD(T)', 'CCD'):
+            raise NotImplementedError("swapped-in (perturbed) integrals with model %r are outside the accelerated path"
+                                      % self.model)
+        ERI = self.H.ERI if ERI is None else ERI
+        L = self.H.L if L is None else L
+        return GenericResidual(self, ERI, L)
 
     def _I(self, F, t1, t2):
         with K.mixed_mode(self.mixed):
             return self._intermediates(self._check_F(F), t1.contiguous(), t2.contiguous(), full=True)
 
     def build_Fae(self, o, v, F, L, t1, t2):
+        if self._foreign(L=L) and self.model != 'CC2':
+            return self._generic(L=L).intermediates(F, t1, t2)["Fae"]
         self._own(L=L)
         return self._I(F, t1, t2)["Fae"]
 
     def build_Fmi(self, o, v, F, L, t1, t2):
+        if self._foreign(L=L) and self.model != 'CC2':
+            return self._generic(L=L).intermediates(F, t1, t2)["Fmi"]
         self._own(L=L)
         return self._I(F, t1, t2)["Fmi"]
 
     def build_Fme(self, o, v, F, L, t1):
-        self._own(L=L)
         if self.model == 'CCD':
             return None
+        if self._foreign(L=L) and self.model != 'CC2':
+            return self._generic(L=L).intermediates(F, t1, self.t2)["Fme"]
+        self._own(L=L)
         F = self._check_F(F)
         Fme = K.permuted(F[self.o, self.v], (0, 1))
         self._ct("menf,nf->me", self.H.derived("Loovv_menf"), t1.contiguous(), out=Fme, alpha=1.0, beta=1.0)
         return Fme
 
     def build_Wmnij(self, o, v, ERI, t1, t2):
+        if self._foreign(ERI) and self.model != 'CC2':
+            return self._generic(ERI).intermediates(self.H.F, t1, t2)["Wmnij"]
         self._own(ERI)
         if self.model == 'CC2':
             return self._cc2_Wmnij(t1.contiguous())
         return self._I(self.H.F, t1, t2)["Wmnij"]
 
     def build_Wmbej(self, o, v, ERI, L, t1, t2):
+        if self._foreign(ERI, L) and self.model != 'CC2':
+            return self._generic(ERI, L).intermediates(self.H.F, t1, t2)["Wmbej"]
         self._own(ERI, L)
         if self.model == 'CC2':
             return None                                                           # ccwfn.py:638-639
         return K.permuted(self._I(self.H.F, t1, t2)["W1"], (2, 1, 3, 0))          # [j,b,m,e] -> [m,b,e,j]
 
     def build_Wmbje(self, o, v, ERI, t1, t2):
+        if self._foreign(ERI) and self.model != 'CC2':
+            return self._generic(ERI).intermediates(self.H.F, t1, t2)["Wmbje"]
         self._own(ERI)
         if self.model == 'CC2':
             return None                                                           # ccwfn.py:677-678
         return K.permuted(self._I(self.H.F, t1, t2)["W2"], (2, 1, 0, 3))          # [j,b,m,e] -> [m,b,j,e]
 
     def build_Zmbij(self, o, v, ERI, t1, t2):
-        self._own(ERI)
         if self.model == 'CCD':
             return None
+        if self._foreign(ERI) and self.model != 'CC2':
+            return self._generic(ERI).intermediates(self.H.F, t1, t2)["Zmbij"]
+        self._own(ERI)
         if self.model == 'CC2':
             return self._cc2_Zmbij(t1.contiguous())
         return K.permuted(self._I(self.H.F, t1, t2)["Zijmb"], (2, 3, 0, 1))       # [i,j,m,b] -> [m,b,i,j]
@@ -766,6 +808,8 @@ class CCwfn(object):
     def r_T1(self, o, v, F, ERI, L, t1, t2, Fae=None, Fme=None, Fmi=None):
         """T1 residual (ccwfn.py:718-761).  The intermediates are rebuilt internally in the fused layouts;
         the Fae/Fme/Fmi arguments are accepted for signature compatibility."""
+        if self._foreign(ERI, L) and self.model != 'CC2':
+            return self._generic(ERI, L).residuals(F, t1, t2)[0]
         self._own(ERI, L)
         F = self._check_F(F)
         t1, t2 = t1.contiguous(), t2.contiguous()
@@ -782,6 +826,8 @@ class CCwfn(object):
     def r_T2(self, o, v, F, ERI, t1, t2, Fae=None, Fme=None, Fmi=None, Wmnij=None, Wmbej=None, Wmbje=None,
              Zmbij=None):
         """Symmetrised T2 residual (ccwfn.py:764-791)."""
+        if self._foreign(ERI) and self.model != 'CC2':
+            return K.symmetrize_r2(self._generic(ERI).residuals(F, t1, t2)[1])
         self._own(ERI)
         F = self._check_F(F)
         t1, t2 = t1.contiguous(), t2.contiguous()

@@ -38,14 +38,72 @@ class ContractionBackend(object):
     def _resident(self, x):
         if not isinstance(x, torch.Tensor):
             x = torch.from_numpy(np.ascontiguousarray(x))
-        if x.is_complex():
-            raise NotImplementedError("complex operands are outside the accelerated path")
-        if x.device != self.device1 or x.dtype != torch.float64:
-            x = x.to(self.device1, dtype=torch.float64)
+        want = torch.complex128 if x.is_complex() else torch.float64
+        if x.device != self.device1 or x.dtype != want:
+            x = x.to(self.device1, dtype=want)
         return x
 
     def __call__(self, subscripts, *operands, **kw):
-        return self.engine(subscripts, *[self._resident(x) for x in operands], **kw)
+        ops = [self._resident(x) for x in operands]
+        if any(x.is_complex() for x in ops):
+            return self._complex(subscripts, ops, **kw)
+        return self.engine(subscripts, *ops, **kw)
+
+    # ---- complex operands (RT-CC: the reference upcasts real operands to complex and lets torch.einsum do complex
+    # arithmetic, device.py:79-83).  Here a complex contraction is real GEMMs on the real / imaginary parts, which are
+    # strided float64 views of the complex storage: 3 products for complex x complex (Karatsuba / "3M":
+    # (Ar + Ai)(Br + Bi) - ArBr - AiBi is the imaginary part), 2 for complex x real.  Result: complex128.
+    def _complex(self, subscripts, ops, out=None, alpha=1.0, beta=0.0):
+        from . import kernels as K
+        if out is not None or beta != 0.0:
+            raise NotImplementedError("complex contractions return a new tensor (no in-place / accumulate form)")
+        ins, res = subscripts.replace(" ", "").split("->")
+        ins = ins.split(",")
+        if len(ops) != len(ins):
+            raise PyCCError("contract: %d operands for %r" % (len(ops), subscripts))
+
+        def parts(x):
+            return (x.real, x.imag) if x.is_complex() else (x, None)
+
+        def cplx(re, im):
+            z = torch.empty(tuple(re.shape), dtype=torch.complex128, device=re.device)
+            K.strided_axpby(z.real, re, 1.0, 0.0)
+            K.strided_axpby(z.imag, im, 1.0, 0.0)
+            return z
+
+        def pair(sub, A, B, scale=1.0):
+            (ar, ai), (br, bi) = parts(A), parts(B)
+            if ai is None:                                             # real x complex
+                return cplx(self.engine(sub, ar, br, alpha=scale), self.engine(sub, ar, bi, alpha=scale))
+            if bi is None:                                             # complex x real
+                return cplx(self.engine(sub, ar, br, alpha=scale), self.engine(sub, ai, br, alpha=scale))
+            p1 = self.engine(sub, ar, br, alpha=scale)
+            p2 = self.engine(sub, ai, bi, alpha=scale)
+            sa = K.strided_axpby(K.permuted(ar, tuple(range(ar.dim()))), ai, 1.0, 1.0)       # Ar + Ai
+            sb = K.strided_axpby(K.permuted(br, tuple(range(br.dim()))), bi, 1.0, 1.0)       # Br + Bi
+            im = self.engine(sub, sa, sb, alpha=scale)
+            K.strided_axpby(im, p1, -1.0, 1.0)
+            K.strided_axpby(im, p2, -1.0, 1.0)
+            K.strided_axpby(p1, p2, -1.0, 1.0)                                               # ArBr - AiBi
+            return cplx(p1, im)
+
+        if len(ops) == 1:
+            (xr, xi) = parts(ops[0])
+            sub = "%s->%s" % (ins[0], res)
+            return cplx(self.engine(sub, xr, alpha=alpha), self.engine(sub, xi, alpha=alpha))
+        cur, cur_idx = ops[0], ins[0]
+        for n in range(1, len(ops)):                    # left to right; intermediates keep every index still needed
+            last = n == len(ops) - 1
+            later = "".join(ins[n + 1:]) + res
+            tgt = res if last else "".join(ch for ch in dict.fromkeys(cur_idx + ins[n]) if ch in later)
+            sub = "%s,%s->%s" % (cur_idx, ins[n], tgt)
+            scale = alpha if last else 1.0
+            if cur.is_complex() or ops[n].is_complex():
+                cur = pair(sub, cur, ops[n], scale)
+            else:
+                cur = self.engine(sub, cur, ops[n], alpha=scale)
+            cur_idx = tgt
+        return cur
 
 
 class DeviceManager(object):
