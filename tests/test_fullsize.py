@@ -94,13 +94,16 @@ def test_config1_mixed_precision_iteration_within_1e6(config1):
 
 
 def test_config2_ladder_rows_match_oracle_and_are_linear():
-    """o=40, v=300: r2[:,:,a,:] += 1/2 tau_ijef <ab|ef> (ccwfn.py:931) against numpy on sampled rows a; linearity"""
+    """o=40, v=300: r2[:,:,a,:] += 1/2 tau_ijef <ab|ef> (ccwfn.py:931) -- evaluated in pair-packed form, general mode on an
+    unsymmetric tau and (i >= j) mode on a pair-symmetric one -- against numpy on sampled rows a; linearity; the packed
+    rows themselves against <ab|ef> rebuilt on the host"""
     no, nv = 40, 300
     dev = torch.device(DEV)
     syn = make_synthetic(no, nv, seed=0, device=dev)
     H = BlockHamiltonian.from_factor(syn, dev, names=("oovv", "vvvv"))
-    w = types.SimpleNamespace(H=H, no=no, nv=nv, part=pycc_b200.parallel.Serial())
-    ladder = lambda tau, r2: pycc_b200.ccwfn._ladder(w, tau, r2)
+    assert not H.has("vvvv") and H.vvvv_packed is not None          # 64.8 GB as a block, 32.6 GB packed
+    w = types.SimpleNamespace(H=H, no=no, nv=nv, part=pycc_b200.parallel.Serial(), device1=dev)
+    ladder = lambda tau, r2, **kw: pycc_b200.ccwfn._ladder(w, tau, r2, **kw)
     g = torch.Generator(device=dev).manual_seed(5)
     tau1 = torch.randn((no, no, nv, nv), dtype=torch.float64, device=dev, generator=g)
     tau2 = torch.randn((no, no, nv, nv), dtype=torch.float64, device=dev, generator=g)
@@ -112,15 +115,30 @@ def test_config2_ladder_rows_match_oracle_and_are_linear():
     ladder(comb, r12)
     lin = 0.75 * r1 - 1.5 * r2
     assert float((r12 - lin).abs().max()) < 1e-10 * float(lin.abs().max())
+    # pair-symmetric tau: rows (i >= j) only must give the same as the general mode
+    K.strided_axpby(comb, tau1, 1.0, 0.0)
+    K.strided_axpby(comb, tau1.permute(1, 0, 3, 2), 1.0, 1.0)
+    rs, rg = torch.zeros_like(tau1), torch.zeros_like(tau1)
+    ladder(comb, rs, symmetric=True)
+    ladder(comb, rg)
+    assert float((rs - rg).abs().max()) < 1e-11 * float(rg.abs().max())
     # sampled rows against the oracle's einsum on <a b|ef> rebuilt on the host from the factor
     Bv = syn.B[:, no:, no:]
     t1h = tau1.cpu().numpy()
+    tsh = comb.cpu().numpy()
+    V, ldq = H.packed()
     for a in (0, 137, 299):
         vrow = np.einsum("Pe,Pbf->bef", Bv[:, a, :], Bv, optimize=True) * syn.scale          # <ab|ef> for this a
         want = 0.5 * np.einsum("ijef,bef->ijb", t1h, vrow, optimize=True)
         got = r1[:, :, a, :].cpu().numpy()
         assert np.abs(got - want).max() < 1e-10 * max(1.0, np.abs(want).max()), a
-        assert np.abs(H.block("vvvv")[a].cpu().numpy() - vrow).max() < 1e-12
+        want = 0.5 * np.einsum("ijef,bef->ijb", tsh, vrow, optimize=True)
+        got = rs[:, :, a, :].cpu().numpy()
+        assert np.abs(got - want).max() < 1e-10 * max(1.0, np.abs(want).max()), a
+        # the packed rows of this a (pairs (a, b <= a)) unpack to <ab|ef>
+        row = K.pair_count(a)
+        X = K.unpack_pairs((V[0], row * ldq), (V[1], row * ldq), ldq, nv, a + 1).cpu().numpy()
+        assert np.abs(X - vrow[:a + 1]).max() < 1e-12
 
 
 def test_config3_sampled_triples_match_oracle():
