@@ -321,7 +321,7 @@ def main():
     t_setup = time.time()
     syn = make_synthetic(o, v, seed=0, device=dev)
     cc = pycc_b200.ccwfn(syn, model="CCSD(T)", device="GPU", quiet=True, comm=comm)
-    diis = pycc_b200.helper_diis(cc.t1, cc.t2, 8)
+    diis = cc.make_diis(8)
     e_mp2 = float(cc.cc_energy(cc.o, cc.v, cc.H.F, cc.H.L, cc.t1, cc.t2))
     sync()
     t_setup = time.time() - t_setup
@@ -351,6 +351,15 @@ def main():
     clocks = sampler.stop()
     launches = K.launch_count() - l0
     s_iter = rmax(ev0.elapsed_time(ev1) * 1e-3) / args.steps
+
+    # ---- where the step goes on this rank (rank 0): two more steps bracketed phase by phase with CUDA events
+    K.PHASES.on = True
+    K.PHASES.collect()
+    for _ in range(2):
+        step()
+    phases = {k.strip(): {"calls_per_step": c / 2.0, "ms_per_step": ms / 2.0, "nested": k.startswith("  ")}
+              for k, (c, ms) in K.PHASES.collect().items()}
+    K.PHASES.on = False
 
     # ---- parity at the FULL size, in this very run: the first iterations against the energies the unmodified
     # reference printed when it was run once at this size on this pool's host (profiles/reference_fullsize_r02.json)
@@ -438,17 +447,26 @@ def main():
     d_F = torch.empty_like(cc.H.F)
     e2e_steps = max(2, min(args.steps, 3))
 
+    i0, i1 = cc.part.occ_range(o)
+
     def e2e_step():
+        cc._gather_rows()
         cc.t1.copy_(h_t1, non_blocking=True)
-        cc.t2.copy_(h_t2, non_blocking=True)
+        if world > 1:       # each rank uploads ITS rows of t2 over PCIe, the rest arrives over NVLink
+            cc.t2[i0:i1].copy_(h_t2[i0:i1], non_blocking=True)
+            cc.part.all_gather_rows(cc.t2)
+        else:
+            cc.t2.copy_(h_t2, non_blocking=True)
         d_F.copy_(h_F, non_blocking=True)
         out = cc.iterate(d_F)                              # returns host floats (D2H of 2 doubles)
         cc.diis_step(diis, True)
         return out
     t_e2e, _ = cuda_time(e2e_step, e2e_steps, sync)
     t_e2e = rmax(t_e2e)
-    e2e = {"value": t_e2e, "unit": "s/iter", "h2d_bytes_per_step": int((h_t1.numel() + h_t2.numel() + h_F.numel()) * 8),
-           "d2h_bytes_per_step": 16}
+    e2e = {"value": t_e2e, "unit": "s/iter",
+           "h2d_bytes_per_step": int((h_t1.numel() + h_t2[i0:i1].numel() + h_F.numel()) * 8), "d2h_bytes_per_step": 16,
+           "note": "per rank: t1, F and this rank's rows of t2 from pinned host memory%s; (ecc, rms) read back"
+                   % (" + all-gather of the rows over NVLink" if world > 1 else "")}
     n_dp = len(energies)
     del cc, diis, h_t1, h_t2, h_F, d_F, V
     release()
@@ -460,7 +478,7 @@ def main():
     if not args.no_c4:
         syn4 = make_synthetic(30, 280, seed=0, device=dev)
         cc4 = pycc_b200.ccwfn(syn4, model="CCSD(T)", device="GPU", quiet=True, comm=comm)
-        d4 = pycc_b200.helper_diis(cc4.t1, cc4.t2, 8)
+        d4 = cc4.make_diis(8)
         for _ in range(3):
             e4, _ = cc4.iterate()
             cc4.diis_step(d4, True)
@@ -498,7 +516,7 @@ def main():
     mp = None
     if not args.no_mp:
         ccm = pycc_b200.ccwfn(syn, model="CCSD(T)", device="GPU", precision="MP", quiet=True, comm=comm)
-        diism = pycc_b200.helper_diis(ccm.t1, ccm.t2, 8)
+        diism = ccm.make_diis(8)
         e_mp = []
 
         def mstep():
@@ -553,7 +571,7 @@ def main():
                 "warmup": nwarm, "ms_per_step": s_iter * 1e3, "higher_is_better": False,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": cfg, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "t": t_info, "t_c4": c4, "mp": mp,
-                "parity": parity, "clocks": clocks, "gpu_launches": int(launches), "ecc_last": ecc, "rms_last": rms,
+                "parity": parity, "phases": phases, "clocks": clocks, "gpu_launches": int(launches), "ecc_last": ecc, "rms_last": rms,
                 "energies": energies}
         print(json.dumps(line), flush=True)
     if comm is not None:

@@ -185,6 +185,14 @@ int b200cc_update_amps(int no, int nv, const double* eo, const double* ev, const
                        double* r2_half, int symmetrize, int write_r2, double* t1, double* t2,
                        double* sumsq, double* scratch, void* stream);
 
+/* The same update for the rows i in [i0,i1) of t2 only -- one process per GPU: after the all-reduce of the half
+ * residual each rank updates its rows, then the rows are all-gathered (parallel.py).  t1 (replicated, tiny) is updated
+ * in full by every caller when r1 != NULL.  sumsq2[0] = sum (r2/D)^2 over the rows, sumsq2[1] = sum (r1/D)^2.
+ * r2_half is not modified.  scratch: >= 4096 doubles.                                                            */
+int b200cc_update_amps_rows(int no, int nv, int i0, int i1, const double* eo, const double* ev, const double* r1,
+                            const double* r2_half, double* t1, double* t2, double* sumsq2, double* scratch,
+                            void* stream);
+
 /* r2 = half + half^T in place (r_T2, ccwfn.py:790) */
 int b200cc_symmetrize_r2(int no, int nv, double* r2, void* stream);
 
@@ -192,6 +200,12 @@ int b200cc_symmetrize_r2(int no, int nv, double* r2, void* stream);
  * fov: (no,nv) view with leading dimension ldf.  scratch: >= 4096 doubles.                       */
 int b200cc_cc_energy(int no, int nv, const double* fov, b200cc_i64 ldf, const double* t1, const double* t2,
                      const double* Loovv, double* e_out, double* scratch, void* stream);
+
+/* The rows i in [i0,i1) of the doubles part (+ the singles part when with_singles != 0): partial energies of the
+ * ranks are summed by the caller.                                                                              */
+int b200cc_cc_energy_rows(int no, int nv, int i0, int i1, int with_singles, const double* fov, b200cc_i64 ldf,
+                          const double* t1, const double* t2, const double* Loovv, double* e_out, double* scratch,
+                          void* stream);
 
 /* out[q] = sum_i x[i]*y_q[i], q < m <= 16; `ys` is a HOST array of m device pointers.
  * One pass over x; deterministic two-stage reduction.  (helper_diis B matrix, utils.py:330-339;

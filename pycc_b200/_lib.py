@@ -111,6 +111,10 @@ SIGNATURES = {
     "b200cc_div_d1": (C.c_int, [C.c_int, C.c_int, dptr, dptr, dptr, dptr, C.c_void_p]),
     "b200cc_update_amps": (C.c_int, [C.c_int, C.c_int, dptr, dptr, dptr, dptr, C.c_int, C.c_int,
                                      dptr, dptr, dptr, dptr, C.c_void_p]),
+    "b200cc_update_amps_rows": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, dptr, dptr, dptr, dptr, dptr, dptr, dptr,
+                                          dptr, C.c_void_p]),
+    "b200cc_cc_energy_rows": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, dptr, i64, dptr, dptr, dptr, dptr,
+                                        dptr, C.c_void_p]),
     "b200cc_symmetrize_r2": (C.c_int, [C.c_int, C.c_int, dptr, C.c_void_p]),
     "b200cc_cc_energy": (C.c_int, [C.c_int, C.c_int, dptr, i64, dptr, dptr, dptr, dptr, dptr, C.c_void_p]),
     "b200cc_multi_dot": (C.c_int, [i64, dptr, C.c_int, C.POINTER(dptr), dptr, dptr, C.c_void_p]),

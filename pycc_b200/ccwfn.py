@@ -145,7 +145,7 @@ class CCwfn(object):
         say(title(name))
         say(iteration(0, energy=ecc, de=-ecc, e_label="CC Ecorr", note="MP2"))
 
-        diis = helper_diis(self.t1, self.t2, max_diis, self.precision)
+        diis = self.make_diis(max_diis)
         self.trace = []
         for niter in range(1, maxiter + 1):
             ecc_last = ecc
@@ -154,6 +154,7 @@ class CCwfn(object):
             self.trace.append((ecc, rms))
             say(iteration(niter, energy=ecc, de=ediff, rms=rms, e_label="CC Ecorr"))
             if abs(ediff) < e_conv and abs(rms) < r_conv:
+                self._gather_rows()
                 say(converged(name, time.time() - tstart))
                 say("E(REF)  = %20.15f" % self.eref)
                 ecc_t = torch.tensor(ecc, dtype=F64, device=self.device1)
@@ -171,7 +172,24 @@ class CCwfn(object):
                 return ecc_t
             self.diis_step(diis, niter >= start_diis)
         # not converged: the reference falls off the loop and returns None (ccwfn.py:268-319)
+        self._gather_rows()
         return None
+
+    # with several ranks the HBM-bound tail of an iteration (update, energy, DIIS) is sharded over the rows of t2 and
+    # the rows are all-gathered once per iteration (parallel.py); False = every rank repeats the whole tail
+    shard_update = True
+
+    def make_diis(self, max_diis=8):
+        """The DIIS object solve_cc uses: sharded over this wavefunction's ranks when the update is (see shard_update)."""
+        sharded = self.part.size > 1 and self.shard_update
+        return helper_diis(self.t1, self.t2, max_diis, self.precision, comm=self.comm if sharded else None)
+
+    def _gather_rows(self):
+        """Make t2 complete on every rank again after a sharded update (no-op otherwise)."""
+        if getattr(self, "_rows_stale", False):
+            with K.PHASES("all-gather t2"):
+                self.part.all_gather_rows(self.t2)
+            self._rows_stale = False
 
     def t3_density(self):
         """(T) contributions to the Lambda residuals and the one-/two-particle densities (ccwfn.py:1819-1829):
@@ -292,20 +310,43 @@ class CCwfn(object):
         r2 = half + half^T (790), t += r/D and sum (r/D)^2 (281-284), then the energy (286).
         Returns (ecc, rms) as host floats -- the single device->host sync of the iteration."""
         F = self.H.F if F is None else F
+        self._gather_rows()
         # the amplitudes solve_cc iterates are pair-symmetric, t2[i,j,a,b] = t2[j,i,b,a] (the guess <ij|ab>/D is, the
         # update adds a symmetrised residual, DIIS mixes iterates linearly): the ladder runs on rows (i >= j) only
         r1, half = self._residuals_half(F, self.t1, self.t2, symmetric=True)
-        ssq = K.update_amps(r1, half, self.eps_o, self.eps_v, self.t1, self.t2, symmetrize=True,
-                            write_r2=False)
-        e_dev = self.cc_energy(self.o, self.v, F, self.H.L, self.t1, self.t2)
-        ssq_h, ecc = torch.stack((ssq[0], e_dev)).tolist()
+        if self.part.size > 1 and self.shard_update:
+            # every rank holds the summed half residual; it updates ITS rows of t2 (and the small, replicated t1),
+            # the partial sums of squares / energies are added over the ranks; the rows are gathered by diis_step
+            i0, i1 = self.part.occ_range(self.no)
+            Fc = self._check_F(F)
+            with K.PHASES("update+energy"):
+                ss = K.update_amps_rows(r1, half, self.eps_o, self.eps_v, self.t1, self.t2, i0, i1)
+                e_p = K.cc_energy_rows(Fc[self.o, self.v], self.t1, self.t2, self.H.derived("Loovv"), i0, i1,
+                                       self.part.rank == 0)
+                both = torch.stack((ss[0], e_p[0]))
+                self.part.all_reduce_sum(both)
+                ssq2, ecc, ssq1 = torch.cat((both, ss[1:2])).tolist()
+            self._rows_stale = True
+            return ecc, (ssq2 + ssq1) ** 0.5
+        with K.PHASES("update+energy"):
+            ssq = K.update_amps(r1, half, self.eps_o, self.eps_v, self.t1, self.t2, symmetrize=True,
+                                write_r2=False)
+            e_dev = self.cc_energy(self.o, self.v, F, self.H.L, self.t1, self.t2)
+            ssq_h, ecc = torch.stack((ssq[0], e_dev)).tolist()
         return ecc, ssq_h ** 0.5
 
     def diis_step(self, diis, extrapolate=True):
-        """ccwfn.py:317-319"""
-        diis.add_error_vector(self.t1, self.t2)
-        if extrapolate:
-            self.t1, self.t2 = diis.extrapolate(self.t1, self.t2)
+        """ccwfn.py:317-319.  After a sharded update (iterate with several ranks) t2 is complete only in this rank's rows:
+        a sharded DIIS object (make_diis) reads just those and all-gathers the extrapolant; otherwise the rows are
+        gathered first."""
+        with K.PHASES("diis"):
+            if getattr(diis, "comm", None) is None or not extrapolate or diis.max_diis == 0:
+                self._gather_rows()
+            diis.add_error_vector(self.t1, self.t2)
+            if extrapolate:
+                self.t1, self.t2 = diis.extrapolate(self.t1, self.t2)
+                if getattr(diis, "comm", None) is not None and diis.max_diis != 0:
+                    self._rows_stale = False                # the extrapolant was all-gathered
 
     # =============================================================================================
     # residuals (ccwfn.py:321-372)
@@ -363,19 +404,22 @@ class CCwfn(object):
         t1 = t1.contiguous()
         t2 = t2.contiguous()
         cc2 = self.model == 'CC2'
-        I = self._intermediates(F, t1, t2, rings=not cc2)
+        with K.PHASES("intermediates"):
+            I = self._intermediates(F, t1, t2, rings=not cc2)
         # one flat buffer [ r2 half | rank-partial part of r1 ] so that ONE all-reduce carries both
         n2, n1 = t2.numel(), t1.numel()
         buf = torch.empty(n2 + n1, dtype=F64, device=self.device1)
         half = buf[:n2].view(t2.shape)
         r1p = buf[n2:].view(t1.shape)
-        r1 = self._r1(F, t1, t2, I, r1p)
+        with K.PHASES("r1"):
+            r1 = self._r1(F, t1, t2, I, r1p)
         if cc2:
             self._r2_half_cc2(F, t1, t2, half)
         else:
             self._r2_half(F, t1, t2, I, half, symmetric=symmetric)
         if self.part.size > 1:
-            self.part.all_reduce_sum(buf)
+            with K.PHASES("all-reduce r2"):
+                self.part.all_reduce_sum(buf)
         K.strided_axpby(r1, r1p, 1.0, 1.0)
         if self.model == 'CCD':
             r1.zero_()
@@ -405,7 +449,8 @@ class CCwfn(object):
         o, v, no, nv = self.o, self.v, self.no, self.nv
         i0, i1 = (0, no) if full else self.part.occ_range(no)
         ni = i1 - i0
-        A = self._amps(t1, t2)
+        with K.PHASES("  amps (tau, ring layouts)"):
+            A = self._amps(t1, t2)
         I = {"amps": A, "occ": (i0, i1)}
         ccd = self.model == 'CCD'
         Fov = F[o, v]
@@ -443,6 +488,8 @@ class CCwfn(object):
         if ni == 0 or not rings:           # rings=False: the one-body intermediates only (CC2's r1)
             return I
 
+        I["_span"] = K.PHASES("  Wmnij, W1/W2, Z")
+        I["_span"].__enter__()
         # ---------------- Wmnij[m,n,i_g,j]                               (ccwfn.py:596-603)
         ooov = H.block("ooov")
         Wfull = K.permuted(H.block("oooo"), (0, 1, 2, 3))
@@ -488,6 +535,7 @@ class CCwfn(object):
         # ---------------- Z'[i_g,j,m,b] = Zmbij[m,b,i,j] = <mb|ef> tau_ijef   (ccwfn.py:715)
         if not ccd:
             I["Zijmb"] = ct("ijef,mbef->ijmb", A["tau"][i0:i1], H.block("ovvv"))
+        I.pop("_span").__exit__(None, None, None)
         return I
 
     def _Loovv_emnf(self, m0, m1):
@@ -616,7 +664,8 @@ class CCwfn(object):
         # 1/2 tau_ijef <ab|ef>  -- the particle-particle ladder, local a rows, all (i,j)      931
         if ni > 0:
             K.strided_axpby(r2[i0:i1], oovv[i0:i1], 0.5, 0.0)                      # 1/2 <ab|ij>       922
-        self._ladder(A["tau"], r2, symmetric=symmetric)
+        with K.PHASES("ladder"):
+            self._ladder(A["tau"], r2, symmetric=symmetric)
         if ni == 0:
             return r2
         rg = r2[i0:i1]                                                             # rows i_g (contiguous)
@@ -637,6 +686,8 @@ class CCwfn(object):
         # 1/2 tau_mnab W_mnij                                                       930
         ct("mnij,mnab->ijab", I["Wmnij"], A["tau"], out=rg, alpha=0.5, beta=1.0)
         # ring terms, columns j_g, in [i,a,j,b] layout                              933-935
+        span = K.PHASES("ring terms")
+        span.__enter__()
         R = ct("iame,jbme->iajb", A["s_iame"], I["W1"])          # (2t2 - t2^T) W_mbej
         ct("iame,jbme->iajb", A["t2_iame"], I["W2"], out=R, alpha=1.0, beta=1.0)   # t2 W_mbje^T
         K.strided_axpby(r2[:, i0:i1], R.permute(0, 2, 1, 3), 1.0, 1.0)
@@ -644,6 +695,7 @@ class CCwfn(object):
         ct("jame,ibme->jaib", t2_jame, I["W2"], out=R, alpha=1.0, beta=0.0)        # t2_mjae W_mbie
         K.strided_axpby(rg, R.permute(2, 0, 1, 3), 1.0, 1.0)
         del R, t2_jame
+        span.__exit__(None, None, None)
         if not ccd:
             ooov, ovov = H.block("ooov"), H.block("ovov")
             # - t_ma ( Z_mbij + <mb|ij> + t_ie <mb|ej> )  as one batched product    932, 940, 936-937

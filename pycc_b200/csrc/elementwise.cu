@@ -254,6 +254,106 @@ __global__ void __launch_bounds__(256) energy_kernel(int no, int nv, const doubl
   if (threadIdx.x == 0) scratch[blockIdx.x] = part;
 }
 
+// ---- the same two passes for a RANGE OF ROWS i in [i0, i1) (multi-GPU: each rank updates only its rows of t2 after the
+// all-reduce of the half residual, then the rows are all-gathered; parallel.py) --------------------------------------
+// r[i,j,a,b] = half[i,j,a,b] + half[j,i,b,a];  t2[i,j,a,b] += r/D;  partial sum of (r/D)^2.  No partner writes: the
+// rank that owns row j does (j,i) itself.  Work item = (i, j, tile A, tile B); block 32 x 8.
+__global__ void __launch_bounds__(256) update_rows_kernel(int no, int nv, int i0, int i1, const double* __restrict__ eo,
+                                                          const double* __restrict__ ev, const double* __restrict__ half,
+                                                          double* t2, double* scratch) {
+  __shared__ double Y[32][33];
+  __shared__ double red[8];
+  const int nt = (nv + 31) / 32;
+  const i64 nwork = (i64)(i1 - i0) * no * nt * nt;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const i64 vv = (i64)nv * nv;
+  double part = 0.0;
+  for (i64 w = blockIdx.x; w < nwork; w += gridDim.x) {
+    i64 r = w;
+    const int tb = (int)(r % nt); r /= nt;
+    const int ta = (int)(r % nt); r /= nt;
+    const int j = (int)(r % no);
+    const int i = i0 + (int)(r / no);
+    const int a0 = ta * 32, b0 = tb * 32;
+    const double* Hij = half + ((i64)i * no + j) * vv;
+    const double* Hji = half + ((i64)j * no + i) * vv;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+      const int y = ty + k;       // Y[y][x] = H_ji[b0+y][a0+x]
+      Y[y][tx] = (b0 + y < nv && a0 + tx < nv) ? Hji[(i64)(b0 + y) * nv + a0 + tx] : 0.0;
+    }
+    __syncthreads();
+    const double eij = eo[i] + eo[j];
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+      const int y = ty + k;
+      const int a = a0 + y, b = b0 + tx;
+      if (a < nv && b < nv) {
+        const i64 off = ((i64)i * no + j) * vv + (i64)a * nv + b;
+        const double d = (Hij[(i64)a * nv + b] + Y[tx][y]) / (eij - ev[a] - ev[b]);
+        t2[off] += d;
+        part += d * d;
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const int tid = ty * 32 + tx;
+    double v = warp_sum(part);
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    if (tid < 32) {
+      double sm = tid < 8 ? red[tid] : 0.0;
+      sm = warp_sum(sm);
+      if (tid == 0) scratch[blockIdx.x] = sm;
+    }
+  }
+}
+
+// t1 += r1/D and sum (r1/D)^2 (tiny; one block)
+__global__ void __launch_bounds__(256) update_t1_kernel(int no, int nv, const double* __restrict__ eo,
+                                                        const double* __restrict__ ev, const double* __restrict__ r1,
+                                                        double* t1, double* out) {
+  __shared__ double red[8];
+  double part = 0.0;
+  for (int e = threadIdx.x; e < no * nv; e += 256) {
+    const int i = e / nv, a = e - i * nv;
+    const double d = r1[e] / (eo[i] - ev[a]);
+    t1[e] += d;
+    part += d * d;
+  }
+  part = block_sum<256>(part, red);
+  if (threadIdx.x == 0) out[0] = part;
+}
+
+__global__ void __launch_bounds__(256) energy_rows_kernel(int no, int nv, int i0, int i1, int singles,
+                                                          const double* __restrict__ fov, i64 ldf,
+                                                          const double* __restrict__ t1, const double* __restrict__ t2,
+                                                          const double* __restrict__ L, double* scratch) {
+  __shared__ double red[8];
+  const int vv = nv * nv;
+  double part = 0.0;
+  for (int ij = i0 * no + blockIdx.x; ij < i1 * no; ij += gridDim.x) {
+    const int i = ij / no, j = ij - i * no;
+    const double* ti = t1 + (i64)i * nv;
+    const double* tj = t1 + (i64)j * nv;
+    const i64 base = (i64)ij * vv;
+    for (int ab = threadIdx.x; ab < vv; ab += blockDim.x) {
+      const int a = ab / nv, b = ab - a * nv;
+      part += (t2[base + ab] + ti[a] * tj[b]) * L[base + ab];
+    }
+  }
+  if (blockIdx.x == 0 && singles) {
+    for (int e = threadIdx.x; e < no * nv; e += blockDim.x) {
+      const int i = e / nv, a = e - i * nv;
+      part += 2.0 * fov[(i64)i * ldf + a] * t1[e];
+    }
+  }
+  part = block_sum<256>(part, red);
+  if (threadIdx.x == 0) scratch[blockIdx.x] = part;
+}
+
 // ---- DIIS helpers ------------------------------------------------------------------------------------
 struct PtrPack {
   const double* p[16];
@@ -385,6 +485,42 @@ extern "C" int b200cc_cc_energy(int no, int nv, const double* fov, b200cc_i64 ld
   const int nblk = no * no < 2048 ? no * no : 2048;
   energy_kernel<<<nblk, 256, 0, st>>>(no, nv, fov, ldf, t1, t2, Loovv, scratch);
   if (check_launch("energy_kernel")) return 1;
+  return launch_final_reduce(scratch, nblk, 0, 1, e_out, 0, 1.0, st);
+}
+
+extern "C" int b200cc_update_amps_rows(int no, int nv, int i0, int i1, const double* eo, const double* ev,
+                                       const double* r1, const double* r2_half, double* t1, double* t2,
+                                       double* sumsq2, double* scratch, void* stream) {
+  if (no <= 0 || nv <= 0) return 0;
+  if (i0 < 0 || i1 > no || i1 < i0) { set_error("b200cc_update_amps_rows: bad row range"); return 1; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // sumsq2[0] = doubles of rows [i0,i1), sumsq2[1] = singles (every caller updates the whole, replicated t1)
+  B200CC_CUDA_OK(cudaMemsetAsync(sumsq2, 0, 2 * sizeof(double), st));
+  if (i1 > i0) {
+    const int nt = (nv + 31) / 32;
+    const i64 nwork = (i64)(i1 - i0) * no * nt * nt;
+    const int nblk = (int)(nwork < 2048 ? nwork : 2048);
+    update_rows_kernel<<<nblk, dim3(32, 8), 0, st>>>(no, nv, i0, i1, eo, ev, r2_half, t2, scratch);
+    if (check_launch("update_rows_kernel")) return 1;
+    if (launch_final_reduce(scratch, nblk, 0, 1, sumsq2, 0, 1.0, st)) return 1;
+  }
+  if (r1 != nullptr) {
+    update_t1_kernel<<<1, 256, 0, st>>>(no, nv, eo, ev, r1, t1, sumsq2 + 1);
+    if (check_launch("update_t1_kernel")) return 1;
+  }
+  return 0;
+}
+
+extern "C" int b200cc_cc_energy_rows(int no, int nv, int i0, int i1, int with_singles, const double* fov,
+                                     b200cc_i64 ldf, const double* t1, const double* t2, const double* Loovv,
+                                     double* e_out, double* scratch, void* stream) {
+  if (no <= 0 || nv <= 0) return 0;
+  if (i0 < 0 || i1 > no || i1 < i0) { set_error("b200cc_cc_energy_rows: bad row range"); return 1; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int rows = (i1 - i0) * no;
+  const int nblk = rows < 1 ? 1 : (rows < 2048 ? rows : 2048);
+  energy_rows_kernel<<<nblk, 256, 0, st>>>(no, nv, i0, i1, with_singles, fov, ldf, t1, t2, Loovv, scratch);
+  if (check_launch("energy_rows_kernel")) return 1;
   return launch_final_reduce(scratch, nblk, 0, 1, e_out, 0, 1.0, st);
 }
 

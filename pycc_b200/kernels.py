@@ -416,6 +416,33 @@ def update_amps(r1, r2, eo, ev, t1, t2, symmetrize=True, write_r2=True):
     return out
 
 
+def update_amps_rows(r1, half, eo, ev, t1, t2, i0, i1):
+    """Rows i in [i0,i1) of the fused symmetrise + Jacobi update (b200cc_update_amps_rows); t1 updated in full.
+    Returns a 2-element device tensor: sum (r2/D)^2 over the rows, sum (r1/D)^2."""
+    no, nv = t1.shape
+    out = torch.empty(2, dtype=F64, device=t2.device)
+    sc = _scratch(t2.device, 4096)
+    _lib.check(_lib.get().b200cc_update_amps_rows(no, nv, int(i0), int(i1), _lib.ptr(eo), _lib.ptr(ev),
+                                                  _lib.ptr(_c(r1, "r1")) if r1 is not None else None,
+                                                  _lib.ptr(_c(half, "r2")), _lib.ptr(_c(t1, "t1")), _lib.ptr(_c(t2, "t2")),
+                                                  _lib.ptr(out), _lib.ptr(sc), _lib.stream()), "b200cc_update_amps_rows")
+    return out
+
+
+def cc_energy_rows(fov, t1, t2, Loovv, i0, i1, with_singles):
+    """Partial energy of the rows i in [i0,i1) (b200cc_cc_energy_rows) as a 1-element device tensor."""
+    no, nv = t1.shape
+    if fov.stride(1) != 1 and nv > 1:
+        raise B200ccError("cc_energy: fov must be unit-stride along the virtual index")
+    out = torch.empty(1, dtype=F64, device=t2.device)
+    sc = _scratch(t2.device, 4096)
+    _lib.check(_lib.get().b200cc_cc_energy_rows(no, nv, int(i0), int(i1), int(bool(with_singles)), _lib.ptr(fov),
+                                                int(fov.stride(0)), _lib.ptr(_c(t1, "t1")), _lib.ptr(_c(t2, "t2")),
+                                                _lib.ptr(_c(Loovv, "Loovv")), _lib.ptr(out), _lib.ptr(sc), _lib.stream()),
+               "b200cc_cc_energy_rows")
+    return out
+
+
 def symmetrize_r2(r2):
     no, nv = r2.shape[0], r2.shape[2]
     _lib.check(_lib.get().b200cc_symmetrize_r2(no, nv, _lib.ptr(_c(r2, "r2")), _lib.stream()),
@@ -532,6 +559,50 @@ def t3_density_forms(no, nv, i, j, k0, nk, M3, t1, t2s, oovvs, fov, eo, ev, W2ab
     d.dvv, d.Dov, d.S1 = _lib.ptr(dvv), _lib.ptr(Dov), _lib.ptr(S1)
     d.scratch = _lib.ptr(sc)
     _lib.check(_lib.get().b200cc_t3_density_forms(C.byref(d), _lib.stream()), "b200cc_t3_density_forms")
+
+
+# ---- per-phase device timing of an iteration (bench.py "phases"; off unless B200CC_PHASES=1 / PHASES.on = True) ----------
+class _Phases:
+    """``with PHASES("ladder"):`` brackets a stretch of launches with CUDA events on the current stream; ``collect()``
+    synchronises and returns {name: [calls, ms]} accumulated since the last collect.  A no-op when off."""
+
+    def __init__(self):
+        self.on = bool(int(os.environ.get("B200CC_PHASES", "0")))
+        self._pending = []
+
+    class _Span:
+        def __init__(self, owner, name):
+            self.owner, self.name = owner, name
+
+        def __enter__(self):
+            if self.owner.on and torch.cuda.is_available():
+                self.a = torch.cuda.Event(enable_timing=True)
+                self.a.record()
+            return self
+
+        def __exit__(self, *exc):
+            if self.owner.on and torch.cuda.is_available():
+                b = torch.cuda.Event(enable_timing=True)
+                b.record()
+                self.owner._pending.append((self.name, self.a, b))
+            return False
+
+    def __call__(self, name):
+        return self._Span(self, name)
+
+    def collect(self):
+        out = {}
+        if self._pending:
+            torch.cuda.synchronize()
+            for name, a, b in self._pending:
+                k = out.setdefault(name, [0, 0.0])
+                k[0] += 1
+                k[1] += a.elapsed_time(b)
+            self._pending = []
+        return out
+
+
+PHASES = _Phases()
 
 
 def launch_count():

@@ -10,9 +10,12 @@ doubles) per CCSD iteration and ONE scalar all-reduce for E(T):
 * every other o^3v^3 / o^4v^2 / o^2v^3 term of r2 is split over an occupied index -- rank g computes
   r2[i_g] rows (F/W_mnij/Z/t1-driven terms) and r2[:, j_g] columns (ring terms, whose W_mbej/W_mbje
   intermediates are built only for the local j_g, so they are never gathered);
-* t1, t2, DIIS and the fused update are replicated: after the all-reduce every rank holds the same r2
-  and performs the same (deterministic) update, so the amplitudes stay bitwise identical on all ranks
-  and no all-gather of t2 is needed;
+* after the all-reduce every rank holds the same half residual; the HBM-bound tail of the iteration is then SHARDED
+  over the rows i_g of t2: symmetrise + Jacobi update + rms, the energy, and DIIS (history, B-matrix dots and the
+  extrapolation all on the rank's rows; the dots and the two scalars are summed with tiny all-reduces), and ONE
+  all-gather of the t2 rows (o^2v^2 doubles in total, 1/N per rank) ends the iteration.  t1 is replicated.  The kernels
+  are deterministic and every rank solves the same small DIIS system, so the gathered amplitudes are identical on all
+  ranks (``CCwfn.shard_update = False`` restores the fully replicated tail);
 * (T): the (i>=j>=k) triples are dealt round-robin (equal cost), energies summed with a scalar all-reduce.
 """
 from __future__ import annotations
@@ -66,6 +69,23 @@ class Comm:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t
 
+    def all_gather_rows(self, t):
+        """``t``: a contiguous tensor whose leading (occupied) dimension is split over the ranks by ``occ_range``; every
+        rank holds valid data in its own rows.  Afterwards every rank holds all rows.  NCCL with equal shares: one
+        all-gather; otherwise (gloo in the CPU tests, ragged shares) one broadcast per rank."""
+        n = t.shape[0]
+        bounds = [split(n, self.size, r) for r in range(self.size)]
+        lo, hi = bounds[self.rank]
+        if dist.get_backend(self.group) == "nccl" and len({b - a for a, b in bounds}) == 1 and hi > lo:
+            mine = t[lo:hi].clone()
+            dist.all_gather_into_tensor(t.view(-1), mine.view(-1), group=self.group)
+            return t
+        for r, (a, b) in enumerate(bounds):
+            if b > a:
+                dist.broadcast(t[a:b], src=dist.get_global_rank(self.group, r) if self.group is not None else r,
+                               group=self.group)
+        return t
+
     def all_reduce_max_scalar(self, x):
         t = torch.tensor([float(x)], dtype=torch.float64)
         if dist.get_backend(self.group) == "nccl":
@@ -88,6 +108,9 @@ class Serial:
         return 0, no
 
     def all_reduce_sum(self, t):
+        return t
+
+    def all_gather_rows(self, t):
         return t
 
     def barrier(self):

@@ -72,11 +72,25 @@ def concatenate(arrays):
 
 
 class helper_diis(object):
-    def __init__(self, t1, t2, max_diis, precision='DP'):
+    """Pulay DIIS with the reference's interface (utils.py:257-361): ``helper_diis(t1, t2, max_diis, precision)``,
+    ``add_error_vector(t1, t2)``, ``extrapolate(t1, t2) -> (t1, t2)``.  Iterates and error vectors are flat device
+    buffers; B is cached and only its newest row is computed (one fused multi-dot pass), the extrapolant is one fused
+    multi-axpy.
+
+    ``comm`` (parallel.Comm, more than one rank): the history, the dots and the extrapolation are SHARDED over the rows
+    i of t2 (``comm.occ_range``): a rank stores and touches only [t1 | t2[i0:i1]]; the B-matrix dots of the t2 rows are
+    summed over the ranks (t1, replicated, is counted once), every rank solves the same (m+1) x (m+1) system, writes
+    its rows of the extrapolant into the caller's t2 and the rows are all-gathered."""
+
+    def __init__(self, t1, t2, max_diis, precision='DP', comm=None):
         self.max_diis = max_diis
         self.precision = precision
-        self.shapes = (tuple(t1.shape), tuple(t2.shape))
-        self.n1, self.n2 = t1.numel(), t2.numel()
+        self.comm = comm if (comm is not None and comm.size > 1) else None
+        self.rows = self.comm.occ_range(t2.shape[0]) if self.comm is not None else (0, t2.shape[0])
+        i0, i1 = self.rows
+        self.shapes = (tuple(t1.shape), (i1 - i0,) + tuple(t2.shape[1:]))
+        self.n1 = t1.numel()
+        self.n2 = (i1 - i0) * (t2.numel() // max(t2.shape[0], 1))
         self.diis_size = 0
         self.last_coefficients = None
         if max_diis == 0:
@@ -90,9 +104,11 @@ class helper_diis(object):
 
     # -- flat storage -----------------------------------------------------------------------------
     def _flat(self, t1, t2):
+        i0, i1 = self.rows
         buf = torch.empty(self.n1 + self.n2, dtype=t2.dtype, device=t2.device)
         K.strided_axpby(buf[:self.n1].view(self.shapes[0]), t1, 1.0, 0.0)
-        K.strided_axpby(buf[self.n1:].view(self.shapes[1]), t2, 1.0, 0.0)
+        if self.n2:
+            K.strided_axpby(buf[self.n1:].view(self.shapes[1]), t2[i0:i1], 1.0, 0.0)
         return buf
 
     @staticmethod
@@ -102,6 +118,18 @@ class helper_diis(object):
 
     def _split(self, buf):
         return buf[:self.n1].view(self.shapes[0]), buf[self.n1:].view(self.shapes[1])
+
+    def _row_dots(self, err, others):
+        """err . other for every stored error vector, summed over the ranks' row shares (t1 counted once)."""
+        if self.comm is None:
+            return K.multi_dot(err, others).tolist()
+        m = len(others)
+        d1 = K.multi_dot(err[:self.n1], [x[:self.n1] for x in others])
+        d = torch.zeros(m, dtype=err.dtype, device=err.device)
+        if self.n2:
+            d = K.multi_dot(err[self.n1:], [x[self.n1:] for x in others])
+        self.comm.all_reduce_sum(d)
+        return K.axpbyz(1.0, d, 1.0, d1, d).tolist()
 
     # -- reference interface -----------------------------------------------------------------------
     def add_error_vector(self, t1, t2):
@@ -120,12 +148,13 @@ class helper_diis(object):
         # be longer -- max_diis > 16, or start_diis > max_diis, which the reference accepts, utils.py:317-320)
         new = self._ids[-1]
         for c0 in range(0, len(self.errors), 16):
-            dots = K.multi_dot(err, self.errors[c0:c0 + 16]).tolist()
+            dots = self._row_dots(err, self.errors[c0:c0 + 16])
             for eid, d in zip(self._ids[c0:c0 + 16], dots):
                 self._dots[(eid, new)] = self._dots[(new, eid)] = d
 
     def extrapolate(self, t1, t2):
-        """Pulay extrapolation (utils.py:297-361); returns (t1, t2) unchanged when max_diis == 0."""
+        """Pulay extrapolation (utils.py:297-361); returns (t1, t2) unchanged when max_diis == 0.  Sharded: the rows of
+        the extrapolant are written into the given ``t2`` and all-gathered (``t2`` is returned, complete on every rank)."""
         if self.max_diis == 0:
             return t1, t2
         if len(self.errors) > self.max_diis:
@@ -154,7 +183,14 @@ class helper_diis(object):
             K.multi_axpy(c[c0:min(m, c0 + 16)], self.vals[1 + c0:min(m, c0 + 16) + 1], part)
             K.axpbyz(1.0, new, 1.0, part, new)
         self.old = self._clone(new)
-        return self._split(new)
+        if self.comm is None:
+            return self._split(new)
+        n1, n2 = self._split(new)
+        i0, i1 = self.rows
+        if self.n2:
+            K.strided_axpby(t2[i0:i1], n2, 1.0, 0.0)
+        self.comm.all_gather_rows(t2)
+        return n1, t2
 
 
 # ---- solver text output: same lines as the reference prints (utils.py:200-254) -------------------------

@@ -336,6 +336,34 @@ class EmuLib:
         _vec(sumsq, 1)[0] = s
         return 0
 
+    def b200cc_update_amps_rows(self, no, nv, i0, i1, eo, ev, r1, r2, t1, t2, sumsq2, scratch, stream):
+        self._count("update_amps_rows", 2)
+        n2 = no * no * nv * nv
+        R2 = _vec(r2, n2).reshape(no, no, nv, nv)
+        full = (R2 + R2.transpose(1, 0, 3, 2))[i0:i1]
+        d2 = full / self._d2(no, nv, eo, ev)[i0:i1]
+        _vec(t2, n2).reshape(no, no, nv, nv)[i0:i1] += d2
+        out = _vec(sumsq2, 2)
+        out[0], out[1] = float(np.sum(d2 * d2)), 0.0
+        if r1:
+            D = _vec(eo, no)[:, None] - _vec(ev, nv)[None, :]
+            d1 = _vec(r1, no * nv).reshape(no, nv) / D
+            _vec(t1, no * nv)[...] += d1.ravel()
+            out[1] = float(np.sum(d1 * d1))
+        return 0
+
+    def b200cc_cc_energy_rows(self, no, nv, i0, i1, with_singles, fov, ldf, t1, t2, L, e_out, scratch, stream):
+        self._count("cc_energy_rows", 2)
+        f = _arr(fov, (no, nv), (ldf, 1))
+        T1 = _arr(t1, (no, nv), (nv, 1))
+        n2 = no * no * nv * nv
+        tau = _vec(t2, n2).reshape(no, no, nv, nv) + np.einsum("ia,jb->ijab", T1, T1)
+        e = np.sum(tau[i0:i1] * _vec(L, n2).reshape(no, no, nv, nv)[i0:i1])
+        if with_singles:
+            e += 2.0 * np.sum(f * T1)
+        _vec(e_out, 1)[0] = e
+        return 0
+
     def b200cc_symmetrize_r2(self, no, nv, r2, stream):
         self._count("symmetrize")
         R2 = _vec(r2, no * no * nv * nv).reshape(no, no, nv, nv)
