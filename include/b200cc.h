@@ -71,6 +71,15 @@ typedef struct {
                                       __syncthreads pipeline; kept as a cross-check); 4 = 128x128 warp-specialised
                                       (8 DMMA warps + 4 cp.async producer warps, mbarrier pipeline); 5 = 80x128 ditto;
                                       6 / 7 = as 4 / 5 with cp.async.bulk.tensor (TMA) operand staging, K-major aligned operands only */
+  /* optional THIRD and FOURTH K segment accumulated into the same tile (K3 = 0: none; K4 needs K3, K3 needs K2) -- TMA
+     kernels only.  Used by (T) to sum two of the six t3 products into ONE output array (W needs them at transposed row
+     pairs: the second product reads a constant copy of its operand with the pair transposed), which halves the t3
+     traffic through HBM.  With bcoords set and K3 > 0 a batch entry carries 8 slab indices {A1,B1,A2,B2,A3,B3,A4,B4}. */
+  int K3, K4;
+  const double *A3, *B3, *A4, *B4;
+  b200cc_i64 lda3, ldb3, lda4, ldb4;
+  b200cc_i64 strideA3, strideB3, strideA4, strideB4;
+  int nbA3, nbB3, nbA4, nbB4;
 } b200cc_gemm_desc;
 
 int b200cc_dgemm(const b200cc_gemm_desc* d, void* stream);
@@ -223,6 +232,10 @@ int b200cc_multi_axpy(b200cc_i64 n, int m, const double* c, const double* const*
  * GEMM outputs Q1..Q6 (each (nv*nv) x nv) produced by b200cc_dgemm:
  *   W[a,b,c] = Q1[a,b,c]+Q2[a,c,b]+Q3[c,a,b]+Q4[c,b,a]+Q5[b,c,a]+Q6[b,a,c]
  * Q: device, [ntrip][6][nv^3].  ijk: device int32 [ntrip][3].  fov: (no,nv) view, leading dim ldf.
+ * q_blocked is a set of layout flags: bit 0 = the arrays are cube-blocked (b200cc_t_q_size), bit 1 = PAIRED: only three
+ * arrays per triple, [ntrip][3][nv^3], in which the GEMM (K3/K4 segments of b200cc_gemm_desc) has already summed
+ *   R1[x,y,z] = Q1[x,y,z] + Q6[y,x,z],   R2[x,y,z] = Q2[x,y,z] + Q3[y,x,z],   R3[x,y,z] = Q4[x,y,z] + Q5[y,x,z],
+ *   W[a,b,c] = R1[a,b,c] + R2[a,c,b] + R3[c,b,a]     (half the t3 bytes through HBM; same flags for b200cc_t3_assemble).
  * et_out[0] (+)= sum over the batch (accumulate != 0 adds to the existing value).
  * scratch >= number of CTAs doubles (b200cc_t_energy_scratch).                                   */
 b200cc_i64 b200cc_t_energy_scratch(int nv, int ntrip);

@@ -47,6 +47,11 @@ class GemmDesc(C.Structure):
         ("bcoords", dptr),
         ("nbA1", C.c_int), ("nbB1", C.c_int), ("nbA2", C.c_int), ("nbB2", C.c_int),
         ("config", C.c_int),
+        ("K3", C.c_int), ("K4", C.c_int),
+        ("A3", dptr), ("B3", dptr), ("A4", dptr), ("B4", dptr),
+        ("lda3", i64), ("ldb3", i64), ("lda4", i64), ("ldb4", i64),
+        ("strideA3", i64), ("strideB3", i64), ("strideA4", i64), ("strideB4", i64),
+        ("nbA3", C.c_int), ("nbB3", C.c_int), ("nbA4", C.c_int), ("nbB4", C.c_int),
     ]
 
 

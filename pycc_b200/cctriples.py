@@ -19,6 +19,8 @@ signatures: ``t3c_ijk``, ``t3d_ijk`` (generic in the passed W blocks), ``t_vikin
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -27,6 +29,9 @@ from ._lib import B200ccError
 
 F64 = torch.float64
 _QCACHE = {}
+# t_tjl sums the six t3 products of a triple pairwise inside the GEMM (TriplesEngine(paired=True)); B200CC_T_PAIRED=0
+# restores the six-array form
+PAIRED = os.environ.get("B200CC_T_PAIRED", "1") != "0"
 
 # per term q: (occupied index of the <mb|ef> slab and of the t2[x] slab,
 #              (p,q) of t2[p,q] in the particle GEMM, (p,q) of Y[p,q] in the hole GEMM)
@@ -49,7 +54,7 @@ def triples_list(no):
 class TriplesEngine:
     """Owns the constant operands of the (T) GEMMs for one wavefunction state."""
 
-    def __init__(self, ccwfn, t1=None, t2=None, q_bytes=None, use_tma=True, cube_q=False, dressed=None):
+    def __init__(self, ccwfn, t1=None, t2=None, q_bytes=None, use_tma=True, cube_q=False, dressed=None, paired=False):
         """``dressed = (Wvvvo, Wovoo)``: build the t3 numerators of cctriples.py:50-62 from these blocks ([a,b,e,i] and
         [m,b,i,j], no permutational symmetry assumed -- the T1-dressed CC3 intermediates) instead of the integrals."""
         self.w = ccwfn
@@ -89,12 +94,25 @@ class TriplesEngine:
         if self.mixed:
             for t in (self.t2, self.t2p, self.Y):
                 K.register_constant(t, self._planes)
+        # PAIRED products (the energy path, FP64 TMA kernels): W needs Q1 and Q6 (Q2/Q3, Q4/Q5) at TRANSPOSED row pairs with
+        # the same column index, so the GEMM sums each pair in its accumulators -- four K segments per output, the second
+        # product reading constant copies of its operands with the pair transposed, GT[i,a,b,e] = G[i,b,a,e] (one more
+        # <mb|ef>-sized block per Hamiltonian) and t2pT[i,a,b,m] = t2p[i,b,a,m]: three arrays per triple instead of six go
+        # through HBM (48 v^3 bytes written + read per triple instead of 96 v^3), half as many GEMM units with twice the K.
+        self.paired = bool(paired) and self.tma and not self.mixed and dressed is None
+        if self.paired:
+            if "ovvv_ibae" not in H._derived:
+                H._derived["ovvv_ibae"] = K.permuted(self.ovvv, (0, 3, 2, 1))
+            self.GT = H._derived["ovvv_ibae"]
+            self.t2pT = K.permuted(self.t2, (0, 3, 2, 1))         # [i,a,b,m] = t2[i,m,b,a]
+        self.nq = 3 if self.paired else 6
         nv = self.nv
         # optional: the TMA GEMM can write Q as contiguous 8x8x8 cubes (4 KB runs for the energy kernel).  Measured
         # on B200 this is SLOWER (1.35 vs 2.66 TB/s in the energy kernel), so the plain (v,v,v) layout is the default.
         self.cube = bool(cube_q) and self.tma and not self.mixed
         self.qsz = K.q_size(nv, self.cube)
-        per = 6 * self.qsz * 8
+        self.qflags = (1 if self.cube else 0) | (2 if self.paired else 0)
+        per = self.nq * self.qsz * 8
         if q_bytes is None:
             q_bytes = 8 << 30
             if self.dev.type == "cuda":
@@ -115,7 +133,7 @@ class TriplesEngine:
     def qbuf(self, nb):
         """The Q workspace ([nb][6][v^3] doubles) is kept per device across engines (grow-only), so repeated
         (T) evaluations do not pay a multi-GB cudaMalloc each."""
-        need = nb * 6 * self.qsz
+        need = nb * self.nq * self.qsz
         buf = _QCACHE.get(self.dev)
         if buf is None or buf.numel() < need:
             _QCACHE.pop(self.dev, None)
@@ -146,6 +164,23 @@ class TriplesEngine:
         nb = len(trip)
         Q = self.qbuf(nb) if Q is None else Q
         no, nv = self.no, self.nv
+        if self.paired:
+            T = np.asarray(trip, dtype=np.int64).reshape(-1, 3)
+            co = np.empty((nb, 3, 8), dtype=np.int32)
+            for r, (qa, qb) in enumerate(((0, 5), (1, 2), (3, 4))):       # R1 = Q1 + Q6^T, R2 = Q2 + Q3^T, R3 = Q4 + Q5^T
+                for base, q in ((0, qa), (4, qb)):
+                    x, (p1, q1), (p2, q2) = _TERMS[q]
+                    co[:, r, base + 0] = T[:, x]
+                    co[:, r, base + 1] = T[:, p1] * no + T[:, q1]
+                    co[:, r, base + 2] = T[:, x]
+                    co[:, r, base + 3] = T[:, p2] * no + T[:, q2]
+            co = torch.from_numpy(co.reshape(nb * 3, 8)).to(self.dev)
+            v2, v3 = nv * nv, nv ** 3
+            K.dgemm(v2, nv, nv, self.G, nv, 0, self.t2, nv, 0, Q, nv, 1.0, 0.0, batch=3 * nb,
+                    sA=v3, sB=v2, sC=self.qsz, seg2=(self.t2p, no, self.Y, no, no, no * v2, nv * no),
+                    seg3=(self.GT, nv, self.t2, nv, nv, v3, v2), seg4=(self.t2pT, no, self.Y, no, no, no * v2, nv * no),
+                    bcoords=co, nbatch=(no, no * no) * 4, ksplit=1, out_cube_nv=nv if self.cube else 0)
+            return Q
         if self.tma:
             T = np.asarray(trip, dtype=np.int64).reshape(-1, 3)
             co = np.empty((nb, 6, 4), dtype=np.int32)
@@ -176,19 +211,19 @@ class TriplesEngine:
             Q = self.build_q(chunk)
             ijk = torch.tensor(np.asarray(chunk, dtype=np.int32).reshape(-1, 3), dtype=torch.int32).to(self.dev)
             K.t_energy_batch(self.no, self.nv, ijk, Q, self.t1, self.t2, self.oovv, self.fov,
-                             w.eps_o, w.eps_v, et, accumulate=True, blocked=self.cube)
+                             w.eps_o, w.eps_v, et, accumulate=True, blocked=self.qflags)
         return et
 
     def t3_parts(self, i, j, k, with_denom):
         """(connected, disconnected) t3 numerators of one triple as (v,v,v) tensors."""
         Q = self.build_q([(i, j, k)])
         return K.t3_assemble(self.no, self.nv, i, j, k, Q, self.t1, self.t2, self.oovv, self.fov,
-                             self.w.eps_o, self.w.eps_v, with_denom, blocked=self.cube)
+                             self.w.eps_o, self.w.eps_v, with_denom, blocked=self.qflags)
 
 
 def t_tjl(ccwfn, triples=None):
     """E(T), Lee-Rendell formulation (reference: cctriples.py:177-239).  Returns a 0-d device tensor."""
-    eng = TriplesEngine(ccwfn)
+    eng = TriplesEngine(ccwfn, paired=PAIRED)
     comm = getattr(ccwfn, "comm", None)
     trip = triples_list(ccwfn.no) if triples is None else list(triples)
     # i = j = k contributes exactly zero (the bracket vanishes identically): skip those tiles

@@ -456,6 +456,7 @@ class CCwfn(object):
         Fov = F[o, v]
         Loovv = H.derived("Loovv")
 
+        K.PHASES.mark("  Fme, Fae, Fmi")
         # ---------------- Fme = f_me + t_nf L_mnef                       (ccwfn.py:563-564)
         Fme = K.permuted(Fov, (0, 1))
         if not ccd:
@@ -485,11 +486,11 @@ class CCwfn(object):
             ct("ne,mnie->mi", t1, H.derived("Looov"), out=Fmi, alpha=1.0, beta=1.0)
         I["Fae"], I["Fmi"] = Fae, Fmi
         del tauh
+        K.PHASES.mark(None)
         if ni == 0 or not rings:           # rings=False: the one-body intermediates only (CC2's r1)
             return I
 
-        I["_span"] = K.PHASES("  Wmnij, W1/W2, Z")
-        I["_span"].__enter__()
+        K.PHASES.mark("  Wmnij")
         # ---------------- Wmnij[m,n,i_g,j]                               (ccwfn.py:596-603)
         ooov = H.block("ooov")
         Wfull = K.permuted(H.block("oooo"), (0, 1, 2, 3))
@@ -504,6 +505,7 @@ class CCwfn(object):
         # ---------------- ring intermediates in [j_g,b,m,e] layout (every o^3v^3 GEMM is then K-major x K-major)
         #   W1[j,b,m,e] = Wmbej[m,b,e,j]    (ccwfn.py:641-645)
         #   W2[j,b,m,e] = Wmbje[m,b,j,e]    (ccwfn.py:680-683)
+        K.PHASES.mark("  W1, W2: three o3v3 GEMMs + layouts")
         taut = K.build_tau(t1, t2, 0.5, 0.0 if ccd else 1.0)
         taut_jbnf = K.permuted(taut[i0:i1], (0, 3, 1, 2))         # [j,b,n,f] = tau(1/2,1)[j,n,f,b]
         del taut
@@ -516,6 +518,7 @@ class CCwfn(object):
         W2 = K.permuted(H.derived("ovov_mejb")[:, :, i0:i1, :], (2, 3, 0, 1), -1.0)
         ct("jbnf,menf->jbme", taut_jbnf, H.derived("oovv_mfne"), out=W2, alpha=1.0, beta=1.0)
         del taut_jbnf
+        K.PHASES.mark("  W1, W2: t1 terms (two passes over <mb|ef>)")
         if not ccd:
             ovvv = H.block("ovvv")
             t1g = t1[i0:i1]
@@ -533,9 +536,10 @@ class CCwfn(object):
         I["W1"], I["W2"] = W1, W2
 
         # ---------------- Z'[i_g,j,m,b] = Zmbij[m,b,i,j] = <mb|ef> tau_ijef   (ccwfn.py:715)
+        K.PHASES.mark("  Z = tau.<mb|ef> (o3v3)")
         if not ccd:
             I["Zijmb"] = ct("ijef,mbef->ijmb", A["tau"][i0:i1], H.block("ovvv"))
-        I.pop("_span").__exit__(None, None, None)
+        K.PHASES.mark(None)
         return I
 
     def _Loovv_emnf(self, m0, m1):
@@ -670,6 +674,7 @@ class CCwfn(object):
             return r2
         rg = r2[i0:i1]                                                             # rows i_g (contiguous)
         t2g, t1g = t2[i0:i1], t1[i0:i1]
+        K.PHASES.mark("r2: F and Wmnij terms")
         # t2_ijae (F_be - 1/2 t_mb F_me)                                           923-925
         Fx = I["Fae"]
         if not ccd:
@@ -686,8 +691,7 @@ class CCwfn(object):
         # 1/2 tau_mnab W_mnij                                                       930
         ct("mnij,mnab->ijab", I["Wmnij"], A["tau"], out=rg, alpha=0.5, beta=1.0)
         # ring terms, columns j_g, in [i,a,j,b] layout                              933-935
-        span = K.PHASES("ring terms")
-        span.__enter__()
+        K.PHASES.mark("r2: ring terms (three o3v3 GEMMs)")
         R = ct("iame,jbme->iajb", A["s_iame"], I["W1"])          # (2t2 - t2^T) W_mbej
         ct("iame,jbme->iajb", A["t2_iame"], I["W2"], out=R, alpha=1.0, beta=1.0)   # t2 W_mbje^T
         K.strided_axpby(r2[:, i0:i1], R.permute(0, 2, 1, 3), 1.0, 1.0)
@@ -695,7 +699,7 @@ class CCwfn(object):
         ct("jame,ibme->jaib", t2_jame, I["W2"], out=R, alpha=1.0, beta=0.0)        # t2_mjae W_mbie
         K.strided_axpby(rg, R.permute(2, 0, 1, 3), 1.0, 1.0)
         del R, t2_jame
-        span.__exit__(None, None, None)
+        K.PHASES.mark("r2: t1 terms (Z, <mb|ej>, <ma|je>, <ab|ej>)")
         if not ccd:
             ooov, ovov = H.block("ooov"), H.block("ovov")
             # - t_ma ( Z_mbij + <mb|ij> + t_ie <mb|ej> )  as one batched product    932, 940, 936-937
@@ -714,6 +718,7 @@ class CCwfn(object):
                     batch=ni * no, sA=no * nv, sB=0, sC=nv * nv)
             # t_ie <ab|ej>,  <ab|ej> = <ja|be>                                        939
             ct("ie,jabe->ijab", t1g, H.block("ovvv"), out=rg, alpha=1.0, beta=1.0)
+        K.PHASES.mark(None)
         return r2
 
     def _ladder(self, tau, r2, symmetric=False):

@@ -53,6 +53,15 @@ struct KParams {
   const int* bcoords;
   int nbA1, nbB1, nbA2, nbB2;
   int cube_nv;   // > 0: C written as contiguous 8x8x8 cubes of (x = row / nv, y = row % nv, z = col)
+  // third / fourth K segment (TMA kernels only): kt2, kt3 = cumulative k-tile counts after segments 2 and 3
+  int K3, K4, kt2, kt3, bc_stride;
+  const double *A3, *B3, *A4, *B4;
+  i64 lda3, ldb3, lda4, ldb4, sA3, sB3, sA4, sB4;
+  int nbA3, nbB3, nbA4, nbB4;
+};
+
+struct alignas(64) TMapSet {
+  CUtensorMap a[4], b[4];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -670,8 +679,7 @@ __device__ __forceinline__ void load_frags_swz(const unsigned char* __restrict__
 
 template <class CF>
 __global__ void __launch_bounds__(CF::NT + WS_PRODUCER_THREADS, 1)
-    dgemm_tma_kernel(const KParams p, const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
-                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2) {
+    dgemm_tma_kernel(const KParams p, const __grid_constant__ TMapSet tm) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   constexpr int MI = CF::MI, NI = CF::NI;
   constexpr int A_BYTES = CF::BM * 128, B_BYTES = CF::BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
@@ -699,10 +707,15 @@ __global__ void __launch_bounds__(CF::NT + WS_PRODUCER_THREADS, 1)
       uint32_t phase = 0;
       for (int u = blockIdx.x; u < p.units; u += G) {
         const Unit w = decode_unit<CF>(p, u);
-        int bA1 = p.sA1 ? w.b : 0, bB1 = p.sB1 ? w.b : 0, bA2 = p.sA2 ? w.b : 0, bB2 = p.sB2 ? w.b : 0;
-        if (p.bcoords) {   // (T): each batch entry names its own slab of every operand
-          const int4 c = reinterpret_cast<const int4*>(p.bcoords)[w.b];
-          bA1 = c.x; bB1 = c.y; bA2 = c.z; bB2 = c.w;
+        int bA[4] = {p.sA1 ? w.b : 0, p.sA2 ? w.b : 0, p.sA3 ? w.b : 0, p.sA4 ? w.b : 0};
+        int bB[4] = {p.sB1 ? w.b : 0, p.sB2 ? w.b : 0, p.sB3 ? w.b : 0, p.sB4 ? w.b : 0};
+        if (p.bcoords) {   // (T): each batch entry names its own slab of every operand: {A1,B1,A2,B2[,A3,B3,A4,B4]}
+          const int4 c = reinterpret_cast<const int4*>(p.bcoords + (i64)w.b * p.bc_stride)[0];
+          bA[0] = c.x; bB[0] = c.y; bA[1] = c.z; bB[1] = c.w;
+          if (p.bc_stride == 8) {
+            const int4 e = reinterpret_cast<const int4*>(p.bcoords + (i64)w.b * 8)[1];
+            bA[2] = e.x; bB[2] = e.y; bA[3] = e.z; bB[3] = e.w;
+          }
         }
         for (int t = 0; t < w.nkt; ++t) {
           mbar_wait(empty_bar + stage, phase ^ 1u);
@@ -710,13 +723,10 @@ __global__ void __launch_bounds__(CF::NT + WS_PRODUCER_THREADS, 1)
           unsigned char* Bs = As + A_BYTES;
           mbar_expect_tx(full_bar + stage, STAGE_BYTES);
           const int kt = w.kt_begin + t;
-          if (kt < p.kt1) {
-            tma_load_3d(As, &tmA1, kt * BK, w.m0, bA1, full_bar + stage);
-            tma_load_3d(Bs, &tmB1, kt * BK, w.n0, bB1, full_bar + stage);
-          } else {
-            tma_load_3d(As, &tmA2, (kt - p.kt1) * BK, w.m0, bA2, full_bar + stage);
-            tma_load_3d(Bs, &tmB2, (kt - p.kt1) * BK, w.n0, bB2, full_bar + stage);
-          }
+          const int seg = (kt >= p.kt1 ? 1 : 0) + (kt >= p.kt2 ? 1 : 0) + (kt >= p.kt3 ? 1 : 0);
+          const int k0 = (kt - (seg == 0 ? 0 : (seg == 1 ? p.kt1 : (seg == 2 ? p.kt2 : p.kt3)))) * BK;
+          tma_load_3d(As, &tm.a[seg], k0, w.m0, bA[seg], full_bar + stage);
+          tma_load_3d(Bs, &tm.b[seg], k0, w.n0, bB[seg], full_bar + stage);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -868,16 +878,22 @@ static int launch_tma(KParams& p, cudaStream_t st) {
   p.tiles = (int)tiles;
   p.units = (int)units;
   p.nfast = p.tiles_n < p.tiles_m ? 1 : 0;
-  CUtensorMap tA1, tB1, tA2, tB2;
+  TMapSet tm;
   const bool bc = p.bcoords != nullptr;
-  if (make_tmap(&tA1, p.A1, p.M, p.K1, p.lda1, p.sA1, bc ? p.nbA1 : p.batch, CF::BM)) return 1;
-  if (make_tmap(&tB1, p.B1, p.N, p.K1, p.ldb1, p.sB1, bc ? p.nbB1 : p.batch, CF::BN)) return 1;
+  if (make_tmap(&tm.a[0], p.A1, p.M, p.K1, p.lda1, p.sA1, bc ? p.nbA1 : p.batch, CF::BM)) return 1;
+  if (make_tmap(&tm.b[0], p.B1, p.N, p.K1, p.ldb1, p.sB1, bc ? p.nbB1 : p.batch, CF::BN)) return 1;
+  for (int sgm = 1; sgm < 4; ++sgm) { tm.a[sgm] = tm.a[0]; tm.b[sgm] = tm.b[0]; }
   if (p.K2 > 0) {
-    if (make_tmap(&tA2, p.A2, p.M, p.K2, p.lda2, p.sA2, bc ? p.nbA2 : p.batch, CF::BM)) return 1;
-    if (make_tmap(&tB2, p.B2, p.N, p.K2, p.ldb2, p.sB2, bc ? p.nbB2 : p.batch, CF::BN)) return 1;
-  } else {
-    tA2 = tA1;
-    tB2 = tB1;
+    if (make_tmap(&tm.a[1], p.A2, p.M, p.K2, p.lda2, p.sA2, bc ? p.nbA2 : p.batch, CF::BM)) return 1;
+    if (make_tmap(&tm.b[1], p.B2, p.N, p.K2, p.ldb2, p.sB2, bc ? p.nbB2 : p.batch, CF::BN)) return 1;
+  }
+  if (p.K3 > 0) {
+    if (make_tmap(&tm.a[2], p.A3, p.M, p.K3, p.lda3, p.sA3, bc ? p.nbA3 : p.batch, CF::BM)) return 1;
+    if (make_tmap(&tm.b[2], p.B3, p.N, p.K3, p.ldb3, p.sB3, bc ? p.nbB3 : p.batch, CF::BN)) return 1;
+  }
+  if (p.K4 > 0) {
+    if (make_tmap(&tm.a[3], p.A4, p.M, p.K4, p.lda4, p.sA4, bc ? p.nbA4 : p.batch, CF::BM)) return 1;
+    if (make_tmap(&tm.b[3], p.B4, p.N, p.K4, p.ldb4, p.sB4, bc ? p.nbB4 : p.batch, CF::BN)) return 1;
   }
   constexpr int SMEM = STAGES * (CF::BM + CF::BN) * 128 + 2 * STAGES * (int)sizeof(uint64_t) + 1024;
   static bool configured = false;
@@ -886,7 +902,7 @@ static int launch_tma(KParams& p, cudaStream_t st) {
     configured = true;
   }
   const int grid = pick_grid(p);
-  dgemm_tma_kernel<CF><<<grid, CF::NT + WS_PRODUCER_THREADS, SMEM, st>>>(p, tA1, tB1, tA2, tB2);
+  dgemm_tma_kernel<CF><<<grid, CF::NT + WS_PRODUCER_THREADS, SMEM, st>>>(p, tm);
   return check_launch("dgemm_tma_kernel");
 }
 
@@ -989,6 +1005,19 @@ extern "C" int b200cc_dgemm(const b200cc_gemm_desc* d, void* stream) {
   p.table = d->table;
   p.kt1 = (d->K1 + BK - 1) / BK;
   p.kt_total = p.kt1 + (d->K2 + BK - 1) / BK;
+  // optional third / fourth K segment (the paired (T) products): TMA kernels only, checked below
+  p.K3 = d->K3 > 0 ? d->K3 : 0; p.K4 = (p.K3 > 0 && d->K4 > 0) ? d->K4 : 0;
+  p.A3 = d->A3; p.B3 = d->B3; p.A4 = d->A4; p.B4 = d->B4;
+  p.lda3 = d->lda3; p.ldb3 = d->ldb3; p.lda4 = d->lda4; p.ldb4 = d->ldb4;
+  p.sA3 = p.K3 > 0 ? d->strideA3 : 0; p.sB3 = p.K3 > 0 ? d->strideB3 : 0;
+  p.sA4 = p.K4 > 0 ? d->strideA4 : 0; p.sB4 = p.K4 > 0 ? d->strideB4 : 0;
+  p.nbA3 = d->nbA3; p.nbB3 = d->nbB3; p.nbA4 = d->nbA4; p.nbB4 = d->nbB4;
+  p.kt2 = p.kt_total;
+  p.kt_total += (p.K3 + BK - 1) / BK;
+  p.kt3 = p.kt_total;
+  p.kt_total += (p.K4 + BK - 1) / BK;
+  p.bc_stride = p.K3 > 0 ? 8 : 4;
+  if (d->K3 > 0 && d->K2 <= 0) { set_error("b200cc_dgemm: a third K segment needs the second one"); return 1; }
   p.ksplit = ksplit; p.batch = d->batch; p.ws = d->workspace;
   p.kt_per_split = (p.kt_total + ksplit - 1) / ksplit;
   if (p.kt_per_split < 1) p.kt_per_split = 1;
@@ -1017,7 +1046,15 @@ extern "C" int b200cc_dgemm(const b200cc_gemm_desc* d, void* stream) {
   const bool v2 = va && vb;
   const int ta = d->transA ? 1 : 0, tb = d->transB ? 1 : 0;
 
-  const bool tma_ok = !ta && !tb && !d->table && v2 && d->K1 > 0;
+  bool seg34 = true;
+  if (p.K3 > 0)
+    seg34 = al16(p.A3) && al16(p.B3) && even(p.lda3) && even(p.ldb3) && even(p.sA3) && even(p.sB3) &&
+            (p.K4 == 0 || (al16(p.A4) && al16(p.B4) && even(p.lda4) && even(p.ldb4) && even(p.sA4) && even(p.sB4)));
+  const bool tma_ok = !ta && !tb && !d->table && v2 && d->K1 > 0 && seg34;
+  if (p.K3 > 0 && !tma_ok) {
+    set_error("b200cc_dgemm: K3/K4 segments need the TMA path (K-major, 16-byte aligned operands and strides, no table)");
+    return 1;
+  }
   if (d->bcoords && !tma_ok) {
     set_error("b200cc_dgemm: bcoords needs the TMA path (K-major, 16-byte aligned operands and strides)");
     return 1;
@@ -1043,6 +1080,7 @@ extern "C" int b200cc_dgemm(const b200cc_gemm_desc* d, void* stream) {
     set_error("b200cc_dgemm: out_cube_nv needs a TMA kernel (config 6/7), beta = 0 and no split-K");
     return 1;
   }
+  if (p.K3 > 0 && cfg != 6 && cfg != 7) { set_error("b200cc_dgemm: K3/K4 segments are only implemented by the TMA kernels (config 6/7)"); return 1; }
   if (d->bcoords && cfg != 6 && cfg != 7) { set_error("b200cc_dgemm: bcoords is only implemented by the TMA kernels (config 6/7)"); return 1; }
   int rc;
   if (cfg == 2) rc = dispatch<CfgB, false>(p, ta, tb, v2, st);

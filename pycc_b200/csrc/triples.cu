@@ -18,6 +18,8 @@ constexpr int TT = 8;  // cube edge
 struct TArgs {
   int no, nv, nt;
   int blocked;   // Q stored as contiguous 8x8x8 cubes (written so by the TMA GEMM epilogue), else plain (v,v,v)
+  int paired;    // 3 arrays per triple instead of 6: R1[x,y,z] = Q1[x,y,z] + Q6[y,x,z], R2 = Q2 + Q3^T, R3 = Q4 + Q5^T (the
+                 // GEMM summed each pair in its accumulators), W[a,b,c] = R1[a,b,c] + R2[a,c,b] + R3[c,b,a]
   const int* ijk;
   const double* Q;
   const double *t1, *t2, *oovv, *fov, *eo, *ev;
@@ -36,7 +38,10 @@ __host__ __device__ __forceinline__ i64 qsize(int blocked, int nv) {
   return nc8 * nc8 * nc8 * 512;
 }
 
-__device__ __forceinline__ double wsum(const double* __restrict__ Q, i64 v3, int blocked, int nv, int x, int y, int z) {
+__device__ __forceinline__ double wsum(const double* __restrict__ Q, i64 v3, int blocked, int nv, int x, int y, int z,
+                                       int paired = 0) {
+  if (paired)
+    return Q[qoff(blocked, nv, x, y, z)] + Q[v3 + qoff(blocked, nv, x, z, y)] + Q[2 * v3 + qoff(blocked, nv, z, y, x)];
   return Q[qoff(blocked, nv, x, y, z)] + Q[v3 + qoff(blocked, nv, x, z, y)] + Q[2 * v3 + qoff(blocked, nv, z, x, y)] +
          Q[3 * v3 + qoff(blocked, nv, z, y, x)] + Q[4 * v3 + qoff(blocked, nv, y, z, x)] +
          Q[5 * v3 + qoff(blocked, nv, y, x, z)];
@@ -73,8 +78,11 @@ __device__ __forceinline__ Disc make_disc(const TArgs& p, int i, int j, int k) {
 // (Measured on B200: 2.66 TB/s of Q traffic vs 1.93 TB/s for direct per-thread gathers; issuing all 36
 //  loads up front at one CTA per SM was slower, 2.04 TB/s.)
 constexpr int SA = 73, SB = 9, WTILE = 8 * SA;   // padded tile pitch (doubles)
+// array n of NQ (6 plain, 3 paired) has the index order of Q_{QSRC(n)}: paired R1, R2, R3 are laid out like Q1, Q2, Q4
+template <int NQ>
+__host__ __device__ constexpr int qsrc(int n) { return NQ == 6 ? n : (n == 2 ? 3 : n); }
 
-template <bool BLOCKED, bool HOIST>
+template <bool BLOCKED, bool HOIST, int NQ>
 __global__ void __launch_bounds__(512, 2) t_energy_kernel(const TArgs p, double* scratch) {
   __shared__ double Wsm[6][WTILE];
   __shared__ double red[16];
@@ -89,7 +97,7 @@ __global__ void __launch_bounds__(512, 2) t_energy_kernel(const TArgs p, double*
   const int i = p.ijk[3 * trip], j = p.ijk[3 * trip + 1], k = p.ijk[3 * trip + 2];
   const int nv = p.nv;
   const i64 v3 = qsize(p.blocked, nv);
-  const double* Q = p.Q + (i64)trip * 6 * v3;
+  const double* Q = p.Q + (i64)trip * NQ * v3;
   const int T[3] = {TA * TT, TB * TT, TC * TT};
   const int u[3] = {(int)(threadIdx.x >> 6), (int)((threadIdx.x >> 3) & 7), (int)(threadIdx.x & 7)};
 
@@ -110,12 +118,12 @@ __global__ void __launch_bounds__(512, 2) t_energy_kernel(const TArgs p, double*
     dsto[r] = l[0] * SA + l[1] * SB + l[2];
   }
 #pragma unroll
-  for (int n = 0; n < 6; ++n) {
+  for (int n = 0; n < NQ; ++n) {
     const double* Qn = Q + (i64)n * v3;
 #pragma unroll
     for (int P = 0; P < 6; ++P) {
       // Q_n coordinate k of W[P(a,b,c)] is cube axis rho_k = PERM[P][PI[n][k]]
-      const int r0 = PERM[P][PI[n][0]], r1 = PERM[P][PI[n][1]], r2 = PERM[P][PI[n][2]];
+      const int r0 = PERM[P][PI[qsrc<NQ>(n)][0]], r1 = PERM[P][PI[qsrc<NQ>(n)][1]], r2 = PERM[P][PI[qsrc<NQ>(n)][2]];
       double val = 0.0;
       double* dst;
       if (HOIST) {
@@ -182,7 +190,7 @@ __global__ void __launch_bounds__(256) t3_assemble_kernel(const TArgs p, int i, 
     const int c = (int)(e % nv);
     const int b = (int)((e / nv) % nv);
     const int a = (int)(e / ((i64)nv * nv));
-    double w = wsum(p.Q, qs, p.blocked, nv, a, b, c);   // t3c_ijk numerator
+    double w = wsum(p.Q, qs, p.blocked, nv, a, b, c, p.paired);   // t3c_ijk numerator
     double v = D(a, b, c);                   // t3d_ijk numerator
     if (with_denom) {
       const double den = p.eo[i] + p.eo[j] + p.eo[k] - p.ev[a] - p.ev[b] - p.ev[c];
@@ -244,6 +252,7 @@ __device__ __forceinline__ double te_disc(const double* tiles, const double* vec
          tl(3, X, Y) * vc(5, Z) + tl(4, X, Z) * vc(4, Y) + tl(5, Y, Z) * vc(3, X);
 }
 
+template <int NQ>
 __global__ void __launch_bounds__(512, 2) t_energy_cp_kernel(const TArgs p, double* scratch) {
   extern __shared__ double raw[];    // [3][6][512] | tiles | vecs
   __shared__ double red[16];
@@ -259,7 +268,7 @@ __global__ void __launch_bounds__(512, 2) t_energy_cp_kernel(const TArgs p, doub
   const int i = p.ijk[3 * trip], j = p.ijk[3 * trip + 1], k = p.ijk[3 * trip + 2];
   const int nv = p.nv, no = p.no;
   const i64 vv = (i64)nv * nv, v3 = vv * nv;
-  const double* Q = p.Q + (i64)trip * 6 * v3;
+  const double* Q = p.Q + (i64)trip * NQ * v3;
   const int T[3] = {TA * TT, TB * TT, TC * TT};
   const int u[3] = {(int)(threadIdx.x >> 6), (int)((threadIdx.x >> 3) & 7), (int)(threadIdx.x & 7)};
   constexpr int PERM[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
@@ -304,14 +313,14 @@ __global__ void __launch_bounds__(512, 2) t_energy_cp_kernel(const TArgs p, doub
   }
   double W[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
+  for (int half = 0; half < NQ / 3; ++half) {      // 18 source blocks per round: two rounds plain, one paired
 #pragma unroll
     for (int nn = 0; nn < 3; ++nn) {
       const int n = half * 3 + nn;
       const double* Qn = Q + (i64)n * v3;
 #pragma unroll
       for (int P = 0; P < 6; ++P) {
-        const int r0 = PERM[P][PI[n][0]], r1 = PERM[P][PI[n][1]], r2 = PERM[P][PI[n][2]];
+        const int r0 = PERM[P][PI[qsrc<NQ>(n)][0]], r1 = PERM[P][PI[qsrc<NQ>(n)][1]], r2 = PERM[P][PI[qsrc<NQ>(n)][2]];
         const i64 origin = ((i64)T[r0] * nv + T[r1]) * nv + T[r2];
         const bool ok = (u[0] < nv - T[r0]) & (u[1] < nv - T[r1]) & (u[2] < nv - T[r2]);
         cp_async8(raw + (nn * 6 + P) * 512 + dsto[r0 * 2 + (r1 > r2 ? 1 : 0)], Qn + (ok ? origin + tpart : 0), ok);
@@ -322,7 +331,7 @@ __global__ void __launch_bounds__(512, 2) t_energy_cp_kernel(const TArgs p, doub
     __syncthreads();
 #pragma unroll
     for (int P = 0; P < 6; ++P) W[P] += raw[P * 512 + s] + raw[(6 + P) * 512 + s] + raw[(12 + P) * 512 + s];
-    if (half == 0) __syncthreads();   // everyone has read round 0 before round 1 overwrites it
+    if (half + 1 < NQ / 3) __syncthreads();   // everyone has read this round before the next overwrites it
   }
 
   const int l[3] = {u[0], u[1], u[2]};
@@ -665,7 +674,7 @@ extern "C" int b200cc_t_energy_batch(int no, int nv, int ntrip, const int* ijk, 
   if (ntrip > 65535) { set_error("b200cc_t_energy_batch: ntrip > 65535"); return 1; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TArgs p;
-  p.no = no; p.nv = nv; p.nt = (nv + TT - 1) / TT; p.blocked = q_blocked ? 1 : 0;
+  p.no = no; p.nv = nv; p.nt = (nv + TT - 1) / TT; p.blocked = (q_blocked & 1) ? 1 : 0; p.paired = (q_blocked & 2) ? 1 : 0;
   p.ijk = ijk; p.Q = Q; p.t1 = t1; p.t2 = t2; p.oovv = oovv; p.fov = fov; p.eo = eo; p.ev = ev; p.ldf = ldf;
   const int ncube = sorted_cubes(nv);
   // hoisted index arithmetic measured 2.47 vs 2.03 TB/s on B200 (profiles/t_probe_r01_hoist.log); B200CC_T_HOIST=0 selects
@@ -676,14 +685,20 @@ extern "C" int b200cc_t_energy_batch(int no, int nv, int ntrip, const int* ijk, 
   constexpr int TE_SMEM = TE_DOUBLES * (int)sizeof(double);
   static bool configured = false;
   if (!configured) {
-    B200CC_CUDA_OK(cudaFuncSetAttribute(t_energy_cp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TE_SMEM));
+    B200CC_CUDA_OK(cudaFuncSetAttribute(t_energy_cp_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, TE_SMEM));
+    B200CC_CUDA_OK(cudaFuncSetAttribute(t_energy_cp_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TE_SMEM));
     // (forcing the largest shared-memory carve-out was measured much SLOWER, 1.86 vs 2.88 TB/s: cp.async.ca wants its L1)
     configured = true;
   }
-  if (p.blocked) t_energy_kernel<true, false><<<dim3(ncube, ntrip), 512, 0, st>>>(p, scratch);
-  else if (use_cp) t_energy_cp_kernel<<<dim3(ncube, ntrip), 512, TE_SMEM, st>>>(p, scratch);
-  else if (hoist) t_energy_kernel<false, true><<<dim3(ncube, ntrip), 512, 0, st>>>(p, scratch);
-  else t_energy_kernel<false, false><<<dim3(ncube, ntrip), 512, 0, st>>>(p, scratch);
+  const dim3 grid(ncube, ntrip);
+  if (p.paired) {
+    if (p.blocked) t_energy_kernel<true, false, 3><<<grid, 512, 0, st>>>(p, scratch);
+    else if (use_cp) t_energy_cp_kernel<3><<<grid, 512, TE_SMEM, st>>>(p, scratch);
+    else t_energy_kernel<false, true, 3><<<grid, 512, 0, st>>>(p, scratch);
+  } else if (p.blocked) t_energy_kernel<true, false, 6><<<grid, 512, 0, st>>>(p, scratch);
+  else if (use_cp) t_energy_cp_kernel<6><<<grid, 512, TE_SMEM, st>>>(p, scratch);
+  else if (hoist) t_energy_kernel<false, true, 6><<<grid, 512, 0, st>>>(p, scratch);
+  else t_energy_kernel<false, false, 6><<<grid, 512, 0, st>>>(p, scratch);
   if (check_launch("t_energy_kernel")) return 1;
   const i64 nparts = (i64)ncube * ntrip;
   if (nparts > 2147483647LL) { set_error("b200cc_t_energy_batch: too many partials"); return 1; }
@@ -697,7 +712,7 @@ extern "C" int b200cc_t3_assemble(int no, int nv, int i, int j, int k, const dou
                                   double* v3_out, void* stream) {
   if (nv <= 0) return 0;
   TArgs p;
-  p.no = no; p.nv = nv; p.nt = (nv + TT - 1) / TT; p.blocked = q_blocked ? 1 : 0;
+  p.no = no; p.nv = nv; p.nt = (nv + TT - 1) / TT; p.blocked = (q_blocked & 1) ? 1 : 0; p.paired = (q_blocked & 2) ? 1 : 0;
   p.ijk = nullptr; p.Q = Q; p.t1 = t1; p.t2 = t2; p.oovv = oovv; p.fov = fov; p.eo = eo; p.ev = ev; p.ldf = ldf;
   const i64 v3 = (i64)nv * nv * nv;
   i64 blocks = (v3 + 255) / 256;

@@ -223,15 +223,17 @@ def _mixed_eligible(M, N, K, A, B, transA, transB, batch, seg2, table, bcoords, 
 
 def dgemm(M, N, K, A, lda, transA, B, ldb, transB, Cmat, ldc, alpha=1.0, beta=0.0,
           batch=1, sA=0, sB=0, sC=0, seg2=None, table=None, table_align16=False, ksplit=None, config=0,
-          bcoords=None, nbatch=None, out_cube_nv=0, mp_kchunk=None):
+          bcoords=None, nbatch=None, out_cube_nv=0, mp_kchunk=None, seg3=None, seg4=None):
     """C[b] = alpha * (opA[b] opB[b]^T [+ second K segment]) + beta * C[b]; see b200cc_dgemm.
     ``mp_kchunk``: FP32 accumulation run when the product is routed to the mixed-precision kernel.
 
-    A, B, Cmat: tensor, (tensor, element offset) or raw address.  seg2 = (A2, lda2, B2, ldb2, K2, sA2, sB2).
+    A, B, Cmat: tensor, (tensor, element offset) or raw address.  seg2 = (A2, lda2, B2, ldb2, K2, sA2, sB2);
+    seg3 / seg4 likewise (TMA kernels only; with bcoords each batch entry then carries 8 slab indices and ``nbatch``
+    8 slab counts).
     """
     if M == 0 or N == 0 or batch == 0:
         return
-    if _mixed_eligible(M, N, K, A, B, transA, transB, batch, seg2, table, bcoords, out_cube_nv):
+    if seg3 is None and _mixed_eligible(M, N, K, A, B, transA, transB, batch, seg2, table, bcoords, out_cube_nv):
         # with bcoords every operand is a stack of slabs (counts in nbatch) that the batch entries index
         nA1, nB1, nA2, nB2 = (int(x) for x in nbatch) if bcoords is not None else (batch,) * 4
         Ah, Al, lpa = _split_operand(A, M, K, lda, nA1, sA)
@@ -261,15 +263,26 @@ def dgemm(M, N, K, A, lda, transA, B, ldb, transB, Cmat, ldc, alpha=1.0, beta=0.
     d.alpha, d.beta, d.batch = float(alpha), float(beta), int(batch)
     d.table = _lib.ptr(table) if table is not None else None
     d.table_align16 = int(bool(table_align16))
+    K34 = 0
+    for n_, seg in ((3, seg3), (4, seg4)):
+        if seg is not None:
+            As, ldas, Bs, ldbs, Ks, sAs, sBs = seg
+            setattr(d, "A%d" % n_, _addr(As)); setattr(d, "B%d" % n_, _addr(Bs))
+            setattr(d, "lda%d" % n_, int(ldas)); setattr(d, "ldb%d" % n_, int(ldbs)); setattr(d, "K%d" % n_, int(Ks))
+            setattr(d, "strideA%d" % n_, int(sAs)); setattr(d, "strideB%d" % n_, int(sBs))
+            K34 += int(Ks)
     if ksplit is None:
-        ksplit = auto_ksplit(M, N, K + K2, batch)
+        ksplit = auto_ksplit(M, N, K + K2 + K34, batch)
     d.ksplit = int(ksplit)
     d.config = int(config) if config else DEFAULT_GEMM_CONFIG
     d.out_cube_nv = int(out_cube_nv)
     if bcoords is not None:
         # per-batch operand indices (int32 [batch,4]) + the extent of each operand's batch dimension
         d.bcoords = _lib.ptr(bcoords)
-        d.nbA1, d.nbB1, d.nbA2, d.nbB2 = (int(x) for x in nbatch)
+        nb = [int(x) for x in nbatch]
+        d.nbA1, d.nbB1, d.nbA2, d.nbB2 = nb[:4]
+        if len(nb) == 8:
+            d.nbA3, d.nbB3, d.nbA4, d.nbB4 = nb[4:]
     ws = None
     if ksplit > 1:
         dev = _dev(table if table is not None else Cmat)
@@ -496,14 +509,15 @@ def multi_axpy(coeffs, xs, out):
 
 def q_size(nv, blocked):
     """doubles per Q array (plain v^3, or padded to whole 8x8x8 cubes when blocked)"""
-    return int(_lib.get().b200cc_t_q_size(int(nv), int(bool(blocked))))
+    return int(_lib.get().b200cc_t_q_size(int(nv), int(blocked) & 1))
 
 
 def t_energy_batch(no, nv, ijk, Q, t1, t2, oovv, fov, eo, ev, et, accumulate=True, blocked=False):
+    """``blocked``: Q layout flags (bit 0 = cube-blocked arrays, bit 1 = paired: three summed arrays per triple)."""
     ntrip = ijk.shape[0]
     n = int(_lib.get().b200cc_t_energy_scratch(nv, ntrip))
     sc = _scratch(Q.device, max(n, 1))
-    _lib.check(_lib.get().b200cc_t_energy_batch(no, nv, ntrip, _lib.ptr(ijk), _lib.ptr(Q), int(bool(blocked)),
+    _lib.check(_lib.get().b200cc_t_energy_batch(no, nv, ntrip, _lib.ptr(ijk), _lib.ptr(Q), int(blocked),
                                                 _lib.ptr(_c(t1, "t1")),
                                                 _lib.ptr(_c(t2, "t2")), _lib.ptr(_c(oovv, "oovv")), _lib.ptr(fov),
                                                 int(fov.stride(0)), _lib.ptr(eo), _lib.ptr(ev), _lib.ptr(et),
@@ -515,7 +529,7 @@ def t_energy_batch(no, nv, ijk, Q, t1, t2, oovv, fov, eo, ev, et, accumulate=Tru
 def t3_assemble(no, nv, i, j, k, Q, t1, t2, oovv, fov, eo, ev, with_denom, blocked=False):
     w3 = torch.empty((nv, nv, nv), dtype=F64, device=Q.device)
     d3 = torch.empty((nv, nv, nv), dtype=F64, device=Q.device)
-    _lib.check(_lib.get().b200cc_t3_assemble(no, nv, int(i), int(j), int(k), _lib.ptr(Q), int(bool(blocked)),
+    _lib.check(_lib.get().b200cc_t3_assemble(no, nv, int(i), int(j), int(k), _lib.ptr(Q), int(blocked),
                                              _lib.ptr(_c(t1, "t1")),
                                              _lib.ptr(_c(t2, "t2")), _lib.ptr(_c(oovv, "oovv")), _lib.ptr(fov),
                                              int(fov.stride(0)), _lib.ptr(eo), _lib.ptr(ev), int(bool(with_denom)),
@@ -589,6 +603,17 @@ class _Phases:
 
     def __call__(self, name):
         return self._Span(self, name)
+
+    def mark(self, name):
+        """Sequential form: ends the stretch opened by the previous mark() and, if ``name`` is not None, opens one."""
+        if not (self.on and torch.cuda.is_available()):
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        cur = getattr(self, "_open", None)
+        if cur is not None:
+            self._pending.append((cur[0], cur[1], ev))
+        self._open = (name, ev) if name is not None else None
 
     def collect(self):
         out = {}

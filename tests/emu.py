@@ -89,8 +89,9 @@ class EmuLib:
             return _arr(addr, (rows, K), (1, ld) if trans else (ld, 1))
 
         bc = None
+        nbc = 8 if d.K3 > 0 else 4
         if d.bcoords:
-            bc = _ints(d.bcoords, 4 * d.batch).reshape(d.batch, 4)
+            bc = _ints(d.bcoords, nbc * d.batch).reshape(d.batch, nbc)
         for b in range(d.batch):
             if tab is not None:
                 a1, b1, a2, b2, c = (int(x) for x in tab[b])
@@ -109,6 +110,13 @@ class EmuLib:
             acc = mat(a1, M, d.K1, d.lda1, d.transA) @ mat(b1, N, d.K1, d.ldb1, d.transB).T
             if d.K2 > 0:
                 acc = acc + mat(a2, M, d.K2, d.lda2, d.transA) @ mat(b2, N, d.K2, d.ldb2, d.transB).T
+            if d.K3 > 0:                 # third / fourth K segment (K-major only), slab indices bc[b, 4:8] or b
+                ix = [int(x) for x in bc[b, 4:8]] if bc is not None else [b] * 4
+                acc = acc + (mat(d.A3 + 8 * ix[0] * d.strideA3, M, d.K3, d.lda3, 0)
+                             @ mat(d.B3 + 8 * ix[1] * d.strideB3, N, d.K3, d.ldb3, 0).T)
+                if d.K4 > 0:
+                    acc = acc + (mat(d.A4 + 8 * ix[2] * d.strideA4, M, d.K4, d.lda4, 0)
+                                 @ mat(d.B4 + 8 * ix[3] * d.strideB4, N, d.K4, d.ldb4, 0).T)
             if d.out_cube_nv > 0:        # (T): C written as contiguous 8x8x8 cubes, row = x*nv + y, col = z
                 nv = d.out_cube_nv
                 nc8 = (nv + 7) // 8
@@ -397,7 +405,7 @@ class EmuLib:
 
     # ---- (T) ------------------------------------------------------------------------------------------
     def b200cc_t_q_size(self, nv, blocked):
-        return ((nv + 7) // 8) ** 3 * 512 if blocked else nv ** 3
+        return ((nv + 7) // 8) ** 3 * 512 if (blocked & 1) else nv ** 3
 
     @staticmethod
     def _unblock(Q6, nv, blocked):
@@ -411,6 +419,25 @@ class EmuLib:
     def b200cc_t_energy_scratch(self, nv, ntrip):
         nt = (nv + 7) // 8
         return nt * (nt + 1) * (nt + 2) // 6 * ntrip
+
+    @staticmethod
+    def _Wp(R, nv):
+        """paired layout: W[a,b,c] = R1[a,b,c] + R2[a,c,b] + R3[c,b,a]"""
+        return R[0] + R[1].transpose(0, 2, 1) + R[2].transpose(2, 1, 0)
+
+    def _Wq(self, Q, n, nv, flags):
+        """W of triple n from the Q buffer; flags bit 0 = cube-blocked, bit 1 = paired (3 arrays per triple)"""
+        blocked, paired = flags & 1, flags & 2
+        nq = 3 if paired else 6
+        v3 = self.b200cc_t_q_size(nv, blocked)
+        raw = _vec(Q + 8 * n * nq * v3, nq * v3)
+        if not blocked:
+            arr = raw.reshape(nq, nv, nv, nv)
+        else:
+            nc8 = (nv + 7) // 8
+            arr = raw.reshape(nq, nc8, nc8, nc8, 8, 8, 8).transpose(0, 1, 4, 2, 5, 3, 6).reshape(
+                nq, nc8 * 8, nc8 * 8, nc8 * 8)[:, :nv, :nv, :nv]
+        return self._Wp(arr, nv) if paired else self._W(arr, nv)
 
     @staticmethod
     def _W(Q, nv):
@@ -437,7 +464,6 @@ class EmuLib:
                               scratch, stream):
         self._count("t_energy", 2)
         trip = _ints(ijk, 3 * ntrip).reshape(ntrip, 3)
-        v3 = self.b200cc_t_q_size(nv, blocked)
         a = np.arange(nv)
         eq = ((a[:, None, None] == a[None, :, None]).astype(float) + (a[:, None, None] == a[None, None, :])
               + (a[None, :, None] == a[None, None, :]))
@@ -445,7 +471,7 @@ class EmuLib:
         tot = 0.0
         for n in range(ntrip):
             i, j, k = (int(x) for x in trip[n])
-            W = self._W(self._unblock(_vec(Q + 8 * n * 6 * v3, 6 * v3), nv, blocked), nv)
+            W = self._Wq(Q, n, nv, blocked)
             V = (W + self._disc(no, nv, i, j, k, t1, t2, oovv, fov, ldf)) / (1.0 + eq)
             p = lambda X, *ax: X.transpose(*ax)
             X3 = (W * V + p(W, 0, 2, 1) * p(V, 0, 2, 1) + p(W, 1, 0, 2) * p(V, 1, 0, 2) + p(W, 1, 2, 0) * p(V, 1, 2, 0)
@@ -465,8 +491,7 @@ class EmuLib:
                            stream):
         self._count("t3_assemble")
         v3 = nv ** 3
-        qs = self.b200cc_t_q_size(nv, blocked)
-        W = self._W(self._unblock(_vec(Q, 6 * qs), nv, blocked), nv)
+        W = self._Wq(Q, 0, nv, blocked)
         Dd = self._disc(no, nv, i, j, k, t1, t2, oovv, fov, ldf)
         if with_denom:
             den = self._den(no, nv, i, j, k, eo, ev)

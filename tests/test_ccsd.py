@@ -170,6 +170,29 @@ def test_triples(golden, dev):
     assert abs(float(eng2.energy(tl)[0]) - float(g["e_t_tjl"])) < 1e-12
 
 
+@pytest.mark.parametrize("no,nv", [(4, 10), (6, 26)])
+def test_paired_triples_equal_six_array_form(dev, no, nv):
+    """t_tjl sums the six t3 products pairwise inside the GEMM (four K segments, three arrays per triple through HBM):
+    same E(T) as the six-array form and as the numpy oracle, ragged 8-cubes included"""
+    from pycc_b200.synthetic import make_synthetic, blocks_from_factor
+    from oracle import triples_oracle as to
+    syn = make_synthetic(no, nv, seed=7, fock_noise=0.01)
+    cc = pycc_b200.ccwfn(syn, model="CCSD(T)", device="GPU", quiet=True)
+    cc.t1 = T(0.05 * np.random.default_rng(3).standard_normal((no, nv)))
+    trip = [t for t in cctriples.triples_list(no) if not (t[0] == t[1] == t[2])]
+    e6 = cctriples.TriplesEngine(cc, paired=False)
+    e3 = cctriples.TriplesEngine(cc, paired=True)
+    assert e3.paired and e3.nq == 3 and not e6.paired
+    a, b = float(e6.energy(trip)[0]), float(e3.energy(trip)[0])
+    bl = blocks_from_factor(syn, names=("ovvv", "ooov", "oovv"))
+    want = to.t_tjl(cc.t1.cpu().numpy(), cc.t2.cpu().numpy(), syn.F, bl["ovvv"], bl["ooov"], bl["oovv"])
+    assert abs(a - want) < 1e-12 and abs(b - want) < 1e-12
+    w6, d6 = e6.t3_parts(no - 1, 1, 0, True)
+    w3, d3 = e3.t3_parts(no - 1, 1, 0, True)
+    assert float((w6 - w3).abs().max()) < 1e-13 and float((d6 - d3).abs().max()) == 0.0
+    assert abs(float(cctriples.t_tjl(cc)) - want) < 1e-12
+
+
 def test_vikings_cross_formulations(dev):
     # the reference's own cross-check (tests/test_005_ccsd_t_energy.py:30-36), on the smallest golden case
     from tests.conftest import load_golden, GOLDEN
