@@ -536,9 +536,12 @@ class CCwfn(object):
         I["W1"], I["W2"] = W1, W2
 
         # ---------------- Z'[i_g,j,m,b] = Zmbij[m,b,i,j] = <mb|ef> tau_ijef   (ccwfn.py:715)
+        # Sharded over m, not over i: a rank then reads only ITS slabs <m_g b|ef> of the 8.6 GB block (all (i,j) rows of tau)
+        # and the contraction with t_ma below gives a partial sum over m_g for every r2 row -- the all-reduce of r2 adds
+        # the partial sums.  (Sharded over i, every rank streamed the whole block.)
         K.PHASES.mark("  Z = tau.<mb|ef> (o3v3)")
         if not ccd:
-            I["Zijmb"] = ct("ijef,mbef->ijmb", A["tau"][i0:i1], H.block("ovvv"))
+            I["Zijmb"] = ct("ijef,mbef->ijmb", A["tau"], H.block("ovvv")[i0:i1])
         K.PHASES.mark(None)
         return I
 
@@ -703,21 +706,24 @@ class CCwfn(object):
         if not ccd:
             ooov, ovov = H.block("ooov"), H.block("ovov")
             # - t_ma ( Z_mbij + <mb|ij> + t_ie <mb|ej> )  as one batched product    932, 940, 936-937
-            Zs = I["Zijmb"]
-            K.strided_axpby(Zs, ooov[i0:i1], 1.0, 1.0)                             # <mb|ij> = ooov[i,j,m,b]
-            # Y1[i,j,m,b] = sum_e t_ie <jm|be>: batch (j,m)
-            K.dgemm(ni, nv, nv, t1g, nv, 0, oovv, nv, 0, Zs, no * no * nv, 1.0, 1.0,
-                    batch=no * no, sA=0, sB=nv * nv, sC=nv)
-            K.dgemm(nv, nv, no, t1, nv, 1, Zs, nv, 1, rg, nv, -1.0, 1.0,
-                    batch=ni * no, sA=0, sB=no * nv, sC=nv * nv)
+            # for this rank's m in [i0,i1) and ALL rows (i,j): a partial sum over m, completed by the all-reduce of r2
+            Zs = I["Zijmb"]                                                        # [i, j, m_g, b]
+            K.strided_axpby(Zs, ooov[:, :, i0:i1, :], 1.0, 1.0)                    # <mb|ij> = ooov[i,j,m,b]
+            # Y1[i,j,m,b] = sum_e t_ie <jm|be>: per j a batch over m_g
+            for j in range(no):
+                K.dgemm(no, nv, nv, t1, nv, 0, (oovv, (j * no + i0) * nv * nv), nv, 0, (Zs, j * ni * nv), no * ni * nv,
+                        1.0, 1.0, batch=ni, sA=0, sB=nv * nv, sC=nv)
+            K.dgemm(nv, nv, ni, (t1, i0 * nv), nv, 1, Zs, nv, 1, r2, nv, -1.0, 1.0,
+                    batch=no * no, sA=0, sB=ni * nv, sC=nv * nv)
             # - t_ie t_mb <ma|je>                                                    938
             Y2 = torch.empty((ni, no, no, nv), dtype=F64, device=self.device1)       # [i,j,m,a]
             K.dgemm(ni, no * nv, nv, t1g, nv, 0, ovov, no * nv, 0, Y2, no * no * nv, 1.0, 0.0,
                     batch=no, sA=0, sB=nv, sC=no * nv)
             K.dgemm(nv, nv, no, Y2, nv, 1, t1, nv, 1, rg, nv, -1.0, 1.0,
                     batch=ni * no, sA=no * nv, sB=0, sC=nv * nv)
-            # t_ie <ab|ej>,  <ab|ej> = <ja|be>                                        939
-            ct("ie,jabe->ijab", t1g, H.block("ovvv"), out=rg, alpha=1.0, beta=1.0)
+            # t_ie <ab|ej>,  <ab|ej> = <ja|be>: all rows i, this rank's COLUMNS j -- it reads only its slabs <j_g a|be>   939
+            K.dgemm(no, ni * nv * nv, nv, t1, nv, 0, (H.block("ovvv"), i0 * nv ** 3), nv, 0, (r2, i0 * nv * nv),
+                    no * nv * nv, 1.0, 1.0)
         K.PHASES.mark(None)
         return r2
 
