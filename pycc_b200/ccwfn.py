@@ -521,15 +521,42 @@ class CCwfn(object):
         K.PHASES.mark("  W1, W2: t1 terms (two passes over <mb|ef>)")
         if not ccd:
             ovvv = H.block("ovvv")
-            t1g = t1[i0:i1]
-            # + t_jf <mb|ef>: natural GEMM output is [m,b,e,j]; fold into [j,b,m,e]
-            tmp = ct("mbef,jf->mbej", ovvv, t1g)
-            K.strided_axpby(W1, tmp.permute(3, 1, 0, 2), 1.0, 1.0)
-            # - t_jf <mb|fe>: batch (m,b): C[j,e] = t1[j,:] . ovvv[m,b][f,e]   -> [m,b,j,e]
-            K.dgemm(ni, nv, nv, t1g, nv, 0, ovvv, nv, 1, tmp, nv, 1.0, 0.0,
-                    batch=no * nv, sA=0, sB=nv * nv, sC=ni * nv)
-            K.strided_axpby(W2, tmp.view(no, nv, ni, nv).permute(2, 1, 0, 3), -1.0, 1.0)
-            del tmp
+            if ni == no or full:
+                t1g = t1[i0:i1]
+                # + t_jf <mb|ef>: natural GEMM output is [m,b,e,j]; fold into [j,b,m,e]
+                tmp = ct("mbef,jf->mbej", ovvv, t1g)
+                K.strided_axpby(W1, tmp.permute(3, 1, 0, 2), 1.0, 1.0)
+                # - t_jf <mb|fe>: batch (m,b): C[j,e] = t1[j,:] . ovvv[m,b][f,e]   -> [m,b,j,e]
+                K.dgemm(ni, nv, nv, t1g, nv, 0, ovvv, nv, 1, tmp, nv, 1.0, 0.0,
+                        batch=no * nv, sA=0, sB=nv * nv, sC=ni * nv)
+                K.strided_axpby(W2, tmp.view(no, nv, ni, nv).permute(2, 1, 0, 3), -1.0, 1.0)
+                del tmp
+            else:
+                # Several ranks: W1 / W2 are column-sharded (j_g) but these two terms need every slab <mb|ef> for each j.
+                # Evaluated as above they stream the whole 8.6 GB block twice on EVERY rank with a handful of columns
+                # (11 ms of a 160 ms step at N = 8).  Instead each rank contracts ITS slabs m_g with ALL of t1 (an o x o/N
+                # share of the work, 1/N of the block read) and the ranks swap pieces: rank d receives the columns j_d of
+                # everybody's slabs (2 o^2v^2 / N doubles per rank over NVLink) and adds them to its W1 / W2.
+                P1 = ct("mbef,jf->mbej", ovvv[i0:i1], t1)                                # sum_f <mb|ef> t_jf   [m_g,b,e,j]
+                P2 = torch.empty((ni, nv, no, nv), dtype=F64, device=self.device1)       # sum_f t_jf <mb|fe>   [m_g,b,j,e]
+                K.dgemm(no, nv, nv, t1, nv, 0, (ovvv, i0 * nv ** 3), nv, 1, P2, nv, 1.0, 0.0,
+                        batch=ni * nv, sA=0, sB=nv * nv, sC=no * nv)
+                # all-to-all: rank d gets the columns j_d of this rank's slabs m_g (both pieces in one message)
+                bounds = [self.part.occ_range_of(no, r) for r in range(self.part.size)]
+                send, recv = [], []
+                for (a, b) in bounds:
+                    buf = torch.empty((2, ni, nv, nv, b - a), dtype=F64, device=self.device1)
+                    K.strided_axpby(buf[0], P1[:, :, :, a:b], 1.0, 0.0)                      # [m_g,b,e,j_d]
+                    K.strided_axpby(buf[1], P2[:, :, a:b, :].permute(0, 1, 3, 2), 1.0, 0.0)  # [m_g,b,e,j_d] = P2[m,b,j,e]
+                    send.append(buf)
+                    recv.append(torch.empty((2, b - a, nv, nv, ni), dtype=F64, device=self.device1))
+                del P1, P2
+                self.part.exchange(send, recv)
+                for (a, b), got in zip(bounds, recv):                                        # got[.][m_r,b,e,j_g]
+                    if b > a:
+                        K.strided_axpby(W1[:, :, a:b, :], got[0].permute(3, 1, 0, 2), 1.0, 1.0)
+                        K.strided_axpby(W2[:, :, a:b, :], got[1].permute(3, 1, 0, 2), -1.0, 1.0)
+                del send, recv
             # - t_nb <mn|ej> = - t_nb ooov[n,m,j,e]  and  + t_nb <mn|je>
             ct("nb,nmje->jbme", t1, ooov[:, :, i0:i1, :], out=W1, alpha=-1.0, beta=1.0)
             ct("nb,mnje->jbme", t1, ooov[:, :, i0:i1, :], out=W2, alpha=1.0, beta=1.0)
@@ -709,10 +736,9 @@ class CCwfn(object):
             # for this rank's m in [i0,i1) and ALL rows (i,j): a partial sum over m, completed by the all-reduce of r2
             Zs = I["Zijmb"]                                                        # [i, j, m_g, b]
             K.strided_axpby(Zs, ooov[:, :, i0:i1, :], 1.0, 1.0)                    # <mb|ij> = ooov[i,j,m,b]
-            # Y1[i,j,m,b] = sum_e t_ie <jm|be>: per j a batch over m_g
-            for j in range(no):
-                K.dgemm(no, nv, nv, t1, nv, 0, (oovv, (j * no + i0) * nv * nv), nv, 0, (Zs, j * ni * nv), no * ni * nv,
-                        1.0, 1.0, batch=ni, sA=0, sB=nv * nv, sC=nv)
+            # Y1[i,j,m,b] = sum_e t_ie <jm|be>: batch j, N = (m_g, b)
+            K.dgemm(no, ni * nv, nv, t1, nv, 0, (oovv, i0 * nv * nv), nv, 0, Zs, no * ni * nv, 1.0, 1.0,
+                    batch=no, sA=0, sB=no * nv * nv, sC=ni * nv)
             K.dgemm(nv, nv, ni, (t1, i0 * nv), nv, 1, Zs, nv, 1, r2, nv, -1.0, 1.0,
                     batch=no * no, sA=0, sB=ni * nv, sC=nv * nv)
             # - t_ie t_mb <ma|je>                                                    938

@@ -65,6 +65,9 @@ class Comm:
     def occ_range(self, no):
         return split(no, self.size, self.rank)
 
+    def occ_range_of(self, no, rank):
+        return split(no, self.size, rank)
+
     def all_reduce_sum(self, t):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t
@@ -86,6 +89,33 @@ class Comm:
                                group=self.group)
         return t
 
+    def exchange(self, send, recv):
+        """All-to-all with preallocated buffers: ``send[d]`` goes to rank d, ``recv[r]`` receives rank r's piece."""
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_to_all(recv, send, group=self.group)
+            return recv
+        for r in range(self.size):
+            src = dist.get_global_rank(self.group, r) if self.group is not None else r
+            for d in range(self.size):
+                if r == self.rank:
+                    buf = send[d]
+                elif d == self.rank:
+                    buf = recv[r]
+                else:
+                    continue
+                if r == self.rank and d == self.rank:
+                    recv[r].copy_(send[d])
+                    continue
+                if buf.numel() == 0:
+                    continue
+                # point-to-point as a two-member exchange: gloo supports send / recv
+                if r == self.rank:
+                    dist.send(buf, dst=dist.get_global_rank(self.group, d) if self.group is not None else d,
+                              group=self.group)
+                else:
+                    dist.recv(buf, src=src, group=self.group)
+        return recv
+
     def all_reduce_max_scalar(self, x):
         t = torch.tensor([float(x)], dtype=torch.float64)
         if dist.get_backend(self.group) == "nccl":
@@ -105,6 +135,9 @@ class Serial:
         return 0, nv
 
     def occ_range(self, no):
+        return 0, no
+
+    def occ_range_of(self, no, rank):
         return 0, no
 
     def all_reduce_sum(self, t):
