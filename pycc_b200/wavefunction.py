@@ -76,15 +76,19 @@ class IntegralReference:
 
     @classmethod
     def from_psi4(cls, scf_wfn):
-        import psi4                                   # optional; same calls as hamiltonian.py:58-68
-        C = scf_wfn.Ca_subset("AO", "ALL")
-        npC = np.asarray(C)
-        F = npC.T @ np.asarray(scf_wfn.Fa_subset("AO")) @ npC
+        """From a psi4 ``Wavefunction``.  The reference asks psi4 for the full n^4 MO array (``mints.mo_eri(C,C,C,C)``,
+        hamiltonian.py:67) and forms ``ERI`` and ``L`` from it on the host -- 2 x 107 GB at o=40, v=300.  Here only what
+        psi4 alone can provide is taken from it -- the AO Fock matrix, the AO repulsion integrals ``mints.ao_eri()``
+        (chemist order) and the MO coefficients, exactly the inputs hamiltonian.py:54-67 starts from -- and the AO -> MO
+        transformation runs on the device, block by block (``from_ao``): the n^4 MO array never exists."""
+        import psi4                                   # optional dependency
+        C = np.asarray(scf_wfn.Ca_subset("AO", "ALL"))
+        F_ao = np.asarray(scf_wfn.Fa_subset("AO"))
         mints = psi4.core.MintsHelper(scf_wfn.basisset())
-        ERI = np.asarray(mints.mo_eri(C, C, C, C)).swapaxes(1, 2)
+        eri_ao = np.asarray(mints.ao_eri())
         nfzc = int(sum(scf_wfn.frzcpi()))
         no = int(sum(scf_wfn.doccpi())) - nfzc
-        return cls.from_arrays(F, ERI, no, nfzc, scf_wfn.energy())
+        return cls.from_ao(F_ao, eri_ao, C, no, nfzc, scf_wfn.energy())
 
 
 def resolve_reference(x):
