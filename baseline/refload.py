@@ -118,7 +118,8 @@ class HostBlockIntegrals:
             for g in _SYM:
                 for name in STORED:
                     if name in self.blocks and all(pat[t] == name[g[t]] for t in range(4)):
-                        return self.blocks[name].transpose(g)
+                        blk = self.blocks[name]
+                        return blk.transpose(g) if isinstance(blk, np.ndarray) else blk.permute(*g)   # numpy / torch
             raise KeyError("no stored block for pattern %r" % pat)
         if pat not in self._cache:
             a = self.eri[key]
@@ -195,6 +196,13 @@ def reference_wfn(ref, F, no, ERI, L=None, blocks=None, nfzc=0, model="CCSD", de
     w.Dijab = eo.reshape(-1, 1, 1, 1) + eo.reshape(-1, 1, 1) - ev.reshape(-1, 1) - ev
     w.Dia = eo.reshape(-1, 1) - ev
     w.t1 = np.zeros((w.no, w.nv))
+    if device == "GPU" and isinstance(ERI, HostBlockIntegrals):
+        # device-resident blocks (torch tensors on the compute device): the reference's device='GPU' path WITHOUT its
+        # per-call host->device copies of the ERI slices (device.py:70-74) -- the library-formulation bar of bench.py
+        H.F, H.eps = mgr.seed_compute(H.F), mgr.seed_compute(H.eps)
+        w.Dijab, w.Dia, w.t1 = mgr.seed_compute(w.Dijab), mgr.seed_compute(w.Dia), mgr.seed_compute(w.t1)
+        w.t2 = ERI[w.o, w.o, w.v, w.v] / w.Dijab
+        return w
     w.t2 = np.array(ERI[w.o, w.o, w.v, w.v]) / w.Dijab
     if device == "GPU":
         # what wavefunction.py:165-169 and ccwfn.py:195-211 do for device='GPU': F / eps / denominators / amplitudes

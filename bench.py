@@ -216,6 +216,47 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def gpu_library_leg(o, v, dev, log=None):
+    """The same-box LIBRARY bar ('GPU-side comparison bar'): the reference's own, unmodified CCSD iteration
+    (baseline/_ref: residuals as written -- nine o^3v^3 and the dense o^2v^4 ladder --, update, energy, helper_diis) on
+    torch tensors, i.e. torch.einsum -> cuBLAS DGEMM + ATen elementwise kernels, with every integral block ALREADY
+    RESIDENT on the GPU -- the reference's device='GPU' path minus the per-call host->device copies of the ERI slices it
+    would pay (device.py:70-74: 64.8 GB for <ab|ef> per iteration over PCIe).  What a library formulation of the step
+    reaches on this very GPU.  None of this package's kernels run in the timed part (the blocks are generated by them
+    beforehand)."""
+    import gc
+    import torch
+    from baseline import refload
+    from pycc_b200.hamiltonian import BlockHamiltonian
+    from pycc_b200.synthetic import make_synthetic
+    ref = refload.load_reference()
+    syn = make_synthetic(o, v, seed=0, device=dev)
+    keep = BlockHamiltonian.keep_vvvv_bytes
+    BlockHamiltonian.keep_vvvv_bytes = 1 << 50            # the library path needs the full FP64 <ab|ef> block
+    try:
+        H = BlockHamiltonian.from_factor(syn, dev)
+    finally:
+        BlockHamiltonian.keep_vvvv_bytes = keep
+    blocks = {k: H.block(k) for k in ("oooo", "ooov", "oovv", "ovov", "ovvv", "vvvv")}
+    del H
+    gc.collect()
+    torch.cuda.empty_cache()
+    w = refload.reference_wfn(ref, syn.F, syn.no, None, blocks=blocks, device="GPU")
+    assert w.t2.is_cuda and w.device1.type == "cuda"
+    torch.cuda.synchronize()
+
+    def echo(line):                                        # device work is asynchronous: settle it at every print
+        torch.cuda.synchronize()
+        if log is not None:
+            log(line)
+    secs, en = refload.timed_solve_cc(w, 3, echo=echo)
+    peak = torch.cuda.max_memory_allocated(dev) / 2**30
+    return {"value": float(min(secs[1:])), "unit": "s/iter", "all": [round(x, 4) for x in secs], "energies": en,
+            "peak_gb": peak,
+            "what": "unmodified reference CCSD iteration (9 o^3v^3 terms + dense 2 o^2 v^4 ladder) on torch CUDA tensors: "
+                    "torch.einsum -> cuBLAS DGEMM, integral blocks resident in HBM (no per-call H2D copies)"}
+
+
 def workload_config(o, v, parallelism):
     return {"workload": "RHF-CCSD iteration o=%d v=%d FP64 (synthetic integrals, seed 0); inputs >> L2 "
                         "(integral blocks streamed from HBM every step)" % (o, v), "parallelism": parallelism}
@@ -271,6 +312,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-mp", action="store_true", help="skip the mixed-precision (precision='MP') leg")
     ap.add_argument("--no-c4", action="store_true", help="skip BASELINE configs[3]: the full (T) at o=30, v=280")
+    ap.add_argument("--no-lib", action="store_true", help="skip the same-box library bar (reference code on torch/cuBLAS)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -560,6 +602,15 @@ def main():
         del ccm, diism
         release()
 
+    lib = None
+    if world == 1 and not args.no_lib:
+        try:
+            lib = gpu_library_leg(o, v, dev)
+            lib["speedup_of_this_package"] = lib["value"] / s_iter
+        except Exception as exc:                    # e.g. baseline/_ref absent, or out of memory
+            lib = {"unavailable": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
+        release()
+
     if rank == 0:
         cpu = None
         if not args.no_cpu and world == 1:          # reported at N=1 only (rank 0)
@@ -570,7 +621,7 @@ def main():
         line = {"metric": METRIC, "value": s_iter, "unit": "s/iter", "n_gpus": world, "steps": args.steps,
                 "warmup": nwarm, "ms_per_step": s_iter * 1e3, "higher_is_better": False,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": cfg, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "t": t_info, "t_c4": c4, "mp": mp,
+                "config": cfg, "roofline": roofline, "cpu_baseline": cpu, "gpu_library_baseline": lib, "e2e": e2e, "t": t_info, "t_c4": c4, "mp": mp,
                 "parity": parity, "phases": phases, "clocks": clocks, "gpu_launches": int(launches), "ecc_last": ecc, "rms_last": rms,
                 "energies": energies}
         print(json.dumps(line), flush=True)
