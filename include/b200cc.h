@@ -165,6 +165,14 @@ int b200cc_unpack_pairs(const double* vp, const double* vm, b200cc_i64 ldq, int 
 int b200cc_pack_tau(const double* tau, int no, int nv, int tri, double* tp, double* tm, b200cc_i64 ldq, void* stream);
 int b200cc_ladder_unpack(const double* S, const double* A, b200cc_i64 lds, int no, int nv, int tri, int a0, int a1,
                          double alpha, double* r2, void* stream);
+/* The same pair form for Z_mbij = <mb|ef> tau_ijef (ccwfn.py:715) with pair-symmetric tau:
+ *   X+-[(m,b),Q] = <mb|ef> +- <mb|fe>  (b200cc_pack_rows: `nrows` (v,v) slabs of a constant block, once per Hamiltonian),
+ *   S = T+ X+^T, A = T- X-^T over the rows pair(i,j) (the T+- of the ladder),  Z[i,j] = S + A,  Z[j,i] = S - A
+ * (b200cc_pair_rows_unpack: out[(i*no+j)*ldo + c] = S[p,c] + A[p,c], out[(j*no+i)*ldo + c] = S[p,c] - A[p,c]):
+ * o^3v^3 executed flop instead of 2 o^3v^3.                                                                       */
+int b200cc_pack_rows(const double* src, b200cc_i64 nrows, int nv, double* xp, double* xm, b200cc_i64 ldq, void* stream);
+int b200cc_pair_rows_unpack(const double* S, const double* A, b200cc_i64 lds, int no, b200cc_i64 ncols, double* out,
+                            b200cc_i64 ldo, void* stream);
 
 /* ---- tensor permutation / strided axpby -------------------------------------------------------
  * out[sum_d i_d*so[d]] = alpha * in[sum_d i_d*si[d]] + beta * out[...]  for i_d < shape[d], rank <= 6.

@@ -20,6 +20,7 @@ Index conventions follow the reference: t1[i,a], t2[i,j,a,b]; intermediates retu
 """
 from __future__ import annotations
 
+import os
 import time
 
 import numpy as np
@@ -405,7 +406,7 @@ class CCwfn(object):
         t2 = t2.contiguous()
         cc2 = self.model == 'CC2'
         with K.PHASES("intermediates"):
-            I = self._intermediates(F, t1, t2, rings=not cc2)
+            I = self._intermediates(F, t1, t2, rings=not cc2, symmetric=symmetric)
         # one flat buffer [ r2 half | rank-partial part of r1 ] so that ONE all-reduce carries both
         n2, n1 = t2.numel(), t1.numel()
         buf = torch.empty(n2 + n1, dtype=F64, device=self.device1)
@@ -432,17 +433,20 @@ class CCwfn(object):
         return r1, half
 
     # ---- shared per-iteration rearrangements of the amplitudes -----------------------------------
-    def _amps(self, t1, t2):
-        """o^2v^2 permutations of t2 / tau reused by several contractions ("ring layout" [i,a,m,e])."""
+    def _amps(self, t1, t2, symmetric=False):
+        """o^2v^2 permutations of t2 / tau reused by several contractions ("ring layout" [i,a,m,e]).  ``symmetric``
+        (pair-symmetric t2): also T+- of tau over the pairs (e >= f), rows (i >= j) -- shared by the ladder and Z."""
         A = {}
         A["tau"] = K.build_tau(t1, t2, 1.0, 1.0)                 # t2 + t1 t1
+        if symmetric:
+            A["Tpm"] = K.pack_tau(A["tau"], True)
         A["t2_iame"] = K.permuted(t2, (0, 2, 1, 3))               # [i,a,m,e] = t2[i,m,a,e]
         s = K.permuted(t2, (0, 2, 1, 3), 2.0)                     # s~[i,a,m,e] = 2 t2[i,m,a,e] - t2[i,m,e,a]
         K.strided_axpby(s, t2.permute(0, 3, 1, 2), -1.0, 1.0)
         A["s_iame"] = s
         return A
 
-    def _intermediates(self, F, t1, t2, full=False, rings=True):
+    def _intermediates(self, F, t1, t2, full=False, rings=True, symmetric=False):
         """Fae, Fmi, Fme (replicated) and the LOCAL slices of Wmnij (rows i_g), W1/W2 (columns j_g) and
         Z' (rows i_g).  ``full=True`` ignores the rank partition (public build_* methods)."""
         H, ct = self.H, self._ct
@@ -450,7 +454,7 @@ class CCwfn(object):
         i0, i1 = (0, no) if full else self.part.occ_range(no)
         ni = i1 - i0
         with K.PHASES("  amps (tau, ring layouts)"):
-            A = self._amps(t1, t2)
+            A = self._amps(t1, t2, symmetric)
         I = {"amps": A, "occ": (i0, i1)}
         ccd = self.model == 'CCD'
         Fov = F[o, v]
@@ -567,10 +571,36 @@ class CCwfn(object):
         # and the contraction with t_ma below gives a partial sum over m_g for every r2 row -- the all-reduce of r2 adds
         # the partial sums.  (Sharded over i, every rank streamed the whole block.)
         K.PHASES.mark("  Z = tau.<mb|ef> (o3v3)")
-        if not ccd:
+        if not ccd and "Tpm" in A and self.pair_z:
+            # pair-symmetric tau: Z in pair form like the ladder -- S = T+ X+^T, A = T- X-^T over the rows (i >= j) with
+            # X+-[(m,b),Q] = <mb|ef> +- <mb|fe> packed once per Hamiltonian; Z[i,j] = S + A, Z[j,i] = S - A: half the flops
+            T = A["Tpm"]
+            M, ldq = T.shape[1], T.shape[2]
+            X = self._ovvv_packed(i0, i1)
+            ncols = ni * nv
+            lds = (ncols + 1) // 2 * 2
+            SA = torch.empty((2, M, lds), dtype=F64, device=self.device1)
+            K.dgemm(M, ncols, K.pair_count(nv), T, ldq, 0, X, ldq, 0, SA, lds, 1.0, 0.0,
+                    batch=2, sA=M * ldq, sB=ncols * ldq, sC=M * lds)
+            Z = torch.empty((no, no, ni, nv), dtype=F64, device=self.device1)
+            I["Zijmb"] = K.pair_rows_unpack(SA[0], SA[1], lds, no, ncols, Z, ncols)
+            del SA
+        elif not ccd:
             I["Zijmb"] = ct("ijef,mbef->ijmb", A["tau"], H.block("ovvv")[i0:i1])
         K.PHASES.mark(None)
         return I
+
+    # Z_mbij in pair form when tau is pair-symmetric (solve_cc's iterations); False = always the dense o^3v^3 product
+    pair_z = os.environ.get("B200CC_PAIR_Z", "1") != "0"
+
+    def _ovvv_packed(self, m0, m1):
+        """Constant X+-[2, (m,b), ldq] of the slabs <mb|ef>, m in [m0,m1): built once per Hamiltonian (8.7 GB for all m at
+        o=40, v=300; a rank packs only its own slabs)."""
+        key = ("ovvv_packed", m0, m1)
+        if key not in self.H._derived:
+            nv = self.nv
+            self.H._derived[key] = K.pack_rows((self.H.block("ovvv"), m0 * nv ** 3), (m1 - m0) * nv, nv)
+        return self.H._derived[key]
 
     def _Loovv_emnf(self, m0, m1):
         """Constant [e, m, n, f] copy of Loovv[m0:m1] (K-major operand of the Fae contraction), built once."""
@@ -699,7 +729,7 @@ class CCwfn(object):
         if ni > 0:
             K.strided_axpby(r2[i0:i1], oovv[i0:i1], 0.5, 0.0)                      # 1/2 <ab|ij>       922
         with K.PHASES("ladder"):
-            self._ladder(A["tau"], r2, symmetric=symmetric)
+            self._ladder(A["tau"], r2, symmetric=symmetric, T=A.get("Tpm") if symmetric else None)
         if ni == 0:
             return r2
         rg = r2[i0:i1]                                                             # rows i_g (contiguous)
@@ -753,7 +783,7 @@ class CCwfn(object):
         K.PHASES.mark(None)
         return r2
 
-    def _ladder(self, tau, r2, symmetric=False):
+    def _ladder(self, tau, r2, symmetric=False, T=None):
         """r2[i,j,a,b] += 1/2 sum_ef tau[i,j,e,f] <ab|ef>  (ccwfn.py:931) in symmetric / antisymmetric pair form
         (csrc/pairs.cu): T+- = (tau_ef +- tau_fe)/2 over pairs (e >= f), S = T+ V+^T and A = T- V-^T as ONE batched
         GEMM (batch 2, N = K = v(v+1)/2), then r2[..,a,b] += (S+A)/2, r2[..,b,a] += (S-A)/2.  ``symmetric``: tau is
@@ -772,7 +802,8 @@ class CCwfn(object):
         row0 = K.pair_count(a_lo) - K.pair_count(r_lo)           # first of them among the resident packed rows
         nres = H.npairs_local
         tri = bool(symmetric)
-        T = K.pack_tau(tau, tri)                                 # [2, M, ldq]
+        if T is None:
+            T = K.pack_tau(tau, tri)                             # [2, M, ldq]
         M, ldq = T.shape[1], T.shape[2]
         lds = (npl + 1) // 2 * 2
         SA = torch.empty((2, M, lds), dtype=F64, device=self.device1)

@@ -78,15 +78,18 @@ __global__ void __launch_bounds__(256) unpack_pairs_kernel(const double* __restr
 // ---- tau -> T+, T- --------------------------------------------------------------------------------------------------
 // grid.x = 32x32 tile pairs (te >= tf) of the (e,f) plane, grid.y = rows m; block 32 x 8.
 // tri = 0: m = i*no + j over all (i,j);  tri = 1: m = pair(i,j) over i >= j, slab tau[i,j].
-__global__ void __launch_bounds__(256) pack_tau_kernel(const double* __restrict__ tau, int no, int nv, int tri,
-                                                       double* __restrict__ tp, double* __restrict__ tm, i64 ldq) {
+// fs = 1/2 for amplitudes (T+-), 1 for integral rows (X+- = x_ef +- x_fe, b200cc_pack_rows); nrows: number of (v,v) slabs
+// when tri == 0
+__global__ void __launch_bounds__(256) pack_tau_kernel(const double* __restrict__ tau, i64 nrows, int no, int nv, int tri,
+                                                       double fs, double* __restrict__ tp, double* __restrict__ tm,
+                                                       i64 ldq) {
   __shared__ double X[32][33], Y[32][33];
   const int nt = (nv + 31) / 32;
   const int tx = threadIdx.x, ty = threadIdx.y;
   const i64 vv = (i64)nv * nv;
   const i64 nq = pair_index(nv, 0);
   const int ntp = nt * (nt + 1) / 2;
-  for (i64 m = blockIdx.y; m < (tri ? pair_index(no, 0) : (i64)no * no); m += gridDim.y) {
+  for (i64 m = blockIdx.y; m < (tri ? pair_index(no, 0) : nrows); m += gridDim.y) {
     i64 slab = m;
     if (tri) {
       const int i = pair_row(m);
@@ -115,8 +118,8 @@ __global__ void __launch_bounds__(256) pack_tau_kernel(const double* __restrict_
         if (e < nv && f <= e) {
           const double x = X[r][tx], y = Y[tx][r];                         // tau[e,f], tau[f,e]
           const i64 q = pair_index(e, f);
-          op[q] = (e == f) ? x : 0.5 * (x + y);
-          om[q] = (e == f) ? 0.0 : 0.5 * (x - y);
+          op[q] = (e == f) ? x : fs * (x + y);
+          om[q] = (e == f) ? 0.0 : fs * (x - y);
         }
       }
     }
@@ -216,8 +219,53 @@ extern "C" int b200cc_pack_tau(const double* tau, int no, int nv, int tri, doubl
   const int nt = (nv + 31) / 32;
   const i64 M = tri ? pair_index(no, 0) : (i64)no * no;
   dim3 grid((unsigned)(nt * (nt + 1) / 2 + 1), (unsigned)(M < 65535 ? M : 65535)), block(32, 8);
-  pack_tau_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(tau, no, nv, tri ? 1 : 0, tp, tm, ldq);
+  pack_tau_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(tau, (i64)no * no, no, nv, tri ? 1 : 0, 0.5, tp,
+                                                                         tm, ldq);
   return check_launch("pack_tau_kernel");
+}
+
+extern "C" int b200cc_pack_rows(const double* src, b200cc_i64 nrows, int nv, double* xp, double* xm, b200cc_i64 ldq,
+                                void* stream) {
+  if (nrows < 0 || nv <= 0) { set_error("b200cc_pack_rows: bad size"); return 1; }
+  if (ldq < pair_index(nv, 0)) { set_error("b200cc_pack_rows: ldq < v(v+1)/2"); return 1; }
+  if (nrows == 0) return 0;
+  const int nt = (nv + 31) / 32;
+  dim3 grid((unsigned)(nt * (nt + 1) / 2 + 1), (unsigned)(nrows < 65535 ? nrows : 65535)), block(32, 8);
+  pack_tau_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(src, nrows, 1, nv, 0, 1.0, xp, xm, ldq);
+  return check_launch("pack_tau_kernel(rows)");
+}
+
+// out[(i*no + j)*ldo + c] = S[p,c] + A[p,c],  out[(j*no + i)*ldo + c] = S[p,c] - A[p,c],  p = pair(i,j), i >= j, c < ncols
+namespace b200cc {
+__global__ void __launch_bounds__(256) pair_rows_unpack_kernel(const double* __restrict__ S, const double* __restrict__ A,
+                                                               i64 lds, int no, i64 ncols, double* __restrict__ out,
+                                                               i64 ldo) {
+  const i64 np = pair_index(no, 0);
+  for (i64 p = blockIdx.y; p < np; p += gridDim.y) {
+    const int i = pair_row(p), j = (int)(p - pair_index(i, 0));
+    const double* Sp = S + p * lds;
+    const double* Ap = A + p * lds;
+    double* oij = out + ((i64)i * no + j) * ldo;
+    double* oji = out + ((i64)j * no + i) * ldo;
+    for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < ncols; c += (i64)gridDim.x * blockDim.x) {
+      const double s = Sp[c], d = Ap[c];
+      oij[c] = s + d;
+      if (i != j) oji[c] = s - d;
+    }
+  }
+}
+}  // namespace b200cc
+
+extern "C" int b200cc_pair_rows_unpack(const double* S, const double* A, b200cc_i64 lds, int no, b200cc_i64 ncols,
+                                       double* out, b200cc_i64 ldo, void* stream) {
+  if (no <= 0 || ncols < 0) { set_error("b200cc_pair_rows_unpack: bad size"); return 1; }
+  if (ncols == 0) return 0;
+  const i64 np = pair_index(no, 0);
+  i64 gx = (ncols + 255) / 256;
+  if (gx > 64) gx = 64;
+  dim3 grid((unsigned)gx, (unsigned)(np < 65535 ? np : 65535));
+  pair_rows_unpack_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(S, A, lds, no, ncols, out, ldo);
+  return check_launch("pair_rows_unpack_kernel");
 }
 
 extern "C" int b200cc_ladder_unpack(const double* S, const double* A, b200cc_i64 lds, int no, int nv, int tri, int a0,

@@ -336,6 +336,24 @@ def pack_tau(tau, tri, out=None):
     return out
 
 
+def pack_rows(src, nrows, nv, out=None):
+    """``nrows`` contiguous (v,v) slabs x[e,f] -> [2, nrows, ldq]: X+ = x_ef + x_fe (x_ee), X- = x_ef - x_fe over the pairs
+    (e >= f) (b200cc_pack_rows); ``src``: tensor or (tensor, element offset)."""
+    ldq = pair_ld(nv)
+    if out is None:
+        out = torch.empty((2, int(nrows), ldq), dtype=F64, device=_dev(src))
+    _lib.check(_lib.get().b200cc_pack_rows(_addr(src), int(nrows), int(nv), _lib.ptr(out[0]), _lib.ptr(out[1]), int(ldq),
+                                           _lib.stream()), "b200cc_pack_rows")
+    return out
+
+
+def pair_rows_unpack(S, A, lds, no, ncols, out, ldo):
+    """out[i,j,:ncols] = S[p] + A[p], out[j,i,:ncols] = S[p] - A[p] for p = pair(i,j), i >= j (b200cc_pair_rows_unpack)."""
+    _lib.check(_lib.get().b200cc_pair_rows_unpack(_addr(S), _addr(A), int(lds), int(no), int(ncols), _addr(out), int(ldo),
+                                                  _lib.stream()), "b200cc_pair_rows_unpack")
+    return out
+
+
 def ladder_unpack(S, A, lds, no, nv, tri, a0, a1, alpha, r2):
     """r2 += alpha * (the ladder held as S / A over the pairs of rows a in [a0,a1)) (b200cc_ladder_unpack)."""
     _lib.check(_lib.get().b200cc_ladder_unpack(_addr(S), _addr(A), int(lds), int(no), int(nv), int(bool(tri)), int(a0),

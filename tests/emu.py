@@ -255,6 +255,35 @@ class EmuLib:
         Mn[:, :nq] = np.where(e == f, 0.0, 0.5 * (x - y))
         return 0
 
+    def b200cc_pack_rows(self, src, nrows, nv, xp, xm, ldq, stream):
+        self._count("pack_rows")
+        if nrows <= 0:
+            return 0
+        X = _vec(src, nrows * nv * nv).reshape(nrows, nv, nv)
+        e, f = self._pairs(nv)
+        nq = len(e)
+        P = _arr(xp, (nrows, ldq), (ldq, 1))
+        Mn = _arr(xm, (nrows, ldq), (ldq, 1))
+        P[...] = 0.0
+        Mn[...] = 0.0
+        x, y = X[:, e, f], X[:, f, e]
+        P[:, :nq] = np.where(e == f, x, x + y)
+        Mn[:, :nq] = np.where(e == f, 0.0, x - y)
+        return 0
+
+    def b200cc_pair_rows_unpack(self, S, A, lds, no, ncols, out, ldo, stream):
+        self._count("pair_rows_unpack")
+        if ncols <= 0:
+            return 0
+        i, j = self._pairs(no)
+        Sm = _arr(S, (len(i), ncols), (lds, 1))
+        Am = _arr(A, (len(i), ncols), (lds, 1))
+        O = _arr(out, (no * no, ncols), (ldo, 1))
+        O[i * no + j] = Sm + Am
+        off = i != j
+        O[j[off] * no + i[off]] = (Sm - Am)[off]
+        return 0
+
     def b200cc_ladder_unpack(self, S, A, lds, no, nv, tri, a0, a1, alpha, r2, stream):
         self._count("ladder_unpack")
         if a1 <= a0:

@@ -148,6 +148,26 @@ def test_ladder_matches_einsum(dev, no, nv, packed_only):
     assert np.abs(full.cpu().numpy() - vvvv).max() < 1e-14
 
 
+@pytest.mark.parametrize("no,nv", [(3, 7), (4, 10), (5, 34)])
+def test_z_in_pair_form_matches_dense(dev, no, nv):
+    """Z_mbij = <mb|ef> tau_ijef (ccwfn.py:715) for pair-symmetric amplitudes: pair form (T+- of the ladder, packed
+    <mb|ef>) against the dense o^3v^3 product and against numpy"""
+    syn = make_synthetic(no, nv, seed=5, fock_noise=0.01)
+    cc = pycc_b200.ccwfn(syn, model="CCSD", device="GPU", quiet=True)
+    rng = np.random.default_rng(2)
+    t1 = 0.1 * rng.standard_normal((no, nv))
+    t2 = rng.standard_normal((no, no, nv, nv))
+    t2 = t2 + t2.transpose(1, 0, 3, 2)
+    F = cc._check_F(cc.H.F)
+    Zp = cc._intermediates(F, T(t1), T(t2), full=True, symmetric=True)["Zijmb"].cpu().numpy()
+    Zd = cc._intermediates(F, T(t1), T(t2), full=True, symmetric=False)["Zijmb"].cpu().numpy()
+    ovvv = blocks_from_factor(syn, names=("ovvv",))["ovvv"]
+    tau = t2 + np.einsum("ia,jb->ijab", t1, t1)
+    want = np.einsum("ijef,mbef->ijmb", tau, ovvv)
+    assert np.abs(Zd - want).max() < 1e-12 and np.abs(Zp - want).max() < 1e-12
+    assert ("ovvv_packed", 0, no) in cc.H._derived
+
+
 def test_host_block_is_packed_and_large_blocks_released(dev, packed_only):
     """from_arrays / from_blocks: the FP64 block handed in is packed at construction and, beyond keep_vvvv_bytes,
     released; a caller's own BlockHamiltonian is left alone"""
