@@ -440,7 +440,8 @@ class CCwfn(object):
         A["tau"] = K.build_tau(t1, t2, 1.0, 1.0)                 # t2 + t1 t1
         if symmetric:
             A["Tpm"] = K.pack_tau(A["tau"], True)
-        A["t2_iame"] = K.permuted(t2, (0, 2, 1, 3))               # [i,a,m,e] = t2[i,m,a,e]
+        if not (symmetric and self.fuse_rings):
+            A["t2_iame"] = K.permuted(t2, (0, 2, 1, 3))           # [i,a,m,e] = t2[i,m,a,e]
         s = K.permuted(t2, (0, 2, 1, 3), 2.0)                     # s~[i,a,m,e] = 2 t2[i,m,a,e] - t2[i,m,e,a]
         K.strided_axpby(s, t2.permute(0, 3, 1, 2), -1.0, 1.0)
         A["s_iame"] = s
@@ -515,13 +516,19 @@ class CCwfn(object):
         del taut
         t2_jbnf = K.permuted(t2[:, i0:i1], (1, 3, 0, 2))          # [j,b,n,f] = t2[n,j,f,b]
         oovv_menf = H.derived("oovv_menf")
+        # Pair-symmetric amplitudes (solve_cc): the residual only needs D = W1 + 1/2 W2 and W2 (see _r2_half), and
+        #   D = lin(W1) + 1/2 lin(W2) + 1/2 sum_nf (t2[n,j,f,b] - tau(1/2,1)[j,n,f,b]) L_mnef
+        # (the two quadratic terms of W1 and half the one of W2 combine, L = 2<mn|ef> - <mn|fe>): TWO o^3v^3 GEMMs build
+        # {D, W2} where {W1, W2} take three.  The linear parts must be complete before they are mixed, so the GEMMs come
+        # after the t1 terms on this branch.
+        fused = bool(symmetric) and self.fuse_rings and not full
         W1 = K.permuted(oovv_menf[:, :, i0:i1, :], (2, 3, 0, 1))  # <mb|ej> = <mj|eb> -> [j,b,m,e]
-        ct("jbnf,menf->jbme", taut_jbnf, oovv_menf, out=W1, alpha=-1.0, beta=1.0)
-        ct("jbnf,menf->jbme", t2_jbnf, H.derived("Loovv_menf"), out=W1, alpha=0.5, beta=1.0)
-        del t2_jbnf
         W2 = K.permuted(H.derived("ovov_mejb")[:, :, i0:i1, :], (2, 3, 0, 1), -1.0)
-        ct("jbnf,menf->jbme", taut_jbnf, H.derived("oovv_mfne"), out=W2, alpha=1.0, beta=1.0)
-        del taut_jbnf
+        if not fused:
+            ct("jbnf,menf->jbme", taut_jbnf, oovv_menf, out=W1, alpha=-1.0, beta=1.0)
+            ct("jbnf,menf->jbme", t2_jbnf, H.derived("Loovv_menf"), out=W1, alpha=0.5, beta=1.0)
+            ct("jbnf,menf->jbme", taut_jbnf, H.derived("oovv_mfne"), out=W2, alpha=1.0, beta=1.0)
+            del t2_jbnf, taut_jbnf
         K.PHASES.mark("  W1, W2: t1 terms (two passes over <mb|ef>)")
         if not ccd:
             ovvv = H.block("ovvv")
@@ -564,7 +571,16 @@ class CCwfn(object):
             # - t_nb <mn|ej> = - t_nb ooov[n,m,j,e]  and  + t_nb <mn|je>
             ct("nb,nmje->jbme", t1, ooov[:, :, i0:i1, :], out=W1, alpha=-1.0, beta=1.0)
             ct("nb,mnje->jbme", t1, ooov[:, :, i0:i1, :], out=W2, alpha=1.0, beta=1.0)
-        I["W1"], I["W2"] = W1, W2
+        if fused:
+            K.PHASES.mark("  D, W2: two o3v3 GEMMs")
+            K.strided_axpby(W1, W2, 0.5, 1.0)                                     # lin(W1) + 1/2 lin(W2)
+            ct("jbnf,menf->jbme", taut_jbnf, H.derived("oovv_mfne"), out=W2, alpha=1.0, beta=1.0)
+            K.strided_axpby(t2_jbnf, taut_jbnf, -1.0, 1.0)                        # t2[n,j,f,b] - tau(1/2,1)[j,n,f,b]
+            ct("jbnf,menf->jbme", t2_jbnf, H.derived("Loovv_menf"), out=W1, alpha=0.5, beta=1.0)
+            del t2_jbnf, taut_jbnf
+            I["D"], I["W2"] = W1, W2
+        else:
+            I["W1"], I["W2"] = W1, W2
 
         # ---------------- Z'[i_g,j,m,b] = Zmbij[m,b,i,j] = <mb|ef> tau_ijef   (ccwfn.py:715)
         # Sharded over m, not over i: a rank then reads only ITS slabs <m_g b|ef> of the 8.6 GB block (all (i,j) rows of tau)
@@ -592,6 +608,8 @@ class CCwfn(object):
 
     # Z_mbij in pair form when tau is pair-symmetric (solve_cc's iterations); False = always the dense o^3v^3 product
     pair_z = os.environ.get("B200CC_PAIR_Z", "1") != "0"
+    # ring terms through {D = W1 + 1/2 W2, W2} (four o^3v^3 GEMMs instead of six) when t2 is pair-symmetric
+    fuse_rings = os.environ.get("B200CC_FUSE_RINGS", "1") != "0"
 
     def _ovvv_packed(self, m0, m1):
         """Constant X+-[2, (m,b), ldq] of the slabs <mb|ef>, m in [m0,m1): built once per Hamiltonian (8.7 GB for all m at
@@ -752,12 +770,23 @@ class CCwfn(object):
         ct("mnij,mnab->ijab", I["Wmnij"], A["tau"], out=rg, alpha=0.5, beta=1.0)
         # ring terms, columns j_g, in [i,a,j,b] layout                              933-935
         K.PHASES.mark("r2: ring terms (three o3v3 GEMMs)")
-        R = ct("iame,jbme->iajb", A["s_iame"], I["W1"])          # (2t2 - t2^T) W_mbej
-        ct("iame,jbme->iajb", A["t2_iame"], I["W2"], out=R, alpha=1.0, beta=1.0)   # t2 W_mbje^T
-        K.strided_axpby(r2[:, i0:i1], R.permute(0, 2, 1, 3), 1.0, 1.0)
         t2_jame = K.permuted(t2, (1, 2, 0, 3))                   # [j,a,m,e] = t2[m,j,a,e]
-        ct("jame,ibme->jaib", t2_jame, I["W2"], out=R, alpha=1.0, beta=0.0)        # t2_mjae W_mbie
-        K.strided_axpby(rg, R.permute(2, 0, 1, 3), 1.0, 1.0)
+        if "D" in I:
+            # pair-symmetric t2: with u = 2t2 - t2^T and t2 = (u + t2^T)/2, lines 933-935 are
+            #   u.(W1 + 1/2 W2) + 1/2 X[i,a,j,b] + X[j,a,i,b],   X[x,a,y,b] = sum_me t2[m,x,a,e] W_mbye
+            # (t2[i,m,e,a] = t2[m,i,a,e]): TWO o^3v^3 GEMMs instead of three -- the closed-shell (1/2 + P_ij) form
+            R = ct("iame,jbme->iajb", A["s_iame"], I["D"])
+            X = ct("jame,ibme->jaib", t2_jame, I["W2"])                            # [x, a, y in j_g, b]
+            K.strided_axpby(R, X, 0.5, 1.0)
+            K.strided_axpby(r2[:, i0:i1], R.permute(0, 2, 1, 3), 1.0, 1.0)
+            K.strided_axpby(rg, X.permute(2, 0, 1, 3), 1.0, 1.0)
+            del X
+        else:
+            R = ct("iame,jbme->iajb", A["s_iame"], I["W1"])          # (2t2 - t2^T) W_mbej
+            ct("iame,jbme->iajb", A["t2_iame"], I["W2"], out=R, alpha=1.0, beta=1.0)   # t2 W_mbje^T
+            K.strided_axpby(r2[:, i0:i1], R.permute(0, 2, 1, 3), 1.0, 1.0)
+            ct("jame,ibme->jaib", t2_jame, I["W2"], out=R, alpha=1.0, beta=0.0)        # t2_mjae W_mbie
+            K.strided_axpby(rg, R.permute(2, 0, 1, 3), 1.0, 1.0)
         del R, t2_jame
         K.PHASES.mark("r2: t1 terms (Z, <mb|ej>, <ma|je>, <ab|ej>)")
         if not ccd:
