@@ -474,10 +474,28 @@ class CCwfn(object):
         tauh = K.build_tau(t1, t2, 1.0, 0.0 if ccd else 0.5)
         pk = torch.zeros(nv * nv + no * no, dtype=F64, device=self.device1)
         Fae_p, Fmi_p = pk[:nv * nv].view(nv, nv), pk[nv * nv:].view(no, no)
+        P1 = P2 = None
+        if ni > 0 and rings and not ccd:
+            # ONE pair of passes over this rank's slabs <m_g b|ef> serves four terms of the reference:
+            #   P1[m,b,e,j] = sum_f <mb|ef> t_jf,   P2[m,b,j,e] = sum_f t_jf <mb|fe>          (for ALL j)
+            # -> the t1 terms of W_mbej / W_mbje (642, 681), Fae's t_mf L_mafe = 2 P2[m,a,m,e] - P1[m,a,e,m] (496) and
+            #    t_ie <ab|ej> = P1[j,a,b,i] (939: <ab|ej> = <ja|be>) -- instead of four separate sweeps of the 8.6 GB block
+            K.PHASES.mark("  P1, P2 = t1.<mb|ef> (two passes over the rank's slabs)")
+            ovvv = H.block("ovvv")
+            P1 = ct("mbef,jf->mbej", ovvv[i0:i1], t1)
+            P2 = torch.empty((ni, nv, no, nv), dtype=F64, device=self.device1)
+            K.dgemm(no, nv, nv, t1, nv, 0, (ovvv, i0 * nv ** 3), nv, 1, P2, nv, 1.0, 0.0,
+                    batch=ni * nv, sA=0, sB=nv * nv, sC=no * nv)
+            I["P1"] = P1
+            K.PHASES.mark("  Fme, Fae, Fmi")
         if ni > 0:
             ct("mnaf,emnf->ae", tauh[i0:i1], self._Loovv_emnf(i0, i1), out=Fae_p, alpha=-1.0, beta=1.0)
             ct("inef,mnef->mi", tauh[:, i0:i1], Loovv[:, i0:i1], out=Fmi_p, alpha=1.0, beta=1.0)
-            if not ccd:
+            if P1 is not None:
+                for ml in range(ni):                                  # the j = m diagonal of the two pieces
+                    K.strided_axpby(Fae_p, P2[ml, :, i0 + ml, :], 2.0, 1.0)
+                    K.strided_axpby(Fae_p, P1[ml, :, :, i0 + ml], -1.0, 1.0)
+            elif not ccd:
                 self._fae_ovvv(t1, Fae_p, i0, i1)
         if self.part.size > 1 and not full:
             self.part.all_reduce_sum(pk)
@@ -529,30 +547,17 @@ class CCwfn(object):
             ct("jbnf,menf->jbme", t2_jbnf, H.derived("Loovv_menf"), out=W1, alpha=0.5, beta=1.0)
             ct("jbnf,menf->jbme", taut_jbnf, H.derived("oovv_mfne"), out=W2, alpha=1.0, beta=1.0)
             del t2_jbnf, taut_jbnf
-        K.PHASES.mark("  W1, W2: t1 terms (two passes over <mb|ef>)")
+        K.PHASES.mark("  W1, W2: t1 terms (from P1, P2)")
         if not ccd:
-            ovvv = H.block("ovvv")
-            if ni == no or full:
-                t1g = t1[i0:i1]
-                # + t_jf <mb|ef>: natural GEMM output is [m,b,e,j]; fold into [j,b,m,e]
-                tmp = ct("mbef,jf->mbej", ovvv, t1g)
-                K.strided_axpby(W1, tmp.permute(3, 1, 0, 2), 1.0, 1.0)
-                # - t_jf <mb|fe>: batch (m,b): C[j,e] = t1[j,:] . ovvv[m,b][f,e]   -> [m,b,j,e]
-                K.dgemm(ni, nv, nv, t1g, nv, 0, ovvv, nv, 1, tmp, nv, 1.0, 0.0,
-                        batch=no * nv, sA=0, sB=nv * nv, sC=ni * nv)
-                K.strided_axpby(W2, tmp.view(no, nv, ni, nv).permute(2, 1, 0, 3), -1.0, 1.0)
-                del tmp
+            if self.part.size == 1 or full:
+                # [m,b,e,j] -> [j,b,m,e]  and  [m,b,j,e] -> [j,b,m,e]
+                K.strided_axpby(W1, P1[:, :, :, i0:i1].permute(3, 1, 0, 2), 1.0, 1.0)
+                K.strided_axpby(W2, P2[:, :, i0:i1, :].permute(2, 1, 0, 3), -1.0, 1.0)
             else:
                 # Several ranks: W1 / W2 are column-sharded (j_g) but these two terms need every slab <mb|ef> for each j.
-                # Evaluated as above they stream the whole 8.6 GB block twice on EVERY rank with a handful of columns
-                # (11 ms of a 160 ms step at N = 8).  Instead each rank contracts ITS slabs m_g with ALL of t1 (an o x o/N
-                # share of the work, 1/N of the block read) and the ranks swap pieces: rank d receives the columns j_d of
-                # everybody's slabs (2 o^2v^2 / N doubles per rank over NVLink) and adds them to its W1 / W2.
-                P1 = ct("mbef,jf->mbej", ovvv[i0:i1], t1)                                # sum_f <mb|ef> t_jf   [m_g,b,e,j]
-                P2 = torch.empty((ni, nv, no, nv), dtype=F64, device=self.device1)       # sum_f t_jf <mb|fe>   [m_g,b,j,e]
-                K.dgemm(no, nv, nv, t1, nv, 0, (ovvv, i0 * nv ** 3), nv, 1, P2, nv, 1.0, 0.0,
-                        batch=ni * nv, sA=0, sB=nv * nv, sC=no * nv)
-                # all-to-all: rank d gets the columns j_d of this rank's slabs m_g (both pieces in one message)
+                # Each rank has contracted ITS slabs m_g with ALL of t1 (an o x o/N share of the work, 1/N of the block
+                # read); the ranks swap pieces: rank d receives the columns j_d of everybody's slabs (2 o^2v^2 / N
+                # doubles per rank over NVLink, both pieces in one message) and adds them to its W1 / W2.
                 bounds = [self.part.occ_range_of(no, r) for r in range(self.part.size)]
                 send, recv = [], []
                 for (a, b) in bounds:
@@ -561,13 +566,13 @@ class CCwfn(object):
                     K.strided_axpby(buf[1], P2[:, :, a:b, :].permute(0, 1, 3, 2), 1.0, 0.0)  # [m_g,b,e,j_d] = P2[m,b,j,e]
                     send.append(buf)
                     recv.append(torch.empty((2, b - a, nv, nv, ni), dtype=F64, device=self.device1))
-                del P1, P2
                 self.part.exchange(send, recv)
                 for (a, b), got in zip(bounds, recv):                                        # got[.][m_r,b,e,j_g]
                     if b > a:
                         K.strided_axpby(W1[:, :, a:b, :], got[0].permute(3, 1, 0, 2), 1.0, 1.0)
                         K.strided_axpby(W2[:, :, a:b, :], got[1].permute(3, 1, 0, 2), -1.0, 1.0)
                 del send, recv
+            del P2
             # - t_nb <mn|ej> = - t_nb ooov[n,m,j,e]  and  + t_nb <mn|je>
             ct("nb,nmje->jbme", t1, ooov[:, :, i0:i1, :], out=W1, alpha=-1.0, beta=1.0)
             ct("nb,mnje->jbme", t1, ooov[:, :, i0:i1, :], out=W2, alpha=1.0, beta=1.0)
@@ -806,9 +811,8 @@ class CCwfn(object):
                     batch=no, sA=0, sB=nv, sC=no * nv)
             K.dgemm(nv, nv, no, Y2, nv, 1, t1, nv, 1, rg, nv, -1.0, 1.0,
                     batch=ni * no, sA=no * nv, sB=0, sC=nv * nv)
-            # t_ie <ab|ej>,  <ab|ej> = <ja|be>: all rows i, this rank's COLUMNS j -- it reads only its slabs <j_g a|be>   939
-            K.dgemm(no, ni * nv * nv, nv, t1, nv, 0, (H.block("ovvv"), i0 * nv ** 3), nv, 0, (r2, i0 * nv * nv),
-                    no * nv * nv, 1.0, 1.0)
+            # t_ie <ab|ej> = sum_e t_ie <ja|be> = P1[j,a,b,i]: all rows i, this rank's COLUMNS j (its own slabs)      939
+            K.strided_axpby(r2[:, i0:i1], I["P1"].permute(3, 0, 1, 2), 1.0, 1.0)
         K.PHASES.mark(None)
         return r2
 

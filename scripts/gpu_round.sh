@@ -5,7 +5,7 @@ tag=${1:-r02}
 shift
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi_$tag.txt 2>&1
-timeout 1500 python -m pytest tests -m gpu -x -q "$@" > gpurun_out/gpu_tests_$tag.log 2>&1
+timeout 1500 python -m pytest tests -m gpu -q "$@" > gpurun_out/gpu_tests_$tag.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/gpu_tests_$tag.log
 tail -5 gpurun_out/gpu_tests_$tag.log
 timeout 900 python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
