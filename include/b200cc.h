@@ -174,6 +174,10 @@ int b200cc_pack_rows(const double* src, b200cc_i64 nrows, int nv, double* xp, do
 int b200cc_pair_rows_unpack(const double* S, const double* A, b200cc_i64 lds, int no, b200cc_i64 ncols, double* out,
                             b200cc_i64 ldo, void* stream);
 
+/* The two "ring layouts" of t2 that the o^3v^3 products of the residual read (ccwfn.py:933-935), in ONE pass over t2:
+ *   u[i,a,m,e] = 2 t2[i,m,a,e] - t2[i,m,e,a],   tb[i,a,m,e] = t2[i,m,e,a]      (both (no,nv,no,nv), contiguous)      */
+int b200cc_ring_layouts(const double* t2, int no, int nv, double* u, double* tb, void* stream);
+
 /* ---- tensor permutation / strided axpby -------------------------------------------------------
  * out[sum_d i_d*so[d]] = alpha * in[sum_d i_d*si[d]] + beta * out[...]  for i_d < shape[d], rank <= 6.
  * Replaces tensordot's permute+contiguous copies and swapaxes/clone/+ ATen passes

@@ -110,6 +110,7 @@ SIGNATURES = {
                                        C.c_void_p]),
     "b200cc_pack_rows": (C.c_int, [dptr, i64, C.c_int, dptr, dptr, i64, C.c_void_p]),
     "b200cc_pair_rows_unpack": (C.c_int, [dptr, dptr, i64, C.c_int, i64, dptr, i64, C.c_void_p]),
+    "b200cc_ring_layouts": (C.c_int, [dptr, C.c_int, C.c_int, dptr, dptr, C.c_void_p]),
     "b200cc_permute": (C.c_int, [C.c_int, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64),
                                  C.c_double, dptr, C.c_double, dptr, C.c_void_p]),
     "b200cc_axpbyz": (C.c_int, [i64, C.c_double, dptr, C.c_double, dptr, dptr, C.c_void_p]),

@@ -440,8 +440,11 @@ class CCwfn(object):
         A["tau"] = K.build_tau(t1, t2, 1.0, 1.0)                 # t2 + t1 t1
         if symmetric:
             A["Tpm"] = K.pack_tau(A["tau"], True)
-        if not (symmetric and self.fuse_rings):
-            A["t2_iame"] = K.permuted(t2, (0, 2, 1, 3))           # [i,a,m,e] = t2[i,m,a,e]
+        if symmetric and self.fuse_rings:
+            # both operands of the two ring products in ONE pass over t2 (pair symmetry: t2[m,j,a,e] = t2[j,m,e,a])
+            A["s_iame"], A["t2_jame"] = K.ring_layouts(t2)
+            return A
+        A["t2_iame"] = K.permuted(t2, (0, 2, 1, 3))               # [i,a,m,e] = t2[i,m,a,e]
         s = K.permuted(t2, (0, 2, 1, 3), 2.0)                     # s~[i,a,m,e] = 2 t2[i,m,a,e] - t2[i,m,e,a]
         K.strided_axpby(s, t2.permute(0, 3, 1, 2), -1.0, 1.0)
         A["s_iame"] = s
@@ -775,7 +778,7 @@ class CCwfn(object):
         ct("mnij,mnab->ijab", I["Wmnij"], A["tau"], out=rg, alpha=0.5, beta=1.0)
         # ring terms, columns j_g, in [i,a,j,b] layout                              933-935
         K.PHASES.mark("r2: ring terms (three o3v3 GEMMs)")
-        t2_jame = K.permuted(t2, (1, 2, 0, 3))                   # [j,a,m,e] = t2[m,j,a,e]
+        t2_jame = A["t2_jame"] if "t2_jame" in A else K.permuted(t2, (1, 2, 0, 3))      # [j,a,m,e] = t2[m,j,a,e]
         if "D" in I:
             # pair-symmetric t2: with u = 2t2 - t2^T and t2 = (u + t2^T)/2, lines 933-935 are
             #   u.(W1 + 1/2 W2) + 1/2 X[i,a,j,b] + X[j,a,i,b],   X[x,a,y,b] = sum_me t2[m,x,a,e] W_mbye

@@ -186,9 +186,54 @@ __global__ void __launch_bounds__(256) ladder_unpack_kernel(const double* __rest
   }
 }
 
+// ---- ring layouts of t2 in one pass -----------------------------------------------------------------------------
+// u[i,a,m,e] = 2 t2[i,m,a,e] - t2[i,m,e,a]   and   tb[i,a,m,e] = t2[i,m,e,a]   from ONE read of t2 (both come from the
+// (i,m) slab; the transposed element through a 32x32 shared tile).  Replaces three permute passes per iteration.
+// grid.x = 32x32 tiles of the (a,e) plane, grid.y = (i,m) slabs; block 32 x 8.
+__global__ void __launch_bounds__(256) ring_layouts_kernel(const double* __restrict__ t2, int no, int nv,
+                                                           double* __restrict__ u, double* __restrict__ tb) {
+  __shared__ double X[32][33], Y[32][33];
+  const int nt = (nv + 31) / 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const i64 vv = (i64)nv * nv;
+  for (i64 im = blockIdx.y; im < (i64)no * no; im += gridDim.y) {
+    const int i = (int)(im / no), m = (int)(im - (i64)i * no);
+    const double* T = t2 + im * vv;
+    for (int w = blockIdx.x; w < nt * nt; w += gridDim.x) {
+      const int a0 = (w / nt) * 32, e0 = (w % nt) * 32;
+      __syncthreads();
+      for (int r = ty; r < 32; r += 8) {
+        const int a = a0 + r, e = e0 + tx;
+        X[r][tx] = (a < nv && e < nv) ? T[(i64)a * nv + e] : 0.0;            // t2[i,m,a,e]
+        const int e2 = e0 + r, a2 = a0 + tx;
+        Y[r][tx] = (e2 < nv && a2 < nv) ? T[(i64)e2 * nv + a2] : 0.0;        // t2[i,m,e,a] with e = e0 + r
+      }
+      __syncthreads();
+      for (int r = ty; r < 32; r += 8) {
+        const int a = a0 + r, e = e0 + tx;
+        if (a < nv && e < nv) {
+          const i64 o = (((i64)i * nv + a) * no + m) * nv + e;
+          const double x = X[r][tx], y = Y[tx][r];
+          u[o] = 2.0 * x - y;
+          tb[o] = y;
+        }
+      }
+    }
+  }
+}
+
 }  // namespace b200cc
 
 using namespace b200cc;
+
+extern "C" int b200cc_ring_layouts(const double* t2, int no, int nv, double* u, double* tb, void* stream) {
+  if (no <= 0 || nv <= 0) return 0;
+  const int nt = (nv + 31) / 32;
+  const i64 slabs = (i64)no * no;
+  dim3 grid((unsigned)(nt * nt), (unsigned)(slabs < 65535 ? slabs : 65535)), block(32, 8);
+  ring_layouts_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(t2, no, nv, u, tb);
+  return check_launch("ring_layouts_kernel");
+}
 
 extern "C" b200cc_i64 b200cc_pair_count(int n) { return pair_index(n, 0); }
 

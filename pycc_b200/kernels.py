@@ -354,6 +354,16 @@ def pair_rows_unpack(S, A, lds, no, ncols, out, ldo):
     return out
 
 
+def ring_layouts(t2):
+    """(u, tb): u[i,a,m,e] = 2 t2[i,m,a,e] - t2[i,m,e,a], tb[i,a,m,e] = t2[i,m,e,a] in one pass (b200cc_ring_layouts)."""
+    no, nv = t2.shape[0], t2.shape[2]
+    u = torch.empty((no, nv, no, nv), dtype=F64, device=t2.device)
+    tb = torch.empty((no, nv, no, nv), dtype=F64, device=t2.device)
+    _lib.check(_lib.get().b200cc_ring_layouts(_lib.ptr(_c(t2, "t2")), int(no), int(nv), _lib.ptr(u), _lib.ptr(tb),
+                                              _lib.stream()), "b200cc_ring_layouts")
+    return u, tb
+
+
 def ladder_unpack(S, A, lds, no, nv, tri, a0, a1, alpha, r2):
     """r2 += alpha * (the ladder held as S / A over the pairs of rows a in [a0,a1)) (b200cc_ladder_unpack)."""
     _lib.check(_lib.get().b200cc_ladder_unpack(_addr(S), _addr(A), int(lds), int(no), int(nv), int(bool(tri)), int(a0),

@@ -284,6 +284,14 @@ class EmuLib:
         O[j[off] * no + i[off]] = (Sm - Am)[off]
         return 0
 
+    def b200cc_ring_layouts(self, t2, no, nv, u, tb, stream):
+        self._count("ring_layouts")
+        n = no * no * nv * nv
+        T = _vec(t2, n).reshape(no, no, nv, nv)
+        _vec(u, n).reshape(no, nv, no, nv)[...] = (2.0 * T - T.transpose(0, 1, 3, 2)).transpose(0, 2, 1, 3)
+        _vec(tb, n).reshape(no, nv, no, nv)[...] = T.transpose(0, 3, 1, 2)
+        return 0
+
     def b200cc_ladder_unpack(self, S, A, lds, no, nv, tri, a0, a1, alpha, r2, stream):
         self._count("ladder_unpack")
         if a1 <= a0:

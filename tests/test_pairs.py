@@ -124,6 +124,31 @@ def test_pack_tau_and_ladder_unpack(dev, no, nv, tri):
     assert np.abs(r2.cpu().numpy() - want).max() < 1e-14
 
 
+@pytest.mark.parametrize("no,nv", [(1, 1), (3, 7), (2, 33), (5, 40)])
+def test_ring_layouts_and_pair_rows(dev, no, nv):
+    rng = np.random.default_rng(no + nv)
+    t2 = rng.standard_normal((no, no, nv, nv))
+    u, tb = K.ring_layouts(T(t2))
+    assert np.array_equal(u.cpu().numpy(), (2.0 * t2 - t2.transpose(0, 1, 3, 2)).transpose(0, 2, 1, 3))
+    assert np.array_equal(tb.cpu().numpy(), t2.transpose(0, 3, 1, 2))
+    # X+- of integral rows and the (i,j) / (j,i) scatter of S +- A
+    X = rng.standard_normal((no * nv, nv, nv))
+    P = K.pack_rows(T(X), no * nv, nv).cpu().numpy()
+    e, f = np.tril_indices(nv)
+    nq = len(e)
+    assert np.array_equal(P[0, :, :nq], np.where(e == f, X[:, e, f], X[:, e, f] + X[:, f, e]))
+    assert np.array_equal(P[1, :, :nq], np.where(e == f, 0.0, X[:, e, f] - X[:, f, e])) and np.all(P[:, :, nq:] == 0.0)
+    npair, ncols = no * (no + 1) // 2, 2 * nv + 1
+    S, A = rng.standard_normal((npair, ncols + 2)), rng.standard_normal((npair, ncols + 2))
+    out = torch.zeros((no, no, ncols), dtype=torch.float64, device=dev)
+    K.pair_rows_unpack(T(S), T(A), ncols + 2, no, ncols, out, ncols)
+    i, j = np.tril_indices(no)
+    want = np.zeros((no, no, ncols))
+    want[j, i] = (S - A)[:, :ncols]
+    want[i, j] = (S + A)[:, :ncols]
+    assert np.array_equal(out.cpu().numpy(), want)
+
+
 @pytest.mark.parametrize("no,nv", [(3, 7), (4, 10), (2, 33)])
 def test_ladder_matches_einsum(dev, no, nv, packed_only):
     """general mode on an unsymmetric tau, tri mode on a pair-symmetric one -- both against 'ijef,abef->ijab'"""
