@@ -303,6 +303,46 @@ typedef struct {
 b200cc_i64 b200cc_t3_density_scratch(int nv);
 int b200cc_t3_density_forms(const b200cc_t3d_desc* d, void* stream);
 
+/* ---- (T), fused (a,b,c)-driven form: the t3 tile never goes through HBM (csrc/triples_abc.cu) -------------------
+ * Replaces, for a list of virtual triples a >= b >= c: t3c_abc (cctriples.py:75-105), t3d_abc (149-173) and the
+ * Lee-Rendell bracket of t_tjl (208-237) with the roles of (i,j,k) and (a,b,c) exchanged -- same E(T).  One persistent
+ * CTA per (a,b,c): three FP64 DMMA GEMMs [o^2 pairs] x [o], K = 2v + 2o, operands streamed by TMA, accumulated into the
+ * CTA's private o^3 tile, followed by the energy evaluation of that tile in the same kernel.
+ *   et_out[0] (+)= sum over the listed (a,b,c) of their E(T) contributions (weights 2 - d_ab - d_ac - d_bc included).
+ * Needs even o <= b200cc_t_abc_max_no(), even v <= 1023.  Constant operands (built once per amplitude set):
+ *   G[l][x][y][e]   = <le|xy>  (= ovvv[l,e,x,y], Wvvvo[y,x,e,l])          o v^3
+ *   t2x[x][y][l][m] = t2[l,m,x,y]                                         o^2 v^2
+ *   Ox[z][p][q][m]  = -<mz|pq> (= -Wovoo[m,z,p,q])                        o^3 v
+ *   oovvx[x][y][i][j] = <ij|xy>                                           o^2 v^2
+ * abc / sorted: device int32, one entry per triple packed as  x0 | x1 << 10 | x2 << 20  with x0 >= x1 >= x2
+ * (sorted: the occupied triples i >= j >= k, i = j = k left out -- they contribute exactly zero).
+ * wtile: grid * o^3 doubles of scratch (after a call with nabc = 1, grid = 1 it holds W_abc[i][j][k], the connected
+ * numerator -- the parity hook for t3c_abc); partial: grid doubles. */
+typedef struct b200cc_t_abc_desc {
+  int struct_size;          /* sizeof(b200cc_t_abc_desc), checked by the library */
+  int no, nv;
+  int nabc, nsorted;
+  const int* abc;
+  const int* sorted;
+  const double* G;
+  const double* t2;
+  const double* t2x;
+  const double* Ox;
+  const double* oovvx;
+  const double* t1;
+  const double* fov;        /* F[o,v] block, row pitch ldf */
+  b200cc_i64 ldf;
+  const double* eo;
+  const double* ev;
+  double* wtile;
+  double* partial;
+  double* et_out;
+  int accumulate;
+  int grid;                 /* CTAs to launch (one per SM); the scratch arrays are sized by it */
+} b200cc_t_abc_desc;
+int b200cc_t_abc_max_no(void);
+int b200cc_t_abc(const b200cc_t_abc_desc* d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,6 +92,23 @@ class T3dDesc(C.Structure):
     ]
 
 
+class TAbcDesc(C.Structure):
+    """Mirror of ``b200cc_t_abc_desc`` (include/b200cc.h)."""
+    _fields_ = [
+        ("struct_size", C.c_int),
+        ("no", C.c_int), ("nv", C.c_int),
+        ("nabc", C.c_int), ("nsorted", C.c_int),
+        ("abc", dptr), ("sorted", dptr),
+        ("G", dptr), ("t2", dptr), ("t2x", dptr), ("Ox", dptr), ("oovvx", dptr), ("t1", dptr),
+        ("fov", dptr),
+        ("ldf", i64),
+        ("eo", dptr), ("ev", dptr),
+        ("wtile", dptr), ("partial", dptr), ("et_out", dptr),
+        ("accumulate", C.c_int),
+        ("grid", C.c_int),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/b200cc.h declares
 SIGNATURES = {
     "b200cc_version": (C.c_int, []),
@@ -136,6 +153,8 @@ SIGNATURES = {
     "b200cc_t3_connected_batch": (C.c_int, [C.c_int, C.c_int, C.c_int, dptr, dptr, dptr, dptr, dptr, C.c_void_p]),
     "b200cc_t3_density_scratch": (i64, [C.c_int]),
     "b200cc_t3_density_forms": (C.c_int, [C.POINTER(T3dDesc), C.c_void_p]),
+    "b200cc_t_abc_max_no": (C.c_int, []),
+    "b200cc_t_abc": (C.c_int, [C.POINTER(TAbcDesc), C.c_void_p]),
 }
 
 _LIB = None

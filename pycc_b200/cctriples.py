@@ -32,6 +32,8 @@ _QCACHE = {}
 # t_tjl sums the six t3 products of a triple pairwise inside the GEMM (TriplesEngine(paired=True)); B200CC_T_PAIRED=0
 # restores the six-array form
 PAIRED = os.environ.get("B200CC_T_PAIRED", "1") != "0"
+# 'auto' takes the fused (a,b,c)-driven kernel when it applies; False until it is the measured winner on the B200
+AUTO_ABC = False
 
 # per term q: (occupied index of the <mb|ef> slab and of the t2[x] slab,
 #              (p,q) of t2[p,q] in the particle GEMM, (p,q) of Y[p,q] in the hole GEMM)
@@ -221,8 +223,108 @@ class TriplesEngine:
                              self.w.eps_o, self.w.eps_v, with_denom, blocked=self.qflags)
 
 
+# ---- fused (a,b,c)-driven (T): the o^3 tile of a virtual triple stays on the chip (csrc/triples_abc.cu) -------------
+# 'abc' / 'ijk' force a formulation, 'auto' takes the fused one whenever its kernel applies (even o <= 40, even v, FP64)
+ALGO = os.environ.get("B200CC_T_ALGO", "auto")
+
+
+def _pack3(x0, x1, x2):
+    return (x0 | (x1 << 10) | (x2 << 20)).astype(np.int32)
+
+
+def abc_list(nv):
+    """All a >= b >= c except a = b = c (which contributes exactly zero), packed a | b << 10 | c << 20, c fastest --
+    consecutive entries share the slabs of a (and mostly b), so the CTAs running side by side meet in L2."""
+    out = []
+    for a in range(nv):
+        b, c = np.tril_indices(a + 1)
+        keep = ~((b == a) & (c == a))
+        out.append(_pack3(np.full(int(keep.sum()), a, dtype=np.int64), b[keep].astype(np.int64), c[keep].astype(np.int64)))
+    return np.concatenate(out) if out else np.zeros(0, dtype=np.int32)
+
+
+def sorted_occ(no):
+    """The occupied triples i >= j >= k (i = j = k left out) the energy phase of a tile visits, packed like abc_list."""
+    t = np.asarray([t for t in triples_list(no) if not (t[0] == t[1] == t[2])], dtype=np.int64).reshape(-1, 3)
+    return _pack3(t[:, 0], t[:, 1], t[:, 2])
+
+
+class FusedTriples:
+    """(T) in the (a,b,c)-driven form of the reference (t3c_abc / t3d_abc, cctriples.py:75-105, 149-173) with the
+    Lee-Rendell bracket of t_tjl (208-237) in exchanged roles: one launch of ``b200cc_t_abc`` does the twelve
+    contractions, the disconnected part, the denominators and the energy of every listed (a,b,c) without writing a t3
+    array.  Constant operands: ``G[l,x,y,e] = <le|xy>`` (shared with the (i,j,k)-driven engine), ``t2x[x,y,l,m]``,
+    ``Ox[z,p,q,m] = -<mz|pq>`` and ``oovvx[x,y,i,j]``."""
+
+    def __init__(self, ccwfn, t1=None, t2=None, grid=None):
+        self.w = ccwfn
+        H = ccwfn.H
+        self.no, self.nv = ccwfn.no, ccwfn.nv
+        self.t1 = (ccwfn.t1 if t1 is None else t1).contiguous()
+        self.t2 = (ccwfn.t2 if t2 is None else t2).contiguous()
+        self.dev = self.t2.device
+        self.fov = H.F[ccwfn.o, ccwfn.v]
+        if "ovvv_iabe" not in H._derived:
+            H._derived["ovvv_iabe"] = K.permuted(H.block("ovvv"), (0, 2, 3, 1))
+        self.G = H._derived["ovvv_iabe"]
+        if "ooov_zpqm_neg" not in H._derived:
+            H._derived["ooov_zpqm_neg"] = K.permuted(H.block("ooov"), (3, 0, 1, 2), -1.0)    # -<mz|pq> = -ooov[p,q,m,z]
+        self.Ox = H._derived["ooov_zpqm_neg"]
+        if "oovv_abij" not in H._derived:
+            H._derived["oovv_abij"] = K.permuted(H.block("oovv"), (2, 3, 0, 1))
+        self.oovvx = H._derived["oovv_abij"]
+        self.t2x = K.permuted(self.t2, (2, 3, 0, 1))
+        self.grid = int(grid) if grid else K.NSM
+        self.sorted = torch.from_numpy(sorted_occ(self.no)).to(self.dev)
+        self.wtile = torch.empty(self.grid * self.no ** 3, dtype=F64, device=self.dev)
+        self.partial = torch.empty(self.grid, dtype=F64, device=self.dev)
+
+    @staticmethod
+    def applies(ccwfn):
+        return (ccwfn.no % 2 == 0 and ccwfn.nv % 2 == 0 and 2 <= ccwfn.no <= K.t_abc_max_no() and ccwfn.nv <= 1023
+                and not bool(getattr(ccwfn, "mixed", False)))
+
+    def energy(self, abc):
+        """Sum of the contributions of the packed virtual triples ``abc`` (numpy int32 or device tensor)."""
+        et = torch.zeros(1, dtype=F64, device=self.dev)
+        if not isinstance(abc, torch.Tensor):
+            abc = torch.from_numpy(np.ascontiguousarray(abc, dtype=np.int32)).to(self.dev)
+        if abc.numel() == 0:
+            return et
+        w = self.w
+        K.t_abc(self.no, self.nv, abc, self.sorted, self.G, self.t2, self.t2x, self.Ox, self.oovvx, self.t1, self.fov,
+                w.eps_o, w.eps_v, et, self.wtile, self.partial, self.grid, accumulate=True)
+        return et
+
+    def w_tile(self, a, b, c):
+        """Connected numerator W_abc[i,j,k] (= t3c_abc without denominators) of one virtual triple, as left in the CTA's tile."""
+        keep = self.grid
+        self.grid = 1
+        try:
+            self.energy(_pack3(np.asarray([a]), np.asarray([b]), np.asarray([c])))
+        finally:
+            self.grid = keep
+        return self.wtile[:self.no ** 3].view(self.no, self.no, self.no).clone()
+
+
+def t_tjl_abc(ccwfn, abc=None):
+    """E(T) through the fused (a,b,c)-driven kernel; same value as :func:`t_tjl`.  Virtual triples are dealt round-robin
+    to the ranks of ``ccwfn.comm``; one scalar all-reduce."""
+    eng = FusedTriples(ccwfn)
+    comm = getattr(ccwfn, "comm", None)
+    lst = abc_list(ccwfn.nv) if abc is None else np.asarray(abc, dtype=np.int32)
+    if comm is not None and comm.size > 1:
+        lst = lst[comm.rank::comm.size]
+    et = eng.energy(lst)
+    if comm is not None and comm.size > 1:
+        comm.all_reduce_sum(et)
+    return et[0]
+
+
 def t_tjl(ccwfn, triples=None):
     """E(T), Lee-Rendell formulation (reference: cctriples.py:177-239).  Returns a 0-d device tensor."""
+    if triples is None and (ALGO == "abc" or (ALGO == "auto" and AUTO_ABC)) and FusedTriples.applies(ccwfn):
+        return t_tjl_abc(ccwfn)
     eng = TriplesEngine(ccwfn, paired=PAIRED)
     comm = getattr(ccwfn, "comm", None)
     trip = triples_list(ccwfn.no) if triples is None else list(triples)

@@ -1,0 +1,409 @@
+// triples_abc.cu -- (T) with the t3 tile kept on the chip: the (a,b,c)-driven form (reference: cctriples.py:75-105
+// t3c_abc, 149-173 t3d_abc) evaluated with the Lee-Rendell bracket (cctriples.py:208-237) in the roles of the occupied
+// and virtual indices exchanged.
+//
+// For fixed a >= b >= c the connected numerator is an o^3 tile
+//     W_abc[i,j,k] = G(a,b,c)[i,j,k] + G(c,b,a)[k,j,i] + G(b,c,a)[j,k,i]
+//     G(x,y,z)[l,p,q] =  sum_e <le|xy> t2[q,p,z,e] + sum_e <le|xz> t2[p,q,y,e]
+//                      - sum_m t2[l,m,x,y] <mz|pq> - sum_m t2[l,m,x,z] <my|qp>
+// (the twelve contractions of cctriples.py:83-95 grouped by the occupied index that sits on the integral): three
+// GEMMs [o^2 pairs] x [o] with K = 2v + 2o.  ONE persistent CTA owns an (a,b,c): a TMA producer thread streams the
+// operand tiles (pairs: up to 320 rows x 16 k as a 4-D box of t2 / <mz|pq>, lone index: 40 rows x 16 k) through a
+// 4-stage mbarrier ring, 8 consumer warps run FP64 DMMA on 5x5 fragments each and add their accumulators into the CTA's
+// private o^3 tile (512 KB at o = 40: L2-resident, never streamed through HBM); the same CTA then evaluates the
+// disconnected part, 1/(1+delta), X/Y/Z, the denominator and the bracket for all i >= j >= k of the tile and keeps a
+// running sum in registers.  No t3 array is written or read back: per (a,b,c) the kernel moves 2.5 MB of tile traffic
+// through L2 against 26 MB of operands.
+#include <cuda.h>
+#include <stdlib.h>
+#include "common.cuh"
+#include "pipe.cuh"
+
+namespace b200cc {
+
+constexpr int ABK = 16, AST = 4;
+constexpr int A_MI = 5, A_NCMAX = 5;
+constexpr int A_PROWS = 64 * A_MI;                 // 320 pair rows per tile (8 warps x MI fragments of 8 rows)
+constexpr int A_PBYTES = A_PROWS * 128, A_LBYTES = 8 * A_NCMAX * 128, A_STAGE = A_PBYTES + A_LBYTES;
+constexpr int A_CONSUMERS = 256, A_THREADS = A_CONSUMERS + 128;
+constexpr int A_SMEM = AST * A_STAGE + (2 * AST + 1) * (int)sizeof(uint64_t) + 1024;
+
+struct alignas(64) AbcMaps {
+  CUtensorMap g, t2x, t2a, t2b, oxa, oxb;
+};
+
+struct AbcParams {
+  int no, nv, nabc, pp, tiles_p, ktv, kto, nsorted;
+  const int* abc;
+  const int* sorted;
+  const double *t2x, *oovvx, *t1, *fov, *eo, *ev;
+  i64 ldf;
+  double* wtile;
+  double* partial;
+};
+
+__device__ __forceinline__ void named_bar_consumers() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+
+template <int MC, int NC>
+__device__ __forceinline__ void abc_frags(const unsigned char* __restrict__ Ps, const unsigned char* __restrict__ Ls, int off,
+                                          double (&a)[A_MI], double (&b)[A_NCMAX], int w, int g) {
+#pragma unroll
+  for (int i = 0; i < MC; ++i) a[i] = *reinterpret_cast<const double*>(Ps + (8 * (w + 8 * i) + g) * 128 + off);
+#pragma unroll
+  for (int j = 0; j < NC; ++j) b[j] = *reinterpret_cast<const double*>(Ls + (8 * j + g) * 128 + off);
+}
+
+template <int MC, int NC>
+__device__ __forceinline__ void abc_mma(double (&acc)[A_MI][A_NCMAX][2], const double (&a)[A_MI], const double (&b)[A_NCMAX]) {
+#pragma unroll
+  for (int i = 0; i < MC; ++i)
+#pragma unroll
+    for (int j = 0; j < NC; ++j) dmma(acc[i][j], a[i], b[j]);
+}
+
+// the k-loop of one unit (all four K segments: the consumer does not see the segment boundaries)
+template <int MC, int NC>
+__device__ __forceinline__ void abc_kloop(double (&acc)[A_MI][A_NCMAX][2], const unsigned char* tiles, uint64_t* full_bar,
+                                          uint64_t* empty_bar, int& stage, uint32_t& phase, int nkt, const int (&off)[4],
+                                          int w, int g, int lane) {
+  double a0[A_MI], b0[A_NCMAX], a1[A_MI], b1[A_NCMAX];
+  mbar_wait(full_bar + stage, phase);
+  abc_frags<MC, NC>(tiles + stage * A_STAGE, tiles + stage * A_STAGE + A_PBYTES, off[0], a0, b0, w, g);
+  for (int t = 0; t < nkt; ++t) {
+    const unsigned char* Ps = tiles + stage * A_STAGE;
+    const unsigned char* Ls = Ps + A_PBYTES;
+    abc_frags<MC, NC>(Ps, Ls, off[1], a1, b1, w, g);
+    abc_mma<MC, NC>(acc, a0, b0);
+    abc_frags<MC, NC>(Ps, Ls, off[2], a0, b0, w, g);
+    abc_mma<MC, NC>(acc, a1, b1);
+    abc_frags<MC, NC>(Ps, Ls, off[3], a1, b1, w, g);
+    abc_mma<MC, NC>(acc, a0, b0);
+    int nstage = stage + 1;
+    uint32_t nphase = phase;
+    if (nstage == AST) { nstage = 0; nphase ^= 1u; }
+    if (t + 1 < nkt) {
+      mbar_wait(full_bar + nstage, nphase);
+      abc_frags<MC, NC>(tiles + nstage * A_STAGE, tiles + nstage * A_STAGE + A_PBYTES, off[0], a0, b0, w, g);
+    }
+    abc_mma<MC, NC>(acc, a1, b1);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_bar + stage);
+    stage = nstage;
+    phase = nphase;
+  }
+}
+
+__device__ __forceinline__ void abc_decode(int packed, int& a, int& b, int& c) {
+  a = packed & 1023;
+  b = (packed >> 10) & 1023;
+  c = (packed >> 20) & 1023;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(A_THREADS, 1) t_abc_kernel(const AbcParams p, const __grid_constant__ AbcMaps tm) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + AST * A_STAGE);
+  uint64_t* empty_bar = full_bar + AST;
+  uint64_t* edone_bar = empty_bar + AST;
+  __shared__ double red[A_CONSUMERS / 32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int no = p.no, nv = p.nv;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < AST; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, A_CONSUMERS / 32);
+    }
+    mbar_init(edone_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  const int KT = 2 * p.ktv + 2 * p.kto;
+
+  if (warp >= A_CONSUMERS / 32) {
+    // ============================ producer: one thread drives the TMA unit ============================
+    reg_dec<40>();
+    if (warp == A_CONSUMERS / 32 && lane == 0) {
+      const uint32_t tx = (uint32_t)(p.pp * no * 128 + 8 * NC * 128);
+      int stage = 0;
+      uint32_t phase = 0, ephase = 0;
+      bool first = true;
+      for (int n = blockIdx.x; n < p.nabc; n += gridDim.x) {
+        // the energy phase of the previous (a,b,c) stages its small matrices in the (then idle) operand ring
+        if (!first) { mbar_wait(edone_bar, ephase); ephase ^= 1u; }
+        first = false;
+        int a, b, c;
+        abc_decode(p.abc[n], a, b, c);
+        for (int grp = 0; grp < 3; ++grp) {
+          const int x = grp == 0 ? a : (grp == 1 ? c : b);
+          const int y = grp == 2 ? c : b;
+          const int z = grp == 0 ? c : a;
+          const bool swap = grp == 2;
+          const int sxy = x * nv + y, sxz = x * nv + z;
+          for (int pt = 0; pt < p.tiles_p; ++pt) {
+            const int p0 = pt * p.pp;
+            for (int seg = 0; seg < 4; ++seg) {
+              const int nk = seg < 2 ? p.ktv : p.kto;
+              const CUtensorMap* lm = seg < 2 ? &tm.g : &tm.t2x;
+              const int lslab = (seg & 1) ? sxz : sxy;
+              const int pslab = (seg & 1) ? y : z;
+              // (seg & 1) == 0: rows (p,q) of t2[q,p,.,.] / <m.|pq>;  == 1: of t2[p,q,.,.] / <m.|qp>;  swap exchanges them
+              const bool second = ((seg & 1) != 0) != swap;
+              const CUtensorMap* pm = seg < 2 ? (second ? &tm.t2b : &tm.t2a) : (second ? &tm.oxb : &tm.oxa);
+              for (int t = 0; t < nk; ++t) {
+                mbar_wait(empty_bar + stage, phase ^ 1u);
+                unsigned char* Ps = tiles + stage * A_STAGE;
+                mbar_expect_tx(full_bar + stage, tx);
+                tma_load_3d(Ps + A_PBYTES, lm, t * ABK, 0, lslab, full_bar + stage);
+                tma_load_4d(Ps, pm, t * ABK, 0, p0, pslab, full_bar + stage);
+                if (++stage == AST) { stage = 0; phase ^= 1u; }
+              }
+            }
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ======================================== consumers ========================================
+  reg_inc<216>();
+  const int w = warp, g = lane >> 2, q2 = lane & 3;
+  int off[4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) off[s] = ((((q2 >> 1) * 4 + s) ^ g) << 4) + ((q2 & 1) << 3);
+  int stage = 0;
+  uint32_t phase = 0;
+  double e_acc = 0.0;
+  const int oo = no * no;
+  double* W = p.wtile + (i64)blockIdx.x * oo * no;
+  double* sm = reinterpret_cast<double*>(tiles);
+
+  for (int n = blockIdx.x; n < p.nabc; n += gridDim.x) {
+    int a, b, c;
+    abc_decode(p.abc[n], a, b, c);
+    for (int grp = 0; grp < 3; ++grp) {
+      for (int pt = 0; pt < p.tiles_p; ++pt) {
+        const int p0 = pt * p.pp;
+        const int rows_valid = min(p.pp, no - p0) * no;
+        const int nf = (rows_valid + 7) >> 3;
+        int mc = 0;
+#pragma unroll
+        for (int i = 0; i < A_MI; ++i) mc += (w + 8 * i < nf) ? 1 : 0;
+        double acc[A_MI][A_NCMAX][2];
+#pragma unroll
+        for (int i = 0; i < A_MI; ++i)
+#pragma unroll
+          for (int j = 0; j < A_NCMAX; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        switch (mc) {
+          case 5: abc_kloop<5, NC>(acc, tiles, full_bar, empty_bar, stage, phase, KT, off, w, g, lane); break;
+          case 4: abc_kloop<4, NC>(acc, tiles, full_bar, empty_bar, stage, phase, KT, off, w, g, lane); break;
+          case 3: abc_kloop<3, NC>(acc, tiles, full_bar, empty_bar, stage, phase, KT, off, w, g, lane); break;
+          case 2: abc_kloop<2, NC>(acc, tiles, full_bar, empty_bar, stage, phase, KT, off, w, g, lane); break;
+          case 1: abc_kloop<1, NC>(acc, tiles, full_bar, empty_bar, stage, phase, KT, off, w, g, lane); break;
+          default:
+            for (int t = 0; t < KT; ++t) {      // no fragment of this warp in range: keep the ring moving
+              mbar_wait(full_bar + stage, phase);
+              __syncwarp();
+              if (lane == 0) mbar_arrive(empty_bar + stage);
+              if (++stage == AST) { stage = 0; phase ^= 1u; }
+            }
+        }
+        // ---- epilogue: add the accumulators into the CTA's tile W[i][j][k]
+#pragma unroll
+        for (int i = 0; i < A_MI; ++i) {
+          if (i >= mc) continue;
+          const int r = 8 * (w + 8 * i) + g;
+          if (r >= rows_valid) continue;
+          const int u = r / no, ww = r - u * no, pu = p0 + u;
+#pragma unroll
+          for (int j = 0; j < NC; ++j) {
+            const int l = 8 * j + 2 * q2;
+            if (l >= no) continue;                     // no is even: l + 1 < no as well
+            if (grp == 0) {                            // (l,p,q) = (i,j,k)
+              double* d = W + (i64)l * oo + pu * no + ww;
+              d[0] = acc[i][j][0];
+              d[oo] = acc[i][j][1];
+            } else if (grp == 1) {                     // (l,p,q) = (k,j,i)
+              double2* d = reinterpret_cast<double2*>(W + (i64)ww * oo + pu * no + l);
+              double2 v = *d;
+              v.x += acc[i][j][0];
+              v.y += acc[i][j][1];
+              *d = v;
+            } else {                                   // rows (q,p): (l,p,q) = (j,k,i)
+              double* d = W + (i64)pu * oo + l * no + ww;
+              d[0] += acc[i][j][0];
+              d[no] += acc[i][j][1];
+            }
+          }
+        }
+      }
+      named_bar_consumers();      // group grp complete in W before the next group's read-modify-write
+    }
+
+    // ---- energy of this (a,b,c): cctriples.py:149-173 (disconnected part) and 208-237 with (ijk) <-> (abc)
+    {
+      const i64 sab = ((i64)a * nv + b) * oo, sac = ((i64)a * nv + c) * oo, sbc = ((i64)b * nv + c) * oo;
+      for (int idx = tid; idx < oo; idx += A_CONSUMERS) {
+        sm[idx] = p.oovvx[sab + idx];
+        sm[oo + idx] = p.oovvx[sac + idx];
+        sm[2 * oo + idx] = p.oovvx[sbc + idx];
+        sm[3 * oo + idx] = p.t2x[sab + idx];
+        sm[4 * oo + idx] = p.t2x[sac + idx];
+        sm[5 * oo + idx] = p.t2x[sbc + idx];
+      }
+      double* vec = sm + 6 * oo;        // t1[:,a], t1[:,b], t1[:,c], f[:,a], f[:,b], f[:,c], eps_o
+      for (int idx = tid; idx < no; idx += A_CONSUMERS) {
+        vec[idx] = p.t1[(i64)idx * nv + a];
+        vec[no + idx] = p.t1[(i64)idx * nv + b];
+        vec[2 * no + idx] = p.t1[(i64)idx * nv + c];
+        vec[3 * no + idx] = p.fov[(i64)idx * p.ldf + a];
+        vec[4 * no + idx] = p.fov[(i64)idx * p.ldf + b];
+        vec[5 * no + idx] = p.fov[(i64)idx * p.ldf + c];
+        vec[6 * no + idx] = p.eo[idx];
+      }
+      named_bar_consumers();
+      const double* Mab = sm, *Mac = sm + oo, *Mbc = sm + 2 * oo, *Tab = sm + 3 * oo, *Tac = sm + 4 * oo, *Tbc = sm + 5 * oo;
+      const double* t1a = vec, *t1b = vec + no, *t1c = vec + 2 * no, *fa = vec + 3 * no, *fb = vec + 4 * no,
+                   *fc = vec + 5 * no, *eo = vec + 6 * no;
+      const double dv = p.ev[a] + p.ev[b] + p.ev[c];
+      const double wabc = 2.0 - (double)((a == b) + (a == c) + (b == c));
+      auto disc = [&](int I, int J, int Kx) {
+        return Mab[I * no + J] * t1c[Kx] + Mac[I * no + Kx] * t1b[J] + Mbc[J * no + Kx] * t1a[I] +
+               Tab[I * no + J] * fc[Kx] + Tac[I * no + Kx] * fb[J] + Tbc[J * no + Kx] * fa[I];
+      };
+      double e_abc = 0.0;
+      for (int s = tid; s < p.nsorted; s += A_CONSUMERS) {
+        int i, j, k;
+        abc_decode(p.sorted[s], i, j, k);
+        const double w_ijk = W[(i64)i * oo + j * no + k], w_ikj = W[(i64)i * oo + k * no + j];
+        const double w_jik = W[(i64)j * oo + i * no + k], w_jki = W[(i64)j * oo + k * no + i];
+        const double w_kij = W[(i64)k * oo + i * no + j], w_kji = W[(i64)k * oo + j * no + i];
+        const double sc = 1.0 / (1.0 + (double)((i == j) + (i == k) + (j == k)));
+        const double v_ijk = (w_ijk + disc(i, j, k)) * sc, v_ikj = (w_ikj + disc(i, k, j)) * sc;
+        const double v_jik = (w_jik + disc(j, i, k)) * sc, v_jki = (w_jki + disc(j, k, i)) * sc;
+        const double v_kij = (w_kij + disc(k, i, j)) * sc, v_kji = (w_kji + disc(k, j, i)) * sc;
+        const double X = w_ijk * v_ijk + w_ikj * v_ikj + w_jik * v_jik + w_jki * v_jki + w_kij * v_kij + w_kji * v_kji;
+        const double Y = v_ijk + v_jki + v_kij, Z = v_ikj + v_jik + v_kji;
+        const double Wc = w_ijk + w_jki + w_kij, Wo = w_ikj + w_jik + w_kji;
+        e_abc += ((Y - 2.0 * Z) * Wc + (Z - 2.0 * Y) * Wo + 3.0 * X) / (eo[i] + eo[j] + eo[k] - dv);
+      }
+      e_acc += wabc * e_abc;
+      // generic-proxy accesses of the ring are done; the next TMA writes into it go through the async proxy
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      named_bar_consumers();
+      if (tid == 0) mbar_arrive(edone_bar);
+    }
+  }
+
+  // ---- per-CTA partial sum (deterministic: fixed thread -> triple and CTA -> (a,b,c) maps)
+  e_acc = warp_sum(e_acc);
+  if (lane == 0) red[warp] = e_acc;
+  named_bar_consumers();
+  if (tid == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < A_CONSUMERS / 32; ++i) s += red[i];
+    p.partial[blockIdx.x] = s;
+  }
+}
+
+// rank-`rank` tensor map of doubles: dims[0] is the contiguous dimension, strides (in doubles) for dims 1..rank-1
+static int make_tmap_nd(CUtensorMap* tm, const double* base, int rank, const cuuint64_t* dims, const i64* strides,
+                        const cuuint32_t* box) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available"); return 1; }
+  cuuint64_t gstr[4];
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = (cuuint64_t)strides[i] * 8;
+  cuuint32_t est[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, rank, const_cast<double*>(base), dims, gstr, box, est,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("b200cc_t_abc: cuTensorMapEncodeTiled failed (%d)", (int)r); return 1; }
+  return 0;
+}
+
+template <int NC>
+static int launch_abc(const AbcParams& p, const AbcMaps& tm, int grid, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    B200CC_CUDA_OK(cudaFuncSetAttribute(t_abc_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM));
+    configured = true;
+  }
+  t_abc_kernel<NC><<<grid, A_THREADS, A_SMEM, st>>>(p, tm);
+  return check_launch("t_abc_kernel");
+}
+
+}  // namespace b200cc
+
+using namespace b200cc;
+
+extern "C" int b200cc_t_abc_max_no(void) { return 8 * A_NCMAX; }
+
+extern "C" int b200cc_t_abc(const b200cc_t_abc_desc* d, void* stream) {
+  if (!d) { set_error("b200cc_t_abc: null descriptor"); return 1; }
+  if (d->struct_size != (int)sizeof(b200cc_t_abc_desc)) {
+    set_error("b200cc_t_abc: descriptor is %d bytes, this library's b200cc_t_abc_desc is %d (stale binding? see include/b200cc.h)",
+              d->struct_size, (int)sizeof(b200cc_t_abc_desc));
+    return 1;
+  }
+  const int no = d->no, nv = d->nv;
+  if (no <= 0 || nv <= 0 || (no & 1) || (nv & 1) || no > 8 * A_NCMAX || nv > 1023) {
+    set_error("b200cc_t_abc: needs even o <= %d and even v <= 1023 (got o = %d, v = %d)", 8 * A_NCMAX, no, nv);
+    return 1;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (d->nabc <= 0) {
+    if (!d->accumulate) B200CC_CUDA_OK(cudaMemsetAsync(d->et_out, 0, sizeof(double), st));
+    return 0;
+  }
+  if (d->grid <= 0) { set_error("b200cc_t_abc: grid must be positive (the scratch arrays are sized by it)"); return 1; }
+  const int grid = d->grid < d->nabc ? d->grid : d->nabc;
+  AbcParams p;
+  p.no = no; p.nv = nv; p.nabc = d->nabc;
+  p.pp = A_PROWS / no < no ? A_PROWS / no : no;
+  p.tiles_p = (no + p.pp - 1) / p.pp;
+  p.ktv = (nv + ABK - 1) / ABK;
+  p.kto = (no + ABK - 1) / ABK;
+  p.nsorted = d->nsorted;
+  p.abc = d->abc; p.sorted = d->sorted;
+  p.t2x = d->t2x; p.oovvx = d->oovvx; p.t1 = d->t1; p.fov = d->fov; p.eo = d->eo; p.ev = d->ev; p.ldf = d->ldf;
+  p.wtile = d->wtile; p.partial = d->partial;
+  if ((6 * no * no + 7 * no) * (int)sizeof(double) > AST * A_STAGE) { set_error("b200cc_t_abc: o too large for the staging area"); return 1; }
+  const int nc = (no + 7) / 8;
+  const i64 O = no, V = nv;
+  AbcMaps tm;
+  {
+    // lone-index operands: {k, l, slab}
+    cuuint64_t dg[3] = {(cuuint64_t)V, (cuuint64_t)O, (cuuint64_t)(V * V)};
+    i64 sg[2] = {V * V * V, V};
+    cuuint32_t bl[3] = {(cuuint32_t)ABK, (cuuint32_t)(8 * nc), 1};
+    if (make_tmap_nd(&tm.g, d->G, 3, dg, sg, bl)) return 1;
+    cuuint64_t dt[3] = {(cuuint64_t)O, (cuuint64_t)O, (cuuint64_t)(V * V)};
+    i64 stx[2] = {O, O * O};
+    if (make_tmap_nd(&tm.t2x, d->t2x, 3, dt, stx, bl)) return 1;
+    // pair operands: {k, w (fast row index), u (tiled row index), slab}
+    cuuint32_t bp[4] = {(cuuint32_t)ABK, (cuuint32_t)no, (cuuint32_t)p.pp, 1};
+    cuuint64_t d2[4] = {(cuuint64_t)V, (cuuint64_t)O, (cuuint64_t)O, (cuuint64_t)V};
+    i64 s2a[3] = {O * V * V, V * V, V};        // rows (u = p, w = q) of t2[q,p,slab,e]
+    i64 s2b[3] = {V * V, O * V * V, V};        // rows (u = p, w = q) of t2[p,q,slab,e]
+    if (make_tmap_nd(&tm.t2a, d->t2, 4, d2, s2a, bp)) return 1;
+    if (make_tmap_nd(&tm.t2b, d->t2, 4, d2, s2b, bp)) return 1;
+    cuuint64_t dx[4] = {(cuuint64_t)O, (cuuint64_t)O, (cuuint64_t)O, (cuuint64_t)V};
+    i64 sxa[3] = {O, O * O, O * O * O};        // rows (u = p, w = q) of Ox[slab,p,q,m]
+    i64 sxb[3] = {O * O, O, O * O * O};        // rows (u = p, w = q) of Ox[slab,q,p,m]
+    if (make_tmap_nd(&tm.oxa, d->Ox, 4, dx, sxa, bp)) return 1;
+    if (make_tmap_nd(&tm.oxb, d->Ox, 4, dx, sxb, bp)) return 1;
+  }
+  int rc;
+  switch (nc) {
+    case 1: rc = launch_abc<1>(p, tm, grid, st); break;
+    case 2: rc = launch_abc<2>(p, tm, grid, st); break;
+    case 3: rc = launch_abc<3>(p, tm, grid, st); break;
+    case 4: rc = launch_abc<4>(p, tm, grid, st); break;
+    default: rc = launch_abc<5>(p, tm, grid, st); break;
+  }
+  if (rc) return rc;
+  return launch_final_reduce(d->partial, grid, 0, 1, d->et_out, d->accumulate, 1.0, st);
+}

@@ -12,7 +12,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import GemmDesc, Gemm3Desc, T3dDesc, B200ccError, i64
+from ._lib import GemmDesc, Gemm3Desc, T3dDesc, TAbcDesc, B200ccError, i64
 
 NSM = 148                   # B200
 # tile-config override for experiments (0 = library heuristic); see b200cc_gemm_desc.config
@@ -551,6 +551,31 @@ def t_energy_batch(no, nv, ijk, Q, t1, t2, oovv, fov, eo, ev, et, accumulate=Tru
                                                 int(fov.stride(0)), _lib.ptr(eo), _lib.ptr(ev), _lib.ptr(et),
                                                 int(accumulate), _lib.ptr(sc), _lib.stream()),
                "b200cc_t_energy_batch")
+    return et
+
+
+def t_abc_max_no():
+    """largest o the fused (a,b,c)-driven (T) kernel takes (b200cc_t_abc_max_no)"""
+    return int(_lib.get().b200cc_t_abc_max_no())
+
+
+def t_abc(no, nv, abc, sorted_ijk, G, t2, t2x, Ox, oovvx, t1, fov, eo, ev, et, wtile, partial, grid, accumulate=True):
+    """E(T) contributions of the packed virtual triples ``abc`` (int32, a | b << 10 | c << 20, a >= b >= c), fused
+    (a,b,c)-driven kernel (b200cc_t_abc): ``et[0] (+)= ...``.  ``wtile``: grid * o^3 doubles, ``partial``: grid doubles."""
+    d = TAbcDesc()
+    d.struct_size = C.sizeof(TAbcDesc)
+    d.no, d.nv = int(no), int(nv)
+    d.nabc, d.nsorted = int(abc.numel()), int(sorted_ijk.numel())
+    d.abc, d.sorted = _lib.ptr(abc), _lib.ptr(sorted_ijk)
+    d.G, d.t2, d.t2x = _lib.ptr(_c(G, "G")), _lib.ptr(_c(t2, "t2")), _lib.ptr(_c(t2x, "t2x"))
+    d.Ox, d.oovvx, d.t1 = _lib.ptr(_c(Ox, "Ox")), _lib.ptr(_c(oovvx, "oovvx")), _lib.ptr(_c(t1, "t1"))
+    d.fov, d.ldf = _lib.ptr(fov), int(fov.stride(0))
+    d.eo, d.ev = _lib.ptr(eo), _lib.ptr(ev)
+    if wtile.numel() < int(grid) * no ** 3 or partial.numel() < int(grid):
+        raise B200ccError("t_abc: scratch too small for grid = %d" % grid)
+    d.wtile, d.partial, d.et_out = _lib.ptr(wtile), _lib.ptr(partial), _lib.ptr(et)
+    d.accumulate, d.grid = int(bool(accumulate)), int(grid)
+    _lib.check(_lib.get().b200cc_t_abc(C.byref(d), _lib.stream()), "b200cc_t_abc")
     return et
 
 

@@ -539,6 +539,63 @@ class EmuLib:
         return 0
 
 
+    # ---- (T), fused (a,b,c)-driven form ------------------------------------------------------------------
+    def b200cc_t_abc_max_no(self):
+        return 40
+
+    def b200cc_t_abc(self, dref, stream):
+        d = dref._obj
+        self._count("t_abc", 2)
+        no, nv = d.no, d.nv
+        if no % 2 or nv % 2 or no > 40 or nv > 1023:
+            self.err = b"b200cc_t_abc: needs even o <= 40 and even v <= 1023"
+            return 1
+        o2, o3, v2 = no * no, no ** 3, nv * nv
+        G = _vec(d.G, no * nv ** 3).reshape(no, nv, nv, nv)            # [l,x,y,e]
+        t2 = _vec(d.t2, o2 * v2).reshape(no, no, nv, nv)
+        t2x = _vec(d.t2x, o2 * v2).reshape(nv, nv, no, no)              # [x,y,l,m]
+        Ox = _vec(d.Ox, nv * o3).reshape(nv, no, no, no)                # [z,p,q,m] = -<mz|pq>
+        Kx = _vec(d.oovvx, o2 * v2).reshape(nv, nv, no, no)             # [x,y,i,j]
+        t1 = _arr(d.t1, (no, nv), (nv, 1))
+        f = _arr(d.fov, (no, nv), (d.ldf, 1))
+        eo, ev = _vec(d.eo, no), _vec(d.ev, nv)
+        abc = _ints(d.abc, d.nabc)
+        srt = _ints(d.sorted, d.nsorted)
+        si, sj, sk = srt & 1023, (srt >> 10) & 1023, (srt >> 20) & 1023
+        e = np.einsum
+
+        def Gf(x, y, z):                                                # [l,p,q]
+            return (e("le,qpe->lpq", G[:, x, y], t2[:, :, z]) + e("le,pqe->lpq", G[:, x, z], t2[:, :, y])
+                    + e("lm,pqm->lpq", t2x[x, y], Ox[z]) + e("lm,qpm->lpq", t2x[x, z], Ox[y]))
+
+        grid = min(d.grid, d.nabc)
+        tiles = _vec(d.wtile, max(grid, 1) * o3).reshape(max(grid, 1), no, no, no)
+        tot = 0.0
+        for n in range(d.nabc):
+            a, b, c = int(abc[n]) & 1023, (int(abc[n]) >> 10) & 1023, (int(abc[n]) >> 20) & 1023
+            W = Gf(a, b, c) + Gf(c, b, a).transpose(2, 1, 0) + Gf(b, c, a).transpose(2, 0, 1)
+            tiles[n % grid] = W
+            D = (e("ij,k->ijk", Kx[a, b], t1[:, c]) + e("ik,j->ijk", Kx[a, c], t1[:, b]) + e("jk,i->ijk", Kx[b, c], t1[:, a])
+                 + e("ij,k->ijk", t2x[a, b], f[:, c]) + e("ik,j->ijk", t2x[a, c], f[:, b]) + e("jk,i->ijk", t2x[b, c], f[:, a]))
+            w = lambda X, i, j, k: X[i, j, k]
+            sc = 1.0 / (1.0 + (si == sj).astype(float) + (si == sk) + (sj == sk))
+            perms = {"ijk": (si, sj, sk), "ikj": (si, sk, sj), "jik": (sj, si, sk), "jki": (sj, sk, si),
+                     "kij": (sk, si, sj), "kji": (sk, sj, si)}
+            Wp = {key: W[ix] for key, ix in perms.items()}
+            Vp = {key: (W[ix] + D[ix]) * sc for key, ix in perms.items()}
+            X = sum(Wp[key] * Vp[key] for key in perms)
+            Y = Vp["ijk"] + Vp["jki"] + Vp["kij"]
+            Z = Vp["ikj"] + Vp["jik"] + Vp["kji"]
+            Wc = Wp["ijk"] + Wp["jki"] + Wp["kij"]
+            Wo = Wp["ikj"] + Wp["jik"] + Wp["kji"]
+            den = eo[si] + eo[sj] + eo[sk] - (ev[a] + ev[b] + ev[c])
+            wabc = 2.0 - (float(a == b) + float(a == c) + float(b == c))
+            tot += wabc * float(np.sum(((Y - 2 * Z) * Wc + (Z - 2 * Y) * Wo + 3 * X) / den))
+        o = _vec(d.et_out, 1)
+        o[0] = o[0] + tot if d.accumulate else tot
+        return 0
+
+
     # ---- (T) densities -------------------------------------------------------------------------------
     def b200cc_t3_connected_batch(self, no, nv, ntrip, ijk, Q, eo, ev, m3, stream):
         self._count("t3_connected")
