@@ -42,6 +42,12 @@ struct AbcParams {
   double* partial;
 };
 
+// Fire-and-forget FP64 add performed at the L2 (no load round trip in the epilogue).  Every address of the CTA's private
+// tile receives exactly one add per group and the groups are separated by barriers, so the sum order is fixed.
+__device__ __forceinline__ void red_add(double* p, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(p), "d"(v) : "memory");
+}
+
 __device__ __forceinline__ void named_bar_consumers() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 
 template <int MC, int NC>
@@ -226,34 +232,35 @@ __global__ void __launch_bounds__(A_THREADS, 1) t_abc_kernel(const AbcParams p, 
               d[0] = acc[i][j][0];
               d[oo] = acc[i][j][1];
             } else if (grp == 1) {                     // (l,p,q) = (k,j,i)
-              double2* d = reinterpret_cast<double2*>(W + (i64)ww * oo + pu * no + l);
-              double2 v = *d;
-              v.x += acc[i][j][0];
-              v.y += acc[i][j][1];
-              *d = v;
+              double* d = W + (i64)ww * oo + pu * no + l;
+              red_add(d, acc[i][j][0]);
+              red_add(d + 1, acc[i][j][1]);
             } else {                                   // rows (q,p): (l,p,q) = (j,k,i)
               double* d = W + (i64)pu * oo + l * no + ww;
-              d[0] += acc[i][j][0];
-              d[no] += acc[i][j][1];
+              red_add(d, acc[i][j][0]);
+              red_add(d + no, acc[i][j][1]);
             }
           }
         }
       }
-      named_bar_consumers();      // group grp complete in W before the next group's read-modify-write
+      named_bar_consumers();      // group grp complete in W before the next group adds to it / the energy phase reads it
     }
 
     // ---- energy of this (a,b,c): cctriples.py:149-173 (disconnected part) and 208-237 with (ijk) <-> (abc)
     {
       const i64 sab = ((i64)a * nv + b) * oo, sac = ((i64)a * nv + c) * oo, sbc = ((i64)b * nv + c) * oo;
+      // o x o matrices with an odd row pitch: the bracket reads them at all six permutations of (i,j,k)
+      const int ldm = no + 1, mm = no * ldm;
       for (int idx = tid; idx < oo; idx += A_CONSUMERS) {
-        sm[idx] = p.oovvx[sab + idx];
-        sm[oo + idx] = p.oovvx[sac + idx];
-        sm[2 * oo + idx] = p.oovvx[sbc + idx];
-        sm[3 * oo + idx] = p.t2x[sab + idx];
-        sm[4 * oo + idx] = p.t2x[sac + idx];
-        sm[5 * oo + idx] = p.t2x[sbc + idx];
+        const int r = idx / no, dst = idx + r;
+        sm[dst] = p.oovvx[sab + idx];
+        sm[mm + dst] = p.oovvx[sac + idx];
+        sm[2 * mm + dst] = p.oovvx[sbc + idx];
+        sm[3 * mm + dst] = p.t2x[sab + idx];
+        sm[4 * mm + dst] = p.t2x[sac + idx];
+        sm[5 * mm + dst] = p.t2x[sbc + idx];
       }
-      double* vec = sm + 6 * oo;        // t1[:,a], t1[:,b], t1[:,c], f[:,a], f[:,b], f[:,c], eps_o
+      double* vec = sm + 6 * mm;        // t1[:,a], t1[:,b], t1[:,c], f[:,a], f[:,b], f[:,c], eps_o
       for (int idx = tid; idx < no; idx += A_CONSUMERS) {
         vec[idx] = p.t1[(i64)idx * nv + a];
         vec[no + idx] = p.t1[(i64)idx * nv + b];
@@ -264,22 +271,23 @@ __global__ void __launch_bounds__(A_THREADS, 1) t_abc_kernel(const AbcParams p, 
         vec[6 * no + idx] = p.eo[idx];
       }
       named_bar_consumers();
-      const double* Mab = sm, *Mac = sm + oo, *Mbc = sm + 2 * oo, *Tab = sm + 3 * oo, *Tac = sm + 4 * oo, *Tbc = sm + 5 * oo;
+      const double* Mab = sm, *Mac = sm + mm, *Mbc = sm + 2 * mm, *Tab = sm + 3 * mm, *Tac = sm + 4 * mm, *Tbc = sm + 5 * mm;
       const double* t1a = vec, *t1b = vec + no, *t1c = vec + 2 * no, *fa = vec + 3 * no, *fb = vec + 4 * no,
                    *fc = vec + 5 * no, *eo = vec + 6 * no;
       const double dv = p.ev[a] + p.ev[b] + p.ev[c];
       const double wabc = 2.0 - (double)((a == b) + (a == c) + (b == c));
       auto disc = [&](int I, int J, int Kx) {
-        return Mab[I * no + J] * t1c[Kx] + Mac[I * no + Kx] * t1b[J] + Mbc[J * no + Kx] * t1a[I] +
-               Tab[I * no + J] * fc[Kx] + Tac[I * no + Kx] * fb[J] + Tbc[J * no + Kx] * fa[I];
+        return Mab[I * ldm + J] * t1c[Kx] + Mac[I * ldm + Kx] * t1b[J] + Mbc[J * ldm + Kx] * t1a[I] +
+               Tab[I * ldm + J] * fc[Kx] + Tac[I * ldm + Kx] * fb[J] + Tbc[J * ldm + Kx] * fa[I];
       };
       double e_abc = 0.0;
+#pragma unroll 4
       for (int s = tid; s < p.nsorted; s += A_CONSUMERS) {
         int i, j, k;
         abc_decode(p.sorted[s], i, j, k);
-        const double w_ijk = W[(i64)i * oo + j * no + k], w_ikj = W[(i64)i * oo + k * no + j];
-        const double w_jik = W[(i64)j * oo + i * no + k], w_jki = W[(i64)j * oo + k * no + i];
-        const double w_kij = W[(i64)k * oo + i * no + j], w_kji = W[(i64)k * oo + j * no + i];
+        const double w_ijk = __ldcg(&W[(i64)i * oo + j * no + k]), w_ikj = __ldcg(&W[(i64)i * oo + k * no + j]);
+        const double w_jik = __ldcg(&W[(i64)j * oo + i * no + k]), w_jki = __ldcg(&W[(i64)j * oo + k * no + i]);
+        const double w_kij = __ldcg(&W[(i64)k * oo + i * no + j]), w_kji = __ldcg(&W[(i64)k * oo + j * no + i]);
         const double sc = 1.0 / (1.0 + (double)((i == j) + (i == k) + (j == k)));
         const double v_ijk = (w_ijk + disc(i, j, k)) * sc, v_ikj = (w_ikj + disc(i, k, j)) * sc;
         const double v_jik = (w_jik + disc(j, i, k)) * sc, v_jki = (w_jki + disc(j, k, i)) * sc;
@@ -370,7 +378,7 @@ extern "C" int b200cc_t_abc(const b200cc_t_abc_desc* d, void* stream) {
   p.abc = d->abc; p.sorted = d->sorted;
   p.t2x = d->t2x; p.oovvx = d->oovvx; p.t1 = d->t1; p.fov = d->fov; p.eo = d->eo; p.ev = d->ev; p.ldf = d->ldf;
   p.wtile = d->wtile; p.partial = d->partial;
-  if ((6 * no * no + 7 * no) * (int)sizeof(double) > AST * A_STAGE) { set_error("b200cc_t_abc: o too large for the staging area"); return 1; }
+  if ((6 * no * (no + 1) + 7 * no) * (int)sizeof(double) > AST * A_STAGE) { set_error("b200cc_t_abc: o too large for the staging area"); return 1; }
   const int nc = (no + 7) / 8;
   const i64 O = no, V = nv;
   AbcMaps tm;
