@@ -311,6 +311,7 @@ def main():
     ap.add_argument("--t-triples", type=int, default=0, help="(T): time only this many triples per rank (0 = the full job)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-mp", action="store_true", help="skip the mixed-precision (precision='MP') leg")
+    ap.add_argument("--t-compare", action="store_true", help="(T): also time the (i,j,k)-driven formulation of the same job")
     ap.add_argument("--no-c4", action="store_true", help="skip BASELINE configs[3]: the full (T) at o=30, v=280")
     ap.add_argument("--no-lib", action="store_true", help="skip the same-box library bar (reference code on torch/cuBLAS)")
     args = ap.parse_args()
@@ -467,18 +468,37 @@ def main():
                         "is the reference's flop count for the same term over the time of the whole ladder"}
 
     # ---- (T): the FULL job at this size, all (i>=j>=k) triples dealt round-robin to the ranks
-    def t_job(wfn, nsample):
+    def t_job(wfn, nsample, force_ijk=False):
         trip = [t for t in cctriples.triples_list(wfn.no) if not (t[0] == t[1] == t[2])]
+        if cctriples.fused_selected(wfn) and not force_ijk:
+            # fused (a,b,c)-driven kernel (csrc/triples_abc.cu): the units are the virtual triples a >= b >= c, dealt
+            # round-robin to the ranks; --t-triples R times R rounds of one (a,b,c) per SM and rank from the middle of the list
+            lst = cctriples.abc_list(wfn.nv)
+            n = K.NSM * world
+            run = lst if not nsample else lst[lst.size // 2: lst.size // 2 + nsample * n]
+            cctriples.t_tjl_abc(wfn, run[:n])                      # warm-up
+            t_t, et = cuda_time(lambda: cctriples.t_tjl_abc(wfn, run), 1, sync)
+            t_t = rmax(t_t)
+            rate = cctriples.t_flops_abc(wfn.no, wfn.nv, len(run)) / t_t / 1e12
+            full = len(run) == lst.size
+            return {"o": wfn.no, "v": wfn.nv, "tflops": rate, "unit": "TFLOP/s (FP64 executed, whole job over all GPUs)",
+                    "algorithm": "fused (a,b,c)-driven: t3 tile kept on chip (cctriples.py:75-105 + 208-237 in exchanged roles)",
+                    "triples_timed": len(trip) if full else 0, "triples_total": len(trip),
+                    "abc_timed": int(len(run)), "abc_total": int(lst.size), "seconds": t_t,
+                    "frac_of_fp64_peak_per_gpu": rate / world / peak, "e_t": float(et)}, run
         run = trip if not nsample else trip[:: max(1, len(trip) // (nsample * world))][:nsample * world]
         cctriples.t_tjl(wfn, run[:2 * world])                      # warm-up (allocates the Q workspace once)
         t_t, et = cuda_time(lambda: cctriples.t_tjl(wfn, run), 1, sync)
         t_t = rmax(t_t)
         rate = t_flops_per_triple(wfn.no, wfn.nv) * len(run) / t_t / 1e12
         return {"o": wfn.no, "v": wfn.nv, "tflops": rate, "unit": "TFLOP/s (FP64, whole job over all GPUs)",
+                "algorithm": "(i,j,k)-driven: paired GEMMs + energy kernel, t3 through HBM once",
                 "triples_timed": len(run), "triples_total": len(trip), "seconds": t_t,
                 "frac_of_fp64_peak_per_gpu": rate / world / peak, "e_t": float(et)}, run
 
     t_info, t_run = t_job(cc, args.t_triples)
+    if args.t_compare and "abc_total" in t_info:
+        t_info["ijk_driven"] = t_job(cc, args.t_triples, force_ijk=True)[0]
     t_info["amplitudes"] = "after %d CCSD iterations" % len(energies)
 
     # ---- e2e: the same step through the public API with HOST amplitudes: every step uploads t1, t2 (and F)

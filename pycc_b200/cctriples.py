@@ -32,8 +32,9 @@ _QCACHE = {}
 # t_tjl sums the six t3 products of a triple pairwise inside the GEMM (TriplesEngine(paired=True)); B200CC_T_PAIRED=0
 # restores the six-array form
 PAIRED = os.environ.get("B200CC_T_PAIRED", "1") != "0"
-# 'auto' takes the fused (a,b,c)-driven kernel when it applies; False until it is the measured winner on the B200
-AUTO_ABC = False
+# 'auto' takes the fused (a,b,c)-driven kernel when it applies: measured on the B200 it is the faster formulation at both
+# bench shapes (o=40,v=300: 37 s vs 43 s for the whole job; o=30,v=280: 13.2 s vs 14.4 s; profiles/t_abc_probe_r02.json)
+AUTO_ABC = True
 
 # per term q: (occupied index of the <mb|ef> slab and of the t2[x] slab,
 #              (p,q) of t2[p,q] in the particle GEMM, (p,q) of Y[p,q] in the hole GEMM)
@@ -307,6 +308,18 @@ class FusedTriples:
         return self.wtile[:self.no ** 3].view(self.no, self.no, self.no).clone()
 
 
+def fused_selected(ccwfn):
+    """True when t_tjl(ccwfn) runs the fused (a,b,c)-driven kernel (B200CC_T_ALGO / cctriples.ALGO and its shape limits)."""
+    return (ALGO == "abc" or (ALGO == "auto" and AUTO_ABC)) and FusedTriples.applies(ccwfn)
+
+
+def t_flops_abc(no, nv, nabc=None):
+    """FP64 flop EXECUTED by the fused form for ``nabc`` virtual triples (default: the whole job): twelve contractions of
+    2 o^3 K flop, K = v (particle) or o (hole), per (a,b,c)."""
+    n = nv * (nv + 1) * (nv + 2) // 6 - nv if nabc is None else nabc
+    return 12.0 * no ** 3 * (nv + no) * n
+
+
 def t_tjl_abc(ccwfn, abc=None):
     """E(T) through the fused (a,b,c)-driven kernel; same value as :func:`t_tjl`.  Virtual triples are dealt round-robin
     to the ranks of ``ccwfn.comm``; one scalar all-reduce."""
@@ -323,7 +336,7 @@ def t_tjl_abc(ccwfn, abc=None):
 
 def t_tjl(ccwfn, triples=None):
     """E(T), Lee-Rendell formulation (reference: cctriples.py:177-239).  Returns a 0-d device tensor."""
-    if triples is None and (ALGO == "abc" or (ALGO == "auto" and AUTO_ABC)) and FusedTriples.applies(ccwfn):
+    if triples is None and fused_selected(ccwfn):
         return t_tjl_abc(ccwfn)
     eng = TriplesEngine(ccwfn, paired=PAIRED)
     comm = getattr(ccwfn, "comm", None)
