@@ -404,6 +404,38 @@ extern "C" int b200cc_t_abc(const b200cc_t_abc_desc* d, void* stream) {
     if (make_tmap_nd(&tm.oxa, d->Ox, 4, dx, sxa, bp)) return 1;
     if (make_tmap_nd(&tm.oxb, d->Ox, 4, dx, sxb, bp)) return 1;
   }
+  // The tiles are written and read back within a millisecond by the CTA that owns them: ask the L2 to keep them
+  // (persisting access window over the scratch, operands stream past them), so the t3 tile is not written back to HBM
+  // between its groups.  B200CC_TABC_L2PERSIST=0 switches the window off.
+  static const bool persist = [] { const char* e = getenv("B200CC_TABC_L2PERSIST"); return !(e && e[0] == '0'); }();
+  bool window = false;
+  if (persist) {
+    static size_t max_persist = 0, max_window = 0;
+    static bool probed = false;
+    if (!probed) {
+      int dev = 0, v1 = 0, v2 = 0;
+      if (cudaGetDevice(&dev) == cudaSuccess &&
+          cudaDeviceGetAttribute(&v1, cudaDevAttrMaxPersistingL2CacheSize, dev) == cudaSuccess &&
+          cudaDeviceGetAttribute(&v2, cudaDevAttrMaxAccessPolicyWindowSize, dev) == cudaSuccess) {
+        max_persist = (size_t)v1;
+        max_window = (size_t)v2;
+        if (max_persist > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, max_persist) != cudaSuccess) max_persist = 0;
+      }
+      (void)cudaGetLastError();
+      probed = true;
+    }
+    const size_t bytes = (size_t)grid * O * O * O * sizeof(double);
+    if (max_persist > 0 && max_window > 0) {
+      cudaStreamAttrValue av;
+      av.accessPolicyWindow.base_ptr = d->wtile;
+      av.accessPolicyWindow.num_bytes = bytes < max_window ? bytes : max_window;
+      av.accessPolicyWindow.hitRatio = bytes <= max_persist ? 1.0f : (float)((double)max_persist / (double)bytes);
+      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      window = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
+      (void)cudaGetLastError();
+    }
+  }
   int rc;
   switch (nc) {
     case 1: rc = launch_abc<1>(p, tm, grid, st); break;
@@ -411,6 +443,16 @@ extern "C" int b200cc_t_abc(const b200cc_t_abc_desc* d, void* stream) {
     case 3: rc = launch_abc<3>(p, tm, grid, st); break;
     case 4: rc = launch_abc<4>(p, tm, grid, st); break;
     default: rc = launch_abc<5>(p, tm, grid, st); break;
+  }
+  if (window) {
+    cudaStreamAttrValue av;
+    av.accessPolicyWindow.base_ptr = nullptr;
+    av.accessPolicyWindow.num_bytes = 0;
+    av.accessPolicyWindow.hitRatio = 0.0f;
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+    av.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    (void)cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+    (void)cudaGetLastError();
   }
   if (rc) return rc;
   return launch_final_reduce(d->partial, grid, 0, 1, d->et_out, d->accumulate, 1.0, st);
