@@ -10,6 +10,12 @@ RHF, on the stored Dirac blocks (``ovvv``, ``ooov``, ``oovv``):
                                     restated with masks/weights over the full
                                     (a,b,c) cube -- same sum, vectorised
   t_vikings cctriples.py:243-307    full-loop cross-check (same E(T))
+  t3c_abc   cctriples.py:75-105     connected numerator for fixed (a,b,c): an o^3 tile
+  t3d_abc   cctriples.py:149-173    disconnected numerator for fixed (a,b,c)
+  abc_energy                        the Lee-Rendell bracket of cctriples.py:208-237 applied to one
+                                    (a,b,c) tile with the roles of the occupied and virtual indices
+                                    exchanged (the form the fused CUDA kernel evaluates); the sum over
+                                    a >= b >= c equals t_tjl -- checked against the reference's e_t_tjl
 
 Block identities (8-fold symmetry):  ERI[v,v,v,o][x,y,e,i] = ovvv[i,e,y,x],
 ERI[o,v,o,o][m,c,j,k] = ooov[j,k,m,c],  ERI[v,o,v,v][d,k,b,c] = ovvv[k,d,c,b].
@@ -116,6 +122,74 @@ def t_tjl(t1, t2, F, ovvv, ooov, oovv, nfzc=0, triples=None):
         w = 2.0 - (float(i == j) + float(i == k) + float(j == k))
         et += triple_energy(W, V, D, w)
     return et
+
+
+def t3c_abc(a, b, c, t2, ovvv, ooov, F=None, with_denom=False, nfzc=0):
+    """Connected t3 numerator for one (a,b,c) as an (o,o,o) tile   (cctriples.py:83-95), term by term in the
+    reference's order.  Wvvvo[x,y][e,i] = ovvv[i,e,y,x];  Wovoo[:,c,:,:][m,j,k] = ooov[j,k,m,c].
+    ``ovvv`` may be a dict {i: slab} or an array; only slices [:, :, y, x] of it are taken."""
+    no = t2.shape[0]
+
+    def Wv(x, y):                    # [e,i] = <xy|ei> = ovvv[i,e,y,x]
+        return np.stack([np.asarray(ovvv[i])[:, y, x] for i in range(no)], axis=1)
+
+    def Wo(x):                       # [m,j,k] = <mx|jk> = ooov[j,k,m,x]
+        return ooov[:, :, :, x].transpose(2, 0, 1)
+    W = es("ei,kje->ijk", Wv(b, a), t2[:, :, c])
+    W += es("ei,jke->ijk", Wv(c, a), t2[:, :, b])
+    W += es("ek,jie->ijk", Wv(a, c), t2[:, :, b])
+    W += es("ek,ije->ijk", Wv(b, c), t2[:, :, a])
+    W += es("ej,ike->ijk", Wv(c, b), t2[:, :, a])
+    W += es("ej,kie->ijk", Wv(a, b), t2[:, :, c])
+    W -= es("mjk,im->ijk", Wo(c), t2[:, :, a, b])
+    W -= es("mkj,im->ijk", Wo(b), t2[:, :, a, c])
+    W -= es("mij,km->ijk", Wo(b), t2[:, :, c, a])
+    W -= es("mji,km->ijk", Wo(a), t2[:, :, c, b])
+    W -= es("mki,jm->ijk", Wo(a), t2[:, :, b, c])
+    W -= es("mik,jm->ijk", Wo(c), t2[:, :, b, a])
+    if with_denom:
+        return W / _denom_abc(F, no, a, b, c, nfzc)
+    return W
+
+
+def _denom_abc(F, no, a, b, c, nfzc=0):
+    eps = np.diagonal(F)
+    eo, ev = eps[nfzc:nfzc + no], eps[nfzc + no:]
+    return (eo[:, None, None] + eo[None, :, None] + eo[None, None, :]) - (ev[a] + ev[b] + ev[c])
+
+
+def t3d_abc(a, b, c, t1, t2, oovv, F, with_denom=False, nfzc=0):
+    """Disconnected t3 numerator for one (a,b,c)   (cctriples.py:155-163)."""
+    no = t2.shape[0]
+    Fov = F[nfzc:nfzc + no, nfzc + no:]
+    V = es("ij,k->ijk", oovv[:, :, a, b], t1[:, c])
+    V += es("ik,j->ijk", oovv[:, :, a, c], t1[:, b])
+    V += es("jk,i->ijk", oovv[:, :, b, c], t1[:, a])
+    V += es("ij,k->ijk", t2[:, :, a, b], Fov[:, c])
+    V += es("ik,j->ijk", t2[:, :, a, c], Fov[:, b])
+    V += es("jk,i->ijk", t2[:, :, b, c], Fov[:, a])
+    if with_denom:
+        return V / _denom_abc(F, no, a, b, c, nfzc)
+    return V
+
+
+def abc_energy(a, b, c, t1, t2, F, ovvv, ooov, oovv, nfzc=0):
+    """Contribution of the virtual triple a >= b >= c to E(T): ``triple_energy`` (cctriples.py:210-237) on the (o,o,o)
+    tile, i.e. with the roles of (i,j,k) and (a,b,c) exchanged -- 1/(1+delta) over the occupied indices, the i >= j >= k
+    mask, the weight 2 - d_ab - d_ac - d_bc.  Summed over all a >= b >= c this is t_tjl (W and V are symmetric under
+    simultaneous permutations of the occupied and the virtual triple)."""
+    no = t2.shape[0]
+    W = t3c_abc(a, b, c, t2, ovvv, ooov)
+    V = W + t3d_abc(a, b, c, t1, t2, oovv, F, nfzc=nfzc)
+    w = 2.0 - (float(a == b) + float(a == c) + float(b == c))
+    return triple_energy(W, V, _denom_abc(F, no, a, b, c, nfzc), w)
+
+
+def t_tjl_abc(t1, t2, F, ovvv, ooov, oovv, nfzc=0):
+    """E(T) as the sum of abc_energy over a >= b >= c."""
+    nv = t2.shape[2]
+    return sum(abc_energy(a, b, c, t1, t2, F, ovvv, ooov, oovv, nfzc)
+               for a in range(nv) for b in range(a + 1) for c in range(b + 1))
 
 
 def t_vikings(t1, t2, F, ovvv, ooov, oovv, nfzc=0):

@@ -165,3 +165,33 @@ def test_config3_sampled_triples_match_oracle():
         assert abs(want) > 1e-12 and abs(e - want) < 1e-9 * abs(want) + 1e-16, (t, e, want)
     # the batch equals the sum of its members (batching / ordering independence)
     assert abs(float(cctriples.t_tjl(w, trip)) - sum(got)) < 1e-14
+
+
+def test_config3_fused_abc_tiles_match_oracle():
+    """o=30, v=280 through the fused (a,b,c)-driven kernel (the default (T) path at this shape): the E(T) contributions of
+    individual virtual triples and one connected o^3 tile against the numpy oracle's restatement of t3c_abc / t3d_abc
+    (cctriples.py:75-105, 149-173) + the bracket in exchanged roles; the pieces of a partition of a list add up."""
+    no, nv = 30, 280
+    dev = torch.device(DEV)
+    syn = make_synthetic(no, nv, seed=0, device=dev)
+    H = BlockHamiltonian.from_factor(syn, dev, names=("ooov", "oovv", "ovvv"))
+    eo, ev = H.eps[H.o].contiguous(), H.eps[H.v].contiguous()
+    g = torch.Generator(device=dev).manual_seed(3)
+    t1 = 0.01 * torch.randn((no, nv), dtype=torch.float64, device=dev, generator=g)
+    t2 = K.div_d2(H.block("oovv"), eo, ev)
+    w = types.SimpleNamespace(H=H, no=no, nv=nv, o=H.o, v=H.v, comm=None, eps_o=eo, eps_v=ev, t1=t1, t2=t2, mixed=False)
+    assert cctriples.fused_selected(w)
+    eng = cctriples.FusedTriples(w)
+    abc = [(279, 140, 3), (200, 200, 17), (77, 5, 5), (12, 11, 10)]
+    pack = lambda L: cctriples._pack3(*(np.asarray(x) for x in zip(*L)))
+    got = [float(eng.energy(pack([t]))[0]) for t in abc]
+    ovvv = H.block("ovvv").cpu().numpy()
+    ooov, oovv = H.block("ooov").cpu().numpy(), H.block("oovv").cpu().numpy()
+    t1h, t2h, F = t1.cpu().numpy(), t2.cpu().numpy(), H.F.cpu().numpy()
+    for t, e in zip(abc, got):
+        want = to.abc_energy(*t, t1h, t2h, F, ovvv, ooov, oovv)
+        assert abs(want) > 1e-14 and abs(e - want) < 1e-9 * abs(want) + 1e-16, (t, e, want)
+    assert abs(float(eng.energy(pack(abc))[0]) - sum(got)) < 1e-14
+    W = eng.w_tile(*abc[0]).cpu().numpy()
+    ref = to.t3c_abc(*abc[0], t2h, ovvv, ooov)
+    assert np.abs(W - ref).max() < 1e-12 * max(1.0, np.abs(ref).max())

@@ -95,3 +95,15 @@ def test_t_energy(golden):
     if syn.nv <= 10:
         ev = to.t_vikings(t1, t2, syn.F, b["ovvv"], b["ooov"], b["oovv"])
         assert abs(ev - float(g["e_t_vikings"])) < TOL
+
+
+def test_abc_tiles_and_exchanged_role_energy(golden):
+    """t3c_abc / t3d_abc (cctriples.py:75-105, 149-173) against the reference's own outputs, and the Lee-Rendell bracket
+    applied per (a,b,c) tile with exchanged roles -- the formulation of the fused CUDA kernel -- against the reference's
+    E(T) (t_tjl == t_vikings == t_vikings_inverted, its tests/test_005_ccsd_t_energy.py:30-36)."""
+    g, syn = golden
+    b = blocks_from_factor(syn)
+    t1, t2 = g["conv_t1"], g["conv_t2"]
+    assert np.abs(to.t3c_abc(2, 1, 0, t2, b["ovvv"], b["ooov"], syn.F, True) - g["t3c_abc_210"]).max() < TOL
+    assert np.abs(to.t3d_abc(2, 1, 0, t1, t2, b["oovv"], syn.F, True) - g["t3d_abc_210"]).max() < TOL
+    assert abs(to.t_tjl_abc(t1, t2, syn.F, b["ovvv"], b["ooov"], b["oovv"]) - float(g["e_t_tjl"])) < TOL
