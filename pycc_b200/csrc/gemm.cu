@@ -37,6 +37,9 @@ struct Cfg {
 };
 typedef Cfg<4, 2, 4, 8> CfgB;  // 128 x 128,  8 warps
 typedef Cfg<2, 4, 5, 4> CfgC;  //  80 x 128,  8 warps (M = o^2 = 400, 1600, ... divide by 80)
+// tall-skinny products (one extent = o <= 40: the t1 contractions with <mb|ef>, Fae / Fmi builds, r1 terms)
+typedef Cfg<1, 8, 5, 4> CfgD;  //  40 x 256
+typedef Cfg<8, 1, 4, 5> CfgE;  // 256 x  40
 
 struct KParams {
   int M, N, K1, K2;
@@ -178,6 +181,76 @@ __device__ __forceinline__ Unit decode_unit(const KParams& p, int u) {
   return w;
 }
 
+// Epilogue of one work unit: C = alpha*acc + beta*C (or raw partials into the split-K workspace).  With beta != 0 the old
+// values of a whole fragment row are loaded BEFORE the first store of that row: load -> fma -> store pairs in program order
+// serialise on the memory latency (the store waits for its load, the next load issues behind the store) -- measured
+// 20 us per 128 x 128 tile, 1.5 ms of a 4.0 ms short-K product with 11 250 tiles.
+template <class CF, bool TABLE>
+__device__ __forceinline__ void gemm_epilogue(const double (&acc)[CF::MI][CF::NI][2], const KParams& p, const Unit& w,
+                                              int wm, int wn, int g, int q) {
+  constexpr int MI = CF::MI, NI = CF::NI;
+  const bool split = p.ksplit > 1;
+  double* C;
+  if (split) C = p.ws + ((i64)w.z * p.batch + w.b) * (i64)p.M * p.N;
+  else if (TABLE && p.table) C = reinterpret_cast<double*>(p.table[5 * (i64)w.b + 4]);
+  else C = p.C + (i64)w.b * p.sC;
+  const i64 ldo = split ? (i64)p.N : p.ldc;
+  const double alpha = split ? 1.0 : p.alpha, beta = split ? 0.0 : p.beta;
+  const bool cube = !split && p.cube_nv > 0;
+  const bool vec = split ? ((p.N & 1) == 0 && (((i64)p.M * p.N) & 1) == 0) : (p.cvec != 0 || cube);
+  const int nc8 = (p.cube_nv + 7) >> 3;
+#pragma unroll
+  for (int i = 0; i < MI; ++i) {
+    const int row = w.m0 + 8 * (wm + CF::WARPS_M * i) + g;
+    if (row >= p.M) continue;
+    const int cx = cube ? row / p.cube_nv : 0, cy = cube ? row - cx * p.cube_nv : 0;
+    // JC fragment columns at a time: JC loads in flight, then JC stores (a whole row of 8 would cost 48 more registers)
+    constexpr int JC = NI >= 8 ? 4 : NI;
+#pragma unroll
+    for (int j0 = 0; j0 < NI; j0 += JC) {
+      double* cp[JC];
+      double o0[JC], o1[JC];
+#pragma unroll
+      for (int jj = 0; jj < JC; ++jj) {
+        const int j = j0 + jj;
+        const int col = w.n0 + 8 * (wn + CF::WARPS_N * j) + 2 * q;
+        // (T): Q stored as 4 KB cubes so that the energy kernel reads it in fully contiguous runs
+        cp[jj] = cube ? C + ((((i64)(cx >> 3) * nc8 + (cy >> 3)) * nc8 + (col >> 3)) << 9) + ((cx & 7) << 6) +
+                            ((cy & 7) << 3) + (col & 7)
+                      : C + (i64)row * ldo + col;
+        o0[jj] = o1[jj] = 0.0;
+        if (beta != 0.0 && col < p.N) {
+          if (vec && col + 1 < p.N) {
+            const double2 o = *reinterpret_cast<const double2*>(cp[jj]);
+            o0[jj] = o.x;
+            o1[jj] = o.y;
+          } else {
+            o0[jj] = cp[jj][0];
+            if (col + 1 < p.N) o1[jj] = cp[jj][1];
+          }
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < JC; ++jj) {
+        const int j = j0 + jj;
+        const int col = w.n0 + 8 * (wn + CF::WARPS_N * j) + 2 * q;
+        if (j >= NI || col >= p.N) continue;
+        double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
+        if (beta != 0.0) {
+          v0 += beta * o0[jj];
+          v1 += beta * o1[jj];
+        }
+        if (vec && col + 1 < p.N) {
+          *reinterpret_cast<double2*>(cp[jj]) = make_double2(v0, v1);
+        } else {
+          cp[jj][0] = v0;
+          if (col + 1 < p.N) cp[jj][1] = v1;
+        }
+      }
+    }
+  }
+}
+
 template <class CF, bool TA, bool TB, int VEC>
 __global__ void __launch_bounds__(CF::NT, 1) dgemm_kernel(const KParams p) {
   extern __shared__ __align__(16) double smem[];
@@ -283,47 +356,7 @@ __global__ void __launch_bounds__(CF::NT, 1) dgemm_kernel(const KParams p) {
     }
 
     // ---- epilogue: C = alpha*acc + beta*C, or raw partials into the split-K workspace
-    const bool split = p.ksplit > 1;
-    double* C;
-    if (split) C = p.ws + ((i64)w.z * p.batch + w.b) * (i64)p.M * p.N;
-    else if (p.table) C = reinterpret_cast<double*>(p.table[5 * (i64)w.b + 4]);
-    else C = p.C + (i64)w.b * p.sC;
-    const i64 ldo = split ? (i64)p.N : p.ldc;
-    const double alpha = split ? 1.0 : p.alpha, beta = split ? 0.0 : p.beta;
-    const bool cube = !split && p.cube_nv > 0;
-    const bool vec = split ? ((p.N & 1) == 0 && (((i64)p.M * p.N) & 1) == 0) : (p.cvec != 0 || cube);
-    const int nc8 = (p.cube_nv + 7) >> 3;
-#pragma unroll
-    for (int i = 0; i < MI; ++i) {
-      const int row = w.m0 + 8 * (wm + CF::WARPS_M * i) + g;
-      if (row >= p.M) continue;
-      const int cx = cube ? row / p.cube_nv : 0, cy = cube ? row - cx * p.cube_nv : 0;
-#pragma unroll
-      for (int j = 0; j < NI; ++j) {
-        const int col = w.n0 + 8 * (wn + CF::WARPS_N * j) + 2 * q;
-        if (col >= p.N) continue;
-        // (T): Q stored as 4 KB cubes so that the energy kernel reads it in fully contiguous runs
-        double* c = cube ? C + ((((i64)(cx >> 3) * nc8 + (cy >> 3)) * nc8 + (col >> 3)) << 9) + ((cx & 7) << 6) +
-                               ((cy & 7) << 3) + (col & 7)
-                         : C + (i64)row * ldo + col;
-        double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
-        if (vec && col + 1 < p.N) {
-          if (beta != 0.0) {
-            const double2 o = *reinterpret_cast<const double2*>(c);
-            v0 += beta * o.x;
-            v1 += beta * o.y;
-          }
-          *reinterpret_cast<double2*>(c) = make_double2(v0, v1);
-        } else {
-          if (beta != 0.0) v0 += beta * c[0];
-          c[0] = v0;
-          if (col + 1 < p.N) {
-            if (beta != 0.0) v1 += beta * c[1];
-            c[1] = v1;
-          }
-        }
-      }
-    }
+    gemm_epilogue<CF, true>(acc, p, w, wm, wn, g, q);
   }
   cp_async_wait<0>();
 }
@@ -375,7 +408,7 @@ template <class CF>
 __device__ __forceinline__ void mma_select(double (&acc)[CF::MI][CF::NI][2], const double (&a)[CF::MI],
                                            const double (&b)[CF::NI], int code) {
   constexpr int MI = CF::MI, MH = (CF::MI + 1) / 2, NI = CF::NI;
-  static_assert(NI == 4 || NI == 8, "mma_select is written for NI = 4 or 8");
+  static_assert(NI == 4 || NI == 5 || NI == 8, "mma_select is written for NI = 4, 5 or 8");
   // code = 8 * (rows: 0 = all MI, 1 = first ceil(MI/2)) + (in-range N fragments - 1)
 #define B200CC_ARM(C, MC, NC) \
   case C: mma_block<CF, MC, (NC <= NI ? NC : NI)>(acc, a, b); break;
@@ -538,48 +571,8 @@ __global__ void __launch_bounds__(CF::NT + WS_PRODUCER_THREADS, 1) dgemm_ws_kern
       consume_unit<CF, TA, TB>(acc, smem, full_bar, empty_bar, stage, phase, w.nkt, code, wm, wn, g, q, lane);
     }
 
-    // ---- epilogue (same as the plain kernel)
-    const bool split = p.ksplit > 1;
-    double* C;
-    if (split) C = p.ws + ((i64)w.z * p.batch + w.b) * (i64)p.M * p.N;
-    else if (p.table) C = reinterpret_cast<double*>(p.table[5 * (i64)w.b + 4]);
-    else C = p.C + (i64)w.b * p.sC;
-    const i64 ldo = split ? (i64)p.N : p.ldc;
-    const double alpha = split ? 1.0 : p.alpha, beta = split ? 0.0 : p.beta;
-    const bool cube = !split && p.cube_nv > 0;
-    const bool vec = split ? ((p.N & 1) == 0 && (((i64)p.M * p.N) & 1) == 0) : (p.cvec != 0 || cube);
-    const int nc8 = (p.cube_nv + 7) >> 3;
-#pragma unroll
-    for (int i = 0; i < MI; ++i) {
-      const int row = w.m0 + 8 * (wm + CF::WARPS_M * i) + g;
-      if (row >= p.M) continue;
-      const int cx = cube ? row / p.cube_nv : 0, cy = cube ? row - cx * p.cube_nv : 0;
-#pragma unroll
-      for (int j = 0; j < NI; ++j) {
-        const int col = w.n0 + 8 * (wn + CF::WARPS_N * j) + 2 * q;
-        if (col >= p.N) continue;
-        // (T): Q stored as 4 KB cubes so that the energy kernel reads it in fully contiguous runs
-        double* c = cube ? C + ((((i64)(cx >> 3) * nc8 + (cy >> 3)) * nc8 + (col >> 3)) << 9) + ((cx & 7) << 6) +
-                               ((cy & 7) << 3) + (col & 7)
-                         : C + (i64)row * ldo + col;
-        double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
-        if (vec && col + 1 < p.N) {
-          if (beta != 0.0) {
-            const double2 o = *reinterpret_cast<const double2*>(c);
-            v0 += beta * o.x;
-            v1 += beta * o.y;
-          }
-          *reinterpret_cast<double2*>(c) = make_double2(v0, v1);
-        } else {
-          if (beta != 0.0) v0 += beta * c[0];
-          c[0] = v0;
-          if (col + 1 < p.N) {
-            if (beta != 0.0) v1 += beta * c[1];
-            c[1] = v1;
-          }
-        }
-      }
-    }
+    // ---- epilogue: C = alpha*acc + beta*C, or raw partials into the split-K workspace
+    gemm_epilogue<CF, true>(acc, p, w, wm, wn, g, q);
   }
 }
 
@@ -733,47 +726,8 @@ __global__ void __launch_bounds__(CF::NT + WS_PRODUCER_THREADS, 1)
       }
     }
 
-    // ---- epilogue
-    const bool split = p.ksplit > 1;
-    double* C;
-    if (split) C = p.ws + ((i64)w.z * p.batch + w.b) * (i64)p.M * p.N;
-    else C = p.C + (i64)w.b * p.sC;
-    const i64 ldo = split ? (i64)p.N : p.ldc;
-    const double alpha = split ? 1.0 : p.alpha, beta = split ? 0.0 : p.beta;
-    const bool cube = !split && p.cube_nv > 0;
-    const bool vec = split ? ((p.N & 1) == 0 && (((i64)p.M * p.N) & 1) == 0) : (p.cvec != 0 || cube);
-    const int nc8 = (p.cube_nv + 7) >> 3;
-#pragma unroll
-    for (int i = 0; i < MI; ++i) {
-      const int row = w.m0 + 8 * (wm + CF::WARPS_M * i) + g;
-      if (row >= p.M) continue;
-      const int cx = cube ? row / p.cube_nv : 0, cy = cube ? row - cx * p.cube_nv : 0;
-#pragma unroll
-      for (int j = 0; j < NI; ++j) {
-        const int col = w.n0 + 8 * (wn + CF::WARPS_N * j) + 2 * q;
-        if (col >= p.N) continue;
-        // (T): Q stored as 4 KB cubes so that the energy kernel reads it in fully contiguous runs
-        double* c = cube ? C + ((((i64)(cx >> 3) * nc8 + (cy >> 3)) * nc8 + (col >> 3)) << 9) + ((cx & 7) << 6) +
-                               ((cy & 7) << 3) + (col & 7)
-                         : C + (i64)row * ldo + col;
-        double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
-        if (vec && col + 1 < p.N) {
-          if (beta != 0.0) {
-            const double2 o = *reinterpret_cast<const double2*>(c);
-            v0 += beta * o.x;
-            v1 += beta * o.y;
-          }
-          *reinterpret_cast<double2*>(c) = make_double2(v0, v1);
-        } else {
-          if (beta != 0.0) v0 += beta * c[0];
-          c[0] = v0;
-          if (col + 1 < p.N) {
-            if (beta != 0.0) v1 += beta * c[1];
-            c[1] = v1;
-          }
-        }
-      }
-    }
+    // ---- epilogue: C = alpha*acc + beta*C, or raw partials into the split-K workspace
+    gemm_epilogue<CF, false>(acc, p, w, wm, wn, g, q);
   }
 }
 
@@ -1000,6 +954,13 @@ extern "C" int b200cc_dgemm(const b200cc_gemm_desc* d, void* stream) {
     const double c4 = cost(128, 4, 128, 2, 1.0), c5 = cost(80, 2, 128, 4, 0.97);
     cfg = (d->M >= 80 && c5 < 0.97 * c4) ? 5 : 4;
     if (tma_ok) cfg += 2;   // same tiles, operands staged by the TMA unit instead of cp.async producer warps
+    // one extent <= 40 (= o at the bench shapes): a 40-wide tile wastes no fragment of it (config 8/9 = 40 x 256 /
+    // 256 x 40; +2 = TMA).  kernels.auto_ksplit mirrors this rule when it counts output tiles.
+    static const bool skinny = [] { const char* e = getenv("B200CC_GEMM_SKINNY"); return !(e && e[0] == '0'); }();
+    if (skinny && d->out_cube_nv == 0 && p.K3 == 0 && !d->bcoords) {
+      if (d->M <= 40) cfg = tma_ok ? 10 : 8;
+      else if (d->N <= 40) cfg = tma_ok ? 11 : 9;
+    }
   }
   if (d->out_cube_nv > 0 && (cfg != 6 && cfg != 7 || d->beta != 0.0 || ksplit > 1)) {
     set_error("b200cc_dgemm: out_cube_nv needs a TMA kernel (config 6/7), beta = 0 and no split-K");
@@ -1011,6 +972,12 @@ extern "C" int b200cc_dgemm(const b200cc_gemm_desc* d, void* stream) {
   if (cfg == 2) rc = dispatch<CfgB, false>(p, ta, tb, v2, st);
   else if (cfg == 4) rc = dispatch<CfgB, true>(p, ta, tb, v2, st);
   else if (cfg == 5) rc = dispatch<CfgC, true>(p, ta, tb, v2, st);
+  else if (cfg == 8) rc = dispatch<CfgD, true>(p, ta, tb, v2, st);
+  else if (cfg == 9) rc = dispatch<CfgE, true>(p, ta, tb, v2, st);
+  else if (cfg == 10 || cfg == 11) {
+    if (!tma_ok) { set_error("b200cc_dgemm: config 10/11 (TMA) needs K-major 16-byte aligned operands without an address table"); return 1; }
+    rc = cfg == 10 ? launch_tma<CfgD>(p, st) : launch_tma<CfgE>(p, st);
+  }
   else if (cfg == 6) {
     if (!tma_ok) { set_error("b200cc_dgemm: config 6 (TMA) needs K-major 16-byte aligned operands without an address table"); return 1; }
     rc = launch_tma<CfgB>(p, st);

@@ -36,11 +36,24 @@ def _dev(x):
     return x.device
 
 
+SKINNY = os.environ.get("B200CC_GEMM_SKINNY", "1") != "0"
+
+
+def _gemm_tiles(M, N):
+    """output tiles of one batch entry under the library's tile choice (gemm.cu: 40 x 256 / 256 x 40 tiles when one
+    extent is <= 40, else 128 x 128)"""
+    if SKINNY and M <= 40:
+        return (N + 255) // 256
+    if SKINNY and N <= 40:
+        return (M + 255) // 256
+    return ((M + 127) // 128) * ((N + 127) // 128)
+
+
 def auto_ksplit(M, N, K, batch):
     """Split-K factor.  The GEMM is persistent (one CTA per SM doing ceil(units/148) rounds), so splitting K
     pays when the output has too few tiles to fill the SMs (Fae, Fmi, r1 terms) or when it fills the last
     round badly (Wmnij: 169 tiles = 2 rounds at 57 %); each split costs an extra M*N partial write + read."""
-    tiles = ((M + 127) // 128) * ((N + 127) // 128) * batch
+    tiles = _gemm_tiles(M, N) * batch
     kt = (K + 15) // 16
     if kt < 64 or tiles >= 8 * NSM:
         return 1

@@ -207,3 +207,37 @@ def test_dgemm_tma_batch_segments_splitk():
     C = torch.empty(M, N, dtype=torch.float64, device=DEV)
     K.dgemm(M, N, Kd, A, Kd, 0, B, Kd, 0, C, N, ksplit=7, config=6)
     assert relerr(C, A @ B.t()) < 1e-12
+
+
+SKINNY = [(40, 300, 300), (8, 700, 64), (30, 257, 1000), (40, 40, 5000), (3600, 40, 300), (1000, 24, 90), (257, 38, 17),
+          (40, 1300, 40)]
+
+
+@pytest.mark.parametrize("M,N,Kd", SKINNY)
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("batch", [1, 5])
+def test_dgemm_skinny_tiles(M, N, Kd, ta, tb, batch):
+    """one extent <= 40 takes the 40 x 256 / 256 x 40 tile configurations (gemm.cu configs 8-11: cp.async producers for
+    transposed / unaligned operands, TMA for K-major ones), with split-K chosen by kernels.auto_ksplit"""
+    A = rnd(batch, Kd, M, seed=1) if ta else rnd(batch, M, Kd, seed=1)
+    B = rnd(batch, Kd, N, seed=2) if tb else rnd(batch, N, Kd, seed=2)
+    C0 = rnd(batch, M, N, seed=3)
+    C = C0.clone()
+    K.dgemm(M, N, Kd, A, A.stride(1), ta, B, B.stride(1), tb, C, N, alpha=1.25, beta=0.5, batch=batch,
+            sA=M * Kd, sB=N * Kd, sC=M * N)
+    Am = A.transpose(1, 2) if ta else A
+    Bm = B.transpose(1, 2) if tb else B
+    ref = 1.25 * torch.einsum("bmk,bnk->bmn", Am, Bm) + 0.5 * C0
+    assert relerr(C, ref) < 1e-12
+
+
+@pytest.mark.parametrize("cfg", [8, 9, 10, 11])
+def test_dgemm_skinny_configs_forced_on_general_shapes(cfg):
+    """the skinny tile configurations are ordinary tilings: forced onto a shape with several ragged tiles in both
+    directions they give the same product"""
+    M, N, Kd = 300, 530, 777 + (cfg % 2)
+    Kd += Kd % 2
+    A, B = rnd(M, Kd, seed=4), rnd(N, Kd, seed=5)
+    C = torch.zeros(M, N, dtype=torch.float64, device=DEV)
+    K.dgemm(M, N, Kd, A, Kd, 0, B, Kd, 0, C, N, config=cfg, ksplit=1)
+    assert relerr(C, A @ B.t()) < 1e-12
