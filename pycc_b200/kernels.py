@@ -55,6 +55,10 @@ def auto_ksplit(M, N, K, batch):
     round badly (Wmnij: 169 tiles = 2 rounds at 57 %); each split costs an extra M*N partial write + read."""
     tiles = _gemm_tiles(M, N) * batch
     kt = (K + 15) // 16
+    if kt >= 2048 and 8 * NSM <= tiles < 16 * NSM:
+        # long-K products are scheduled dynamically (one CTA per unit): with 8-16 units per SM the last wave costs up to a
+        # whole unit (measured: Z in pair form, 1316 units of 2822 k-tiles, 0.92 of the tensor bound); halves finish closer
+        return 2
     if kt < 64 or tiles >= 8 * NSM:
         return 1
     best, best_t = 1, None
