@@ -59,6 +59,7 @@ struct KParams {
   int cube_nv;   // > 0: C written as contiguous 8x8x8 cubes of (x = row / nv, y = row % nv, z = col)
   // third / fourth K segment (TMA kernels only): kt2, kt3 = cumulative k-tile counts after segments 2 and 3
   int K3, K4, kt2, kt3, bc_stride;
+  int tile0, compact;   // split-K of the LAST wave only: units cover output tiles [tile0, tiles*batch), partials in compact tile slots
   const double *A3, *B3, *A4, *B4;
   i64 lda3, ldb3, lda4, ldb4, sA3, sB3, sA4, sB4;
   int nbA3, nbB3, nbA4, nbB4;
@@ -155,7 +156,7 @@ static inline int pick_grid(const KParams& p) {
 }
 
 struct Unit {
-  int m0, n0, b, z, kt_begin, nkt;
+  int m0, n0, b, z, kt_begin, nkt, tidx;
 };
 struct LState {
   const double *A1, *B1, *A2, *B2;
@@ -165,9 +166,10 @@ struct LState {
 template <class CF>
 __device__ __forceinline__ Unit decode_unit(const KParams& p, int u) {
   Unit w;
-  const int per = p.tiles * p.batch;
+  const int per = p.tiles * p.batch - p.tile0;      // output tiles covered by this launch (all of them unless tile0 > 0)
   w.z = u / per;
-  const int rem = u - w.z * per;
+  w.tidx = u - w.z * per;
+  const int rem = p.tile0 + w.tidx;
   w.b = rem / p.tiles;
   const int t = rem - w.b * p.tiles;
   int tm, tn;
@@ -190,14 +192,17 @@ __device__ __forceinline__ void gemm_epilogue(const double (&acc)[CF::MI][CF::NI
                                               int wm, int wn, int g, int q) {
   constexpr int MI = CF::MI, NI = CF::NI;
   const bool split = p.ksplit > 1;
+  const bool compact = split && p.compact != 0;     // partial tile (z, tidx) as a dense BM x BN block of the workspace
   double* C;
-  if (split) C = p.ws + ((i64)w.z * p.batch + w.b) * (i64)p.M * p.N;
+  if (compact) C = p.ws + ((i64)w.z * (p.tiles * p.batch - p.tile0) + w.tidx) * (i64)(CF::BM * CF::BN) -
+                   ((i64)w.m0 * CF::BN + w.n0);
+  else if (split) C = p.ws + ((i64)w.z * p.batch + w.b) * (i64)p.M * p.N;
   else if (TABLE && p.table) C = reinterpret_cast<double*>(p.table[5 * (i64)w.b + 4]);
   else C = p.C + (i64)w.b * p.sC;
-  const i64 ldo = split ? (i64)p.N : p.ldc;
+  const i64 ldo = compact ? (i64)CF::BN : (split ? (i64)p.N : p.ldc);
   const double alpha = split ? 1.0 : p.alpha, beta = split ? 0.0 : p.beta;
   const bool cube = !split && p.cube_nv > 0;
-  const bool vec = split ? ((p.N & 1) == 0 && (((i64)p.M * p.N) & 1) == 0) : (p.cvec != 0 || cube);
+  const bool vec = compact ? true : (split ? ((p.N & 1) == 0 && (((i64)p.M * p.N) & 1) == 0) : (p.cvec != 0 || cube));
   const int nc8 = (p.cube_nv + 7) >> 3;
 #pragma unroll
   for (int i = 0; i < MI; ++i) {
@@ -747,6 +752,47 @@ static int make_tmap(CUtensorMap* tm, const double* base, int rows, int K, i64 l
   return 0;
 }
 
+// ---- split-K of the last wave ------------------------------------------------------------------------------------
+// A long-K product with U units runs floor(U / #SM) full waves and one wave with U mod #SM units that costs a whole unit
+// time however few they are (8-GPU shapes: 1128 units = 7 waves + 92 units -> 8 unit times for 7.62 of work).  The full
+// waves are launched as they are; the remaining output tiles get their own launch with K split s ways (s chosen so that
+// rem * s fills whole waves of 1/s-units), raw partials in compact BM x BN slots of a library-owned workspace, and a
+// reduction kernel that applies alpha / beta.  Deterministic: the partials of a tile are summed in split order.
+__global__ void splitk_reduce_tail_kernel(const double* __restrict__ ws, int ksplit, int ntail, int tile0, int tiles,
+                                          int tiles_m, int tiles_n, int nfast, int BM, int BN, int M, int N, double alpha,
+                                          double beta, double* C, i64 ldc, i64 sC) {
+  const int tidx = blockIdx.x;
+  const int idx = tile0 + tidx;
+  const int b = idx / tiles, t = idx - b * tiles;
+  int tm, tn;
+  if (nfast) { tn = t % tiles_n; tm = t / tiles_n; }
+  else { tm = t % tiles_m; tn = t / tiles_m; }
+  const int m0 = tm * BM, n0 = tn * BN;
+  const i64 slot = (i64)BM * BN;
+  for (int e = threadIdx.x; e < BM * BN; e += blockDim.x) {
+    const int r = e / BN, c = e - r * BN;
+    const int row = m0 + r, col = n0 + c;
+    if (row >= M || col >= N) continue;
+    double sum = 0.0;
+    for (int z = 0; z < ksplit; ++z) sum += ws[((i64)z * ntail + tidx) * slot + e];
+    double* dst = C + (i64)b * sC + (i64)row * ldc + col;
+    *dst = (beta != 0.0) ? alpha * sum + beta * (*dst) : alpha * sum;
+  }
+}
+
+static double* tail_workspace(size_t doubles) {
+  static double* buf = nullptr;
+  static size_t cap = 0;
+  if (doubles > cap) {
+    if (buf) cudaFree(buf);
+    buf = nullptr;
+    cap = 0;
+    if (cudaMalloc(&buf, doubles * sizeof(double)) != cudaSuccess) { (void)cudaGetLastError(); buf = nullptr; return nullptr; }
+    cap = doubles;
+  }
+  return buf;
+}
+
 template <class CF>
 static int launch_tma(KParams& p, cudaStream_t st) {
   p.tiles_m = (p.M + CF::BM - 1) / CF::BM;
@@ -779,6 +825,45 @@ static int launch_tma(KParams& p, cudaStream_t st) {
   if (!configured) {
     B200CC_CUDA_OK(cudaFuncSetAttribute(dgemm_tma_kernel<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
+  }
+  // split-K of the last wave (see above): long-K, no caller split, plain output
+  static const bool tail_on = [] { const char* e = getenv("B200CC_GEMM_TAIL"); return !(e && e[0] == '0'); }();
+  const int nsm = sm_count();
+  // Only where waves are countable: few of them (the unsynchronised end of a long run of waves costs as much as the split
+  // saves -- measured at N = 1: ladder 195.8 -> 199.1 ms) and tiles of equal cost (M = 820 has a half-cost seventh row tile:
+  // a uniform split by the caller balances those better -- measured at the N = 8 ladder shape: 26.5 vs 28.3 ms).
+  const bool ragged_m = p.tiles_m <= 16 && (p.M % CF::BM) != 0;
+  if (tail_on && p.ksplit == 1 && p.kt_total >= 512 && p.cube_nv == 0 && p.units > nsm && p.units <= 16 * nsm && !ragged_m) {
+    const int rem = p.units % nsm;
+    int best_s = 1;
+    double best_c = 1.0;
+    if (rem > 0) {
+      for (int sp = 2; sp <= 16 && p.kt_total / sp >= 96; ++sp) {
+        const double c = (double)(((i64)rem * sp + nsm - 1) / nsm) / sp + 0.01 * sp;   // waves of 1/sp-units (+ per-split overhead)
+        if (c < best_c - 1e-9) { best_c = c; best_s = sp; }
+      }
+    }
+    if (best_s > 1 && best_c < 0.9) {
+      double* ws = tail_workspace((size_t)rem * best_s * CF::BM * CF::BN);
+      if (ws) {
+        KParams bulk = p;
+        bulk.units = p.units - rem;
+        dgemm_tma_kernel<CF><<<pick_grid(bulk), CF::NT + WS_PRODUCER_THREADS, SMEM, st>>>(bulk, tm);
+        if (check_launch("dgemm_tma_kernel")) return 1;
+        KParams tail = p;
+        tail.tile0 = p.units - rem;
+        tail.compact = 1;
+        tail.ksplit = best_s;
+        tail.ws = ws;
+        tail.kt_per_split = (p.kt_total + best_s - 1) / best_s;
+        tail.units = rem * best_s;
+        dgemm_tma_kernel<CF><<<pick_grid(tail), CF::NT + WS_PRODUCER_THREADS, SMEM, st>>>(tail, tm);
+        if (check_launch("dgemm_tma_kernel")) return 1;
+        splitk_reduce_tail_kernel<<<rem, 256, 0, st>>>(ws, best_s, rem, tail.tile0, p.tiles, p.tiles_m, p.tiles_n, p.nfast,
+                                                       CF::BM, CF::BN, p.M, p.N, p.alpha, p.beta, p.C, p.ldc, p.sC);
+        return check_launch("splitk_reduce_tail_kernel");
+      }
+    }
   }
   const int grid = pick_grid(p);
   dgemm_tma_kernel<CF><<<grid, CF::NT + WS_PRODUCER_THREADS, SMEM, st>>>(p, tm);
@@ -898,6 +983,7 @@ extern "C" int b200cc_dgemm(const b200cc_gemm_desc* d, void* stream) {
   p.bc_stride = p.K3 > 0 ? 8 : 4;
   if (d->K3 > 0 && d->K2 <= 0) { set_error("b200cc_dgemm: a third K segment needs the second one"); return 1; }
   p.ksplit = ksplit; p.batch = d->batch; p.ws = d->workspace;
+  p.tile0 = 0; p.compact = 0;
   p.kt_per_split = (p.kt_total + ksplit - 1) / ksplit;
   if (p.kt_per_split < 1) p.kt_per_split = 1;
   p.bcoords = d->bcoords;

@@ -49,7 +49,7 @@ def _gemm_tiles(M, N):
     return ((M + 127) // 128) * ((N + 127) // 128)
 
 
-def auto_ksplit(M, N, K, batch):
+def auto_ksplit(M, N, K, batch, tma_like=False):
     """Split-K factor.  The GEMM is persistent (one CTA per SM doing ceil(units/148) rounds), so splitting K
     pays when the output has too few tiles to fill the SMs (Fae, Fmi, r1 terms) or when it fills the last
     round badly (Wmnij: 169 tiles = 2 rounds at 57 %); each split costs an extra M*N partial write + read."""
@@ -59,6 +59,10 @@ def auto_ksplit(M, N, K, batch):
         # long-K products are scheduled dynamically (one CTA per unit): with 8-16 units per SM the last wave costs up to a
         # whole unit (measured: Z in pair form, 1316 units of 2822 k-tiles, 0.92 of the tensor bound); halves finish closer
         return 2
+    if tma_like and kt >= 512 and NSM < tiles <= 16 * NSM and not (M % 128 and (M + 127) // 128 <= 16):
+        # K-major long-K products with equal-cost tiles and few waves: the library splits K for the LAST wave only
+        # (gemm.cu, "split-K of the last wave"; same conditions there)
+        return 1
     if kt < 64 or tiles >= 8 * NSM:
         return 1
     best, best_t = 1, None
@@ -289,7 +293,8 @@ def dgemm(M, N, K, A, lda, transA, B, ldb, transB, Cmat, ldc, alpha=1.0, beta=0.
             setattr(d, "strideA%d" % n_, int(sAs)); setattr(d, "strideB%d" % n_, int(sBs))
             K34 += int(Ks)
     if ksplit is None:
-        ksplit = auto_ksplit(M, N, K + K2 + K34, batch)
+        ksplit = auto_ksplit(M, N, K + K2 + K34, batch,
+                             tma_like=not transA and not transB and table is None and not out_cube_nv)
     d.ksplit = int(ksplit)
     d.config = int(config) if config else DEFAULT_GEMM_CONFIG
     d.out_cube_nv = int(out_cube_nv)

@@ -241,3 +241,20 @@ def test_dgemm_skinny_configs_forced_on_general_shapes(cfg):
     C = torch.zeros(M, N, dtype=torch.float64, device=DEV)
     K.dgemm(M, N, Kd, A, Kd, 0, B, Kd, 0, C, N, config=cfg, ksplit=1)
     assert relerr(C, A @ B.t()) < 1e-12
+
+
+@pytest.mark.parametrize("M,N,Kd,batch", [(2000, 1500, 9000, 1), (1290, 1100, 8200, 2), (820, 3000, 8192, 2)])
+@pytest.mark.parametrize("beta", [0.0, -0.5])
+def test_dgemm_split_k_of_the_last_wave(M, N, Kd, batch, beta):
+    """long-K K-major products with more units than SMs: the full waves run unsplit, the tiles of the last partial wave get
+    their own launch with K split (compact partial tiles + reduction kernel) -- same product, bit-identical between runs"""
+    A, B = rnd(batch, M, Kd, seed=6), rnd(batch, N, Kd, seed=7)
+    C0 = rnd(batch, M, N, seed=8)
+    outs = []
+    for _ in range(2):
+        C = C0.clone()
+        K.dgemm(M, N, Kd, A, Kd, 0, B, Kd, 0, C, N, alpha=0.5, beta=beta, batch=batch, sA=M * Kd, sB=N * Kd, sC=M * N)
+        outs.append(C)
+    ref = 0.5 * torch.einsum("bmk,bnk->bmn", A, B) + beta * C0
+    assert relerr(outs[0], ref) < 1e-12
+    assert torch.equal(outs[0], outs[1])
