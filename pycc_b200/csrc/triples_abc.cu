@@ -26,7 +26,6 @@ constexpr int A_MI = 5, A_NCMAX = 5;
 constexpr int A_PROWS = 64 * A_MI;                 // 320 pair rows per tile (8 warps x MI fragments of 8 rows)
 constexpr int A_PBYTES = A_PROWS * 128, A_LBYTES = 8 * A_NCMAX * 128, A_STAGE = A_PBYTES + A_LBYTES;
 constexpr int A_CONSUMERS = 256, A_THREADS = A_CONSUMERS + 128;
-constexpr int A_HELPERS = 96, A_ETHREADS = A_CONSUMERS + A_HELPERS;   // warps 9-11 join the consumers for the bracket
 constexpr int A_SMEM = AST * A_STAGE + (2 * AST + 1) * (int)sizeof(uint64_t) + 1024;
 
 struct alignas(64) AbcMaps {
@@ -106,44 +105,6 @@ __device__ __forceinline__ void abc_decode(int packed, int& a, int& b, int& c) {
   c = (packed >> 20) & 1023;
 }
 
-// Bracket of one (a,b,c) tile for the sorted occupied triples s = first, first + A_ETHREADS, ...: cctriples.py:149-173
-// (disconnected part) and 208-237 with (ijk) <-> (abc).  sm: six o x o matrices (odd pitch) + seven o-vectors staged by
-// the consumers; W: the CTA's tile, read at the L2 (the epilogue's adds are performed there).
-template <int UNROLL>
-__device__ __forceinline__ double abc_bracket(const AbcParams& p, const double* sm, const double* W, int a, int b, int c,
-                                              int first) {
-  const int no = p.no, oo = no * no, ldm = no + 1, mm = no * ldm;
-  const double* vec = sm + 6 * mm;
-  const double* Mab = sm, *Mac = sm + mm, *Mbc = sm + 2 * mm, *Tab = sm + 3 * mm, *Tac = sm + 4 * mm, *Tbc = sm + 5 * mm;
-  const double* t1a = vec, *t1b = vec + no, *t1c = vec + 2 * no, *fa = vec + 3 * no, *fb = vec + 4 * no,
-               *fc = vec + 5 * no, *eo = vec + 6 * no;
-  const double dv = p.ev[a] + p.ev[b] + p.ev[c];
-  auto disc = [&](int I, int J, int Kx) {
-    return Mab[I * ldm + J] * t1c[Kx] + Mac[I * ldm + Kx] * t1b[J] + Mbc[J * ldm + Kx] * t1a[I] +
-           Tab[I * ldm + J] * fc[Kx] + Tac[I * ldm + Kx] * fb[J] + Tbc[J * ldm + Kx] * fa[I];
-  };
-  double e_abc = 0.0;
-#pragma unroll UNROLL
-  for (int s = first; s < p.nsorted; s += A_ETHREADS) {
-    int i, j, k;
-    abc_decode(p.sorted[s], i, j, k);
-    const double w_ijk = __ldcg(&W[(i64)i * oo + j * no + k]), w_ikj = __ldcg(&W[(i64)i * oo + k * no + j]);
-    const double w_jik = __ldcg(&W[(i64)j * oo + i * no + k]), w_jki = __ldcg(&W[(i64)j * oo + k * no + i]);
-    const double w_kij = __ldcg(&W[(i64)k * oo + i * no + j]), w_kji = __ldcg(&W[(i64)k * oo + j * no + i]);
-    const double sc = 1.0 / (1.0 + (double)((i == j) + (i == k) + (j == k)));
-    const double v_ijk = (w_ijk + disc(i, j, k)) * sc, v_ikj = (w_ikj + disc(i, k, j)) * sc;
-    const double v_jik = (w_jik + disc(j, i, k)) * sc, v_jki = (w_jki + disc(j, k, i)) * sc;
-    const double v_kij = (w_kij + disc(k, i, j)) * sc, v_kji = (w_kji + disc(k, j, i)) * sc;
-    const double X = w_ijk * v_ijk + w_ikj * v_ikj + w_jik * v_jik + w_jki * v_jki + w_kij * v_kij + w_kji * v_kji;
-    const double Y = v_ijk + v_jki + v_kij, Z = v_ikj + v_jik + v_kji;
-    const double Wc = w_ijk + w_jki + w_kij, Wo = w_ikj + w_jik + w_kji;
-    e_abc += ((Y - 2.0 * Z) * Wc + (Z - 2.0 * Y) * Wo + 3.0 * X) / (eo[i] + eo[j] + eo[k] - dv);
-  }
-  return (2.0 - (double)((a == b) + (a == c) + (b == c))) * e_abc;
-}
-
-__device__ __forceinline__ void bar_energy(int id) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "n"(A_ETHREADS) : "memory"); }
-
 template <int NC>
 __global__ void __launch_bounds__(A_THREADS, 1) t_abc_kernel(const AbcParams p, const __grid_constant__ AbcMaps tm) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -151,7 +112,7 @@ __global__ void __launch_bounds__(A_THREADS, 1) t_abc_kernel(const AbcParams p, 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + AST * A_STAGE);
   uint64_t* empty_bar = full_bar + AST;
   uint64_t* edone_bar = empty_bar + AST;
-  __shared__ double red[A_ETHREADS / 32];
+  __shared__ double red[A_CONSUMERS / 32];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int no = p.no, nv = p.nv;
   if (tid == 0) {
@@ -166,30 +127,10 @@ __global__ void __launch_bounds__(A_THREADS, 1) t_abc_kernel(const AbcParams p, 
   __syncthreads();
   const int KT = 2 * p.ktv + 2 * p.kto;
 
-  // registers: 256 consumers x 208 + 128 (producer, helpers) x 88 = the 384 x 168 of the launch
-  if (warp >= A_CONSUMERS / 32) reg_dec<88>();
-  if (warp > A_CONSUMERS / 32) {
-    // ============================ helper warps: a share of every tile's bracket ============================
-    const int et = tid - 32;                      // 256 .. 351 in the bracket's thread numbering
-    const double* smh = reinterpret_cast<const double*>(tiles);
-    const double* Wh = p.wtile + (i64)blockIdx.x * no * no * no;
-    double e_acc = 0.0;
-    for (int n = blockIdx.x; n < p.nabc; n += gridDim.x) {
-      int a, b, c;
-      abc_decode(p.abc[n], a, b, c);
-      bar_energy(2);                              // the tile is complete and the matrices are staged
-      e_acc += abc_bracket<1>(p, smh, Wh, a, b, c, et);
-      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-      bar_energy(3);
-    }
-    e_acc = warp_sum(e_acc);
-    if (lane == 0) red[warp - 1] = e_acc;
-    bar_energy(3);
-    return;
-  }
-  if (warp == A_CONSUMERS / 32) {
+  if (warp >= A_CONSUMERS / 32) {
     // ============================ producer: one thread drives the TMA unit ============================
-    if (lane == 0) {
+    reg_dec<40>();
+    if (warp == A_CONSUMERS / 32 && lane == 0) {
       const uint32_t tx = (uint32_t)(p.pp * no * 128 + 8 * NC * 128);
       int stage = 0;
       uint32_t phase = 0, ephase = 0;
@@ -233,7 +174,7 @@ __global__ void __launch_bounds__(A_THREADS, 1) t_abc_kernel(const AbcParams p, 
   }
 
   // ======================================== consumers ========================================
-  reg_inc<208>();
+  reg_inc<216>();
   const int w = warp, g = lane >> 2, q2 = lane & 3;
   int off[4];
 #pragma unroll
@@ -329,11 +270,37 @@ __global__ void __launch_bounds__(A_THREADS, 1) t_abc_kernel(const AbcParams p, 
         vec[5 * no + idx] = p.fov[(i64)idx * p.ldf + c];
         vec[6 * no + idx] = p.eo[idx];
       }
-      bar_energy(2);                              // consumers + helper warps
-      e_acc += abc_bracket<4>(p, sm, W, a, b, c, tid);
+      named_bar_consumers();
+      const double* Mab = sm, *Mac = sm + mm, *Mbc = sm + 2 * mm, *Tab = sm + 3 * mm, *Tac = sm + 4 * mm, *Tbc = sm + 5 * mm;
+      const double* t1a = vec, *t1b = vec + no, *t1c = vec + 2 * no, *fa = vec + 3 * no, *fb = vec + 4 * no,
+                   *fc = vec + 5 * no, *eo = vec + 6 * no;
+      const double dv = p.ev[a] + p.ev[b] + p.ev[c];
+      const double wabc = 2.0 - (double)((a == b) + (a == c) + (b == c));
+      auto disc = [&](int I, int J, int Kx) {
+        return Mab[I * ldm + J] * t1c[Kx] + Mac[I * ldm + Kx] * t1b[J] + Mbc[J * ldm + Kx] * t1a[I] +
+               Tab[I * ldm + J] * fc[Kx] + Tac[I * ldm + Kx] * fb[J] + Tbc[J * ldm + Kx] * fa[I];
+      };
+      double e_abc = 0.0;
+#pragma unroll 4
+      for (int s = tid; s < p.nsorted; s += A_CONSUMERS) {
+        int i, j, k;
+        abc_decode(p.sorted[s], i, j, k);
+        const double w_ijk = __ldcg(&W[(i64)i * oo + j * no + k]), w_ikj = __ldcg(&W[(i64)i * oo + k * no + j]);
+        const double w_jik = __ldcg(&W[(i64)j * oo + i * no + k]), w_jki = __ldcg(&W[(i64)j * oo + k * no + i]);
+        const double w_kij = __ldcg(&W[(i64)k * oo + i * no + j]), w_kji = __ldcg(&W[(i64)k * oo + j * no + i]);
+        const double sc = 1.0 / (1.0 + (double)((i == j) + (i == k) + (j == k)));
+        const double v_ijk = (w_ijk + disc(i, j, k)) * sc, v_ikj = (w_ikj + disc(i, k, j)) * sc;
+        const double v_jik = (w_jik + disc(j, i, k)) * sc, v_jki = (w_jki + disc(j, k, i)) * sc;
+        const double v_kij = (w_kij + disc(k, i, j)) * sc, v_kji = (w_kji + disc(k, j, i)) * sc;
+        const double X = w_ijk * v_ijk + w_ikj * v_ikj + w_jik * v_jik + w_jki * v_jki + w_kij * v_kij + w_kji * v_kji;
+        const double Y = v_ijk + v_jki + v_kij, Z = v_ikj + v_jik + v_kji;
+        const double Wc = w_ijk + w_jki + w_kij, Wo = w_ikj + w_jik + w_kji;
+        e_abc += ((Y - 2.0 * Z) * Wc + (Z - 2.0 * Y) * Wo + 3.0 * X) / (eo[i] + eo[j] + eo[k] - dv);
+      }
+      e_acc += wabc * e_abc;
       // generic-proxy accesses of the ring are done; the next TMA writes into it go through the async proxy
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-      bar_energy(3);
+      named_bar_consumers();
       if (tid == 0) mbar_arrive(edone_bar);
     }
   }
@@ -341,11 +308,11 @@ __global__ void __launch_bounds__(A_THREADS, 1) t_abc_kernel(const AbcParams p, 
   // ---- per-CTA partial sum (deterministic: fixed thread -> triple and CTA -> (a,b,c) maps)
   e_acc = warp_sum(e_acc);
   if (lane == 0) red[warp] = e_acc;
-  bar_energy(3);
+  named_bar_consumers();
   if (tid == 0) {
     double s = 0.0;
 #pragma unroll
-    for (int i = 0; i < A_ETHREADS / 32; ++i) s += red[i];
+    for (int i = 0; i < A_CONSUMERS / 32; ++i) s += red[i];
     p.partial[blockIdx.x] = s;
   }
 }
