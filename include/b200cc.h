@@ -339,6 +339,7 @@ typedef struct b200cc_t_abc_desc {
   double* et_out;
   int accumulate;
   int grid;                 /* CTAs to launch (one per SM); the scratch arrays are sized by it */
+  int fov_is_zero;          /* caller vouches that F[o,v] = 0 (canonical reference): its terms of t3d_abc are not evaluated */
 } b200cc_t_abc_desc;
 int b200cc_t_abc_max_no(void);
 int b200cc_t_abc(const b200cc_t_abc_desc* d, void* stream);

@@ -106,6 +106,7 @@ class TAbcDesc(C.Structure):
         ("wtile", dptr), ("partial", dptr), ("et_out", dptr),
         ("accumulate", C.c_int),
         ("grid", C.c_int),
+        ("fov_is_zero", C.c_int),
     ]
 
 

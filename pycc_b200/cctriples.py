@@ -265,6 +265,8 @@ class FusedTriples:
         self.t2 = (ccwfn.t2 if t2 is None else t2).contiguous()
         self.dev = self.t2.device
         self.fov = H.F[ccwfn.o, ccwfn.v]
+        # canonical reference: the f_kc terms of t3d_abc (cctriples.py:161-163) vanish identically and are not evaluated
+        self.fov_is_zero = not bool(torch.count_nonzero(self.fov))
         if "ovvv_iabe" not in H._derived:
             H._derived["ovvv_iabe"] = K.permuted(H.block("ovvv"), (0, 2, 3, 1))
         self.G = H._derived["ovvv_iabe"]
@@ -294,7 +296,8 @@ class FusedTriples:
             return et
         w = self.w
         K.t_abc(self.no, self.nv, abc, self.sorted, self.G, self.t2, self.t2x, self.Ox, self.oovvx, self.t1, self.fov,
-                w.eps_o, w.eps_v, et, self.wtile, self.partial, self.grid, accumulate=True)
+                w.eps_o, w.eps_v, et, self.wtile, self.partial, self.grid, accumulate=True,
+                fov_is_zero=self.fov_is_zero)
         return et
 
     def w_tile(self, a, b, c):

@@ -33,7 +33,7 @@ struct alignas(64) AbcMaps {
 };
 
 struct AbcParams {
-  int no, nv, nabc, pp, tiles_p, ktv, kto, nsorted;
+  int no, nv, nabc, pp, tiles_p, ktv, kto, nsorted, fzero;
   const int* abc;
   const int* sorted;
   const double *t2x, *oovvx, *t1, *fov, *eo, *ev;
@@ -256,9 +256,11 @@ __global__ void __launch_bounds__(A_THREADS, 1) t_abc_kernel(const AbcParams p, 
         sm[dst] = p.oovvx[sab + idx];
         sm[mm + dst] = p.oovvx[sac + idx];
         sm[2 * mm + dst] = p.oovvx[sbc + idx];
-        sm[3 * mm + dst] = p.t2x[sab + idx];
-        sm[4 * mm + dst] = p.t2x[sac + idx];
-        sm[5 * mm + dst] = p.t2x[sbc + idx];
+        if (!p.fzero) {
+          sm[3 * mm + dst] = p.t2x[sab + idx];
+          sm[4 * mm + dst] = p.t2x[sac + idx];
+          sm[5 * mm + dst] = p.t2x[sbc + idx];
+        }
       }
       double* vec = sm + 6 * mm;        // t1[:,a], t1[:,b], t1[:,c], f[:,a], f[:,b], f[:,c], eps_o
       for (int idx = tid; idx < no; idx += A_CONSUMERS) {
@@ -276,26 +278,63 @@ __global__ void __launch_bounds__(A_THREADS, 1) t_abc_kernel(const AbcParams p, 
                    *fc = vec + 5 * no, *eo = vec + 6 * no;
       const double dv = p.ev[a] + p.ev[b] + p.ev[c];
       const double wabc = 2.0 - (double)((a == b) + (a == c) + (b == c));
-      auto disc = [&](int I, int J, int Kx) {
-        return Mab[I * ldm + J] * t1c[Kx] + Mac[I * ldm + Kx] * t1b[J] + Mbc[J * ldm + Kx] * t1a[I] +
-               Tab[I * ldm + J] * fc[Kx] + Tac[I * ldm + Kx] * fb[J] + Tbc[J * ldm + Kx] * fa[I];
+      // disconnected part at (I,J,K) with the t1 / f entries of its indices already in registers; the f terms vanish
+      // identically for a canonical reference (F_ov = 0, p.fzero): the bracket is bound by its shared-memory reads
+      // (75 LDS.64 per triple as first written), so they are not issued then
+      const bool fz = p.fzero != 0;
+      auto disc = [&](int I, int J, int Kx, double cK, double bJ, double aI, double fcK, double fbJ, double faI) {
+        double d = Mab[I * ldm + J] * cK + Mac[I * ldm + Kx] * bJ + Mbc[J * ldm + Kx] * aI;
+        if (!fz) d += Tab[I * ldm + J] * fcK + Tac[I * ldm + Kx] * fbJ + Tbc[J * ldm + Kx] * faI;
+        return d;
       };
       double e_abc = 0.0;
-#pragma unroll 4
-      for (int s = tid; s < p.nsorted; s += A_CONSUMERS) {
-        int i, j, k;
-        abc_decode(p.sorted[s], i, j, k);
-        const double w_ijk = __ldcg(&W[(i64)i * oo + j * no + k]), w_ikj = __ldcg(&W[(i64)i * oo + k * no + j]);
-        const double w_jik = __ldcg(&W[(i64)j * oo + i * no + k]), w_jki = __ldcg(&W[(i64)j * oo + k * no + i]);
-        const double w_kij = __ldcg(&W[(i64)k * oo + i * no + j]), w_kji = __ldcg(&W[(i64)k * oo + j * no + i]);
-        const double sc = 1.0 / (1.0 + (double)((i == j) + (i == k) + (j == k)));
-        const double v_ijk = (w_ijk + disc(i, j, k)) * sc, v_ikj = (w_ikj + disc(i, k, j)) * sc;
-        const double v_jik = (w_jik + disc(j, i, k)) * sc, v_jki = (w_jki + disc(j, k, i)) * sc;
-        const double v_kij = (w_kij + disc(k, i, j)) * sc, v_kji = (w_kji + disc(k, j, i)) * sc;
-        const double X = w_ijk * v_ijk + w_ikj * v_ikj + w_jik * v_jik + w_jki * v_jki + w_kij * v_kij + w_kji * v_kji;
-        const double Y = v_ijk + v_jki + v_kij, Z = v_ikj + v_jik + v_kji;
-        const double Wc = w_ijk + w_jki + w_kij, Wo = w_ikj + w_jik + w_kji;
-        e_abc += ((Y - 2.0 * Z) * Wc + (Z - 2.0 * Y) * Wo + 3.0 * X) / (eo[i] + eo[j] + eo[k] - dv);
+      // EB triples per pass with all their tile reads issued before the first use: one L2 round trip per pass, not per
+      // triple (measured: the loop was latency-bound -- 96 more threads on it changed nothing)
+      constexpr int EB = 4;
+      for (int s0 = tid; s0 < p.nsorted; s0 += EB * A_CONSUMERS) {
+        int ti[EB], tj[EB], tk[EB];
+        double wv[EB][6];
+#pragma unroll
+        for (int u = 0; u < EB; ++u) {
+          const int s = s0 + u * A_CONSUMERS;
+          abc_decode(p.sorted[s < p.nsorted ? s : s0], ti[u], tj[u], tk[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < EB; ++u) {
+          const int i = ti[u], j = tj[u], k = tk[u];
+          wv[u][0] = __ldcg(&W[(i64)i * oo + j * no + k]);
+          wv[u][1] = __ldcg(&W[(i64)i * oo + k * no + j]);
+          wv[u][2] = __ldcg(&W[(i64)j * oo + i * no + k]);
+          wv[u][3] = __ldcg(&W[(i64)j * oo + k * no + i]);
+          wv[u][4] = __ldcg(&W[(i64)k * oo + i * no + j]);
+          wv[u][5] = __ldcg(&W[(i64)k * oo + j * no + i]);
+        }
+#pragma unroll
+        for (int u = 0; u < EB; ++u) {
+          if (s0 + u * A_CONSUMERS >= p.nsorted) continue;
+          const int i = ti[u], j = tj[u], k = tk[u];
+          const double w_ijk = wv[u][0], w_ikj = wv[u][1], w_jik = wv[u][2], w_jki = wv[u][3], w_kij = wv[u][4],
+                       w_kji = wv[u][5];
+          const double sc = 1.0 / (1.0 + (double)((i == j) + (i == k) + (j == k)));
+          const double a_i = t1a[i], a_j = t1a[j], a_k = t1a[k], b_i = t1b[i], b_j = t1b[j], b_k = t1b[k];
+          const double c_i = t1c[i], c_j = t1c[j], c_k = t1c[k];
+          double fa_i = 0.0, fa_j = 0.0, fa_k = 0.0, fb_i = 0.0, fb_j = 0.0, fb_k = 0.0, fc_i = 0.0, fc_j = 0.0, fc_k = 0.0;
+          if (!fz) {
+            fa_i = fa[i]; fa_j = fa[j]; fa_k = fa[k];
+            fb_i = fb[i]; fb_j = fb[j]; fb_k = fb[k];
+            fc_i = fc[i]; fc_j = fc[j]; fc_k = fc[k];
+          }
+          const double v_ijk = (w_ijk + disc(i, j, k, c_k, b_j, a_i, fc_k, fb_j, fa_i)) * sc;
+          const double v_ikj = (w_ikj + disc(i, k, j, c_j, b_k, a_i, fc_j, fb_k, fa_i)) * sc;
+          const double v_jik = (w_jik + disc(j, i, k, c_k, b_i, a_j, fc_k, fb_i, fa_j)) * sc;
+          const double v_jki = (w_jki + disc(j, k, i, c_i, b_k, a_j, fc_i, fb_k, fa_j)) * sc;
+          const double v_kij = (w_kij + disc(k, i, j, c_j, b_i, a_k, fc_j, fb_i, fa_k)) * sc;
+          const double v_kji = (w_kji + disc(k, j, i, c_i, b_j, a_k, fc_i, fb_j, fa_k)) * sc;
+          const double X = w_ijk * v_ijk + w_ikj * v_ikj + w_jik * v_jik + w_jki * v_jki + w_kij * v_kij + w_kji * v_kji;
+          const double Y = v_ijk + v_jki + v_kij, Z = v_ikj + v_jik + v_kji;
+          const double Wc = w_ijk + w_jki + w_kij, Wo = w_ikj + w_jik + w_kji;
+          e_abc += ((Y - 2.0 * Z) * Wc + (Z - 2.0 * Y) * Wo + 3.0 * X) / (eo[i] + eo[j] + eo[k] - dv);
+        }
       }
       e_acc += wabc * e_abc;
       // generic-proxy accesses of the ring are done; the next TMA writes into it go through the async proxy
@@ -375,6 +414,7 @@ extern "C" int b200cc_t_abc(const b200cc_t_abc_desc* d, void* stream) {
   p.ktv = (nv + ABK - 1) / ABK;
   p.kto = (no + ABK - 1) / ABK;
   p.nsorted = d->nsorted;
+  p.fzero = d->fov_is_zero ? 1 : 0;
   p.abc = d->abc; p.sorted = d->sorted;
   p.t2x = d->t2x; p.oovvx = d->oovvx; p.t1 = d->t1; p.fov = d->fov; p.eo = d->eo; p.ev = d->ev; p.ldf = d->ldf;
   p.wtile = d->wtile; p.partial = d->partial;

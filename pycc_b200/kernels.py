@@ -581,7 +581,8 @@ def t_abc_max_no():
     return int(_lib.get().b200cc_t_abc_max_no())
 
 
-def t_abc(no, nv, abc, sorted_ijk, G, t2, t2x, Ox, oovvx, t1, fov, eo, ev, et, wtile, partial, grid, accumulate=True):
+def t_abc(no, nv, abc, sorted_ijk, G, t2, t2x, Ox, oovvx, t1, fov, eo, ev, et, wtile, partial, grid, accumulate=True,
+          fov_is_zero=False):
     """E(T) contributions of the packed virtual triples ``abc`` (int32, a | b << 10 | c << 20, a >= b >= c), fused
     (a,b,c)-driven kernel (b200cc_t_abc): ``et[0] (+)= ...``.  ``wtile``: grid * o^3 doubles, ``partial``: grid doubles."""
     d = TAbcDesc()
@@ -597,6 +598,7 @@ def t_abc(no, nv, abc, sorted_ijk, G, t2, t2x, Ox, oovvx, t1, fov, eo, ev, et, w
         raise B200ccError("t_abc: scratch too small for grid = %d" % grid)
     d.wtile, d.partial, d.et_out = _lib.ptr(wtile), _lib.ptr(partial), _lib.ptr(et)
     d.accumulate, d.grid = int(bool(accumulate)), int(grid)
+    d.fov_is_zero = int(bool(fov_is_zero))
     _lib.check(_lib.get().b200cc_t_abc(C.byref(d), _lib.stream()), "b200cc_t_abc")
     return et
 
