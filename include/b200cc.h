@@ -317,7 +317,10 @@ int b200cc_t3_density_forms(const b200cc_t3d_desc* d, void* stream);
  * abc / sorted: device int32, one entry per triple packed as  x0 | x1 << 10 | x2 << 20  with x0 >= x1 >= x2
  * (sorted: the occupied triples i >= j >= k, i = j = k left out -- they contribute exactly zero).
  * wtile: grid * o^3 doubles of scratch (after a call with nabc = 1, grid = 1 it holds W_abc[i][j][k], the connected
- * numerator -- the parity hook for t3c_abc); partial: grid doubles. */
+ * numerator -- the parity hook for t3c_abc); partial: grid doubles.
+ * While the job runs the scratch tiles are pinned in the L2 by a persisting access window (so the t3 tile is not written
+ * back to HBM); the call waits for the job on `stream` and then releases the window and the L2 set-aside, i.e. unlike
+ * the other entry points it returns after its kernels have finished (B200CC_TABC_L2PERSIST=0: no window, no wait). */
 typedef struct b200cc_t_abc_desc {
   int struct_size;          /* sizeof(b200cc_t_abc_desc), checked by the library */
   int no, nv;
