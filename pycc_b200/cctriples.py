@@ -260,23 +260,51 @@ class FusedTriples:
     def __init__(self, ccwfn, t1=None, t2=None, grid=None):
         self.w = ccwfn
         H = ccwfn.H
-        self.no, self.nv = ccwfn.no, ccwfn.nv
-        self.t1 = (ccwfn.t1 if t1 is None else t1).contiguous()
-        self.t2 = (ccwfn.t2 if t2 is None else t2).contiguous()
-        self.dev = self.t2.device
-        self.fov = H.F[ccwfn.o, ccwfn.v]
+        no, nv = ccwfn.no, ccwfn.nv
+        self.no_real, self.nv_real = no, nv
+        # The kernel wants even extents (16-byte TMA pitches).  Odd ones are padded by one index whose amplitudes and
+        # integrals are zero and whose orbital energy is far away: every t3 numerator it touches is exactly zero, so the
+        # padded problem has the same E(T); the padded constants are built once per Hamiltonian.
+        self.no, self.nv = no + (no & 1), nv + (nv & 1)
+        po, pv = self.no, self.nv
+        padded = (po, pv) != (no, nv)
+        t1 = (ccwfn.t1 if t1 is None else t1).contiguous()
+        t2 = (ccwfn.t2 if t2 is None else t2).contiguous()
+        self.dev = t2.device
+        fov = H.F[ccwfn.o, ccwfn.v]
         # canonical reference: the f_kc terms of t3d_abc (cctriples.py:161-163) vanish identically and are not evaluated
-        self.fov_is_zero = not bool(torch.count_nonzero(self.fov))
-        if "ovvv_iabe" not in H._derived:
-            H._derived["ovvv_iabe"] = K.permuted(H.block("ovvv"), (0, 2, 3, 1))
-        self.G = H._derived["ovvv_iabe"]
-        if "ooov_zpqm_neg" not in H._derived:
-            H._derived["ooov_zpqm_neg"] = K.permuted(H.block("ooov"), (3, 0, 1, 2), -1.0)    # -<mz|pq> = -ooov[p,q,m,z]
-        self.Ox = H._derived["ooov_zpqm_neg"]
-        if "oovv_abij" not in H._derived:
-            H._derived["oovv_abij"] = K.permuted(H.block("oovv"), (2, 3, 0, 1))
-        self.oovvx = H._derived["oovv_abij"]
-        self.t2x = K.permuted(self.t2, (2, 3, 0, 1))
+        self.fov_is_zero = not bool(torch.count_nonzero(fov))
+
+        def const(key, build):
+            key = key + ("_pad%dx%d" % (po, pv) if padded else "")
+            if key not in H._derived:
+                H._derived[key] = build()
+            return H._derived[key]
+
+        def embed(shape, src, alpha=1.0):
+            """zero tensor of ``shape`` with alpha * (permuted view ``src``) copied into its leading corner"""
+            out = torch.zeros(shape, dtype=F64, device=self.dev)
+            K.strided_axpby(out[tuple(slice(0, n) for n in src.shape)], src, alpha, 0.0)
+            return out
+
+        if not padded:
+            self.t1, self.t2, self.fov = t1, t2, fov
+            self.eo, self.ev = ccwfn.eps_o, ccwfn.eps_v
+            self.G = const("ovvv_iabe", lambda: K.permuted(H.block("ovvv"), (0, 2, 3, 1)))
+            self.Ox = const("ooov_zpqm_neg", lambda: K.permuted(H.block("ooov"), (3, 0, 1, 2), -1.0))   # -<mz|pq> = -ooov[p,q,m,z]
+            self.oovvx = const("oovv_abij", lambda: K.permuted(H.block("oovv"), (2, 3, 0, 1)))
+            self.t2x = K.permuted(t2, (2, 3, 0, 1))
+        else:
+            self.t1 = embed((po, pv), t1)
+            self.t2 = embed((po, po, pv, pv), t2)
+            self.fov = embed((po, pv), fov)
+            far = 1.0e3 + float(ccwfn.eps_v.abs().max()) + float(ccwfn.eps_o.abs().max())
+            self.eo = torch.cat((ccwfn.eps_o, torch.full((po - no,), -far, dtype=F64, device=self.dev)))
+            self.ev = torch.cat((ccwfn.eps_v, torch.full((pv - nv,), far, dtype=F64, device=self.dev)))
+            self.G = const("ovvv_iabe", lambda: embed((po, pv, pv, pv), H.block("ovvv").permute(0, 2, 3, 1)))
+            self.Ox = const("ooov_zpqm_neg", lambda: embed((pv, po, po, po), H.block("ooov").permute(3, 0, 1, 2), -1.0))
+            self.oovvx = const("oovv_abij", lambda: embed((pv, pv, po, po), H.block("oovv").permute(2, 3, 0, 1)))
+            self.t2x = K.permuted(self.t2, (2, 3, 0, 1))
         self.grid = int(grid) if grid else K.NSM
         self.sorted = torch.from_numpy(sorted_occ(self.no)).to(self.dev)
         self.wtile = torch.empty(self.grid * self.no ** 3, dtype=F64, device=self.dev)
@@ -284,8 +312,12 @@ class FusedTriples:
 
     @staticmethod
     def applies(ccwfn):
-        return (ccwfn.no % 2 == 0 and ccwfn.nv % 2 == 0 and 2 <= ccwfn.no <= K.t_abc_max_no() and ccwfn.nv <= 1023
-                and not bool(getattr(ccwfn, "mixed", False)))
+        po, pv = ccwfn.no + (ccwfn.no & 1), ccwfn.nv + (ccwfn.nv & 1)
+        return 2 <= po <= K.t_abc_max_no() and pv <= 1023 and not bool(getattr(ccwfn, "mixed", False))
+
+    def abc_all(self):
+        """every virtual triple of the (padded) problem"""
+        return abc_list(self.nv)
 
     def energy(self, abc):
         """Sum of the contributions of the packed virtual triples ``abc`` (numpy int32 or device tensor)."""
@@ -294,9 +326,8 @@ class FusedTriples:
             abc = torch.from_numpy(np.ascontiguousarray(abc, dtype=np.int32)).to(self.dev)
         if abc.numel() == 0:
             return et
-        w = self.w
         K.t_abc(self.no, self.nv, abc, self.sorted, self.G, self.t2, self.t2x, self.Ox, self.oovvx, self.t1, self.fov,
-                w.eps_o, w.eps_v, et, self.wtile, self.partial, self.grid, accumulate=True,
+                self.eo, self.ev, et, self.wtile, self.partial, self.grid, accumulate=True,
                 fov_is_zero=self.fov_is_zero)
         return et
 
@@ -308,7 +339,8 @@ class FusedTriples:
             self.energy(_pack3(np.asarray([a]), np.asarray([b]), np.asarray([c])))
         finally:
             self.grid = keep
-        return self.wtile[:self.no ** 3].view(self.no, self.no, self.no).clone()
+        n = self.no_real
+        return self.wtile[:self.no ** 3].view(self.no, self.no, self.no)[:n, :n, :n].clone()
 
 
 def fused_selected(ccwfn):
@@ -328,7 +360,7 @@ def t_tjl_abc(ccwfn, abc=None):
     to the ranks of ``ccwfn.comm``; one scalar all-reduce."""
     eng = FusedTriples(ccwfn)
     comm = getattr(ccwfn, "comm", None)
-    lst = abc_list(ccwfn.nv) if abc is None else np.asarray(abc, dtype=np.int32)
+    lst = eng.abc_all() if abc is None else np.asarray(abc, dtype=np.int32)
     if comm is not None and comm.size > 1:
         lst = lst[comm.rank::comm.size]
     et = eng.energy(lst)
