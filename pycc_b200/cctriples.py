@@ -225,7 +225,7 @@ class TriplesEngine:
 
 
 # ---- fused (a,b,c)-driven (T): the o^3 tile of a virtual triple stays on the chip (csrc/triples_abc.cu) -------------
-# 'abc' / 'ijk' force a formulation, 'auto' takes the fused one whenever its kernel applies (even o <= 40, even v, FP64)
+# 'abc' / 'ijk' force a formulation, 'auto' takes the fused one whenever its kernel applies (o <= 64, v <= 1023, FP64)
 ALGO = os.environ.get("B200CC_T_ALGO", "auto")
 
 

@@ -22,18 +22,24 @@
 namespace b200cc {
 
 constexpr int ABK = 16, AST = 4;
-constexpr int A_MI = 5, A_NCMAX = 5;
-constexpr int A_PROWS = 64 * A_MI;                 // 320 pair rows per tile (8 warps x MI fragments of 8 rows)
-constexpr int A_PBYTES = A_PROWS * 128, A_LBYTES = 8 * A_NCMAX * 128, A_STAGE = A_PBYTES + A_LBYTES;
 constexpr int A_CONSUMERS = 256, A_THREADS = A_CONSUMERS + 128;
-constexpr int A_SMEM = AST * A_STAGE + (2 * AST + 1) * (int)sizeof(uint64_t) + 1024;
+
+// CTA tile geometry: 8 consumer warps x MI fragments of 8 pair rows, NCMAX fragments of 8 lone indices.
+//   MI = 5: 320 x 40 (o <= 40: the bench shapes), MI = 3: 192 x 64 (40 < o <= 64)
+template <int MI_>
+struct AG {
+  static constexpr int MI = MI_, NCMAX = MI_ == 5 ? 5 : 8;
+  static constexpr int PROWS = 64 * MI_;
+  static constexpr int PBYTES = PROWS * 128, LBYTES = 8 * NCMAX * 128, STAGE = PBYTES + LBYTES;
+  static constexpr int SMEM = AST * STAGE + (2 * AST + 1) * (int)sizeof(uint64_t) + 1024;
+};
 
 struct alignas(64) AbcMaps {
   CUtensorMap g, t2x, t2a, t2b, oxa, oxb;
 };
 
 struct AbcParams {
-  int no, nv, nabc, pp, tiles_p, ktv, kto, nsorted, fzero;
+  int no, nv, nabc, pp, tiles_p, ktv, kto, nsorted, fzero, tglob;
   const int* abc;
   const int* sorted;
   const double *t2x, *oovvx, *t1, *fov, *eo, *ev;
@@ -50,17 +56,17 @@ __device__ __forceinline__ void red_add(double* p, double v) {
 
 __device__ __forceinline__ void named_bar_consumers() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 
-template <int MC, int NC>
+template <class G, int MC, int NC>
 __device__ __forceinline__ void abc_frags(const unsigned char* __restrict__ Ps, const unsigned char* __restrict__ Ls, int off,
-                                          double (&a)[A_MI], double (&b)[A_NCMAX], int w, int g) {
+                                          double (&a)[G::MI], double (&b)[G::NCMAX], int w, int g) {
 #pragma unroll
   for (int i = 0; i < MC; ++i) a[i] = *reinterpret_cast<const double*>(Ps + (8 * (w + 8 * i) + g) * 128 + off);
 #pragma unroll
   for (int j = 0; j < NC; ++j) b[j] = *reinterpret_cast<const double*>(Ls + (8 * j + g) * 128 + off);
 }
 
-template <int MC, int NC>
-__device__ __forceinline__ void abc_mma(double (&acc)[A_MI][A_NCMAX][2], const double (&a)[A_MI], const double (&b)[A_NCMAX]) {
+template <class G, int MC, int NC>
+__device__ __forceinline__ void abc_mma(double (&acc)[G::MI][G::NCMAX][2], const double (&a)[G::MI], const double (&b)[G::NCMAX]) {
 #pragma unroll
   for (int i = 0; i < MC; ++i)
 #pragma unroll
@@ -68,30 +74,30 @@ __device__ __forceinline__ void abc_mma(double (&acc)[A_MI][A_NCMAX][2], const d
 }
 
 // the k-loop of one unit (all four K segments: the consumer does not see the segment boundaries)
-template <int MC, int NC>
-__device__ __forceinline__ void abc_kloop(double (&acc)[A_MI][A_NCMAX][2], const unsigned char* tiles, uint64_t* full_bar,
+template <class G, int MC, int NC>
+__device__ __forceinline__ void abc_kloop(double (&acc)[G::MI][G::NCMAX][2], const unsigned char* tiles, uint64_t* full_bar,
                                           uint64_t* empty_bar, int& stage, uint32_t& phase, int nkt, const int (&off)[4],
                                           int w, int g, int lane) {
-  double a0[A_MI], b0[A_NCMAX], a1[A_MI], b1[A_NCMAX];
+  double a0[G::MI], b0[G::NCMAX], a1[G::MI], b1[G::NCMAX];
   mbar_wait(full_bar + stage, phase);
-  abc_frags<MC, NC>(tiles + stage * A_STAGE, tiles + stage * A_STAGE + A_PBYTES, off[0], a0, b0, w, g);
+  abc_frags<G, MC, NC>(tiles + stage * G::STAGE, tiles + stage * G::STAGE + G::PBYTES, off[0], a0, b0, w, g);
   for (int t = 0; t < nkt; ++t) {
-    const unsigned char* Ps = tiles + stage * A_STAGE;
-    const unsigned char* Ls = Ps + A_PBYTES;
-    abc_frags<MC, NC>(Ps, Ls, off[1], a1, b1, w, g);
-    abc_mma<MC, NC>(acc, a0, b0);
-    abc_frags<MC, NC>(Ps, Ls, off[2], a0, b0, w, g);
-    abc_mma<MC, NC>(acc, a1, b1);
-    abc_frags<MC, NC>(Ps, Ls, off[3], a1, b1, w, g);
-    abc_mma<MC, NC>(acc, a0, b0);
+    const unsigned char* Ps = tiles + stage * G::STAGE;
+    const unsigned char* Ls = Ps + G::PBYTES;
+    abc_frags<G, MC, NC>(Ps, Ls, off[1], a1, b1, w, g);
+    abc_mma<G, MC, NC>(acc, a0, b0);
+    abc_frags<G, MC, NC>(Ps, Ls, off[2], a0, b0, w, g);
+    abc_mma<G, MC, NC>(acc, a1, b1);
+    abc_frags<G, MC, NC>(Ps, Ls, off[3], a1, b1, w, g);
+    abc_mma<G, MC, NC>(acc, a0, b0);
     int nstage = stage + 1;
     uint32_t nphase = phase;
     if (nstage == AST) { nstage = 0; nphase ^= 1u; }
     if (t + 1 < nkt) {
       mbar_wait(full_bar + nstage, nphase);
-      abc_frags<MC, NC>(tiles + nstage * A_STAGE, tiles + nstage * A_STAGE + A_PBYTES, off[0], a0, b0, w, g);
+      abc_frags<G, MC, NC>(tiles + nstage * G::STAGE, tiles + nstage * G::STAGE + G::PBYTES, off[0], a0, b0, w, g);
     }
-    abc_mma<MC, NC>(acc, a1, b1);
+    abc_mma<G, MC, NC>(acc, a1, b1);
     __syncwarp();
     if (lane == 0) mbar_arrive(empty_bar + stage);
     stage = nstage;
@@ -105,11 +111,12 @@ __device__ __forceinline__ void abc_decode(int packed, int& a, int& b, int& c) {
   c = (packed >> 20) & 1023;
 }
 
-template <int NC>
+template <int MI, int NC>
 __global__ void __launch_bounds__(A_THREADS, 1) t_abc_kernel(const AbcParams p, const __grid_constant__ AbcMaps tm) {
+  using G = AG<MI>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + AST * A_STAGE);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + AST * G::STAGE);
   uint64_t* empty_bar = full_bar + AST;
   uint64_t* edone_bar = empty_bar + AST;
   __shared__ double red[A_CONSUMERS / 32];
@@ -159,9 +166,9 @@ __global__ void __launch_bounds__(A_THREADS, 1) t_abc_kernel(const AbcParams p, 
               const CUtensorMap* pm = seg < 2 ? (second ? &tm.t2b : &tm.t2a) : (second ? &tm.oxb : &tm.oxa);
               for (int t = 0; t < nk; ++t) {
                 mbar_wait(empty_bar + stage, phase ^ 1u);
-                unsigned char* Ps = tiles + stage * A_STAGE;
+                unsigned char* Ps = tiles + stage * G::STAGE;
                 mbar_expect_tx(full_bar + stage, tx);
-                tma_load_3d(Ps + A_PBYTES, lm, t * ABK, 0, lslab, full_bar + stage);
+                tma_load_3d(Ps + G::PBYTES, lm, t * ABK, 0, lslab, full_bar + stage);
                 tma_load_4d(Ps, pm, t * ABK, 0, p0, pslab, full_bar + stage);
                 if (++stage == AST) { stage = 0; phase ^= 1u; }
               }
@@ -196,18 +203,18 @@ __global__ void __launch_bounds__(A_THREADS, 1) t_abc_kernel(const AbcParams p, 
         const int nf = (rows_valid + 7) >> 3;
         int mc = 0;
 #pragma unroll
-        for (int i = 0; i < A_MI; ++i) mc += (w + 8 * i < nf) ? 1 : 0;
-        double acc[A_MI][A_NCMAX][2];
+        for (int i = 0; i < G::MI; ++i) mc += (w + 8 * i < nf) ? 1 : 0;
+        double acc[G::MI][G::NCMAX][2];
 #pragma unroll
-        for (int i = 0; i < A_MI; ++i)
+        for (int i = 0; i < G::MI; ++i)
 #pragma unroll
-          for (int j = 0; j < A_NCMAX; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+          for (int j = 0; j < G::NCMAX; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
         switch (mc) {
-          case 5: abc_kloop<5, NC>(acc, tiles, full_bar, empty_bar, stage, phase, KT, off, w, g, lane); break;
-          case 4: abc_kloop<4, NC>(acc, tiles, full_bar, empty_bar, stage, phase, KT, off, w, g, lane); break;
-          case 3: abc_kloop<3, NC>(acc, tiles, full_bar, empty_bar, stage, phase, KT, off, w, g, lane); break;
-          case 2: abc_kloop<2, NC>(acc, tiles, full_bar, empty_bar, stage, phase, KT, off, w, g, lane); break;
-          case 1: abc_kloop<1, NC>(acc, tiles, full_bar, empty_bar, stage, phase, KT, off, w, g, lane); break;
+          case 5: if constexpr (G::MI >= 5) abc_kloop<G, 5, NC>(acc, tiles, full_bar, empty_bar, stage, phase, KT, off, w, g, lane); break;
+          case 4: if constexpr (G::MI >= 4) abc_kloop<G, 4, NC>(acc, tiles, full_bar, empty_bar, stage, phase, KT, off, w, g, lane); break;
+          case 3: abc_kloop<G, 3, NC>(acc, tiles, full_bar, empty_bar, stage, phase, KT, off, w, g, lane); break;
+          case 2: abc_kloop<G, 2, NC>(acc, tiles, full_bar, empty_bar, stage, phase, KT, off, w, g, lane); break;
+          case 1: abc_kloop<G, 1, NC>(acc, tiles, full_bar, empty_bar, stage, phase, KT, off, w, g, lane); break;
           default:
             for (int t = 0; t < KT; ++t) {      // no fragment of this warp in range: keep the ring moving
               mbar_wait(full_bar + stage, phase);
@@ -218,7 +225,7 @@ __global__ void __launch_bounds__(A_THREADS, 1) t_abc_kernel(const AbcParams p, 
         }
         // ---- epilogue: add the accumulators into the CTA's tile W[i][j][k]
 #pragma unroll
-        for (int i = 0; i < A_MI; ++i) {
+        for (int i = 0; i < G::MI; ++i) {
           if (i >= mc) continue;
           const int r = 8 * (w + 8 * i) + g;
           if (r >= rows_valid) continue;
@@ -256,13 +263,14 @@ __global__ void __launch_bounds__(A_THREADS, 1) t_abc_kernel(const AbcParams p, 
         sm[dst] = p.oovvx[sab + idx];
         sm[mm + dst] = p.oovvx[sac + idx];
         sm[2 * mm + dst] = p.oovvx[sbc + idx];
-        if (!p.fzero) {
+        if (!p.fzero && !p.tglob) {
           sm[3 * mm + dst] = p.t2x[sab + idx];
           sm[4 * mm + dst] = p.t2x[sac + idx];
           sm[5 * mm + dst] = p.t2x[sbc + idx];
         }
       }
-      double* vec = sm + 6 * mm;        // t1[:,a], t1[:,b], t1[:,c], f[:,a], f[:,b], f[:,c], eps_o
+      // (o > 40 with a non-canonical reference: six matrices do not fit the ring, the three of t2 are read in place)
+      double* vec = sm + ((p.tglob || p.fzero) ? 3 : 6) * mm;        // t1[:,a], t1[:,b], t1[:,c], f[:,a], f[:,b], f[:,c], eps_o
       for (int idx = tid; idx < no; idx += A_CONSUMERS) {
         vec[idx] = p.t1[(i64)idx * nv + a];
         vec[no + idx] = p.t1[(i64)idx * nv + b];
@@ -273,7 +281,10 @@ __global__ void __launch_bounds__(A_THREADS, 1) t_abc_kernel(const AbcParams p, 
         vec[6 * no + idx] = p.eo[idx];
       }
       named_bar_consumers();
-      const double* Mab = sm, *Mac = sm + mm, *Mbc = sm + 2 * mm, *Tab = sm + 3 * mm, *Tac = sm + 4 * mm, *Tbc = sm + 5 * mm;
+      const double* Mab = sm, *Mac = sm + mm, *Mbc = sm + 2 * mm;
+      const double* Tab = p.tglob ? p.t2x + sab : sm + 3 * mm, *Tac = p.tglob ? p.t2x + sac : sm + 4 * mm,
+                   *Tbc = p.tglob ? p.t2x + sbc : sm + 5 * mm;
+      const int ldt = p.tglob ? no : ldm;
       const double* t1a = vec, *t1b = vec + no, *t1c = vec + 2 * no, *fa = vec + 3 * no, *fb = vec + 4 * no,
                    *fc = vec + 5 * no, *eo = vec + 6 * no;
       const double dv = p.ev[a] + p.ev[b] + p.ev[c];
@@ -284,7 +295,7 @@ __global__ void __launch_bounds__(A_THREADS, 1) t_abc_kernel(const AbcParams p, 
       const bool fz = p.fzero != 0;
       auto disc = [&](int I, int J, int Kx, double cK, double bJ, double aI, double fcK, double fbJ, double faI) {
         double d = Mab[I * ldm + J] * cK + Mac[I * ldm + Kx] * bJ + Mbc[J * ldm + Kx] * aI;
-        if (!fz) d += Tab[I * ldm + J] * fcK + Tac[I * ldm + Kx] * fbJ + Tbc[J * ldm + Kx] * faI;
+        if (!fz) d += Tab[I * ldt + J] * fcK + Tac[I * ldt + Kx] * fbJ + Tbc[J * ldt + Kx] * faI;
         return d;
       };
       double e_abc = 0.0;
@@ -371,22 +382,24 @@ static int make_tmap_nd(CUtensorMap* tm, const double* base, int rank, const cuu
   return 0;
 }
 
-template <int NC>
+template <int MI, int NC>
 static int launch_abc(const AbcParams& p, const AbcMaps& tm, int grid, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    B200CC_CUDA_OK(cudaFuncSetAttribute(t_abc_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM));
+    B200CC_CUDA_OK(cudaFuncSetAttribute(t_abc_kernel<MI, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, AG<MI>::SMEM));
     configured = true;
   }
-  t_abc_kernel<NC><<<grid, A_THREADS, A_SMEM, st>>>(p, tm);
+  t_abc_kernel<MI, NC><<<grid, A_THREADS, AG<MI>::SMEM, st>>>(p, tm);
   return check_launch("t_abc_kernel");
 }
+
+constexpr int A_MAX_NO = 8 * AG<3>::NCMAX;     // 64
 
 }  // namespace b200cc
 
 using namespace b200cc;
 
-extern "C" int b200cc_t_abc_max_no(void) { return 8 * A_NCMAX; }
+extern "C" int b200cc_t_abc_max_no(void) { return A_MAX_NO; }
 
 extern "C" int b200cc_t_abc(const b200cc_t_abc_desc* d, void* stream) {
   if (!d) { set_error("b200cc_t_abc: null descriptor"); return 1; }
@@ -396,8 +409,8 @@ extern "C" int b200cc_t_abc(const b200cc_t_abc_desc* d, void* stream) {
     return 1;
   }
   const int no = d->no, nv = d->nv;
-  if (no <= 0 || nv <= 0 || (no & 1) || (nv & 1) || no > 8 * A_NCMAX || nv > 1023) {
-    set_error("b200cc_t_abc: needs even o <= %d and even v <= 1023 (got o = %d, v = %d)", 8 * A_NCMAX, no, nv);
+  if (no <= 0 || nv <= 0 || (no & 1) || (nv & 1) || no > A_MAX_NO || nv > 1023) {
+    set_error("b200cc_t_abc: needs even o <= %d and even v <= 1023 (got o = %d, v = %d)", A_MAX_NO, no, nv);
     return 1;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -409,7 +422,9 @@ extern "C" int b200cc_t_abc(const b200cc_t_abc_desc* d, void* stream) {
   const int grid = d->grid < d->nabc ? d->grid : d->nabc;
   AbcParams p;
   p.no = no; p.nv = nv; p.nabc = d->nabc;
-  p.pp = A_PROWS / no < no ? A_PROWS / no : no;
+  const bool wide = no > 8 * AG<5>::NCMAX;          // 40 < o <= 64: the 192 x 64 tile
+  const int prows = wide ? AG<3>::PROWS : AG<5>::PROWS, stage_bytes = wide ? AG<3>::STAGE : AG<5>::STAGE;
+  p.pp = prows / no < no ? prows / no : no;
   p.tiles_p = (no + p.pp - 1) / p.pp;
   p.ktv = (nv + ABK - 1) / ABK;
   p.kto = (no + ABK - 1) / ABK;
@@ -418,7 +433,13 @@ extern "C" int b200cc_t_abc(const b200cc_t_abc_desc* d, void* stream) {
   p.abc = d->abc; p.sorted = d->sorted;
   p.t2x = d->t2x; p.oovvx = d->oovvx; p.t1 = d->t1; p.fov = d->fov; p.eo = d->eo; p.ev = d->ev; p.ldf = d->ldf;
   p.wtile = d->wtile; p.partial = d->partial;
-  if ((6 * no * (no + 1) + 7 * no) * (int)sizeof(double) > AST * A_STAGE) { set_error("b200cc_t_abc: o too large for the staging area"); return 1; }
+  // the bracket stages its o x o matrices in the operand ring: all six, or -- when they do not fit -- only the three of
+  // <ij|ab> (the t2 ones, needed for a non-canonical reference only, are then read in place)
+  p.tglob = (!p.fzero && (6 * no * (no + 1) + 7 * no) * (int)sizeof(double) > AST * stage_bytes) ? 1 : 0;
+  if (((p.tglob || p.fzero ? 3 : 6) * no * (no + 1) + 7 * no) * (int)sizeof(double) > AST * stage_bytes) {
+    set_error("b200cc_t_abc: o too large for the staging area");
+    return 1;
+  }
   const int nc = (no + 7) / 8;
   const i64 O = no, V = nv;
   AbcMaps tm;
@@ -477,12 +498,20 @@ extern "C" int b200cc_t_abc(const b200cc_t_abc_desc* d, void* stream) {
     }
   }
   int rc;
-  switch (nc) {
-    case 1: rc = launch_abc<1>(p, tm, grid, st); break;
-    case 2: rc = launch_abc<2>(p, tm, grid, st); break;
-    case 3: rc = launch_abc<3>(p, tm, grid, st); break;
-    case 4: rc = launch_abc<4>(p, tm, grid, st); break;
-    default: rc = launch_abc<5>(p, tm, grid, st); break;
+  if (!wide) {
+    switch (nc) {
+      case 1: rc = launch_abc<5, 1>(p, tm, grid, st); break;
+      case 2: rc = launch_abc<5, 2>(p, tm, grid, st); break;
+      case 3: rc = launch_abc<5, 3>(p, tm, grid, st); break;
+      case 4: rc = launch_abc<5, 4>(p, tm, grid, st); break;
+      default: rc = launch_abc<5, 5>(p, tm, grid, st); break;
+    }
+  } else {
+    switch (nc) {
+      case 6: rc = launch_abc<3, 6>(p, tm, grid, st); break;
+      case 7: rc = launch_abc<3, 7>(p, tm, grid, st); break;
+      default: rc = launch_abc<3, 8>(p, tm, grid, st); break;
+    }
   }
   if (rc) return rc;
   rc = launch_final_reduce(d->partial, grid, 0, 1, d->et_out, d->accumulate, 1.0, st);

@@ -541,14 +541,14 @@ class EmuLib:
 
     # ---- (T), fused (a,b,c)-driven form ------------------------------------------------------------------
     def b200cc_t_abc_max_no(self):
-        return 40
+        return 64
 
     def b200cc_t_abc(self, dref, stream):
         d = dref._obj
         self._count("t_abc", 2)
         no, nv = d.no, d.nv
-        if no % 2 or nv % 2 or no > 40 or nv > 1023:
-            self.err = b"b200cc_t_abc: needs even o <= 40 and even v <= 1023"
+        if no % 2 or nv % 2 or no > 64 or nv > 1023:
+            self.err = b"b200cc_t_abc: needs even o <= 64 and even v <= 1023"
             return 1
         o2, o3, v2 = no * no, no ** 3, nv * nv
         G = _vec(d.G, no * nv ** 3).reshape(no, nv, nv, nv)            # [l,x,y,e]
