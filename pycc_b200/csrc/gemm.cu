@@ -832,7 +832,10 @@ static int launch_tma(KParams& p, cudaStream_t st) {
   // Only where waves are countable: few of them (the unsynchronised end of a long run of waves costs as much as the split
   // saves -- measured at N = 1: ladder 195.8 -> 199.1 ms) and tiles of equal cost (M = 820 has a half-cost seventh row tile:
   // a uniform split by the caller balances those better -- measured at the N = 8 ladder shape: 26.5 vs 28.3 ms).
-  const bool ragged_m = p.tiles_m <= 16 && (p.M % CF::BM) != 0;
+  // (a mildly ragged last row tile -- M = 1500: 12 tiles, the last at 3/4 cost -- keeps the waves countable)
+  const int rem_rows = p.M % CF::BM;
+  const int rag_frags = ((rem_rows + 7) / 8 + CF::WARPS_M - 1) / CF::WARPS_M;       // fragments per warp in the last row tile
+  const bool ragged_m = p.tiles_m <= 16 && rem_rows != 0 && 10 * rag_frags < 7 * CF::MI;
   if (tail_on && p.ksplit == 1 && p.kt_total >= 512 && p.cube_nv == 0 && p.units > nsm && p.units <= 16 * nsm && !ragged_m) {
     const int rem = p.units % nsm;
     int best_s = 1;

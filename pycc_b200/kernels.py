@@ -49,6 +49,16 @@ def _gemm_tiles(M, N):
     return ((M + 127) // 128) * ((N + 127) // 128)
 
 
+def _ragged_rows(M):
+    """gemm.cu's test for a last 128-row tile that is much cheaper than a full one (few row tiles, < 0.7 of the cost):
+    such products are balanced by a uniform split instead of the split-K of the last wave"""
+    rem = M % 128
+    if rem == 0 or (M + 127) // 128 > 16:
+        return False
+    frags_per_warp = -(-(-(-rem // 8)) // 4)          # ceil(ceil(rem / 8) / 4 warps)
+    return 10 * frags_per_warp < 7 * 4
+
+
 def auto_ksplit(M, N, K, batch, tma_like=False):
     """Split-K factor.  The GEMM is persistent (one CTA per SM doing ceil(units/148) rounds), so splitting K
     pays when the output has too few tiles to fill the SMs (Fae, Fmi, r1 terms) or when it fills the last
@@ -59,7 +69,7 @@ def auto_ksplit(M, N, K, batch, tma_like=False):
         # long-K products are scheduled dynamically (one CTA per unit): with 8-16 units per SM the last wave costs up to a
         # whole unit (measured: Z in pair form, 1316 units of 2822 k-tiles, 0.92 of the tensor bound); halves finish closer
         return 2
-    if tma_like and kt >= 512 and NSM < tiles <= 16 * NSM and not (M % 128 and (M + 127) // 128 <= 16):
+    if tma_like and kt >= 512 and NSM < tiles <= 16 * NSM and not _ragged_rows(M):
         # K-major long-K products with equal-cost tiles and few waves: the library splits K for the LAST wave only
         # (gemm.cu, "split-K of the last wave"; same conditions there)
         return 1

@@ -12,7 +12,7 @@ from pycc_b200 import kernels as K
 dev = torch.device("cuda:0")
 out = {}
 for n in (1, 2, 4, 8):
-    shapes = {"o3v3": (12000, 12000 // n, 12000, 1), "ladder": (820, (45150 + n - 1) // n, 45150, 2),
+    shapes = {"o3v3": (12000, 12000 // n, 12000, 1), "o3v3_T": (12000 // n, 12000, 12000, 1), "ladder": (820, (45150 + n - 1) // n, 45150, 2),
               "Z": (820, 12000 // n, 45150, 2)}
     for name, (M, N, Kd, b) in shapes.items():
         ld = (Kd + 15) // 16 * 16
