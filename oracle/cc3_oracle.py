@@ -12,7 +12,8 @@ written against the six stored Dirac blocks through ``lambda_oracle.eri`` (any <
 
 PARITY PINNED: ``tests/test_cc3.py::test_oracle_*`` checks the five intermediates, (X1, X2), the CC3 residuals at a
 generic point and the full ``solve_cc`` trace against outputs of the reference's own, unmodified code
-(``tests/golden/cc3_*.npz`` from ``tests/golden/make_golden_cc3.py``).
+(``tests/golden/cc3_*.npz`` from ``tests/golden/make_golden_cc3.py``); the real-time variant (explicit-field triples,
+real and complex amplitudes) against ``tests/golden/rtcc3_*.npz`` (``make_golden_rtcc3.py``).
 
 Only ``tests/`` may import this module, as the checker.
 """
@@ -58,8 +59,17 @@ def t3c_ijk(P, i, j, k, t2, Wvvvo, Wovoo, F):
     return t3 / ((eo[i] + eo[j] + eo[k]) - (ev[:, None, None] + ev[None, :, None] + ev[None, None, :]))
 
 
-def t_residual(P, F, t1, t2, W=None):
-    """(X1, X2) of _cc3_t_residual (ccwfn.py:374-430, real_time = False)."""
+def t3_pert_ijk(P, i, j, k, t2, V, F):
+    """Explicit-field coupling of the connected triples, with denominators (cctriples.py:679-705):
+    D t3[a,b,c] = V_ld t2[i,j,a,d] t2[k,l,c,b] -- ONE term, no permutations, as the reference writes it."""
+    t3 = es("al,lcb->abc", es("ld,ad->al", V[P.o, P.v], t2[i, j]), t2[k])
+    eps = np.diagonal(F)
+    eo, ev = eps[P.o], eps[P.v]
+    return t3 / ((eo[i] + eo[j] + eo[k]) - (ev[:, None, None] + ev[None, :, None] + ev[None, None, :]))
+
+
+def t_residual(P, F, t1, t2, W=None, real_time=False):
+    """(X1, X2) of _cc3_t_residual (ccwfn.py:374-430); ``real_time``: t3 -= t3_pert_ijk(V = F - H.F) (421-423)."""
     W = intermediates(P, t1) if W is None else W
     no = P.no
     Fme = F[P.o, P.v] + es("nf,mnef->me", t1, lint(P, "oovv"))            # build_Fme, ccwfn.py:563-564
@@ -70,6 +80,8 @@ def t_residual(P, F, t1, t2, W=None):
         for j in range(no):
             for k in range(no):
                 t3 = t3c_ijk(P, i, j, k, t2, W["Wabei"], W["Wmbij"], F)
+                if real_time:
+                    t3 = t3 - t3_pert_ijk(P, i, j, k, t2, F - P.F, F)
                 u = t3 - t3.transpose(2, 1, 0)
                 p = 2.0 * t3 - t3.transpose(0, 2, 1) - t3.transpose(2, 1, 0)
                 X1[i] += es("abc,bc->a", u, Loovv[j, k])
@@ -79,10 +91,10 @@ def t_residual(P, F, t1, t2, W=None):
     return X1, X2
 
 
-def residuals(P, F, t1, t2):
+def residuals(P, F, t1, t2, real_time=False):
     """CC3 residuals: the CCSD ones plus the connected-triples terms (ccwfn.py:358-367)."""
     r1, r2 = P.residuals(F, t1, t2)
-    X1, X2 = t_residual(P, F, t1, t2)
+    X1, X2 = t_residual(P, F, t1, t2, real_time=real_time)
     return r1 + X1, r2 + X2 + X2.transpose(1, 0, 3, 2)
 
 

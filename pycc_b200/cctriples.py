@@ -57,9 +57,14 @@ def triples_list(no):
 class TriplesEngine:
     """Owns the constant operands of the (T) GEMMs for one wavefunction state."""
 
-    def __init__(self, ccwfn, t1=None, t2=None, q_bytes=None, use_tma=True, cube_q=False, dressed=None, paired=False):
+    def __init__(self, ccwfn, t1=None, t2=None, q_bytes=None, use_tma=True, cube_q=False, dressed=None, paired=False,
+                 pert=None):
         """``dressed = (Wvvvo, Wovoo)``: build the t3 numerators of cctriples.py:50-62 from these blocks ([a,b,e,i] and
-        [m,b,i,j], no permutational symmetry assumed -- the T1-dressed CC3 intermediates) instead of the integrals."""
+        [m,b,i,j], no permutational symmetry assumed -- the T1-dressed CC3 intermediates) instead of the integrals.
+        ``pert = V_ov`` (real-time CC3, with ``dressed``): the numerators also carry the explicit-field term of
+        t3_pert_ijk (cctriples.py:694-695), -V_ld t2[i,j,a,d] t2[k,l,c,b].  It has the shape of the fourth hole term
+        (cctriples.py:60, -W_ovoo[m,a,j,i] t2[k,m,c,b]) and of no other, so ONLY the Q4 product reads a second copy of the
+        hole operand, Y'[j,i,a,m] = Y[j,i,a,m] - V_md t2[i,j,a,d], stacked behind Y: no extra pass over the t3 tile."""
         self.w = ccwfn
         H = ccwfn.H
         self.no, self.nv = ccwfn.no, ccwfn.nv
@@ -81,6 +86,19 @@ class TriplesEngine:
             # the natural-layout operand of the non-TMA path is [i][e][(a,b)] = Wvvvo[b,a,e,i]
             self.ovvv = None if self.tma else K.permuted(Wvvvo, (3, 2, 1, 0))
             self.Y = K.permuted(Wovoo, (2, 3, 1, 0), -1.0)        # Y[j,k,c,m] = -Wovoo[m,c,j,k]
+        self.ypert = 0
+        if pert is not None:
+            if dressed is None:
+                raise B200ccError("TriplesEngine: the explicit-field term is built for the dressed (CC3) numerators only")
+            no, nv = self.no, self.nv
+            X = torch.empty((no, no, nv, no), dtype=F64, device=self.dev)           # X[i,j,a,m] = t2[i,j,a,d] V[m,d]
+            K.dgemm(no * no * nv, no, nv, self.t2, nv, 0, pert.contiguous(), nv, 0, X, no)
+            Ycat = torch.empty((2, no, no, nv, no), dtype=F64, device=self.dev)
+            K.strided_axpby(Ycat[0], self.Y, 1.0, 0.0)
+            K.strided_axpby(Ycat[1], self.Y, 1.0, 0.0)
+            K.strided_axpby(Ycat[1], X.permute(1, 0, 2, 3), -1.0, 1.0)
+            self.Y, self.ypert = Ycat, no * no
+            del X
         if self.tma:
             if dressed is not None:
                 self.G = K.permuted(dressed[0], (3, 1, 0, 2))
@@ -157,7 +175,7 @@ class TriplesEngine:
             tab[:, q, 0] = p_ovvv + 8 * T[:, x] * v3
             tab[:, q, 1] = p_t2 + 8 * (T[:, p1] * no + T[:, q1]) * v2
             tab[:, q, 2] = p_t2 + 8 * T[:, x] * no * v2
-            tab[:, q, 3] = p_Y + 8 * (T[:, p2] * no + T[:, q2]) * nv * no
+            tab[:, q, 3] = p_Y + 8 * (T[:, p2] * no + T[:, q2] + (self.ypert if q == 3 else 0)) * nv * no
             tab[:, q, 4] = p_Q + 8 * (np.arange(nb) * 6 + q) * self.qsz
         aligned = bool(np.all(tab % 16 == 0))
         return torch.from_numpy(tab.reshape(nb * 6, 5)).to(self.dev), aligned
@@ -191,12 +209,13 @@ class TriplesEngine:
                 co[:, q, 0] = T[:, x]
                 co[:, q, 1] = T[:, p1] * no + T[:, q1]
                 co[:, q, 2] = T[:, x]
-                co[:, q, 3] = T[:, p2] * no + T[:, q2]
+                co[:, q, 3] = T[:, p2] * no + T[:, q2] + (self.ypert if q == 3 else 0)
             co = torch.from_numpy(co.reshape(nb * 6, 4)).to(self.dev)
             with K.mixed_mode(self.mixed):
                 K.dgemm(nv * nv, nv, nv, self.G, nv, 0, self.t2, nv, 0, Q, nv, 1.0, 0.0, batch=6 * nb,
                         sA=nv ** 3, sB=nv * nv, sC=self.qsz, seg2=(self.t2p, no, self.Y, no, no, no * nv * nv, nv * no),
-                        bcoords=co, nbatch=(no, no * no, no, no * no), ksplit=1, out_cube_nv=nv if self.cube else 0,
+                        bcoords=co, nbatch=(no, no * no, no, no * no + self.ypert), ksplit=1,
+                        out_cube_nv=nv if self.cube else 0,
                         mp_kchunk=512)      # K = v + o fits one FP32 run (<= 64 MMAs: bias < 1e-6 of E(T))
             return Q
         tab, aligned = self.table(trip, Q)
@@ -735,9 +754,12 @@ def t3_density(o, v, no, nv, t1, t2, F, ERI, L, contract, comm=None, k_batch=Non
 
 
 # ---- CC3: connected-triples contribution to the T residuals ----------------------------------
-def cc3_t_residual(ccwfn, F, t1, t2, Fme, W, k_batch=None, work_bytes=None):
-    """(X1, X2) of ``CCwfn._cc3_t_residual`` (reference: ccwfn.py:374-430, real_time = False) from the T1-dressed
-    intermediates ``W`` (dict with Wabei, Wmbij, Wmnie, Wamef in the reference's index orders).
+def cc3_t_residual(ccwfn, F, t1, t2, Fme, W, k_batch=None, work_bytes=None, V=None):
+    """(X1, X2) of ``CCwfn._cc3_t_residual`` (reference: ccwfn.py:374-430) from the T1-dressed intermediates ``W`` (dict
+    with Wabei, Wmbij, Wmnie, Wamef in the reference's index orders).  ``V`` (the o-v block of F - H.F; real_time = True,
+    ccwfn.py:421-423): every t3 is corrected by t3_pert_ijk inside its numerator GEMMs (TriplesEngine ``pert``).  That one
+    term is not symmetric under (i,a) <-> (j,b), so the tile of (i,j,k) no longer serves the loop body (j,i): with V the
+    loop runs over ALL ordered pairs (i,j), one build each (twice the t3 GEMMs of the field-free case).
 
     Same machinery as :func:`t3_density`, fed with dressed operands: for a pair i >= j and a run of k the t3
     numerators are the batched two-segment GEMMs of the (T) engine on (Wabei, Wmbij); ``b200cc_t3_connected_batch``
@@ -763,7 +785,7 @@ def cc3_t_residual(ccwfn, F, t1, t2, Fme, W, k_batch=None, work_bytes=None):
     kb = int(max(1, min(no, work_bytes // (13 * 8 * v3)))) if k_batch is None else int(max(1, min(no, k_batch)))
     kb = max(1, min(kb, (2 ** 32 - 1) // v3))
     kb = -(-no // -(-no // kb))
-    eng = TriplesEngine(shim, t1, t2, q_bytes=kb * 6 * v3 * 8, dressed=(W["Wabei"], W["Wmbij"]))
+    eng = TriplesEngine(shim, t1, t2, q_bytes=kb * 6 * v3 * 8, dressed=(W["Wabei"], W["Wmbij"]), pert=V)
     Wamef = W["Wamef"].contiguous()                               # [d,k,b,c]: K-major in (k,b,c) as stored
     Wq = K.permuted(W["Wmnie"], (0, 2, 1, 3))                      # [j,l,k,c]
     Loovv = H.derived("Loovv")
@@ -778,8 +800,11 @@ def cc3_t_residual(ccwfn, F, t1, t2, Fme, W, k_batch=None, work_bytes=None):
     gij, dv, s1 = z(nv, nv), z(nv), z(nv)                         # accumulators of the forms kernel that CC3 ignores
     try:
         for j0 in range(no):
-            for i0 in range(j0, no):
-                bodies = ((i0, j0, False),) if i0 == j0 else ((i0, j0, False), (j0, i0, True))
+            for i0 in range(j0 if V is None else 0, no):
+                if V is not None or i0 == j0:
+                    bodies = ((i0, j0, False),)
+                else:
+                    bodies = ((i0, j0, False), (j0, i0, True))
                 nb = len(bodies)
                 for k0 in range(0, no, kb):
                     nk = min(kb, no - k0)

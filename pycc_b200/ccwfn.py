@@ -295,16 +295,19 @@ class CCwfn(object):
         return K.strided_axpby(W, Z.permute(2, 3, 0, 1), 1.0, 1.0)
 
     def _cc3_t_residual(self, o, v, F, ERI, L, t1, t2, Fme, real_time=False):
-        """(X1, X2): the connected-triples contributions to the T1 / T2 residuals (ccwfn.py:374-430)."""
-        if real_time:
-            raise NotImplementedError("the explicit-field (real-time) CC3 triples are outside the accelerated path")
+        """(X1, X2): the connected-triples contributions to the T1 / T2 residuals (ccwfn.py:374-430).  ``real_time``:
+        every t3 is corrected by the explicit-field term t3_pert_ijk(V = F - H.F) (ccwfn.py:421-423)."""
         self._own(ERI, L)
         from . import cctriples
         t1 = t1.contiguous()
+        F = self._check_F(F)
+        V = None
+        if real_time:
+            V = K.strided_axpby(K.permuted(F[o, v], (0, 1)), self._check_F(self.H.F)[o, v], -1.0, 1.0)
         Wmnij = self.build_cc3_Wmnij(o, v, ERI, t1)
         W = {"Wmbij": self.build_cc3_Wmbij(o, v, ERI, t1, Wmnij), "Wmnie": self.build_cc3_Wmnie(o, v, ERI, t1),
              "Wamef": self.build_cc3_Wamef(o, v, ERI, t1), "Wabei": self.build_cc3_Wabei(o, v, ERI, t1)}
-        return cctriples.cc3_t_residual(self, self._check_F(F), t1, t2, Fme, W)
+        return cctriples.cc3_t_residual(self, F, t1, t2, Fme, W, V=V)
 
     def iterate(self, F=None):
         """One Jacobi step of solve_cc (ccwfn.py:272-286): residuals, then ONE fused pass doing
@@ -355,35 +358,39 @@ class CCwfn(object):
     def residuals(self, F, t1, t2, real_time=False):
         """(r1, r2) for the given Fock matrix and amplitudes; r2 symmetrised as in r_T2 (ccwfn.py:790)."""
         if _is_complex(t1) or _is_complex(t2) or _is_complex(F):
-            return self._residuals_complex(F, t1, t2)
-        if real_time and self.model == 'CC3':
-            # ccwfn.py:399-404: with real_time the CC3 triples use the explicit-field intermediates
-            raise NotImplementedError("the explicit-field (real-time) CC3 triples are outside the accelerated path")
+            return self._residuals_complex(F, t1, t2, real_time)
         if self._foreign():
             # someone swapped H.ERI / H.L (perturbed integrals, ccderiv.py:250-259): term-by-term generic evaluation
             r1, half = self._generic().residuals(F, t1, t2)
             return r1, K.symmetrize_r2(half)
-        r1, half = self._residuals_half(F, t1, t2)
+        r1, half = self._residuals_half(F, t1, t2, real_time=real_time)
         K.symmetrize_r2(half)
         return r1, half
 
-    def _residuals_complex(self, F, t1, t2):
+    def _residuals_complex(self, F, t1, t2, real_time=False):
         """(r1, r2) for COMPLEX t1, t2 (and optionally a complex Hermitian F) as torch.complex128 tensors: the RT-CC
         right-hand side (rt/rtcc.py:136-141).  Five fused real residuals, see utils.complex_from_real_samples -- a
         complex right-hand side costs 5 real residuals where complex arithmetic would cost 4 (3 with the 3M trick)
         real GEMMs per contraction, with the same kernels and the same sharding over ranks."""
         from .utils import complex_from_real_samples
+        degree = 4
         if self.model == 'CC3':
-            # the CC3 triples terms are of degree 5 in (F, t1, t2) scaled together (t3 ~ Wabei(t1^3) t2, contracted
-            # with Wamef(t1) / Fme): the five-sample quartic interpolation below would be silently wrong (~1e-4)
-            raise NotImplementedError("complex amplitudes with model='CC3' (RT-CC3) are outside the accelerated path")
+            # the CC3 triples terms are of degree 5 in (F, t1, t2) scaled together (t3 ~ Wabei(t1^3) t2, contracted with
+            # Wamef(t1) / Fme; the explicit-field term V t2 t2 W(t1) stays below): six samples.  The t3 denominators hold
+            # diag(F): they are the same in every sample only if that diagonal is real (a Hermitian field, rtcc.py:136)
+            degree = 5
+            if _is_complex(F):
+                Fc = F if isinstance(F, torch.Tensor) else torch.as_tensor(np.asarray(F))
+                if float(torch.diagonal(Fc).imag.abs().max()) != 0.0:
+                    raise NotImplementedError("complex CC3 residuals need a Fock matrix with a real diagonal "
+                                              "(the t3 denominators are not polynomial in Im f_pp)")
 
         def real_residual(Fs, t1s, t2s):
-            r1, half = self._residuals_half(Fs, t1s, t2s)
+            r1, half = self._residuals_half(Fs, t1s, t2s, real_time=real_time)
             K.symmetrize_r2(half)
             return r1, half.view(t2s.shape)
 
-        r1, r2 = complex_from_real_samples(real_residual, (F, t1, t2), self.device1)
+        r1, r2 = complex_from_real_samples(real_residual, (F, t1, t2), self.device1, degree=degree)
         return r1, r2
 
     def _check_F(self, F):
@@ -392,15 +399,15 @@ class CCwfn(object):
         F = F.to(self.device1, dtype=F64)
         return F if F.is_contiguous() else F.contiguous()
 
-    def _residuals_half(self, F, t1, t2, symmetric=False):
+    def _residuals_half(self, F, t1, t2, symmetric=False, real_time=False):
         """r1 and the UNsymmetrised half of r2 (ccwfn.py:922-940), fused formulation.  With several ranks
         each computes its share of r2 (see parallel.py) and ONE all-reduce sums them.  precision='MP': the large
         K-major contractions inside run on the split-TF32 tcgen05 kernel (kernels.mixed_mode).
         ``symmetric``: the caller vouches that t2[i,j,a,b] = t2[j,i,b,a] (halves the ladder once more)."""
         with K.mixed_mode(self.mixed):
-            return self._residuals_half_impl(F, t1, t2, symmetric)
+            return self._residuals_half_impl(F, t1, t2, symmetric, real_time)
 
-    def _residuals_half_impl(self, F, t1, t2, symmetric=False):
+    def _residuals_half_impl(self, F, t1, t2, symmetric=False, real_time=False):
         F = self._check_F(F)
         t1 = t1.contiguous()
         t2 = t2.contiguous()
@@ -427,7 +434,7 @@ class CCwfn(object):
         if self.model == 'CC3':
             # connected triples (ccwfn.py:364-367): r1 += X1, r2 += X2 + X2^T -- X2 joins the unsymmetrised half
             Fme = self.build_Fme(self.o, self.v, F, self.H.L, t1)
-            X1, X2 = self._cc3_t_residual(self.o, self.v, F, self.H.ERI, self.H.L, t1, t2, Fme)
+            X1, X2 = self._cc3_t_residual(self.o, self.v, F, self.H.ERI, self.H.L, t1, t2, Fme, real_time=real_time)
             K.strided_axpby(r1, X1, 1.0, 1.0)
             K.strided_axpby(half, X2, 1.0, 1.0)
         return r1, half

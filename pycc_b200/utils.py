@@ -237,15 +237,20 @@ def solve_params(method, e_conv, r_conv, maxiter, max_diis, start_diis):
 CPLX_PTS = (-2.0, -1.0, 0.0, 1.0, 2.0)
 CPLX_RE = (1.0 / 12.0, -5.0 / 6.0, 2.5, -5.0 / 6.0, 1.0 / 12.0)
 CPLX_IM = (1.0 / 6.0, -5.0 / 6.0, 0.0, 5.0 / 6.0, -1.0 / 6.0)
+# degree <= 5 (the CC3 triples terms): six half-integer points; the weights solve sum_k w_k s_k^m = Re / Im (i^m), m <= 5
+CPLX5_PTS = (-2.5, -1.5, -0.5, 0.5, 1.5, 2.5)
+CPLX5_RE = (65.0 / 768.0, -145.0 / 256.0, 377.0 / 384.0, 377.0 / 384.0, -145.0 / 256.0, 65.0 / 768.0)
+CPLX5_IM = (-13.0 / 384.0, 145.0 / 384.0, -377.0 / 192.0, 377.0 / 192.0, -145.0 / 384.0, 13.0 / 384.0)
+CPLX_RULES = {4: (CPLX_PTS, CPLX_RE, CPLX_IM), 5: (CPLX5_PTS, CPLX5_RE, CPLX5_IM)}
 
 
 def is_complex(x):
     return x.is_complex() if isinstance(x, torch.Tensor) else np.iscomplexobj(x)
 
 
-def complex_from_real_samples(fn, args, device):
+def complex_from_real_samples(fn, args, device, degree=4):
     """Evaluate ``fn(*args) -> tuple of real tensors`` for COMPLEX ``args`` when fn is polynomial of total degree <= 4
-    in its arguments (scaled together), using only real evaluations.
+    in its arguments (scaled together), using only real evaluations (``degree=5``: six samples, see CPLX5_*).
 
     For x = x_re + s x_im the map s -> fn(x(s)) is then a real polynomial of degree <= 4 in the real parameter s, and
     its value at s = i follows EXACTLY from the five samples s = -2..2:
@@ -272,9 +277,10 @@ def complex_from_real_samples(fn, args, device):
             return re
         return K.axpbyz(1.0, re, s, im, torch.empty_like(re))
 
+    pts, w_re, w_im = CPLX_RULES[int(degree)]
     P = [planes(a) for a in args]
     samples = []
-    for s in CPLX_PTS:
+    for s in pts:
         out = fn(*[at(re, im, s) for re, im in P])
         samples.append([o.contiguous() for o in out])
     result = []
@@ -284,9 +290,9 @@ def complex_from_real_samples(fn, args, device):
         zr = torch.view_as_real(z)
         tmp = torch.empty(shape, dtype=torch.float64, device=device)
         flat = [smp[q].reshape(-1) for smp in samples]
-        K.multi_axpy(CPLX_RE, flat, tmp.view(-1))
+        K.multi_axpy(w_re, flat, tmp.view(-1))
         K.strided_axpby(zr[..., 0], tmp, 1.0, 0.0)
-        K.multi_axpy([w for w in CPLX_IM if w != 0.0], [r for r, w in zip(flat, CPLX_IM) if w != 0.0], tmp.view(-1))
+        K.multi_axpy([w for w in w_im if w != 0.0], [r for r, w in zip(flat, w_im) if w != 0.0], tmp.view(-1))
         K.strided_axpby(zr[..., 1], tmp, 1.0, 0.0)
         result.append(z)
     return result

@@ -123,17 +123,96 @@ def test_cc3_odd_sizes(dev):
         assert np.abs(Y2.cpu().numpy() - X2).max() < 1e-12, (no, nv)
 
 
-def test_cc3_complex_and_real_time_refused(dev):
-    """The five-sample complex evaluation is exact for quartic residuals only; the CC3 triples terms are of degree 5, so
-    complex CC3 amplitudes (and real_time=True, whose explicit-field triples are not built) must raise, not return a
-    silently wrong residual."""
-    syn = make_synthetic(3, 5, seed=3, fock_noise=0.01)
+# ---- real-time CC3: explicit-field triples (ccwfn.py:421-423, cctriples.py:679-705), real and complex amplitudes ----
+RT = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "rtcc3_*.npz")))
+
+
+def load_rt(path):
+    g = dict(np.load(path))
+    tag = os.path.basename(path)[6:-4]
+    r = dict(np.load(os.path.join(ROOT, "tests", "golden", "ref_%s.npz" % tag)))
+    syn = Synthetic(int(r["no"]), int(r["nv"]), r["B"], r["F"], float(r["scale"]), int(r["seed"]))
+    return g, r, syn
+
+
+@pytest.fixture(params=RT, ids=[os.path.basename(p)[6:-4] for p in RT])
+def rt(request):
+    return load_rt(request.param)
+
+
+def TC(x):
+    return torch.from_numpy(np.array(x, order="C", copy=True)).to(DEV[0])
+
+
+def test_oracle_rtcc3(rt):
+    g, r, syn = rt
+    P = co.Problem(blocks_from_factor(syn), syn.F, syn.no)
+    X1, X2 = c3.t_residual(P, g["F_el"], g["t1"], g["t2"], real_time=True)
+    assert np.abs(X1 - g["X1_el"]).max() < 1e-13 and np.abs(X2 - g["X2_el"]).max() < 1e-13
+    Y1, Y2 = c3.t_residual(P, g["F_el"], g["t1"], g["t2"], real_time=False)
+    assert np.abs(Y2 - g["X2_el"]).max() > 1e-5                      # the field term is not negligible in the fixture
+    for name in ("el", "mag"):
+        r1, r2 = c3.residuals(P, g["F_" + name], g["c1"], g["c2"], real_time=True)
+        assert np.abs(r1 - g["c_r1_" + name]).max() < 1e-12, name
+        assert np.abs(r2 - g["c_r2_" + name]).max() < 1e-12, name
+
+
+def test_rtcc3_real_amplitudes(rt, dev):
+    g, r, syn = rt
     cc = pycc_b200.ccwfn(syn, model="CC3", device="GPU", quiet=True)
-    t1, t2 = cc.t1.clone(), cc.t2.clone()
+    o, v, H = cc.o, cc.v, cc.H
+    F, t1, t2 = T(g["F_el"]), T(g["t1"]), T(g["t2"])
+    Fme = cc.build_Fme(o, v, F, H.L, t1)
+    X1, X2 = cc._cc3_t_residual(o, v, F, H.ERI, H.L, t1, t2, Fme, real_time=True)
+    assert np.abs(X1.cpu().numpy() - g["X1_el"]).max() < 1e-12
+    assert np.abs(X2.cpu().numpy() - g["X2_el"]).max() < 1e-12
+    r1, r2 = cc.residuals(F, t1, t2, real_time=True)
+    assert np.abs(r1.cpu().numpy() - g["r1_el"]).max() < 1e-12
+    assert np.abs(r2.cpu().numpy() - g["r2_el"]).max() < 1e-12
+    # without a field (F = H.F) real_time changes nothing
+    a1, a2 = cc.residuals(H.F, t1, t2, real_time=True)
+    b1, b2 = cc.residuals(H.F, t1, t2)
+    assert np.abs((a1 - b1).cpu().numpy()).max() < 1e-13 and np.abs((a2 - b2).cpu().numpy()).max() < 1e-13
+
+
+@pytest.mark.parametrize("field", ["el", "mag"])
+def test_rtcc3_complex_amplitudes(rt, dev, field):
+    """rtcc.f (rt/rtcc.py:136-141) with model='CC3': complex amplitudes, Hermitian field; six real residuals."""
+    g, r, syn = rt
+    cc = pycc_b200.ccwfn(syn, model="CC3", device="GPU", quiet=True)
+    r1, r2 = cc.residuals(TC(g["F_" + field]), TC(g["c1"]), TC(g["c2"]), real_time=True)
+    assert r1.is_complex() and r2.is_complex()
+    assert np.abs(r1.cpu().numpy() - g["c_r1_" + field]).max() < 1e-10
+    assert np.abs(r2.cpu().numpy() - g["c_r2_" + field]).max() < 1e-10
+
+
+def test_rtcc3_odd_sizes_and_refusals(dev):
+    """odd o / v (the address-table operand path reads the second hole operand), k-run chunking; a Fock matrix with a
+    complex DIAGONAL makes the t3 denominators non-polynomial in the sample parameter: refused, not silently wrong."""
+    from pycc_b200 import cctriples
+    for (no, nv, kb) in ((3, 5, None), (5, 6, 2)):
+        syn = make_synthetic(no, nv, seed=11, fock_noise=0.01)
+        P = co.Problem(blocks_from_factor(syn), syn.F, no)
+        rng = np.random.default_rng(2)
+        t1 = 0.05 * rng.standard_normal((no, nv))
+        t2 = 0.05 * rng.standard_normal((no, no, nv, nv))
+        m = rng.standard_normal(syn.F.shape)
+        F = syn.F + 0.03 * (m + m.T)
+        X1, X2 = c3.t_residual(P, F, t1, t2, real_time=True)
+        cc = pycc_b200.ccwfn(syn, model="CC3", device="GPU", quiet=True)
+        o, v, H = cc.o, cc.v, cc.H
+        a1, a2, Fd = T(t1), T(t2), T(F)
+        Wmnij = cc.build_cc3_Wmnij(o, v, H.ERI, a1)
+        W = {"Wmbij": cc.build_cc3_Wmbij(o, v, H.ERI, a1, Wmnij), "Wmnie": cc.build_cc3_Wmnie(o, v, H.ERI, a1),
+             "Wamef": cc.build_cc3_Wamef(o, v, H.ERI, a1), "Wabei": cc.build_cc3_Wabei(o, v, H.ERI, a1)}
+        V = T(np.ascontiguousarray((F - syn.F)[:no, no:]))
+        Y1, Y2 = cctriples.cc3_t_residual(cc, Fd, a1, a2, cc.build_Fme(o, v, Fd, H.L, a1), W, k_batch=kb, V=V)
+        assert np.abs(Y1.cpu().numpy() - X1).max() < 1e-12, (no, nv)
+        assert np.abs(Y2.cpu().numpy() - X2).max() < 1e-12, (no, nv)
+    Fbad = torch.as_tensor(syn.F).to(torch.complex128)
+    Fbad[0, 0] += 0.01j
     with pytest.raises(NotImplementedError):
-        cc.residuals(cc.H.F, t1.to(torch.complex128), t2.to(torch.complex128))
-    with pytest.raises(NotImplementedError):
-        cc.residuals(cc.H.F, t1, t2, real_time=True)
+        cc.residuals(Fbad.to(DEV[0]), a1.to(torch.complex128), a2.to(torch.complex128), real_time=True)
 
 
 @pytest.mark.gpu
