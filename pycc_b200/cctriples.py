@@ -754,12 +754,14 @@ def t3_density(o, v, no, nv, t1, t2, F, ERI, L, contract, comm=None, k_batch=Non
 
 
 # ---- CC3: connected-triples contribution to the T residuals ----------------------------------
-def cc3_t_residual(ccwfn, F, t1, t2, Fme, W, k_batch=None, work_bytes=None, V=None):
+def cc3_t_residual(ccwfn, F, t1, t2, Fme, W, k_batch=None, work_bytes=None, V=None, comm=None, reduce=True):
     """(X1, X2) of ``CCwfn._cc3_t_residual`` (reference: ccwfn.py:374-430) from the T1-dressed intermediates ``W`` (dict
     with Wabei, Wmbij, Wmnie, Wamef in the reference's index orders).  ``V`` (the o-v block of F - H.F; real_time = True,
     ccwfn.py:421-423): every t3 is corrected by t3_pert_ijk inside its numerator GEMMs (TriplesEngine ``pert``).  That one
     term is not symmetric under (i,a) <-> (j,b), so the tile of (i,j,k) no longer serves the loop body (j,i): with V the
     loop runs over ALL ordered pairs (i,j), one build each (twice the t3 GEMMs of the field-free case).
+    ``comm``: the pairs are dealt round-robin over the ranks (equal cost each); ``reduce`` sums the partial (X1, X2) with
+    one all-reduce each, ``reduce=False`` hands the rank's partial sums to a caller that all-reduces them itself.
 
     Same machinery as :func:`t3_density`, fed with dressed operands: for a pair i >= j and a run of k the t3
     numerators are the batched two-segment GEMMs of the (T) engine on (Wabei, Wmbij); ``b200cc_t3_connected_batch``
@@ -799,33 +801,38 @@ def cc3_t_residual(ccwfn, F, t1, t2, Fme, W, k_batch=None, work_bytes=None, V=No
     Ctmp = torch.empty(2 * v2, dtype=F64, device=dev)
     gij, dv, s1 = z(nv, nv), z(nv), z(nv)                         # accumulators of the forms kernel that CC3 ignores
     try:
-        for j0 in range(no):
-            for i0 in range(j0 if V is None else 0, no):
-                if V is not None or i0 == j0:
-                    bodies = ((i0, j0, False),)
-                else:
-                    bodies = ((i0, j0, False), (j0, i0, True))
-                nb = len(bodies)
-                for k0 in range(0, no, kb):
-                    nk = min(kb, no - k0)
-                    trip = [(i0, j0, k) for k in range(k0, k0 + nk)]
-                    ijk = torch.tensor(np.asarray(trip, dtype=np.int32), dtype=torch.int32).to(dev)
-                    Q = eng.build_q(trip)
-                    K.t3_connected_batch(no, nv, ijk, Q, eo, ev, M3)
-                    kc, kbc, seg = nk * nv, nk * v2, nk * v3
-                    for q, (i, j, swap) in enumerate(bodies):
-                        # weights: "t2s" -> L_jkbc (its Dov output is the X1[i] increment), "fov" -> H_me
-                        K.t3_density_forms(no, nv, i, j, k0, nk, M3, t1, Loovv, Loovv, Fme, eo, ev, junk[0], junk[1],
-                                           Pab[q], NB[q * seg:(q + 1) * seg], gij, X2[i, j], dv, X1[i], s1,
-                                           swap_ab=swap)
-                        K.dgemm(v2, no, kc, Pab[q], kc, 0, (Wq, (j * no * no + k0) * nv), no * nv, 0, X2T[i], no,
-                                -1.0, 1.0)
-                    M = nb * nv
-                    K.dgemm(M, nv, kbc, NB, kbc, 0, (Wamef, k0 * v2), no * v2, 0, Ctmp, nv, 1.0, 0.0,
-                            ksplit=K.balanced_ksplit(M, nv, kbc))
-                    for q, (i, j, _) in enumerate(bodies):
-                        K.axpbyz(1.0, X2[i, j].view(-1), 1.0, Ctmp[q * v2:(q + 1) * v2], X2[i, j].view(-1))
+        pairs = [(i0, j0) for j0 in range(no) for i0 in range(j0 if V is None else 0, no)]
+        if comm is not None:
+            pairs = pairs[comm.rank::comm.size]
+        for (i0, j0) in pairs:
+            if V is not None or i0 == j0:
+                bodies = ((i0, j0, False),)
+            else:
+                bodies = ((i0, j0, False), (j0, i0, True))
+            nb = len(bodies)
+            for k0 in range(0, no, kb):
+                nk = min(kb, no - k0)
+                trip = [(i0, j0, k) for k in range(k0, k0 + nk)]
+                ijk = torch.tensor(np.asarray(trip, dtype=np.int32), dtype=torch.int32).to(dev)
+                Q = eng.build_q(trip)
+                K.t3_connected_batch(no, nv, ijk, Q, eo, ev, M3)
+                kc, kbc, seg = nk * nv, nk * v2, nk * v3
+                for q, (i, j, swap) in enumerate(bodies):
+                    # weights: "t2s" -> L_jkbc (its Dov output is the X1[i] increment), "fov" -> H_me
+                    K.t3_density_forms(no, nv, i, j, k0, nk, M3, t1, Loovv, Loovv, Fme, eo, ev, junk[0], junk[1],
+                                       Pab[q], NB[q * seg:(q + 1) * seg], gij, X2[i, j], dv, X1[i], s1,
+                                       swap_ab=swap)
+                    K.dgemm(v2, no, kc, Pab[q], kc, 0, (Wq, (j * no * no + k0) * nv), no * nv, 0, X2T[i], no,
+                            -1.0, 1.0)
+                M = nb * nv
+                K.dgemm(M, nv, kbc, NB, kbc, 0, (Wamef, k0 * v2), no * v2, 0, Ctmp, nv, 1.0, 0.0,
+                        ksplit=K.balanced_ksplit(M, nv, kbc))
+                for q, (i, j, _) in enumerate(bodies):
+                    K.axpbyz(1.0, X2[i, j].view(-1), 1.0, Ctmp[q * v2:(q + 1) * v2], X2[i, j].view(-1))
     finally:
         eng.close()
     K.strided_axpby(X2, X2T.view(no, nv, nv, no).permute(0, 3, 1, 2), 1.0, 1.0)
+    if comm is not None and reduce:
+        comm.all_reduce_sum(X1)
+        comm.all_reduce_sum(X2)
     return X1, X2

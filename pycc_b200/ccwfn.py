@@ -275,11 +275,19 @@ class CCwfn(object):
              Z_abei = -t_ma (<mb|ei> + t_if <mb|ef>)
         (the reference's symmetric + antisymmetric split of <ab|ef> sums back to the block: ONE pass over <ab|ef>)."""
         self._own(ERI)
-        if self.part.size > 1:
-            raise NotImplementedError("CC3 intermediates need the whole <ab|ef> block on this rank")
         ct, t1 = self._ct, t1.contiguous()
         Z = K.permuted(self._E('vovv'), (0, 1, 2, 3))                                   # [e,i,a,b]
-        if self._vvvv_released():
+        if self.part.size > 1 and self.H.a_range != (0, self.nv):
+            # <ab|ef> a-sharded over the ranks (parallel.py): each contracts the pairs it holds, ONE all-reduce of the
+            # o v^3 piece; every other term of W_abei is replicated
+            if self.H.a_range != tuple(self.part.a_range(self.nv)):
+                raise NotImplementedError("<ab|ef> rows resident on this rank are neither its share nor the whole block")
+            piece = torch.zeros((self.nv, self.nv, self.nv, self.no), dtype=F64, device=self.device1)
+            self._t1_vvvv(t1, piece)
+            self.part.all_reduce_sum(piece)
+            K.strided_axpby(Z, piece.permute(2, 3, 0, 1), 1.0, 1.0)
+            del piece
+        elif self._vvvv_released():
             self._t1_vvvv(t1, Z.permute(2, 3, 0, 1))
         else:
             ct('if,abef->eiab', t1, self._E('vvvv'), out=Z, alpha=1.0, beta=1.0)
@@ -294,9 +302,11 @@ class CCwfn(object):
         W = ct('ma,mbei->abei', t1, Zmbei, alpha=-1.0)
         return K.strided_axpby(W, Z.permute(2, 3, 0, 1), 1.0, 1.0)
 
-    def _cc3_t_residual(self, o, v, F, ERI, L, t1, t2, Fme, real_time=False):
+    def _cc3_t_residual(self, o, v, F, ERI, L, t1, t2, Fme, real_time=False, reduce=True):
         """(X1, X2): the connected-triples contributions to the T1 / T2 residuals (ccwfn.py:374-430).  ``real_time``:
-        every t3 is corrected by the explicit-field term t3_pert_ijk(V = F - H.F) (ccwfn.py:421-423)."""
+        every t3 is corrected by the explicit-field term t3_pert_ijk(V = F - H.F) (ccwfn.py:421-423).  With several
+        ranks the (i,j) pairs of the triples loop are dealt round-robin; ``reduce=False`` returns this rank's partial
+        sums (the caller adds them to a buffer it all-reduces anyway)."""
         self._own(ERI, L)
         from . import cctriples
         t1 = t1.contiguous()
@@ -307,7 +317,8 @@ class CCwfn(object):
         Wmnij = self.build_cc3_Wmnij(o, v, ERI, t1)
         W = {"Wmbij": self.build_cc3_Wmbij(o, v, ERI, t1, Wmnij), "Wmnie": self.build_cc3_Wmnie(o, v, ERI, t1),
              "Wamef": self.build_cc3_Wamef(o, v, ERI, t1), "Wabei": self.build_cc3_Wabei(o, v, ERI, t1)}
-        return cctriples.cc3_t_residual(self, F, t1, t2, Fme, W, V=V)
+        comm = self.part if self.part.size > 1 else None
+        return cctriples.cc3_t_residual(self, F, t1, t2, Fme, W, V=V, comm=comm, reduce=reduce)
 
     def iterate(self, F=None):
         """One Jacobi step of solve_cc (ccwfn.py:272-286): residuals, then ONE fused pass doing
@@ -425,18 +436,21 @@ class CCwfn(object):
             self._r2_half_cc2(F, t1, t2, half)
         else:
             self._r2_half(F, t1, t2, I, half, symmetric=symmetric)
+        if self.model == 'CC3':
+            # connected triples (ccwfn.py:364-367): r1 += X1, r2 += X2 + X2^T -- X2 joins the unsymmetrised half, the
+            # rank's partial sums (its (i,j) pairs of the triples loop) join the rank-partial buffers before the all-reduce
+            Fme = self.build_Fme(self.o, self.v, F, self.H.L, t1)
+            X1, X2 = self._cc3_t_residual(self.o, self.v, F, self.H.ERI, self.H.L, t1, t2, Fme, real_time=real_time,
+                                          reduce=False)
+            K.strided_axpby(r1p, X1, 1.0, 1.0)
+            K.strided_axpby(half, X2, 1.0, 1.0)
+            del X1, X2
         if self.part.size > 1:
             with K.PHASES("all-reduce r2"):
                 self.part.all_reduce_sum(buf)
         K.strided_axpby(r1, r1p, 1.0, 1.0)
         if self.model == 'CCD':
             r1.zero_()
-        if self.model == 'CC3':
-            # connected triples (ccwfn.py:364-367): r1 += X1, r2 += X2 + X2^T -- X2 joins the unsymmetrised half
-            Fme = self.build_Fme(self.o, self.v, F, self.H.L, t1)
-            X1, X2 = self._cc3_t_residual(self.o, self.v, F, self.H.ERI, self.H.L, t1, t2, Fme, real_time=real_time)
-            K.strided_axpby(r1, X1, 1.0, 1.0)
-            K.strided_axpby(half, X2, 1.0, 1.0)
         return r1, half
 
     # ---- shared per-iteration rearrangements of the amplitudes -----------------------------------

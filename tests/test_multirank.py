@@ -186,3 +186,55 @@ def test_lambda_with_sharded_vvvv_mixed_precision():
         assert p.exitcode == 0
     for rank, dh, de, dl, n, nref in res:
         assert dh < 1e-6 and de < 1e-6 and dl < 1e-6, (rank, dh, de, dl)
+
+
+def _worker_cc3(rank, world, port, tag, q):
+    """model='CC3' on several ranks: t1.<ab|ef> of W_abei from the rank's pairs (one all-reduce), the (i,j) pairs of the
+    triples loop dealt round-robin, their partial (X1, X2) summed by the residual's own all-reduce."""
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import pycc_b200
+        from pycc_b200.parallel import Comm
+        from tests import emu
+        from tests.test_cc3 import load, load_rt
+        g, r, syn = load(os.path.join(ROOT, "tests", "golden", "cc3_%s.npz" % tag))
+        grt, _, _ = load_rt(os.path.join(ROOT, "tests", "golden", "rtcc3_%s.npz" % tag))
+        with emu.install():
+            comm = Comm()
+            cc = pycc_b200.ccwfn(syn, model="CC3", device="GPU", quiet=True, comm=comm)
+            assert cc.H.a_range == tuple(comm.a_range(syn.nv))
+            o, v, H = cc.o, cc.v, cc.H
+            t1, t2 = torch.from_numpy(g["t1"].copy()), torch.from_numpy(g["t2"].copy())
+            dw = float(np.abs(cc.build_cc3_Wabei(o, v, H.ERI, t1).numpy() - g["Wabei"]).max())
+            X1, X2 = cc._cc3_t_residual(o, v, H.F, H.ERI, H.L, t1, t2, cc.build_Fme(o, v, H.F, H.L, t1))
+            dx = max(float(np.abs(X1.numpy() - g["X1"]).max()), float(np.abs(X2.numpy() - g["X2"]).max()))
+            r1, r2 = cc.residuals(H.F, t1, t2)
+            dr = max(float(np.abs(r1.numpy() - g["r1"]).max()), float(np.abs(r2.numpy() - g["r2"]).max()))
+            F_el = torch.from_numpy(grt["F_el"].copy())
+            q1, q2 = cc.residuals(F_el, t1, t2, real_time=True)
+            drt = max(float(np.abs(q1.numpy() - grt["r1_el"]).max()), float(np.abs(q2.numpy() - grt["r2_el"]).max()))
+            ecc = cc.solve_cc(1e-12, 1e-12)
+            q.put((rank, dw, dx, dr, drt, abs(float(ecc) - float(g["ecc"])), len(cc.trace), len(g["trace_ecc_rms"]),
+                   float(np.abs(cc.t2.numpy() - g["conv_t2"]).max())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_cc3_on_several_ranks(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 500) + 40 + world
+    procs = [ctx.Process(target=_worker_cc3, args=(r, world, port, "o4v10_s1_noise", q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, dw, dx, dr, drt, de, n, nref, dt in res:
+        assert dw < 1e-12 and dx < 1e-12 and dr < 1e-12 and drt < 1e-12, (rank, dw, dx, dr, drt)
+        assert de < 1e-11 and n == nref and dt < 1e-10, (rank, de, n, nref, dt)
