@@ -347,7 +347,8 @@ class BlockHamiltonian:
         return H
 
     @classmethod
-    def from_ao(cls, F_ao, eri_ao, C, no, nfzc=0, device="cuda", a_range=None, chunk_bytes=4 << 30):
+    def from_ao(cls, F_ao, eri_ao, C, no, nfzc=0, device="cuda", a_range=None, chunk_bytes=4 << 30, stream_ao=None,
+                slab_bytes=1 << 30):
         """AO -> MO integral staging straight into the six device blocks (reference:
         hamiltonian.py:54-70, which asks psi4 for the full n^4 MO array on the host and forms ERI and L there).
 
@@ -361,7 +362,15 @@ class BlockHamiltonian:
         as four quarter transformations per block family.  The first two indices (p,r) are transformed once per
         family -- (o,o) feeds oooo/ooov/ovov, (o,v) feeds oovv/ovvv -- and <ab|ef> is produced in row chunks of a
         (``chunk_bytes``), directly for this rank's ``a_range``: neither the n^4 MO array nor L ever exists, on
-        the host or on the device.  The AO array itself is held on the device (nbf^4 doubles)."""
+        the host or on the device.
+
+        The AO array (nbf^4 doubles) is held on the device when it fits next to the blocks.  Otherwise (``stream_ao``:
+        None = decide from the free device memory, True / False = force) it STAYS ON THE HOST -- a numpy array or
+        ``np.memmap`` -- and every first quarter transformation, the only step that reads it, streams it in slabs of the
+        first AO index (``slab_bytes`` each, through two pinned staging buffers so that the copy of slab s+1 overlaps the
+        GEMM of slab s) and accumulates  X1[p,lam,nu,sig] += C[mu_slab,p]^T (mu_slab lam|nu sig):  one pass for the
+        occupied family, one pass per <ab|ef> row chunk (raise ``chunk_bytes`` for fewer passes).  nbf is then bounded by
+        the host memory (or the file), not by HBM."""
         dev = torch.device(device)
         ct = Contractor()
         def as_dev(x):
@@ -374,9 +383,67 @@ class BlockHamiltonian:
         Co = K.permuted(C[:, nfzc:nfzc + no], (0, 1))
         Cv = K.permuted(C[:, nfzc + no:], (0, 1))
         F = ct("mp,mn,nq->pq", C, as_dev(F_ao), C)
-        AO = as_dev(eri_ao)
-        if tuple(AO.shape) != (nbf,) * 4:
+        if tuple(eri_ao.shape) != (nbf,) * 4:
             raise B200ccError("from_ao: eri_ao must have shape (nbf,nbf,nbf,nbf) = %r" % ((nbf,) * 4,))
+        on_device = isinstance(eri_ao, torch.Tensor) and eri_ao.device.type == dev.type == "cuda"
+        if stream_ao is None:
+            stream_ao = False
+            if not on_device and dev.type == "cuda":
+                # resident AO array + the <ab|ef> rows + one o nbf^3 intermediate and its successor must fit
+                nv_, na_ = nmo - no - nfzc, (nmo - no - nfzc) if a_range is None else int(a_range[1]) - int(a_range[0])
+                need = 8 * (nbf ** 4 + na_ * nv_ ** 3 + 2 * max(no, 1) * nbf ** 3) + chunk_bytes
+                stream_ao = need > int(torch.cuda.mem_get_info(dev)[0] * 0.9)
+        if stream_ao and on_device:
+            raise B200ccError("from_ao: stream_ao=True needs the AO array on the host")
+        AO = None if stream_ao else as_dev(eri_ao)
+        host = None
+        if stream_ao:
+            host = eri_ao.detach().cpu().numpy() if isinstance(eri_ao, torch.Tensor) else eri_ao
+            nslab = max(1, min(nbf, int(slab_bytes // (8 * nbf ** 3))))
+            stage = [torch.empty((nslab, nbf, nbf, nbf), dtype=torch.float64,
+                                 pin_memory=(dev.type == "cuda")) for _ in range(2)]
+            dslab = [torch.empty((nslab, nbf, nbf, nbf), dtype=torch.float64, device=dev) for _ in range(2)]
+            copy_stream = torch.cuda.Stream(dev) if dev.type == "cuda" else None
+            copied = [None, None]          # event: the H2D copy out of stage[b] / into dslab[b] has completed
+            consumed = [None, None]        # event: the GEMM that read dslab[b] has been issued on the compute stream
+
+        def upload(bounds, idx):
+            """host rows -> pinned stage[b] (host copy) -> dslab[b] (async, copy stream); returns the slab's event"""
+            m0, m1 = bounds[idx]
+            b = idx & 1
+            if copied[b] is not None:
+                copied[b].synchronize()                              # stage[b] is free again
+            np.copyto(stage[b][:m1 - m0].numpy(), np.asarray(host[m0:m1], dtype=np.float64))
+            if copy_stream is None:
+                dslab[b][:m1 - m0].copy_(stage[b][:m1 - m0])
+                return None
+            with torch.cuda.stream(copy_stream):
+                if consumed[b] is not None:
+                    copy_stream.wait_event(consumed[b])              # dslab[b] is free again
+                dslab[b][:m1 - m0].copy_(stage[b][:m1 - m0], non_blocking=True)
+                copied[b] = torch.cuda.Event()
+                copied[b].record(copy_stream)
+            return copied[b]
+
+        def first_quarter(Cx):
+            """X1[p,lam,nu,sig] = C[mu,p] (mu lam|nu sig): ONE GEMM on the resident AO array, or a sweep over host slabs
+            (pinned staging + copy stream: the host copy and the H2D copy of slab s+1 run under the GEMM of slab s)."""
+            if not stream_ao:
+                return ct("mp,mlns->plns", Cx, AO)
+            X1 = torch.zeros((Cx.shape[1], nbf, nbf, nbf), dtype=torch.float64, device=dev)
+            bounds = [(m0, min(nbf, m0 + nslab)) for m0 in range(0, nbf, nslab)]
+            ready = upload(bounds, 0)
+            for idx, (m0, m1) in enumerate(bounds):
+                b = idx & 1
+                if ready is not None:
+                    torch.cuda.current_stream(dev).wait_event(ready)
+                ct("mp,mlns->plns", K.permuted(Cx[m0:m1], (0, 1)), dslab[b][:m1 - m0], out=X1, alpha=1.0, beta=1.0)
+                if copy_stream is not None:
+                    consumed[b] = torch.cuda.Event()
+                    consumed[b].record(torch.cuda.current_stream(dev))
+                if idx + 1 < len(bounds):
+                    ready = upload(bounds, idx + 1)
+            return X1
 
         def finish(X2, Cq, Cs):
             """X2[p,r,nu,sig] -> <pq|rs>[p,q,r,s]"""
@@ -386,7 +453,7 @@ class BlockHamiltonian:
             return K.permuted(Z, (0, 2, 1, 3))
 
         blocks = {}
-        X1 = ct("mp,mlns->plns", Co, AO)                        # first index -> occupied
+        X1 = first_quarter(Co)                                  # first index -> occupied
         X2 = ct("plns,lr->prns", X1, Co)                        # (p,r) = (o,o)
         blocks["oooo"] = finish(X2, Co, Co)
         blocks["ooov"] = finish(X2, Co, Cv)                     # <mn|ie> = (mi|ne)
@@ -403,7 +470,7 @@ class BlockHamiltonian:
         for a0 in range(0, na, rows):
             a1 = min(na, a0 + rows)
             Ca = K.permuted(Cv[:, a_lo + a0:a_lo + a1], (0, 1))
-            X1 = ct("mp,mlns->plns", Ca, AO)
+            X1 = first_quarter(Ca)
             X2 = ct("plns,lr->prns", X1, Cv)                    # (a,e)
             del X1
             Y = ct("prns,nq->prqs", X2, Cv)
@@ -414,6 +481,8 @@ class BlockHamiltonian:
             del Z
         blocks["vvvv"] = vvvv
         del AO
+        if stream_ao:
+            del stage, dslab
         return cls(F, blocks, no, nfzc, dev, a_range)
 
     # ---- derived constant layouts (built once, cached) ---------------------------------------------

@@ -87,3 +87,33 @@ def test_shape_error(dev):
     F_ao, chem, C = ao_problem(2, 3, 0, 6, seed=1)
     with pytest.raises(B200ccError):
         BlockHamiltonian.from_ao(F_ao, chem[:5], C, 2, 0, dev)
+
+
+@pytest.mark.parametrize("slab_rows", [1, 3, 100])
+def test_host_streamed_ao_equals_resident(dev, slab_rows):
+    """nbf too large for the AO array to sit in HBM: it stays on the host and every first quarter transformation sweeps
+    it in slabs of the first AO index (ragged last slab; one sweep per <ab|ef> row chunk)."""
+    no, nv, nfzc, nbf = 3, 6, 1, 11
+    F_ao, chem, C = ao_problem(no, nv, nfzc, nbf, seed=7)
+    Hr = BlockHamiltonian.from_ao(F_ao, chem, C, no, nfzc, dev, stream_ao=False)
+    Hs = BlockHamiltonian.from_ao(F_ao, chem, C, no, nfzc, dev, stream_ao=True, slab_bytes=8 * nbf ** 3 * slab_rows,
+                                  chunk_bytes=8 * nbf ** 3 * 4, a_range=(1, 6))
+    for name in ("oooo", "ooov", "oovv", "ovov", "ovvv"):
+        assert np.abs((Hs.block(name) - Hr.block(name)).cpu().numpy()).max() < 1e-13, name
+    assert np.abs((Hs.block("vvvv") - Hr.block("vvvv")[1:6]).cpu().numpy()).max() < 1e-13
+    assert np.abs((Hs.F - Hr.F).cpu().numpy()).max() == 0.0
+
+
+def test_host_streamed_ao_from_memmap(dev, tmp_path):
+    no, nv, nfzc, nbf = 2, 5, 0, 8
+    F_ao, chem, C = ao_problem(no, nv, nfzc, nbf, seed=9)
+    mm = np.memmap(tmp_path / "ao.bin", dtype=np.float64, mode="w+", shape=chem.shape)
+    mm[:] = chem
+    mm.flush()
+    _, ERI, _ = ao.mo_hamiltonian(F_ao, chem, C)
+    H = BlockHamiltonian.from_ao(F_ao, np.memmap(tmp_path / "ao.bin", dtype=np.float64, mode="r", shape=chem.shape), C,
+                                 no, nfzc, dev, stream_ao=True, slab_bytes=8 * nbf ** 3 * 3)
+    o, v = H.o, H.v
+    for pat in ("oooo", "ovvv", "vvvv", "ovvo"):
+        key = tuple(o if c == "o" else v for c in pat)
+        assert np.abs(H.ERI[key].cpu().numpy() - ERI[key]).max() < 1e-12, pat
