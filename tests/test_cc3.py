@@ -186,6 +186,28 @@ def test_rtcc3_complex_amplitudes(rt, dev, field):
     assert np.abs(r2.cpu().numpy() - g["c_r2_" + field]).max() < 1e-10
 
 
+def test_t3_pert_public_functions(rt, dev):
+    """cctriples.t3_pert_ijk / t3_pert_abc in the reference's signatures (cctriples.py:679-720) against the oracle's
+    restatement (itself pinned through (X1, X2) of the rtcc3 goldens); the two forms are the same tensor."""
+    from pycc_b200 import cctriples
+    g, r, syn = rt
+    P = co.Problem(blocks_from_factor(syn), syn.F, syn.no)
+    cc = pycc_b200.ccwfn(syn, model="CC3", device="GPU", quiet=True)
+    o, v = cc.o, cc.v
+    F, t2 = T(g["F_el"]), T(g["t2"])
+    V = T(g["F_el"] - syn.F)
+    for (i, j, k) in ((2, 1, 0), (0, 2, 2), (1, 1, 1)):
+        want = c3.t3_pert_ijk(P, i, j, k, g["t2"], g["F_el"] - syn.F, g["F_el"])
+        got = cctriples.t3_pert_ijk(o, v, i, j, k, t2, V, F, cc.contract)
+        assert np.abs(got.cpu().numpy() - want).max() < 1e-13, (i, j, k)
+        raw = cctriples.t3_pert_ijk(o, v, i, j, k, t2, V, F, cc.contract, WithDenom=False)
+        for (a, b, c) in ((0, 1, 2), (3, 3, 1)):
+            x = cctriples.t3_pert_abc(o, v, a, b, c, t2, V, F, cc.contract, WithDenom=False)
+            assert abs(float(x[i, j, k]) - float(raw[a, b, c])) < 1e-14
+            y = cctriples.t3_pert_abc(o, v, a, b, c, t2, V, F, cc.contract)
+            assert abs(float(y[i, j, k]) - want[a, b, c]) < 1e-13
+
+
 def test_rtcc3_odd_sizes_and_refusals(dev):
     """odd o / v (the address-table operand path reads the second hole operand), k-run chunking; a Fock matrix with a
     complex DIAGONAL makes the t3 denominators non-polynomial in the sample parameter: refused, not silently wrong."""
