@@ -62,15 +62,17 @@ class IntegralReference:
         return r
 
     @classmethod
-    def from_ao(cls, F_ao, eri_ao, C, no, nfzc=0, eref=0.0):
+    def from_ao(cls, F_ao, eri_ao, C, no, nfzc=0, eref=0.0, stream_ao=None):
         """AO-basis inputs (Fock matrix, chemist-order repulsion integrals, MO coefficients): the AO -> MO
-        transformation runs on the device, straight into the six blocks (BlockHamiltonian.from_ao)."""
+        transformation runs on the device, straight into the six blocks (BlockHamiltonian.from_ao).  ``eri_ao`` may be a
+        host array / np.memmap too large for the device: it is then streamed in slabs (``stream_ao``: None = decide
+        from the free device memory)."""
         r = cls(eref)
 
         def make(device, comm, mixed):
             nv = np.asarray(C).shape[1] - no - nfzc
             a_range = None if comm is None else comm.a_range(nv)
-            return BlockHamiltonian.from_ao(F_ao, eri_ao, C, no, nfzc, device, a_range=a_range)
+            return BlockHamiltonian.from_ao(F_ao, eri_ao, C, no, nfzc, device, a_range=a_range, stream_ao=stream_ao)
         r._make = make
         return r
 

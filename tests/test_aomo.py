@@ -117,3 +117,14 @@ def test_host_streamed_ao_from_memmap(dev, tmp_path):
     for pat in ("oooo", "ovvv", "vvvv", "ovvo"):
         key = tuple(o if c == "o" else v for c in pat)
         assert np.abs(H.ERI[key].cpu().numpy() - ERI[key]).max() < 1e-12, pat
+
+
+def test_ccsd_from_host_streamed_ao(dev):
+    """the whole chain with the AO tensor kept on the host: same energy as with the resident tensor"""
+    no, nv, nfzc, nbf = 3, 6, 1, 12
+    F_ao, chem, C = ao_problem(no, nv, nfzc, nbf, seed=5)
+    e_s = pycc_b200.ccwfn(IntegralReference.from_ao(F_ao, chem, C, no, nfzc, stream_ao=True), model="CCSD",
+                          device="GPU", quiet=True).solve_cc(1e-11, 1e-11)
+    e_r = pycc_b200.ccwfn(IntegralReference.from_ao(F_ao, chem, C, no, nfzc, stream_ao=False), model="CCSD",
+                          device="GPU", quiet=True).solve_cc(1e-11, 1e-11)
+    assert e_s is not None and abs(float(e_s) - float(e_r)) < 1e-13
