@@ -380,10 +380,16 @@ class CCwfn(object):
 
     def _residuals_complex(self, F, t1, t2, real_time=False):
         """(r1, r2) for COMPLEX t1, t2 (and optionally a complex Hermitian F) as torch.complex128 tensors: the RT-CC
-        right-hand side (rt/rtcc.py:136-141).  Five fused real residuals, see utils.complex_from_real_samples -- a
-        complex right-hand side costs 5 real residuals where complex arithmetic would cost 4 (3 with the 3M trick)
-        real GEMMs per contraction, with the same kernels and the same sharding over ranks."""
-        from .utils import complex_from_real_samples
+        right-hand side (rt/rtcc.py:136-141), from REAL evaluations of the fused kernels (no complex kernel exists):
+
+        * everything but the ladder: five real residuals, see utils.complex_from_real_samples (six for CC3);
+        * the v^4 ladder (ccwfn.py:931) is LINEAR in tau = t2 + t1 t1, and <ab|ef> is real: its contribution is
+          L(Re tau) + i L(Im tau) -- two ladder GEMMs instead of one per sample;
+        * pair-symmetric amplitudes (t2[i,j,a,b] = t2[j,i,b,a] in both planes -- what an RT-CC propagation carries)
+          take the (i >= j) formulation of ``iterate`` in every sample (four o^3v^3 GEMMs instead of six, half the
+          ladder rows, Z in pair form), detected with one o^2v^2 pass per plane.
+        With the same rank sharding as the real residual (the two ladder pieces take one all-reduce each)."""
+        from .utils import complex_from_real_samples, real_planes, planes_to_complex
         degree = 4
         if self.model == 'CC3':
             # the CC3 triples terms are of degree 5 in (F, t1, t2) scaled together (t3 ~ Wabei(t1^3) t2, contracted with
@@ -395,14 +401,64 @@ class CCwfn(object):
                 if float(torch.diagonal(Fc).imag.abs().max()) != 0.0:
                     raise NotImplementedError("complex CC3 residuals need a Fock matrix with a real diagonal "
                                               "(the t3 denominators are not polynomial in Im f_pp)")
+        dev = self.device1
+        P = [real_planes(x, dev) for x in (F, t1, t2)]
+        (x1, y1), (x2, y2) = P[1], P[2]
+        symmetric = self.complex_pair_mode and self._pair_symmetric(x2) and (y2 is None or self._pair_symmetric(y2))
+        native_ladder = self.complex_native_ladder and self.model != 'CC2'
 
         def real_residual(Fs, t1s, t2s):
-            r1, half = self._residuals_half(Fs, t1s, t2s, real_time=real_time)
-            K.symmetrize_r2(half)
+            r1, half = self._residuals_half(Fs, t1s, t2s, symmetric=symmetric, real_time=real_time,
+                                            ladder=not native_ladder)
             return r1, half.view(t2s.shape)
 
-        r1, r2 = complex_from_real_samples(real_residual, (F, t1, t2), self.device1, degree=degree)
-        return r1, r2
+        (r1re, r1im), (hre, him) = complex_from_real_samples(real_residual, None, dev, degree=degree, as_planes=True,
+                                                             planes=P)
+        if native_ladder:
+            # Re tau = x2 + x1 x1 - y1 y1,  Im tau = y2 + x1 y1 + y1 x1 = y2 + (x1+y1)(x1+y1) - x1 x1 - y1 y1
+            tre = K.build_tau(x1, x2, 1.0, 1.0)
+            tim = None
+            if y1 is not None or y2 is not None:
+                z2 = torch.zeros_like(x2) if y2 is None else y2
+                if y1 is None:
+                    tim = z2
+                else:
+                    yy = K.build_tau(y1, x2, 0.0, 1.0)                                   # y1 y1
+                    xx = K.build_tau(x1, x2, 0.0, 1.0)                                   # x1 x1
+                    s1 = K.axpbyz(1.0, x1, 1.0, y1, torch.empty_like(x1))
+                    tim = K.build_tau(s1, z2, 1.0, 1.0)                                  # y2 + (x1+y1)(x1+y1)
+                    K.axpbyz(1.0, tim.view(-1), -1.0, xx.view(-1), tim.view(-1))
+                    K.axpbyz(1.0, tim.view(-1), -1.0, yy.view(-1), tim.view(-1))
+                    K.axpbyz(1.0, tre.view(-1), -1.0, yy.view(-1), tre.view(-1))
+                    del xx, yy
+            with K.mixed_mode(self.mixed):
+                for tau, acc in ((tre, hre), (tim, him)):
+                    if tau is None:
+                        continue
+                    piece = torch.zeros_like(tau)
+                    self._ladder(tau, piece, symmetric=symmetric)
+                    if self.part.size > 1:
+                        self.part.all_reduce_sum(piece)
+                    K.axpbyz(1.0, acc.view(-1), 1.0, piece.view(-1), acc.view(-1))
+                    del piece
+        K.symmetrize_r2(hre)
+        K.symmetrize_r2(him)
+        return planes_to_complex(r1re, r1im), planes_to_complex(hre, him)
+
+    # switches of the complex path (tests compare the settings): the (i >= j) formulation for pair-symmetric amplitudes,
+    # the ladder evaluated on the two planes of tau instead of inside every sample
+    complex_pair_mode = True
+    complex_native_ladder = True
+
+    def _pair_symmetric(self, t2, tol=1e-14):
+        """t2[i,j,a,b] == t2[j,i,b,a] to ``tol`` of its norm (one pass with the permute and dot kernels)."""
+        d = K.permuted(t2, (0, 1, 2, 3))
+        K.strided_axpby(d, t2.permute(1, 0, 3, 2), -1.0, 1.0)
+        dd = float(K.multi_dot(d.view(-1), [d.view(-1)])[0])
+        if dd == 0.0:
+            return True
+        flat = t2.contiguous().view(-1)
+        return dd <= tol * tol * float(K.multi_dot(flat, [flat])[0])
 
     def _check_F(self, F):
         if not isinstance(F, torch.Tensor):
@@ -410,15 +466,15 @@ class CCwfn(object):
         F = F.to(self.device1, dtype=F64)
         return F if F.is_contiguous() else F.contiguous()
 
-    def _residuals_half(self, F, t1, t2, symmetric=False, real_time=False):
+    def _residuals_half(self, F, t1, t2, symmetric=False, real_time=False, ladder=True):
         """r1 and the UNsymmetrised half of r2 (ccwfn.py:922-940), fused formulation.  With several ranks
         each computes its share of r2 (see parallel.py) and ONE all-reduce sums them.  precision='MP': the large
         K-major contractions inside run on the split-TF32 tcgen05 kernel (kernels.mixed_mode).
         ``symmetric``: the caller vouches that t2[i,j,a,b] = t2[j,i,b,a] (halves the ladder once more)."""
         with K.mixed_mode(self.mixed):
-            return self._residuals_half_impl(F, t1, t2, symmetric, real_time)
+            return self._residuals_half_impl(F, t1, t2, symmetric, real_time, ladder)
 
-    def _residuals_half_impl(self, F, t1, t2, symmetric=False, real_time=False):
+    def _residuals_half_impl(self, F, t1, t2, symmetric=False, real_time=False, ladder=True):
         F = self._check_F(F)
         t1 = t1.contiguous()
         t2 = t2.contiguous()
@@ -435,7 +491,7 @@ class CCwfn(object):
         if cc2:
             self._r2_half_cc2(F, t1, t2, half)
         else:
-            self._r2_half(F, t1, t2, I, half, symmetric=symmetric)
+            self._r2_half(F, t1, t2, I, half, symmetric=symmetric, ladder=ladder)
         if self.model == 'CC3':
             # connected triples (ccwfn.py:364-367): r1 += X1, r2 += X2 + X2^T -- X2 joins the unsymmetrised half, the
             # rank's partial sums (its (i,j) pairs of the triples loop) join the rank-partial buffers before the all-reduce
@@ -759,7 +815,7 @@ class CCwfn(object):
         return half
 
     # ---- r2, unsymmetrised half (ccwfn.py:922-940): this rank's share -------------------------------------
-    def _r2_half(self, F, t1, t2, I, r2=None, symmetric=False):
+    def _r2_half(self, F, t1, t2, I, r2=None, symmetric=False, ladder=True):
         H, ct = self.H, self._ct
         o, v, no, nv = self.o, self.v, self.no, self.nv
         A = I["amps"]
@@ -775,8 +831,9 @@ class CCwfn(object):
         # 1/2 tau_ijef <ab|ef>  -- the particle-particle ladder, local a rows, all (i,j)      931
         if ni > 0:
             K.strided_axpby(r2[i0:i1], oovv[i0:i1], 0.5, 0.0)                      # 1/2 <ab|ij>       922
-        with K.PHASES("ladder"):
-            self._ladder(A["tau"], r2, symmetric=symmetric, T=A.get("Tpm") if symmetric else None)
+        if ladder:                                   # (the complex path evaluates the ladder on the two planes of tau)
+            with K.PHASES("ladder"):
+                self._ladder(A["tau"], r2, symmetric=symmetric, T=A.get("Tpm") if symmetric else None)
         if ni == 0:
             return r2
         rg = r2[i0:i1]                                                             # rows i_g (contiguous)

@@ -248,7 +248,30 @@ def is_complex(x):
     return x.is_complex() if isinstance(x, torch.Tensor) else np.iscomplexobj(x)
 
 
-def complex_from_real_samples(fn, args, device, degree=4):
+def real_planes(x, device):
+    """(re, im) contiguous float64 device copies of ``x`` (tensor or array); im is None for real input."""
+    from . import kernels as K
+    if not isinstance(x, torch.Tensor):
+        x = torch.from_numpy(np.ascontiguousarray(np.asarray(x)))
+    x = x.to(device)
+    ident = tuple(range(x.dim()))
+    if x.is_complex():
+        xr = torch.view_as_real(x.to(torch.complex128))
+        return K.permuted(xr[..., 0], ident), K.permuted(xr[..., 1], ident)
+    return K.permuted(x.to(torch.float64), ident), None
+
+
+def planes_to_complex(re, im):
+    """complex128 tensor from two equally shaped float64 planes (our strided copy kernel, no torch arithmetic)."""
+    from . import kernels as K
+    z = torch.empty(tuple(re.shape), dtype=torch.complex128, device=re.device)
+    zr = torch.view_as_real(z)
+    K.strided_axpby(zr[..., 0], re, 1.0, 0.0)
+    K.strided_axpby(zr[..., 1], im, 1.0, 0.0)
+    return z
+
+
+def complex_from_real_samples(fn, args, device, degree=4, as_planes=False, planes=None):
     """Evaluate ``fn(*args) -> tuple of real tensors`` for COMPLEX ``args`` when fn is polynomial of total degree <= 4
     in its arguments (scaled together), using only real evaluations (``degree=5``: six samples, see CPLX5_*).
 
@@ -259,18 +282,9 @@ def complex_from_real_samples(fn, args, device, degree=4):
     (weights sum to 4.3 in magnitude: less than one digit of round-off amplification).  The CCSD T residual
     (quartic in t1; every Fock term carries at most two amplitudes) and the Lambda residual with HBAR rebuilt from
     (F, t1, t2) (checked numerically with the oracle: exact at degree 4) both qualify.  Each sample runs the fused
-    FP64 kernels of the energy path, so no complex kernel exists in the library.  Returns complex128 tensors."""
+    FP64 kernels of the energy path, so no complex kernel exists in the library.  Returns complex128 tensors, or with
+    ``as_planes`` a list of (re, im) float64 pairs; ``planes``: the (re, im) pairs of ``args`` if the caller has them."""
     from . import kernels as K
-
-    def planes(x):
-        if not isinstance(x, torch.Tensor):
-            x = torch.from_numpy(np.ascontiguousarray(np.asarray(x)))
-        x = x.to(device)
-        ident = tuple(range(x.dim()))
-        if x.is_complex():
-            xr = torch.view_as_real(x.to(torch.complex128))
-            return K.permuted(xr[..., 0], ident), K.permuted(xr[..., 1], ident)
-        return K.permuted(x.to(torch.float64), ident), None
 
     def at(re, im, s):
         if im is None or s == 0.0:
@@ -278,7 +292,7 @@ def complex_from_real_samples(fn, args, device, degree=4):
         return K.axpbyz(1.0, re, s, im, torch.empty_like(re))
 
     pts, w_re, w_im = CPLX_RULES[int(degree)]
-    P = [planes(a) for a in args]
+    P = [real_planes(a, device) for a in args] if planes is None else planes
     samples = []
     for s in pts:
         out = fn(*[at(re, im, s) for re, im in P])
@@ -286,13 +300,13 @@ def complex_from_real_samples(fn, args, device, degree=4):
     result = []
     for q in range(len(samples[0])):
         shape = tuple(samples[0][q].shape)
-        z = torch.empty(shape, dtype=torch.complex128, device=device)
-        zr = torch.view_as_real(z)
-        tmp = torch.empty(shape, dtype=torch.float64, device=device)
         flat = [smp[q].reshape(-1) for smp in samples]
-        K.multi_axpy(w_re, flat, tmp.view(-1))
-        K.strided_axpby(zr[..., 0], tmp, 1.0, 0.0)
-        K.multi_axpy([w for w in w_im if w != 0.0], [r for r, w in zip(flat, w_im) if w != 0.0], tmp.view(-1))
-        K.strided_axpby(zr[..., 1], tmp, 1.0, 0.0)
-        result.append(z)
+        re = torch.empty(shape, dtype=torch.float64, device=device)
+        im = torch.empty(shape, dtype=torch.float64, device=device)
+        K.multi_axpy(w_re, flat, re.view(-1))
+        K.multi_axpy([w for w in w_im if w != 0.0], [r for r, w in zip(flat, w_im) if w != 0.0], im.view(-1))
+        for smp in samples:
+            smp[q] = None                                            # release the samples of this output
+        del flat
+        result.append((re, im) if as_planes else planes_to_complex(re, im))
     return result

@@ -49,6 +49,20 @@ out = {"o": o, "v": v, "cc3_iter_s": t1 - t0, "ccsd_iter_s": t3 - t2, "intermedi
        "triples_s_est": t_trip, "triples_tflops_executed": fl / t_trip / 1e12,
        "triples_tflops_reference_formulation": o**3 * (14 * v**4 + 14 * o * v**3) / t_trip / 1e12,
        "launches_per_iter": launches, "ecc": ecc, "rms": rms, "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}
+# real-time CC3 residual with real amplitudes (explicit-field triples: one t3 build per ORDERED pair) next to the
+# field-free residual of the same amplitudes
+n = cc.no + cc.nv
+g = torch.Generator(device=dev).manual_seed(1)
+M = 0.01 * torch.randn((n, n), dtype=torch.float64, device=dev, generator=g)
+Ff = (H.F + M + M.T).contiguous()
+cc.residuals(H.F, cc.t1, cc.t2)
+tc = clock()
+cc.residuals(H.F, cc.t1, cc.t2)
+td = clock()
+cc.residuals(Ff, cc.t1, cc.t2, real_time=True)
+te = clock()
+out["residual_s"] = td - tc
+out["residual_real_time_s"] = te - td
 print(json.dumps(out))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/cc3_probe_o%dv%d.json" % (o, v), "w"), indent=1)

@@ -36,16 +36,33 @@ def timeit(fn, reps=3):
     return e0.elapsed_time(e1) / reps
 
 
-l0 = K.launch_count()
-ms_real = timeit(lambda: cc.residuals(F, t1, t2))
-l1 = K.launch_count()
-ms_cplx = timeit(lambda: cc.residuals(F, z1, z2, real_time=True))
-l2 = K.launch_count()
-fl = 2 * o**2 * v**4 + 7 * 2 * o**3 * v**3 + 2 * 2 * o**4 * v**2 + 8 * 2 * o**2 * v**3      # executed, one real residual
-out = {"o": o, "v": v, "real_residual_ms": ms_real, "complex_residual_ms": ms_cplx, "ratio": ms_cplx / ms_real,
-       "launches_real": (l1 - l0) // 4, "launches_complex": (l2 - l1) // 4,
-       "tflops_fp64_executed": 5 * fl / (ms_cplx * 1e-3) / 1e12,
-       "complex_equivalent_tflops": 4 * fl / (ms_cplx * 1e-3) / 1e12}
+REPS = 3 if o * v <= 6000 else 1
+fl = 2 * o**2 * v**4 + 7 * 2 * o**3 * v**3 + 2 * 2 * o**4 * v**2 + 8 * 2 * o**2 * v**3      # reference count, one real residual
+
+
+def sym_residual():
+    r1, half = cc._residuals_half(F, t1, t2, symmetric=True)
+    K.symmetrize_r2(half)
+
+
+ms_real = timeit(lambda: cc.residuals(F, t1, t2), REPS)                  # general mode (what residuals() runs)
+ms_sym = timeit(sym_residual, REPS)                                      # (i >= j) mode (what iterate() runs)
+out = {"o": o, "v": v, "real_residual_ms": ms_real, "real_residual_pair_mode_ms": ms_sym, "complex_ms": {},
+       "amplitudes": "pair-symmetric in both planes (MP1 doubles), Hermitian field"}
+for pair in (True, False):
+    for native in (True, False):
+        cc.complex_pair_mode, cc.complex_native_ladder = pair, native
+        l0 = K.launch_count()
+        ms = timeit(lambda: cc.residuals(F, z1, z2, real_time=True), REPS)
+        out["complex_ms"]["pair_mode=%d,native_ladder=%d" % (pair, native)] = {
+            "ms": ms, "ratio_to_real_general": ms / ms_real, "ratio_to_real_pair_mode": ms / ms_sym,
+            "launches": (K.launch_count() - l0) // (REPS + 1)}
+cc.complex_pair_mode = cc.complex_native_ladder = True
+best = out["complex_ms"]["pair_mode=1,native_ladder=1"]["ms"]
+out["complex_residual_ms"] = best
+out["ratio"] = best / ms_real
+out["round1_formulation_ms"] = out["complex_ms"]["pair_mode=0,native_ladder=0"]["ms"]
+out["complex_equivalent_tflops"] = 4 * fl / (best * 1e-3) / 1e12
 print(json.dumps(out))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/rt_probe_o%dv%d.json" % (o, v), "w"), indent=1)

@@ -480,3 +480,21 @@ def test_cube_blocked_q_layout(golden, dev):
     i, j, k = (int(x) for x in g["triples"][0])
     w3, _ = eng.t3_parts(i, j, k, False)
     assert np.abs(w3.cpu().numpy() - g["W3"][0]).max() < 1e-12
+
+
+@pytest.mark.parametrize("no,nv", [(1, 1), (1, 2), (2, 1), (5, 1), (1, 5), (3, 2)])
+def test_degenerate_shapes(dev, no, nv):
+    """one occupied / one virtual orbital (H2 in a minimal basis has o = v = 1): every tile is ragged, the pair-packed
+    ladder has a single pair, the (T) loop a single triple -- CCSD(T) and both (T) formulations against the oracle"""
+    from pycc_b200.synthetic import make_synthetic, blocks_from_factor
+    from oracle import ccsd_oracle as co, triples_oracle as to
+    syn = make_synthetic(no, nv, seed=1, fock_noise=0.01)
+    b = blocks_from_factor(syn)
+    P = co.Problem(b, syn.F, no)
+    e_ref, t1, t2, trace = co.solve_cc(P, 1e-11, 1e-11)
+    et = to.t_tjl(t1, t2, syn.F, b["ovvv"], b["ooov"], b["oovv"])
+    cc = pycc_b200.ccwfn(syn, model="CCSD(T)", device="GPU", quiet=True)
+    e = cc.solve_cc(1e-11, 1e-11)
+    assert len(cc.trace) == len(trace) and abs(float(e) - (e_ref + et)) < 1e-11
+    assert np.abs(cc.t2.cpu().numpy() - t2).max() < 1e-10
+    assert abs(float(cctriples.t_vikings(cc)) - et) < 1e-12

@@ -72,6 +72,31 @@ def test_complex_residuals_match_reference(cplx, dev, field):
     assert np.abs(r1b.cpu().numpy() - g["r1_" + field]).max() < 1e-11
 
 
+def test_pair_symmetric_complex_amplitudes(cplx, dev):
+    """Amplitudes with t2[i,j,a,b] = t2[j,i,b,a] in both planes (what an RT-CC propagation carries) take the (i >= j)
+    formulation of ``iterate`` in every sample and the ladder on the two planes of tau; every setting of the two
+    switches gives the reference's complex einsum result (oracle pinned by the goldens above)."""
+    g, r, syn = cplx
+    P = co.Problem(blocks_from_factor(syn), syn.F, syn.no)
+    t2s = 0.5 * (g["t2"] + g["t2"].transpose(1, 0, 3, 2))
+    cc = pycc_b200.ccwfn(syn, model="CCSD", device="GPU", quiet=True)
+    assert cc._pair_symmetric(T(t2s.real)) and cc._pair_symmetric(T(t2s.imag))
+    assert not cc._pair_symmetric(T(g["t2"].real))
+    for field in ("el", "mag"):
+        want1, want2 = P.residuals(g["F_" + field], g["t1"], t2s)
+        for pair in (True, False):
+            for native in (True, False):
+                cc.complex_pair_mode, cc.complex_native_ladder = pair, native
+                r1, r2 = cc.residuals(T(g["F_" + field]), T(g["t1"]), T(t2s), real_time=True)
+                assert np.abs(r1.cpu().numpy() - want1).max() < 1e-11, (field, pair, native)
+                assert np.abs(r2.cpu().numpy() - want2).max() < 1e-11, (field, pair, native)
+    # complex F with REAL amplitudes: the imaginary plane of tau is absent
+    cc.complex_pair_mode = cc.complex_native_ladder = True
+    want1, want2 = P.residuals(g["F_mag"], g["t1"].real, t2s.real)
+    r1, r2 = cc.residuals(T(g["F_mag"]), T(g["t1"].real.copy()), T(t2s.real.copy()), real_time=True)
+    assert np.abs(r1.cpu().numpy() - want1).max() < 1e-11 and np.abs(r2.cpu().numpy() - want2).max() < 1e-11
+
+
 def test_real_amplitudes_in_complex_container(cplx, dev):
     g, r, syn = cplx
     cc = pycc_b200.ccwfn(syn, model="CCSD", device="GPU", quiet=True)

@@ -238,3 +238,48 @@ def test_cc3_on_several_ranks(world):
     for rank, dw, dx, dr, drt, de, n, nref, dt in res:
         assert dw < 1e-12 and dx < 1e-12 and dr < 1e-12 and drt < 1e-12, (rank, dw, dx, dr, drt)
         assert de < 1e-11 and n == nref and dt < 1e-10, (rank, de, n, nref, dt)
+
+
+def _worker_complex(rank, world, port, tag, q):
+    """the RT-CC right-hand side on several ranks: sampled residuals with the sharded formulation, the two ladder planes
+    all-reduced separately; generic and pair-symmetric complex amplitudes against the reference's golden / the oracle"""
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import pycc_b200
+        from pycc_b200.parallel import Comm
+        from pycc_b200.synthetic import blocks_from_factor
+        from oracle import ccsd_oracle as co
+        from tests import emu
+        from tests.test_complex import load
+        g, r, syn = load(os.path.join(ROOT, "tests", "golden", "cplx_%s.npz" % tag))
+        P = co.Problem(blocks_from_factor(syn), syn.F, syn.no)
+        T = lambda x: torch.from_numpy(np.array(x, order="C", copy=True))
+        with emu.install():
+            cc = pycc_b200.ccwfn(syn, model="CCSD", device="GPU", quiet=True, comm=Comm())
+            r1, r2 = cc.residuals(T(g["F_mag"]), T(g["t1"]), T(g["t2"]), real_time=True)
+            d_gen = max(float(np.abs(r1.numpy() - g["r1_mag"]).max()), float(np.abs(r2.numpy() - g["r2_mag"]).max()))
+            t2s = 0.5 * (g["t2"] + g["t2"].transpose(1, 0, 3, 2))
+            w1, w2 = P.residuals(g["F_mag"], g["t1"], t2s)
+            r1, r2 = cc.residuals(T(g["F_mag"]), T(g["t1"]), T(t2s), real_time=True)
+            d_sym = max(float(np.abs(r1.numpy() - w1).max()), float(np.abs(r2.numpy() - w2).max()))
+            q.put((rank, d_gen, d_sym))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_complex_residual_on_two_ranks():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 500) + 55
+    procs = [ctx.Process(target=_worker_complex, args=(r, 2, port, "o4v10_s1_noise", q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, d_gen, d_sym in res:
+        assert d_gen < 1e-11 and d_sym < 1e-11, (rank, d_gen, d_sym)
