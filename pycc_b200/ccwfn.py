@@ -406,14 +406,22 @@ class CCwfn(object):
         (x1, y1), (x2, y2) = P[1], P[2]
         symmetric = self.complex_pair_mode and self._pair_symmetric(x2) and (y2 is None or self._pair_symmetric(y2))
         native_ladder = self.complex_native_ladder and self.model != 'CC2'
+        # every o^3v^3 product on the planes as well: single rank, both amplitude planes present, t1 in play
+        native_heavy = (native_ladder and self.complex_native_heavy and self.part.size == 1 and y1 is not None
+                        and y2 is not None and self.model in ('CCSD', 'CCSD(T)', 'CC3'))
+        lin = []
 
         def real_residual(Fs, t1s, t2s):
             r1, half = self._residuals_half(Fs, t1s, t2s, symmetric=symmetric, real_time=real_time,
-                                            ladder=not native_ladder)
+                                            ladder=not native_ladder, heavy=not native_heavy)
+            if native_heavy:
+                I = self._last_I
+                self._last_I = None
+                return r1, half.view(t2s.shape), I["W1"], I["W2"]
             return r1, half.view(t2s.shape)
 
-        (r1re, r1im), (hre, him) = complex_from_real_samples(real_residual, None, dev, degree=degree, as_planes=True,
-                                                             planes=P)
+        out = complex_from_real_samples(real_residual, None, dev, degree=degree, as_planes=True, planes=P)
+        (r1re, r1im), (hre, him) = out[0], out[1]
         if native_ladder:
             # Re tau = x2 + x1 x1 - y1 y1,  Im tau = y2 + x1 y1 + y1 x1 = y2 + (x1+y1)(x1+y1) - x1 x1 - y1 y1
             tre = K.build_tau(x1, x2, 1.0, 1.0)
@@ -441,14 +449,104 @@ class CCwfn(object):
                         self.part.all_reduce_sum(piece)
                     K.axpbyz(1.0, acc.view(-1), 1.0, piece.view(-1), acc.view(-1))
                     del piece
+                if native_heavy:
+                    self._complex_heavy((x1, y1), (x2, y2), (tre, tim), out[2], out[3], (hre, him), symmetric)
         K.symmetrize_r2(hre)
         K.symmetrize_r2(him)
         return planes_to_complex(r1re, r1im), planes_to_complex(hre, him)
+
+    def _complex_heavy(self, t1p, t2p, taup, W1lin, W2lin, half, symmetric):
+        """The o^3v^3 products of the residual for complex amplitudes, on planes (single rank; see _residuals_complex):
+
+        * W_mbej / W_mbje (ccwfn.py:641-645, 680-683): their linear parts (integrals + t1 terms) arrive as planes
+          ``W1lin``, ``W2lin`` (interpolated from the samples: they are linear in t1); the products of t2 / tau(1/2,1)
+          with the REAL blocks <mn|ef>, L_mnef are plane-wise -- two GEMMs each instead of one per sample;
+        * the ring terms (933-935) are complex x complex: the 3M form (three real GEMMs per product);
+        * Z_mbij = <mb|ef> tau_ijef (715) plane-wise, then - t_ma Z_mbij (932) as four small batched products.
+        Pair-symmetric amplitudes use the {D = W1 + W2/2, W2} form of ``_r2_half`` (two ring products instead of three)
+        and Z in pair form."""
+        H, ct = self.H, self._ct
+        no, nv = self.no, self.nv
+        oovv_menf, oovv_mfne, L_menf = H.derived("oovv_menf"), H.derived("oovv_mfne"), H.derived("Loovv_menf")
+        fused = bool(symmetric) and self.fuse_rings
+
+        def add(a, x, b, y):                                       # a x + b y on equally shaped contiguous tensors
+            return K.axpbyz(a, x.view(-1), b, y.view(-1), torch.empty_like(x).view(-1)).view(x.shape)
+
+        def cprod(sub, Xp, Yp):
+            """(X_re + i X_im)(Y_re + i Y_im) contracted as ``sub``: the 3M form, three real GEMMs"""
+            p1 = ct(sub, Xp[0], Yp[0])
+            p2 = ct(sub, Xp[1], Yp[1])
+            p3 = ct(sub, add(1.0, Xp[0], 1.0, Xp[1]), add(1.0, Yp[0], 1.0, Yp[1]))
+            K.axpbyz(1.0, p3.view(-1), -1.0, p1.view(-1), p3.view(-1))
+            K.axpbyz(1.0, p3.view(-1), -1.0, p2.view(-1), p3.view(-1))            # Im = P3 - P1 - P2
+            K.axpbyz(1.0, p1.view(-1), -1.0, p2.view(-1), p1.view(-1))            # Re = P1 - P2
+            return p1, p3
+
+        # ---- W1 / W2 (or D / W2) on planes: quadratic parts from tau(1/2,1) = tau - t2/2 and t2 ------------------
+        W1, W2, lay = [], [], []
+        for p in range(2):
+            taut = add(1.0, taup[p], -0.5, t2p[p])                                 # tau(1/2, 1) = t2/2 + t1 t1
+            taut_jbnf = K.permuted(taut, (0, 3, 1, 2))                             # [j,b,n,f] = tau(1/2,1)[j,n,f,b]
+            del taut
+            t2_jbnf = K.permuted(t2p[p], (1, 3, 0, 2))                             # [j,b,n,f] = t2[n,j,f,b]
+            A, B = W1lin[p], W2lin[p]
+            if fused:
+                K.strided_axpby(A, B, 0.5, 1.0)                                    # lin(W1) + 1/2 lin(W2)
+                ct("jbnf,menf->jbme", taut_jbnf, oovv_mfne, out=B, alpha=1.0, beta=1.0)
+                K.strided_axpby(t2_jbnf, taut_jbnf, -1.0, 1.0)
+                ct("jbnf,menf->jbme", t2_jbnf, L_menf, out=A, alpha=0.5, beta=1.0)      # D
+            else:
+                ct("jbnf,menf->jbme", taut_jbnf, oovv_menf, out=A, alpha=-1.0, beta=1.0)
+                ct("jbnf,menf->jbme", t2_jbnf, L_menf, out=A, alpha=0.5, beta=1.0)
+                ct("jbnf,menf->jbme", taut_jbnf, oovv_mfne, out=B, alpha=1.0, beta=1.0)
+            del taut_jbnf, t2_jbnf
+            W1.append(A)
+            W2.append(B)
+            if fused:
+                lay.append(K.ring_layouts(t2p[p]))                                 # (s_iame, t2_jame)
+            else:
+                s = K.permuted(t2p[p], (0, 2, 1, 3), 2.0)
+                K.strided_axpby(s, t2p[p].permute(0, 3, 1, 2), -1.0, 1.0)
+                lay.append((s, K.permuted(t2p[p], (1, 2, 0, 3)), K.permuted(t2p[p], (0, 2, 1, 3))))
+        # ---- ring terms (see _r2_half for the two forms) -----------------------------------------------------------
+        s_iame = (lay[0][0], lay[1][0])
+        t2_jame = (lay[0][1], lay[1][1])
+        if fused:
+            R = cprod("iame,jbme->iajb", s_iame, W1)                               # u . D
+            X = cprod("jame,ibme->jaib", t2_jame, W2)
+            for p in range(2):
+                K.strided_axpby(R[p], X[p], 0.5, 1.0)
+                K.strided_axpby(half[p], R[p].permute(0, 2, 1, 3), 1.0, 1.0)
+                K.strided_axpby(half[p], X[p].permute(2, 0, 1, 3), 1.0, 1.0)
+        else:
+            t2_iame = (lay[0][2], lay[1][2])
+            R = cprod("iame,jbme->iajb", s_iame, W1)
+            R2 = cprod("iame,jbme->iajb", t2_iame, W2)
+            X = cprod("jame,ibme->jaib", t2_jame, W2)
+            for p in range(2):
+                K.strided_axpby(R[p], R2[p], 1.0, 1.0)
+                K.strided_axpby(half[p], R[p].permute(0, 2, 1, 3), 1.0, 1.0)
+                K.strided_axpby(half[p], X[p].permute(2, 0, 1, 3), 1.0, 1.0)
+            del R2
+        del R, X, W1, W2, lay, s_iame, t2_jame
+        # ---- Z and - t_ma Z_mbij -----------------------------------------------------------------------------------
+        Z = []
+        for p in range(2):
+            A = {"tau": taup[p]}
+            if symmetric and self.pair_z:
+                A["Tpm"] = K.pack_tau(taup[p], True)
+            Z.append(self._zgemm(A, 0, no))                                        # [i, j, m, b]
+        for (zp, tp, hp, alpha) in ((0, 0, 0, -1.0), (1, 1, 0, 1.0), (1, 0, 1, -1.0), (0, 1, 1, -1.0)):
+            # half[hp][i,j,a,b] += alpha sum_m t1[tp][m,a] Z[zp][i,j,m,b]
+            K.dgemm(nv, nv, no, t1p[tp], nv, 1, Z[zp], nv, 1, half[hp], nv, alpha, 1.0,
+                    batch=no * no, sA=0, sB=no * nv, sC=nv * nv)
 
     # switches of the complex path (tests compare the settings): the (i >= j) formulation for pair-symmetric amplitudes,
     # the ladder evaluated on the two planes of tau instead of inside every sample
     complex_pair_mode = True
     complex_native_ladder = True
+    complex_native_heavy = True
 
     def _pair_symmetric(self, t2, tol=1e-14):
         """t2[i,j,a,b] == t2[j,i,b,a] to ``tol`` of its norm (one pass with the permute and dot kernels)."""
@@ -466,21 +564,22 @@ class CCwfn(object):
         F = F.to(self.device1, dtype=F64)
         return F if F.is_contiguous() else F.contiguous()
 
-    def _residuals_half(self, F, t1, t2, symmetric=False, real_time=False, ladder=True):
+    def _residuals_half(self, F, t1, t2, symmetric=False, real_time=False, ladder=True, heavy=True):
         """r1 and the UNsymmetrised half of r2 (ccwfn.py:922-940), fused formulation.  With several ranks
         each computes its share of r2 (see parallel.py) and ONE all-reduce sums them.  precision='MP': the large
         K-major contractions inside run on the split-TF32 tcgen05 kernel (kernels.mixed_mode).
         ``symmetric``: the caller vouches that t2[i,j,a,b] = t2[j,i,b,a] (halves the ladder once more)."""
         with K.mixed_mode(self.mixed):
-            return self._residuals_half_impl(F, t1, t2, symmetric, real_time, ladder)
+            return self._residuals_half_impl(F, t1, t2, symmetric, real_time, ladder, heavy)
 
-    def _residuals_half_impl(self, F, t1, t2, symmetric=False, real_time=False, ladder=True):
+    def _residuals_half_impl(self, F, t1, t2, symmetric=False, real_time=False, ladder=True, heavy=True):
         F = self._check_F(F)
         t1 = t1.contiguous()
         t2 = t2.contiguous()
         cc2 = self.model == 'CC2'
         with K.PHASES("intermediates"):
-            I = self._intermediates(F, t1, t2, rings=not cc2, symmetric=symmetric)
+            I = self._intermediates(F, t1, t2, rings=not cc2, symmetric=symmetric, heavy=heavy)
+        self._last_I = I if not heavy else None
         # one flat buffer [ r2 half | rank-partial part of r1 ] so that ONE all-reduce carries both
         n2, n1 = t2.numel(), t1.numel()
         buf = torch.empty(n2 + n1, dtype=F64, device=self.device1)
@@ -491,7 +590,7 @@ class CCwfn(object):
         if cc2:
             self._r2_half_cc2(F, t1, t2, half)
         else:
-            self._r2_half(F, t1, t2, I, half, symmetric=symmetric, ladder=ladder)
+            self._r2_half(F, t1, t2, I, half, symmetric=symmetric, ladder=ladder, rings=heavy)
         if self.model == 'CC3':
             # connected triples (ccwfn.py:364-367): r1 += X1, r2 += X2 + X2^T -- X2 joins the unsymmetrised half, the
             # rank's partial sums (its (i,j) pairs of the triples loop) join the rank-partial buffers before the all-reduce
@@ -527,9 +626,12 @@ class CCwfn(object):
         A["s_iame"] = s
         return A
 
-    def _intermediates(self, F, t1, t2, full=False, rings=True, symmetric=False):
+    def _intermediates(self, F, t1, t2, full=False, rings=True, symmetric=False, heavy=True):
         """Fae, Fmi, Fme (replicated) and the LOCAL slices of Wmnij (rows i_g), W1/W2 (columns j_g) and
-        Z' (rows i_g).  ``full=True`` ignores the rank partition (public build_* methods)."""
+        Z' (rows i_g).  ``full=True`` ignores the rank partition (public build_* methods).  ``heavy=False`` (the complex
+        path, _residuals_complex): the o^3v^3 GEMMs are left out -- W1 / W2 come back with their linear parts only
+        (integral + t1 terms, I["W1"], I["W2"], unmixed) and Z' as zeros; the caller evaluates those products on the
+        real and imaginary planes itself."""
         H, ct = self.H, self._ct
         o, v, no, nv = self.o, self.v, self.no, self.nv
         i0, i1 = (0, no) if full else self.part.occ_range(no)
@@ -619,13 +721,14 @@ class CCwfn(object):
         # (the two quadratic terms of W1 and half the one of W2 combine, L = 2<mn|ef> - <mn|fe>): TWO o^3v^3 GEMMs build
         # {D, W2} where {W1, W2} take three.  The linear parts must be complete before they are mixed, so the GEMMs come
         # after the t1 terms on this branch.
-        fused = bool(symmetric) and self.fuse_rings and not full
+        fused = bool(symmetric) and self.fuse_rings and not full and heavy
         W1 = K.permuted(oovv_menf[:, :, i0:i1, :], (2, 3, 0, 1))  # <mb|ej> = <mj|eb> -> [j,b,m,e]
         W2 = K.permuted(H.derived("ovov_mejb")[:, :, i0:i1, :], (2, 3, 0, 1), -1.0)
-        if not fused:
+        if not fused and heavy:
             ct("jbnf,menf->jbme", taut_jbnf, oovv_menf, out=W1, alpha=-1.0, beta=1.0)
             ct("jbnf,menf->jbme", t2_jbnf, H.derived("Loovv_menf"), out=W1, alpha=0.5, beta=1.0)
             ct("jbnf,menf->jbme", taut_jbnf, H.derived("oovv_mfne"), out=W2, alpha=1.0, beta=1.0)
+        if not fused:
             del t2_jbnf, taut_jbnf
         K.PHASES.mark("  W1, W2: t1 terms (from P1, P2)")
         if not ccd:
@@ -672,9 +775,21 @@ class CCwfn(object):
         # and the contraction with t_ma below gives a partial sum over m_g for every r2 row -- the all-reduce of r2 adds
         # the partial sums.  (Sharded over i, every rank streamed the whole block.)
         K.PHASES.mark("  Z = tau.<mb|ef> (o3v3)")
-        if not ccd and "Tpm" in A and self.pair_z:
-            # pair-symmetric tau: Z in pair form like the ladder -- S = T+ X+^T, A = T- X-^T over the rows (i >= j) with
-            # X+-[(m,b),Q] = <mb|ef> +- <mb|fe> packed once per Hamiltonian; Z[i,j] = S + A, Z[j,i] = S - A: half the flops
+        if not ccd and not heavy:
+            I["Zijmb"] = torch.zeros((no, no, ni, nv), dtype=F64, device=self.device1)
+        elif not ccd:
+            I["Zijmb"] = self._zgemm(A, i0, i1)
+        K.PHASES.mark(None)
+        return I
+
+    def _zgemm(self, A, i0, i1):
+        """Z'[i,j,m_g,b] = Zmbij[m,b,i,j] = <mb|ef> tau_ijef (ccwfn.py:715) for the slabs m in [i0,i1); ``A``: the dict of
+        _amps (tau, and T+- when tau is pair-symmetric: Z in pair form like the ladder -- S = T+ X+^T, A = T- X-^T over
+        the rows (i >= j) with X+-[(m,b),Q] = <mb|ef> +- <mb|fe> packed once per Hamiltonian; Z[i,j] = S + A,
+        Z[j,i] = S - A: half the flops)."""
+        no, nv = self.no, self.nv
+        ni = i1 - i0
+        if "Tpm" in A and self.pair_z:
             T = A["Tpm"]
             M, ldq = T.shape[1], T.shape[2]
             X = self._ovvv_packed(i0, i1)
@@ -684,12 +799,8 @@ class CCwfn(object):
             K.dgemm(M, ncols, K.pair_count(nv), T, ldq, 0, X, ldq, 0, SA, lds, 1.0, 0.0,
                     batch=2, sA=M * ldq, sB=ncols * ldq, sC=M * lds)
             Z = torch.empty((no, no, ni, nv), dtype=F64, device=self.device1)
-            I["Zijmb"] = K.pair_rows_unpack(SA[0], SA[1], lds, no, ncols, Z, ncols)
-            del SA
-        elif not ccd:
-            I["Zijmb"] = ct("ijef,mbef->ijmb", A["tau"], H.block("ovvv")[i0:i1])
-        K.PHASES.mark(None)
-        return I
+            return K.pair_rows_unpack(SA[0], SA[1], lds, no, ncols, Z, ncols)
+        return self._ct("ijef,mbef->ijmb", A["tau"], self.H.block("ovvv")[i0:i1])
 
     # Z_mbij in pair form when tau is pair-symmetric (solve_cc's iterations); False = always the dense o^3v^3 product
     pair_z = os.environ.get("B200CC_PAIR_Z", "1") != "0"
@@ -815,7 +926,7 @@ class CCwfn(object):
         return half
 
     # ---- r2, unsymmetrised half (ccwfn.py:922-940): this rank's share -------------------------------------
-    def _r2_half(self, F, t1, t2, I, r2=None, symmetric=False, ladder=True):
+    def _r2_half(self, F, t1, t2, I, r2=None, symmetric=False, ladder=True, rings=True):
         H, ct = self.H, self._ct
         o, v, no, nv = self.o, self.v, self.no, self.nv
         A = I["amps"]
@@ -856,8 +967,12 @@ class CCwfn(object):
         ct("mnij,mnab->ijab", I["Wmnij"], A["tau"], out=rg, alpha=0.5, beta=1.0)
         # ring terms, columns j_g, in [i,a,j,b] layout                              933-935
         K.PHASES.mark("r2: ring terms (three o3v3 GEMMs)")
-        t2_jame = A["t2_jame"] if "t2_jame" in A else K.permuted(t2, (1, 2, 0, 3))      # [j,a,m,e] = t2[m,j,a,e]
-        if "D" in I:
+        t2_jame = None
+        if rings:
+            t2_jame = A["t2_jame"] if "t2_jame" in A else K.permuted(t2, (1, 2, 0, 3))  # [j,a,m,e] = t2[m,j,a,e]
+        if not rings:
+            R = None                             # (the complex path evaluates the ring products on the planes)
+        elif "D" in I:
             # pair-symmetric t2: with u = 2t2 - t2^T and t2 = (u + t2^T)/2, lines 933-935 are
             #   u.(W1 + 1/2 W2) + 1/2 X[i,a,j,b] + X[j,a,i,b],   X[x,a,y,b] = sum_me t2[m,x,a,e] W_mbye
             # (t2[i,m,e,a] = t2[m,i,a,e]): TWO o^3v^3 GEMMs instead of three -- the closed-shell (1/2 + P_ij) form

@@ -67,6 +67,11 @@ def test_complex_residuals_match_reference(cplx, dev, field):
     assert r1.is_complex() and r2.is_complex()
     assert np.abs(r1.cpu().numpy() - g["r1_" + field]).max() < 1e-11
     assert np.abs(r2.cpu().numpy() - g["r2_" + field]).max() < 1e-11
+    # the plane-wise evaluation of the heavy products switched off (samples only) gives the same
+    cc.complex_native_heavy = False
+    r1c, r2c = cc.residuals(T(g["F_" + field]), T(g["t1"]), T(g["t2"]), real_time=True)
+    assert np.abs(r2c.cpu().numpy() - g["r2_" + field]).max() < 1e-11
+    cc.complex_native_heavy = True
     # numpy inputs (as rtcc hands them over on the reference's CPU path) are accepted too
     r1b, _ = cc.residuals(g["F_" + field], T(g["t1"]), T(g["t2"]))
     assert np.abs(r1b.cpu().numpy() - g["r1_" + field]).max() < 1e-11
@@ -74,8 +79,8 @@ def test_complex_residuals_match_reference(cplx, dev, field):
 
 def test_pair_symmetric_complex_amplitudes(cplx, dev):
     """Amplitudes with t2[i,j,a,b] = t2[j,i,b,a] in both planes (what an RT-CC propagation carries) take the (i >= j)
-    formulation of ``iterate`` in every sample and the ladder on the two planes of tau; every setting of the two
-    switches gives the reference's complex einsum result (oracle pinned by the goldens above)."""
+    formulation of ``iterate`` in every sample, the ladder and the o^3v^3 products on the two planes (3M for the ring
+    terms); every setting of the switches gives the reference's complex einsum result (oracle pinned by the goldens)."""
     g, r, syn = cplx
     P = co.Problem(blocks_from_factor(syn), syn.F, syn.no)
     t2s = 0.5 * (g["t2"] + g["t2"].transpose(1, 0, 3, 2))
@@ -85,13 +90,13 @@ def test_pair_symmetric_complex_amplitudes(cplx, dev):
     for field in ("el", "mag"):
         want1, want2 = P.residuals(g["F_" + field], g["t1"], t2s)
         for pair in (True, False):
-            for native in (True, False):
-                cc.complex_pair_mode, cc.complex_native_ladder = pair, native
+            for native, heavy in ((True, True), (True, False), (False, False)):
+                cc.complex_pair_mode, cc.complex_native_ladder, cc.complex_native_heavy = pair, native, heavy
                 r1, r2 = cc.residuals(T(g["F_" + field]), T(g["t1"]), T(t2s), real_time=True)
-                assert np.abs(r1.cpu().numpy() - want1).max() < 1e-11, (field, pair, native)
-                assert np.abs(r2.cpu().numpy() - want2).max() < 1e-11, (field, pair, native)
+                assert np.abs(r1.cpu().numpy() - want1).max() < 1e-11, (field, pair, native, heavy)
+                assert np.abs(r2.cpu().numpy() - want2).max() < 1e-11, (field, pair, native, heavy)
     # complex F with REAL amplitudes: the imaginary plane of tau is absent
-    cc.complex_pair_mode = cc.complex_native_ladder = True
+    cc.complex_pair_mode = cc.complex_native_ladder = cc.complex_native_heavy = True
     want1, want2 = P.residuals(g["F_mag"], g["t1"].real, t2s.real)
     r1, r2 = cc.residuals(T(g["F_mag"]), T(g["t1"].real.copy()), T(t2s.real.copy()), real_time=True)
     assert np.abs(r1.cpu().numpy() - want1).max() < 1e-11 and np.abs(r2.cpu().numpy() - want2).max() < 1e-11
