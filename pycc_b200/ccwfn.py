@@ -711,10 +711,12 @@ class CCwfn(object):
         #   W1[j,b,m,e] = Wmbej[m,b,e,j]    (ccwfn.py:641-645)
         #   W2[j,b,m,e] = Wmbje[m,b,j,e]    (ccwfn.py:680-683)
         K.PHASES.mark("  W1, W2: three o3v3 GEMMs + layouts")
-        taut = K.build_tau(t1, t2, 0.5, 0.0 if ccd else 1.0)
-        taut_jbnf = K.permuted(taut[i0:i1], (0, 3, 1, 2))         # [j,b,n,f] = tau(1/2,1)[j,n,f,b]
-        del taut
-        t2_jbnf = K.permuted(t2[:, i0:i1], (1, 3, 0, 2))          # [j,b,n,f] = t2[n,j,f,b]
+        taut_jbnf = t2_jbnf = None
+        if heavy:
+            taut = K.build_tau(t1, t2, 0.5, 0.0 if ccd else 1.0)
+            taut_jbnf = K.permuted(taut[i0:i1], (0, 3, 1, 2))     # [j,b,n,f] = tau(1/2,1)[j,n,f,b]
+            del taut
+            t2_jbnf = K.permuted(t2[:, i0:i1], (1, 3, 0, 2))      # [j,b,n,f] = t2[n,j,f,b]
         oovv_menf = H.derived("oovv_menf")
         # Pair-symmetric amplitudes (solve_cc): the residual only needs D = W1 + 1/2 W2 and W2 (see _r2_half), and
         #   D = lin(W1) + 1/2 lin(W2) + 1/2 sum_nf (t2[n,j,f,b] - tau(1/2,1)[j,n,f,b]) L_mnef
