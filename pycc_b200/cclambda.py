@@ -118,8 +118,13 @@ class cclambda(object):
             else:
                 t1 = t1.contiguous()
                 vovv = w.H.ERI[v, o, v, v]
-                ct("ijem,emab->ijab", ct("ijef,mf->ijem", l2, t1), vovv, out=half, alpha=-0.5, beta=1.0)
-                ct("ijfm,fmba->ijab", ct("ijef,me->ijfm", l2, t1), vovv, out=half, alpha=-0.5, beta=1.0)
+                if symmetric:
+                    # l2[i,j,e,f] = l2[j,i,f,e]: the second product is the first with (i,a) <-> (j,b) exchanged, and the
+                    # caller adds half^T to half -- ONE o^3v^3 GEMM with twice the weight gives the same symmetrised sum
+                    ct("ijem,emab->ijab", ct("ijef,mf->ijem", l2, t1), vovv, out=half, alpha=-1.0, beta=1.0)
+                else:
+                    ct("ijem,emab->ijab", ct("ijef,mf->ijem", l2, t1), vovv, out=half, alpha=-0.5, beta=1.0)
+                    ct("ijfm,fmba->ijab", ct("ijef,me->ijfm", l2, t1), vovv, out=half, alpha=-0.5, beta=1.0)
                 tau = K.build_tau(t1, t2.contiguous(), 1.0, 1.0)
             ct("ijmn,mnab->ijab", ct("ijef,mnef->ijmn", l2, tau), oovv, out=half, alpha=0.5, beta=1.0)
         return half
