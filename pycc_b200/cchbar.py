@@ -170,7 +170,9 @@ class cchbar(object):
         with K.mixed_mode(getattr(w, "mixed", False), cache=False):
             for alpha, sub, a, b in todo:
                 if sharded and "E:vvvv" in (a, b):
-                    self._vvvv_term_sharded(out, alpha, sub, a, b, env)
+                    if sub != "if,abef->abei" or b != "E:vvvv":
+                        raise NotImplementedError("sharded <ab|ef> in HBAR term %r" % sub)
+                    self._vvvv_term_sharded(out, alpha, sub, self._operand(env, a))
                     continue
                 if "E:vvvv" in (a, b) and w._vvvv_released():
                     # precision='MP' / 'SP': only the TF32 planes of <ab|ef> are resident
@@ -183,26 +185,84 @@ class cchbar(object):
         env[key] = out
         return out
 
-    def _vvvv_term_sharded(self, out, alpha, sub, a, b, env):
+    def _vvvv_term_sharded(self, out, alpha, sub, t1):
         """A term whose integral operand is <ab|ef> when that block is sharded over the ranks (parallel.py): each rank
         contracts the pairs (a >= b) it holds -- giving the (a,b) and (b,a) elements -- the pieces are summed with one
         all-reduce and added to the (replicated) block.  Only 't_if <ab|ef> -> abei' (Hvvvo) occurs."""
         w = self.ccwfn
-        if sub != "if,abef->abei" or b != "E:vvvv":
-            raise NotImplementedError("sharded <ab|ef> in HBAR term %r" % sub)
         a_lo, a_hi = w.part.a_range(w.nv)
         r_lo, r_hi = w.H.a_range
         if (r_lo, r_hi) != (a_lo, a_hi) and (r_lo, r_hi) != (0, w.nv):
             raise NotImplementedError("<ab|ef> rows resident on this rank are neither its share nor the whole block")
         piece = torch.zeros_like(out)
         if (r_lo, r_hi) == (a_lo, a_hi):
-            w._t1_vvvv(self._operand(env, a), piece, alpha)                  # this rank's pairs, from the packed form
+            w._t1_vvvv(t1, piece, alpha)                                     # this rank's pairs, from the packed form
             w.part.all_reduce_sum(piece)
         elif w.H.has("vvvv"):                                                # every rank holds the whole FP64 block
-            w._ct(sub, self._operand(env, a), w.H.block("vvvv"), out=piece, alpha=alpha, beta=0.0)
+            w._ct(sub, t1, w.H.block("vvvv"), out=piece, alpha=alpha, beta=0.0)
         else:
-            w._t1_vvvv(self._operand(env, a), piece, alpha)                  # whole packed form on every rank
+            w._t1_vvvv(t1, piece, alpha)                                     # whole packed form on every rank
         K.strided_axpby(out, piece, 1.0, 1.0)
+
+    # ---- the same tables for COMPLEX (F, t1, t2) carried as pairs of real planes (planes.py) -------------------------
+    def _operand_p(self, env, name):
+        from .planes import Planes, cprod, cterm, copy_real
+        if name in env:
+            return env[name]
+        ct = self.ccwfn._ct
+        if name.startswith("I:"):
+            alpha, sub, a, b = _INTER[name]
+            return cprod(ct, alpha, sub, self._operand_p(env, a), self._operand_p(env, b))
+        if name.startswith("X:"):
+            init, terms = _DRESSED[name]
+            x = copy_real(_view(self.ccwfn.H, init))
+            for alpha, sub, a, b in terms:
+                cterm(ct, alpha, sub, self._operand_p(env, a), self._operand_p(env, b), x)
+            return x
+        return _view(self.ccwfn.H, name)                          # a real integral block
+
+    def _build_p(self, key, env):
+        from .planes import Planes, cterm, copy_real, copy_planes
+        init, terms, singles = _TABLE[key]
+        w = self.ccwfn
+        if init.startswith("F:"):
+            sl = {"o": self.o, "v": self.v}
+            out = copy_planes(env["F"].view(lambda x: x[sl[init[2]], sl[init[3]]]))
+        else:
+            out = copy_real(_view(w.H, init))
+        todo = list(terms) + ([] if w.model == "CCD" else list(singles))
+        sharded = w.part.size > 1
+        with K.mixed_mode(getattr(w, "mixed", False), cache=False):
+            for alpha, sub, a, b in todo:
+                if "E:vvvv" in (a, b):
+                    # t_if <ab|ef> is linear in t1 and <ab|ef> is real: once per plane, through whichever form of the
+                    # block this rank holds (sharded pairs + all-reduce, TF32 planes / packed form, or the full block)
+                    if sub != "if,abef->abei" or b != "E:vvvv":
+                        raise NotImplementedError("HBAR term %r with complex amplitudes" % sub)
+                    t1p = self._operand_p(env, a)
+                    for src, dst in ((t1p.re, out.re), (t1p.im, out.im)):
+                        if src is None:
+                            continue
+                        if sharded:
+                            self._vvvv_term_sharded(dst, alpha, sub, src)
+                        elif w._vvvv_released():
+                            w._t1_vvvv(src, dst, alpha)
+                        else:
+                            w._ct(sub, src, w.H.block("vvvv"), out=dst, alpha=alpha, beta=1.0)
+                    continue
+                cterm(w._ct, alpha, sub, self._operand_p(env, a), self._operand_p(env, b), out)
+        env[key] = out
+        return out
+
+    def build_all_planes(self, F, t1, t2):
+        """The eager blocks for complex (F, t1, t2) given as ``planes.Planes``: every "amplitude x integral" term runs
+        once per plane on the real kernels (two products where five real samples of the whole build take five), the
+        few amplitude x amplitude-dependent terms (all o^2v^3 or smaller) take four.  Returns a dict of Planes."""
+        from .planes import Planes, complex_tau
+        w = self.ccwfn
+        env = {"t1": t1, "t2": t2, "F": F, "Fov": F.view(lambda x: x[self.o, self.v])}
+        env["tau"] = t2 if w.model == "CCD" else complex_tau(t1, t2)
+        return {k: self._build_p(k, env) for k in EAGER}
 
     def build_all(self, F, t1, t2, with_vvvv=False):
         """Every block in dependency order (Hvvvo needs Hov, Hovoo needs Hov and Hoooo); H_abef only on request."""

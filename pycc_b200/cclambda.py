@@ -162,10 +162,14 @@ class cclambda(object):
 
     def residuals(self, F, t1, t2, l1, l2):
         """(r1, r2) with HBAR rebuilt from (F, t1, t2)                                      cclambda.py:202-256
-        Complex amplitudes / a complex Hermitian F (the Lambda half of rtcc.f, rt/rtcc.py:143-147) are evaluated from
-        five real samples (utils.complex_from_real_samples; the residual is exactly quartic in the joint scaling)."""
+        Complex amplitudes / a complex Hermitian F (the Lambda half of rtcc.f, rt/rtcc.py:143-147): HBAR and the residual
+        are carried as pairs of real planes through the same term tables (planes.py, ``_residuals_planes``);
+        ``complex_on_planes = False`` selects the round-1 evaluation from five real samples of the whole residual
+        (utils.complex_from_real_samples; the residual is exactly quartic in the joint scaling)."""
         from .utils import complex_from_real_samples, is_complex
         if any(is_complex(x) for x in (F, t1, t2, l1, l2)):
+            if self.complex_on_planes:
+                return self._residuals_planes(F, t1, t2, l1, l2)
             return tuple(complex_from_real_samples(self.residuals, (F, t1, t2, l1, l2), self.l2.device))
         hb = self.hbar.build_all(F, t1, t2)
         Goo, Gvv = self.build_Goo(t2, l2), self.build_Gvv(t2, l2)
@@ -176,6 +180,68 @@ class cclambda(object):
         half = self._r_L2_half(l1, l2, hb["Hov"], hb["Hvv"], hb["Hoo"], hb["Hoooo"], None, hb["Hovvo"],
                                hb["Hovov"], hb["Hvovv"], hb["Hooov"], Gvv, Goo, W, t1=t1, t2=t2)
         return r1, K.symmetrize_r2(half)
+
+    complex_on_planes = True
+
+    def _residuals_planes(self, F, t1, t2, l1, l2):
+        """cclambda.py:202-256 for complex arguments on pairs of real planes.  Cost in real GEMMs: every amplitude x
+        integral product of HBAR (incl. the three o^2v^4 terms of H_abei) and the lambda2 ladder twice (once per plane),
+        the three o^3v^3 products lambda2 x {W, H_ovov, H_ovvo} three times (3M), everything smaller four times --
+        against five evaluations of everything when the residual is sampled."""
+        from .planes import Planes, cterm, cprod, copy_real, copy_planes
+        from .utils import real_planes, planes_to_complex
+        w, ct = self.ccwfn, self.ccwfn._ct
+        dev = self.l2.device
+        Fp, t1p, t2p, l1p, l2p = (Planes(*real_planes(x, dev)) for x in (F, t1, t2, l1, l2))
+        hb = self.hbar.build_all_planes(Fp, t1p, t2p)
+        Goo = cprod(ct, 1.0, "mjab,ijab->mi", t2p, l2p)                                     # cclambda.py:281
+        Gvv = cprod(ct, -1.0, "ijeb,ijab->ae", t2p, l2p)                                    # cclambda.py:306
+        W = Planes(self._w(hb["Hovvo"].re, hb["Hovov"].re), self._w(hb["Hovvo"].im, hb["Hovov"].im))
+        env = dict(hb)
+        env.update(l1=l1p, l2=l2p, Gvv=Gvv, Goo=Goo, W=W, Loovv=w.H.derived("Loovv"))
+        ccd = w.model == "CCD"
+        with K.mixed_mode(getattr(w, "mixed", False), cache=False):
+            r1 = copy_planes(hb["Hov"], 2.0).full()
+            if ccd:
+                r1 = Planes(torch.zeros_like(r1.re), torch.zeros_like(r1.re))
+            else:
+                for alpha, sub, a, b in _R1:
+                    cterm(ct, alpha, sub, env[a], env[b], r1)
+            half = copy_real(env["Loovv"])
+            for alpha, sub, a, b in (_R2 if ccd else _R2_SINGLES + _R2):
+                cterm(ct, alpha, sub, env[a], env[b], half)
+        self._ladder_planes(half, l2p, t1p, t2p)
+        K.symmetrize_r2(half.re)
+        K.symmetrize_r2(half.im)
+        return planes_to_complex(r1.re, r1.im), planes_to_complex(half.re, half.im)
+
+    def _ladder_planes(self, half, l2, t1, t2):
+        """``_ladder`` for Planes: the bare ladder once per plane of lambda2 (<ab|ef> is real), the H_abef corrections
+        with their small complex x complex first factors."""
+        from .planes import Planes, cterm, cprod, complex_tau
+        w, ct = self.ccwfn, self.ccwfn._ct
+        with K.mixed_mode(getattr(w, "mixed", False), cache=False):
+            for src, dst in ((l2.re, half.re), (l2.im, half.im)):
+                if src is None:
+                    continue
+                if w.part.size > 1:
+                    piece = torch.zeros_like(dst)
+                    w._ladder(src, piece)
+                    w.part.all_reduce_sum(piece)
+                    K.strided_axpby(dst, piece, 1.0, 1.0)
+                else:
+                    w._ladder(src, dst)
+            o, v = w.o, w.v
+            oovv = w.H.ERI[o, o, v, v]
+            if w.model == "CCD":
+                tau = t2
+            else:
+                vovv = w.H.ERI[v, o, v, v]
+                cterm(ct, -0.5, "ijem,emab->ijab", cprod(ct, 1.0, "ijef,mf->ijem", l2, t1), vovv, half)
+                cterm(ct, -0.5, "ijfm,fmba->ijab", cprod(ct, 1.0, "ijef,me->ijfm", l2, t1), vovv, half)
+                tau = complex_tau(t1, t2)
+            cterm(ct, 0.5, "ijmn,mnab->ijab", cprod(ct, 1.0, "ijef,mnef->ijmn", l2, tau), oovv, half)
+        return half
 
     # ---- solve_lambda (cclambda.py:69-200) -------------------------------------------------------------------
     def solve_lambda(self, e_conv=1e-7, r_conv=1e-7, maxiter=100, max_diis=8, start_diis=1):

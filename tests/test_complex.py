@@ -152,3 +152,29 @@ def test_complex_lambda_residuals_match_reference(cplx, dev, field):
     assert q1.is_complex() and q2.is_complex()
     assert np.abs(q1.cpu().numpy() - g["rl1_" + field]).max() < 1e-10
     assert np.abs(q2.cpu().numpy() - g["rl2_" + field]).max() < 1e-10
+
+
+def test_complex_lambda_residuals_every_evaluation(cplx, dev):
+    """The Lambda right-hand side on pairs of real planes (default), with the three-product form forced for every complex x
+    complex term, and from five real samples of the whole residual (round 1): all three equal the reference's output."""
+    from pycc_b200 import planes
+    g, r, syn = cplx
+    cc = pycc_b200.ccwfn(syn, model="CCSD", device="GPU", quiet=True)
+    cc.t1, cc.t2 = T(r["conv_t1"]), T(r["conv_t2"])
+    lm = pycc_b200.cclambda(cc, pycc_b200.cchbar(cc))
+    args = (T(g["F_mag"]), T(g["t1"]), T(g["t2"]), T(g["l1"]), T(g["l2"]))
+    keep = planes.THREE_M_MIN_OUT
+    try:
+        for on_planes, min_out in ((True, keep), (True, 0), (False, keep)):
+            lm.complex_on_planes, planes.THREE_M_MIN_OUT = on_planes, min_out
+            q1, q2 = lm.residuals(*args)
+            assert np.abs(q1.cpu().numpy() - g["rl1_mag"]).max() < 1e-10, (on_planes, min_out)
+            assert np.abs(q2.cpu().numpy() - g["rl2_mag"]).max() < 1e-10, (on_planes, min_out)
+    finally:
+        lm.complex_on_planes, planes.THREE_M_MIN_OUT = True, keep
+    # real t and lambda with a complex Hermitian F: missing imaginary planes
+    q1, q2 = lm.residuals(T(g["F_mag"]), T(g["t1"].real.copy()), T(g["t2"].real.copy()), T(g["l1"].real.copy()),
+                          T(g["l2"].real.copy()))
+    P = co.Problem(blocks_from_factor(syn), syn.F, syn.no)
+    w1, w2 = lo.residuals(P, g["t1"].real, g["t2"].real, g["l1"].real, g["l2"].real, F=g["F_mag"])
+    assert np.abs(q1.cpu().numpy() - w1).max() < 1e-10 and np.abs(q2.cpu().numpy() - w2).max() < 1e-10

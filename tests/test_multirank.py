@@ -265,7 +265,12 @@ def _worker_complex(rank, world, port, tag, q):
             w1, w2 = P.residuals(g["F_mag"], g["t1"], t2s)
             r1, r2 = cc.residuals(T(g["F_mag"]), T(g["t1"]), T(t2s), real_time=True)
             d_sym = max(float(np.abs(r1.numpy() - w1).max()), float(np.abs(r2.numpy() - w2).max()))
-            q.put((rank, d_gen, d_sym))
+            # the Lambda half on planes with the sharded <ab|ef>: t1.<ab|ef> of H_abei and the lambda2 ladder per plane
+            cc.t1, cc.t2 = T(r["conv_t1"]), T(r["conv_t2"])
+            lm = pycc_b200.cclambda(cc, pycc_b200.cchbar(cc))
+            q1, q2 = lm.residuals(T(g["F_mag"]), T(g["t1"]), T(g["t2"]), T(g["l1"]), T(g["l2"]))
+            d_lam = max(float(np.abs(q1.numpy() - g["rl1_mag"]).max()), float(np.abs(q2.numpy() - g["rl2_mag"]).max()))
+            q.put((rank, d_gen, max(d_sym, d_lam / 10.0)))
     finally:
         dist.destroy_process_group()
 
