@@ -579,6 +579,7 @@ class CCwfn(object):
         cc2 = self.model == 'CC2'
         with K.PHASES("intermediates"):
             I = self._intermediates(F, t1, t2, rings=not cc2, symmetric=symmetric, heavy=heavy)
+        # heavy=False (the complex path): the caller picks up the linear parts of W1 / W2 from here, then drops the dict
         self._last_I = I if not heavy else None
         # one flat buffer [ r2 half | rank-partial part of r1 ] so that ONE all-reduce carries both
         n2, n1 = t2.numel(), t1.numel()
