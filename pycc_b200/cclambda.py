@@ -207,6 +207,10 @@ class cclambda(object):
             else:
                 for alpha, sub, a, b in _R1:
                     cterm(ct, alpha, sub, env[a], env[b], r1)
+            # H_abei / H_mbij (both planes: 2 x o v^3 doubles) are read by r_L1 only
+            for k in ("Hvvvo", "Hovoo"):
+                hb.pop(k, None)
+                env.pop(k, None)
             half = copy_real(env["Loovv"])
             for alpha, sub, a, b in (_R2 if ccd else _R2_SINGLES + _R2):
                 cterm(ct, alpha, sub, env[a], env[b], half)
